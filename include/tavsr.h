@@ -1,0 +1,218 @@
+/*
+ * tavsr.h — C ABI of libtavsr_sm100.so: the B200 (sm_100a) kernels behind the Branchformer encoder
+ * stack and the CTC scorer of david-gimeno/tailored-avsr.
+ *
+ * The reference has no FFI for this path: its plug-in surface is the Python module API
+ * (src/encoder/branchformer/encoder.py:324, src/encoder/branchformer/encoder_layer.py:153,
+ * src/encoder/audiovisual/tailored/encoder_layer.py:118, src/ctc/ctc.py:133-188).  The drop-in
+ * Python modules in tailored_avsr_b200/ keep those signatures and bind the entry points below
+ * through ctypes; each entry point names the reference op sequence it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless stated otherwise;
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
+ *   - return value 0 = ok, negative = error (tavsr_last_error() gives a thread-local message);
+ *   - no exceptions cross the boundary, no hidden allocations on the data path: scratch memory is
+ *     passed in by the caller (tavsr_*_workspace_bytes says how much);
+ *   - "tf32 mode" = fp32 storage, operands rounded to TF32 for the tensor cores, fp32 accumulate.
+ *   - row-major activations: (rows = utterance-major frames, b*T + t), leading dimension in
+ *     ELEMENTS.
+ */
+#ifndef TAVSR_H_
+#define TAVSR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TAVSR_VERSION 100
+
+#define TAVSR_OK 0
+#define TAVSR_ERR_INVALID (-1)
+#define TAVSR_ERR_CUDA (-2)
+#define TAVSR_ERR_UNSUPPORTED (-3)
+
+/* activation codes (espnet get_activation / cgMLP GELU) */
+#define TAVSR_ACT_NONE 0
+#define TAVSR_ACT_SWISH 1
+#define TAVSR_ACT_GELU 2
+#define TAVSR_ACT_RELU 3
+
+/* operand dtype of the tensor-core GEMMs */
+#define TAVSR_DT_TF32 0 /* fp32 storage, kind::tf32 */
+#define TAVSR_DT_BF16 1 /* bf16 storage, kind::f16  */
+
+int tavsr_version(void);
+const char* tavsr_last_error(void);
+/* debug knobs (descriptor variants etc.); not part of the stable surface */
+int tavsr_debug_set(int key, int value);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+long long tavsr_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Y[M,N] = act(X[M,K] . W[N,K]^T + bias)          tcgen05 / TMEM / TMA GEMM
+ * Replaces torch.nn.Linear + activation: FFN w_1 + Swish (espnet PositionwiseFeedForward, called at
+ * encoder_layer.py:194,314), cgMLP channel_proj1 + GELU (encoder_layer.py:220), fused
+ * linear_q|k|v (encoder_layer.py:208), linear_pos.
+ * round_out != 0 rounds Y to TF32 (legal when Y only feeds further tensor-core products).
+ * Requirements: K % 4 == 0, N % 4 == 0, ld* % 4 == 0 (16-byte TMA strides), 16-byte aligned bases.
+ * ---------------------------------------------------------------------------------------------- */
+int tavsr_gemm_bias_act(const void* x, long long ldx, const void* w, long long ldw,
+                        const float* bias, void* y, long long ldy, int M, int N, int K, int act,
+                        int round_out, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Row-complete GEMM, N == 256 (the model width): one thread owns one output row, so everything that
+ * follows the projection in the reference layer is fused into the epilogue:
+ *
+ *   acc  = X . W^T                      (or  rowscale1[seg]*X.W^T + rowscale2[seg]*X2.W^T,
+ *                                        seg = row / rows_per_seg — the learned_ave merge,
+ *                                        encoder_layer.py:291-293)
+ *   v0   = residual + alpha * (acc + bias)                      (encoder_layer.py:194,291,314)
+ *   v1   = ln0 ? LayerNorm(v0; ln0, eps0) : v0                  (norm_final, encoder_layer.py:316)
+ *   out_main = v1            (optional, fp32)
+ *   out_lnA  = LayerNorm(v1; lnA, eps)   out_lnB = LayerNorm(v1; lnB, eps)   (next block's norms)
+ *   dots_out[row] = (v1 . dot1, v1 . dot2)                      (pooling_proj / weight_proj,
+ *                                                                encoder_layer.py:243,258)
+ * All pointer members may be NULL to disable that stage.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct tavsr_rowln_args {
+  int struct_size; /* sizeof(tavsr_rowln_args), for forward compatibility */
+  int M, K;        /* N is 256 */
+  int dtype;       /* TAVSR_DT_* */
+  const void* x;
+  long long ldx;
+  const void* x2; /* second operand (merge) or NULL */
+  long long ldx2;
+  const void* w; /* [256, K] */
+  long long ldw;
+  const float* bias; /* [256] or NULL */
+  const float* residual;
+  long long ldr;
+  float alpha;
+  const float* rowscale1; /* [ceil(M / rows_per_seg)] */
+  const float* rowscale2;
+  int rows_per_seg;
+  const float* ln0_g;
+  const float* ln0_b;
+  float eps0;
+  float* out_main;
+  long long ld_main;
+  int round_main;
+  const float* lnA_g;
+  const float* lnA_b;
+  float* out_lnA;
+  long long ld_lnA;
+  int round_lnA;
+  const float* lnB_g;
+  const float* lnB_b;
+  float* out_lnB;
+  long long ld_lnB;
+  int round_lnB;
+  float eps;
+  const float* dot1; /* [256] */
+  const float* dot2;
+  float* dots_out; /* [M,2] */
+} tavsr_rowln_args;
+
+int tavsr_gemm_rowln(const tavsr_rowln_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stand-alone LayerNorm over the last dim D (D % 128 == 0, D <= 2048) producing up to two affine
+ * variants of the same normalised row (espnet LayerNorm, eps 1e-12; torch LayerNorm of the
+ * `linear` input layer, encoder.py:126, eps 1e-5).  scale multiplies the result (x * sqrt(d) of
+ * RelPositionalEncoding).
+ * ---------------------------------------------------------------------------------------------- */
+int tavsr_layernorm(const float* x, long long ldx, int M, int D, float eps, const float* gA,
+                    const float* bA, float* outA, long long ldA, int roundA, const float* gB,
+                    const float* bB, float* outB, long long ldB, int roundB, float scale,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused relative-position multi-head self-attention (espnet RelPositionMultiHeadedAttention.forward
+ * as called at encoder_layer.py:208 / tailored encoder_layer.py:192,239), flash style: the
+ * (B,h,T,T) score tensors and the (B,h,T,2T-1) pre-shift tensor never reach HBM.
+ *   qkv   [B*T, ld_qkv]   q | k | v, each H*64 wide (output of the fused projection)
+ *   pos   [2T-1, ld_pos]  linear_pos(pos_emb) for this layer, row k <-> relative position T-1-k
+ *   u, v  [H*64]          pos_bias_u / pos_bias_v
+ *   lens  [B] int32       valid keys per utterance (mask.sum); keys >= lens[b] get probability 0
+ *   ctx   [B*T, ld_ctx]   softmax(((q+u)k^T + rel_shift((q+v)p^T)) / 8) v, heads concatenated
+ * d_k is fixed to 64.
+ * ---------------------------------------------------------------------------------------------- */
+int tavsr_relpos_attn_fwd(const float* qkv, long long ld_qkv, const float* pos, long long ld_pos,
+                          const float* u, const float* v, const int32_t* lens, float* ctx,
+                          long long ld_ctx, int B, int T, int H, int round_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Convolutional spatial gating unit (espnet ConvolutionalSpatialGatingUnit.forward, reached through
+ * self.cgmlp at encoder_layer.py:220):  h = [r | g] (C = 2*Ch wide, post-GELU);
+ *   out = r * (dwconv_k(LayerNorm_Ch(g)) + conv_bias),  zero padding (k-1)/2 on the normalised
+ * sequence at t<0 and t>=T, the key-padding mask is NOT applied (espnet ignores it).
+ *   stats [B*T,2] scratch (mean, rstd).  Kernel size must be 31.
+ * ---------------------------------------------------------------------------------------------- */
+int tavsr_csgu_fwd(const float* h, long long ldh, const float* norm_g, const float* norm_b,
+                   const float* conv_w /* [Ch,31] */, const float* conv_b, float* out,
+                   long long ldo, float* stats, int B, int T, int Ch, int ksize, float eps,
+                   int round_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * learned_ave merge weights (encoder_layer.py:241-289).  dotsK[row] = (x_K . pooling_projK.weight,
+ * x_K . weight_projK.weight) come from tavsr_gemm_rowln.  Per utterance b:
+ *   s_K = softmax_{t < lens[b]}((dotsK[.,0] + pool_bK) / sqrt(size));  omega_K = sum_t s_K dotsK[.,1] + wproj_bK
+ *   (w1, w2) = softmax(omega_1, omega_2)  -> weight_global / weight_local
+ * ---------------------------------------------------------------------------------------------- */
+int tavsr_merge_learned_ave_weights(const float* dots1, const float* dots2, const int32_t* lens,
+                                    float pool_b1, float pool_b2, float wproj_b1, float wproj_b2,
+                                    float inv_sqrt_size, float* w1, float* w2, int B, int T,
+                                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * CTC head: logits = hs . W^T + b in fp32 FMA (argmax must be bit-stable), then log-softmax /
+ * softmax / argmax over V <= 64 (ctc.py:143,160-188).  Any of lp / prob / amax may be NULL.
+ * ---------------------------------------------------------------------------------------------- */
+int tavsr_ctc_head(const float* hs, long long ldh, const float* w /* [V,D] */, const float* b,
+                   float* logp, float* prob, int64_t* amax, int M, int D, int V, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * CTC loss, log domain, blank = 0 (torch.nn.CTCLoss(reduction="none", zero_infinity) at
+ * ctc.py:41,60-61): one warp per utterance.
+ *   logp    [B, T, V]      log-softmax (batch-major; the reference's (T,B,V) transpose is a view)
+ *   targets [B, Lmax]      int64, padded (ys_pad); tlens [B] int64/int32 as int32 here
+ *   hlens   [B] int32      valid frames
+ *   nll     [B]            per-utterance negative log likelihood (inf -> 0 when zero_infinity)
+ *   grad    [B, T, V]      optional: d(sum_b gscale*nll_b)/d(logits) = gscale*(softmax - occupancy)
+ *                          for t < hlens[b], 0 elsewhere (what ATen's backward folds through
+ *                          log_softmax); needs `alpha_ws` of tavsr_ctc_workspace_bytes.
+ * ---------------------------------------------------------------------------------------------- */
+size_t tavsr_ctc_workspace_bytes(int B, int T, int Lmax);
+int tavsr_ctc_loss(const float* logp, const int64_t* targets, long long ld_targets,
+                   const int32_t* hlens, const int32_t* tlens, float* nll, float* grad,
+                   float gscale, void* alpha_ws, int B, int T, int V, int Lmax, int zero_infinity,
+                   void* stream);
+
+/* Greedy CTC decode: collapse repeats of `amax` and drop blank (espnet_model.py:590-592,
+ * maskctc_model.py:287-291).  lens == NULL collapses over all T frames (what _calc_ctc_loss does).
+ * tokens [B,T] padded with -1, ntok [B]. */
+int tavsr_ctc_greedy(const int64_t* amax, const int32_t* lens, int64_t* tokens, int32_t* ntok,
+                     int B, int T, int blank, void* stream);
+
+/* CTC prefix scoring step (espnet CTCPrefixScoreTH.__call__ as driven by CTCPrefixScorer,
+ * src/inference/asr_inference.py:142).  One utterance, `nhyp` hypotheses, all V candidates.
+ *   logp   [T,V]         log-softmax of the utterance
+ *   r_prev [nhyp,T,2]    (log r^n, log r^b) of each hypothesis
+ *   last   [nhyp] int32  last label of each hypothesis (<0: empty prefix)
+ *   plen   [nhyp] int32  prefix length |h|
+ *   psi_prev [nhyp]      previous prefix score
+ *   r_new  [nhyp,V,T,2]  new forward variables per candidate
+ *   score  [nhyp,V]      log psi(h.c) - psi_prev; eos gets the full-sequence score, blank logzero */
+int tavsr_ctc_prefix_score(const float* logp, const float* r_prev, const int32_t* last,
+                           const int32_t* plen, const float* psi_prev, float* r_new, float* score,
+                           int T, int Tvalid, int V, int nhyp, int blank, int eos, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TAVSR_H_ */

@@ -1,0 +1,471 @@
+// CTC scorer kernels: fp32 head (logits + log-softmax / softmax / argmax), warp-per-utterance
+// log-domain forward-backward loss with gradient w.r.t. the logits, greedy decode, prefix scoring.
+// Reference: src/ctc/ctc.py:58-69,133-188 (torch.nn.CTCLoss(reduction="none", zero_infinity)),
+// greedy call sites src/models/espnet_model.py:590-592, prefix scoring via espnet
+// CTCPrefixScoreTH (src/inference/asr_inference.py:142).
+#include <atomic>
+
+#include "host.h"
+#include "ptx.cuh"
+
+namespace tavsr {
+extern std::atomic<long long> g_launches;
+
+namespace ctc {
+
+constexpr int kVPad = 64;  // V <= 64 (EN 41, ES 37)
+
+// ------------------------------------------------------------------------------------------------
+// Head: logits in plain fp32 FMA (argmax must not flip on near ties, so no TF32 here).
+// Block = 8 warps; W^T staged in shared memory as [D][64]; each warp handles 4 frames per pass,
+// lane l produces vocabulary entries l and l+32.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ctc_head_kernel(const float* __restrict__ hs, long long ldh, const float* __restrict__ w,
+                const float* __restrict__ bias, float* __restrict__ logp, float* __restrict__ prob,
+                int64_t* __restrict__ amax, int M, int D, int V) {
+  extern __shared__ float sm[];
+  float* Wt = sm;                       // [D][64]
+  float* Hs = sm + D * kVPad;           // [8 warps][4 frames][D]
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < D * kVPad; i += 256) {
+    const int k = i / kVPad, v = i % kVPad;
+    Wt[i] = v < V ? __ldg(w + static_cast<long long>(v) * D + k) : 0.f;
+  }
+  __syncthreads();
+  const float b0 = lane < V ? __ldg(bias + lane) : 0.f;
+  const float b1 = lane + 32 < V ? __ldg(bias + lane + 32) : 0.f;
+  float* hw = Hs + warp * 4 * D;
+  const int groups = (M + 3) / 4;
+  for (int grp = blockIdx.x * 8 + warp; grp < groups; grp += gridDim.x * 8) {
+    const int m0 = grp * 4;
+    __syncwarp();
+    for (int i = lane * 4; i < 4 * D; i += 128) {
+      const int f = i / D, k = i % D;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m0 + f < M)
+        x = __ldg(reinterpret_cast<const float4*>(hs + static_cast<long long>(m0 + f) * ldh + k));
+      *reinterpret_cast<float4*>(hw + i) = x;
+    }
+    __syncwarp();
+    float acc[4][2];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) { acc[f][0] = b0; acc[f][1] = b1; }
+    for (int k = 0; k < D; k += 4) {
+      float4 x[4];
+#pragma unroll
+      for (int f = 0; f < 4; ++f) x[f] = *reinterpret_cast<const float4*>(hw + f * D + k);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const float w0 = Wt[(k + kk) * kVPad + lane];
+        const float w1 = Wt[(k + kk) * kVPad + lane + 32];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+          const float xv = kk == 0 ? x[f].x : (kk == 1 ? x[f].y : (kk == 2 ? x[f].z : x[f].w));
+          acc[f][0] = fmaf(xv, w0, acc[f][0]);
+          acc[f][1] = fmaf(xv, w1, acc[f][1]);
+        }
+      }
+    }
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      const int m = m0 + f;
+      if (m >= M) break;  // warp-uniform
+      const float x0 = lane < V ? acc[f][0] : -INFINITY;
+      const float x1 = lane + 32 < V ? acc[f][1] : -INFINITY;
+      // argmax with lowest-index tie-break (torch.argmax returns the first maximal index)
+      float bv = x0;
+      int bi = lane;
+      if (x1 > bv) { bv = x1; bi = lane + 32; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      const float e0 = lane < V ? expf(x0 - bv) : 0.f;
+      const float e1 = lane + 32 < V ? expf(x1 - bv) : 0.f;
+      const float se = warp_sum(e0 + e1);
+      const float lse = bv + logf(se);
+      if (logp) {
+        if (lane < V) logp[static_cast<long long>(m) * V + lane] = x0 - lse;
+        if (lane + 32 < V) logp[static_cast<long long>(m) * V + lane + 32] = x1 - lse;
+      }
+      if (prob) {
+        const float inv = 1.0f / se;
+        if (lane < V) prob[static_cast<long long>(m) * V + lane] = e0 * inv;
+        if (lane + 32 < V) prob[static_cast<long long>(m) * V + lane + 32] = e1 * inv;
+      }
+      if (amax && lane == 0) amax[m] = bi;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Loss: one warp per utterance; the S = 2L+1 lattice states are striped over the lanes in
+// contiguous chunks of kC states, so s-1 / s-2 neighbours are mostly in-thread and the chunk
+// boundary is crossed with two warp shuffles per time step.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float lse2(float a, float b) {
+  const float m = fmaxf(a, b);
+  if (m == -INFINITY) return -INFINITY;
+  return m + logf(expf(a - m) + expf(b - m));
+}
+__device__ __forceinline__ float lse3(float a, float b, float c) {
+  const float m = fmaxf(fmaxf(a, b), c);
+  if (m == -INFINITY) return -INFINITY;
+  return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
+}
+
+template <int kC>
+__global__ void __launch_bounds__(128)
+ctc_loss_kernel(const float* __restrict__ logp, const int64_t* __restrict__ targets,
+                long long ld_targets, const int32_t* __restrict__ hlens,
+                const int32_t* __restrict__ tlens, float* __restrict__ nll_out,
+                float* __restrict__ grad, float gscale, float* __restrict__ alpha_ws, int B, int T,
+                int V, int Lmax, int zero_infinity) {
+  __shared__ float s_row[4][2][kVPad];   // per warp, double-buffered log-prob row
+  __shared__ float s_occ[4][kVPad];
+  __shared__ float s_fin[4][2];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 4 + warp;
+  if (b >= B) return;
+  int L = tlens[b];
+  L = L < 0 ? 0 : (L > Lmax ? Lmax : L);
+  int Tb = hlens[b];
+  Tb = Tb < 0 ? 0 : (Tb > T ? T : Tb);
+  const int S = 2 * L + 1;
+  const int Sws = 2 * Lmax + 1;
+  const float* lp = logp + static_cast<long long>(b) * T * V;
+  const int64_t* tg = targets + static_cast<long long>(b) * ld_targets;
+  float* aws = alpha_ws ? alpha_ws + static_cast<long long>(b) * T * Sws : nullptr;
+  float* gb = grad ? grad + static_cast<long long>(b) * T * V : nullptr;
+
+  // per-state constants
+  int lab[kC];
+  bool skip_in[kC];   // transition s-2 -> s allowed
+  bool skip_out[kC];  // transition s -> s+2 allowed
+#pragma unroll
+  for (int i = 0; i < kC; ++i) {
+    const int s = lane * kC + i;
+    int l = 0;
+    bool si = false, so = false;
+    if (s < S && (s & 1)) {
+      l = static_cast<int>(tg[(s - 1) >> 1]);
+      if (s >= 3) si = static_cast<int>(tg[(s - 3) >> 1]) != l;
+      if (s + 2 < S) so = static_cast<int>(tg[(s + 1) >> 1]) != l;
+    }
+    lab[i] = (l >= 0 && l < V) ? l : 0;
+    skip_in[i] = si;
+    skip_out[i] = so;
+  }
+
+  // log-prob rows are prefetched one time step ahead into registers (fetch) and published to the
+  // warp through shared memory (commit), so the global-load latency is off the serial chain.
+  float pre0 = 0.f, pre1 = 0.f;
+  auto fetch = [&](int t) {
+    if (t >= 0 && t < Tb) {
+      if (lane < V) pre0 = __ldg(lp + static_cast<long long>(t) * V + lane);
+      if (lane + 32 < V) pre1 = __ldg(lp + static_cast<long long>(t) * V + lane + 32);
+    }
+  };
+  auto commit = [&](int buf) {
+    if (lane < V) s_row[warp][buf][lane] = pre0;
+    if (lane + 32 < V) s_row[warp][buf][lane + 32] = pre1;
+  };
+
+  float nll = INFINITY;
+  float a[kC];
+  if (Tb > 0) {
+    // ---------------- alpha ----------------
+    fetch(0);
+    commit(0);
+    fetch(1);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < kC; ++i) {
+      const int s = lane * kC + i;
+      a[i] = (s < S && s < 2) ? s_row[warp][0][lab[i]] : -INFINITY;
+      if (aws && s < S) aws[s] = a[i];
+    }
+    for (int t = 1; t < Tb; ++t) {
+      const int buf = t & 1;
+      commit(buf);
+      fetch(t + 1);
+      // neighbours from the previous lane
+      float pm1 = __shfl_up_sync(0xffffffffu, a[kC - 1], 1);
+      float pm2 = __shfl_up_sync(0xffffffffu, a[kC - 2], 1);
+      if (lane == 0) { pm1 = -INFINITY; pm2 = -INFINITY; }
+      __syncwarp();
+      float n[kC];
+#pragma unroll
+      for (int i = 0; i < kC; ++i) {
+        const int s = lane * kC + i;
+        const float x1 = i >= 1 ? a[i - 1] : pm1;
+        // s-2 neighbour: in-thread for i >= 2, else the previous lane's last / second-to-last state
+        const float two = skip_in[i] ? (i >= 2 ? a[i - 2] : (i == 1 ? pm1 : pm2)) : -INFINITY;
+        const float v = lse3(a[i], x1, two);
+        n[i] = s < S ? v + s_row[warp][buf][lab[i]] : -INFINITY;
+      }
+#pragma unroll
+      for (int i = 0; i < kC; ++i) {
+        a[i] = n[i];
+        const int s = lane * kC + i;
+        if (aws && s < S) aws[static_cast<long long>(t) * Sws + s] = a[i];
+      }
+      __syncwarp();
+    }
+    // final: logaddexp(alpha[S-1], alpha[S-2])
+    if (lane == 0) { s_fin[warp][0] = -INFINITY; s_fin[warp][1] = -INFINITY; }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < kC; ++i) {
+      const int s = lane * kC + i;
+      if (s == S - 1) s_fin[warp][0] = a[i];
+      if (S >= 2 && s == S - 2) s_fin[warp][1] = a[i];
+    }
+    __syncwarp();
+    nll = -lse2(s_fin[warp][0], s_fin[warp][1]);
+  } else {
+    nll = (L == 0) ? 0.f : INFINITY;
+  }
+  const bool infeasible = !(nll < INFINITY);  // inf or nan
+  if (lane == 0) nll_out[b] = (infeasible && zero_infinity) ? 0.f : nll;
+  if (!gb) return;
+
+  // ---------------- beta + gradient ----------------
+  if (infeasible || Tb == 0) {
+    for (int i = lane; i < T * V; i += 32) gb[i] = zero_infinity || Tb == 0 ? 0.f : NAN;
+    return;
+  }
+  for (int i = Tb * V + lane; i < T * V; i += 32) gb[i] = 0.f;
+  float bt[kC];
+  float apre[kC];  // alpha_t prefetched one step ahead of the beta recursion
+#pragma unroll
+  for (int i = 0; i < kC; ++i) {
+    const int s = lane * kC + i;
+    apre[i] = s < S ? aws[static_cast<long long>(Tb - 1) * Sws + s] : -INFINITY;
+  }
+  fetch(Tb - 1);
+  for (int t = Tb - 1; t >= 0; --t) {
+    const int buf = t & 1;
+    commit(buf);
+    fetch(t - 1);
+    if (lane < kVPad / 2) { s_occ[warp][lane] = 0.f; s_occ[warp][lane + 32] = 0.f; }
+    float np1 = 0.f, np2 = 0.f;
+    if (t < Tb - 1) {
+      np1 = __shfl_down_sync(0xffffffffu, bt[0], 1);
+      np2 = __shfl_down_sync(0xffffffffu, bt[1], 1);
+      if (lane == 31) { np1 = -INFINITY; np2 = -INFINITY; }
+    }
+    __syncwarp();
+    float n[kC];
+#pragma unroll
+    for (int i = 0; i < kC; ++i) {
+      const int s = lane * kC + i;
+      float v;
+      if (t == Tb - 1) {
+        v = (s < S && s >= S - 2) ? 0.f : -INFINITY;
+      } else {
+        const float x1 = i + 1 < kC ? bt[i + 1] : np1;
+        const float two =
+            skip_out[i] ? (i + 2 < kC ? bt[i + 2] : (i + 2 == kC ? np1 : np2)) : -INFINITY;
+        v = lse3(bt[i], x1, two);
+      }
+      n[i] = s < S ? v + s_row[warp][buf][lab[i]] : -INFINITY;
+    }
+#pragma unroll
+    for (int i = 0; i < kC; ++i) {
+      bt[i] = n[i];
+      const int s = lane * kC + i;
+      if (s < S) {
+        const float e = expf(apre[i] + bt[i] + nll - s_row[warp][buf][lab[i]]);
+        if (e > 0.f) atomicAdd(&s_occ[warp][lab[i]], e);
+        if (t > 0) apre[i] = aws[static_cast<long long>(t - 1) * Sws + s];
+      }
+    }
+    __syncwarp();
+    if (lane < V)
+      gb[static_cast<long long>(t) * V + lane] =
+          gscale * (expf(s_row[warp][buf][lane]) - s_occ[warp][lane]);
+    if (lane + 32 < V)
+      gb[static_cast<long long>(t) * V + lane + 32] =
+          gscale * (expf(s_row[warp][buf][lane + 32]) - s_occ[warp][lane + 32]);
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Greedy decode: collapse repeats, drop blank.  One warp per utterance, ballot compaction.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+ctc_greedy_kernel(const int64_t* __restrict__ amax, const int32_t* __restrict__ lens,
+                  int64_t* __restrict__ tokens, int32_t* __restrict__ ntok, int B, int T,
+                  int blank) {
+  const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const int lane = threadIdx.x & 31;
+  int n = lens ? lens[b] : T;
+  n = n < 0 ? 0 : (n > T ? T : n);
+  const int64_t* a = amax + static_cast<long long>(b) * T;
+  int64_t* out = tokens + static_cast<long long>(b) * T;
+  int count = 0;
+  for (int t0 = 0; t0 < n; t0 += 32) {
+    const int t = t0 + lane;
+    bool keep = false;
+    int64_t tok = blank;
+    if (t < n) {
+      tok = a[t];
+      keep = tok != blank && (t == 0 || a[t - 1] != tok);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (keep) out[count + __popc(m & ((1u << lane) - 1u))] = tok;
+    count += __popc(m);
+  }
+  for (int t = count + lane; t < T; t += 32) out[t] = -1;
+  if (lane == 0) ntok[b] = count;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Prefix scoring step: one thread per (hypothesis, candidate token), serial in T.
+// r layouts: r_prev [nhyp][T][2], r_new [nhyp][T][V][2].
+// ------------------------------------------------------------------------------------------------
+constexpr float kLogZero = -1e10f;
+
+__global__ void __launch_bounds__(128)
+ctc_prefix_kernel(const float* __restrict__ logp, const float* __restrict__ r_prev,
+                  const int32_t* __restrict__ last, const int32_t* __restrict__ plen,
+                  const float* __restrict__ psi_prev, float* __restrict__ r_new,
+                  float* __restrict__ score, int T, int Tvalid, int V, int nhyp, int blank,
+                  int eos) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nhyp * V) return;
+  const int hy = idx / V, c = idx % V;
+  const float* rp = r_prev + static_cast<long long>(hy) * T * 2;
+  float2* rn = reinterpret_cast<float2*>(r_new) + static_cast<long long>(hy) * T * V + c;
+  const int pl = plen[hy];
+  const int lastl = last[hy];
+  const int start = pl > 1 ? pl : 1;
+  auto lpx = [&](int t, int v) -> float {
+    if (t < Tvalid) return logp[static_cast<long long>(t) * V + v];
+    return v == blank ? 0.f : kLogZero;
+  };
+  auto phi = [&](int t) -> float {
+    const float rn_ = rp[2 * t], rb_ = rp[2 * t + 1];
+    return c == lastl ? rb_ : lse2(rn_, rb_);
+  };
+  float psi;
+  if (c == blank) {
+    for (int t = 0; t < T; ++t) rn[static_cast<long long>(t) * V] = make_float2(kLogZero, kLogZero);
+    score[idx] = kLogZero - psi_prev[hy];
+    return;
+  }
+  float rnn = kLogZero, rnb = kLogZero;
+  for (int t = 0; t < start - 1; ++t) rn[static_cast<long long>(t) * V] = make_float2(kLogZero, kLogZero);
+  if (pl == 0) rnn = lpx(0, c);
+  rn[static_cast<long long>(start - 1) * V] = make_float2(rnn, rnb);
+  psi = rnn;
+  for (int t = start; t < T; ++t) {
+    const float ph = phi(t - 1);
+    const float xc = lpx(t, c);
+    const float nn = lse2(rnn, ph) + xc;
+    const float nb = lse2(rnn, rnb) + lpx(t, blank);
+    psi = lse2(psi, ph + xc);
+    rnn = nn;
+    rnb = nb;
+    rn[static_cast<long long>(t) * V] = make_float2(rnn, rnb);
+  }
+  if (c == eos) {
+    const int te = (Tvalid > 0 ? Tvalid : 1) - 1;
+    psi = lse2(rp[2 * te], rp[2 * te + 1]);
+  }
+  score[idx] = psi - psi_prev[hy];
+}
+
+}  // namespace ctc
+}  // namespace tavsr
+
+using namespace tavsr;
+
+extern "C" int tavsr_ctc_head(const float* hs, long long ldh, const float* w, const float* b,
+                              float* logp, float* prob, int64_t* amax, int M, int D, int V,
+                              void* stream) {
+  TAVSR_REQUIRE(M > 0 && D > 0 && D % 4 == 0 && D <= 512, "ctc_head: bad D=%d", D);
+  TAVSR_REQUIRE(V > 0 && V <= ctc::kVPad, "ctc_head: V=%d > 64 not built", V);
+  TAVSR_REQUIRE(hs && w && b && ldh % 4 == 0, "ctc_head: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int smem = (D * ctc::kVPad + 8 * 4 * D) * 4;
+  static int configured = 0;
+  if (configured < smem) {
+    TAVSR_CUDA_OK(cudaFuncSetAttribute(ctc::ctc_head_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  const int groups = (M + 3) / 4;
+  int grid = (groups + 7) / 8;
+  if (grid > 2 * num_sms()) grid = 2 * num_sms();
+  ctc::ctc_head_kernel<<<grid, 256, smem, s>>>(hs, ldh, w, b, logp, prob, amax, M, D, V);
+  TAVSR_CUDA_OK(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+extern "C" size_t tavsr_ctc_workspace_bytes(int B, int T, int Lmax) {
+  return static_cast<size_t>(B) * T * (2 * static_cast<size_t>(Lmax) + 1) * sizeof(float);
+}
+
+extern "C" int tavsr_ctc_loss(const float* logp, const int64_t* targets, long long ld_targets,
+                              const int32_t* hlens, const int32_t* tlens, float* nll, float* grad,
+                              float gscale, void* alpha_ws, int B, int T, int V, int Lmax,
+                              int zero_infinity, void* stream) {
+  TAVSR_REQUIRE(B > 0 && T > 0 && V > 0 && V <= ctc::kVPad && Lmax >= 0, "ctc_loss: bad shape");
+  TAVSR_REQUIRE(logp && targets && hlens && tlens && nll, "ctc_loss: null pointer");
+  TAVSR_REQUIRE(!grad || alpha_ws, "ctc_loss: gradient needs the alpha workspace");
+  const int S = 2 * Lmax + 1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int grid = (B + 3) / 4;
+  float* aws = static_cast<float*>(alpha_ws);
+  if (!grad) aws = nullptr;
+#define TAVSR_CTC_CASE(C)                                                                       \
+  ctc::ctc_loss_kernel<C><<<grid, 128, 0, s>>>(logp, targets, ld_targets, hlens, tlens, nll,    \
+                                               grad, gscale, aws, B, T, V, Lmax, zero_infinity)
+  if (S <= 64) TAVSR_CTC_CASE(2);
+  else if (S <= 128) TAVSR_CTC_CASE(4);
+  else if (S <= 256) TAVSR_CTC_CASE(8);
+  else if (S <= 512) TAVSR_CTC_CASE(16);
+  else if (S <= 1024) TAVSR_CTC_CASE(32);
+  else return set_error(TAVSR_ERR_UNSUPPORTED, "ctc_loss: target length %d > 511 not built", Lmax);
+#undef TAVSR_CTC_CASE
+  TAVSR_CUDA_OK(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+extern "C" int tavsr_ctc_greedy(const int64_t* amax, const int32_t* lens, int64_t* tokens,
+                                int32_t* ntok, int B, int T, int blank, void* stream) {
+  TAVSR_REQUIRE(B > 0 && T > 0 && amax && tokens && ntok, "ctc_greedy: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ctc::ctc_greedy_kernel<<<(B + 3) / 4, 128, 0, s>>>(amax, lens, tokens, ntok, B, T, blank);
+  TAVSR_CUDA_OK(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+extern "C" int tavsr_ctc_prefix_score(const float* logp, const float* r_prev, const int32_t* last,
+                                      const int32_t* plen, const float* psi_prev, float* r_new,
+                                      float* score, int T, int Tvalid, int V, int nhyp, int blank,
+                                      int eos, void* stream) {
+  TAVSR_REQUIRE(T > 0 && V > 0 && nhyp > 0 && Tvalid >= 0 && Tvalid <= T,
+                "ctc_prefix_score: bad shape");
+  TAVSR_REQUIRE(logp && r_prev && last && plen && psi_prev && r_new && score,
+                "ctc_prefix_score: null pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int n = nhyp * V;
+  ctc::ctc_prefix_kernel<<<(n + 127) / 128, 128, 0, s>>>(logp, r_prev, last, plen, psi_prev, r_new,
+                                                         score, T, Tvalid, V, nhyp, blank, eos);
+  TAVSR_CUDA_OK(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}

@@ -1,0 +1,230 @@
+// Host launchers + C ABI for the tcgen05 GEMM family (see gemm_sm100.cuh).
+#include "gemm_sm100.cuh"
+
+#include <atomic>
+
+#include "host.h"
+
+namespace tavsr {
+
+thread_local char g_last_error[512] = "";
+int g_debug[16] = {0};
+std::atomic<long long> g_launches{0};
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tensor maps
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+struct TmapKey {
+  const void* ptr;
+  uint64_t rows, cols, ld;
+  uint32_t box_rows, box_cols;
+  int elem_bytes, flags;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld &&
+           box_rows == o.box_rows && box_cols == o.box_cols && elem_bytes == o.elem_bytes &&
+           flags == o.flags;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    auto mix = [&h](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+    mix(k.rows); mix(k.cols); mix(k.ld); mix(k.box_rows); mix(k.box_cols);
+    mix(static_cast<uint64_t>(k.elem_bytes)); mix(static_cast<uint64_t>(k.flags));
+    return h;
+  }
+};
+
+int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, bool is_bf16, uint64_t rows,
+                 uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols,
+                 bool l2_promote_256) {
+  static std::mutex mu;
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  const int tf32_type = g_debug[1];  // debug: 1 -> TFLOAT32 tensor-map dtype
+  TmapKey key{ptr, rows, cols, ld, box_rows, box_cols, elem_bytes,
+              (is_bf16 ? 1 : 0) | (l2_promote_256 ? 2 : 0) | (tf32_type << 2)};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return set_error(TAVSR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * elem_bytes) % 16 != 0)
+    return set_error(TAVSR_ERR_INVALID,
+                     "TMA operand must be 16-byte aligned with a 16-byte multiple row pitch "
+                     "(ptr=%p ld=%llu elem=%d)",
+                     ptr, static_cast<unsigned long long>(ld), elem_bytes);
+  if (box_cols * elem_bytes != 128 || box_rows > 256)
+    return set_error(TAVSR_ERR_INVALID, "bad TMA box %u x %u", box_rows, box_cols);
+  CUtensorMapDataType dt = is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                   : (tf32_type ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32
+                                                : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * static_cast<uint64_t>(elem_bytes)};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, dt, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   l2_promote_256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                  : CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(TAVSR_ERR_CUDA,
+                     "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box=%ux%u",
+                     static_cast<int>(r), static_cast<unsigned long long>(rows),
+                     static_cast<unsigned long long>(cols), static_cast<unsigned long long>(ld),
+                     box_rows, box_cols);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() > 65536) cache.clear();
+    cache.emplace(key, *out);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------------
+template <bool kTf32, int kBlockN, int kMode, bool kDual>
+static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<kTf32, kBlockN, kMode, kDual>;
+  auto kern = gemm_sm100_kernel<kTf32, kBlockN, kMode, kDual>;
+  static bool configured = false;
+  if (!configured) {
+    TAVSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(p);
+  TAVSR_CUDA_OK(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+}  // namespace tavsr
+
+using namespace tavsr;
+
+extern "C" int tavsr_version(void) { return TAVSR_VERSION; }
+extern "C" const char* tavsr_last_error(void) { return g_last_error; }
+extern "C" int tavsr_debug_set(int key, int value) {
+  if (key < 0 || key >= 16) return TAVSR_ERR_INVALID;
+  g_debug[key] = value;
+  return 0;
+}
+extern "C" long long tavsr_launch_count(void) { return g_launches.load(); }
+
+extern "C" int tavsr_gemm_bias_act(const void* x, long long ldx, const void* w, long long ldw,
+                                   const float* bias, void* y, long long ldy, int M, int N, int K,
+                                   int act, int round_out, int dtype, void* stream) {
+  TAVSR_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  TAVSR_REQUIRE(dtype == TAVSR_DT_TF32, "gemm: only TAVSR_DT_TF32 is built in this round");
+  TAVSR_REQUIRE(K % 4 == 0 && N % 4 == 0, "gemm: K and N must be multiples of 4 (K=%d N=%d)", K, N);
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K;
+  p.bias = bias; p.act = act; p.round_c = round_out;
+  // tile-width heuristic: fewer waves of 148 CTAs wins; ties go to the wider tile
+  const int mt = (M + 127) / 128;
+  const int sms = num_sms();
+  const int t256 = mt * ((N + 255) / 256), t128 = mt * ((N + 127) / 128);
+  const double cost256 = static_cast<double>((t256 + sms - 1) / sms) * 2.0;
+  const double cost128 = static_cast<double>((t128 + sms - 1) / sms) * 1.0;
+  const bool use128 = (N <= 128) || (cost128 < cost256) || g_debug[2] == 128;
+  const int bn = (use128 && g_debug[2] != 256) ? 128 : 256;
+  p.num_m_tiles = mt;
+  p.num_n_tiles = (N + bn - 1) / bn;
+  int rc;
+  if ((rc = make_tmap_2d(&p.tmA, x, 4, false, M, K, ldx, 128, 32))) return rc;
+  if ((rc = make_tmap_2d(&p.tmB, w, 4, false, N, K, ldw, bn, 32))) return rc;
+  if ((rc = make_tmap_2d(&p.tmC, y, 4, false, M, N, ldy, 32, 32, false))) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (bn == 128) return launch_gemm<true, 128, kModeTiled, false>(p, s);
+  return launch_gemm<true, 256, kModeTiled, false>(p, s);
+}
+
+extern "C" int tavsr_gemm_rowln(const tavsr_rowln_args* a, void* stream) {
+  TAVSR_REQUIRE(a != nullptr && a->struct_size == static_cast<int>(sizeof(tavsr_rowln_args)),
+                "rowln: bad args struct (size %d, expected %d)", a ? a->struct_size : -1,
+                static_cast<int>(sizeof(tavsr_rowln_args)));
+  TAVSR_REQUIRE(a->M > 0 && a->K > 0 && a->K % 4 == 0, "rowln: bad shape M=%d K=%d", a->M, a->K);
+  TAVSR_REQUIRE(a->dtype == TAVSR_DT_TF32, "rowln: only TAVSR_DT_TF32 is built in this round");
+  TAVSR_REQUIRE(a->x && a->w, "rowln: x and w are required");
+  const bool dual = a->x2 != nullptr;
+  TAVSR_REQUIRE(!dual || (a->rowscale1 && a->rowscale2 && a->rows_per_seg > 0),
+                "rowln: dual mode needs rowscale1/2 and rows_per_seg");
+  TAVSR_REQUIRE(!(a->ln0_g && !a->ln0_b) && !(a->lnA_g && !(a->lnA_b && a->out_lnA)) &&
+                    !(a->lnB_g && !(a->lnB_b && a->out_lnB)),
+                "rowln: LayerNorm stages need gamma, beta and an output");
+  TAVSR_REQUIRE(!a->dots_out || (a->dot1 && a->dot2), "rowln: dots_out needs dot1 and dot2");
+  TAVSR_REQUIRE(!a->residual || a->ldr % 4 == 0, "rowln: residual pitch must be a multiple of 4");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = a->M; p.N = 256; p.K = a->K;
+  p.num_m_tiles = (a->M + 127) / 128;
+  p.num_n_tiles = 1;
+  p.bias = a->bias;
+  p.act = ACT_NONE;
+  p.round_c = a->round_main;
+  p.residual = a->residual; p.ldr = a->ldr; p.alpha = a->alpha;
+  p.rowscale1 = a->rowscale1; p.rowscale2 = a->rowscale2; p.rows_per_seg = a->rows_per_seg;
+  p.ln0_g = a->ln0_g; p.ln0_b = a->ln0_b;
+  p.lnA_g = a->lnA_g; p.lnA_b = a->lnA_b; p.lnB_g = a->lnB_g; p.lnB_b = a->lnB_b;
+  p.has_main = a->out_main != nullptr;
+  p.round_lnA = a->round_lnA; p.round_lnB = a->round_lnB;
+  p.dot1 = a->dot1; p.dot2 = a->dot2; p.dots_out = a->dots_out;
+  p.eps = a->eps;
+  p.eps0 = a->eps0;
+  int rc;
+  if ((rc = make_tmap_2d(&p.tmA, a->x, 4, false, a->M, a->K, a->ldx, 128, 32))) return rc;
+  if (dual && (rc = make_tmap_2d(&p.tmA2, a->x2, 4, false, a->M, a->K, a->ldx2, 128, 32))) return rc;
+  if ((rc = make_tmap_2d(&p.tmB, a->w, 4, false, 256, a->K, a->ldw, 256, 32))) return rc;
+  if (a->out_main &&
+      (rc = make_tmap_2d(&p.tmC, a->out_main, 4, false, a->M, 256, a->ld_main, 32, 32, false)))
+    return rc;
+  if (a->lnA_g &&
+      (rc = make_tmap_2d(&p.tmLnA, a->out_lnA, 4, false, a->M, 256, a->ld_lnA, 32, 32, false)))
+    return rc;
+  if (a->lnB_g &&
+      (rc = make_tmap_2d(&p.tmLnB, a->out_lnB, 4, false, a->M, 256, a->ld_lnB, 32, 32, false)))
+    return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dual) return launch_gemm<true, 256, kModeRowLN, true>(p, s);
+  return launch_gemm<true, 256, kModeRowLN, false>(p, s);
+}

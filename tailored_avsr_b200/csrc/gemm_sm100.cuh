@@ -1,0 +1,483 @@
+// tcgen05 / TMEM / TMA GEMM family for sm_100a.
+//
+//   Y[M,N] = epilogue( X[M,K] . W[N,K]^T )          (both operands K-major == torch nn.Linear)
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      : TMA producer  (cp.async.bulk.tensor, 128B-swizzled K-major tiles, mbarrier ring)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (accumulators live in TMEM)
+//   warps 2..   : epilogue      (tcgen05.ld -> registers -> fused math -> swizzled smem -> TMA store)
+// Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the mainloop of
+// tile i+1.
+//
+// Two epilogue families:
+//   kModeTiled : out = act(acc + bias), arbitrary N (tiled by kBlockN), 8 epilogue warps.
+//   kModeRowLN : kBlockN == N == 256, one thread owns one output row (TMEM lane == row), so
+//                LayerNorm statistics, chained LayerNorms, residual adds and row dot-products are
+//                thread-local.  Optionally two A operands / two accumulators combined with
+//                per-utterance scalars (the Branchformer learned_ave merge,
+//                reference src/encoder/branchformer/encoder_layer.py:291-293).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "ptx.cuh"
+
+namespace tavsr {
+
+enum : int { ACT_NONE = 0, ACT_SWISH = 1, ACT_GELU = 2, ACT_RELU = 3 };
+enum : int { kModeTiled = 0, kModeRowLN = 1 };
+
+struct alignas(64) GemmParams {
+  CUtensorMap tmA;    // activations  (K inner, M rows), box {128 B, 128}
+  CUtensorMap tmA2;   // second activation operand (dual mode)
+  CUtensorMap tmB;    // weights      (K inner, N rows), box {128 B, kBlockN}
+  CUtensorMap tmC;    // main output  (N inner, M rows), box {128 B, 32}
+  CUtensorMap tmLnA;  // LayerNorm output A
+  CUtensorMap tmLnB;  // LayerNorm output B
+  int M, N, K;
+  int num_m_tiles, num_n_tiles;
+  const float* bias;
+  int act;
+  int round_c;  // round main output to tf32 (output only feeds tensor-core GEMMs)
+  // ---- RowLN mode ----
+  const float* residual;  // [M, ldr] fp32 or null
+  long long ldr;
+  float alpha;                // v0 = residual + alpha * (combine(acc) + bias)
+  const float* rowscale1;     // dual: per-segment scalars, segment = row / rows_per_seg
+  const float* rowscale2;
+  int rows_per_seg;
+  const float* ln0_g;  // optional first LayerNorm applied to v0 (-> v1); main output is v1
+  const float* ln0_b;
+  const float* lnA_g;  // optional LayerNorm outputs of v1
+  const float* lnA_b;
+  const float* lnB_g;
+  const float* lnB_b;
+  int has_main, round_lnA, round_lnB;
+  const float* dot1;  // optional row dot-products of v1 with two 256-vectors
+  const float* dot2;
+  float* dots_out;    // [M,2]
+  float eps;
+  float eps0;  // eps of ln0
+};
+
+template <bool kTf32, int kBlockN, int kMode, bool kDual>
+struct GemmCfg {
+  static constexpr int kBlockM = 128;
+  static constexpr int kElemBytes = kTf32 ? 4 : 2;
+  static constexpr int kBlockK = 128 / kElemBytes;  // one 128B swizzle row
+  static constexpr int kUmmaK = 32 / kElemBytes;
+  static constexpr int kABytes = kBlockM * 128;
+  static constexpr int kBBytes = kBlockN * 128;
+  static constexpr int kStageBytes = kABytes * (kDual ? 2 : 1) + kBBytes;
+  static constexpr int kStages = kDual ? 2 : (kBlockN == 256 ? 3 : 4);
+  static constexpr int kAccCols = kBlockN * (kDual ? 2 : 1);
+  static constexpr int kAccStages = (512 / kAccCols) >= 2 ? 2 : 1;
+  static constexpr int kEpiWarps = kMode == kModeTiled ? 8 : 4;
+  static constexpr int kThreads = 64 + 32 * kEpiWarps;
+  static constexpr int kStagingBytes = kEpiWarps * 2 * 4096;
+  // params staged in smem: bias[2][kBlockN] (tiled) or 9 x 256 floats (rowln)
+  static constexpr int kParamFloats = kMode == kModeTiled ? 2 * kBlockN : 9 * 256;
+  static constexpr int kSmemBytes =
+      1024 /*align slack*/ + kStages * kStageBytes + kStagingBytes + kParamFloats * 4 + 256;
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  switch (act) {
+    case ACT_SWISH: return x / (1.0f + __expf(-x));
+    case ACT_GELU: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+    case ACT_RELU: return fmaxf(x, 0.0f);
+    default: return x;
+  }
+}
+
+// Write one 32-float row chunk into a per-warp staging box (32 rows x 128 B, 128B-swizzled so that
+// it matches a TMA store with CU_TENSOR_MAP_SWIZZLE_128B) and issue the TMA store.
+struct WarpStager {
+  uint8_t* base;  // 2 x 4096 B, 1024-aligned
+  int buf;
+  __device__ __forceinline__ void store(const CUtensorMap* tm, const float (&v)[32], int col0,
+                                        int row0) {
+    const uint32_t lane = lane_id();
+    if (lane == 0) tma_store_wait_read<1>();
+    __syncwarp();
+    uint8_t* dst = base + buf * 4096 + lane * 128;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 f = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      *reinterpret_cast<float4*>(dst + ((j ^ (lane & 7)) << 4)) = f;
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tm, base + buf * 4096, col0, row0);
+      tma_store_commit();
+    }
+    buf ^= 1;
+  }
+  __device__ __forceinline__ void drain() {
+    if (lane_id() == 0) tma_store_wait_all<0>();
+    __syncwarp();
+  }
+};
+
+template <bool kTf32, int kBlockN, int kMode, bool kDual>
+__global__ void __launch_bounds__(GemmCfg<kTf32, kBlockN, kMode, kDual>::kThreads, 1)
+gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
+  using Cfg = GemmCfg<kTf32, kBlockN, kMode, kDual>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int kAccStages = Cfg::kAccStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* s_stage = smem;                                        // kStages * kStageBytes
+  uint8_t* s_staging = s_stage + kStages * Cfg::kStageBytes;      // kEpiWarps * 8192
+  float* s_param = reinterpret_cast<float*>(s_staging + Cfg::kStagingBytes);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_param + Cfg::kParamFloats);
+  uint64_t* full_bar = s_bar;                  // [kStages]
+  uint64_t* empty_bar = s_bar + kStages;       // [kStages]
+  uint64_t* tfull_bar = s_bar + 2 * kStages;   // [kAccStages]
+  uint64_t* tempty_bar = tfull_bar + kAccStages;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tempty_bar + kAccStages);
+
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_kb = (p.K + Cfg::kBlockK - 1) / Cfg::kBlockK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    if (kDual) tma_prefetch_desc(&p.tmA2);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < kAccStages; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], Cfg::kEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(s_tmem, 512);
+    tmem_relinquish();
+  }
+  if (kMode == kModeRowLN && warp >= 2) {
+    // stage the per-column parameter vectors once (N == 256)
+    const float* srcs[9] = {p.bias, p.ln0_g, p.ln0_b, p.lnA_g, p.lnA_b,
+                            p.lnB_g, p.lnB_b, p.dot1, p.dot2};
+    for (int v = 0; v < 9; ++v) {
+      for (int i = threadIdx.x - 64; i < 256; i += 32 * Cfg::kEpiWarps)
+        s_param[v * 256 + i] = srcs[v] ? srcs[v][i] : 0.0f;
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.num_n_tiles;
+        const int n_blk = tile % p.num_n_tiles;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* st = s_stage + s * Cfg::kStageBytes;
+          mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+          tma_load_2d(st, &p.tmA, &full_bar[s], kb * Cfg::kBlockK, m_blk * Cfg::kBlockM);
+          if (kDual)
+            tma_load_2d(st + Cfg::kABytes, &p.tmA2, &full_bar[s], kb * Cfg::kBlockK,
+                        m_blk * Cfg::kBlockM);
+          tma_load_2d(st + Cfg::kABytes * (kDual ? 2 : 1), &p.tmB, &full_bar[s],
+                      kb * Cfg::kBlockK, n_blk * kBlockN);
+          if (++s == kStages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      constexpr uint32_t idesc =
+          umma_idesc(kTf32 ? UMMA_FMT_TF32 : UMMA_FMT_BF16, Cfg::kBlockM, kBlockN);
+      int s = 0;
+      uint32_t ph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[as], aph ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d0 = tmem_base + as * Cfg::kAccCols;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(s_stage + s * Cfg::kStageBytes);
+          const uint32_t b_addr = a_addr + Cfg::kABytes * (kDual ? 2 : 1);
+          const uint64_t a_desc = umma_desc_kmajor_sw128(a_addr);
+          const uint64_t b_desc = umma_desc_kmajor_sw128(b_addr);
+#pragma unroll
+          for (int k = 0; k < Cfg::kBlockK / Cfg::kUmmaK; ++k) {
+            const uint32_t acc = (kb | k) ? 1u : 0u;
+            // advancing K inside the 128B swizzle row: +32 bytes == +2 in the (addr>>4) field
+            umma_ss<kTf32>(d0, a_desc + 2 * k, b_desc + 2 * k, idesc, acc);
+            if (kDual) {
+              const uint64_t a2_desc = umma_desc_kmajor_sw128(a_addr + Cfg::kABytes);
+              umma_ss<kTf32>(d0 + kBlockN, a2_desc + 2 * k, b_desc + 2 * k, idesc, acc);
+            }
+          }
+          umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
+          if (++s == kStages) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+        if (++as == kAccStages) { as = 0; aph ^= 1; }
+      }
+    }
+  } else {
+    // ===================================== epilogue =========================================
+    const int ew = warp - 2;          // 0 .. kEpiWarps-1
+    const int q = warp & 3;           // TMEM lane quadrant this warp may access
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    WarpStager stager{s_staging + ew * 8192, 0};
+    int as = 0;
+    uint32_t aph = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile / p.num_n_tiles;
+      const int n_blk = tile % p.num_n_tiles;
+      const int m0 = m_blk * Cfg::kBlockM;
+      const int n0 = n_blk * kBlockN;
+      const uint32_t tacc = tmem_base + lane_off + as * Cfg::kAccCols;
+
+      if constexpr (kMode == kModeTiled) {
+        // ---- bias for this tile into smem (double-buffered by iteration parity) ----
+        float* sb = s_param + (it & 1) * kBlockN;
+        for (int i = threadIdx.x - 64; i < kBlockN; i += 32 * Cfg::kEpiWarps)
+          sb[i] = (p.bias && n0 + i < p.N) ? p.bias[n0 + i] : 0.0f;
+        named_bar_sync(1, 32 * Cfg::kEpiWarps);
+
+        mbar_wait(&tfull_bar[as], aph);
+        tc_fence_after_sync();
+        const int half = ew >> 2;
+        constexpr int kChunks = kBlockN / 64;  // 32-col chunks per warp (half the tile)
+        for (int c = 0; c < kChunks; ++c) {
+          const int col = half * (kBlockN / 2) + c * 32;
+          if (n0 + col >= p.N) break;  // warp-uniform
+          uint32_t r[32];
+          tmem_ld32(tacc + col, r);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(r[j]) + sb[col + j];
+            x = apply_act(x, p.act);
+            v[j] = p.round_c ? round_tf32(x) : x;
+          }
+          stager.store(&p.tmC, v, n0 + col, m0 + q * 32);
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      } else {
+        // ---------------------------- row-complete epilogue ----------------------------------
+        const float* s_bias = s_param;
+        const float* s_g0 = s_param + 256;
+        const float* s_b0 = s_param + 512;
+        const float* s_gA = s_param + 768;
+        const float* s_bA = s_param + 1024;
+        const float* s_gB = s_param + 1280;
+        const float* s_bB = s_param + 1536;
+        const float* s_d1 = s_param + 1792;
+        const float* s_d2 = s_param + 2048;
+        const int m = m0 + q * 32 + static_cast<int>(lane);
+        const bool valid = m < p.M;
+        const bool has_ln0 = p.ln0_g != nullptr;
+        const bool has_lnA = p.lnA_g != nullptr;
+        const bool has_lnB = p.lnB_g != nullptr;
+        const bool any_ln = has_ln0 || has_lnA || has_lnB;
+        const bool has_dots = p.dots_out != nullptr;
+        float w1 = 1.0f, w2 = 0.0f;
+        if (kDual) {
+          const int seg = (valid ? m : p.M - 1) / p.rows_per_seg;
+          w1 = p.rowscale1[seg];
+          w2 = p.rowscale2[seg];
+        }
+        mbar_wait(&tfull_bar[as], aph);
+        tc_fence_after_sync();
+
+        // PASS A: v0 = residual + alpha * (combine(acc) + bias)
+        float sum = 0.0f, dd1 = 0.0f, dd2 = 0.0f;
+        for (int c = 0; c < 8; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tacc + c * 32, r);
+          float res[32];
+          if (p.residual != nullptr && valid) {
+            const float4* rp =
+                reinterpret_cast<const float4*>(p.residual + static_cast<long long>(m) * p.ldr + c * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 f = __ldg(rp + j);
+              res[4 * j] = f.x; res[4 * j + 1] = f.y; res[4 * j + 2] = f.z; res[4 * j + 3] = f.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) res[j] = 0.0f;
+          }
+          tmem_ld_wait();
+          float v[32];
+          if (kDual) {
+            uint32_t r2[32];
+            tmem_ld32(tacc + kBlockN + c * 32, r2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              v[j] = w1 * __uint_as_float(r[j]) + w2 * __uint_as_float(r2[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v[j] = res[j] + p.alpha * (v[j] + s_bias[c * 32 + j]);
+            sum += v[j];
+          }
+          if (any_ln) {
+            uint32_t w[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(v[j]);
+            tmem_st32(tacc + c * 32, w);
+          }
+          if (!has_ln0) {
+            if (has_dots) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                dd1 += v[j] * s_d1[c * 32 + j];
+                dd2 += v[j] * s_d2[c * 32 + j];
+              }
+            }
+            if (p.has_main) {
+              if (p.round_c) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
+              }
+              stager.store(&p.tmC, v, c * 32, m0 + q * 32);
+            }
+          }
+        }
+        if (any_ln) {
+          tmem_st_wait();
+          float mean = sum * (1.0f / 256.0f);
+          // PASS B: centred second moment of v0
+          float ss = 0.0f;
+          for (int c = 0; c < 8; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tacc + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float d = __uint_as_float(r[j]) - mean;
+              ss += d * d;
+            }
+          }
+          float rstd = rsqrtf(ss * (1.0f / 256.0f) + (has_ln0 ? p.eps0 : p.eps));
+          if (has_ln0) {
+            // PASS C: v1 = LN0(v0) -> TMEM, main output, dots, new sum
+            float sum1 = 0.0f;
+            for (int c = 0; c < 8; ++c) {
+              uint32_t r[32];
+              tmem_ld32(tacc + c * 32, r);
+              tmem_ld_wait();
+              float v[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                v[j] = (__uint_as_float(r[j]) - mean) * rstd * s_g0[c * 32 + j] + s_b0[c * 32 + j];
+                sum1 += v[j];
+                r[j] = __float_as_uint(v[j]);
+              }
+              tmem_st32(tacc + c * 32, r);
+              if (has_dots) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  dd1 += v[j] * s_d1[c * 32 + j];
+                  dd2 += v[j] * s_d2[c * 32 + j];
+                }
+              }
+              if (p.has_main) {
+                if (p.round_c) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
+                }
+                stager.store(&p.tmC, v, c * 32, m0 + q * 32);
+              }
+            }
+            tmem_st_wait();
+            mean = sum1 * (1.0f / 256.0f);
+            // PASS D: centred second moment of v1
+            ss = 0.0f;
+            for (int c = 0; c < 8; ++c) {
+              uint32_t r[32];
+              tmem_ld32(tacc + c * 32, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float d = __uint_as_float(r[j]) - mean;
+                ss += d * d;
+              }
+            }
+            rstd = rsqrtf(ss * (1.0f / 256.0f) + p.eps);
+          }
+          // PASS E: LayerNorm outputs of v1
+          if (has_lnA || has_lnB) {
+            for (int c = 0; c < 8; ++c) {
+              uint32_t r[32];
+              tmem_ld32(tacc + c * 32, r);
+              tmem_ld_wait();
+              float v[32];
+              if (has_lnA) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const float y =
+                      (__uint_as_float(r[j]) - mean) * rstd * s_gA[c * 32 + j] + s_bA[c * 32 + j];
+                  v[j] = p.round_lnA ? round_tf32(y) : y;
+                }
+                stager.store(&p.tmLnA, v, c * 32, m0 + q * 32);
+              }
+              if (has_lnB) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const float y =
+                      (__uint_as_float(r[j]) - mean) * rstd * s_gB[c * 32 + j] + s_bB[c * 32 + j];
+                  v[j] = p.round_lnB ? round_tf32(y) : y;
+                }
+                stager.store(&p.tmLnB, v, c * 32, m0 + q * 32);
+              }
+            }
+          }
+        }
+        if (has_dots && valid) {
+          reinterpret_cast<float2*>(p.dots_out)[m] = make_float2(dd1, dd2);
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      }
+      if (++as == kAccStages) { as = 0; aph ^= 1; }
+    }
+    stager.drain();
+  }
+
+  // ---- teardown ----
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace tavsr

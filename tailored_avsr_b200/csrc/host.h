@@ -1,0 +1,53 @@
+// Host-side helpers shared by the C-ABI entry points: thread-local error string, CUDA error
+// checking, TMA tensor-map encoding (driver entry point resolved at run time so the library links
+// against cudart only) with a small cache.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+
+#include "../../include/tavsr.h"
+
+namespace tavsr {
+
+extern thread_local char g_last_error[512];
+extern int g_debug[16];
+
+inline int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define TAVSR_CUDA_OK(expr)                                                               \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess)                                                                \
+      return ::tavsr::set_error(TAVSR_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,           \
+                                cudaGetErrorString(_e), __FILE__, __LINE__);              \
+  } while (0)
+
+#define TAVSR_REQUIRE(cond, ...)                                            \
+  do {                                                                      \
+    if (!(cond)) return ::tavsr::set_error(TAVSR_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+// Encode (or fetch from cache) a 2-D row-major tensor map:
+//   inner dim = `cols` elements (contiguous), outer dim = `rows`, row pitch `ld` elements.
+//   box = {box_cols, box_rows}, 128-byte swizzle (box_cols * elem_bytes must be 128).
+// Returns 0 on success.
+int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, bool is_bf16, uint64_t rows,
+                 uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols,
+                 bool l2_promote_256 = true);
+
+int num_sms();
+
+}  // namespace tavsr

@@ -1,0 +1,269 @@
+// Memory-bound row kernels: stand-alone LayerNorm, the cgMLP convolutional spatial gating unit
+// (LayerNorm statistics + depthwise conv k=31 over time + gate multiply) and the learned_ave merge
+// weights.  All are coalesced along the channel dimension and use warp-shuffle reductions.
+#include <atomic>
+
+#include "host.h"
+#include "ptx.cuh"
+
+namespace tavsr {
+extern std::atomic<long long> g_launches;
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, row kept in registers (D <= 2048 -> <= 16 float4 per lane).
+// ------------------------------------------------------------------------------------------------
+template <int kVec>  // number of float4 per lane: D = 128 * kVec
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, long long ldx, int M, float eps,
+                 const float* __restrict__ gA, const float* __restrict__ bA,
+                 float* __restrict__ outA, long long ldA, int roundA,
+                 const float* __restrict__ gB, const float* __restrict__ bB,
+                 float* __restrict__ outB, long long ldB, int roundB, float scale) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const uint32_t lane = lane_id();
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * ldx);
+  float4 v[kVec];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) {
+    v[i] = __ldg(xr + lane + 32 * i);
+    sum += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  const float inv_d = 1.0f / (128.0f * kVec);
+  const float mean = warp_sum(sum) * inv_d;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+  }
+  const float rstd = rsqrtf(warp_sum(ss) * inv_d + eps);
+  auto emit = [&](const float* g, const float* b, float* out, long long ld, int rnd) {
+    float4* o = reinterpret_cast<float4*>(out + static_cast<long long>(row) * ld);
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+      const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + lane + 32 * i);
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + lane + 32 * i);
+      float4 y;
+      y.x = (v[i].x * rstd * gg.x + bb.x) * scale;
+      y.y = (v[i].y * rstd * gg.y + bb.y) * scale;
+      y.z = (v[i].z * rstd * gg.z + bb.z) * scale;
+      y.w = (v[i].w * rstd * gg.w + bb.w) * scale;
+      if (rnd) { y.x = round_tf32(y.x); y.y = round_tf32(y.y); y.z = round_tf32(y.z); y.w = round_tf32(y.w); }
+      o[lane + 32 * i] = y;
+    }
+  };
+  if (outA) emit(gA, bA, outA, ldA, roundA);
+  if (outB) emit(gB, bB, outB, ldB, roundB);
+}
+
+// ------------------------------------------------------------------------------------------------
+// CSGU pass 1: LayerNorm statistics of the gate half, one warp per frame.
+// ------------------------------------------------------------------------------------------------
+template <int kVec>  // Ch = 128 * kVec
+__global__ void __launch_bounds__(256)
+csgu_stats_kernel(const float* __restrict__ h, long long ldh, int M, int Ch, float eps,
+                  float2* __restrict__ stats) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const uint32_t lane = lane_id();
+  const float4* g = reinterpret_cast<const float4*>(h + static_cast<long long>(row) * ldh + Ch);
+  float4 v[kVec];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) {
+    v[i] = __ldg(g + lane + 32 * i);
+    sum += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  const float inv_d = 1.0f / (128.0f * kVec);
+  const float mean = warp_sum(sum) * inv_d;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    ss += a * a + b * b + c * c + d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(ss) * inv_d + eps);
+  if (lane == 0) stats[row] = make_float2(mean, rstd);
+}
+
+// ------------------------------------------------------------------------------------------------
+// CSGU pass 2: out[b,t,c] = r[b,t,c] * (sum_k w[c,k] * LN(g)[b,t+k-15,c] + cb[c])
+// One thread per channel (lanes -> consecutive channels: every global access is a coalesced 128 B
+// line per warp), each thread slides over kSeg output frames keeping the 31 taps in registers and
+// computing 16 outputs per pass from a register window.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTaps = 31;
+constexpr int kHalo = 15;
+constexpr int kSeg = 64;   // output frames per CTA
+constexpr int kGrp = 16;   // outputs per register pass
+
+__global__ void __launch_bounds__(128)
+csgu_conv_kernel(const float* __restrict__ h, long long ldh, const float* __restrict__ norm_g,
+                 const float* __restrict__ norm_b, const float* __restrict__ conv_w,
+                 const float* __restrict__ conv_b, const float2* __restrict__ stats,
+                 float* __restrict__ out, long long ldo, int T, int Ch, int round_out) {
+  __shared__ float2 s_stats[kSeg + 2 * kHalo];
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  const int t0 = blockIdx.y * kSeg;
+  const int b = blockIdx.z;
+  const long long row0 = static_cast<long long>(b) * T;
+  for (int i = threadIdx.x; i < kSeg + 2 * kHalo; i += 128) {
+    const int t = t0 - kHalo + i;
+    s_stats[i] = (t >= 0 && t < T) ? stats[row0 + t] : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  if (c >= Ch) return;
+  float w[kTaps];
+#pragma unroll
+  for (int k = 0; k < kTaps; ++k) w[k] = __ldg(conv_w + static_cast<long long>(c) * kTaps + k);
+  const float gam = __ldg(norm_g + c), bet = __ldg(norm_b + c), cb = __ldg(conv_b + c);
+  const float* gcol = h + Ch + c;
+  const float* rcol = h + c;
+
+  for (int g0 = 0; g0 < kSeg; g0 += kGrp) {
+    const int tb = t0 + g0;  // first output frame of this group
+    if (tb >= T) break;
+    float acc[kGrp];
+#pragma unroll
+    for (int o = 0; o < kGrp; ++o) acc[o] = 0.f;
+#pragma unroll
+    for (int ii = 0; ii < kGrp + kTaps - 1; ++ii) {
+      const int t = tb - kHalo + ii;
+      float xn = 0.f;
+      if (t >= 0 && t < T) {
+        const float2 st = s_stats[g0 + ii];
+        xn = (__ldg(gcol + (row0 + t) * ldh) - st.x) * st.y * gam + bet;
+      }
+#pragma unroll
+      for (int o = 0; o < kGrp; ++o) {
+        const int k = ii - o;
+        if (k >= 0 && k < kTaps) acc[o] = fmaf(w[k], xn, acc[o]);
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < kGrp; ++o) {
+      const int t = tb + o;
+      if (t < T) {
+        float y = __ldg(rcol + (row0 + t) * ldh) * (acc[o] + cb);
+        out[(row0 + t) * ldo + c] = round_out ? round_tf32(y) : y;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// learned_ave merge weights: one warp per utterance.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+merge_weights_kernel(const float2* __restrict__ dots1, const float2* __restrict__ dots2,
+                     const int32_t* __restrict__ lens, float pool_b1, float pool_b2, float wproj_b1,
+                     float wproj_b2, float inv_sqrt, float* __restrict__ w1, float* __restrict__ w2,
+                     int B, int T) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const uint32_t lane = lane_id();
+  int len = lens ? lens[b] : T;
+  len = len < 0 ? 0 : (len > T ? T : len);
+  float omega[2];
+#pragma unroll
+  for (int br = 0; br < 2; ++br) {
+    const float2* d = (br == 0 ? dots1 : dots2) + static_cast<long long>(b) * T;
+    const float pb = br == 0 ? pool_b1 : pool_b2;
+    float mx = -INFINITY;
+    for (int t = lane; t < len; t += 32) mx = fmaxf(mx, (d[t].x + pb) * inv_sqrt);
+    mx = warp_max(mx);
+    float se = 0.f, sz = 0.f;
+    for (int t = lane; t < len; t += 32) {
+      const float2 v = d[t];
+      const float e = expf((v.x + pb) * inv_sqrt - mx);
+      se += e;
+      sz += e * v.y;
+    }
+    se = warp_sum(se);
+    sz = warp_sum(sz);
+    // len == 0: every score is masked, softmax-then-zero gives an all-zero pooling vector
+    omega[br] = (len > 0 ? sz / se : 0.f) + (br == 0 ? wproj_b1 : wproj_b2);
+  }
+  if (lane == 0) {
+    const float m = fmaxf(omega[0], omega[1]);
+    const float e0 = expf(omega[0] - m), e1 = expf(omega[1] - m);
+    w1[b] = e0 / (e0 + e1);
+    w2[b] = e1 / (e0 + e1);
+  }
+}
+
+}  // namespace tavsr
+
+using namespace tavsr;
+
+extern "C" int tavsr_layernorm(const float* x, long long ldx, int M, int D, float eps,
+                               const float* gA, const float* bA, float* outA, long long ldA,
+                               int roundA, const float* gB, const float* bB, float* outB,
+                               long long ldB, int roundB, float scale, void* stream) {
+  TAVSR_REQUIRE(M > 0 && D > 0 && D % 128 == 0 && D <= 2048, "layernorm: D=%d unsupported", D);
+  TAVSR_REQUIRE(ldx % 4 == 0 && (!outA || ldA % 4 == 0) && (!outB || ldB % 4 == 0),
+                "layernorm: pitches must be multiples of 4");
+  TAVSR_REQUIRE((!outA || (gA && bA)) && (!outB || (gB && bB)), "layernorm: missing affine");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int rows_per_block = 8;
+  const int grid = (M + rows_per_block - 1) / rows_per_block;
+#define TAVSR_LN_CASE(V)                                                                          \
+  case V:                                                                                         \
+    layernorm_kernel<V><<<grid, 256, 0, s>>>(x, ldx, M, eps, gA, bA, outA, ldA, roundA, gB, bB,   \
+                                             outB, ldB, roundB, scale);                           \
+    break;
+  switch (D / 128) {
+    TAVSR_LN_CASE(1) TAVSR_LN_CASE(2) TAVSR_LN_CASE(3) TAVSR_LN_CASE(4) TAVSR_LN_CASE(6)
+    TAVSR_LN_CASE(8) TAVSR_LN_CASE(16)
+    default:
+      return set_error(TAVSR_ERR_UNSUPPORTED, "layernorm: D=%d not instantiated", D);
+  }
+#undef TAVSR_LN_CASE
+  TAVSR_CUDA_OK(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+extern "C" int tavsr_csgu_fwd(const float* h, long long ldh, const float* norm_g,
+                              const float* norm_b, const float* conv_w, const float* conv_b,
+                              float* out, long long ldo, float* stats, int B, int T, int Ch,
+                              int ksize, float eps, int round_out, void* stream) {
+  TAVSR_REQUIRE(ksize == kTaps, "csgu: only kernel size 31 is built (got %d)", ksize);
+  TAVSR_REQUIRE(B > 0 && T > 0 && Ch > 0 && Ch % 128 == 0 && Ch <= 2048, "csgu: bad shape");
+  TAVSR_REQUIRE(ldh % 4 == 0 && stats != nullptr, "csgu: bad pitch / missing stats scratch");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int M = B * T;
+  const int grid1 = (M + 7) / 8;
+  float2* st = reinterpret_cast<float2*>(stats);
+  switch (Ch / 128) {
+    case 1: csgu_stats_kernel<1><<<grid1, 256, 0, s>>>(h, ldh, M, Ch, eps, st); break;
+    case 2: csgu_stats_kernel<2><<<grid1, 256, 0, s>>>(h, ldh, M, Ch, eps, st); break;
+    case 4: csgu_stats_kernel<4><<<grid1, 256, 0, s>>>(h, ldh, M, Ch, eps, st); break;
+    case 8: csgu_stats_kernel<8><<<grid1, 256, 0, s>>>(h, ldh, M, Ch, eps, st); break;
+    case 16: csgu_stats_kernel<16><<<grid1, 256, 0, s>>>(h, ldh, M, Ch, eps, st); break;
+    default: return set_error(TAVSR_ERR_UNSUPPORTED, "csgu: Ch=%d not instantiated", Ch);
+  }
+  TAVSR_CUDA_OK(cudaGetLastError());
+  dim3 grid2(Ch / 128, (T + kSeg - 1) / kSeg, B);
+  csgu_conv_kernel<<<grid2, 128, 0, s>>>(h, ldh, norm_g, norm_b, conv_w, conv_b, st, out, ldo, T,
+                                         Ch, round_out);
+  TAVSR_CUDA_OK(cudaGetLastError());
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  return 0;
+}
+
+extern "C" int tavsr_merge_learned_ave_weights(const float* dots1, const float* dots2,
+                                               const int32_t* lens, float pool_b1, float pool_b2,
+                                               float wproj_b1, float wproj_b2, float inv_sqrt_size,
+                                               float* w1, float* w2, int B, int T, void* stream) {
+  TAVSR_REQUIRE(B > 0 && T > 0 && dots1 && dots2 && w1 && w2, "merge_weights: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  merge_weights_kernel<<<(B + 3) / 4, 128, 0, s>>>(
+      reinterpret_cast<const float2*>(dots1), reinterpret_cast<const float2*>(dots2), lens,
+      pool_b1, pool_b2, wproj_b1, wproj_b2, inv_sqrt_size, w1, w2, B, T);
+  TAVSR_CUDA_OK(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}

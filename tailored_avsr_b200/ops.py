@@ -1,0 +1,236 @@
+"""Tensor-level wrappers over the C ABI (include/tavsr.h).
+
+PyTorch is used only for device memory and streams: every function here takes CUDA tensors, passes
+raw device pointers + the current stream to libtavsr_sm100.so and returns the output tensors.
+There is no CPU or eager fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SWISH, DT_TF32, RowLNArgs, check
+
+__all__ = [
+    "ACT_NONE", "ACT_SWISH", "ACT_GELU", "ACT_RELU",
+    "gemm_bias_act", "gemm_rowln", "layernorm", "relpos_attn", "csgu", "merge_weights",
+    "ctc_head", "ctc_loss", "ctc_greedy", "ctc_prefix_score", "launch_count",
+]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _chk2d(t: torch.Tensor, name: str, dtype=torch.float32) -> None:
+    if not t.is_cuda:
+        raise _lib.TavsrError(f"{name} must be a CUDA tensor (no CPU fallback exists)")
+    if t.dtype != dtype or t.dim() != 2 or t.stride(1) != 1:
+        raise _lib.TavsrError(f"{name} must be 2-D {dtype} with unit inner stride, got "
+                              f"{tuple(t.shape)} {t.dtype} strides {t.stride()}")
+
+
+def launch_count() -> int:
+    return int(_lib.load().tavsr_launch_count())
+
+
+def gemm_bias_act(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: int = ACT_NONE,
+                  round_out: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = act(x @ w.T + bias) on the tcgen05 GEMM (tavsr_gemm_bias_act)."""
+    _chk2d(x, "x")
+    _chk2d(w, "w")
+    M, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), device=x.device, dtype=torch.float32)
+    _chk2d(out, "out")
+    lib = _lib.load()
+    check(lib.tavsr_gemm_bias_act(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), _p(bias),
+                                  out.data_ptr(), out.stride(0), M, N, K, act, int(round_out),
+                                  DT_TF32, _stream()), "tavsr_gemm_bias_act")
+    return out
+
+
+def gemm_rowln(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
+               x2: Optional[torch.Tensor] = None,
+               rowscale: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, rows_per_seg: int = 0,
+               residual: Optional[torch.Tensor] = None, alpha: float = 1.0,
+               ln0: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, eps0: float = 1e-12,
+               out_main: Optional[torch.Tensor] = None, round_main: bool = False,
+               lnA: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+               out_lnA: Optional[torch.Tensor] = None, round_lnA: bool = False,
+               lnB: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+               out_lnB: Optional[torch.Tensor] = None, round_lnB: bool = False,
+               eps: float = 1e-12,
+               dots: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+               dots_out: Optional[torch.Tensor] = None) -> None:
+    """Row-complete N=256 GEMM with fused residual / LayerNorm / row-dot epilogue (tavsr_gemm_rowln)."""
+    _chk2d(x, "x")
+    _chk2d(w, "w")
+    a = RowLNArgs()
+    a.struct_size = ctypes.sizeof(RowLNArgs)
+    a.M, a.K = x.shape
+    a.dtype = DT_TF32
+    a.x, a.ldx = x.data_ptr(), x.stride(0)
+    if x2 is not None:
+        _chk2d(x2, "x2")
+        a.x2, a.ldx2 = x2.data_ptr(), x2.stride(0)
+        a.rowscale1, a.rowscale2 = rowscale[0].data_ptr(), rowscale[1].data_ptr()
+        a.rows_per_seg = rows_per_seg
+    a.w, a.ldw = w.data_ptr(), w.stride(0)
+    a.bias = _p(bias)
+    if residual is not None:
+        _chk2d(residual, "residual")
+        a.residual, a.ldr = residual.data_ptr(), residual.stride(0)
+    a.alpha = alpha
+    if ln0 is not None:
+        a.ln0_g, a.ln0_b = ln0[0].data_ptr(), ln0[1].data_ptr()
+    a.eps0 = eps0
+    if out_main is not None:
+        _chk2d(out_main, "out_main")
+        a.out_main, a.ld_main = out_main.data_ptr(), out_main.stride(0)
+    a.round_main = int(round_main)
+    if lnA is not None:
+        _chk2d(out_lnA, "out_lnA")
+        a.lnA_g, a.lnA_b = lnA[0].data_ptr(), lnA[1].data_ptr()
+        a.out_lnA, a.ld_lnA = out_lnA.data_ptr(), out_lnA.stride(0)
+    a.round_lnA = int(round_lnA)
+    if lnB is not None:
+        _chk2d(out_lnB, "out_lnB")
+        a.lnB_g, a.lnB_b = lnB[0].data_ptr(), lnB[1].data_ptr()
+        a.out_lnB, a.ld_lnB = out_lnB.data_ptr(), out_lnB.stride(0)
+    a.round_lnB = int(round_lnB)
+    a.eps = eps
+    if dots is not None:
+        a.dot1, a.dot2 = dots[0].data_ptr(), dots[1].data_ptr()
+        a.dots_out = dots_out.data_ptr()
+    check(_lib.load().tavsr_gemm_rowln(ctypes.byref(a), _stream()), "tavsr_gemm_rowln")
+
+
+def layernorm(x: torch.Tensor, gA: torch.Tensor, bA: torch.Tensor, eps: float = 1e-12,
+              round_out: bool = False, scale: float = 1.0, out: Optional[torch.Tensor] = None,
+              gB: Optional[torch.Tensor] = None, bB: Optional[torch.Tensor] = None,
+              outB: Optional[torch.Tensor] = None, roundB: bool = False) -> torch.Tensor:
+    _chk2d(x, "x")
+    M, D = x.shape
+    if out is None:
+        out = torch.empty((M, D), device=x.device, dtype=torch.float32)
+    check(_lib.load().tavsr_layernorm(x.data_ptr(), x.stride(0), M, D, eps, gA.data_ptr(),
+                                      bA.data_ptr(), out.data_ptr(), out.stride(0), int(round_out),
+                                      _p(gB), _p(bB), _p(outB),
+                                      outB.stride(0) if outB is not None else 0, int(roundB),
+                                      scale, _stream()), "tavsr_layernorm")
+    return out
+
+
+def relpos_attn(qkv: torch.Tensor, pos: torch.Tensor, u: torch.Tensor, v: torch.Tensor,
+                lens: Optional[torch.Tensor], B: int, T: int, H: int, round_out: bool = True,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """ctx = rel-pos MHSA(qkv) for (B*T, 3*H*64) fused projections (tavsr_relpos_attn_fwd)."""
+    _chk2d(qkv, "qkv")
+    _chk2d(pos, "pos")
+    if out is None:
+        out = torch.empty((B * T, H * 64), device=qkv.device, dtype=torch.float32)
+    check(_lib.load().tavsr_relpos_attn_fwd(qkv.data_ptr(), qkv.stride(0), pos.data_ptr(),
+                                            pos.stride(0), u.data_ptr(), v.data_ptr(), _p(lens),
+                                            out.data_ptr(), out.stride(0), B, T, H,
+                                            int(round_out), _stream()), "tavsr_relpos_attn_fwd")
+    return out
+
+
+def csgu(h: torch.Tensor, norm_g: torch.Tensor, norm_b: torch.Tensor, conv_w: torch.Tensor,
+         conv_b: torch.Tensor, B: int, T: int, eps: float = 1e-12, round_out: bool = True,
+         out: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = r * (dwconv31(LN(g)) + b) for h = [r | g] (tavsr_csgu_fwd)."""
+    _chk2d(h, "h")
+    Ch = h.shape[1] // 2
+    if out is None:
+        out = torch.empty((B * T, Ch), device=h.device, dtype=torch.float32)
+    if stats is None:
+        stats = torch.empty((B * T, 2), device=h.device, dtype=torch.float32)
+    ksize = conv_w.shape[-1]
+    check(_lib.load().tavsr_csgu_fwd(h.data_ptr(), h.stride(0), norm_g.data_ptr(),
+                                     norm_b.data_ptr(), conv_w.data_ptr(), conv_b.data_ptr(),
+                                     out.data_ptr(), out.stride(0), stats.data_ptr(), B, T, Ch,
+                                     ksize, eps, int(round_out), _stream()), "tavsr_csgu_fwd")
+    return out
+
+
+def merge_weights(dots1: torch.Tensor, dots2: torch.Tensor, lens: Optional[torch.Tensor],
+                  pool_b1: float, pool_b2: float, wproj_b1: float, wproj_b2: float, size: int,
+                  B: int, T: int, w1: Optional[torch.Tensor] = None,
+                  w2: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    if w1 is None:
+        w1 = torch.empty((B,), device=dots1.device, dtype=torch.float32)
+    if w2 is None:
+        w2 = torch.empty((B,), device=dots1.device, dtype=torch.float32)
+    check(_lib.load().tavsr_merge_learned_ave_weights(
+        dots1.data_ptr(), dots2.data_ptr(), _p(lens), pool_b1, pool_b2, wproj_b1, wproj_b2,
+        1.0 / math.sqrt(size), w1.data_ptr(), w2.data_ptr(), B, T, _stream()),
+        "tavsr_merge_learned_ave_weights")
+    return w1, w2
+
+
+def ctc_head(hs: torch.Tensor, w: torch.Tensor, b: torch.Tensor, want_logp: bool = True,
+             want_prob: bool = False, want_argmax: bool = False):
+    """(logp, prob, argmax) of ctc_lo(hs) over the vocabulary, fp32 FMA (tavsr_ctc_head)."""
+    _chk2d(hs, "hs")
+    M, D = hs.shape
+    V = w.shape[0]
+    logp = torch.empty((M, V), device=hs.device, dtype=torch.float32) if want_logp else None
+    prob = torch.empty((M, V), device=hs.device, dtype=torch.float32) if want_prob else None
+    amax = torch.empty((M,), device=hs.device, dtype=torch.int64) if want_argmax else None
+    check(_lib.load().tavsr_ctc_head(hs.data_ptr(), hs.stride(0), w.data_ptr(), b.data_ptr(),
+                                     _p(logp), _p(prob), _p(amax), M, D, V, _stream()),
+          "tavsr_ctc_head")
+    return logp, prob, amax
+
+
+def ctc_loss(logp: torch.Tensor, targets: torch.Tensor, hlens: torch.Tensor, tlens: torch.Tensor,
+             want_grad: bool = False, gscale: float = 1.0, zero_infinity: bool = True):
+    """Per-utterance NLL (and optionally d/dlogits) from (B,T,V) log-probs (tavsr_ctc_loss)."""
+    B, T, V = logp.shape
+    Lmax = targets.shape[1]
+    nll = torch.empty((B,), device=logp.device, dtype=torch.float32)
+    grad = ws = None
+    lib = _lib.load()
+    if want_grad:
+        grad = torch.empty((B, T, V), device=logp.device, dtype=torch.float32)
+        ws = torch.empty((lib.tavsr_ctc_workspace_bytes(B, T, Lmax) // 4,), device=logp.device,
+                         dtype=torch.float32)
+    check(lib.tavsr_ctc_loss(logp.data_ptr(), targets.data_ptr(), targets.stride(0),
+                             hlens.data_ptr(), tlens.data_ptr(), nll.data_ptr(), _p(grad), gscale,
+                             _p(ws), B, T, V, Lmax, int(zero_infinity), _stream()),
+          "tavsr_ctc_loss")
+    return nll, grad
+
+
+def ctc_greedy(amax: torch.Tensor, lens: Optional[torch.Tensor], blank: int = 0):
+    B, T = amax.shape
+    tokens = torch.empty((B, T), device=amax.device, dtype=torch.int64)
+    ntok = torch.empty((B,), device=amax.device, dtype=torch.int32)
+    check(_lib.load().tavsr_ctc_greedy(amax.data_ptr(), _p(lens), tokens.data_ptr(),
+                                       ntok.data_ptr(), B, T, blank, _stream()),
+          "tavsr_ctc_greedy")
+    return tokens, ntok
+
+
+def ctc_prefix_score(logp: torch.Tensor, r_prev: torch.Tensor, last: torch.Tensor,
+                     plen: torch.Tensor, psi_prev: torch.Tensor, Tvalid: int, blank: int, eos: int):
+    T, V = logp.shape
+    nhyp = r_prev.shape[0]
+    r_new = torch.empty((nhyp, T, V, 2), device=logp.device, dtype=torch.float32)
+    score = torch.empty((nhyp, V), device=logp.device, dtype=torch.float32)
+    check(_lib.load().tavsr_ctc_prefix_score(logp.data_ptr(), r_prev.data_ptr(), last.data_ptr(),
+                                             plen.data_ptr(), psi_prev.data_ptr(),
+                                             r_new.data_ptr(), score.data_ptr(), T, Tvalid, V, nhyp,
+                                             blank, eos, _stream()), "tavsr_ctc_prefix_score")
+    return r_new, score

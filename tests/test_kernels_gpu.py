@@ -1,0 +1,289 @@
+"""Per-kernel parity of the CUDA path (through the C ABI) against plain torch fp64/fp32 math.
+
+These are kernel unit tests; whole-layer / whole-encoder parity against the oracle lives in
+test_parity_gpu.py.  Tolerances: TF32 tensor-core products are compared with a relative
+Frobenius bound of 2e-3 (10-bit mantissa operands, fp32 accumulate); pure fp32 kernels with 1e-5.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from tailored_avsr_b200 import ops
+    return ops
+
+
+def rel_fro(a, b):
+    a = a.double().cpu()
+    b = b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def max_rel(a, b):
+    a = a.double().cpu()
+    b = b.double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+DEV = "cuda"
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 32), (128, 256, 256), (200, 768, 256),
+                                   (1992, 2048, 256), (8000, 2048, 256), (333, 128, 64),
+                                   (8000, 768, 256), (500, 3072, 256), (77, 48, 1024)])
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_gemm_bias_act(M, N, K, act):
+    ops = _ops()
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K + act)
+    x = torch.randn(M, K, generator=g).to(DEV)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    y = ops.gemm_bias_act(x, w, b, act=act)
+    ref = x.double() @ w.double().t() + b.double()
+    if act == 1:
+        ref = ref * torch.sigmoid(ref)
+    elif act == 2:
+        ref = F.gelu(ref)
+    torch.cuda.synchronize()
+    assert rel_fro(y, ref) < 2e-3, (rel_fro(y, ref), max_rel(y, ref))
+    assert max_rel(y, ref) < 5e-3
+
+
+def test_gemm_exact_on_tf32_representable_inputs():
+    """With operands exactly representable in TF32 the product must match fp32 to ~1e-6."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(0)
+    M, N, K = 384, 512, 256
+    x = torch.randint(-8, 9, (M, K), generator=g).float().to(DEV)
+    w = (torch.randint(-8, 9, (N, K), generator=g).float() / 8).to(DEV)
+    y = ops.gemm_bias_act(x, w, None)
+    ref = x.double() @ w.double().t()
+    assert max_rel(y, ref) < 1e-6
+
+
+def _ln(x, g, b, eps):
+    return F.layer_norm(x, (x.shape[-1],), g, b, eps)
+
+
+@pytest.mark.parametrize("M,K", [(128, 256), (1992, 2048), (300, 1024), (8000, 256), (64, 4864)])
+def test_gemm_rowln_residual_two_ln(M, K):
+    ops = _ops()
+    g = torch.Generator().manual_seed(M + K)
+    x = torch.randn(M, K, generator=g).to(DEV)
+    w = (torch.randn(256, K, generator=g) / math.sqrt(K)).to(DEV)
+    b = torch.randn(256, generator=g).to(DEV)
+    res = torch.randn(M, 256, generator=g).to(DEV)
+    gA, bA, gB, bB = [torch.randn(256, generator=g).to(DEV) for _ in range(4)]
+    main = torch.empty(M, 256, device=DEV)
+    oA = torch.empty(M, 256, device=DEV)
+    oB = torch.empty(M, 256, device=DEV)
+    ops.gemm_rowln(x, w, b, residual=res, alpha=0.5, out_main=main, lnA=(gA, bA), out_lnA=oA,
+                   lnB=(gB, bB), out_lnB=oB, eps=1e-12)
+    v = res.double() + 0.5 * (x.double() @ w.double().t() + b.double())
+    assert rel_fro(main, v) < 2e-3
+    assert rel_fro(oA, _ln(v, gA.double(), bA.double(), 1e-12)) < 3e-3
+    assert rel_fro(oB, _ln(v, gB.double(), bB.double(), 1e-12)) < 3e-3
+
+
+def test_gemm_rowln_chained_ln_and_dots():
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    M, K = 700, 2048
+    x = torch.randn(M, K, generator=g).to(DEV)
+    w = (torch.randn(256, K, generator=g) / math.sqrt(K)).to(DEV)
+    b = torch.randn(256, generator=g).to(DEV)
+    res = torch.randn(M, 256, generator=g).to(DEV)
+    g0, b0, gA, bA, d1, d2 = [torch.randn(256, generator=g).to(DEV) for _ in range(6)]
+    main = torch.empty(M, 256, device=DEV)
+    oA = torch.empty(M, 256, device=DEV)
+    dots = torch.empty(M, 2, device=DEV)
+    ops.gemm_rowln(x, w, b, residual=res, alpha=0.5, ln0=(g0, b0), eps0=1e-5, out_main=main,
+                   lnA=(gA, bA), out_lnA=oA, eps=1e-12, dots=(d1, d2), dots_out=dots)
+    v0 = res.double() + 0.5 * (x.double() @ w.double().t() + b.double())
+    v1 = _ln(v0, g0.double(), b0.double(), 1e-5)
+    assert rel_fro(main, v1) < 3e-3
+    assert rel_fro(oA, _ln(v1, gA.double(), bA.double(), 1e-12)) < 3e-3
+    ref_d = torch.stack([v1 @ d1.double(), v1 @ d2.double()], dim=1)
+    assert rel_fro(dots, ref_d) < 3e-3
+
+
+def test_gemm_rowln_dual_merge():
+    ops = _ops()
+    g = torch.Generator().manual_seed(11)
+    B, T = 5, 77
+    M = B * T
+    x1 = torch.randn(M, 256, generator=g).to(DEV)
+    x2 = torch.randn(M, 256, generator=g).to(DEV)
+    w = (torch.randn(256, 256, generator=g) / 16).to(DEV)
+    b = torch.randn(256, generator=g).to(DEV)
+    res = torch.randn(M, 256, generator=g).to(DEV)
+    w1 = torch.rand(B, generator=g).to(DEV)
+    w2 = 1 - w1
+    gA, bA = torch.randn(256, generator=g).to(DEV), torch.randn(256, generator=g).to(DEV)
+    main = torch.empty(M, 256, device=DEV)
+    oA = torch.empty(M, 256, device=DEV)
+    ops.gemm_rowln(x1, w, b, x2=x2, rowscale=(w1, w2), rows_per_seg=T, residual=res, alpha=1.0,
+                   out_main=main, lnA=(gA, bA), out_lnA=oA)
+    mix = (w1.double().repeat_interleave(T)[:, None] * x1.double()
+           + w2.double().repeat_interleave(T)[:, None] * x2.double())
+    v = res.double() + mix @ w.double().t() + b.double()
+    assert rel_fro(main, v) < 2e-3
+    assert rel_fro(oA, _ln(v, gA.double(), bA.double(), 1e-12)) < 3e-3
+
+
+@pytest.mark.parametrize("M,D", [(1000, 256), (37, 1024), (8, 512)])
+def test_layernorm(M, D):
+    ops = _ops()
+    g = torch.Generator().manual_seed(M)
+    x = (torch.randn(M, D, generator=g) * 3 + 1).to(DEV)
+    gA, bA, gB, bB = [torch.randn(D, generator=g).to(DEV) for _ in range(4)]
+    oB = torch.empty(M, D, device=DEV)
+    oA = ops.layernorm(x, gA, bA, eps=1e-12, gB=gB, bB=bB, outB=oB, scale=1.0)
+    assert max_rel(oA, _ln(x.double(), gA.double(), bA.double(), 1e-12)) < 1e-5
+    assert max_rel(oB, _ln(x.double(), gB.double(), bB.double(), 1e-12)) < 1e-5
+
+
+def _rel_shift(x):
+    b, h, t, n = x.shape
+    zero_pad = torch.zeros((b, h, t, 1), dtype=x.dtype)
+    x_padded = torch.cat([zero_pad, x], dim=-1).view(b, h, n + 1, t)
+    return x_padded[:, :, 1:].view_as(x)[:, :, :, : n // 2 + 1]
+
+
+@pytest.mark.parametrize("B,T,lens", [(2, 64, [64, 40]), (3, 100, [100, 1, 77]), (2, 250, [250, 130]),
+                                      (1, 17, [17]), (2, 130, [0, 130])])
+def test_relpos_attention(B, T, lens):
+    ops = _ops()
+    H, dk = 4, 64
+    g = torch.Generator().manual_seed(T)
+    qkv = torch.randn(B * T, 3 * H * dk, generator=g)
+    pos = torch.randn(2 * T - 1, H * dk, generator=g)
+    u = torch.randn(H * dk, generator=g) * 0.5
+    v = torch.randn(H * dk, generator=g) * 0.5
+    lens_t = torch.tensor(lens, dtype=torch.int32)
+    out = ops.relpos_attn(qkv.to(DEV), pos.to(DEV), u.to(DEV), v.to(DEV), lens_t.to(DEV), B, T, H,
+                          round_out=False)
+    # espnet-style reference in fp64
+    q, k, vv = [t.double().view(B, T, H, dk).transpose(1, 2) for t in qkv.split(H * dk, dim=1)]
+    p = pos.double().view(1, 2 * T - 1, H, dk).transpose(1, 2)
+    ac = (q + u.double().view(1, H, 1, dk)) @ k.transpose(-2, -1)
+    bd = _rel_shift((q + v.double().view(1, H, 1, dk)) @ p.transpose(-2, -1))
+    scores = (ac + bd) / math.sqrt(dk)
+    mask = (torch.arange(T)[None, :] >= lens_t[:, None].long())[:, None, None, :]
+    scores = scores.masked_fill(mask, torch.finfo(torch.float64).min)
+    attn = torch.softmax(scores, dim=-1).masked_fill(mask, 0.0)
+    ref = (attn @ vv).transpose(1, 2).reshape(B * T, H * dk)
+    assert rel_fro(out, ref) < 3e-3, rel_fro(out, ref)
+    assert max_rel(out, ref) < 1e-2
+
+
+@pytest.mark.parametrize("B,T", [(2, 64), (3, 100), (2, 250), (1, 7)])
+def test_csgu(B, T):
+    ops = _ops()
+    Ch = 1024
+    g = torch.Generator().manual_seed(B * T)
+    h = torch.randn(B * T, 2 * Ch, generator=g)
+    ng, nb = torch.randn(Ch, generator=g), torch.randn(Ch, generator=g)
+    cw = torch.randn(Ch, 1, 31, generator=g) * 0.2
+    cb = torch.randn(Ch, generator=g)
+    out = ops.csgu(h.to(DEV), ng.to(DEV), nb.to(DEV), cw.to(DEV).contiguous(), cb.to(DEV), B, T,
+                   round_out=False)
+    hd = h.double().view(B, T, 2 * Ch)
+    r, gt = hd.chunk(2, dim=-1)
+    gt = F.layer_norm(gt, (Ch,), ng.double(), nb.double(), 1e-12)
+    gt = F.conv1d(gt.transpose(1, 2), cw.double(), cb.double(), padding=15, groups=Ch).transpose(1, 2)
+    ref = (r * gt).reshape(B * T, Ch)
+    assert max_rel(out, ref) < 1e-5, max_rel(out, ref)
+
+
+def test_merge_weights():
+    ops = _ops()
+    B, T = 6, 90
+    g = torch.Generator().manual_seed(3)
+    d1 = torch.randn(B * T, 2, generator=g) * 4
+    d2 = torch.randn(B * T, 2, generator=g) * 4
+    lens = torch.tensor([90, 1, 45, 0, 89, 33], dtype=torch.int32)
+    pb1, pb2, wb1, wb2 = 0.3, -0.2, 0.1, 0.7
+    w1, w2 = ops.merge_weights(d1.to(DEV), d2.to(DEV), lens.to(DEV), pb1, pb2, wb1, wb2, 256, B, T)
+    om = []
+    for d, pb, wb in ((d1, pb1, wb1), (d2, pb2, wb2)):
+        dd = d.double().view(B, T, 2)
+        sc = (dd[..., 0] + pb) / 16.0
+        mask = torch.arange(T)[None, :] >= lens[:, None].long()
+        sc = sc.masked_fill(mask, torch.finfo(torch.float32).min)
+        s = torch.softmax(sc, dim=-1).masked_fill(mask, 0.0)
+        om.append((s * dd[..., 1]).sum(-1) + wb)
+    ref = torch.softmax(torch.stack(om, dim=-1), dim=-1)
+    assert max_rel(w1, ref[:, 0]) < 1e-5
+    assert max_rel(w2, ref[:, 1]) < 1e-5
+
+
+@pytest.mark.parametrize("M,V", [(1992, 41), (100, 37), (5, 64), (3, 5)])
+def test_ctc_head(M, V):
+    ops = _ops()
+    g = torch.Generator().manual_seed(V)
+    hs = torch.randn(M, 256, generator=g)
+    w = torch.randn(V, 256, generator=g) / 16
+    b = torch.randn(V, generator=g)
+    logp, prob, amax = ops.ctc_head(hs.to(DEV), w.to(DEV), b.to(DEV), True, True, True)
+    logits = hs @ w.t() + b
+    assert (logp.cpu() - F.log_softmax(logits, dim=-1)).abs().max() < 2e-5
+    assert (prob.cpu() - F.softmax(logits, dim=-1)).abs().max() < 2e-6
+    assert torch.equal(amax.cpu(), logits.argmax(-1))
+
+
+@pytest.mark.parametrize("B,T,V,Lmax", [(8, 249, 41, 100), (4, 50, 37, 30), (3, 20, 5, 12),
+                                        (2, 300, 41, 140), (2, 600, 41, 300)])
+def test_ctc_loss_and_grad(B, T, V, Lmax):
+    ops = _ops()
+    g = torch.Generator().manual_seed(B + T)
+    logits = torch.randn(B, T, V, generator=g)
+    targets = torch.randint(1, V, (B, Lmax), generator=g)
+    # make repeats likely
+    targets[:, 1::3] = targets[:, 0::3][:, : targets[:, 1::3].shape[1]]
+    tlens = torch.randint(1, Lmax + 1, (B,), generator=g)
+    tlens[0] = Lmax
+    hlens = torch.randint(T // 2, T + 1, (B,), generator=g)
+    hlens[0] = T
+    if B > 2:
+        hlens[2] = 3  # infeasible when the target is long
+        tlens[2] = Lmax
+    logits_ref = logits.clone().double().requires_grad_(True)
+    lp_ref = logits_ref.log_softmax(-1)
+    flat = torch.cat([targets[i, : tlens[i]] for i in range(B)])
+    loss_ref = F.ctc_loss(lp_ref.transpose(0, 1), flat, hlens, tlens, blank=0, reduction="none",
+                          zero_infinity=True)
+    (loss_ref.sum() / B).backward()
+    logp = F.log_softmax(logits, dim=-1).to(DEV)
+    pad = targets.clone()
+    for i in range(B):
+        pad[i, tlens[i]:] = -1
+    nll, grad = ops.ctc_loss(logp, pad.to(DEV), hlens.int().to(DEV), tlens.int().to(DEV),
+                             want_grad=True, gscale=1.0 / B)
+    assert torch.allclose(nll.cpu().double(), loss_ref.detach(), rtol=1e-5, atol=1e-4), (nll, loss_ref)
+    gref = logits_ref.grad
+    assert (grad.cpu().double() - gref).abs().max() < 1e-5 * max(1.0, float(gref.abs().max()))
+    nll2, _ = ops.ctc_loss(logp, pad.to(DEV), hlens.int().to(DEV), tlens.int().to(DEV))
+    assert torch.equal(nll2, nll)
+
+
+def test_ctc_greedy():
+    ops = _ops()
+    g = torch.Generator().manual_seed(0)
+    B, T = 5, 97
+    am = torch.randint(0, 4, (B, T), generator=g)
+    lens = torch.tensor([97, 50, 1, 0, 96], dtype=torch.int32)
+    for use_lens in (True, False):
+        toks, n = ops.ctc_greedy(am.to(DEV), lens.to(DEV) if use_lens else None)
+        for b in range(B):
+            L = int(lens[b]) if use_lens else T
+            seq = am[b, :L].tolist()
+            ref = [x for i, x in enumerate(seq) if x != 0 and (i == 0 or seq[i - 1] != x)]
+            assert int(n[b]) == len(ref)
+            assert toks[b, : len(ref)].tolist() == ref
+            assert (toks[b, len(ref):] == -1).all()
