@@ -1,0 +1,104 @@
+"""TEST INFRASTRUCTURE: the parity cases shared by oracle/gen_golden.py (which runs the REAL
+reference on them), tests/test_oracle_cpu.py (oracle vs golden) and tests/test_parity_gpu.py
+(CUDA path vs oracle and vs golden).  Every input and weight is regenerated from seeds
+(oracle/synth.py), only the reference OUTPUTS are stored under tests/golden/."""
+from __future__ import annotations
+
+import copy
+
+import torch
+
+from . import synth
+
+BASE_ENC = dict(
+    output_size=256, attention_heads=4, linear_units=2048, num_blocks=12, cgmlp_linear_units=2048,
+    cgmlp_conv_kernel=31, dropout_rate=0.1, positional_dropout_rate=0.1, attention_dropout_rate=0.1,
+    attn_branch_drop_rate=0.0, input_layer="conv2d", rel_pos_type="latest",
+    pos_enc_layer_type="rel_pos", attention_layer_type="rel_selfattn",
+    positionwise_layer_type="linear", ffn_activation_type="swish", merge_method="learned_ave",
+    use_attn=True, use_cgmlp=True, macaron=True)
+
+BASE_TAILORED = dict(
+    output_size=256, attention_heads=4, linear_units=2048, num_blocks=12, dropout_rate=0.1,
+    positional_dropout_rate=0.1, attention_dropout_rate=0.1, acoustic_branch_drop_rate=0.0,
+    attention_layer_type="rel_selfattn", positionwise_layer_type="linear",
+    ffn_activation_type="swish", cgmlp_linear_units=2048, cgmlp_conv_kernel=31,
+    acoustic_use_attn=[False, True, True, True, False, True, False, True, False, True, True, True],
+    visual_use_attn=[True, True, True, True, False, True, True, True, True, True, True, True],
+    macaron=True, interctc_use_conditioning=False, audiovisual_interctc_conditioning=False)
+
+
+def _enc(**kw):
+    c = copy.deepcopy(BASE_ENC)
+    c.update(kw)
+    return c
+
+
+# kind: "single" (MyBranchformerEncoder), "tailored", "conventional"
+CASES = {
+    # ASR-style conv2d front, learned_ave, ragged lengths (configs/ASR/branchformer_...english.yaml)
+    "asr_small": dict(kind="single", input_size=80, cfg=_enc(num_blocks=3), B=3, Tin=203,
+                      lens=[203, 150, 77], vocab=41, Lmax=12, seed=11),
+    # VSR-style linear front (configs/VSR/conv3dresnet18_branchformer_...english.yaml, post-frontend)
+    "vsr_small": dict(kind="single", input_size=512, cfg=_enc(num_blocks=2, input_layer="linear"),
+                      B=2, Tin=70, lens=[70, 41], vocab=41, Lmax=20, seed=12),
+    # tailored ASR: fixed_ave with pruned branches (configs/ASR/..._tailored.yaml:58-59)
+    "asr_tailored_small": dict(kind="single", input_size=80,
+                               cfg=_enc(num_blocks=3, merge_method="fixed_ave",
+                                        cgmlp_weight=[1.0, 0.0, 0.0]),
+                               B=2, Tin=163, lens=[163, 99], vocab=37, Lmax=10, seed=13),
+    # dormant merges: concat, two-branch fixed_ave
+    "concat_small": dict(kind="single", input_size=512,
+                         cfg=_enc(num_blocks=2, input_layer="linear", merge_method="concat"),
+                         B=2, Tin=50, lens=[50, 33], vocab=41, Lmax=8, seed=14),
+    "fixed_ave_small": dict(kind="single", input_size=512,
+                            cfg=_enc(num_blocks=2, input_layer="linear", merge_method="fixed_ave",
+                                     cgmlp_weight=0.3),
+                            B=2, Tin=50, lens=[50, 20], vocab=41, Lmax=8, seed=15),
+    # unified tailored AV encoder (configs/AVSR/tailored_transformer+ctc_spanish.yaml:79-80 pattern)
+    "av_tailored_small": dict(kind="tailored",
+                              cfg=dict(BASE_TAILORED, num_blocks=3,
+                                       acoustic_use_attn=[False, True, True],
+                                       visual_use_attn=[True, False, True]),
+                              B=2, T=60, lens=[60, 37], vocab=37, Lmax=15, seed=16),
+    # conventional AV encoder: two independent stacks (configs/AVSR/conventional_...spanish.yaml)
+    "av_conventional_small": dict(kind="conventional", cfg=_enc(num_blocks=2, input_layer=None),
+                                  B=2, T=48, lens=[48, 31], vocab=37, Lmax=12, seed=17),
+    # full-depth C1: 12 layers, B=8 x 10 s
+    "asr_c1": dict(kind="single", input_size=80, cfg=_enc(), B=8, Tin=1001, lens=[1001] * 8,
+                   vocab=41, Lmax=100, seed=1, stride_t=8, stride_d=4),
+    # full-depth ragged VSR-like (C2/C4 flavour): padded variable-length batch, garbage in the pad
+    "vsr_ragged12": dict(kind="single", input_size=512, cfg=_enc(input_layer="linear"), B=4, Tin=120,
+                         lens=[120, 95, 64, 48], vocab=41, Lmax=30, seed=18, stride_t=4, stride_d=4),
+}
+
+
+def make_inputs(name: str):
+    """Seeded inputs of a case: dict of tensors (CPU fp32)."""
+    c = CASES[name]
+    s = c["seed"]
+    out = {}
+    lens = torch.tensor(c["lens"], dtype=torch.int64)
+    out["lens"] = lens
+    if c["kind"] == "single":
+        out["x"] = synth.randn((c["B"], c["Tin"], c["input_size"]), s)
+    else:
+        # block inputs post-embed, pre-pos-enc scaling is already applied by the model's
+        # apply_pos_enc (avsr_espnet_model.py:447-448): x * sqrt(d); AV alignment pads with -1
+        d = c["cfg"]["output_size"]
+        a = synth.randn((c["B"], c["T"], d), s) * 4.0
+        v = synth.randn((c["B"], c["T"], d), s + 1000) * 4.0
+        for b, l in enumerate(c["lens"]):
+            v[b, l:] = -1.0 * (d ** 0.5)
+        out["audio"], out["video"] = a, v
+    out["ys_pad"] = synth.rand_targets(c["B"], c["Lmax"], c["vocab"], s + 1)
+    return out
+
+
+def target_lens(name: str, olens: torch.Tensor) -> torch.Tensor:
+    """Target lengths: ~olens/3 clipped to Lmax; the LAST utterance gets Lmax (often infeasible for
+    short inputs -> exercises zero_infinity)."""
+    c = CASES[name]
+    tl = (olens.long() // 3).clamp(1, c["Lmax"])
+    tl[-1] = c["Lmax"]
+    return tl

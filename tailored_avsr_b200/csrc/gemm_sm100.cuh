@@ -84,7 +84,7 @@ struct GemmCfg {
 
 __device__ __forceinline__ float apply_act(float x, int act) {
   switch (act) {
-    case ACT_SWISH: return x / (1.0f + __expf(-x));
+    case ACT_SWISH: return __fdividef(x, 1.0f + __expf(-x));
     case ACT_GELU: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
     case ACT_RELU: return fmaxf(x, 0.0f);
     default: return x;

@@ -46,7 +46,7 @@ inline int set_error(int code, const char* fmt, ...) {
 // Returns 0 on success.
 int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, bool is_bf16, uint64_t rows,
                  uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols,
-                 bool l2_promote_256 = true);
+                 bool is_load = true);
 
 int num_sms();
 

@@ -1,0 +1,118 @@
+"""B200 drop-in for the reference `CTC` module (src/ctc/ctc.py:8-188): same constructor, `ctc_lo`
+parameter names, `forward/softmax/log_softmax/argmax` and the `reduce` attribute; the head, the
+log-domain forward-backward recursion and the greedy decode run as CUDA kernels."""
+from __future__ import annotations
+
+import logging
+from typing import List, Optional
+
+import torch
+import torch.nn.functional as F
+
+from .. import ops
+
+
+class _CTCLossFn(torch.autograd.Function):
+    """loss_b = nll_b; backward uses the gradient w.r.t. the LOGITS produced by the same kernel
+    launch (softmax - occupancy), chained through ctc_lo by autograd."""
+
+    @staticmethod
+    def forward(ctx, logits, logp, targets, hlens, tlens, zero_infinity):
+        want_grad = logits.requires_grad
+        nll, grad = ops.ctc_loss(logp, targets, hlens, tlens, want_grad=want_grad, gscale=1.0,
+                                 zero_infinity=zero_infinity)
+        if want_grad:
+            ctx.save_for_backward(grad)
+        return nll
+
+    @staticmethod
+    def backward(ctx, gout):
+        (grad,) = ctx.saved_tensors
+        return grad * gout.view(-1, 1, 1), None, None, None, None, None
+
+
+class CTC(torch.nn.Module):
+    """CTC module (B200 path).
+
+    Args (ctc.py:21-30): odim, encoder_output_size, dropout_rate, ctc_type ("builtin"), reduce,
+    ignore_nan_grad, zero_infinity.
+    """
+
+    def __init__(self, odim: int, encoder_output_size: int, dropout_rate: float = 0.0,
+                 ctc_type: str = "builtin", reduce: bool = True, ignore_nan_grad: bool = None,
+                 zero_infinity: bool = True):
+        super().__init__()
+        eprojs = encoder_output_size
+        self.dropout_rate = dropout_rate
+        self.ctc_lo = torch.nn.Linear(eprojs, odim)
+        self.ctc_type = ctc_type
+        if ignore_nan_grad is not None:
+            zero_infinity = ignore_nan_grad
+        if self.ctc_type == "builtin":
+            self.zero_infinity = bool(zero_infinity)
+        elif self.ctc_type in ("builtin2", "gtnctc"):
+            raise NotImplementedError(f'ctc_type="{self.ctc_type}" is not built on the B200 path '
+                                      '(every shipped config uses "builtin")')
+        else:
+            raise ValueError(f'ctc_type must be "builtin" or "gtnctc": {self.ctc_type}')
+        self.reduce = reduce
+        if odim > 64:
+            logging.warning("tailored_avsr_b200.CTC: the CUDA head is built for vocabularies <= 64 "
+                            "(char-level EN 41 / ES 37); odim=%d will raise at run time", odim)
+
+    # ---------------------------------------------------------------------------------------
+    def _head(self, hs_pad: torch.Tensor, logp=False, prob=False, amax=False):
+        if not hs_pad.is_cuda:
+            raise RuntimeError("tailored_avsr_b200.CTC runs on CUDA tensors only (no CPU fallback)")
+        B, T, D = hs_pad.shape
+        hs2 = hs_pad.reshape(B * T, D).contiguous().float()
+        return ops.ctc_head(hs2, self.ctc_lo.weight, self.ctc_lo.bias, logp, prob, amax), B, T
+
+    def forward(self, hs_pad, hlens, ys_pad, ys_lens):
+        """CTC loss (ctc.py:133-158): sum_b nll_b / B, or the vector nll_b / B if not self.reduce.
+
+        The reference applies F.dropout with the functional default training=True even in eval
+        (ctc.py:143); that call is kept on the host side so the RNG stream is the reference's.
+        """
+        hs = F.dropout(hs_pad, p=self.dropout_rate) if self.dropout_rate > 0 else hs_pad
+        B, T, _ = hs.shape
+        dev = hs.device
+        targets = ys_pad.to(dev).long().contiguous()
+        hl = hlens.to(dev).to(torch.int32)
+        tl = ys_lens.to(dev).to(torch.int32)
+        needs_grad = torch.is_grad_enabled() and (hs.requires_grad or self.ctc_lo.weight.requires_grad)
+        if needs_grad:
+            # training: logits through autograd (ctc_lo), loss + d/dlogits from the CUDA kernel
+            logits = self.ctc_lo(hs)
+            logp = torch.log_softmax(logits.detach(), dim=2).contiguous()
+            nll = _CTCLossFn.apply(logits, logp, targets, hl, tl, self.zero_infinity)
+        else:
+            (logp, _, _), _, _ = self._head(hs, logp=True)
+            nll, _ = ops.ctc_loss(logp.view(B, T, -1), targets, hl, tl, zero_infinity=self.zero_infinity)
+        loss = nll.sum() / B if self.reduce else nll / B
+        return loss.to(device=hs_pad.device, dtype=hs_pad.dtype)
+
+    def softmax(self, hs_pad):
+        (_, prob, _), B, T = self._head(hs_pad, prob=True)
+        return prob.view(B, T, -1)
+
+    def log_softmax(self, hs_pad):
+        (logp, _, _), B, T = self._head(hs_pad, logp=True)
+        return logp.view(B, T, -1)
+
+    def argmax(self, hs_pad):
+        (_, _, amax), B, T = self._head(hs_pad, amax=True)
+        return amax.view(B, T)
+
+    # ---- extras of the B200 path (device-side replacement of the host groupby loops) ----
+    def greedy(self, hs_pad, hlens: Optional[torch.Tensor] = None, blank: int = 0):
+        """argmax -> collapse repeats -> drop blank on the device (espnet_model.py:590-592,
+        maskctc_model.py:287-291).  Returns (tokens (B,T) padded with -1, ntok (B,))."""
+        amax = self.argmax(hs_pad)
+        lens = None if hlens is None else hlens.to(hs_pad.device).to(torch.int32)
+        return ops.ctc_greedy(amax, lens, blank)
+
+    def greedy_lists(self, hs_pad, hlens=None, blank: int = 0) -> List[List[int]]:
+        tokens, ntok = self.greedy(hs_pad, hlens, blank)
+        tokens, ntok = tokens.cpu(), ntok.cpu()
+        return [tokens[b, : int(ntok[b])].tolist() for b in range(tokens.shape[0])]

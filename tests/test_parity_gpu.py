@@ -1,0 +1,166 @@
+"""Parity of the CUDA drop-in (through the C ABI) against the CPU oracle on the same seeded inputs
+and against the golden vectors of the real reference (tests/golden, oracle/gen_golden.py).
+
+Tolerances (BASELINE.json north_star), tf32 mode = fp32 storage, TF32 tensor-core
+operands, fp32 accumulate:
+  * encoder outputs: max|y-ref|/max|ref| <= 1e-3 and ||y-ref||_F/||ref||_F <= 1e-3 over valid frames
+  * CTC loss given identical hs_pad: relative error <= 1e-4
+  * greedy CTC token sequences given identical hs_pad: exact
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases
+
+from . import _util
+
+pytestmark = pytest.mark.gpu
+ENC_TOL = 1e-3
+DEV = "cuda"
+
+
+def _run_dropin(name, enc):
+    c = cases.CASES[name]
+    inp = cases.make_inputs(name)
+    with torch.no_grad():
+        if c["kind"] == "single":
+            y, olens, _ = enc(inp["x"].to(DEV), inp["lens"].to(DEV))
+            return {"out": y, "olens": olens}
+        from oracle import ref_path
+        d, T = c["cfg"]["output_size"], c["T"]
+        pos = ref_path.rel_pos_emb(T, d).to(DEV)
+        mask = ref_path.make_valid_mask(inp["lens"], T).to(DEV)
+        ya, _, yv, _, _ = enc((inp["audio"].to(DEV), pos), mask, (inp["video"].to(DEV), pos), mask)
+        return {"out": ya, "out_video": yv, "olens": inp["lens"]}
+
+
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_encoder_parity_vs_oracle_and_golden(name):
+    enc, ctc, sd = _util.build_dropin(name)
+    res = _util.run_oracle(name, sd)
+    enc = enc.to(DEV)
+    got = _run_dropin(name, enc)
+    torch.cuda.synchronize()
+    assert torch.equal(got["olens"].cpu().long(), res["olens"].long())
+    lens = res["olens"]
+    for key in ("out", "out_video"):
+        if key in res:
+            mx, fro = _util.rel_errors(got[key], res[key], lens)
+            print(f"{name}:{key}: max-rel {mx:.3e} fro {fro:.3e}")
+            assert mx <= ENC_TOL and fro <= ENC_TOL, (name, key, mx, fro)
+    # golden vectors of the real reference (strided for the 12-layer cases)
+    gold = _util.load_golden(name)
+    c = cases.CASES[name]
+    st, sdd = c.get("stride_t", 1), c.get("stride_d", 1)
+    g = torch.from_numpy(gold["out"])
+    mine = got["out"].cpu()[:, ::st, ::sdd]
+    glens = (lens + st - 1) // st
+    mx, fro = _util.rel_errors(mine, g, glens)
+    assert mx <= 2 * ENC_TOL and fro <= ENC_TOL, (name, "golden", mx, fro)
+    # learned_ave merge weights published on the layers (study_branches.py:44-45)
+    if c["kind"] == "single" and c["cfg"]["merge_method"] == "learned_ave":
+        wg = torch.stack([l.weight_global.flatten().cpu() for l in enc.encoders])
+        assert wg.shape == tuple(gold["weight_global"].shape)
+        assert np.allclose(wg.numpy(), gold["weight_global"], atol=2e-3)
+
+
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_ctc_parity_given_identical_hs(name):
+    _, ctc, sd = _util.build_dropin(name)
+    res = _util.run_oracle(name, sd)
+    gold = _util.load_golden(name)
+    ctc = ctc.to(DEV)
+    hs = res["out"].to(DEV)
+    inp = res["inputs"]
+    with torch.no_grad():
+        loss = ctc(hs, res["olens"].to(DEV), inp["ys_pad"].to(DEV), res["tlens"].to(DEV))
+        ctc.reduce = False
+        loss_vec = ctc(hs, res["olens"].to(DEV), inp["ys_pad"].to(DEV), res["tlens"].to(DEV))
+        ctc.reduce = True
+        amax = ctc.argmax(hs)
+        logp = ctc.log_softmax(hs)
+        prob = ctc.softmax(hs)
+        toks = ctc.greedy_lists(hs)
+        toks_len = ctc.greedy_lists(hs, res["olens"])
+    want = float(res["ctc_loss"])
+    assert abs(float(loss) - want) <= 1e-4 * abs(want), (float(loss), want)
+    assert abs(float(loss) - float(gold["ctc_loss"])) <= 1e-4 * abs(float(gold["ctc_loss"]))
+    assert torch.allclose(loss_vec.cpu(), res["ctc_loss_vec"], rtol=1e-4, atol=1e-5)
+    assert torch.equal(amax.cpu(), res["argmax"])
+    assert np.array_equal(amax.cpu().numpy().astype(np.int16), gold["argmax"])
+    from oracle import ref_path
+    ref_lp = ref_path.ctc_log_softmax(res["out"], sd, "ctc.ctc_lo")
+    assert (logp.cpu() - ref_lp).abs().max() < 2e-5
+    assert (prob.cpu() - ref_lp.exp()).abs().max() < 2e-6
+    assert toks == ref_path.ctc_greedy(res["out"], sd, "ctc.ctc_lo")
+    assert toks_len == ref_path.ctc_greedy(res["out"], sd, "ctc.ctc_lo", lens=res["olens"])
+
+
+def test_ctc_training_gradients_match_torch():
+    """d loss / d hs and d loss / d ctc_lo.{weight,bias} through the CUDA loss kernel."""
+    from oracle import ref_path
+    _, ctc, sd = _util.build_dropin("asr_small")
+    res = _util.run_oracle("asr_small", sd)
+    inp = res["inputs"]
+    ctc = ctc.to(DEV).train()
+    hs = res["out"].to(DEV).requires_grad_(True)
+    loss = ctc(hs, res["olens"].to(DEV), inp["ys_pad"].to(DEV), res["tlens"].to(DEV))
+    loss.backward()
+    hs_ref = res["out"].clone().double().requires_grad_(True)
+    sd64 = {k: v.double().requires_grad_(True) for k, v in sd.items() if k.startswith("ctc.")}
+    ref = ref_path.ctc_loss(hs_ref, res["olens"], inp["ys_pad"], res["tlens"], sd64, "ctc.ctc_lo")
+    ref.backward()
+    assert abs(float(loss) - float(ref)) <= 1e-4 * abs(float(ref))
+    for mine, want in ((hs.grad, hs_ref.grad), (ctc.ctc_lo.weight.grad, sd64["ctc.ctc_lo.weight"].grad),
+                       (ctc.ctc_lo.bias.grad, sd64["ctc.ctc_lo.bias"].grad)):
+        err = (mine.cpu().double() - want).abs().max() / want.abs().max()
+        assert err < 2e-3, float(err)
+
+
+def test_prefix_score_matches_oracle():
+    from oracle import ref_path
+    from tailored_avsr_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    T, V, eos = 40, 41, 40
+    lp = torch.randn(T, V, generator=g).log_softmax(-1)
+    lp64 = lp.double().numpy()
+    r0 = ref_path.ctc_prefix_init(lp64)
+    # three hypotheses: empty, [5], [5, 5] (repeated label), states walked with the oracle
+    r1, _ = ref_path.ctc_prefix_score(lp64, r0, [], 0, eos)
+    r2, _ = ref_path.ctc_prefix_score(lp64, r1[5], [5], 0, eos)
+    hyps = [([], r0), ([5], r1[5]), ([5, 5], r2[5])]
+    r_prev = torch.tensor(np.stack([h[1] for h in hyps]), dtype=torch.float32).to(DEV)
+    last = torch.tensor([-1, 5, 5], dtype=torch.int32).to(DEV)
+    plen = torch.tensor([0, 1, 2], dtype=torch.int32).to(DEV)
+    psi_prev = torch.zeros(3).to(DEV)
+    r_new, score = ops.ctc_prefix_score(lp.to(DEV), r_prev, last, plen, psi_prev, T, 0, eos)
+    for i, (prefix, r) in enumerate(hyps):
+        want_r, want_psi = ref_path.ctc_prefix_score(lp64, r, prefix, 0, eos)
+        got = score[i].cpu().double().numpy()
+        ok = want_psi > -1e9
+        assert np.allclose(got[ok], want_psi[ok], rtol=1e-4, atol=1e-3), (i, got, want_psi)
+        assert (got[~ok] < -1e9).all()
+        got_r = r_new[i].cpu().double().numpy().transpose(1, 0, 2)  # (V,T,2)
+        live = want_r > -1e9
+        assert np.allclose(got_r[live], want_r[live], rtol=1e-4, atol=1e-3)
+
+
+def test_layer_module_standalone_matches_oracle():
+    """MyBranchformerEncoderLayer called on its own with (x, pos_emb), mask like MultiSequential
+    does (encoder.py:376)."""
+    from oracle import ref_path
+    enc, _, sd = _util.build_dropin("concat_small")
+    layer = enc.encoders[1].to(DEV)
+    B, T, d = 2, 45, 256
+    from oracle import synth
+    x = synth.randn((B, T, d), 99)
+    lens = torch.tensor([45, 20])
+    pos = ref_path.rel_pos_emb(T, d)
+    mask = ref_path.make_valid_mask(lens, T)
+    with torch.no_grad():
+        (y, pos_out), mask_out = layer((x.to(DEV), pos.to(DEV)), mask.to(DEV))
+        want, _ = ref_path.branchformer_layer(x, pos, mask, sd, "encoders.1", merge_method="concat")
+    mx, fro = _util.rel_errors(y, want, lens)
+    assert mx <= ENC_TOL and fro <= ENC_TOL, (mx, fro)
+    assert pos_out.shape == (1, 2 * T - 1, d) and mask_out.shape == (B, 1, T)
