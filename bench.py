@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""bench.py — Branchformer encoder + CTC valid frames/s on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (config.workload = "C2"): BASELINE.json configs[1] / SURVEY.md §8d C2 — VSR video-only
+Branchformer (input_layer=linear, 12 two-branch learned_ave blocks, d=256, 4 heads, FFN 2048, cgMLP
+2048, k=31) + CTC (V=41): post-frontend features (32, 250, 512) per GPU, targets (32, 100).
+One step = encoder forward + CTC loss + greedy CTC decode of one batch (a validation step of the
+reference: src/models/espnet_model.py:397-402,578-593).  Synthetic inputs, seeded default-init-like
+weights (oracle/synth.py).
+
+value      = valid frames / s, inputs resident in HBM, CUDA-graph replay, CUDA-event timed per
+             step with an L2 flush (256 MB memset) between steps, summed over K steps, max over ranks.
+e2e        = same metric through EncoderCTCPipeline.run() with pinned HOST inputs: H2D copies of
+             features / lengths / targets and D2H of loss + greedy tokens inside the timed region.
+roofline   = dominant kernel group of the step (CUDA events around every op of one eager step).
+cpu_baseline / --impl reference = the CPU oracle port (oracle/ref_path.py; the reference's own
+             modules cannot travel to the GPU box: espnet is not installable) on the
+             host cores with all threads, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(name="C2", B=32, T=250, feat=512, vocab=41, Lmax=100, layers=12)
+METRIC = "branchformer_encoder_ctc_valid_frames_per_sec"
+UNIT = "frames/s"
+
+
+def enc_cfg():
+    from oracle import cases
+    return dict(cases.BASE_ENC, input_layer="linear")
+
+
+def make_batch(rank: int):
+    from oracle import synth
+    w = WORKLOAD
+    feats = synth.randn((w["B"], w["T"], w["feat"]), 3 + 100 * rank)
+    lens = torch.full((w["B"],), w["T"], dtype=torch.int64)
+    ys = synth.rand_targets(w["B"], w["Lmax"], w["vocab"], 4 + 100 * rank)
+    ylens = torch.full((w["B"],), w["Lmax"], dtype=torch.int64)
+    return feats, lens, ys, ylens
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return p, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.gpu)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                      "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:  # noqa: BLE001
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# --------------------------------------------------------------------------------------------------
+def cpu_oracle_arm(steps: int, warmup: int, sample_B: int):
+    """Times the CPU oracle port on `sample_B` utterances of the workload per step."""
+    from oracle import ref_path, synth
+    from tailored_avsr_b200.ctc.ctc import CTC
+    from tailored_avsr_b200.encoder.branchformer.encoder import MyBranchformerEncoder
+    w = WORKLOAD
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = enc_cfg()
+    enc = MyBranchformerEncoder(input_size=w["feat"], **cfg)  # parameter container only (CPU)
+    ctc = CTC(odim=w["vocab"], encoder_output_size=256)
+    sd = synth.fill_module(enc, seed=0)
+    sd.update(synth.fill_module(ctc, seed=0, prefix="ctc."))
+    feats, lens, ys, ylens = make_batch(0)
+    feats, lens, ys, ylens = feats[:sample_B], lens[:sample_B], ys[:sample_B], ylens[:sample_B]
+
+    def step():
+        with torch.no_grad():
+            out, olens, _ = ref_path.branchformer_encoder(feats, lens, sd, cfg)
+            loss = ref_path.ctc_loss(out, olens, ys, ylens, sd, "ctc.ctc_lo")
+            toks = ref_path.ctc_greedy(out, sd, "ctc.ctc_lo")
+        return float(loss), toks, int(olens.sum())
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    frames = 0
+    for _ in range(steps):
+        frames += step()[2]
+    dt = time.perf_counter() - t0
+    return frames / dt, dt / steps * 1e3, torch.get_num_threads()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sample_B = 8
+    steps = max(1, min(args.steps, 10))
+    warm = max(1, min(args.warmup, 2))
+    fps, ms, cores = cpu_oracle_arm(steps, warm, sample_B)
+    sample = (f"{sample_B} of the {WORKLOAD['B']} utterances of the C2 batch per step "
+              f"({sample_B}x{WORKLOAD['T']} frames), {steps} steps after {warm} warm-up, fp32, "
+              f"torch {torch.__version__} with {cores} threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2", "batch": sample_B, "T": WORKLOAD["T"], "feat": WORKLOAD["feat"],
+                   "layers": 12, "note": "CPU oracle port of the reference path (espnet not "
+                                         "installable: reference modules cannot run on the box)"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------
+def op_cost(name, shapes, extra):
+    """(algorithmic flops, algorithmic bytes) of one op call from its tensor shapes."""
+    if name == "gemm_bias_act":
+        (M, K), (N, _) = shapes[0], shapes[1]
+        return 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N)
+    if name == "gemm_rowln":
+        (M, K), (N, _) = shapes[0], shapes[1]
+        dual = 2 if "x2" in extra else 1
+        outs = 1 + ("lnA" in extra) + ("lnB" in extra) + ("residual" in extra)
+        return 2.0 * M * N * K * dual, 4.0 * (dual * M * K + N * K + outs * M * N)
+    if name == "relpos_attn":
+        M, C = shapes[0]
+        T = (shapes[1][0] + 1) // 2
+        d = C // 3
+        return 2.0 * 3 * T * d * M, 4.0 * (M * C + M * d)
+    if name == "csgu":
+        M, C = shapes[0]
+        return 2.0 * M * (C // 2) * 31, 4.0 * (M * C + M * C // 2)
+    if name == "layernorm":
+        M, D = shapes[0]
+        return 8.0 * M * D, 8.0 * M * D
+    if name == "ctc_head":
+        M, D = shapes[0]
+        V = shapes[1][0]
+        return 2.0 * M * D * V, 4.0 * (M * D + M * V)
+    return 0.0, 0.0
+
+
+def profile_step(pipe, batch_dev, peaks):
+    """One eager step with CUDA events around every op: per-op-group time shares + roofline of the
+    dominant group."""
+    from tailored_avsr_b200 import ops
+    recs = []
+    torch.cuda.synchronize()
+    ops.set_profiler(recs)
+    try:
+        with torch.no_grad():
+            pipe._step(*batch_dev)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_profiler(None)
+    groups = {}
+    total = 0.0
+    for name, shapes, extra, e0, e1 in recs:
+        ms = e0.elapsed_time(e1)
+        key = f"{name}{list(shapes[:2])}" + ("+dual" if "x2" in extra else "")
+        fl, by = op_cost(name, shapes, extra)
+        g = groups.setdefault(key, {"ms": 0.0, "n": 0, "flops": fl, "bytes": by, "name": name})
+        g["ms"] += ms
+        g["n"] += 1
+        total += ms
+    top_key = max(groups, key=lambda k: groups[k]["ms"])
+    top = groups[top_key]
+    avg_s = top["ms"] / top["n"] * 1e-3
+    tensor_bound = top["name"] in ("gemm_bias_act", "gemm_rowln", "relpos_attn")
+    if tensor_bound:
+        achieved = top["flops"] / avg_s / 1e12
+        peak = peaks["bf16_tflops"]
+        roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": None,
+                "peak_note": "measured dense bf16 burst (MEASURED_PEAKS.json); the kernel computes in "
+                             "TF32 whose dense peak is half of bf16",
+                "frac_of_tf32_peak": achieved / (peak / 2)}
+    else:
+        achieved = top["bytes"] / avg_s / 1e9
+        peak = peaks["hbm_gbs"]
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None}
+    roof["kernel"] = top_key
+    roof["avg_launch_us"] = avg_s * 1e6
+    roof["share_of_step"] = top["ms"] / total if total > 0 else None
+    shares = {k: round(v["ms"] / total, 4) for k, v in sorted(groups.items(), key=lambda kv: -kv[1]["ms"])}
+    return roof, shares, total
+
+
+def run_gpu_arm(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+
+    from oracle import synth
+    from tailored_avsr_b200 import ops
+    from tailored_avsr_b200.ctc.ctc import CTC
+    from tailored_avsr_b200.encoder.branchformer.encoder import MyBranchformerEncoder
+    from tailored_avsr_b200.pipeline import EncoderCTCPipeline
+
+    w = WORKLOAD
+    peaks, peak_src = load_peaks()
+    enc = MyBranchformerEncoder(input_size=w["feat"], **enc_cfg())
+    ctc = CTC(odim=w["vocab"], encoder_output_size=256, dropout_rate=0.0)
+    synth.fill_module(enc, seed=0)
+    synth.fill_module(ctc, seed=0, prefix="ctc.")
+    enc, ctc = enc.to(dev).eval(), ctc.to(dev).eval()
+    pipe = EncoderCTCPipeline(enc, ctc, use_cuda_graph=not args.no_graph)
+
+    feats, lens, ys, ylens = make_batch(rank)
+    host = [t.pin_memory() for t in (feats, lens, ys, ylens)]
+    batch_dev = [t.to(dev) for t in host]
+    frames_per_step = int(lens.sum())  # linear front end: olens == ilens
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    # ---- warm-up (also captures the CUDA graph) ----
+    for _ in range(max(args.warmup, 3)):
+        res = pipe.run_device(*batch_dev)
+    torch.cuda.synchronize()
+    loss_ref = float(res["loss"])
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    # ---- timed: device-resident ----
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = ops.launch_count()
+    evs = []
+    for _ in range(args.steps):
+        flush.zero_()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if args.no_graph:
+            pipe.run_device(*batch_dev)
+        else:
+            pipe.replay_static()
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    eager_launches = ops.launch_count() - launches0
+
+    # ---- timed: end to end through the public API with host inputs ----
+    barrier()
+    evs = []
+    for _ in range(args.steps):
+        flush.zero_()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = pipe.run(*host)
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    e2e_ms = sum(a.elapsed_time(b) for a, b in evs)
+    clocks = sampler.stop() if rank == 0 else None
+    assert abs(float(out["loss"]) - loss_ref) <= 1e-5 * abs(loss_ref), "e2e loss differs"
+
+    # kernels per step: count them on one eager (non-graph) step
+    l0 = ops.launch_count()
+    with torch.no_grad():
+        pipe._step(*batch_dev)
+    torch.cuda.synchronize()
+    launches_per_step = ops.launch_count() - l0
+    del eager_launches
+
+    t = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    total_frames = frames_per_step * args.steps * world
+
+    line = None
+    if rank == 0:
+        roof, shares, prof_total_ms = profile_step(pipe, batch_dev, peaks)
+        roof["peak_source"] = peak_src
+        sample_B = 8
+        fps_cpu, ms_cpu, cores = cpu_oracle_arm(2, 1, sample_B) if world == 1 and not args.no_cpu else (None, None, None)
+        h2d = sum(t_.numel() * t_.element_size() for t_ in host)
+        d2h = 4 + w["B"] * w["T"] * 8 + w["B"] * 4
+        flops_per_frame = 2.0 * 12 * (3243008 + 768 * w["T"])
+        value = total_frames / (dev_ms * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
+            "data": "synthetic",
+            "config": {"workload": "C2", "batch_per_gpu": w["B"], "T": w["T"], "feat": w["feat"],
+                       "layers": 12, "vocab": w["vocab"], "target_len": w["Lmax"],
+                       "step": "encoder fwd + CTC loss + greedy decode",
+                       "cuda_graph": not args.no_graph,
+                       "l2": "256 MB memset between steps (outside the per-step event pairs)",
+                       "timing": "CUDA events per step, summed over steps, max over ranks",
+                       "parallelism": f"dp{world} (utterance-sharded, no data-path collective)"},
+            "clocks": clocks,
+            "e2e": {"value": total_frames / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches_per_step": launches_per_step,
+            "roofline": roof,
+            "kernel_time_shares": shares,
+            "eager_step_kernel_ms": prof_total_ms,
+            "model_tflops": value * flops_per_frame / 1e12,
+            "model_frac_of_bf16_sustained": value * flops_per_frame / 1e12 / peaks["bf16_tflops_sustained"],
+            "loss": loss_ref,
+        }
+        if fps_cpu is not None:
+            line["cpu_baseline"] = {
+                "value": fps_cpu, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"{sample_B} of the {w['B']} utterances per step, 2 steps after 1 warm-up "
+                          f"({ms_cpu:.0f} ms/step), fp32 oracle port, torch {torch.__version__}"}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of graph replay")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback); "
+                         "use --impl reference for the CPU arm")
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -67,6 +67,10 @@ CASES = {
     # full-depth C1: 12 layers, B=8 x 10 s
     "asr_c1": dict(kind="single", input_size=80, cfg=_enc(), B=8, Tin=1001, lens=[1001] * 8,
                    vocab=41, Lmax=100, seed=1, stride_t=8, stride_d=4),
+    # TF32 error-growth stress: same C1 shape at reduced batch, "hot" N(0,1/fan_in) weights (1.7x
+    # larger branch outputs than default init); parity tolerance stated separately (3e-3)
+    "asr_c1_hot": dict(kind="single", input_size=80, cfg=_enc(), B=2, Tin=1001, lens=[1001, 801],
+                       vocab=41, Lmax=100, seed=2, stride_t=8, stride_d=4, hot=True, enc_tol=3e-3),
     # full-depth ragged VSR-like (C2/C4 flavour): padded variable-length batch, garbage in the pad
     "vsr_ragged12": dict(kind="single", input_size=512, cfg=_enc(input_layer="linear"), B=4, Tin=120,
                          lens=[120, 95, 64, 48], vocab=41, Lmax=30, seed=18, stride_t=4, stride_d=4),

@@ -37,8 +37,8 @@ def build_reference(ref, name):
                   ctc_type="builtin", reduce=True)
     enc.eval()
     ctc.eval()
-    synth.fill_module(enc, seed=c["seed"])
-    synth.fill_module(ctc, seed=c["seed"], prefix="ctc.")
+    synth.fill_module(enc, seed=c["seed"], hot=c.get("hot", False))
+    synth.fill_module(ctc, seed=c["seed"], prefix="ctc.", hot=c.get("hot", False))
     return enc, ctc
 
 

@@ -22,6 +22,37 @@ __all__ = [
 ]
 
 
+_PROFILE = None  # list collecting (op name, arg shapes, start event, end event) when profiling
+
+
+def set_profiler(records) -> None:
+    """bench.py hook: pass a list to time every op with CUDA events on the launching stream
+    (None switches it off)."""
+    global _PROFILE
+    _PROFILE = records
+
+
+def _profiled(fn):
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        if _PROFILE is None:
+            return fn(*args, **kwargs)
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn(*args, **kwargs)
+        e1.record()
+        shapes = tuple(tuple(a.shape) for a in args if torch.is_tensor(a))
+        extra = {k: (tuple(v.shape) if torch.is_tensor(v) else v) for k, v in kwargs.items()
+                 if k in ("act", "x2", "ln0", "lnA", "lnB", "residual") and v is not None}
+        _PROFILE.append((fn.__name__, shapes, extra, e0, e1))
+        return out
+
+    return wrapper
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -42,6 +73,7 @@ def launch_count() -> int:
     return int(_lib.load().tavsr_launch_count())
 
 
+@_profiled
 def gemm_bias_act(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: int = ACT_NONE,
                   round_out: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out = act(x @ w.T + bias) on the tcgen05 GEMM (tavsr_gemm_bias_act)."""
@@ -59,6 +91,7 @@ def gemm_bias_act(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]
     return out
 
 
+@_profiled
 def gemm_rowln(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
                x2: Optional[torch.Tensor] = None,
                rowscale: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, rows_per_seg: int = 0,
@@ -115,6 +148,7 @@ def gemm_rowln(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = 
     check(_lib.load().tavsr_gemm_rowln(ctypes.byref(a), _stream()), "tavsr_gemm_rowln")
 
 
+@_profiled
 def layernorm(x: torch.Tensor, gA: torch.Tensor, bA: torch.Tensor, eps: float = 1e-12,
               round_out: bool = False, scale: float = 1.0, out: Optional[torch.Tensor] = None,
               gB: Optional[torch.Tensor] = None, bB: Optional[torch.Tensor] = None,
@@ -131,6 +165,7 @@ def layernorm(x: torch.Tensor, gA: torch.Tensor, bA: torch.Tensor, eps: float = 
     return out
 
 
+@_profiled
 def relpos_attn(qkv: torch.Tensor, pos: torch.Tensor, u: torch.Tensor, v: torch.Tensor,
                 lens: Optional[torch.Tensor], B: int, T: int, H: int, round_out: bool = True,
                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -146,6 +181,7 @@ def relpos_attn(qkv: torch.Tensor, pos: torch.Tensor, u: torch.Tensor, v: torch.
     return out
 
 
+@_profiled
 def csgu(h: torch.Tensor, norm_g: torch.Tensor, norm_b: torch.Tensor, conv_w: torch.Tensor,
          conv_b: torch.Tensor, B: int, T: int, eps: float = 1e-12, round_out: bool = True,
          out: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -164,6 +200,7 @@ def csgu(h: torch.Tensor, norm_g: torch.Tensor, norm_b: torch.Tensor, conv_w: to
     return out
 
 
+@_profiled
 def merge_weights(dots1: torch.Tensor, dots2: torch.Tensor, lens: Optional[torch.Tensor],
                   pool_b1: float, pool_b2: float, wproj_b1: float, wproj_b2: float, size: int,
                   B: int, T: int, w1: Optional[torch.Tensor] = None,
@@ -179,6 +216,7 @@ def merge_weights(dots1: torch.Tensor, dots2: torch.Tensor, lens: Optional[torch
     return w1, w2
 
 
+@_profiled
 def ctc_head(hs: torch.Tensor, w: torch.Tensor, b: torch.Tensor, want_logp: bool = True,
              want_prob: bool = False, want_argmax: bool = False):
     """(logp, prob, argmax) of ctc_lo(hs) over the vocabulary, fp32 FMA (tavsr_ctc_head)."""
@@ -194,6 +232,7 @@ def ctc_head(hs: torch.Tensor, w: torch.Tensor, b: torch.Tensor, want_logp: bool
     return logp, prob, amax
 
 
+@_profiled
 def ctc_loss(logp: torch.Tensor, targets: torch.Tensor, hlens: torch.Tensor, tlens: torch.Tensor,
              want_grad: bool = False, gscale: float = 1.0, zero_infinity: bool = True):
     """Per-utterance NLL (and optionally d/dlogits) from (B,T,V) log-probs (tavsr_ctc_loss)."""
@@ -213,6 +252,7 @@ def ctc_loss(logp: torch.Tensor, targets: torch.Tensor, hlens: torch.Tensor, tle
     return nll, grad
 
 
+@_profiled
 def ctc_greedy(amax: torch.Tensor, lens: Optional[torch.Tensor], blank: int = 0):
     B, T = amax.shape
     tokens = torch.empty((B, T), device=amax.device, dtype=torch.int64)
@@ -223,6 +263,7 @@ def ctc_greedy(amax: torch.Tensor, lens: Optional[torch.Tensor], blank: int = 0)
     return tokens, ntok
 
 
+@_profiled
 def ctc_prefix_score(logp: torch.Tensor, r_prev: torch.Tensor, last: torch.Tensor,
                      plen: torch.Tensor, psi_prev: torch.Tensor, Tvalid: int, blank: int, eos: int):
     T, V = logp.shape

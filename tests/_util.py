@@ -33,8 +33,8 @@ def build_dropin(name):
               ctc_type="builtin", reduce=True)
     enc.eval()
     ctc.eval()
-    sd = synth.fill_module(enc, seed=c["seed"])
-    sd.update(synth.fill_module(ctc, seed=c["seed"], prefix="ctc."))
+    sd = synth.fill_module(enc, seed=c["seed"], hot=c.get("hot", False))
+    sd.update(synth.fill_module(ctc, seed=c["seed"], prefix="ctc.", hot=c.get("hot", False)))
     return enc, ctc, sd
 
 

@@ -18,7 +18,6 @@ from oracle import cases, ref_path, reference_loader, synth
 from . import _util
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SMALL = [n for n in cases.CASES if n not in ("asr_c1", "vsr_ragged12")]
 
 
 @pytest.mark.parametrize("name", list(cases.CASES))

@@ -48,7 +48,8 @@ def test_encoder_parity_vs_oracle_and_golden(name):
         if key in res:
             mx, fro = _util.rel_errors(got[key], res[key], lens)
             print(f"{name}:{key}: max-rel {mx:.3e} fro {fro:.3e}")
-            assert mx <= ENC_TOL and fro <= ENC_TOL, (name, key, mx, fro)
+            tol = cases.CASES[name].get("enc_tol", ENC_TOL)
+            assert mx <= tol and fro <= tol, (name, key, mx, fro)
     # golden vectors of the real reference (strided for the 12-layer cases)
     gold = _util.load_golden(name)
     c = cases.CASES[name]
@@ -57,7 +58,7 @@ def test_encoder_parity_vs_oracle_and_golden(name):
     mine = got["out"].cpu()[:, ::st, ::sdd]
     glens = (lens + st - 1) // st
     mx, fro = _util.rel_errors(mine, g, glens)
-    assert mx <= 2 * ENC_TOL and fro <= ENC_TOL, (name, "golden", mx, fro)
+    assert mx <= 2 * tol and fro <= tol, (name, "golden", mx, fro)
     # learned_ave merge weights published on the layers (study_branches.py:44-45)
     if c["kind"] == "single" and c["cfg"]["merge_method"] == "learned_ave":
         wg = torch.stack([l.weight_global.flatten().cpu() for l in enc.encoders])
