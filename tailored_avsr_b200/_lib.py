@@ -95,6 +95,10 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = restype
         fn.argtypes = argtypes
+    # debug knobs, e.g. TAVSR_DEBUG="3=1" forces the 1-CTA GEMM (see gemm_sm100.cu)
+    for kv in filter(None, os.environ.get("TAVSR_DEBUG", "").split(",")):
+        k, v = kv.split("=")
+        lib.tavsr_debug_set(int(k), int(v))
     _lib = lib
     return lib
 

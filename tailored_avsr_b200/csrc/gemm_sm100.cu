@@ -123,22 +123,50 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, bool is_bf16
 // ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
-template <bool kTf32, int kBlockN, int kMode, bool kDual>
+template <bool kTf32, int kBlockN, int kMode, bool kDual, int kCtas, int kAct>
 static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<kTf32, kBlockN, kMode, kDual>;
-  auto kern = gemm_sm100_kernel<kTf32, kBlockN, kMode, kDual>;
+  using Cfg = GemmCfg<kTf32, kBlockN, kMode, kDual, kCtas>;
+  auto kern = gemm_sm100_kernel<kTf32, kBlockN, kMode, kDual, kCtas, kAct>;
   static bool configured = false;
   if (!configured) {
     TAVSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes));
     configured = true;
   }
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(p);
-  TAVSR_CUDA_OK(cudaGetLastError());
+  const int units = p.num_m_tiles * p.num_n_tiles;
+  const int max_units = num_sms() / kCtas;
+  const int grid = (units < max_units ? units : max_units) * kCtas;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(Cfg::kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCtas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  TAVSR_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
+}
+
+// Tiled GEMM dispatch over (tile width, CTA pairing, activation).
+template <int kBlockN, int kCtas>
+static int launch_tiled(const GemmParams& p, cudaStream_t s) {
+  if constexpr (kCtas == 1) {
+    return launch_gemm<true, kBlockN, kModeTiled, false, 1, -1>(p, s);
+  } else {
+  switch (p.act) {
+    case ACT_NONE: return launch_gemm<true, kBlockN, kModeTiled, false, kCtas, ACT_NONE>(p, s);
+    case ACT_SWISH: return launch_gemm<true, kBlockN, kModeTiled, false, kCtas, ACT_SWISH>(p, s);
+    case ACT_GELU: return launch_gemm<true, kBlockN, kModeTiled, false, kCtas, ACT_GELU>(p, s);
+    default: return launch_gemm<true, kBlockN, kModeTiled, false, kCtas, -1>(p, s);
+  }
+  }
 }
 
 }  // namespace tavsr
@@ -164,23 +192,27 @@ extern "C" int tavsr_gemm_bias_act(const void* x, long long ldx, const void* w, 
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K;
   p.bias = bias; p.act = act; p.round_c = round_out;
-  // tile-width heuristic: fewer waves of 148 CTAs wins; ties go to the wider tile
-  const int mt = (M + 127) / 128;
-  const int sms = num_sms();
+  // CTA pairing (cta_group::2): a pair covers 256 rows and shares the B tile, which halves the
+  // per-SM weight traffic and makes room for a deeper pipeline.  g_debug[3] = 1 forces 1-CTA.
+  const int ctas = g_debug[3] == 1 ? 1 : 2;
+  const int rows_per_unit = 128 * ctas;
+  const int mt = (M + rows_per_unit - 1) / rows_per_unit;
+  const int slots = num_sms() / ctas;
+  // tile-width heuristic: fewer waves wins (a 128-wide tile costs about half a 256-wide one)
   const int t256 = mt * ((N + 255) / 256), t128 = mt * ((N + 127) / 128);
-  const double cost256 = static_cast<double>((t256 + sms - 1) / sms) * 2.0;
-  const double cost128 = static_cast<double>((t128 + sms - 1) / sms) * 1.0;
+  const double cost256 = static_cast<double>((t256 + slots - 1) / slots) * 2.0;
+  const double cost128 = static_cast<double>((t128 + slots - 1) / slots) * 1.0;
   const bool use128 = (N <= 128) || (cost128 < cost256) || g_debug[2] == 128;
   const int bn = (use128 && g_debug[2] != 256) ? 128 : 256;
   p.num_m_tiles = mt;
   p.num_n_tiles = (N + bn - 1) / bn;
   int rc;
   if ((rc = make_tmap_2d(&p.tmA, x, 4, false, M, K, ldx, 128, 32))) return rc;
-  if ((rc = make_tmap_2d(&p.tmB, w, 4, false, N, K, ldw, bn, 32))) return rc;
+  if ((rc = make_tmap_2d(&p.tmB, w, 4, false, N, K, ldw, bn / ctas, 32))) return rc;
   if ((rc = make_tmap_2d(&p.tmC, y, 4, false, M, N, ldy, 32, 32, false))) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (bn == 128) return launch_gemm<true, 128, kModeTiled, false>(p, s);
-  return launch_gemm<true, 256, kModeTiled, false>(p, s);
+  if (ctas == 2) return bn == 128 ? launch_tiled<128, 2>(p, s) : launch_tiled<256, 2>(p, s);
+  return bn == 128 ? launch_tiled<128, 1>(p, s) : launch_tiled<256, 1>(p, s);
 }
 
 extern "C" int tavsr_gemm_rowln(const tavsr_rowln_args* a, void* stream) {
@@ -200,8 +232,9 @@ extern "C" int tavsr_gemm_rowln(const tavsr_rowln_args* a, void* stream) {
   TAVSR_REQUIRE(!a->residual || a->ldr % 4 == 0, "rowln: residual pitch must be a multiple of 4");
   GemmParams p;
   memset(&p, 0, sizeof(p));
+  const int ctas = g_debug[3] == 1 ? 1 : 2;
   p.M = a->M; p.N = 256; p.K = a->K;
-  p.num_m_tiles = (a->M + 127) / 128;
+  p.num_m_tiles = (a->M + 128 * ctas - 1) / (128 * ctas);
   p.num_n_tiles = 1;
   p.bias = a->bias;
   p.act = ACT_NONE;
@@ -218,7 +251,7 @@ extern "C" int tavsr_gemm_rowln(const tavsr_rowln_args* a, void* stream) {
   int rc;
   if ((rc = make_tmap_2d(&p.tmA, a->x, 4, false, a->M, a->K, a->ldx, 128, 32))) return rc;
   if (dual && (rc = make_tmap_2d(&p.tmA2, a->x2, 4, false, a->M, a->K, a->ldx2, 128, 32))) return rc;
-  if ((rc = make_tmap_2d(&p.tmB, a->w, 4, false, 256, a->K, a->ldw, 256, 32))) return rc;
+  if ((rc = make_tmap_2d(&p.tmB, a->w, 4, false, 256, a->K, a->ldw, 256 / ctas, 32))) return rc;
   if (a->out_main &&
       (rc = make_tmap_2d(&p.tmC, a->out_main, 4, false, a->M, 256, a->ld_main, 32, 32, false)))
     return rc;
@@ -229,6 +262,10 @@ extern "C" int tavsr_gemm_rowln(const tavsr_rowln_args* a, void* stream) {
       (rc = make_tmap_2d(&p.tmLnB, a->out_lnB, 4, false, a->M, 256, a->ld_lnB, 32, 32, false)))
     return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (dual) return launch_gemm<true, 256, kModeRowLN, true>(p, s);
-  return launch_gemm<true, 256, kModeRowLN, false>(p, s);
+  if (ctas == 2) {
+    if (dual) return launch_gemm<true, 256, kModeRowLN, true, 2, 0>(p, s);
+    return launch_gemm<true, 256, kModeRowLN, false, 2, 0>(p, s);
+  }
+  if (dual) return launch_gemm<true, 256, kModeRowLN, true, 1, 0>(p, s);
+  return launch_gemm<true, 256, kModeRowLN, false, 1, 0>(p, s);
 }

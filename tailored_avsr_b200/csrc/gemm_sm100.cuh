@@ -61,16 +61,16 @@ struct alignas(64) GemmParams {
   float eps0;  // eps of ln0
 };
 
-template <bool kTf32, int kBlockN, int kMode, bool kDual>
+template <bool kTf32, int kBlockN, int kMode, bool kDual, int kCtas>
 struct GemmCfg {
-  static constexpr int kBlockM = 128;
+  static constexpr int kBlockM = 128;               // rows per CTA (a CTA pair covers 256)
   static constexpr int kElemBytes = kTf32 ? 4 : 2;
   static constexpr int kBlockK = 128 / kElemBytes;  // one 128B swizzle row
   static constexpr int kUmmaK = 32 / kElemBytes;
   static constexpr int kABytes = kBlockM * 128;
-  static constexpr int kBBytes = kBlockN * 128;
+  static constexpr int kBRows = kBlockN / kCtas;    // B rows held by this CTA (half in a pair)
+  static constexpr int kBBytes = kBRows * 128;
   static constexpr int kStageBytes = kABytes * (kDual ? 2 : 1) + kBBytes;
-  static constexpr int kStages = kDual ? 2 : (kBlockN == 256 ? 3 : 4);
   static constexpr int kAccCols = kBlockN * (kDual ? 2 : 1);
   static constexpr int kAccStages = (512 / kAccCols) >= 2 ? 2 : 1;
   static constexpr int kEpiWarps = kMode == kModeTiled ? 8 : 4;
@@ -78,11 +78,16 @@ struct GemmCfg {
   static constexpr int kStagingBytes = kEpiWarps * 2 * 4096;
   // params staged in smem: bias[2][kBlockN] (tiled) or 9 x 256 floats (rowln)
   static constexpr int kParamFloats = kMode == kModeTiled ? 2 * kBlockN : 9 * 256;
-  static constexpr int kSmemBytes =
-      1024 /*align slack*/ + kStages * kStageBytes + kStagingBytes + kParamFloats * 4 + 256;
+  static constexpr int kFixedBytes = 1024 /*align slack*/ + kStagingBytes + kParamFloats * 4 + 256;
+  static constexpr int kStagesFit = (227 * 1024 - kFixedBytes) / kStageBytes;
+  static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
+  static constexpr int kSmemBytes = kFixedBytes + kStages * kStageBytes;
+  static_assert(kStages >= 2, "pipeline needs at least two stages");
 };
 
-__device__ __forceinline__ float apply_act(float x, int act) {
+template <int kAct>
+__device__ __forceinline__ float apply_act(float x, int act_rt) {
+  const int act = kAct >= 0 ? kAct : act_rt;
   switch (act) {
     case ACT_SWISH: return __fdividef(x, 1.0f + __expf(-x));
     case ACT_GELU: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
@@ -121,10 +126,11 @@ struct WarpStager {
   }
 };
 
-template <bool kTf32, int kBlockN, int kMode, bool kDual>
-__global__ void __launch_bounds__(GemmCfg<kTf32, kBlockN, kMode, kDual>::kThreads, 1)
+template <bool kTf32, int kBlockN, int kMode, bool kDual, int kCtas, int kAct>
+__global__ void __launch_bounds__(GemmCfg<kTf32, kBlockN, kMode, kDual, kCtas>::kThreads, 1)
 gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<kTf32, kBlockN, kMode, kDual>;
+  using Cfg = GemmCfg<kTf32, kBlockN, kMode, kDual, kCtas>;
+  constexpr bool kPair = kCtas == 2;
   constexpr int kStages = Cfg::kStages;
   constexpr int kAccStages = Cfg::kAccStages;
 
@@ -143,7 +149,11 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
 
   const int warp = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  // Work units: a unit is one CTA tile (kCtas == 1) or one CTA-pair tile of 256 rows (kCtas == 2).
+  const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
+  const int unit0 = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int unit_step = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;  // in units
   const int num_kb = (p.K + Cfg::kBlockK - 1) / Cfg::kBlockK;
 
   if (warp == 0 && lane == 0) {
@@ -156,13 +166,18 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
     }
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], Cfg::kEpiWarps);
+      mbar_init(&tempty_bar[i], Cfg::kEpiWarps * kCtas);  // both CTAs' epilogues free the leader
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(s_tmem, 512);
-    tmem_relinquish();
+    if (kPair) {
+      tmem_alloc_2sm(s_tmem, 512);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(s_tmem, 512);
+      tmem_relinquish();
+    }
   }
   if (kMode == kModeRowLN && warp >= 2) {
     // stage the per-column parameter vectors once (N == 256)
@@ -175,6 +190,7 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
   }
   tc_fence_before_sync();
   __syncthreads();
+  if (kPair) cluster_sync_all();  // peer barriers are initialised before any remote arrive / TMA
   tc_fence_after_sync();
   const uint32_t tmem_base = *s_tmem;
 
@@ -183,33 +199,44 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.num_n_tiles;
+      for (int tile = unit0; tile < num_tiles; tile += unit_step) {
+        const int m_blk = (tile / p.num_n_tiles) * kCtas + static_cast<int>(cta_rank);
         const int n_blk = tile % p.num_n_tiles;
+        const int b_row0 = n_blk * kBlockN + static_cast<int>(cta_rank) * Cfg::kBRows;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* st = s_stage + s * Cfg::kStageBytes;
-          mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
-          tma_load_2d(st, &p.tmA, &full_bar[s], kb * Cfg::kBlockK, m_blk * Cfg::kBlockM);
-          if (kDual)
-            tma_load_2d(st + Cfg::kABytes, &p.tmA2, &full_bar[s], kb * Cfg::kBlockK,
-                        m_blk * Cfg::kBlockM);
-          tma_load_2d(st + Cfg::kABytes * (kDual ? 2 : 1), &p.tmB, &full_bar[s],
-                      kb * Cfg::kBlockK, n_blk * kBlockN);
+          uint8_t* sb = st + Cfg::kABytes * (kDual ? 2 : 1);
+          if (kPair) {
+            // the leader's barrier collects the bytes of both CTAs' loads
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes * 2);
+            tma_load_2d_2sm(st, &p.tmA, &full_bar[s], kb * Cfg::kBlockK, m_blk * Cfg::kBlockM);
+            if (kDual)
+              tma_load_2d_2sm(st + Cfg::kABytes, &p.tmA2, &full_bar[s], kb * Cfg::kBlockK,
+                              m_blk * Cfg::kBlockM);
+            tma_load_2d_2sm(sb, &p.tmB, &full_bar[s], kb * Cfg::kBlockK, b_row0);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+            tma_load_2d(st, &p.tmA, &full_bar[s], kb * Cfg::kBlockK, m_blk * Cfg::kBlockM);
+            if (kDual)
+              tma_load_2d(st + Cfg::kABytes, &p.tmA2, &full_bar[s], kb * Cfg::kBlockK,
+                          m_blk * Cfg::kBlockM);
+            tma_load_2d(sb, &p.tmB, &full_bar[s], kb * Cfg::kBlockK, b_row0);
+          }
           if (++s == kStages) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
-      constexpr uint32_t idesc =
-          umma_idesc(kTf32 ? UMMA_FMT_TF32 : UMMA_FMT_BF16, Cfg::kBlockM, kBlockN);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = umma_idesc(kTf32 ? UMMA_FMT_TF32 : UMMA_FMT_BF16,
+                                            Cfg::kBlockM * kCtas, kBlockN);
       int s = 0;
       uint32_t ph = 0;
       int as = 0;
       uint32_t aph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = unit0; tile < num_tiles; tile += unit_step) {
         mbar_wait(&tempty_bar[as], aph ^ 1);
         tc_fence_after_sync();
         const uint32_t d0 = tmem_base + as * Cfg::kAccCols;
@@ -220,20 +247,25 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
           const uint32_t b_addr = a_addr + Cfg::kABytes * (kDual ? 2 : 1);
           const uint64_t a_desc = umma_desc_kmajor_sw128(a_addr);
           const uint64_t b_desc = umma_desc_kmajor_sw128(b_addr);
+          const uint64_t a2_desc = umma_desc_kmajor_sw128(a_addr + Cfg::kABytes);
 #pragma unroll
           for (int k = 0; k < Cfg::kBlockK / Cfg::kUmmaK; ++k) {
             const uint32_t acc = (kb | k) ? 1u : 0u;
             // advancing K inside the 128B swizzle row: +32 bytes == +2 in the (addr>>4) field
-            umma_ss<kTf32>(d0, a_desc + 2 * k, b_desc + 2 * k, idesc, acc);
-            if (kDual) {
-              const uint64_t a2_desc = umma_desc_kmajor_sw128(a_addr + Cfg::kABytes);
-              umma_ss<kTf32>(d0 + kBlockN, a2_desc + 2 * k, b_desc + 2 * k, idesc, acc);
+            if (kPair) {
+              umma_ss_2sm<kTf32>(d0, a_desc + 2 * k, b_desc + 2 * k, idesc, acc);
+              if (kDual) umma_ss_2sm<kTf32>(d0 + kBlockN, a2_desc + 2 * k, b_desc + 2 * k, idesc, acc);
+            } else {
+              umma_ss<kTf32>(d0, a_desc + 2 * k, b_desc + 2 * k, idesc, acc);
+              if (kDual) umma_ss<kTf32>(d0 + kBlockN, a2_desc + 2 * k, b_desc + 2 * k, idesc, acc);
             }
           }
-          umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) once these MMAs retire
+          if (kPair) umma_commit_2sm(&empty_bar[s]); else umma_commit(&empty_bar[s]);
           if (++s == kStages) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue warps (of both CTAs)
+        if (kPair) umma_commit_2sm(&tfull_bar[as]); else umma_commit(&tfull_bar[as]);
         if (++as == kAccStages) { as = 0; aph ^= 1; }
       }
     }
@@ -246,8 +278,8 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
     int as = 0;
     uint32_t aph = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m_blk = tile / p.num_n_tiles;
+    for (int tile = unit0; tile < num_tiles; tile += unit_step, ++it) {
+      const int m_blk = (tile / p.num_n_tiles) * kCtas + static_cast<int>(cta_rank);
       const int n_blk = tile % p.num_n_tiles;
       const int m0 = m_blk * Cfg::kBlockM;
       const int n0 = n_blk * kBlockN;
@@ -274,14 +306,14 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float x = __uint_as_float(r[j]) + sb[col + j];
-            x = apply_act(x, p.act);
+            x = apply_act<kAct>(x, p.act);
             v[j] = p.round_c ? round_tf32(x) : x;
           }
           stager.store(&p.tmC, v, n0 + col, m0 + q * 32);
         }
         tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        if (lane == 0) { if (kPair) mbar_arrive_leader(&tempty_bar[as]); else mbar_arrive(&tempty_bar[as]); }
       } else {
         // ---------------------------- row-complete epilogue ----------------------------------
         const float* s_bias = s_param;
@@ -463,7 +495,7 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
         }
         tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        if (lane == 0) { if (kPair) mbar_arrive_leader(&tempty_bar[as]); else mbar_arrive(&tempty_bar[as]); }
       }
       if (++as == kAccStages) { as = 0; aph ^= 1; }
     }
@@ -473,10 +505,11 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
   // ---- teardown ----
   tc_fence_before_sync();
   __syncthreads();
+  if (kPair) cluster_sync_all();  // the peer may still be reading this CTA's smem / TMEM
   tc_fence_after_sync();
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc(tmem_base, 512);
+    if (kPair) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 

@@ -90,52 +90,77 @@ csgu_stats_kernel(const float* __restrict__ h, long long ldh, int M, int Ch, flo
 
 // ------------------------------------------------------------------------------------------------
 // CSGU pass 2: out[b,t,c] = r[b,t,c] * (sum_k w[c,k] * LN(g)[b,t+k-15,c] + cb[c])
-// One thread per channel (lanes -> consecutive channels: every global access is a coalesced 128 B
-// line per warp), each thread slides over kSeg output frames keeping the 31 taps in registers and
-// computing 16 outputs per pass from a register window.
+// CTA = 128 channels x kSeg output frames of one utterance.  The (kSeg+30) x 128 gate tile is
+// brought in with cp.async (every request in flight at once: the kernel is bandwidth-, not
+// latency-bound), then one thread per channel slides a register window over it: 16 outputs per
+// pass from 46 shared-memory reads (conflict-free: lanes <-> consecutive channels) and 496 FMAs.
 // ------------------------------------------------------------------------------------------------
 constexpr int kTaps = 31;
 constexpr int kHalo = 15;
 constexpr int kSeg = 64;   // output frames per CTA
 constexpr int kGrp = 16;   // outputs per register pass
+constexpr int kCh = 128;   // channels per CTA
+constexpr int kRows = kSeg + 2 * kHalo;
 
-__global__ void __launch_bounds__(128)
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc),
+               "r"(sz)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kCh, 4)
 csgu_conv_kernel(const float* __restrict__ h, long long ldh, const float* __restrict__ norm_g,
                  const float* __restrict__ norm_b, const float* __restrict__ conv_w,
                  const float* __restrict__ conv_b, const float2* __restrict__ stats,
                  float* __restrict__ out, long long ldo, int T, int Ch, int round_out) {
-  __shared__ float2 s_stats[kSeg + 2 * kHalo];
-  const int c = blockIdx.x * 128 + threadIdx.x;
+  __shared__ __align__(16) float s_tile[kRows][kCh];
+  __shared__ float2 s_ab[kRows];  // per frame: (rstd, -mean*rstd); (0,0) outside [0,T)
+  const int c0 = blockIdx.x * kCh;
   const int t0 = blockIdx.y * kSeg;
   const int b = blockIdx.z;
   const long long row0 = static_cast<long long>(b) * T;
-  for (int i = threadIdx.x; i < kSeg + 2 * kHalo; i += 128) {
-    const int t = t0 - kHalo + i;
-    s_stats[i] = (t >= 0 && t < T) ? stats[row0 + t] : make_float2(0.f, 0.f);
+  const float* gbase = h + Ch + c0;
+  for (int idx = threadIdx.x; idx < kRows * (kCh / 4); idx += kCh) {
+    const int r = idx / (kCh / 4), q = idx % (kCh / 4);
+    const int t = t0 - kHalo + r;
+    const bool ok = t >= 0 && t < T;
+    cp_async16_zfill(&s_tile[r][q * 4], gbase + (row0 + (ok ? t : 0)) * ldh + q * 4, ok);
   }
-  __syncthreads();
-  if (c >= Ch) return;
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int i = threadIdx.x; i < kRows; i += kCh) {
+    const int t = t0 - kHalo + i;
+    float2 ab = make_float2(0.f, 0.f);
+    if (t >= 0 && t < T) {
+      const float2 st = stats[row0 + t];
+      ab = make_float2(st.y, -st.x * st.y);
+    }
+    s_ab[i] = ab;
+  }
+  const int c = c0 + threadIdx.x;
   float w[kTaps];
 #pragma unroll
   for (int k = 0; k < kTaps; ++k) w[k] = __ldg(conv_w + static_cast<long long>(c) * kTaps + k);
   const float gam = __ldg(norm_g + c), bet = __ldg(norm_b + c), cb = __ldg(conv_b + c);
-  const float* gcol = h + Ch + c;
   const float* rcol = h + c;
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
 
   for (int g0 = 0; g0 < kSeg; g0 += kGrp) {
     const int tb = t0 + g0;  // first output frame of this group
     if (tb >= T) break;
+    float rv[kGrp];          // carried half, loaded early so the latency hides behind the FMAs
+#pragma unroll
+    for (int o = 0; o < kGrp; ++o) rv[o] = tb + o < T ? __ldg(rcol + (row0 + tb + o) * ldh) : 0.f;
     float acc[kGrp];
 #pragma unroll
     for (int o = 0; o < kGrp; ++o) acc[o] = 0.f;
 #pragma unroll
     for (int ii = 0; ii < kGrp + kTaps - 1; ++ii) {
-      const int t = tb - kHalo + ii;
-      float xn = 0.f;
-      if (t >= 0 && t < T) {
-        const float2 st = s_stats[g0 + ii];
-        xn = (__ldg(gcol + (row0 + t) * ldh) - st.x) * st.y * gam + bet;
-      }
+      const float2 ab = s_ab[g0 + ii];
+      // LN(g) = (x - mean) * rstd * gamma + beta; exactly 0 outside [0,T) (conv zero padding)
+      const float xh = fmaf(s_tile[g0 + ii][threadIdx.x], ab.x, ab.y);
+      const float xn = ab.x != 0.f ? fmaf(xh, gam, bet) : 0.f;
 #pragma unroll
       for (int o = 0; o < kGrp; ++o) {
         const int k = ii - o;
@@ -146,7 +171,7 @@ csgu_conv_kernel(const float* __restrict__ h, long long ldh, const float* __rest
     for (int o = 0; o < kGrp; ++o) {
       const int t = tb + o;
       if (t < T) {
-        float y = __ldg(rcol + (row0 + t) * ldh) * (acc[o] + cb);
+        const float y = rv[o] * (acc[o] + cb);
         out[(row0 + t) * ldo + c] = round_out ? round_tf32(y) : y;
       }
     }
@@ -246,8 +271,8 @@ extern "C" int tavsr_csgu_fwd(const float* h, long long ldh, const float* norm_g
     default: return set_error(TAVSR_ERR_UNSUPPORTED, "csgu: Ch=%d not instantiated", Ch);
   }
   TAVSR_CUDA_OK(cudaGetLastError());
-  dim3 grid2(Ch / 128, (T + kSeg - 1) / kSeg, B);
-  csgu_conv_kernel<<<grid2, 128, 0, s>>>(h, ldh, norm_g, norm_b, conv_w, conv_b, st, out, ldo, T,
+  dim3 grid2(Ch / kCh, (T + kSeg - 1) / kSeg, B);
+  csgu_conv_kernel<<<grid2, kCh, 0, s>>>(h, ldh, norm_g, norm_b, conv_w, conv_b, st, out, ldo, T,
                                          Ch, round_out);
   TAVSR_CUDA_OK(cudaGetLastError());
   g_launches.fetch_add(2, std::memory_order_relaxed);

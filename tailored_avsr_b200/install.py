@@ -1,0 +1,38 @@
+"""Install hook: rebind the reference's registry entries to the B200 drop-in classes.
+
+The reference selects its encoder through espnet2 `ClassChoices` registries and binds `CTC` at
+import time (src/tasks/asr.py:12,145-166,589-591; src/tasks/avsr.py:43,156-164,683).  A maintainer
+adds to each task file
+
+    from tailored_avsr_b200.install import install_asr      # or install_avsr
+    install_asr(globals())
+
+and `avsr_main.py`, the YAML configs and checkpoints run unchanged.
+"""
+from __future__ import annotations
+
+from .ctc.ctc import CTC
+from .encoder.audiovisual.conventional.encoder import ConventionalEncoder
+from .encoder.audiovisual.tailored.encoder import TailoredEncoder
+from .encoder.branchformer.encoder import MyBranchformerEncoder
+
+
+def _classes(registry):
+    classes = getattr(registry, "classes", None)
+    if not isinstance(classes, dict):
+        raise TypeError("expected an espnet2 ClassChoices registry with a `.classes` dict")
+    return classes
+
+
+def install_asr(namespace: dict) -> None:
+    """`namespace` is the globals() of src/tasks/asr.py."""
+    _classes(namespace["encoder_choices"])["branchformer"] = MyBranchformerEncoder
+    namespace["CTC"] = CTC
+
+
+def install_avsr(namespace: dict) -> None:
+    """`namespace` is the globals() of src/tasks/avsr.py."""
+    classes = _classes(namespace["encoder_choices"])
+    classes["tailored"] = TailoredEncoder
+    classes["conventional"] = ConventionalEncoder
+    namespace["CTC"] = CTC
