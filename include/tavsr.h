@@ -116,9 +116,16 @@ typedef struct tavsr_rowln_args {
   const float* dot1; /* [256] */
   const float* dot2;
   float* dots_out; /* [M,2] */
+  /* Optional split-K scratch (tavsr_rowln_workspace_bytes(M) bytes, ZERO-initialised once, owned
+   * by the caller, one per concurrently used stream).  When present and the problem leaves more
+   * than half of the SMs idle (K >= 1024, few row tiles) the reduction is split in two across CTA
+   * pairs and recombined in the epilogue.  The kernel leaves the flag words zeroed again. */
+  void* workspace;
+  long long workspace_bytes;
 } tavsr_rowln_args;
 
 int tavsr_gemm_rowln(const tavsr_rowln_args* args, void* stream);
+size_t tavsr_rowln_workspace_bytes(int M);
 
 /* ------------------------------------------------------------------------------------------------
  * Stand-alone LayerNorm over the last dim D (D % 128 == 0, D <= 2048) producing up to two affine

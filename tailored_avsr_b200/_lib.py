@@ -40,6 +40,7 @@ class RowLNArgs(Structure):
         ("round_lnB", c_int),
         ("eps", c_float),
         ("dot1", c_void_p), ("dot2", c_void_p), ("dots_out", c_void_p),
+        ("workspace", c_void_p), ("workspace_bytes", c_longlong),
     ]
 
 
@@ -53,6 +54,7 @@ SIGNATURES = {
                                     c_longlong, c_int, c_int, c_int, c_int, c_int, c_int,
                                     c_void_p]),
     "tavsr_gemm_rowln": (c_int, [POINTER(RowLNArgs), c_void_p]),
+    "tavsr_rowln_workspace_bytes": (c_size_t, [c_int]),
     "tavsr_layernorm": (c_int, [c_void_p, c_longlong, c_int, c_int, c_float, c_void_p, c_void_p,
                                 c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_void_p,
                                 c_longlong, c_int, c_float, c_void_p]),

@@ -201,7 +201,8 @@ extern "C" int tavsr_gemm_bias_act(const void* x, long long ldx, const void* w, 
   // tile-width heuristic: fewer waves wins (a 128-wide tile costs about half a 256-wide one)
   const int t256 = mt * ((N + 255) / 256), t128 = mt * ((N + 127) / 128);
   const double cost256 = static_cast<double>((t256 + slots - 1) / slots) * 2.0;
-  const double cost128 = static_cast<double>((t128 + slots - 1) / slots) * 1.0;
+  // (a 128-wide tile moves 1.5x the operand bytes per output element, hence the 1.25 penalty)
+  const double cost128 = static_cast<double>((t128 + slots - 1) / slots) * 1.25;
   const bool use128 = (N <= 128) || (cost128 < cost256) || g_debug[2] == 128;
   const int bn = (use128 && g_debug[2] != 256) ? 128 : 256;
   p.num_m_tiles = mt;
@@ -213,6 +214,11 @@ extern "C" int tavsr_gemm_bias_act(const void* x, long long ldx, const void* w, 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (ctas == 2) return bn == 128 ? launch_tiled<128, 2>(p, s) : launch_tiled<256, 2>(p, s);
   return bn == 128 ? launch_tiled<128, 1>(p, s) : launch_tiled<256, 1>(p, s);
+}
+
+extern "C" size_t tavsr_rowln_workspace_bytes(int M) {
+  const size_t units = (static_cast<size_t>(M) + 255) / 256;
+  return units * 256 * 256 * sizeof(float) + units * 2 * 4 * sizeof(unsigned int);
 }
 
 extern "C" int tavsr_gemm_rowln(const tavsr_rowln_args* a, void* stream) {
@@ -236,6 +242,15 @@ extern "C" int tavsr_gemm_rowln(const tavsr_rowln_args* a, void* stream) {
   p.M = a->M; p.N = 256; p.K = a->K;
   p.num_m_tiles = (a->M + 128 * ctas - 1) / (128 * ctas);
   p.num_n_tiles = 1;
+  // split-K over two CTA pairs when the row tiles alone would leave >= half of the SMs idle
+  if (!dual && ctas == 2 && a->workspace != nullptr && g_debug[4] == 0 && a->K >= 1024 &&
+      a->K % 64 == 0 && 2 * p.num_m_tiles <= num_sms() / 2 &&
+      static_cast<size_t>(a->workspace_bytes) >= tavsr_rowln_workspace_bytes(a->M)) {
+    p.num_n_tiles = 2;
+    const size_t rows = static_cast<size_t>(p.num_m_tiles) * 256;
+    p.partial = static_cast<float*>(a->workspace);
+    p.flags = reinterpret_cast<unsigned int*>(static_cast<char*>(a->workspace) + rows * 256 * 4);
+  }
   p.bias = a->bias;
   p.act = ACT_NONE;
   p.round_c = a->round_main;

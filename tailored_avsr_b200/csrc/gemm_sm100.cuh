@@ -59,6 +59,10 @@ struct alignas(64) GemmParams {
   float* dots_out;    // [M,2]
   float eps;
   float eps0;  // eps of ln0
+  // ---- RowLN split-K (num_n_tiles == 2): unit parity selects the K half; the odd unit dumps its
+  // accumulator to `partial`, the even unit adds it in its epilogue ----
+  float* partial;          // [M_padded, 256] fp32 scratch
+  unsigned int* flags;     // [num_m_tiles * kCtas * 4], zero between launches
 };
 
 template <bool kTf32, int kBlockN, int kMode, bool kDual, int kCtas>
@@ -202,8 +206,12 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
       for (int tile = unit0; tile < num_tiles; tile += unit_step) {
         const int m_blk = (tile / p.num_n_tiles) * kCtas + static_cast<int>(cta_rank);
         const int n_blk = tile % p.num_n_tiles;
-        const int b_row0 = n_blk * kBlockN + static_cast<int>(cta_rank) * Cfg::kBRows;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        // RowLN: N is one tile, the unit's n index selects the K split instead
+        const int b_row0 = (kMode == kModeRowLN ? 0 : n_blk * kBlockN) +
+                           static_cast<int>(cta_rank) * Cfg::kBRows;
+        const int kb_cnt = kMode == kModeRowLN ? num_kb / p.num_n_tiles : num_kb;
+        const int kb_beg = kMode == kModeRowLN ? n_blk * kb_cnt : 0;
+        for (int kb = kb_beg; kb < kb_beg + kb_cnt; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* st = s_stage + s * Cfg::kStageBytes;
           uint8_t* sb = st + Cfg::kABytes * (kDual ? 2 : 1);
@@ -240,7 +248,8 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
         mbar_wait(&tempty_bar[as], aph ^ 1);
         tc_fence_after_sync();
         const uint32_t d0 = tmem_base + as * Cfg::kAccCols;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb_cnt = kMode == kModeRowLN ? num_kb / p.num_n_tiles : num_kb;
+        for (int kb = 0; kb < kb_cnt; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after_sync();
           const uint32_t a_addr = smem_u32(s_stage + s * Cfg::kStageBytes);
@@ -286,34 +295,53 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
       const uint32_t tacc = tmem_base + lane_off + as * Cfg::kAccCols;
 
       if constexpr (kMode == kModeTiled) {
-        // ---- bias for this tile into smem (double-buffered by iteration parity) ----
-        float* sb = s_param + (it & 1) * kBlockN;
-        for (int i = threadIdx.x - 64; i < kBlockN; i += 32 * Cfg::kEpiWarps)
-          sb[i] = (p.bias && n0 + i < p.N) ? p.bias[n0 + i] : 0.0f;
-        named_bar_sync(1, 32 * Cfg::kEpiWarps);
-
         mbar_wait(&tfull_bar[as], aph);
         tc_fence_after_sync();
         const int half = ew >> 2;
         constexpr int kChunks = kBlockN / 64;  // 32-col chunks per warp (half the tile)
-        for (int c = 0; c < kChunks; ++c) {
-          const int col = half * (kBlockN / 2) + c * 32;
-          if (n0 + col >= p.N) break;  // warp-uniform
-          uint32_t r[32];
-          tmem_ld32(tacc + col, r);
-          tmem_ld_wait();
-          float v[32];
+        const int col0 = half * (kBlockN / 2);
+        uint32_t r[2][32];
+        tmem_ld32(tacc + col0, r[0]);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(r[j]) + sb[col + j];
-            x = apply_act<kAct>(x, p.act);
-            v[j] = p.round_c ? round_tf32(x) : x;
+        for (int c = 0; c < kChunks; ++c) {
+          const int col = col0 + c * 32;
+          const bool live = n0 + col < p.N;  // warp-uniform
+          // bias: uniform (same address in every lane) 16-byte loads served by L1
+          float bv[32];
+          if (p.bias != nullptr && n0 + col + 32 <= p.N) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + col);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 f = __ldg(bp + j);
+              bv[4 * j] = f.x; bv[4 * j + 1] = f.y; bv[4 * j + 2] = f.z; bv[4 * j + 3] = f.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              bv[j] = (p.bias != nullptr && n0 + col + j < p.N) ? __ldg(p.bias + n0 + col + j) : 0.f;
           }
-          stager.store(&p.tmC, v, n0 + col, m0 + q * 32);
+          tmem_ld_wait();
+          if (c + 1 < kChunks) {
+            tmem_ld32(tacc + col + 32, r[(c + 1) & 1]);  // overlaps the math of chunk c
+          } else {
+            // every accumulator value of this warp is in registers: release TMEM to the MMA warp
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) {
+              if (kPair) mbar_arrive_leader(&tempty_bar[as]); else mbar_arrive(&tempty_bar[as]);
+            }
+          }
+          if (live) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float x = __uint_as_float(r[c & 1][j]) + bv[j];
+              x = apply_act<kAct>(x, p.act);
+              v[j] = p.round_c ? round_tf32(x) : x;
+            }
+            stager.store(&p.tmC, v, n0 + col, m0 + q * 32);
+          }
         }
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) { if (kPair) mbar_arrive_leader(&tempty_bar[as]); else mbar_arrive(&tempty_bar[as]); }
       } else {
         // ---------------------------- row-complete epilogue ----------------------------------
         const float* s_bias = s_param;
@@ -340,6 +368,49 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
         }
         mbar_wait(&tfull_bar[as], aph);
         tc_fence_after_sync();
+
+        const bool splitk = p.num_n_tiles == 2;
+        unsigned int* flag =
+            splitk ? p.flags + ((static_cast<long long>(m_blk) * 4 + q)) : nullptr;
+        if (splitk && n_blk == 1) {
+          // ---- split-K writer: dump the raw partial accumulator, publish, next tile ----
+          float* prow = p.partial + static_cast<long long>(m) * 256;
+          for (int c = 0; c < 8; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tacc + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              __stcg(reinterpret_cast<float4*>(prow + c * 32) + j,
+                     make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                 __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+          }
+          tc_fence_before_sync();
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) {
+            if (kPair) mbar_arrive_leader(&tempty_bar[as]); else mbar_arrive(&tempty_bar[as]);
+            atomicExch(flag, 1u);
+          }
+          if (++as == kAccStages) { as = 0; aph ^= 1; }
+          continue;
+        }
+        if (splitk) {
+          // ---- split-K reader: wait for the other half of K (bounded spin) ----
+          if (lane == 0) {
+            const long long t0 = clock64();
+            while (atomicAdd(flag, 0u) == 0u) {
+              if (clock64() - t0 > (1ll << 31)) {
+                printf("tavsr: split-K flag timeout (block %d)\n", blockIdx.x);
+                __trap();
+              }
+            }
+            *flag = 0u;  // re-armed for the next launch (stream order)
+            __threadfence();
+          }
+          __syncwarp();
+        }
+        const float* part_row = splitk ? p.partial + static_cast<long long>(m) * 256 : nullptr;
 
         // PASS A: v0 = residual + alpha * (combine(acc) + bias)
         float sum = 0.0f, dd1 = 0.0f, dd2 = 0.0f;
@@ -371,6 +442,14 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          }
+          if (splitk) {
+            const float4* pp = reinterpret_cast<const float4*>(part_row + c * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 f = __ldcg(pp + j);
+              v[4 * j] += f.x; v[4 * j + 1] += f.y; v[4 * j + 2] += f.z; v[4 * j + 3] += f.w;
+            }
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {

@@ -249,7 +249,10 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const void* tmap
 
 // Arrive on the leader CTA's copy of `bar` (works from either CTA of the pair).
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(
+  // relaxed: the only data this arrive orders are TMEM reads, which tcgen05.wait::ld +
+  // tcgen05.fence::before_thread_sync already ordered; a .release at cluster scope would cost a
+  // MEMBAR.ALL + ERRBAR per arrive (18 % of the epilogue stall samples in the first profile).
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(
                    smem_u32(bar) & kPeerBitMask)
                : "memory");
 }

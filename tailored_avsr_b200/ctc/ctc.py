@@ -104,6 +104,26 @@ class CTC(torch.nn.Module):
         (_, _, amax), B, T = self._head(hs_pad, amax=True)
         return amax.view(B, T)
 
+    def loss_and_greedy(self, hs_pad, hlens, ys_pad, ys_lens, greedy_lens=None, blank: int = 0):
+        """Validation-step fusion (espnet_model.py:586-592): ONE head launch yields the
+        log-softmax for the loss and the argmax for the greedy decode.  Returns
+        (loss, tokens (B,T) padded with -1, ntok (B,)).  Inference only (dropout_rate must be 0
+        or the module in the reference's always-on dropout mode is bypassed: use forward())."""
+        if self.dropout_rate > 0:
+            loss = self.forward(hs_pad, hlens, ys_pad, ys_lens)
+            tokens, ntok = self.greedy(hs_pad, greedy_lens, blank)
+            return loss, tokens, ntok
+        B, T, _ = hs_pad.shape
+        dev = hs_pad.device
+        (logp, _, amax), _, _ = self._head(hs_pad, logp=True, amax=True)
+        nll, _ = ops.ctc_loss(logp.view(B, T, -1), ys_pad.to(dev).long().contiguous(),
+                              hlens.to(dev).to(torch.int32), ys_lens.to(dev).to(torch.int32),
+                              zero_infinity=self.zero_infinity)
+        loss = (nll.sum() / B if self.reduce else nll / B).to(dtype=hs_pad.dtype)
+        lens = None if greedy_lens is None else greedy_lens.to(dev).to(torch.int32)
+        tokens, ntok = ops.ctc_greedy(amax.view(B, T), lens, blank)
+        return loss, tokens, ntok
+
     # ---- extras of the B200 path (device-side replacement of the host groupby loops) ----
     def greedy(self, hs_pad, hlens: Optional[torch.Tensor] = None, blank: int = 0):
         """argmax -> collapse repeats -> drop blank on the device (espnet_model.py:590-592,

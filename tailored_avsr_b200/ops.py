@@ -69,6 +69,21 @@ def _chk2d(t: torch.Tensor, name: str, dtype=torch.float32) -> None:
                               f"{tuple(t.shape)} {t.dtype} strides {t.stride()}")
 
 
+_SPLITK_WS = {}  # (device index, stream handle) -> zero-initialised split-K scratch
+
+
+def _splitk_workspace(device, M: int) -> torch.Tensor:
+    """Per-stream scratch for the split-K row-complete GEMM (flag words must start at zero; the
+    kernel re-zeroes them, so one allocation serves every later launch on that stream)."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    need = int(_lib.load().tavsr_rowln_workspace_bytes(M))
+    ws = _SPLITK_WS.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(need, dtype=torch.uint8, device=device)
+        _SPLITK_WS[key] = ws
+    return ws
+
+
 def launch_count() -> int:
     return int(_lib.load().tavsr_launch_count())
 
@@ -145,6 +160,9 @@ def gemm_rowln(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = 
     if dots is not None:
         a.dot1, a.dot2 = dots[0].data_ptr(), dots[1].data_ptr()
         a.dots_out = dots_out.data_ptr()
+    if x2 is None and a.K >= 1024:
+        ws = _splitk_workspace(x.device, a.M)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
     check(_lib.load().tavsr_gemm_rowln(ctypes.byref(a), _stream()), "tavsr_gemm_rowln")
 
 

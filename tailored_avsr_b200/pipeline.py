@@ -35,10 +35,13 @@ class EncoderCTCPipeline:
         out, olens, _ = self.encoder(feats, feats_lens)
         if isinstance(out, tuple):
             out = out[0]
+        if self.greedy and hasattr(self.ctc, "loss_and_greedy"):
+            # like _calc_ctc_loss the collapse runs over all Tmax frames (espnet_model.py:590-592)
+            loss, tokens, ntok = self.ctc.loss_and_greedy(out, olens, ys_pad, ys_lens)
+            return {"encoder_out": out, "olens": olens, "loss": loss, "tokens": tokens, "ntok": ntok}
         loss = self.ctc(out, olens, ys_pad, ys_lens)
         res = {"encoder_out": out, "olens": olens, "loss": loss}
         if self.greedy:
-            # like _calc_ctc_loss the collapse runs over all Tmax frames (espnet_model.py:590-592)
             res["tokens"], res["ntok"] = self.ctc.greedy(out)
         return res
 

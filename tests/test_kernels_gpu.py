@@ -289,3 +289,26 @@ def test_ctc_greedy():
             assert int(n[b]) == len(ref)
             assert toks[b, : len(ref)].tolist() == ref
             assert (toks[b, len(ref):] == -1).all()
+
+
+@pytest.mark.parametrize("M,K", [(8000, 2048), (1992, 1024), (300, 2048), (4096, 1024)])
+def test_gemm_rowln_split_k_matches_unsplit(M, K):
+    """The split-K path (taken when few row tiles leave SMs idle) must agree with the reference
+    product and leave its flag words re-armed: run it twice back to back."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(M ^ K)
+    x = torch.randn(M, K, generator=g).to(DEV)
+    w = (torch.randn(256, K, generator=g) / math.sqrt(K)).to(DEV)
+    b = torch.randn(256, generator=g).to(DEV)
+    res = torch.randn(M, 256, generator=g).to(DEV)
+    g0, b0, gA, bA = [torch.randn(256, generator=g).to(DEV) for _ in range(4)]
+    v0 = res.double() + 0.5 * (x.double() @ w.double().t() + b.double())
+    v1 = _ln(v0, g0.double(), b0.double(), 1e-12)
+    want = _ln(v1, gA.double(), bA.double(), 1e-12)
+    for _ in range(2):
+        main = torch.empty(M, 256, device=DEV)
+        oA = torch.empty(M, 256, device=DEV)
+        ops.gemm_rowln(x, w, b, residual=res, alpha=0.5, ln0=(g0, b0), out_main=main, lnA=(gA, bA),
+                       out_lnA=oA)
+        assert rel_fro(main, v1) < 3e-3
+        assert rel_fro(oA, want) < 3e-3
