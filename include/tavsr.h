@@ -128,6 +128,32 @@ int tavsr_gemm_rowln(const tavsr_rowln_args* args, void* stream);
 size_t tavsr_rowln_workspace_bytes(int M);
 
 /* ------------------------------------------------------------------------------------------------
+ * Fused position-wise feed-forward block (espnet PositionwiseFeedForward + the residual / LayerNorm
+ * lines around it, encoder_layer.py:193-194, 202, 216, 313-316):
+ *
+ *   acc = act(xn . W1^T + b1) . W2^T            hidden = 2048 stays in TMEM / shared memory
+ *   then exactly the tavsr_gemm_rowln epilogue on acc (ep.bias = b2, ep.residual, ep.alpha, ep.ln0,
+ *   ep.out_main, ep.lnA/lnB ...).  ep.x / ep.w / ep.K / ep.x2 / ep.workspace are ignored.
+ * Built for model width 256 and hidden width 2048 (every shipped config).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct tavsr_ffn_args {
+  int struct_size; /* sizeof(tavsr_ffn_args) */
+  int hidden;      /* 2048 */
+  int act;         /* TAVSR_ACT_* */
+  int reserved;
+  const void* xn;  /* [M, 256] LayerNorm-ed input */
+  long long ldxn;
+  const void* w1;  /* [hidden, 256] */
+  long long ldw1;
+  const float* b1; /* [hidden] */
+  const void* w2;  /* [256, hidden] */
+  long long ldw2;
+  tavsr_rowln_args ep;
+} tavsr_ffn_args;
+
+int tavsr_ffn_fused(const tavsr_ffn_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Stand-alone LayerNorm over the last dim D (D % 128 == 0, D <= 2048) producing up to two affine
  * variants of the same normalised row (espnet LayerNorm, eps 1e-12; torch LayerNorm of the
  * `linear` input layer, encoder.py:126, eps 1e-5).  scale multiplies the result (x * sqrt(d) of

@@ -44,6 +44,19 @@ class RowLNArgs(Structure):
     ]
 
 
+class FfnArgs(Structure):
+    """Mirror of `tavsr_ffn_args` (include/tavsr.h)."""
+
+    _fields_ = [
+        ("struct_size", c_int), ("hidden", c_int), ("act", c_int), ("reserved", c_int),
+        ("xn", c_void_p), ("ldxn", c_longlong),
+        ("w1", c_void_p), ("ldw1", c_longlong),
+        ("b1", c_void_p),
+        ("w2", c_void_p), ("ldw2", c_longlong),
+        ("ep", RowLNArgs),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/tavsr.h declares
 SIGNATURES = {
     "tavsr_version": (c_int, []),
@@ -55,6 +68,7 @@ SIGNATURES = {
                                     c_void_p]),
     "tavsr_gemm_rowln": (c_int, [POINTER(RowLNArgs), c_void_p]),
     "tavsr_rowln_workspace_bytes": (c_size_t, [c_int]),
+    "tavsr_ffn_fused": (c_int, [POINTER(FfnArgs), c_void_p]),
     "tavsr_layernorm": (c_int, [c_void_p, c_longlong, c_int, c_int, c_float, c_void_p, c_void_p,
                                 c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_void_p,
                                 c_longlong, c_int, c_float, c_void_p]),

@@ -1,0 +1,55 @@
+// Host launcher + C ABI of the fused feed-forward kernel (see ffn_sm100.cuh).
+#include "ffn_sm100.cuh"
+
+#include <atomic>
+
+#include "host.h"
+
+namespace tavsr {
+extern std::atomic<long long> g_launches;
+int fill_rowln_epilogue(GemmParams& p, const tavsr_rowln_args* a, const char* who);
+
+template <int kAct>
+static int launch_ffn(const FfnParams& p, int m_tiles, cudaStream_t stream) {
+  auto kern = ffn_fused_kernel<kAct>;
+  static bool configured = false;
+  if (!configured) {
+    TAVSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       ffn::kSmemBytes));
+    configured = true;
+  }
+  kern<<<2 * m_tiles, ffn::kThreads, ffn::kSmemBytes, stream>>>(p);
+  TAVSR_CUDA_OK(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+}  // namespace tavsr
+
+using namespace tavsr;
+
+extern "C" int tavsr_ffn_fused(const tavsr_ffn_args* a, void* stream) {
+  TAVSR_REQUIRE(a != nullptr && a->struct_size == static_cast<int>(sizeof(tavsr_ffn_args)),
+                "ffn: bad args struct (size %d, expected %d)", a ? a->struct_size : -1,
+                static_cast<int>(sizeof(tavsr_ffn_args)));
+  TAVSR_REQUIRE(a->hidden == ffn::kHid, "ffn: only hidden = 2048 is built (got %d)", a->hidden);
+  TAVSR_REQUIRE(a->xn && a->w1 && a->w2 && a->ep.M > 0, "ffn: xn, w1, w2 and M are required");
+  TAVSR_REQUIRE(a->ep.x2 == nullptr, "ffn: dual operands are not supported");
+  FfnParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  if ((rc = fill_rowln_epilogue(p.ep, &a->ep, "ffn"))) return rc;
+  const int M = a->ep.M;
+  if ((rc = make_tmap_2d(&p.tmX, a->xn, 4, false, M, ffn::kD, a->ldxn, 128, 32))) return rc;
+  if ((rc = make_tmap_2d(&p.tmW1, a->w1, 4, false, ffn::kHid, ffn::kD, a->ldw1, 128, 32))) return rc;
+  if ((rc = make_tmap_2d(&p.tmW2, a->w2, 4, false, ffn::kD, ffn::kHid, a->ldw2, 128, 32))) return rc;
+  p.b1 = a->b1;
+  p.act = a->act;
+  const int m_tiles = (M + 127) / 128;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (a->act) {
+    case ACT_SWISH: return launch_ffn<ACT_SWISH>(p, m_tiles, s);
+    case ACT_RELU: return launch_ffn<ACT_RELU>(p, m_tiles, s);
+    case ACT_GELU: return launch_ffn<ACT_GELU>(p, m_tiles, s);
+    default: return launch_ffn<ACT_NONE>(p, m_tiles, s);
+  }
+}

@@ -1,0 +1,313 @@
+// Fused position-wise feed-forward block for sm_100a:
+//
+//   y = x + alpha * ( act(LN(x) W1^T + b1) W2^T + b2 )   [+ the row-complete LayerNorm epilogue]
+//
+// (reference: espnet PositionwiseFeedForward called at src/encoder/branchformer/encoder_layer.py
+//  :193-194 and :313-314, followed by the norms at :202,216,316).
+//
+// The 2048-wide hidden activation never leaves the SM.  Work decomposition:
+//   * one 128-row tile of frames per 2-CTA cluster; CTA r of the cluster owns hidden units
+//     [r*1024, (r+1)*1024) and produces a PARTIAL 128x256 output;
+//   * per CTA the hidden half is processed in 8 chunks of 128 units:
+//       GEMM1_j : H_j[128x128] = Xn[128x256] . W1[chunk j]^T       (A, B from smem; D in TMEM)
+//       act_j   : 4 warps read H_j from TMEM, add b1, apply the activation, round to TF32 and write
+//                 it back IN PLACE (tcgen05.ld / tcgen05.st; TMEM lane == frame)
+//       GEMM2_j : D2[128x256] += H_j . W2[:, chunk j]^T             (A from TMEM, B from smem)
+//     issue order GEMM1_0, GEMM1_1, GEMM2_0, GEMM1_2, GEMM2_1, ... so act_{j+1} overlaps GEMM2_j;
+//   * Xn (128 KB) stays resident in smem, W1/W2 stream through a 5 x 16 KB TMA ring;
+//   * TMEM: D2 = columns [0,256), H double buffer = [256,384) and [384,512);
+//   * the two partial outputs are exchanged over distributed shared memory (each CTA finishes 64
+//     of the 128 rows) and completed by rowln_finish() (residual, LayerNorms, TMA stores).
+#pragma once
+#include "gemm_sm100.cuh"
+
+namespace tavsr {
+
+struct alignas(64) FfnParams {
+  CUtensorMap tmX;   // LN(x):  (256 inner, M rows),     box {32, 128}
+  CUtensorMap tmW1;  // W1:     (256 inner, 2048 rows),  box {32, 128}
+  CUtensorMap tmW2;  // W2:     (2048 inner, 256 rows),  box {32, 128}
+  GemmParams ep;     // epilogue description: bias = b2, residual, alpha, ln0/lnA/lnB, tmC/tmLnA/tmLnB
+  const float* b1;   // [2048]
+  int act;
+};
+
+namespace ffn {
+constexpr int kD = 256;          // model width
+constexpr int kHid = 2048;       // hidden width
+constexpr int kHidCta = 1024;    // hidden units per CTA (cluster of 2)
+constexpr int kChunk = 128;      // hidden units per chunk
+constexpr int kNChunk = kHidCta / kChunk;
+constexpr int kUnitBytes = 128 * 128;        // one ring unit: 128 rows x 128 B
+constexpr int kRing = 5;
+constexpr int kXBytes = 8 * kUnitBytes;      // resident LN(x) tile: 8 k-blocks
+constexpr int kThreads = 192;                // TMA warp, MMA warp, 4 activation / epilogue warps
+constexpr int kParamFloats = kHidCta + 9 * 256;
+constexpr int kSmemBytes = 1024 + kXBytes + kRing * kUnitBytes + kParamFloats * 4 + 256;
+constexpr uint32_t kColD2 = 0, kColH = 256;
+}  // namespace ffn
+
+// D[tmem] (+)= A[tmem] . B[smem]^T : A operand read from tensor memory (lane == row, one 32-bit
+// column per K element).
+__device__ __forceinline__ void umma_ts_tf32(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t local_addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, float4 v) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+template <int kAct>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ffn::kThreads, 1)
+ffn_fused_kernel(const __grid_constant__ FfnParams p) {
+  using namespace ffn;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* s_x = smem;                       // 8 x 16 KB, later: peer partial rows (64 KB)
+  uint8_t* s_ring = s_x + kXBytes;           // 5 x 16 KB, later: TMA-store staging (32 KB)
+  float* s_b1 = reinterpret_cast<float*>(s_ring + kRing * kUnitBytes);  // [1024]
+  float* s_param = s_b1 + kHidCta;           // 9 x 256 (rowln_finish layout)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_param + 9 * 256);
+  uint64_t* w_full = bars;                   // [kRing]
+  uint64_t* w_empty = bars + kRing;          // [kRing]
+  uint64_t* x_full = bars + 2 * kRing;       // [1]
+  uint64_t* h_full = x_full + 1;             // [2]  GEMM1 chunk complete
+  uint64_t* h_ready = h_full + 2;            // [2]  activation written back
+  uint64_t* d_full = h_ready + 2;            // [1]  all GEMM2 complete
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(d_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  const uint32_t rank = cluster_ctarank();
+  const int m0 = static_cast<int>(blockIdx.x >> 1) * 128;
+  const int hid0 = static_cast<int>(rank) * kHidCta;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmX);
+    tma_prefetch_desc(&p.tmW1);
+    tma_prefetch_desc(&p.tmW2);
+    for (int i = 0; i < kRing; ++i) {
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_empty[i], 1);
+    }
+    mbar_init(x_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&h_full[i], 1);
+      mbar_init(&h_ready[i], 4);
+    }
+    mbar_init(d_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(s_tmem, 512);
+    tmem_relinquish();
+  }
+  if (warp >= 2) {
+    const float* srcs[9] = {p.ep.bias, p.ep.ln0_g, p.ep.ln0_b, p.ep.lnA_g, p.ep.lnA_b,
+                            p.ep.lnB_g, p.ep.lnB_b, p.ep.dot1, p.ep.dot2};
+    for (int v = 0; v < 9; ++v)
+      for (int i = threadIdx.x - 64; i < 256; i += 128)
+        s_param[v * 256 + i] = srcs[v] ? srcs[v][i] : 0.0f;
+    for (int i = threadIdx.x - 64; i < kHidCta; i += 128) s_b1[i] = p.b1 ? p.b1[hid0 + i] : 0.0f;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(x_full, kXBytes);
+      for (int kb = 0; kb < 8; ++kb)
+        tma_load_2d(s_x + kb * kUnitBytes, &p.tmX, x_full, kb * 32, m0);
+      int s = 0;
+      uint32_t ph = 0;
+      auto next_slot = [&]() -> uint8_t* {
+        mbar_wait(&w_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&w_full[s], kUnitBytes);
+        return s_ring + s * kUnitBytes;
+      };
+      auto advance = [&]() { if (++s == kRing) { s = 0; ph ^= 1; } };
+      auto load_w1 = [&](int j) {  // 8 k-blocks of W1[hid0 + j*128 .. +128, :]
+        for (int kb = 0; kb < 8; ++kb) {
+          uint8_t* dst = next_slot();
+          tma_load_2d(dst, &p.tmW1, &w_full[s], kb * 32, hid0 + j * kChunk);
+          advance();
+        }
+      };
+      auto load_w2 = [&](int j) {  // 4 k-blocks x 2 output halves of W2[:, hid0 + j*128 .. +128]
+        for (int kb = 0; kb < 4; ++kb)
+          for (int nh = 0; nh < 2; ++nh) {
+            uint8_t* dst = next_slot();
+            tma_load_2d(dst, &p.tmW2, &w_full[s], hid0 + j * kChunk + kb * 32, nh * 128);
+            advance();
+          }
+      };
+      // must mirror the MMA issue order below
+      load_w1(0);
+      load_w1(1);
+      for (int j = 0; j < kNChunk; ++j) {
+        load_w2(j);
+        if (j + 2 < kNChunk) load_w1(j + 2);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(UMMA_FMT_TF32, 128, 128);
+      int s = 0;
+      uint32_t ph = 0;
+      auto advance = [&]() { if (++s == kRing) { s = 0; ph ^= 1; } };
+      const uint32_t x_addr = smem_u32(s_x);
+      auto gemm1 = [&](int j) {
+        const uint32_t d = tmem_base + kColH + (j & 1) * kChunk;
+        for (int kb = 0; kb < 8; ++kb) {
+          mbar_wait(&w_full[s], ph);
+          tc_fence_after_sync();
+          const uint64_t a_desc = umma_desc_kmajor_sw128(x_addr + kb * kUnitBytes);
+          const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(s_ring + s * kUnitBytes));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_ss<true>(d, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          umma_commit(&w_empty[s]);
+          advance();
+        }
+        umma_commit(&h_full[j & 1]);
+      };
+      auto gemm2 = [&](int j) {
+        const uint32_t a0 = tmem_base + kColH + (j & 1) * kChunk;
+        for (int kb = 0; kb < 4; ++kb)
+          for (int nh = 0; nh < 2; ++nh) {
+            mbar_wait(&w_full[s], ph);
+            tc_fence_after_sync();
+            const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(s_ring + s * kUnitBytes));
+            const uint32_t d = tmem_base + kColD2 + nh * 128;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_ts_tf32(d, a0 + kb * 32 + k * 8, b_desc + 2 * k, idesc, (j | kb | k) ? 1u : 0u);
+            umma_commit(&w_empty[s]);
+            advance();
+          }
+      };
+      mbar_wait(x_full, 0);
+      tc_fence_after_sync();
+      gemm1(0);
+      gemm1(1);
+      for (int j = 0; j < kNChunk; ++j) {
+        mbar_wait(&h_ready[j & 1], (j >> 1) & 1);  // activation of chunk j is back in TMEM
+        tc_fence_after_sync();
+        gemm2(j);
+        if (j + 2 < kNChunk) gemm1(j + 2);  // reuses H buffer j&1: ordered after gemm2(j)
+      }
+      umma_commit(d_full);
+    }
+  } else {
+    // =============================== activation warps =======================================
+    const int q = warp & 3;  // TMEM lane quadrant
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    for (int j = 0; j < kNChunk; ++j) {
+      mbar_wait(&h_full[j & 1], (j >> 1) & 1);
+      tc_fence_after_sync();
+      const uint32_t th = tmem_base + lane_off + kColH + (j & 1) * kChunk;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(th + c * 32, r);
+        tmem_ld_wait();
+        const float* bb = s_b1 + j * kChunk + c * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float x = apply_act<kAct>(__uint_as_float(r[i]) + bb[i], p.act);
+          r[i] = __float_as_uint(round_tf32(x));
+        }
+        tmem_st32(th + c * 32, r);
+      }
+      tmem_st_wait();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&h_ready[j & 1]);
+    }
+    mbar_wait(d_full, 0);  // every MMA of this CTA has retired: D2 final, s_x and s_ring free
+    tc_fence_after_sync();
+  }
+
+  // ---- exchange the partial outputs across the cluster: CTA r finishes rows [64r, 64r+64) ----
+  __syncthreads();     // reconverge the single-lane role loops before the aligned cluster barrier
+  cluster_sync_all();  // both CTAs' MMAs are done -> both s_x regions may be overwritten
+  if (warp >= 2) {
+    const int q = warp & 3;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t td2 = tmem_base + lane_off + kColD2;
+    const int row_local = (q & 1) * 32 + static_cast<int>(lane);  // row inside the 64-row half
+    if (static_cast<uint32_t>(q >> 1) != rank) {
+      // sender: rows owned by the peer
+      const uint32_t peer = rank ^ 1u;
+      const uint32_t base = mapa_cluster(smem_u32(s_x) + row_local * 1024, peer);
+      for (int c = 0; c < 8; ++c) {
+        uint32_t r[32];
+        tmem_ld32(td2 + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          st_cluster_v4(base + (((c * 8 + i) ^ (row_local & 7)) << 4),
+                        make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                    __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
+      }
+    }
+  }
+  cluster_sync_all();  // release/acquire: the peer's rows are visible in s_x
+  if (warp >= 2) {
+    const int q = warp & 3;
+    if (static_cast<uint32_t>(q >> 1) == rank) {
+      const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+      const uint32_t td2 = tmem_base + lane_off + kColD2;
+      const int row_local = (q & 1) * 32 + static_cast<int>(lane);
+      const uint8_t* rrow = s_x + row_local * 1024;
+      for (int c = 0; c < 8; ++c) {
+        uint32_t r[32];
+        tmem_ld32(td2 + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 f = *reinterpret_cast<const float4*>(rrow + (((c * 8 + i) ^ (row_local & 7)) << 4));
+          r[4 * i] = __float_as_uint(__uint_as_float(r[4 * i]) + f.x);
+          r[4 * i + 1] = __float_as_uint(__uint_as_float(r[4 * i + 1]) + f.y);
+          r[4 * i + 2] = __float_as_uint(__uint_as_float(r[4 * i + 2]) + f.z);
+          r[4 * i + 3] = __float_as_uint(__uint_as_float(r[4 * i + 3]) + f.w);
+        }
+        tmem_st32(td2 + c * 32, r);
+      }
+      tmem_st_wait();
+      WarpStager stager{s_ring + (q & 1) * 8192, 0};
+      rowln_finish<false>(p.ep, s_param, td2, m0 + q * 32, lane, stager, nullptr);
+      stager.drain();
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace tavsr

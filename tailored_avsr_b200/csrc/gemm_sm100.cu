@@ -218,8 +218,44 @@ extern "C" int tavsr_gemm_bias_act(const void* x, long long ldx, const void* w, 
 
 extern "C" size_t tavsr_rowln_workspace_bytes(int M) {
   const size_t units = (static_cast<size_t>(M) + 255) / 256;
-  return units * 256 * 256 * sizeof(float) + units * 2 * 4 * sizeof(unsigned int);
+  return 4096 /* flag words (split-K is only used for <= 37 row units = 296 flags) */ +
+         units * 256 * 256 * sizeof(float);
 }
+
+namespace tavsr {
+// Validates the epilogue part of a rowln description and fills the matching GemmParams fields
+// (shared by tavsr_gemm_rowln and tavsr_ffn_fused).
+int fill_rowln_epilogue(GemmParams& p, const tavsr_rowln_args* a, const char* who) {
+  TAVSR_REQUIRE(!(a->ln0_g && !a->ln0_b) && !(a->lnA_g && !(a->lnA_b && a->out_lnA)) &&
+                    !(a->lnB_g && !(a->lnB_b && a->out_lnB)),
+                "%s: LayerNorm stages need gamma, beta and an output", who);
+  TAVSR_REQUIRE(!a->dots_out || (a->dot1 && a->dot2), "%s: dots_out needs dot1 and dot2", who);
+  TAVSR_REQUIRE(!a->residual || a->ldr % 4 == 0, "%s: residual pitch must be a multiple of 4", who);
+  p.M = a->M; p.N = 256;
+  p.bias = a->bias;
+  p.act = ACT_NONE;
+  p.round_c = a->round_main;
+  p.residual = a->residual; p.ldr = a->ldr; p.alpha = a->alpha;
+  p.ln0_g = a->ln0_g; p.ln0_b = a->ln0_b;
+  p.lnA_g = a->lnA_g; p.lnA_b = a->lnA_b; p.lnB_g = a->lnB_g; p.lnB_b = a->lnB_b;
+  p.has_main = a->out_main != nullptr;
+  p.round_lnA = a->round_lnA; p.round_lnB = a->round_lnB;
+  p.dot1 = a->dot1; p.dot2 = a->dot2; p.dots_out = a->dots_out;
+  p.eps = a->eps;
+  p.eps0 = a->eps0;
+  int rc;
+  if (a->out_main &&
+      (rc = make_tmap_2d(&p.tmC, a->out_main, 4, false, a->M, 256, a->ld_main, 32, 32, false)))
+    return rc;
+  if (a->lnA_g &&
+      (rc = make_tmap_2d(&p.tmLnA, a->out_lnA, 4, false, a->M, 256, a->ld_lnA, 32, 32, false)))
+    return rc;
+  if (a->lnB_g &&
+      (rc = make_tmap_2d(&p.tmLnB, a->out_lnB, 4, false, a->M, 256, a->ld_lnB, 32, 32, false)))
+    return rc;
+  return 0;
+}
+}  // namespace tavsr
 
 extern "C" int tavsr_gemm_rowln(const tavsr_rowln_args* a, void* stream) {
   TAVSR_REQUIRE(a != nullptr && a->struct_size == static_cast<int>(sizeof(tavsr_rowln_args)),
@@ -231,51 +267,30 @@ extern "C" int tavsr_gemm_rowln(const tavsr_rowln_args* a, void* stream) {
   const bool dual = a->x2 != nullptr;
   TAVSR_REQUIRE(!dual || (a->rowscale1 && a->rowscale2 && a->rows_per_seg > 0),
                 "rowln: dual mode needs rowscale1/2 and rows_per_seg");
-  TAVSR_REQUIRE(!(a->ln0_g && !a->ln0_b) && !(a->lnA_g && !(a->lnA_b && a->out_lnA)) &&
-                    !(a->lnB_g && !(a->lnB_b && a->out_lnB)),
-                "rowln: LayerNorm stages need gamma, beta and an output");
-  TAVSR_REQUIRE(!a->dots_out || (a->dot1 && a->dot2), "rowln: dots_out needs dot1 and dot2");
-  TAVSR_REQUIRE(!a->residual || a->ldr % 4 == 0, "rowln: residual pitch must be a multiple of 4");
   GemmParams p;
   memset(&p, 0, sizeof(p));
+  int rc;
+  if ((rc = fill_rowln_epilogue(p, a, "rowln"))) return rc;
   const int ctas = g_debug[3] == 1 ? 1 : 2;
-  p.M = a->M; p.N = 256; p.K = a->K;
+  p.K = a->K;
   p.num_m_tiles = (a->M + 128 * ctas - 1) / (128 * ctas);
   p.num_n_tiles = 1;
+  p.rowscale1 = a->rowscale1; p.rowscale2 = a->rowscale2; p.rows_per_seg = a->rows_per_seg;
   // split-K over two CTA pairs when the row tiles alone would leave >= half of the SMs idle
-  if (!dual && ctas == 2 && a->workspace != nullptr && g_debug[4] == 0 && a->K >= 1024 &&
+  // (measured slower than the unsplit kernel at M = 8000 in round 1 - the fused FFN kernel is the
+  // real fix for K = 2048 - so it is opt-in: g_debug[4] = 1)
+  if (!dual && ctas == 2 && a->workspace != nullptr && g_debug[4] == 1 && a->K >= 1024 &&
       a->K % 64 == 0 && 2 * p.num_m_tiles <= num_sms() / 2 &&
       static_cast<size_t>(a->workspace_bytes) >= tavsr_rowln_workspace_bytes(a->M)) {
     p.num_n_tiles = 2;
-    const size_t rows = static_cast<size_t>(p.num_m_tiles) * 256;
-    p.partial = static_cast<float*>(a->workspace);
-    p.flags = reinterpret_cast<unsigned int*>(static_cast<char*>(a->workspace) + rows * 256 * 4);
+    // flag words live at a FIXED offset (start of the scratch) so that calls with different M
+    // never see an earlier call's partial sums where they expect zeroed flags
+    p.flags = static_cast<unsigned int*>(a->workspace);
+    p.partial = reinterpret_cast<float*>(static_cast<char*>(a->workspace) + 4096);
   }
-  p.bias = a->bias;
-  p.act = ACT_NONE;
-  p.round_c = a->round_main;
-  p.residual = a->residual; p.ldr = a->ldr; p.alpha = a->alpha;
-  p.rowscale1 = a->rowscale1; p.rowscale2 = a->rowscale2; p.rows_per_seg = a->rows_per_seg;
-  p.ln0_g = a->ln0_g; p.ln0_b = a->ln0_b;
-  p.lnA_g = a->lnA_g; p.lnA_b = a->lnA_b; p.lnB_g = a->lnB_g; p.lnB_b = a->lnB_b;
-  p.has_main = a->out_main != nullptr;
-  p.round_lnA = a->round_lnA; p.round_lnB = a->round_lnB;
-  p.dot1 = a->dot1; p.dot2 = a->dot2; p.dots_out = a->dots_out;
-  p.eps = a->eps;
-  p.eps0 = a->eps0;
-  int rc;
   if ((rc = make_tmap_2d(&p.tmA, a->x, 4, false, a->M, a->K, a->ldx, 128, 32))) return rc;
   if (dual && (rc = make_tmap_2d(&p.tmA2, a->x2, 4, false, a->M, a->K, a->ldx2, 128, 32))) return rc;
   if ((rc = make_tmap_2d(&p.tmB, a->w, 4, false, 256, a->K, a->ldw, 256 / ctas, 32))) return rc;
-  if (a->out_main &&
-      (rc = make_tmap_2d(&p.tmC, a->out_main, 4, false, a->M, 256, a->ld_main, 32, 32, false)))
-    return rc;
-  if (a->lnA_g &&
-      (rc = make_tmap_2d(&p.tmLnA, a->out_lnA, 4, false, a->M, 256, a->ld_lnA, 32, 32, false)))
-    return rc;
-  if (a->lnB_g &&
-      (rc = make_tmap_2d(&p.tmLnB, a->out_lnB, 4, false, a->M, 256, a->ld_lnB, 32, 32, false)))
-    return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (ctas == 2) {
     if (dual) return launch_gemm<true, 256, kModeRowLN, true, 2, 0>(p, s);

@@ -130,6 +130,204 @@ struct WarpStager {
   }
 };
 
+// ------------------------------------------------------------------------------------------------
+// Row-complete epilogue math, shared by the RowLN GEMM and the fused FFN kernel.  The calling warp
+// owns TMEM lanes [lane_off, +32) == output rows row0 .. row0+31 (one row per thread) and columns
+// [tacc, tacc+256) hold the finished fp32 accumulator (tacc2: second accumulator in dual mode).
+//   v0 = residual + alpha * (w1*acc + w2*acc2 + partial + bias);  v1 = LN0(v0) (optional)
+//   main = v1;  lnA / lnB = LayerNorm(v1);  dots = (v1.dot1, v1.dot2)
+// Values round-trip TMEM between passes (tcgen05.st), statistics are two-pass (mean, then centred
+// second moment) like torch's LayerNorm.
+// ------------------------------------------------------------------------------------------------
+template <bool kDual>
+__device__ __forceinline__ void rowln_finish(const GemmParams& p, const float* s_param,
+                                             uint32_t tacc, int row0, uint32_t lane,
+                                             WarpStager& stager, const float* part_row) {
+  const float* s_bias = s_param;
+  const float* s_g0 = s_param + 256;
+  const float* s_b0 = s_param + 512;
+  const float* s_gA = s_param + 768;
+  const float* s_bA = s_param + 1024;
+  const float* s_gB = s_param + 1280;
+  const float* s_bB = s_param + 1536;
+  const float* s_d1 = s_param + 1792;
+  const float* s_d2 = s_param + 2048;
+  const int m = row0 + static_cast<int>(lane);
+  const bool valid = m < p.M;
+  const bool has_ln0 = p.ln0_g != nullptr;
+  const bool has_lnA = p.lnA_g != nullptr;
+  const bool has_lnB = p.lnB_g != nullptr;
+  const bool any_ln = has_ln0 || has_lnA || has_lnB;
+  const bool has_dots = p.dots_out != nullptr;
+  const bool splitk = part_row != nullptr;
+  float w1 = 1.0f, w2 = 0.0f;
+  if (kDual) {
+    const int seg = (valid ? m : p.M - 1) / p.rows_per_seg;
+    w1 = p.rowscale1[seg];
+    w2 = p.rowscale2[seg];
+  }
+    // PASS A: v0 = residual + alpha * (combine(acc) + bias)
+    float sum = 0.0f, dd1 = 0.0f, dd2 = 0.0f;
+    for (int c = 0; c < 8; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tacc + c * 32, r);
+      float res[32];
+      if (p.residual != nullptr && valid) {
+        const float4* rp =
+            reinterpret_cast<const float4*>(p.residual + static_cast<long long>(m) * p.ldr + c * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 f = __ldg(rp + j);
+          res[4 * j] = f.x; res[4 * j + 1] = f.y; res[4 * j + 2] = f.z; res[4 * j + 3] = f.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) res[j] = 0.0f;
+      }
+      tmem_ld_wait();
+      float v[32];
+      if (kDual) {
+        uint32_t r2[32];
+        tmem_ld32(tacc + 256 + c * 32, r2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          v[j] = w1 * __uint_as_float(r[j]) + w2 * __uint_as_float(r2[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      }
+      if (splitk) {
+        const float4* pp = reinterpret_cast<const float4*>(part_row + c * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 f = __ldcg(pp + j);
+          v[4 * j] += f.x; v[4 * j + 1] += f.y; v[4 * j + 2] += f.z; v[4 * j + 3] += f.w;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        v[j] = res[j] + p.alpha * (v[j] + s_bias[c * 32 + j]);
+        sum += v[j];
+      }
+      if (any_ln) {
+        uint32_t w[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(v[j]);
+        tmem_st32(tacc + c * 32, w);
+      }
+      if (!has_ln0) {
+        if (has_dots) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            dd1 += v[j] * s_d1[c * 32 + j];
+            dd2 += v[j] * s_d2[c * 32 + j];
+          }
+        }
+        if (p.has_main) {
+          if (p.round_c) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
+          }
+          stager.store(&p.tmC, v, c * 32, row0);
+        }
+      }
+    }
+    if (any_ln) {
+      tmem_st_wait();
+      float mean = sum * (1.0f / 256.0f);
+      // PASS B: centred second moment of v0
+      float ss = 0.0f;
+      for (int c = 0; c < 8; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tacc + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float d = __uint_as_float(r[j]) - mean;
+          ss += d * d;
+        }
+      }
+      float rstd = rsqrtf(ss * (1.0f / 256.0f) + (has_ln0 ? p.eps0 : p.eps));
+      if (has_ln0) {
+        // PASS C: v1 = LN0(v0) -> TMEM, main output, dots, new sum
+        float sum1 = 0.0f;
+        for (int c = 0; c < 8; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tacc + c * 32, r);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v[j] = (__uint_as_float(r[j]) - mean) * rstd * s_g0[c * 32 + j] + s_b0[c * 32 + j];
+            sum1 += v[j];
+            r[j] = __float_as_uint(v[j]);
+          }
+          tmem_st32(tacc + c * 32, r);
+          if (has_dots) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              dd1 += v[j] * s_d1[c * 32 + j];
+              dd2 += v[j] * s_d2[c * 32 + j];
+            }
+          }
+          if (p.has_main) {
+            if (p.round_c) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
+            }
+            stager.store(&p.tmC, v, c * 32, row0);
+          }
+        }
+        tmem_st_wait();
+        mean = sum1 * (1.0f / 256.0f);
+        // PASS D: centred second moment of v1
+        ss = 0.0f;
+        for (int c = 0; c < 8; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tacc + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float d = __uint_as_float(r[j]) - mean;
+            ss += d * d;
+          }
+        }
+        rstd = rsqrtf(ss * (1.0f / 256.0f) + p.eps);
+      }
+      // PASS E: LayerNorm outputs of v1
+      if (has_lnA || has_lnB) {
+        for (int c = 0; c < 8; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tacc + c * 32, r);
+          tmem_ld_wait();
+          float v[32];
+          if (has_lnA) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float y =
+                  (__uint_as_float(r[j]) - mean) * rstd * s_gA[c * 32 + j] + s_bA[c * 32 + j];
+              v[j] = p.round_lnA ? round_tf32(y) : y;
+            }
+            stager.store(&p.tmLnA, v, c * 32, row0);
+          }
+          if (has_lnB) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float y =
+                  (__uint_as_float(r[j]) - mean) * rstd * s_gB[c * 32 + j] + s_bB[c * 32 + j];
+              v[j] = p.round_lnB ? round_tf32(y) : y;
+            }
+            stager.store(&p.tmLnB, v, c * 32, row0);
+          }
+        }
+      }
+    }
+    if (has_dots && valid) {
+      reinterpret_cast<float2*>(p.dots_out)[m] = make_float2(dd1, dd2);
+    }
+}
+
 template <bool kTf32, int kBlockN, int kMode, bool kDual, int kCtas, int kAct>
 __global__ void __launch_bounds__(GemmCfg<kTf32, kBlockN, kMode, kDual, kCtas>::kThreads, 1)
 gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
@@ -344,28 +542,7 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
         }
       } else {
         // ---------------------------- row-complete epilogue ----------------------------------
-        const float* s_bias = s_param;
-        const float* s_g0 = s_param + 256;
-        const float* s_b0 = s_param + 512;
-        const float* s_gA = s_param + 768;
-        const float* s_bA = s_param + 1024;
-        const float* s_gB = s_param + 1280;
-        const float* s_bB = s_param + 1536;
-        const float* s_d1 = s_param + 1792;
-        const float* s_d2 = s_param + 2048;
         const int m = m0 + q * 32 + static_cast<int>(lane);
-        const bool valid = m < p.M;
-        const bool has_ln0 = p.ln0_g != nullptr;
-        const bool has_lnA = p.lnA_g != nullptr;
-        const bool has_lnB = p.lnB_g != nullptr;
-        const bool any_ln = has_ln0 || has_lnA || has_lnB;
-        const bool has_dots = p.dots_out != nullptr;
-        float w1 = 1.0f, w2 = 0.0f;
-        if (kDual) {
-          const int seg = (valid ? m : p.M - 1) / p.rows_per_seg;
-          w1 = p.rowscale1[seg];
-          w2 = p.rowscale2[seg];
-        }
         mbar_wait(&tfull_bar[as], aph);
         tc_fence_after_sync();
 
@@ -411,167 +588,7 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
           __syncwarp();
         }
         const float* part_row = splitk ? p.partial + static_cast<long long>(m) * 256 : nullptr;
-
-        // PASS A: v0 = residual + alpha * (combine(acc) + bias)
-        float sum = 0.0f, dd1 = 0.0f, dd2 = 0.0f;
-        for (int c = 0; c < 8; ++c) {
-          uint32_t r[32];
-          tmem_ld32(tacc + c * 32, r);
-          float res[32];
-          if (p.residual != nullptr && valid) {
-            const float4* rp =
-                reinterpret_cast<const float4*>(p.residual + static_cast<long long>(m) * p.ldr + c * 32);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 f = __ldg(rp + j);
-              res[4 * j] = f.x; res[4 * j + 1] = f.y; res[4 * j + 2] = f.z; res[4 * j + 3] = f.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) res[j] = 0.0f;
-          }
-          tmem_ld_wait();
-          float v[32];
-          if (kDual) {
-            uint32_t r2[32];
-            tmem_ld32(tacc + kBlockN + c * 32, r2);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              v[j] = w1 * __uint_as_float(r[j]) + w2 * __uint_as_float(r2[j]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          }
-          if (splitk) {
-            const float4* pp = reinterpret_cast<const float4*>(part_row + c * 32);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 f = __ldcg(pp + j);
-              v[4 * j] += f.x; v[4 * j + 1] += f.y; v[4 * j + 2] += f.z; v[4 * j + 3] += f.w;
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            v[j] = res[j] + p.alpha * (v[j] + s_bias[c * 32 + j]);
-            sum += v[j];
-          }
-          if (any_ln) {
-            uint32_t w[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(v[j]);
-            tmem_st32(tacc + c * 32, w);
-          }
-          if (!has_ln0) {
-            if (has_dots) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                dd1 += v[j] * s_d1[c * 32 + j];
-                dd2 += v[j] * s_d2[c * 32 + j];
-              }
-            }
-            if (p.has_main) {
-              if (p.round_c) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
-              }
-              stager.store(&p.tmC, v, c * 32, m0 + q * 32);
-            }
-          }
-        }
-        if (any_ln) {
-          tmem_st_wait();
-          float mean = sum * (1.0f / 256.0f);
-          // PASS B: centred second moment of v0
-          float ss = 0.0f;
-          for (int c = 0; c < 8; ++c) {
-            uint32_t r[32];
-            tmem_ld32(tacc + c * 32, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float d = __uint_as_float(r[j]) - mean;
-              ss += d * d;
-            }
-          }
-          float rstd = rsqrtf(ss * (1.0f / 256.0f) + (has_ln0 ? p.eps0 : p.eps));
-          if (has_ln0) {
-            // PASS C: v1 = LN0(v0) -> TMEM, main output, dots, new sum
-            float sum1 = 0.0f;
-            for (int c = 0; c < 8; ++c) {
-              uint32_t r[32];
-              tmem_ld32(tacc + c * 32, r);
-              tmem_ld_wait();
-              float v[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                v[j] = (__uint_as_float(r[j]) - mean) * rstd * s_g0[c * 32 + j] + s_b0[c * 32 + j];
-                sum1 += v[j];
-                r[j] = __float_as_uint(v[j]);
-              }
-              tmem_st32(tacc + c * 32, r);
-              if (has_dots) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  dd1 += v[j] * s_d1[c * 32 + j];
-                  dd2 += v[j] * s_d2[c * 32 + j];
-                }
-              }
-              if (p.has_main) {
-                if (p.round_c) {
-#pragma unroll
-                  for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
-                }
-                stager.store(&p.tmC, v, c * 32, m0 + q * 32);
-              }
-            }
-            tmem_st_wait();
-            mean = sum1 * (1.0f / 256.0f);
-            // PASS D: centred second moment of v1
-            ss = 0.0f;
-            for (int c = 0; c < 8; ++c) {
-              uint32_t r[32];
-              tmem_ld32(tacc + c * 32, r);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float d = __uint_as_float(r[j]) - mean;
-                ss += d * d;
-              }
-            }
-            rstd = rsqrtf(ss * (1.0f / 256.0f) + p.eps);
-          }
-          // PASS E: LayerNorm outputs of v1
-          if (has_lnA || has_lnB) {
-            for (int c = 0; c < 8; ++c) {
-              uint32_t r[32];
-              tmem_ld32(tacc + c * 32, r);
-              tmem_ld_wait();
-              float v[32];
-              if (has_lnA) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  const float y =
-                      (__uint_as_float(r[j]) - mean) * rstd * s_gA[c * 32 + j] + s_bA[c * 32 + j];
-                  v[j] = p.round_lnA ? round_tf32(y) : y;
-                }
-                stager.store(&p.tmLnA, v, c * 32, m0 + q * 32);
-              }
-              if (has_lnB) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  const float y =
-                      (__uint_as_float(r[j]) - mean) * rstd * s_gB[c * 32 + j] + s_bB[c * 32 + j];
-                  v[j] = p.round_lnB ? round_tf32(y) : y;
-                }
-                stager.store(&p.tmLnB, v, c * 32, m0 + q * 32);
-              }
-            }
-          }
-        }
-        if (has_dots && valid) {
-          reinterpret_cast<float2*>(p.dots_out)[m] = make_float2(dd1, dd2);
-        }
+        rowln_finish<kDual>(p, s_param, tacc, m0 + q * 32, lane, stager, part_row);
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) { if (kPair) mbar_arrive_leader(&tempty_bar[as]); else mbar_arrive(&tempty_bar[as]); }

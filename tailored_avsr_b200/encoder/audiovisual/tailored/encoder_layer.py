@@ -69,17 +69,13 @@ class TailoredEncoderLayer(torch.nn.Module):
         # shared macaron FFN over both streams; per-stream branch norms differ -> plain output, then
         # the stream-specific LayerNorm is fused as lnA of two half-height launches below.
         x_a = new2()
-        h = ops.gemm_bias_act(xn, self.feed_forward_macaron.w_1.weight,
-                              self.feed_forward_macaron.w_1.bias,
-                              act=engine.act_code(self.feed_forward_macaron.activation_type))
         xb_in = new2()  # per-stream branch input (its own LayerNorm)
-        w2 = self.feed_forward_macaron.w_2
         for s, tag in enumerate(("acoustic", "visual")):
             norm = getattr(self, f"{tag}_norm_mha", None) if getattr(self, f"{tag}_attn") is not None \
                 else getattr(self, f"{tag}_norm_cgmlp")
             sl = slice(s * M, (s + 1) * M)
-            ops.gemm_rowln(h[sl], w2.weight, w2.bias, residual=x[sl], alpha=0.5, out_main=x_a[sl],
-                           lnA=(norm.weight, norm.bias), out_lnA=xb_in[sl])
+            engine.ffn_block(x[sl], xn[sl], self.feed_forward_macaron, out_main=x_a[sl],
+                             lnA=(norm.weight, norm.bias), out_lnA=xb_in[sl])
         x_b = new2()
         xf = new2()
         lnF = (self.norm_ff.weight, self.norm_ff.bias)

@@ -13,11 +13,11 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SWISH, DT_TF32, RowLNArgs, check
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SWISH, DT_TF32, FfnArgs, RowLNArgs, check
 
 __all__ = [
     "ACT_NONE", "ACT_SWISH", "ACT_GELU", "ACT_RELU",
-    "gemm_bias_act", "gemm_rowln", "layernorm", "relpos_attn", "csgu", "merge_weights",
+    "gemm_bias_act", "gemm_rowln", "ffn_fused", "layernorm", "relpos_attn", "csgu", "merge_weights",
     "ctc_head", "ctc_loss", "ctc_greedy", "ctc_prefix_score", "launch_count",
 ]
 
@@ -106,34 +106,11 @@ def gemm_bias_act(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]
     return out
 
 
-@_profiled
-def gemm_rowln(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
-               x2: Optional[torch.Tensor] = None,
-               rowscale: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, rows_per_seg: int = 0,
-               residual: Optional[torch.Tensor] = None, alpha: float = 1.0,
-               ln0: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, eps0: float = 1e-12,
-               out_main: Optional[torch.Tensor] = None, round_main: bool = False,
-               lnA: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
-               out_lnA: Optional[torch.Tensor] = None, round_lnA: bool = False,
-               lnB: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
-               out_lnB: Optional[torch.Tensor] = None, round_lnB: bool = False,
-               eps: float = 1e-12,
-               dots: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
-               dots_out: Optional[torch.Tensor] = None) -> None:
-    """Row-complete N=256 GEMM with fused residual / LayerNorm / row-dot epilogue (tavsr_gemm_rowln)."""
-    _chk2d(x, "x")
-    _chk2d(w, "w")
-    a = RowLNArgs()
+def _fill_rowln(a: RowLNArgs, M: int, bias, residual, alpha, ln0, eps0, out_main, round_main, lnA,
+                out_lnA, round_lnA, lnB, out_lnB, round_lnB, eps, dots, dots_out) -> None:
     a.struct_size = ctypes.sizeof(RowLNArgs)
-    a.M, a.K = x.shape
+    a.M = M
     a.dtype = DT_TF32
-    a.x, a.ldx = x.data_ptr(), x.stride(0)
-    if x2 is not None:
-        _chk2d(x2, "x2")
-        a.x2, a.ldx2 = x2.data_ptr(), x2.stride(0)
-        a.rowscale1, a.rowscale2 = rowscale[0].data_ptr(), rowscale[1].data_ptr()
-        a.rows_per_seg = rows_per_seg
-    a.w, a.ldw = w.data_ptr(), w.stride(0)
     a.bias = _p(bias)
     if residual is not None:
         _chk2d(residual, "residual")
@@ -160,10 +137,69 @@ def gemm_rowln(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = 
     if dots is not None:
         a.dot1, a.dot2 = dots[0].data_ptr(), dots[1].data_ptr()
         a.dots_out = dots_out.data_ptr()
+
+
+@_profiled
+def gemm_rowln(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
+               x2: Optional[torch.Tensor] = None,
+               rowscale: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, rows_per_seg: int = 0,
+               residual: Optional[torch.Tensor] = None, alpha: float = 1.0,
+               ln0: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, eps0: float = 1e-12,
+               out_main: Optional[torch.Tensor] = None, round_main: bool = False,
+               lnA: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+               out_lnA: Optional[torch.Tensor] = None, round_lnA: bool = False,
+               lnB: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+               out_lnB: Optional[torch.Tensor] = None, round_lnB: bool = False,
+               eps: float = 1e-12,
+               dots: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+               dots_out: Optional[torch.Tensor] = None) -> None:
+    """Row-complete N=256 GEMM with fused residual / LayerNorm / row-dot epilogue (tavsr_gemm_rowln)."""
+    _chk2d(x, "x")
+    _chk2d(w, "w")
+    a = RowLNArgs()
+    _fill_rowln(a, x.shape[0], bias, residual, alpha, ln0, eps0, out_main, round_main, lnA, out_lnA,
+                round_lnA, lnB, out_lnB, round_lnB, eps, dots, dots_out)
+    a.K = x.shape[1]
+    a.x, a.ldx = x.data_ptr(), x.stride(0)
+    if x2 is not None:
+        _chk2d(x2, "x2")
+        a.x2, a.ldx2 = x2.data_ptr(), x2.stride(0)
+        a.rowscale1, a.rowscale2 = rowscale[0].data_ptr(), rowscale[1].data_ptr()
+        a.rows_per_seg = rows_per_seg
+    a.w, a.ldw = w.data_ptr(), w.stride(0)
     if x2 is None and a.K >= 1024:
         ws = _splitk_workspace(x.device, a.M)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
     check(_lib.load().tavsr_gemm_rowln(ctypes.byref(a), _stream()), "tavsr_gemm_rowln")
+
+
+@_profiled
+def ffn_fused(xn: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor,
+              b2: Optional[torch.Tensor], act: int, *,
+              residual: Optional[torch.Tensor] = None, alpha: float = 1.0,
+              ln0: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, eps0: float = 1e-12,
+              out_main: Optional[torch.Tensor] = None, round_main: bool = False,
+              lnA: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+              out_lnA: Optional[torch.Tensor] = None, round_lnA: bool = False,
+              lnB: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+              out_lnB: Optional[torch.Tensor] = None, round_lnB: bool = False,
+              eps: float = 1e-12) -> None:
+    """residual + alpha * (act(xn @ w1.T + b1) @ w2.T + b2) with the row-complete LayerNorm epilogue;
+    the hidden activation stays on chip (tavsr_ffn_fused)."""
+    _chk2d(xn, "xn")
+    _chk2d(w1, "w1")
+    _chk2d(w2, "w2")
+    a = FfnArgs()
+    a.struct_size = ctypes.sizeof(FfnArgs)
+    a.hidden = w1.shape[0]
+    a.act = act
+    a.xn, a.ldxn = xn.data_ptr(), xn.stride(0)
+    a.w1, a.ldw1 = w1.data_ptr(), w1.stride(0)
+    a.b1 = _p(b1)
+    a.w2, a.ldw2 = w2.data_ptr(), w2.stride(0)
+    _fill_rowln(a.ep, xn.shape[0], b2, residual, alpha, ln0, eps0, out_main, round_main, lnA, out_lnA,
+                round_lnA, lnB, out_lnB, round_lnB, eps, None, None)
+    check(_lib.load().tavsr_ffn_fused(ctypes.byref(a), _stream()), "tavsr_ffn_fused")
 
 
 @_profiled

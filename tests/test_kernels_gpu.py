@@ -296,6 +296,8 @@ def test_gemm_rowln_split_k_matches_unsplit(M, K):
     """The split-K path (taken when few row tiles leave SMs idle) must agree with the reference
     product and leave its flag words re-armed: run it twice back to back."""
     ops = _ops()
+    from tailored_avsr_b200 import _lib
+    _lib.load().tavsr_debug_set(4, 1)  # split-K is opt-in (see gemm_sm100.cu)
     g = torch.Generator().manual_seed(M ^ K)
     x = torch.randn(M, K, generator=g).to(DEV)
     w = (torch.randn(256, K, generator=g) / math.sqrt(K)).to(DEV)
@@ -310,5 +312,41 @@ def test_gemm_rowln_split_k_matches_unsplit(M, K):
         oA = torch.empty(M, 256, device=DEV)
         ops.gemm_rowln(x, w, b, residual=res, alpha=0.5, ln0=(g0, b0), out_main=main, lnA=(gA, bA),
                        out_lnA=oA)
-        assert rel_fro(main, v1) < 3e-3
-        assert rel_fro(oA, want) < 3e-3
+        e1, e2 = rel_fro(main, v1), rel_fro(oA, want)
+        if e1 >= 3e-3 or e2 >= 3e-3:
+            _lib.load().tavsr_debug_set(4, 0)
+        assert e1 < 3e-3 and e2 < 3e-3, (e1, e2)
+    _lib.load().tavsr_debug_set(4, 0)
+
+
+@pytest.mark.parametrize("M", [128, 8000, 1992, 77, 333])
+@pytest.mark.parametrize("variant", ["macaron", "final"])
+def test_ffn_fused(M, variant):
+    """Fused FFN (hidden on chip, 2-CTA hidden split + DSMEM reduction) vs fp64."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(M + len(variant))
+    xn = torch.randn(M, 256, generator=g).to(DEV)
+    x = torch.randn(M, 256, generator=g).to(DEV)
+    w1 = (torch.randn(2048, 256, generator=g) / 16).to(DEV)
+    b1 = torch.randn(2048, generator=g).to(DEV) * 0.1
+    w2 = (torch.randn(256, 2048, generator=g) / 45).to(DEV)
+    b2 = torch.randn(256, generator=g).to(DEV) * 0.1
+    g0, b0, gA, bA, gB, bB = [torch.randn(256, generator=g).to(DEV) for _ in range(6)]
+    h = (xn.double() @ w1.double().t() + b1.double())
+    h = h * torch.sigmoid(h)
+    v0 = x.double() + 0.5 * (h @ w2.double().t() + b2.double())
+    main = torch.empty(M, 256, device=DEV)
+    oA = torch.empty(M, 256, device=DEV)
+    oB = torch.empty(M, 256, device=DEV)
+    if variant == "macaron":
+        ops.ffn_fused(xn, w1, b1, w2, b2, 1, residual=x, alpha=0.5, out_main=main, lnA=(gA, bA),
+                      out_lnA=oA, lnB=(gB, bB), out_lnB=oB)
+        assert rel_fro(main, v0) < 2e-3, rel_fro(main, v0)
+        assert rel_fro(oA, _ln(v0, gA.double(), bA.double(), 1e-12)) < 3e-3
+        assert rel_fro(oB, _ln(v0, gB.double(), bB.double(), 1e-12)) < 3e-3
+    else:
+        ops.ffn_fused(xn, w1, b1, w2, b2, 1, residual=x, alpha=0.5, ln0=(g0, b0), out_main=main,
+                      lnA=(gA, bA), out_lnA=oA)
+        v1 = _ln(v0, g0.double(), b0.double(), 1e-12)
+        assert rel_fro(main, v1) < 3e-3, rel_fro(main, v1)
+        assert rel_fro(oA, _ln(v1, gA.double(), bA.double(), 1e-12)) < 3e-3

@@ -52,6 +52,13 @@ if which in ("gemm_merge", "all"):
     o1, o2 = (torch.empty(M, 256, device=DEV) for _ in range(2))
     run(lambda: ops.gemm_rowln(x1, w, b, x2=x2, rowscale=(w1, 1 - w1), rows_per_seg=T, residual=res,
                                out_main=o1, lnA=(gA, gA), out_lnA=o2))
+if which in ("ffn", "all"):
+    xn, x = rn(M, 256), rn(M, 256)
+    w1, b1, w2, b2 = rn(2048, 256) / 16, rn(2048), rn(256, 2048) / 45, rn(256)
+    gA = rn(256)
+    o1, o2, o3 = (torch.empty(M, 256, device=DEV) for _ in range(3))
+    run(lambda: ops.ffn_fused(xn, w1, b1, w2, b2, 1, residual=x, alpha=0.5, out_main=o1, lnA=(gA, gA),
+                              out_lnA=o2, lnB=(gA, gA), out_lnB=o3))
 if which in ("csgu", "all"):
     h, ng = rn(M, 2048), rn(1024)
     cw = rn(1024, 31)
