@@ -107,17 +107,37 @@ ctc_head_kernel(const float* __restrict__ hs, long long ldh, const float* __rest
 // contiguous chunks of kC states, so s-1 / s-2 neighbours are mostly in-thread and the chunk
 // boundary is crossed with two warp shuffles per time step.
 // ------------------------------------------------------------------------------------------------
-// log-sum-exp on the SFU (ex2 / lg2): the arguments are <= 0 and the sum lies in [1, 3], where
-// __expf / __logf are accurate to ~1e-7 absolute — far inside the 1e-4 relative loss budget.
+// The recursions run in the BASE-2 log domain (alpha2 = alpha / ln 2): a log-sum-exp is then
+// 3 FADD + 3 ex2 + 2 FADD + lg2 + FADD with no multiplies, and "log zero" is the finite kNeg
+// instead of -inf so no branch or NaN guard is needed (kNeg + anything finite stays ~kNeg, and
+// ex2(kNeg - m) == 0).  The single warp that owns an utterance is issue-bound, so instruction
+// count per lattice state is what sets the speed of this kernel.
+constexpr float kNeg = -1e30f;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2f(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lse2_b2(float a, float b) {
+  const float m = fmaxf(a, b);
+  return m + lg2f(ex2f(a - m) + ex2f(b - m));
+}
+__device__ __forceinline__ float lse3_b2(float a, float b, float c) {
+  const float m = fmaxf(fmaxf(a, b), c);
+  return m + lg2f(ex2f(a - m) + ex2f(b - m) + ex2f(c - m));
+}
+// natural-log versions used by the prefix scorer (logzero = -1e10 there, espnet's constant)
 __device__ __forceinline__ float lse2(float a, float b) {
   const float m = fmaxf(a, b);
-  if (m == -INFINITY) return -INFINITY;
   return m + __logf(__expf(a - m) + __expf(b - m));
-}
-__device__ __forceinline__ float lse3(float a, float b, float c) {
-  const float m = fmaxf(fmaxf(a, b), c);
-  if (m == -INFINITY) return -INFINITY;
-  return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
 }
 
 template <int kC>
@@ -127,7 +147,7 @@ ctc_loss_kernel(const float* __restrict__ logp, const int64_t* __restrict__ targ
                 const int32_t* __restrict__ tlens, float* __restrict__ nll_out,
                 float* __restrict__ grad, float gscale, float* __restrict__ alpha_ws, int B, int T,
                 int V, int Lmax, int zero_infinity) {
-  __shared__ float s_row[4][2][kVPad];   // per warp, double-buffered log-prob row
+  __shared__ float s_row[4][2][kVPad];   // per warp, double-buffered log2-prob row
   __shared__ float s_occ[4][kVPad];
   __shared__ float s_fin[4][2];
   const int warp = threadIdx.x >> 5;
@@ -149,6 +169,7 @@ ctc_loss_kernel(const float* __restrict__ logp, const int64_t* __restrict__ targ
   int lab[kC];
   bool skip_in[kC];   // transition s-2 -> s allowed
   bool skip_out[kC];  // transition s -> s+2 allowed
+  bool live[kC];      // s < S
 #pragma unroll
   for (int i = 0; i < kC; ++i) {
     const int s = lane * kC + i;
@@ -162,10 +183,12 @@ ctc_loss_kernel(const float* __restrict__ logp, const int64_t* __restrict__ targ
     lab[i] = (l >= 0 && l < V) ? l : 0;
     skip_in[i] = si;
     skip_out[i] = so;
+    live[i] = s < S;
   }
 
   // log-prob rows are prefetched one time step ahead into registers (fetch) and published to the
-  // warp through shared memory (commit), so the global-load latency is off the serial chain.
+  // warp through shared memory (commit, converted to base 2), so the global-load latency is off
+  // the serial chain.
   float pre0 = 0.f, pre1 = 0.f;
   auto fetch = [&](int t) {
     if (t >= 0 && t < Tb) {
@@ -174,8 +197,8 @@ ctc_loss_kernel(const float* __restrict__ logp, const int64_t* __restrict__ targ
     }
   };
   auto commit = [&](int buf) {
-    if (lane < V) s_row[warp][buf][lane] = pre0;
-    if (lane + 32 < V) s_row[warp][buf][lane + 32] = pre1;
+    if (lane < V) s_row[warp][buf][lane] = pre0 * kLog2e;
+    if (lane + 32 < V) s_row[warp][buf][lane + 32] = pre1 * kLog2e;
   };
 
   float nll = INFINITY;
@@ -189,7 +212,7 @@ ctc_loss_kernel(const float* __restrict__ logp, const int64_t* __restrict__ targ
 #pragma unroll
     for (int i = 0; i < kC; ++i) {
       const int s = lane * kC + i;
-      a[i] = (s < S && s < 2) ? s_row[warp][0][lab[i]] : -INFINITY;
+      a[i] = (s < S && s < 2) ? s_row[warp][0][lab[i]] : kNeg;
       if (aws && s < S) aws[s] = a[i];
     }
     for (int t = 1; t < Tb; ++t) {
@@ -199,17 +222,17 @@ ctc_loss_kernel(const float* __restrict__ logp, const int64_t* __restrict__ targ
       // neighbours from the previous lane
       float pm1 = __shfl_up_sync(0xffffffffu, a[kC - 1], 1);
       float pm2 = __shfl_up_sync(0xffffffffu, a[kC - 2], 1);
-      if (lane == 0) { pm1 = -INFINITY; pm2 = -INFINITY; }
+      if (lane == 0) { pm1 = kNeg; pm2 = kNeg; }
       __syncwarp();
       float n[kC];
 #pragma unroll
       for (int i = 0; i < kC; ++i) {
-        const int s = lane * kC + i;
         const float x1 = i >= 1 ? a[i - 1] : pm1;
         // s-2 neighbour: in-thread for i >= 2, else the previous lane's last / second-to-last state
-        const float two = skip_in[i] ? (i >= 2 ? a[i - 2] : (i == 1 ? pm1 : pm2)) : -INFINITY;
-        const float v = lse3(a[i], x1, two);
-        n[i] = s < S ? v + s_row[warp][buf][lab[i]] : -INFINITY;
+        const float x2 = i >= 2 ? a[i - 2] : (i == 1 ? pm1 : pm2);
+        const float two = skip_in[i] ? x2 : kNeg;
+        const float v = lse3_b2(a[i], x1, two) + s_row[warp][buf][lab[i]];
+        n[i] = live[i] ? v : kNeg;
       }
 #pragma unroll
       for (int i = 0; i < kC; ++i) {
@@ -220,7 +243,7 @@ ctc_loss_kernel(const float* __restrict__ logp, const int64_t* __restrict__ targ
       __syncwarp();
     }
     // final: logaddexp(alpha[S-1], alpha[S-2])
-    if (lane == 0) { s_fin[warp][0] = -INFINITY; s_fin[warp][1] = -INFINITY; }
+    if (lane == 0) { s_fin[warp][0] = kNeg; s_fin[warp][1] = kNeg; }
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < kC; ++i) {
@@ -229,7 +252,8 @@ ctc_loss_kernel(const float* __restrict__ logp, const int64_t* __restrict__ targ
       if (S >= 2 && s == S - 2) s_fin[warp][1] = a[i];
     }
     __syncwarp();
-    nll = -lse2(s_fin[warp][0], s_fin[warp][1]);
+    const float fin = lse2_b2(s_fin[warp][0], s_fin[warp][1]);
+    nll = fin < -1e29f ? INFINITY : -fin * kLn2;
   } else {
     nll = (L == 0) ? 0.f : INFINITY;
   }
@@ -243,12 +267,14 @@ ctc_loss_kernel(const float* __restrict__ logp, const int64_t* __restrict__ targ
     return;
   }
   for (int i = Tb * V + lane; i < T * V; i += 32) gb[i] = 0.f;
+  const float nll2 = nll * kLog2e;
   float bt[kC];
   float apre[kC];  // alpha_t prefetched one step ahead of the beta recursion
 #pragma unroll
   for (int i = 0; i < kC; ++i) {
     const int s = lane * kC + i;
-    apre[i] = s < S ? aws[static_cast<long long>(Tb - 1) * Sws + s] : -INFINITY;
+    apre[i] = s < S ? aws[static_cast<long long>(Tb - 1) * Sws + s] : kNeg;
+    bt[i] = kNeg;
   }
   fetch(Tb - 1);
   for (int t = Tb - 1; t >= 0; --t) {
@@ -256,12 +282,9 @@ ctc_loss_kernel(const float* __restrict__ logp, const int64_t* __restrict__ targ
     commit(buf);
     fetch(t - 1);
     if (lane < kVPad / 2) { s_occ[warp][lane] = 0.f; s_occ[warp][lane + 32] = 0.f; }
-    float np1 = 0.f, np2 = 0.f;
-    if (t < Tb - 1) {
-      np1 = __shfl_down_sync(0xffffffffu, bt[0], 1);
-      np2 = __shfl_down_sync(0xffffffffu, bt[1], 1);
-      if (lane == 31) { np1 = -INFINITY; np2 = -INFINITY; }
-    }
+    float np1 = __shfl_down_sync(0xffffffffu, bt[0], 1);
+    float np2 = __shfl_down_sync(0xffffffffu, bt[1], 1);
+    if (lane == 31) { np1 = kNeg; np2 = kNeg; }
     __syncwarp();
     float n[kC];
 #pragma unroll
@@ -269,21 +292,20 @@ ctc_loss_kernel(const float* __restrict__ logp, const int64_t* __restrict__ targ
       const int s = lane * kC + i;
       float v;
       if (t == Tb - 1) {
-        v = (s < S && s >= S - 2) ? 0.f : -INFINITY;
+        v = (s < S && s >= S - 2) ? 0.f : kNeg;
       } else {
         const float x1 = i + 1 < kC ? bt[i + 1] : np1;
-        const float two =
-            skip_out[i] ? (i + 2 < kC ? bt[i + 2] : (i + 2 == kC ? np1 : np2)) : -INFINITY;
-        v = lse3(bt[i], x1, two);
+        const float x2 = i + 2 < kC ? bt[i + 2] : (i + 2 == kC ? np1 : np2);
+        v = lse3_b2(bt[i], x1, skip_out[i] ? x2 : kNeg);
       }
-      n[i] = s < S ? v + s_row[warp][buf][lab[i]] : -INFINITY;
+      n[i] = live[i] ? v + s_row[warp][buf][lab[i]] : kNeg;
     }
 #pragma unroll
     for (int i = 0; i < kC; ++i) {
       bt[i] = n[i];
       const int s = lane * kC + i;
       if (s < S) {
-        const float e = expf(apre[i] + bt[i] + nll - s_row[warp][buf][lab[i]]);
+        const float e = ex2f(apre[i] + bt[i] + nll2 - s_row[warp][buf][lab[i]]);
         if (e > 0.f) atomicAdd(&s_occ[warp][lab[i]], e);
         if (t > 0) apre[i] = aws[static_cast<long long>(t - 1) * Sws + s];
       }
@@ -291,10 +313,10 @@ ctc_loss_kernel(const float* __restrict__ logp, const int64_t* __restrict__ targ
     __syncwarp();
     if (lane < V)
       gb[static_cast<long long>(t) * V + lane] =
-          gscale * (expf(s_row[warp][buf][lane]) - s_occ[warp][lane]);
+          gscale * (ex2f(s_row[warp][buf][lane]) - s_occ[warp][lane]);
     if (lane + 32 < V)
       gb[static_cast<long long>(t) * V + lane + 32] =
-          gscale * (expf(s_row[warp][buf][lane + 32]) - s_occ[warp][lane + 32]);
+          gscale * (ex2f(s_row[warp][buf][lane + 32]) - s_occ[warp][lane + 32]);
     __syncwarp();
   }
 }

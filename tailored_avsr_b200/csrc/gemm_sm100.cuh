@@ -94,7 +94,21 @@ __device__ __forceinline__ float apply_act(float x, int act_rt) {
   const int act = kAct >= 0 ? kAct : act_rt;
   switch (act) {
     case ACT_SWISH: return __fdividef(x, 1.0f + __expf(-x));
-    case ACT_GELU: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+    case ACT_GELU: {
+      // exact-erf GELU with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, i.e. at the fp32
+      // rounding level of the reference's erff) - 2 SFU ops + 8 FMA-pipe ops instead of erff's
+      // ~30-instruction branchy expansion; the epilogue warps are the bottleneck of this GEMM.
+      const float z = fabsf(x) * 0.70710678118654752440f;
+      const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+      float poly = fmaf(1.061405429f, t, -1.453152027f);
+      poly = fmaf(poly, t, 1.421413741f);
+      poly = fmaf(poly, t, -0.284496736f);
+      poly = fmaf(poly, t, 0.254829592f);
+      const float erfc_z = poly * t * __expf(-z * z);   // 1 - erf(z), z >= 0
+      // 0.5 * (1 + erf(x / sqrt 2)) without cancellation in the negative tail
+      const float cdf = x >= 0.f ? fmaf(-0.5f, erfc_z, 1.0f) : 0.5f * erfc_z;
+      return x * cdf;
+    }
     case ACT_RELU: return fmaxf(x, 0.0f);
     default: return x;
   }
