@@ -23,6 +23,20 @@ static int launch_ffn(const FfnParams& p, int m_tiles, cudaStream_t stream) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
+template <int kAct>
+static int launch_ffn2(const Ffn2Params& p, int m_units, cudaStream_t stream) {
+  auto kern = ffn_fused_pair_kernel<kAct>;
+  static bool configured = false;
+  if (!configured) {
+    TAVSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       ffn2::kSmemBytes));
+    configured = true;
+  }
+  kern<<<4 * m_units, ffn::kThreads, ffn2::kSmemBytes, stream>>>(p);
+  TAVSR_CUDA_OK(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
 }  // namespace tavsr
 
 using namespace tavsr;
@@ -34,9 +48,29 @@ extern "C" int tavsr_ffn_fused(const tavsr_ffn_args* a, void* stream) {
   TAVSR_REQUIRE(a->hidden == ffn::kHid, "ffn: only hidden = 2048 is built (got %d)", a->hidden);
   TAVSR_REQUIRE(a->xn && a->w1 && a->w2 && a->ep.M > 0, "ffn: xn, w1, w2 and M are required");
   TAVSR_REQUIRE(a->ep.x2 == nullptr, "ffn: dual operands are not supported");
+  int rc;
+  if (g_debug[5] == 0) {
+    // v2 (default): CTA pairs, cluster of 4
+    Ffn2Params q;
+    memset(&q, 0, sizeof(q));
+    if ((rc = fill_rowln_epilogue(q.ep, &a->ep, "ffn"))) return rc;
+    const int M2 = a->ep.M;
+    if ((rc = make_tmap_2d(&q.tmX, a->xn, 4, false, M2, ffn::kD, a->ldxn, 128, 32))) return rc;
+    if ((rc = make_tmap_2d(&q.tmW1, a->w1, 4, false, ffn::kHid, ffn::kD, a->ldw1, 64, 32))) return rc;
+    if ((rc = make_tmap_2d(&q.tmW2, a->w2, 4, false, ffn::kD, ffn::kHid, a->ldw2, 64, 32))) return rc;
+    q.b1 = a->b1;
+    q.act = a->act;
+    const int m_units = (M2 + 255) / 256;
+    cudaStream_t s2 = static_cast<cudaStream_t>(stream);
+    switch (a->act) {
+      case ACT_SWISH: return launch_ffn2<ACT_SWISH>(q, m_units, s2);
+      case ACT_RELU: return launch_ffn2<ACT_RELU>(q, m_units, s2);
+      case ACT_GELU: return launch_ffn2<ACT_GELU>(q, m_units, s2);
+      default: return launch_ffn2<ACT_NONE>(q, m_units, s2);
+    }
+  }
   FfnParams p;
   memset(&p, 0, sizeof(p));
-  int rc;
   if ((rc = fill_rowln_epilogue(p.ep, &a->ep, "ffn"))) return rc;
   const int M = a->ep.M;
   if ((rc = make_tmap_2d(&p.tmX, a->xn, 4, false, M, ffn::kD, a->ldxn, 128, 32))) return rc;

@@ -310,4 +310,283 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
   }
 }
 
+
+// ================================================================================================
+// v2: CTA pairs.  Cluster of 4 = 2 pairs (cta_group::2, 256 frames per cluster) x 2 hidden halves.
+// Each CTA keeps its own 128 frames of LN(x) resident; every weight unit is split across the pair
+// (64 rows = 8 KB per CTA), so the same 80 KB ring holds 10 units in flight instead of 5 and the
+// per-CTA weight traffic halves - v1 is bound by the TMA round trip with only 5 units in flight.
+// ================================================================================================
+namespace ffn2 {
+constexpr int kHalfUnit = 64 * 128;          // 8 KB: this CTA's half of a 128-row weight unit
+constexpr int kRing = 10;
+constexpr int kSmemBytes = 1024 + ffn::kXBytes + kRing * kHalfUnit + ffn::kParamFloats * 4 + 512;
+}  // namespace ffn2
+
+__device__ __forceinline__ void umma_ts_tf32_2sm(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+struct alignas(64) Ffn2Params {
+  CUtensorMap tmX;   // LN(x):  (256 inner, M rows),     box {32, 128}
+  CUtensorMap tmW1;  // W1:     (256 inner, 2048 rows),  box {32, 64}
+  CUtensorMap tmW2;  // W2:     (2048 inner, 256 rows),  box {32, 64}
+  GemmParams ep;
+  const float* b1;
+  int act;
+};
+
+template <int kAct>
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(ffn::kThreads, 1)
+ffn_fused_pair_kernel(const __grid_constant__ Ffn2Params p) {
+  using namespace ffn;
+  constexpr int kRing2 = ffn2::kRing;
+  constexpr int kHU = ffn2::kHalfUnit;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* s_x = smem;                       // 8 x 16 KB, later: peer partial rows (64 KB)
+  uint8_t* s_ring = s_x + kXBytes;           // 10 x 8 KB, later: TMA-store staging
+  float* s_b1 = reinterpret_cast<float*>(s_ring + kRing2 * kHU);
+  float* s_param = s_b1 + kHidCta;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_param + 9 * 256);
+  uint64_t* w_full = bars;                   // [kRing2]  (leader's copy collects both halves)
+  uint64_t* w_empty = bars + kRing2;         // [kRing2]
+  uint64_t* x_full = bars + 2 * kRing2;      // [1]
+  uint64_t* h_full = x_full + 1;             // [2]
+  uint64_t* h_ready = h_full + 2;            // [2]  leader's copy, 8 arrivals (4 warps x 2 CTAs)
+  uint64_t* d_full = h_ready + 2;            // [1]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(d_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t pr = rank & 1u;             // rank inside the MMA pair (0 = leader)
+  const uint32_t hp = rank >> 1;             // hidden half owned by this pair
+  const uint16_t pair_mask = static_cast<uint16_t>(3u << (rank & ~1u));
+  const int m0 = static_cast<int>(blockIdx.x >> 2) * 256 + static_cast<int>(pr) * 128;
+  const int hid0 = static_cast<int>(hp) * kHidCta;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmX);
+    tma_prefetch_desc(&p.tmW1);
+    tma_prefetch_desc(&p.tmW2);
+    for (int i = 0; i < kRing2; ++i) {
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_empty[i], 1);
+    }
+    mbar_init(x_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&h_full[i], 1);
+      mbar_init(&h_ready[i], 8);
+    }
+    mbar_init(d_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(s_tmem, 512);
+    tmem_relinquish_2sm();
+  }
+  if (warp >= 2) {
+    const float* srcs[9] = {p.ep.bias, p.ep.ln0_g, p.ep.ln0_b, p.ep.lnA_g, p.ep.lnA_b,
+                            p.ep.lnB_g, p.ep.lnB_b, p.ep.dot1, p.ep.dot2};
+    for (int v = 0; v < 9; ++v)
+      for (int i = threadIdx.x - 64; i < 256; i += 128)
+        s_param[v * 256 + i] = srcs[v] ? srcs[v][i] : 0.0f;
+    for (int i = threadIdx.x - 64; i < kHidCta; i += 128) s_b1[i] = p.b1 ? p.b1[hid0 + i] : 0.0f;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();  // every CTA's barriers are initialised before remote arrives / TMA signals
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      if (pr == 0) mbar_arrive_expect_tx(x_full, 2 * kXBytes);
+      for (int kb = 0; kb < 8; ++kb)
+        tma_load_2d_2sm(s_x + kb * kUnitBytes, &p.tmX, x_full, kb * 32, m0);
+      int s = 0;
+      uint32_t ph = 0;
+      auto next_slot = [&]() -> uint8_t* {
+        mbar_wait(&w_empty[s], ph ^ 1);
+        if (pr == 0) mbar_arrive_expect_tx(&w_full[s], 2 * kHU);
+        return s_ring + s * kHU;
+      };
+      auto advance = [&]() { if (++s == kRing2) { s = 0; ph ^= 1; } };
+      auto load_w1 = [&](int j) {
+        for (int kb = 0; kb < 8; ++kb) {
+          uint8_t* dst = next_slot();
+          tma_load_2d_2sm(dst, &p.tmW1, &w_full[s], kb * 32,
+                          hid0 + j * kChunk + static_cast<int>(pr) * 64);
+          advance();
+        }
+      };
+      auto load_w2 = [&](int j) {
+        for (int kb = 0; kb < 4; ++kb)
+          for (int nh = 0; nh < 2; ++nh) {
+            uint8_t* dst = next_slot();
+            tma_load_2d_2sm(dst, &p.tmW2, &w_full[s], hid0 + j * kChunk + kb * 32,
+                            nh * 128 + static_cast<int>(pr) * 64);
+            advance();
+          }
+      };
+      load_w1(0);
+      load_w1(1);
+      for (int j = 0; j < kNChunk; ++j) {
+        load_w2(j);
+        if (j + 2 < kNChunk) load_w1(j + 2);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer (pair leader) =========================
+    if (lane == 0 && pr == 0) {
+      constexpr uint32_t idesc = umma_idesc(UMMA_FMT_TF32, 256, 128);
+      int s = 0;
+      uint32_t ph = 0;
+      auto advance = [&]() { if (++s == kRing2) { s = 0; ph ^= 1; } };
+      const uint32_t x_addr = smem_u32(s_x);
+      auto gemm1 = [&](int j) {
+        const uint32_t d = tmem_base + kColH + (j & 1) * kChunk;
+        for (int kb = 0; kb < 8; ++kb) {
+          mbar_wait(&w_full[s], ph);
+          tc_fence_after_sync();
+          const uint64_t a_desc = umma_desc_kmajor_sw128(x_addr + kb * kUnitBytes);
+          const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(s_ring + s * kHU));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_ss_2sm<true>(d, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          umma_commit_2sm(&w_empty[s], pair_mask);
+          advance();
+        }
+        umma_commit_2sm(&h_full[j & 1], pair_mask);
+      };
+      auto gemm2 = [&](int j) {
+        const uint32_t a0 = tmem_base + kColH + (j & 1) * kChunk;
+        for (int kb = 0; kb < 4; ++kb)
+          for (int nh = 0; nh < 2; ++nh) {
+            mbar_wait(&w_full[s], ph);
+            tc_fence_after_sync();
+            const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(s_ring + s * kHU));
+            const uint32_t d = tmem_base + kColD2 + nh * 128;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_ts_tf32_2sm(d, a0 + kb * 32 + k * 8, b_desc + 2 * k, idesc,
+                               (j | kb | k) ? 1u : 0u);
+            umma_commit_2sm(&w_empty[s], pair_mask);
+            advance();
+          }
+      };
+      mbar_wait(x_full, 0);
+      tc_fence_after_sync();
+      gemm1(0);
+      gemm1(1);
+      for (int j = 0; j < kNChunk; ++j) {
+        mbar_wait(&h_ready[j & 1], (j >> 1) & 1);
+        tc_fence_after_sync();
+        gemm2(j);
+        if (j + 2 < kNChunk) gemm1(j + 2);
+      }
+      umma_commit_2sm(d_full, pair_mask);
+    }
+  } else {
+    // =============================== activation warps =======================================
+    const int q = warp & 3;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    for (int j = 0; j < kNChunk; ++j) {
+      mbar_wait(&h_full[j & 1], (j >> 1) & 1);
+      tc_fence_after_sync();
+      const uint32_t th = tmem_base + lane_off + kColH + (j & 1) * kChunk;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(th + c * 32, r);
+        tmem_ld_wait();
+        const float* bb = s_b1 + j * kChunk + c * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float x = apply_act<kAct>(__uint_as_float(r[i]) + bb[i], p.act);
+          r[i] = __float_as_uint(round_tf32(x));
+        }
+        tmem_st32(th + c * 32, r);
+      }
+      tmem_st_wait();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader_release(&h_ready[j & 1]);
+    }
+    mbar_wait(d_full, 0);
+    tc_fence_after_sync();
+  }
+
+  // ---- exchange partial outputs between the two pairs: CTA r <-> r^2, each finishes 64 rows ----
+  __syncthreads();
+  cluster_sync_all();
+  if (warp >= 2) {
+    const int q = warp & 3;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t td2 = tmem_base + lane_off + kColD2;
+    const int row_local = (q & 1) * 32 + static_cast<int>(lane);
+    if (static_cast<uint32_t>(q >> 1) != hp) {
+      const uint32_t base = mapa_cluster(smem_u32(s_x) + row_local * 1024, rank ^ 2u);
+      for (int c = 0; c < 8; ++c) {
+        uint32_t r[32];
+        tmem_ld32(td2 + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          st_cluster_v4(base + (((c * 8 + i) ^ (row_local & 7)) << 4),
+                        make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                    __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
+      }
+    }
+  }
+  cluster_sync_all();
+  if (warp >= 2) {
+    const int q = warp & 3;
+    if (static_cast<uint32_t>(q >> 1) == hp) {
+      const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+      const uint32_t td2 = tmem_base + lane_off + kColD2;
+      const int row_local = (q & 1) * 32 + static_cast<int>(lane);
+      const uint8_t* rrow = s_x + row_local * 1024;
+      for (int c = 0; c < 8; ++c) {
+        uint32_t r[32];
+        tmem_ld32(td2 + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 f = *reinterpret_cast<const float4*>(rrow + (((c * 8 + i) ^ (row_local & 7)) << 4));
+          r[4 * i] = __float_as_uint(__uint_as_float(r[4 * i]) + f.x);
+          r[4 * i + 1] = __float_as_uint(__uint_as_float(r[4 * i + 1]) + f.y);
+          r[4 * i + 2] = __float_as_uint(__uint_as_float(r[4 * i + 2]) + f.z);
+          r[4 * i + 3] = __float_as_uint(__uint_as_float(r[4 * i + 3]) + f.w);
+        }
+        tmem_st32(td2 + c * 32, r);
+      }
+      tmem_st_wait();
+      WarpStager stager{s_ring + (q & 1) * 8192, 0};
+      rowln_finish<false>(p.ep, s_param, td2, m0 + q * 32, lane, stager, nullptr);
+      stager.drain();
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();  // the pair's TMEM is freed together
+  tc_fence_after_sync();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
 }  // namespace tavsr

@@ -296,12 +296,22 @@ __device__ __forceinline__ void umma_ss_2sm(uint32_t d_tmem, uint64_t a_desc, ui
 }
 
 // Arrives on `bar` (same offset) in BOTH CTAs of the pair once the issued MMAs have retired.
-__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+// `pair_mask` = 0b11 << (cluster rank of the pair's leader): the multicast mask is indexed by
+// cluster rank, so in a 4-CTA cluster the second pair is 0b1100.
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t pair_mask = 3) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
       "[%0], %1;" ::"r"(smem_u32(bar)),
-      "h"(static_cast<uint16_t>(3))
+      "h"(pair_mask)
       : "memory");
+}
+
+// Release-ordered arrive on the leader CTA's copy of `bar` (used where the arrive publishes data
+// written by this thread, e.g. tcgen05.st results consumed by the leader's MMAs).
+__device__ __forceinline__ void mbar_arrive_leader_release(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(
+                   smem_u32(bar) & kPeerBitMask)
+               : "memory");
 }
 
 // ----------------------------------------------------------------------------------------------
