@@ -49,6 +49,7 @@ int tavsr_version(void);
 const char* tavsr_last_error(void);
 /* debug knobs (descriptor variants etc.); not part of the stable surface */
 int tavsr_debug_set(int key, int value);
+int tavsr_debug_set_ptr(void* device_buffer); /* kernel phase timestamps (tools/ only) */
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 long long tavsr_launch_count(void);
 

@@ -62,6 +62,7 @@ SIGNATURES = {
     "tavsr_version": (c_int, []),
     "tavsr_last_error": (c_char_p, []),
     "tavsr_debug_set": (c_int, [c_int, c_int]),
+    "tavsr_debug_set_ptr": (c_int, [c_void_p]),
     "tavsr_launch_count": (c_longlong, []),
     "tavsr_gemm_bias_act": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p,
                                     c_longlong, c_int, c_int, c_int, c_int, c_int, c_int,

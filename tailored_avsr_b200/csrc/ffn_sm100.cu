@@ -7,6 +7,7 @@
 
 namespace tavsr {
 extern std::atomic<long long> g_launches;
+extern void* g_debug_ptr;
 int fill_rowln_epilogue(GemmParams& p, const tavsr_rowln_args* a, const char* who);
 
 template <int kAct>
@@ -32,6 +33,21 @@ static int launch_ffn2(const Ffn2Params& p, int m_units, cudaStream_t stream) {
                                        ffn2::kSmemBytes));
     configured = true;
   }
+  if (g_debug[6]) {
+    int ncl = 0;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(4 * m_units);
+    cfg.blockDim = dim3(ffn::kThreads);
+    cfg.dynamicSmemBytes = ffn2::kSmemBytes;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg);
+    printf("ffn2: max active clusters of 4 = %d (err %d)\n", ncl, static_cast<int>(e));
+    g_debug[6] = 0;
+  }
   kern<<<4 * m_units, ffn::kThreads, ffn2::kSmemBytes, stream>>>(p);
   TAVSR_CUDA_OK(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -49,8 +65,9 @@ extern "C" int tavsr_ffn_fused(const tavsr_ffn_args* a, void* stream) {
   TAVSR_REQUIRE(a->xn && a->w1 && a->w2 && a->ep.M > 0, "ffn: xn, w1, w2 and M are required");
   TAVSR_REQUIRE(a->ep.x2 == nullptr, "ffn: dual operands are not supported");
   int rc;
-  if (g_debug[5] == 0) {
-    // v2 (default): CTA pairs, cluster of 4
+  if (g_debug[5] == 2) {
+    // v2 (opt-in, measured slower than v1 in round 1: its N=128 pair MMAs are issue-bound, see
+    // tools/mma_bench.cu): CTA pairs, cluster of 4
     Ffn2Params q;
     memset(&q, 0, sizeof(q));
     if ((rc = fill_rowln_epilogue(q.ep, &a->ep, "ffn"))) return rc;
@@ -60,6 +77,7 @@ extern "C" int tavsr_ffn_fused(const tavsr_ffn_args* a, void* stream) {
     if ((rc = make_tmap_2d(&q.tmW2, a->w2, 4, false, ffn::kD, ffn::kHid, a->ldw2, 64, 32))) return rc;
     q.b1 = a->b1;
     q.act = a->act;
+    q.dbg = reinterpret_cast<long long*>(g_debug_ptr);
     const int m_units = (M2 + 255) / 256;
     cudaStream_t s2 = static_cast<cudaStream_t>(stream);
     switch (a->act) {
@@ -78,6 +96,7 @@ extern "C" int tavsr_ffn_fused(const tavsr_ffn_args* a, void* stream) {
   if ((rc = make_tmap_2d(&p.tmW2, a->w2, 4, false, ffn::kD, ffn::kHid, a->ldw2, 128, 32))) return rc;
   p.b1 = a->b1;
   p.act = a->act;
+  p.dbg = reinterpret_cast<long long*>(g_debug_ptr);
   const int m_tiles = (M + 127) / 128;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (a->act) {

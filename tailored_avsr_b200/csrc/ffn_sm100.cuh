@@ -30,6 +30,7 @@ struct alignas(64) FfnParams {
   GemmParams ep;     // epilogue description: bias = b2, residual, alpha, ln0/lnA/lnB, tmC/tmLnA/tmLnB
   const float* b1;   // [2048]
   int act;
+  long long* dbg;    // optional [gridDim.x][8] phase timestamps (globaltimer ns)
 };
 
 namespace ffn {
@@ -60,6 +61,17 @@ __device__ __forceinline__ void umma_ts_tf32(uint32_t d_tmem, uint32_t a_tmem, u
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+
+__device__ __forceinline__ long long globaltimer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define FFN_STAMP(slot)                                                              \
+  do {                                                                               \
+    if (p.dbg != nullptr && threadIdx.x == 64)                                       \
+      p.dbg[static_cast<long long>(blockIdx.x) * 8 + (slot)] = globaltimer_ns();     \
+  } while (0)
 
 __device__ __forceinline__ uint32_t mapa_cluster(uint32_t local_addr, uint32_t cta) {
   uint32_t r;
@@ -130,6 +142,7 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *s_tmem;
+  FFN_STAMP(0);
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -225,6 +238,8 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
     for (int j = 0; j < kNChunk; ++j) {
       mbar_wait(&h_full[j & 1], (j >> 1) & 1);
       tc_fence_after_sync();
+      if (j == 0) FFN_STAMP(1);
+      if (j == 1) FFN_STAMP(6);
       const uint32_t th = tmem_base + lane_off + kColH + (j & 1) * kChunk;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -246,11 +261,13 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
     }
     mbar_wait(d_full, 0);  // every MMA of this CTA has retired: D2 final, s_x and s_ring free
     tc_fence_after_sync();
+    FFN_STAMP(2);
   }
 
   // ---- exchange the partial outputs across the cluster: CTA r finishes rows [64r, 64r+64) ----
   __syncthreads();     // reconverge the single-lane role loops before the aligned cluster barrier
   cluster_sync_all();  // both CTAs' MMAs are done -> both s_x regions may be overwritten
+  FFN_STAMP(3);
   if (warp >= 2) {
     const int q = warp & 3;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
@@ -273,6 +290,7 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
     }
   }
   cluster_sync_all();  // release/acquire: the peer's rows are visible in s_x
+  FFN_STAMP(4);
   if (warp >= 2) {
     const int q = warp & 3;
     if (static_cast<uint32_t>(q >> 1) == rank) {
@@ -303,6 +321,7 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
 
   tc_fence_before_sync();
   __syncthreads();
+  FFN_STAMP(5);
   tc_fence_after_sync();
   if (warp == 1) {
     __syncwarp();
@@ -342,6 +361,7 @@ struct alignas(64) Ffn2Params {
   GemmParams ep;
   const float* b1;
   int act;
+  long long* dbg;
 };
 
 template <int kAct>
@@ -408,6 +428,7 @@ ffn_fused_pair_kernel(const __grid_constant__ Ffn2Params p) {
   cluster_sync_all();  // every CTA's barriers are initialised before remote arrives / TMA signals
   tc_fence_after_sync();
   const uint32_t tmem_base = *s_tmem;
+  FFN_STAMP(0);
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -505,6 +526,8 @@ ffn_fused_pair_kernel(const __grid_constant__ Ffn2Params p) {
     for (int j = 0; j < kNChunk; ++j) {
       mbar_wait(&h_full[j & 1], (j >> 1) & 1);
       tc_fence_after_sync();
+      if (j == 0) FFN_STAMP(1);
+      if (j == 1) FFN_STAMP(6);
       const uint32_t th = tmem_base + lane_off + kColH + (j & 1) * kChunk;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -526,11 +549,13 @@ ffn_fused_pair_kernel(const __grid_constant__ Ffn2Params p) {
     }
     mbar_wait(d_full, 0);
     tc_fence_after_sync();
+    FFN_STAMP(2);
   }
 
   // ---- exchange partial outputs between the two pairs: CTA r <-> r^2, each finishes 64 rows ----
   __syncthreads();
   cluster_sync_all();
+  FFN_STAMP(3);
   if (warp >= 2) {
     const int q = warp & 3;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
@@ -551,6 +576,7 @@ ffn_fused_pair_kernel(const __grid_constant__ Ffn2Params p) {
     }
   }
   cluster_sync_all();
+  FFN_STAMP(4);
   if (warp >= 2) {
     const int q = warp & 3;
     if (static_cast<uint32_t>(q >> 1) == hp) {
@@ -581,6 +607,7 @@ ffn_fused_pair_kernel(const __grid_constant__ Ffn2Params p) {
 
   tc_fence_before_sync();
   __syncthreads();
+  FFN_STAMP(5);
   cluster_sync_all();  // the pair's TMEM is freed together
   tc_fence_after_sync();
   if (warp == 1) {

@@ -9,6 +9,7 @@ namespace tavsr {
 
 thread_local char g_last_error[512] = "";
 int g_debug[16] = {0};
+void* g_debug_ptr = nullptr;  // optional device buffer for kernel phase timestamps
 std::atomic<long long> g_launches{0};
 
 int num_sms() {
@@ -181,6 +182,10 @@ extern "C" int tavsr_debug_set(int key, int value) {
   return 0;
 }
 extern "C" long long tavsr_launch_count(void) { return g_launches.load(); }
+extern "C" int tavsr_debug_set_ptr(void* p) {
+  g_debug_ptr = p;
+  return 0;
+}
 
 extern "C" int tavsr_gemm_bias_act(const void* x, long long ldx, const void* w, long long ldw,
                                    const float* bias, void* y, long long ldy, int M, int N, int K,

@@ -321,9 +321,20 @@ def test_gemm_rowln_split_k_matches_unsplit(M, K):
 
 @pytest.mark.parametrize("M", [128, 8000, 1992, 77, 333])
 @pytest.mark.parametrize("variant", ["macaron", "final"])
-def test_ffn_fused(M, variant):
-    """Fused FFN (hidden on chip, 2-CTA hidden split + DSMEM reduction) vs fp64."""
+@pytest.mark.parametrize("version", [0, 2])
+def test_ffn_fused(M, variant, version):
+    """Fused FFN (hidden on chip, hidden split across a cluster + DSMEM reduction) vs fp64;
+    version 0 = default 2-CTA cluster, 2 = CTA-pair (cta_group::2) cluster of 4."""
     ops = _ops()
+    from tailored_avsr_b200 import _lib
+    _lib.load().tavsr_debug_set(5, version)
+    try:
+        _ffn_case(ops, M, variant)
+    finally:
+        _lib.load().tavsr_debug_set(5, 0)
+
+
+def _ffn_case(ops, M, variant):
     g = torch.Generator().manual_seed(M + len(variant))
     xn = torch.randn(M, 256, generator=g).to(DEV)
     x = torch.randn(M, 256, generator=g).to(DEV)

@@ -35,11 +35,10 @@ def ffn():
 
 
 lib = _lib.load()
-lib.tavsr_debug_set(5, 0)
+lib.tavsr_debug_set(5, 2)
 print(f"M={M} ffn pair (v2) us", t(ffn))
-lib.tavsr_debug_set(5, 1)
-print(f"M={M} ffn v1 us", t(ffn))
 lib.tavsr_debug_set(5, 0)
+print(f"M={M} ffn v1 us", t(ffn))
 h = torch.empty(M, 2048, device="cuda")
 
 
@@ -50,3 +49,25 @@ def two():
 
 
 print(f"M={M} two-kernel us", t(two))
+
+# ---- phase breakdown from in-kernel globaltimer stamps ----
+import numpy as np
+for ver in (2, 0):
+    lib.tavsr_debug_set(5, ver)
+    nblk = (4 * ((M + 255) // 256)) if ver == 2 else 2 * ((M + 127) // 128)
+    dbg = torch.zeros(nblk * 8, dtype=torch.int64, device="cuda")
+    lib.tavsr_debug_set_ptr(dbg.data_ptr())
+    if ver == 2:
+        lib.tavsr_debug_set(6, 1)
+    ffn(); torch.cuda.synchronize()
+    dbg.zero_()
+    ffn(); torch.cuda.synchronize()
+    lib.tavsr_debug_set_ptr(None)
+    d = dbg.cpu().numpy().reshape(nblk, 8).astype(np.float64)
+    t0 = d[:, 0].min()
+    names = ["setup done", "first h_full", "d_full (main loop done)", "cluster sync 1", "cluster sync 2 (exchange)", "finish", "second h_full"]
+    print(f"--- version {'v2 pair' if ver == 2 else 'v1'}: {nblk} CTAs; kernel span {(d[:, 5].max() - t0) / 1e3:.1f} us; start spread {(d[:, 0].max() - t0) / 1e3:.1f} us")
+    for i, n in enumerate(names):
+        col = d[:, i]
+        print(f"   {n:28s} median +{(np.median(col) - t0) / 1e3:7.1f} us   max +{(col.max() - t0) / 1e3:7.1f} us")
+lib.tavsr_debug_set(5, 0)
