@@ -1,0 +1,64 @@
+"""world_size-2 gloo tests (CPU) of the utterance-sharded data-parallel host logic."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import ref_path, synth
+from tailored_avsr_b200 import parallel
+
+
+def test_shard_utterances_partition_and_balance():
+    lens = [250, 100, 240, 90, 230, 80, 220, 70, 33]
+    for world in (1, 2, 3, 4, 8):
+        shards = [parallel.shard_utterances(lens, world, r) for r in range(world)]
+        flat = sorted(i for s in shards for i in s)
+        assert flat == list(range(len(lens)))           # every utterance exactly once
+        sizes = [len(s) for s in shards]
+        assert max(sizes) - min(sizes) <= 1
+        work = [sum(lens[i] for i in s) for s in shards]
+        assert max(work) - min(work) <= max(lens)        # length-balanced
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        B, T, V, L = 6, 40, 11, 9
+        lens = torch.tensor([40, 25, 38, 31, 40, 12])
+        hs = synth.randn((B, T, 16), 5)
+        sd = {"ctc_lo.weight": synth.randn((V, 16), 6) * 0.3, "ctc_lo.bias": synth.randn((V,), 7) * 0.1}
+        ys = synth.rand_targets(B, L, V, 8)
+        ylens = torch.tensor([9, 5, 7, 6, 9, 9])           # last one infeasible for 12 frames? (no)
+        mine = parallel.shard_utterances(lens.tolist(), world, rank)
+        idx = torch.tensor(mine)
+        nll_vec = ref_path.ctc_loss(hs[idx], lens[idx], ys[idx], ylens[idx], sd, reduce=False) * len(mine)
+        loss = parallel.global_ctc_loss(nll_vec, B)
+        toks = ref_path.ctc_greedy(hs[idx], sd, lens=lens[idx])
+        all_toks = parallel.gather_token_lists(toks, mine, B)
+        slowest = parallel.max_over_ranks(float(rank + 1), torch.device("cpu"))
+        if rank == 0:
+            full = ref_path.ctc_loss(hs, lens, ys, ylens, sd, reduce=True)
+            ret["loss_ok"] = bool(torch.allclose(loss, full, rtol=1e-6, atol=1e-6))
+            ret["toks_ok"] = all_toks == ref_path.ctc_greedy(hs, sd, lens=lens)
+            ret["max_ok"] = slowest == float(world)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_loss_and_gather_match_single_process():
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+        assert ret.get("loss_ok") and ret.get("toks_ok") and ret.get("max_ok"), dict(ret)
