@@ -61,6 +61,8 @@ relpos_attn_kernel(const float* __restrict__ qkv, long long ld_qkv, const float*
                    long long ld_pos, const float* __restrict__ bias_u,
                    const float* __restrict__ bias_v, const int32_t* __restrict__ lens,
                    float* __restrict__ ctx, long long ld_ctx, int T, int H, int round_out) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float smem[];
   float* Ks = smem;
   float* Vs = Ks + kKT * kLd;
@@ -278,9 +280,8 @@ extern "C" int tavsr_relpos_attn_fwd(const float* qkv, long long ld_qkv, const f
     configured = true;
   }
   dim3 grid((T + attn::kQT - 1) / attn::kQT, H, B);
-  attn::relpos_attn_kernel<<<grid, 128, smem, s>>>(qkv, ld_qkv, pos, ld_pos, u, v, lens, ctx,
-                                                  ld_ctx, T, H, round_out);
-  TAVSR_CUDA_OK(cudaGetLastError());
+  TAVSR_CUDA_OK(launch_kernel(attn::relpos_attn_kernel, grid, dim3(128), smem, s, 0, qkv, ld_qkv, pos,
+                              ld_pos, u, v, lens, ctx, ld_ctx, T, H, round_out));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }

@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(256)
 ctc_head_kernel(const float* __restrict__ hs, long long ldh, const float* __restrict__ w,
                 const float* __restrict__ bias, float* __restrict__ logp, float* __restrict__ prob,
                 int64_t* __restrict__ amax, int M, int D, int V) {
+  pdl_launch_dependents();
   extern __shared__ float sm[];
   float* Wt = sm;                       // [D][64]
   float* Hs = sm + D * kVPad;           // [8 warps][4 frames][D]
@@ -34,6 +35,7 @@ ctc_head_kernel(const float* __restrict__ hs, long long ldh, const float* __rest
     Wt[i] = v < V ? __ldg(w + static_cast<long long>(v) * D + k) : 0.f;
   }
   __syncthreads();
+  pdl_wait();  // W^T staging above only read weights
   const float b0 = lane < V ? __ldg(bias + lane) : 0.f;
   const float b1 = lane + 32 < V ? __ldg(bias + lane + 32) : 0.f;
   float* hw = Hs + warp * 4 * D;
@@ -150,6 +152,8 @@ ctc_loss_kernel(const float* __restrict__ logp, const int64_t* __restrict__ targ
   __shared__ float s_row[4][2][kVPad];   // per warp, double-buffered log2-prob row
   __shared__ float s_occ[4][kVPad];
   __shared__ float s_fin[4][2];
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * 4 + warp;
@@ -328,6 +332,8 @@ __global__ void __launch_bounds__(128)
 ctc_greedy_kernel(const int64_t* __restrict__ amax, const int32_t* __restrict__ lens,
                   int64_t* __restrict__ tokens, int32_t* __restrict__ ntok, int B, int T,
                   int blank) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (b >= B) return;
   const int lane = threadIdx.x & 31;
@@ -364,6 +370,8 @@ ctc_prefix_kernel(const float* __restrict__ logp, const float* __restrict__ r_pr
                   const float* __restrict__ psi_prev, float* __restrict__ r_new,
                   float* __restrict__ score, int T, int Tvalid, int V, int nhyp, int blank,
                   int eos) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nhyp * V) return;
   const int hy = idx / V, c = idx % V;
@@ -430,8 +438,8 @@ extern "C" int tavsr_ctc_head(const float* hs, long long ldh, const float* w, co
   const int groups = (M + 3) / 4;
   int grid = (groups + 7) / 8;
   if (grid > 2 * num_sms()) grid = 2 * num_sms();
-  ctc::ctc_head_kernel<<<grid, 256, smem, s>>>(hs, ldh, w, b, logp, prob, amax, M, D, V);
-  TAVSR_CUDA_OK(cudaGetLastError());
+  TAVSR_CUDA_OK(launch_kernel(ctc::ctc_head_kernel, dim3(grid), dim3(256), smem, s, 0, hs, ldh, w, b, logp,
+                              prob, amax, M, D, V));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
@@ -453,8 +461,9 @@ extern "C" int tavsr_ctc_loss(const float* logp, const int64_t* targets, long lo
   float* aws = static_cast<float*>(alpha_ws);
   if (!grad) aws = nullptr;
 #define TAVSR_CTC_CASE(C)                                                                       \
-  ctc::ctc_loss_kernel<C><<<grid, 128, 0, s>>>(logp, targets, ld_targets, hlens, tlens, nll,    \
-                                               grad, gscale, aws, B, T, V, Lmax, zero_infinity)
+  TAVSR_CUDA_OK(launch_kernel(ctc::ctc_loss_kernel<C>, dim3(grid), dim3(128), 0, s, 0, logp, targets, \
+                              ld_targets, hlens, tlens, nll, grad, gscale, aws, B, T, V, Lmax,      \
+                              zero_infinity))
   if (S <= 64) TAVSR_CTC_CASE(2);
   else if (S <= 128) TAVSR_CTC_CASE(4);
   else if (S <= 256) TAVSR_CTC_CASE(8);
@@ -471,8 +480,8 @@ extern "C" int tavsr_ctc_greedy(const int64_t* amax, const int32_t* lens, int64_
                                 int32_t* ntok, int B, int T, int blank, void* stream) {
   TAVSR_REQUIRE(B > 0 && T > 0 && amax && tokens && ntok, "ctc_greedy: bad arguments");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  ctc::ctc_greedy_kernel<<<(B + 3) / 4, 128, 0, s>>>(amax, lens, tokens, ntok, B, T, blank);
-  TAVSR_CUDA_OK(cudaGetLastError());
+  TAVSR_CUDA_OK(launch_kernel(ctc::ctc_greedy_kernel, dim3((B + 3) / 4), dim3(128), 0, s, 0, amax, lens,
+                              tokens, ntok, B, T, blank));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
@@ -487,9 +496,9 @@ extern "C" int tavsr_ctc_prefix_score(const float* logp, const float* r_prev, co
                 "ctc_prefix_score: null pointer");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int n = nhyp * V;
-  ctc::ctc_prefix_kernel<<<(n + 127) / 128, 128, 0, s>>>(logp, r_prev, last, plen, psi_prev, r_new,
-                                                         score, T, Tvalid, V, nhyp, blank, eos);
-  TAVSR_CUDA_OK(cudaGetLastError());
+  TAVSR_CUDA_OK(launch_kernel(ctc::ctc_prefix_kernel, dim3((n + 127) / 128), dim3(128), 0, s, 0, logp,
+                              r_prev, last, plen, psi_prev, r_new, score, T, Tvalid, V, nhyp, blank,
+                              eos));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }

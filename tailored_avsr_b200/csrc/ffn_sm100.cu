@@ -19,8 +19,7 @@ static int launch_ffn(const FfnParams& p, int m_tiles, cudaStream_t stream) {
                                        ffn::kSmemBytes));
     configured = true;
   }
-  kern<<<2 * m_tiles, ffn::kThreads, ffn::kSmemBytes, stream>>>(p);
-  TAVSR_CUDA_OK(cudaGetLastError());
+  TAVSR_CUDA_OK(launch_kernel(kern, dim3(2 * m_tiles), dim3(ffn::kThreads), ffn::kSmemBytes, stream, 0, p));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
@@ -48,8 +47,7 @@ static int launch_ffn2(const Ffn2Params& p, int m_units, cudaStream_t stream) {
     printf("ffn2: max active clusters of 4 = %d (err %d)\n", ncl, static_cast<int>(e));
     g_debug[6] = 0;
   }
-  kern<<<4 * m_units, ffn::kThreads, ffn2::kSmemBytes, stream>>>(p);
-  TAVSR_CUDA_OK(cudaGetLastError());
+  TAVSR_CUDA_OK(launch_kernel(kern, dim3(4 * m_units), dim3(ffn::kThreads), ffn2::kSmemBytes, stream, 0, p));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }

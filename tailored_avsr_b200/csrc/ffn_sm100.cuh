@@ -104,6 +104,7 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
   uint64_t* d_full = h_ready + 2;            // [1]  all GEMM2 complete
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(d_full + 1);
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
   const uint32_t rank = cluster_ctarank();
@@ -142,6 +143,7 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *s_tmem;
+  pdl_wait();
   FFN_STAMP(0);
 
   if (warp == 0) {
@@ -386,6 +388,7 @@ ffn_fused_pair_kernel(const __grid_constant__ Ffn2Params p) {
   uint64_t* d_full = h_ready + 2;            // [1]
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(d_full + 1);
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
   const uint32_t rank = cluster_ctarank();
@@ -428,6 +431,7 @@ ffn_fused_pair_kernel(const __grid_constant__ Ffn2Params p) {
   cluster_sync_all();  // every CTA's barriers are initialised before remote arrives / TMA signals
   tc_fence_after_sync();
   const uint32_t tmem_base = *s_tmem;
+  pdl_wait();
   FFN_STAMP(0);
 
   if (warp == 0) {

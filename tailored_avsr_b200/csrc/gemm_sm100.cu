@@ -137,20 +137,7 @@ static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
   const int units = p.num_m_tiles * p.num_n_tiles;
   const int max_units = num_sms() / kCtas;
   const int grid = (units < max_units ? units : max_units) * kCtas;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(Cfg::kThreads);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kCtas;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  TAVSR_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
+  TAVSR_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, stream, kCtas, p));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }

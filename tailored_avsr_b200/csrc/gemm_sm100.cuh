@@ -363,6 +363,7 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
   uint64_t* tempty_bar = tfull_bar + kAccStages;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tempty_bar + kAccStages);
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
   // Work units: a unit is one CTA tile (kCtas == 1) or one CTA-pair tile of 256 rows (kCtas == 2).
@@ -409,6 +410,7 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
   if (kPair) cluster_sync_all();  // peer barriers are initialised before any remote arrive / TMA
   tc_fence_after_sync();
   const uint32_t tmem_base = *s_tmem;
+  pdl_wait();  // everything above only touched weights / on-chip state
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================

@@ -32,6 +32,21 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  A kernel launched with the programmatic-stream-
+// serialization attribute may start while its predecessor is still running; it must not touch the
+// predecessor's outputs before pdl_wait() (which returns once the predecessor grid has completed
+// and flushed).  pdl_launch_dependents() lets the successor's CTAs be scheduled early so their
+// prologues (barrier init, TMEM allocation, descriptor prefetch, weight staging) overlap this
+// kernel's main loop and tail.  Both are no-ops for a normally launched kernel.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -19,6 +19,8 @@ layernorm_kernel(const float* __restrict__ x, long long ldx, int M, float eps,
                  float* __restrict__ outA, long long ldA, int roundA,
                  const float* __restrict__ gB, const float* __restrict__ bB,
                  float* __restrict__ outB, long long ldB, int roundB, float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const uint32_t lane = lane_id();
@@ -65,6 +67,8 @@ template <int kVec>  // Ch = 128 * kVec
 __global__ void __launch_bounds__(256)
 csgu_stats_kernel(const float* __restrict__ h, long long ldh, int M, int Ch, float eps,
                   float2* __restrict__ stats) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const uint32_t lane = lane_id();
@@ -116,6 +120,19 @@ csgu_conv_kernel(const float* __restrict__ h, long long ldh, const float* __rest
                  float* __restrict__ out, long long ldo, int T, int Ch, int round_out) {
   __shared__ __align__(16) float s_tile[kRows][kCh];
   __shared__ float2 s_ab[kRows];  // per frame: (rstd, -mean*rstd); (0,0) outside [0,T)
+  pdl_launch_dependents();
+  // weights first (not produced by the predecessor), then wait for the gate activations / stats
+  const int c_early = blockIdx.x * kCh + threadIdx.x;
+  float w[kTaps];
+  float gam = 0.f, bet = 0.f, cb = 0.f;
+  if (c_early < Ch) {
+#pragma unroll
+    for (int k = 0; k < kTaps; ++k) w[k] = __ldg(conv_w + static_cast<long long>(c_early) * kTaps + k);
+    gam = __ldg(norm_g + c_early);
+    bet = __ldg(norm_b + c_early);
+    cb = __ldg(conv_b + c_early);
+  }
+  pdl_wait();
   const int c0 = blockIdx.x * kCh;
   const int t0 = blockIdx.y * kSeg;
   const int b = blockIdx.z;
@@ -138,10 +155,6 @@ csgu_conv_kernel(const float* __restrict__ h, long long ldh, const float* __rest
     s_ab[i] = ab;
   }
   const int c = c0 + threadIdx.x;
-  float w[kTaps];
-#pragma unroll
-  for (int k = 0; k < kTaps; ++k) w[k] = __ldg(conv_w + static_cast<long long>(c) * kTaps + k);
-  const float gam = __ldg(norm_g + c), bet = __ldg(norm_b + c), cb = __ldg(conv_b + c);
   const float* rcol = h + c;
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
@@ -186,6 +199,8 @@ merge_weights_kernel(const float2* __restrict__ dots1, const float2* __restrict_
                      const int32_t* __restrict__ lens, float pool_b1, float pool_b2, float wproj_b1,
                      float wproj_b2, float inv_sqrt, float* __restrict__ w1, float* __restrict__ w2,
                      int B, int T) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
   const uint32_t lane = lane_id();
@@ -236,8 +251,8 @@ extern "C" int tavsr_layernorm(const float* x, long long ldx, int M, int D, floa
   const int grid = (M + rows_per_block - 1) / rows_per_block;
 #define TAVSR_LN_CASE(V)                                                                          \
   case V:                                                                                         \
-    layernorm_kernel<V><<<grid, 256, 0, s>>>(x, ldx, M, eps, gA, bA, outA, ldA, roundA, gB, bB,   \
-                                             outB, ldB, roundB, scale);                           \
+    TAVSR_CUDA_OK(launch_kernel(layernorm_kernel<V>, dim3(grid), dim3(256), 0, s, 0, x, ldx, M, eps, \
+                                gA, bA, outA, ldA, roundA, gB, bB, outB, ldB, roundB, scale));    \
     break;
   switch (D / 128) {
     TAVSR_LN_CASE(1) TAVSR_LN_CASE(2) TAVSR_LN_CASE(3) TAVSR_LN_CASE(4) TAVSR_LN_CASE(6)
@@ -263,18 +278,17 @@ extern "C" int tavsr_csgu_fwd(const float* h, long long ldh, const float* norm_g
   const int grid1 = (M + 7) / 8;
   float2* st = reinterpret_cast<float2*>(stats);
   switch (Ch / 128) {
-    case 1: csgu_stats_kernel<1><<<grid1, 256, 0, s>>>(h, ldh, M, Ch, eps, st); break;
-    case 2: csgu_stats_kernel<2><<<grid1, 256, 0, s>>>(h, ldh, M, Ch, eps, st); break;
-    case 4: csgu_stats_kernel<4><<<grid1, 256, 0, s>>>(h, ldh, M, Ch, eps, st); break;
-    case 8: csgu_stats_kernel<8><<<grid1, 256, 0, s>>>(h, ldh, M, Ch, eps, st); break;
-    case 16: csgu_stats_kernel<16><<<grid1, 256, 0, s>>>(h, ldh, M, Ch, eps, st); break;
+    case 1: TAVSR_CUDA_OK(launch_kernel(csgu_stats_kernel<1>, dim3(grid1), dim3(256), 0, s, 0, h, ldh, M, Ch, eps, st)); break;
+    case 2: TAVSR_CUDA_OK(launch_kernel(csgu_stats_kernel<2>, dim3(grid1), dim3(256), 0, s, 0, h, ldh, M, Ch, eps, st)); break;
+    case 4: TAVSR_CUDA_OK(launch_kernel(csgu_stats_kernel<4>, dim3(grid1), dim3(256), 0, s, 0, h, ldh, M, Ch, eps, st)); break;
+    case 8: TAVSR_CUDA_OK(launch_kernel(csgu_stats_kernel<8>, dim3(grid1), dim3(256), 0, s, 0, h, ldh, M, Ch, eps, st)); break;
+    case 16: TAVSR_CUDA_OK(launch_kernel(csgu_stats_kernel<16>, dim3(grid1), dim3(256), 0, s, 0, h, ldh, M, Ch, eps, st)); break;
     default: return set_error(TAVSR_ERR_UNSUPPORTED, "csgu: Ch=%d not instantiated", Ch);
   }
   TAVSR_CUDA_OK(cudaGetLastError());
   dim3 grid2(Ch / kCh, (T + kSeg - 1) / kSeg, B);
-  csgu_conv_kernel<<<grid2, kCh, 0, s>>>(h, ldh, norm_g, norm_b, conv_w, conv_b, st, out, ldo, T,
-                                         Ch, round_out);
-  TAVSR_CUDA_OK(cudaGetLastError());
+  TAVSR_CUDA_OK(launch_kernel(csgu_conv_kernel, grid2, dim3(kCh), 0, s, 0, h, ldh, norm_g, norm_b, conv_w,
+                              conv_b, static_cast<const float2*>(st), out, ldo, T, Ch, round_out));
   g_launches.fetch_add(2, std::memory_order_relaxed);
   return 0;
 }
@@ -285,10 +299,10 @@ extern "C" int tavsr_merge_learned_ave_weights(const float* dots1, const float* 
                                                float* w1, float* w2, int B, int T, void* stream) {
   TAVSR_REQUIRE(B > 0 && T > 0 && dots1 && dots2 && w1 && w2, "merge_weights: bad arguments");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  merge_weights_kernel<<<(B + 3) / 4, 128, 0, s>>>(
-      reinterpret_cast<const float2*>(dots1), reinterpret_cast<const float2*>(dots2), lens,
-      pool_b1, pool_b2, wproj_b1, wproj_b2, inv_sqrt_size, w1, w2, B, T);
-  TAVSR_CUDA_OK(cudaGetLastError());
+  TAVSR_CUDA_OK(launch_kernel(merge_weights_kernel, dim3((B + 3) / 4), dim3(128), 0, s, 0,
+                              reinterpret_cast<const float2*>(dots1),
+                              reinterpret_cast<const float2*>(dots2), lens, pool_b1, pool_b2,
+                              wproj_b1, wproj_b2, inv_sqrt_size, w1, w2, B, T));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
