@@ -16,10 +16,10 @@ static int launch_ffn(const FfnParams& p, int m_tiles, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     TAVSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       ffn::kSmemBytes));
+                                       ffn::kSmemBytesV1));
     configured = true;
   }
-  TAVSR_CUDA_OK(launch_kernel(kern, dim3(2 * m_tiles), dim3(ffn::kThreads), ffn::kSmemBytes, stream, 0, p));
+  TAVSR_CUDA_OK(launch_kernel(kern, dim3(2 * m_tiles), dim3(ffn::kThreadsV1), ffn::kSmemBytesV1, stream, 0, p));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }

@@ -69,7 +69,7 @@ __device__ __forceinline__ long long globaltimer_ns() {
 }
 #define FFN_STAMP(slot)                                                              \
   do {                                                                               \
-    if (p.dbg != nullptr && threadIdx.x == 64)                                       \
+    if (p.dbg != nullptr && (threadIdx.x == (blockDim.x == 256 ? 128 : 64)))           \
       p.dbg[static_cast<long long>(blockIdx.x) * 8 + (slot)] = globaltimer_ns();     \
   } while (0)
 
@@ -84,24 +84,53 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t addr, float4 v) {
                : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------
+// v1 kernel (default).  Warp roles (8 warps):
+//   0: TMA producer            1: GEMM1 issuer (H_j = Xn . W1_j^T, 128x128x8 MMAs, A/B from smem)
+//   2: GEMM2 issuer (D2 += H_j . W2_j^T, 128x256x8 MMAs, A from TMEM)       3: idle
+//   4-7: activation / epilogue warps (TMEM lane quadrant = warp & 3)
+// Two issuing threads because one thread issues a tcgen05.mma at best every ~89 cycles (127 with a
+// commit every 4; tools/mma_bench.cu) while a 128x128x8 TF32 MMA occupies the tensor pipe for
+// ~70: the GEMM1 and GEMM2 streams are independent between handshakes, so issuing them from two
+// warps keeps the pipe busy (measured 83 cycles per MMA for two issuers vs 127 for one).
+// Weight ring: 6 slots of 16 KB in one FIFO; a W1 unit (128 hidden rows x 32 k) takes one slot, a W2
+// unit (256 output rows x 32 k) takes an even-aligned slot pair.  The schedule
+//   W1_0 W1_1 | W2_0 W1_2 | W2_1 W1_3 | ... | W2_6 | W2_7          (each run = 8 slots)
+// is walked identically by the producer and both issuers.
+// ------------------------------------------------------------------------------------------------
+namespace ffn {
+constexpr int kThreadsV1 = 256;
+constexpr int kRingV1 = 6;
+constexpr int kSmemBytesV1 = 1024 + kXBytes + kRingV1 * kUnitBytes + 512;
+
+// Walks the weight-unit schedule; every role keeps its own copy and therefore the same slot /
+// phase sequence.  `parity` holds one phase bit per slot (bit set = odd number of completed uses).
+struct RingWalker {
+  int slot = 0;
+  uint32_t parity = 0;
+  __device__ __forceinline__ uint32_t phase(int s) const { return (parity >> s) & 1u; }
+  __device__ __forceinline__ void used(int s) { parity ^= 1u << s; }
+  __device__ __forceinline__ void advance(int n) { slot += n; if (slot >= kRingV1) slot -= kRingV1; }
+};
+}  // namespace ffn
+
 template <int kAct>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ffn::kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ffn::kThreadsV1, 1)
 ffn_fused_kernel(const __grid_constant__ FfnParams p) {
   using namespace ffn;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* s_x = smem;                       // 8 x 16 KB, later: peer partial rows (64 KB)
-  uint8_t* s_ring = s_x + kXBytes;           // 5 x 16 KB, later: TMA-store staging (32 KB)
-  float* s_b1 = reinterpret_cast<float*>(s_ring + kRing * kUnitBytes);  // [1024]
-  float* s_param = s_b1 + kHidCta;           // 9 x 256 (rowln_finish layout)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_param + 9 * 256);
-  uint64_t* w_full = bars;                   // [kRing]
-  uint64_t* w_empty = bars + kRing;          // [kRing]
-  uint64_t* x_full = bars + 2 * kRing;       // [1]
+  uint8_t* s_ring = s_x + kXBytes;           // 6 x 16 KB, later: epilogue params + store staging
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + kRingV1 * kUnitBytes);
+  uint64_t* w_full = bars;                   // [6]
+  uint64_t* w_empty = bars + kRingV1;        // [6]
+  uint64_t* x_full = bars + 2 * kRingV1;     // [1]
   uint64_t* h_full = x_full + 1;             // [2]  GEMM1 chunk complete
   uint64_t* h_ready = h_full + 2;            // [2]  activation written back
-  uint64_t* d_full = h_ready + 2;            // [1]  all GEMM2 complete
+  uint64_t* h_free = h_ready + 2;            // [2]  GEMM2 finished reading the H buffer
+  uint64_t* d_full = h_free + 2;             // [1]  all GEMM2 complete
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(d_full + 1);
 
   pdl_launch_dependents();
@@ -115,7 +144,7 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
     tma_prefetch_desc(&p.tmX);
     tma_prefetch_desc(&p.tmW1);
     tma_prefetch_desc(&p.tmW2);
-    for (int i = 0; i < kRing; ++i) {
+    for (int i = 0; i < kRingV1; ++i) {
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
     }
@@ -123,6 +152,7 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&h_full[i], 1);
       mbar_init(&h_ready[i], 4);
+      mbar_init(&h_free[i], 1);
     }
     mbar_init(d_full, 1);
     fence_mbar_init();
@@ -130,14 +160,6 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
   if (warp == 1) {
     tmem_alloc(s_tmem, 512);
     tmem_relinquish();
-  }
-  if (warp >= 2) {
-    const float* srcs[9] = {p.ep.bias, p.ep.ln0_g, p.ep.ln0_b, p.ep.lnA_g, p.ep.lnA_b,
-                            p.ep.lnB_g, p.ep.lnB_b, p.ep.dot1, p.ep.dot2};
-    for (int v = 0; v < 9; ++v)
-      for (int i = threadIdx.x - 64; i < 256; i += 128)
-        s_param[v * 256 + i] = srcs[v] ? srcs[v][i] : 0.0f;
-    for (int i = threadIdx.x - 64; i < kHidCta; i += 128) s_b1[i] = p.b1 ? p.b1[hid0 + i] : 0.0f;
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -152,30 +174,32 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
       mbar_arrive_expect_tx(x_full, kXBytes);
       for (int kb = 0; kb < 8; ++kb)
         tma_load_2d(s_x + kb * kUnitBytes, &p.tmX, x_full, kb * 32, m0);
-      int s = 0;
-      uint32_t ph = 0;
-      auto next_slot = [&]() -> uint8_t* {
-        mbar_wait(&w_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&w_full[s], kUnitBytes);
-        return s_ring + s * kUnitBytes;
-      };
-      auto advance = [&]() { if (++s == kRing) { s = 0; ph ^= 1; } };
-      auto load_w1 = [&](int j) {  // 8 k-blocks of W1[hid0 + j*128 .. +128, :]
+      RingWalker rw;
+      auto load_w1 = [&](int j) {  // 8 k-blocks of W1[hid0 + j*128 .. +128, :], one slot each
         for (int kb = 0; kb < 8; ++kb) {
-          uint8_t* dst = next_slot();
-          tma_load_2d(dst, &p.tmW1, &w_full[s], kb * 32, hid0 + j * kChunk);
-          advance();
+          const int s = rw.slot;
+          mbar_wait(&w_empty[s], rw.phase(s) ^ 1);
+          mbar_arrive_expect_tx(&w_full[s], kUnitBytes);
+          tma_load_2d(s_ring + s * kUnitBytes, &p.tmW1, &w_full[s], kb * 32, hid0 + j * kChunk);
+          rw.used(s);
+          rw.advance(1);
         }
       };
-      auto load_w2 = [&](int j) {  // 4 k-blocks x 2 output halves of W2[:, hid0 + j*128 .. +128]
-        for (int kb = 0; kb < 4; ++kb)
-          for (int nh = 0; nh < 2; ++nh) {
-            uint8_t* dst = next_slot();
-            tma_load_2d(dst, &p.tmW2, &w_full[s], hid0 + j * kChunk + kb * 32, nh * 128);
-            advance();
-          }
+      auto load_w2 = [&](int j) {  // 4 k-blocks of W2[:, hid0 + j*128 .. +128], a slot pair each
+        for (int kb = 0; kb < 4; ++kb) {
+          const int s = rw.slot;  // even
+          mbar_wait(&w_empty[s], rw.phase(s) ^ 1);
+          // the odd slot of the pair may last have held a (later) single-slot W1 unit: its own
+          // barrier says when that one has been consumed (no phase is consumed by this wait)
+          mbar_wait(&w_empty[s + 1], rw.phase(s + 1) ^ 1);
+          mbar_arrive_expect_tx(&w_full[s], 2 * kUnitBytes);
+          tma_load_2d(s_ring + s * kUnitBytes, &p.tmW2, &w_full[s], hid0 + j * kChunk + kb * 32, 0);
+          tma_load_2d(s_ring + (s + 1) * kUnitBytes, &p.tmW2, &w_full[s],
+                      hid0 + j * kChunk + kb * 32, 128);
+          rw.used(s);
+          rw.advance(2);
+        }
       };
-      // must mirror the MMA issue order below
       load_w1(0);
       load_w1(1);
       for (int j = 0; j < kNChunk; ++j) {
@@ -184,17 +208,22 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
       }
     }
   } else if (warp == 1) {
-    // ===================================== MMA issuer =======================================
+    // ===================================== GEMM1 issuer =====================================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc(UMMA_FMT_TF32, 128, 128);
-      int s = 0;
-      uint32_t ph = 0;
-      auto advance = [&]() { if (++s == kRing) { s = 0; ph ^= 1; } };
+      RingWalker rw;
       const uint32_t x_addr = smem_u32(s_x);
+      mbar_wait(x_full, 0);
+      tc_fence_after_sync();
       auto gemm1 = [&](int j) {
+        if (j >= 2) {  // H buffer j&1 was read by GEMM2 of chunk j-2
+          mbar_wait(&h_free[j & 1], ((j - 2) >> 1) & 1);
+          tc_fence_after_sync();
+        }
         const uint32_t d = tmem_base + kColH + (j & 1) * kChunk;
         for (int kb = 0; kb < 8; ++kb) {
-          mbar_wait(&w_full[s], ph);
+          const int s = rw.slot;
+          mbar_wait(&w_full[s], rw.phase(s));
           tc_fence_after_sync();
           const uint64_t a_desc = umma_desc_kmajor_sw128(x_addr + kb * kUnitBytes);
           const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(s_ring + s * kUnitBytes));
@@ -202,38 +231,50 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
           for (int k = 0; k < 4; ++k)
             umma_ss<true>(d, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) ? 1u : 0u);
           umma_commit(&w_empty[s]);
-          advance();
+          rw.used(s);
+          rw.advance(1);
         }
         umma_commit(&h_full[j & 1]);
       };
-      auto gemm2 = [&](int j) {
-        const uint32_t a0 = tmem_base + kColH + (j & 1) * kChunk;
-        for (int kb = 0; kb < 4; ++kb)
-          for (int nh = 0; nh < 2; ++nh) {
-            mbar_wait(&w_full[s], ph);
-            tc_fence_after_sync();
-            const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(s_ring + s * kUnitBytes));
-            const uint32_t d = tmem_base + kColD2 + nh * 128;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_ts_tf32(d, a0 + kb * 32 + k * 8, b_desc + 2 * k, idesc, (j | kb | k) ? 1u : 0u);
-            umma_commit(&w_empty[s]);
-            advance();
-          }
-      };
-      mbar_wait(x_full, 0);
-      tc_fence_after_sync();
       gemm1(0);
       gemm1(1);
       for (int j = 0; j < kNChunk; ++j) {
+        // the W2_j run occupies 4 even slots: account for their phase flips, then move past it
+        for (int kb = 0; kb < 4; ++kb) { rw.used(rw.slot); rw.advance(2); }
+        if (j + 2 < kNChunk) gemm1(j + 2);
+      }
+    }
+  } else if (warp == 2) {
+    // ===================================== GEMM2 issuer =====================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(UMMA_FMT_TF32, 128, 256);
+      RingWalker rw;
+      // skip the two leading W1 runs (16 single-slot units)
+      for (int i = 0; i < 16; ++i) { rw.used(rw.slot); rw.advance(1); }
+      for (int j = 0; j < kNChunk; ++j) {
         mbar_wait(&h_ready[j & 1], (j >> 1) & 1);  // activation of chunk j is back in TMEM
         tc_fence_after_sync();
-        gemm2(j);
-        if (j + 2 < kNChunk) gemm1(j + 2);  // reuses H buffer j&1: ordered after gemm2(j)
+        const uint32_t a0 = tmem_base + kColH + (j & 1) * kChunk;
+        for (int kb = 0; kb < 4; ++kb) {
+          const int s = rw.slot;
+          mbar_wait(&w_full[s], rw.phase(s));
+          tc_fence_after_sync();
+          const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(s_ring + s * kUnitBytes));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_ts_tf32(tmem_base + kColD2, a0 + kb * 32 + k * 8, b_desc + 2 * k, idesc,
+                         (j | kb | k) ? 1u : 0u);
+          umma_commit(&w_empty[s]);
+          rw.used(s);
+          rw.advance(2);
+        }
+        umma_commit(&h_free[j & 1]);
+        if (j + 2 < kNChunk)
+          for (int i = 0; i < 8; ++i) { rw.used(rw.slot); rw.advance(1); }  // skip W1_{j+2}
       }
       umma_commit(d_full);
     }
-  } else {
+  } else if (warp >= 4) {
     // =============================== activation warps =======================================
     const int q = warp & 3;  // TMEM lane quadrant
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
@@ -243,12 +284,18 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
       if (j == 0) FFN_STAMP(1);
       if (j == 1) FFN_STAMP(6);
       const uint32_t th = tmem_base + lane_off + kColH + (j & 1) * kChunk;
+      const float4* b1p = reinterpret_cast<const float4*>(p.b1 + hid0 + j * kChunk);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t r[32];
         tmem_ld32(th + c * 32, r);
+        float bb[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {  // uniform 16-byte loads (every lane reads the same bias)
+          const float4 f = p.b1 ? __ldg(b1p + c * 8 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          bb[4 * i] = f.x; bb[4 * i + 1] = f.y; bb[4 * i + 2] = f.z; bb[4 * i + 3] = f.w;
+        }
         tmem_ld_wait();
-        const float* bb = s_b1 + j * kChunk + c * 32;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const float x = apply_act<kAct>(__uint_as_float(r[i]) + bb[i], p.act);
@@ -266,11 +313,19 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
     FFN_STAMP(2);
   }
 
-  // ---- exchange the partial outputs across the cluster: CTA r finishes rows [64r, 64r+64) ----
+  // ---- epilogue parameters into the (now free) ring area; exchange partial outputs ----
   __syncthreads();     // reconverge the single-lane role loops before the aligned cluster barrier
+  float* s_param = reinterpret_cast<float*>(s_ring + 4 * 8192);  // after the two 16 KB staging areas
+  {
+    const float* srcs[9] = {p.ep.bias, p.ep.ln0_g, p.ep.ln0_b, p.ep.lnA_g, p.ep.lnA_b,
+                            p.ep.lnB_g, p.ep.lnB_b, p.ep.dot1, p.ep.dot2};
+    for (int v = 0; v < 9; ++v)
+      for (int i = threadIdx.x; i < 256; i += kThreadsV1)
+        s_param[v * 256 + i] = srcs[v] ? srcs[v][i] : 0.0f;
+  }
   cluster_sync_all();  // both CTAs' MMAs are done -> both s_x regions may be overwritten
   FFN_STAMP(3);
-  if (warp >= 2) {
+  if (warp >= 4) {
     const int q = warp & 3;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t td2 = tmem_base + lane_off + kColD2;
@@ -293,7 +348,7 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
   }
   cluster_sync_all();  // release/acquire: the peer's rows are visible in s_x
   FFN_STAMP(4);
-  if (warp >= 2) {
+  if (warp >= 4) {
     const int q = warp & 3;
     if (static_cast<uint32_t>(q >> 1) == rank) {
       const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
@@ -330,7 +385,6 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
     tmem_dealloc(tmem_base, 512);
   }
 }
-
 
 // ================================================================================================
 // v2: CTA pairs.  Cluster of 4 = 2 pairs (cta_group::2, 256 frames per cluster) x 2 hidden halves.
