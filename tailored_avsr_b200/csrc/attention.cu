@@ -26,10 +26,12 @@ namespace attn {
 constexpr int kQT = 64;       // query rows per CTA
 constexpr int kKT = 64;       // keys per tile
 constexpr int kD = 64;        // head dim
-constexpr int kLd = 68;       // smem row pitch (floats) of K / V / P tiles: conflict-free fragments
+constexpr int kLd = 72;       // smem row pitch (floats) of K / V / P tiles: 8 banks per row shift ->
+                              // the 64-bit fragment loads of a half-warp hit 32 distinct banks
+constexpr int kLdV = 68;      // V tile pitch: its fragments are row-strided 32-bit loads (4 banks / row)
 constexpr int kPRows = 128;   // P band rows (127 used)
 constexpr int kRLd = 84;      // per-warp R band pitch
-constexpr int kSmemFloats = kKT * kLd * 2 + kPRows * kLd + 4 * 16 * kRLd;
+constexpr int kSmemFloats = kKT * kLd + kKT * kLdV + kPRows * kLd + 4 * 16 * kRLd;
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
   const uint32_t d = smem_u32(smem_dst);
@@ -66,7 +68,7 @@ relpos_attn_kernel(const float* __restrict__ qkv, long long ld_qkv, const float*
   extern __shared__ float smem[];
   float* Ks = smem;
   float* Vs = Ks + kKT * kLd;
-  float* Ps = Vs + kKT * kLd;
+  float* Ps = Vs + kKT * kLdV;
   float* Rs = Ps + kPRows * kLd;
 
   const int i0 = blockIdx.x * kQT;
@@ -91,7 +93,9 @@ relpos_attn_kernel(const float* __restrict__ qkv, long long ld_qkv, const float*
     const int r0 = i0 + warp * 16 + g, r1 = r0 + 8;
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {
-      const int c0 = ks * 8 + t, c1 = c0 + 4;
+      // contraction index permuted inside every 8-block: MMA k = t <-> d = 2t, k = t+4 <-> d = 2t+1,
+      // so the matching B values (k, k+4) sit next to each other in the K-major smem tiles
+      const int c0 = ks * 8 + 2 * t, c1 = c0 + 1;
       const float u0 = __ldg(bias_u + h * kD + c0), u1 = __ldg(bias_u + h * kD + c1);
       const float v0 = __ldg(bias_v + h * kD + c0), v1 = __ldg(bias_v + h * kD + c1);
       const float q00 = r0 < T ? __ldg(qbase + (row_base + r0) * ld_qkv + c0) : 0.f;
@@ -123,7 +127,7 @@ relpos_attn_kernel(const float* __restrict__ qkv, long long ld_qkv, const float*
       const bool ok = j < T;
       const long long grow = row_base + (ok ? j : 0);
       cp_async16(Ks + r * kLd + ch * 4, kbase + grow * ld_qkv + ch * 4, ok);
-      cp_async16(Vs + r * kLd + ch * 4, vbase + grow * ld_qkv + ch * 4, ok);
+      cp_async16(Vs + r * kLdV + ch * 4, vbase + grow * ld_qkv + ch * 4, ok);
     }
     for (int idx = threadIdx.x; idx < (kPRows - 1) * 16; idx += 128) {
       const int x = idx >> 4, ch = idx & 15;
@@ -141,12 +145,11 @@ relpos_attn_kernel(const float* __restrict__ qkv, long long ld_qkv, const float*
 #pragma unroll
       for (int n = 0; n < 10; ++n) {
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        const float* prow = Pw + (8 * n + g) * kLd + t;
+        const float* prow = Pw + (8 * n + g) * kLd + 2 * t;
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
-          const uint32_t b0 = __float_as_uint(prow[ks * 8]);
-          const uint32_t b1 = __float_as_uint(prow[ks * 8 + 4]);
-          mma_tf32(acc, qv[ks], b0, b1);
+          const float2 bb = *reinterpret_cast<const float2*>(prow + ks * 8);
+          mma_tf32(acc, qv[ks], __float_as_uint(bb.x), __float_as_uint(bb.y));
         }
         float* rw = Rw + g * kRLd + 8 * n + 2 * t;
         rw[0] = acc[0]; rw[1] = acc[1];
@@ -161,12 +164,11 @@ relpos_attn_kernel(const float* __restrict__ qkv, long long ld_qkv, const float*
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      const float* krow = Ks + (8 * n + g) * kLd + t;
+      const float* krow = Ks + (8 * n + g) * kLd + 2 * t;
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks) {
-        const uint32_t b0 = __float_as_uint(krow[ks * 8]);
-        const uint32_t b1 = __float_as_uint(krow[ks * 8 + 4]);
-        mma_tf32(acc, qu[ks], b0, b1);
+        const float2 bb = *reinterpret_cast<const float2*>(krow + ks * 8);
+        mma_tf32(acc, qu[ks], __float_as_uint(bb.x), __float_as_uint(bb.y));
       }
       const int jl = 8 * n + 2 * t;
       const float* r_lo = Rw + g * kRLd + (15 - g) + jl;
@@ -221,11 +223,11 @@ relpos_attn_kernel(const float* __restrict__ qkv, long long ld_qkv, const float*
       a[1] = tf32_bits(S[kk][2]);
       a[2] = tf32_bits(S[kk][1]);
       a[3] = tf32_bits(S[kk][3]);
-      const float* v0 = Vs + (8 * kk + 2 * t) * kLd + g;
+      const float* v0 = Vs + (8 * kk + 2 * t) * kLdV + g;
 #pragma unroll
       for (int nd = 0; nd < 8; ++nd) {
         const uint32_t b0 = __float_as_uint(v0[8 * nd]);
-        const uint32_t b1 = __float_as_uint(v0[kLd + 8 * nd]);
+        const uint32_t b1 = __float_as_uint(v0[kLdV + 8 * nd]);
         mma_tf32(O[nd], a, b0, b1);
       }
     }

@@ -104,13 +104,21 @@ constexpr int kRingV1 = 6;
 constexpr int kSmemBytesV1 = 1024 + kXBytes + kRingV1 * kUnitBytes + 512;
 
 // Walks the weight-unit schedule; every role keeps its own copy and therefore the same slot /
-// phase sequence.  `parity` holds one phase bit per slot (bit set = odd number of completed uses).
+// phase sequence.  All units are 32 KB slot pairs (3 super-slots): a W1 unit holds TWO k-blocks of
+// one hidden chunk (8 MMAs per barrier wait + commit, the issuing thread pays ~150 cycles for
+// each of those), a W2 unit one k-block of all 256 output rows (4 MMAs of N=256).
+constexpr int kSuper = kRingV1 / 2;          // 3 super-slots of 32 KB
 struct RingWalker {
   int slot = 0;
   uint32_t parity = 0;
-  __device__ __forceinline__ uint32_t phase(int s) const { return (parity >> s) & 1u; }
-  __device__ __forceinline__ void used(int s) { parity ^= 1u << s; }
-  __device__ __forceinline__ void advance(int n) { slot += n; if (slot >= kRingV1) slot -= kRingV1; }
+  __device__ __forceinline__ uint32_t phase() const { return (parity >> slot) & 1u; }
+  __device__ __forceinline__ void next() {
+    parity ^= 1u << slot;
+    if (++slot == kSuper) slot = 0;
+  }
+  __device__ __forceinline__ void skip(int n) {
+    for (int i = 0; i < n; ++i) next();
+  }
 };
 }  // namespace ffn
 
@@ -144,7 +152,7 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
     tma_prefetch_desc(&p.tmX);
     tma_prefetch_desc(&p.tmW1);
     tma_prefetch_desc(&p.tmW2);
-    for (int i = 0; i < kRingV1; ++i) {
+    for (int i = 0; i < kSuper; ++i) {
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
     }
@@ -175,29 +183,26 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
       for (int kb = 0; kb < 8; ++kb)
         tma_load_2d(s_x + kb * kUnitBytes, &p.tmX, x_full, kb * 32, m0);
       RingWalker rw;
-      auto load_w1 = [&](int j) {  // 8 k-blocks of W1[hid0 + j*128 .. +128, :], one slot each
-        for (int kb = 0; kb < 8; ++kb) {
+      auto load_w1 = [&](int j) {  // 4 units x 2 k-blocks of W1[hid0 + j*128 .. +128, :]
+        for (int u = 0; u < 4; ++u) {
           const int s = rw.slot;
-          mbar_wait(&w_empty[s], rw.phase(s) ^ 1);
-          mbar_arrive_expect_tx(&w_full[s], kUnitBytes);
-          tma_load_2d(s_ring + s * kUnitBytes, &p.tmW1, &w_full[s], kb * 32, hid0 + j * kChunk);
-          rw.used(s);
-          rw.advance(1);
+          mbar_wait(&w_empty[s], rw.phase() ^ 1);
+          mbar_arrive_expect_tx(&w_full[s], 2 * kUnitBytes);
+          uint8_t* dst = s_ring + s * 2 * kUnitBytes;
+          tma_load_2d(dst, &p.tmW1, &w_full[s], (2 * u) * 32, hid0 + j * kChunk);
+          tma_load_2d(dst + kUnitBytes, &p.tmW1, &w_full[s], (2 * u + 1) * 32, hid0 + j * kChunk);
+          rw.next();
         }
       };
-      auto load_w2 = [&](int j) {  // 4 k-blocks of W2[:, hid0 + j*128 .. +128], a slot pair each
+      auto load_w2 = [&](int j) {  // 4 units: one k-block of W2[:, hid0 + j*128 .. +128] each
         for (int kb = 0; kb < 4; ++kb) {
-          const int s = rw.slot;  // even
-          mbar_wait(&w_empty[s], rw.phase(s) ^ 1);
-          // the odd slot of the pair may last have held a (later) single-slot W1 unit: its own
-          // barrier says when that one has been consumed (no phase is consumed by this wait)
-          mbar_wait(&w_empty[s + 1], rw.phase(s + 1) ^ 1);
+          const int s = rw.slot;
+          mbar_wait(&w_empty[s], rw.phase() ^ 1);
           mbar_arrive_expect_tx(&w_full[s], 2 * kUnitBytes);
-          tma_load_2d(s_ring + s * kUnitBytes, &p.tmW2, &w_full[s], hid0 + j * kChunk + kb * 32, 0);
-          tma_load_2d(s_ring + (s + 1) * kUnitBytes, &p.tmW2, &w_full[s],
-                      hid0 + j * kChunk + kb * 32, 128);
-          rw.used(s);
-          rw.advance(2);
+          uint8_t* dst = s_ring + s * 2 * kUnitBytes;
+          tma_load_2d(dst, &p.tmW2, &w_full[s], hid0 + j * kChunk + kb * 32, 0);
+          tma_load_2d(dst + kUnitBytes, &p.tmW2, &w_full[s], hid0 + j * kChunk + kb * 32, 128);
+          rw.next();
         }
       };
       load_w1(0);
@@ -221,26 +226,29 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
           tc_fence_after_sync();
         }
         const uint32_t d = tmem_base + kColH + (j & 1) * kChunk;
-        for (int kb = 0; kb < 8; ++kb) {
+        for (int u = 0; u < 4; ++u) {
           const int s = rw.slot;
-          mbar_wait(&w_full[s], rw.phase(s));
+          mbar_wait(&w_full[s], rw.phase());
           tc_fence_after_sync();
-          const uint64_t a_desc = umma_desc_kmajor_sw128(x_addr + kb * kUnitBytes);
-          const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(s_ring + s * kUnitBytes));
+          const uint32_t b_addr = smem_u32(s_ring + s * 2 * kUnitBytes);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_ss<true>(d, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          for (int h = 0; h < 2; ++h) {
+            const int kb = 2 * u + h;
+            const uint64_t a_desc = umma_desc_kmajor_sw128(x_addr + kb * kUnitBytes);
+            const uint64_t b_desc = umma_desc_kmajor_sw128(b_addr + h * kUnitBytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_ss<true>(d, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          }
           umma_commit(&w_empty[s]);
-          rw.used(s);
-          rw.advance(1);
+          rw.next();
         }
         umma_commit(&h_full[j & 1]);
       };
       gemm1(0);
       gemm1(1);
       for (int j = 0; j < kNChunk; ++j) {
-        // the W2_j run occupies 4 even slots: account for their phase flips, then move past it
-        for (int kb = 0; kb < 4; ++kb) { rw.used(rw.slot); rw.advance(2); }
+        rw.skip(4);  // the W2_j run
         if (j + 2 < kNChunk) gemm1(j + 2);
       }
     }
@@ -249,28 +257,25 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc(UMMA_FMT_TF32, 128, 256);
       RingWalker rw;
-      // skip the two leading W1 runs (16 single-slot units)
-      for (int i = 0; i < 16; ++i) { rw.used(rw.slot); rw.advance(1); }
+      rw.skip(8);  // the two leading W1 runs
       for (int j = 0; j < kNChunk; ++j) {
         mbar_wait(&h_ready[j & 1], (j >> 1) & 1);  // activation of chunk j is back in TMEM
         tc_fence_after_sync();
         const uint32_t a0 = tmem_base + kColH + (j & 1) * kChunk;
         for (int kb = 0; kb < 4; ++kb) {
           const int s = rw.slot;
-          mbar_wait(&w_full[s], rw.phase(s));
+          mbar_wait(&w_full[s], rw.phase());
           tc_fence_after_sync();
-          const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(s_ring + s * kUnitBytes));
+          const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(s_ring + s * 2 * kUnitBytes));
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_ts_tf32(tmem_base + kColD2, a0 + kb * 32 + k * 8, b_desc + 2 * k, idesc,
                          (j | kb | k) ? 1u : 0u);
           umma_commit(&w_empty[s]);
-          rw.used(s);
-          rw.advance(2);
+          rw.next();
         }
         umma_commit(&h_free[j & 1]);
-        if (j + 2 < kNChunk)
-          for (int i = 0; i < 8; ++i) { rw.used(rw.slot); rw.advance(1); }  // skip W1_{j+2}
+        if (j + 2 < kNChunk) rw.skip(4);  // the W1_{j+2} run
       }
       umma_commit(d_full);
     }
