@@ -181,22 +181,31 @@ __device__ __forceinline__ void rowln_finish(const GemmParams& p, const float* s
     w2 = p.rowscale2[seg];
   }
     // PASS A: v0 = residual + alpha * (combine(acc) + bias)
+    // The residual row is read straight from global memory in this thread-per-row layout (each
+    // lane a different 1 KB row): the loads of chunk c+1 are issued before chunk c is processed
+    // so their L2 latency overlaps the TMEM traffic and the math instead of being exposed 8 times.
     float sum = 0.0f, dd1 = 0.0f, dd2 = 0.0f;
+    const bool has_res = p.residual != nullptr && valid;
+    const float4* rp0 = reinterpret_cast<const float4*>(
+        p.residual + (has_res ? static_cast<long long>(m) * p.ldr : 0));
+    float resn[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 f = has_res ? __ldg(rp0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      resn[4 * j] = f.x; resn[4 * j + 1] = f.y; resn[4 * j + 2] = f.z; resn[4 * j + 3] = f.w;
+    }
     for (int c = 0; c < 8; ++c) {
       uint32_t r[32];
       tmem_ld32(tacc + c * 32, r);
       float res[32];
-      if (p.residual != nullptr && valid) {
-        const float4* rp =
-            reinterpret_cast<const float4*>(p.residual + static_cast<long long>(m) * p.ldr + c * 32);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) res[j] = resn[j];
+      if (c + 1 < 8) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          float4 f = __ldg(rp + j);
-          res[4 * j] = f.x; res[4 * j + 1] = f.y; res[4 * j + 2] = f.z; res[4 * j + 3] = f.w;
+          const float4 f = has_res ? __ldg(rp0 + (c + 1) * 8 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          resn[4 * j] = f.x; resn[4 * j + 1] = f.y; resn[4 * j + 2] = f.z; resn[4 * j + 3] = f.w;
         }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) res[j] = 0.0f;
       }
       tmem_ld_wait();
       float v[32];
