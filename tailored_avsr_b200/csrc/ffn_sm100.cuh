@@ -139,7 +139,8 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
   uint64_t* h_ready = h_full + 2;            // [2]  activation written back
   uint64_t* h_free = h_ready + 2;            // [2]  GEMM2 finished reading the H buffer
   uint64_t* d_full = h_free + 2;             // [1]  all GEMM2 complete
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(d_full + 1);
+  uint64_t* w2_avail = d_full + 1;           // [3]  W2 unit landed (forwarded by the GEMM1 issuer)
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(w2_avail + kSuper);
 
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
@@ -155,6 +156,7 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
     for (int i = 0; i < kSuper; ++i) {
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
+      mbar_init(&w2_avail[i], 1);
     }
     mbar_init(x_full, 1);
     for (int i = 0; i < 2; ++i) {
@@ -245,10 +247,21 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
         }
         umma_commit(&h_full[j & 1]);
       };
+      // This thread is the ONLY waiter on w_full: it observes every unit in FIFO order (an mbarrier
+      // parity wait is only sound for a waiter that has seen every earlier phase) and forwards the
+      // arrival of W2 units to the GEMM2 issuer through w2_avail.
+      auto forward_w2 = [&]() {
+        for (int kb = 0; kb < 4; ++kb) {
+          const int s = rw.slot;
+          mbar_wait(&w_full[s], rw.phase());
+          mbar_arrive(&w2_avail[s]);
+          rw.next();
+        }
+      };
       gemm1(0);
       gemm1(1);
       for (int j = 0; j < kNChunk; ++j) {
-        rw.skip(4);  // the W2_j run
+        forward_w2();
         if (j + 2 < kNChunk) gemm1(j + 2);
       }
     }
@@ -256,15 +269,17 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
     // ===================================== GEMM2 issuer =====================================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc(UMMA_FMT_TF32, 128, 256);
-      RingWalker rw;
-      rw.skip(8);  // the two leading W1 runs
+      // slot sequence of the shared FIFO, but phase bits only for this thread's own barrier
+      // (w2_avail): it waits on every phase of it, in order
+      int slot = (8 % kSuper);   // after the two leading W1 runs (8 units)
+      uint32_t parity2 = 0;
       for (int j = 0; j < kNChunk; ++j) {
         mbar_wait(&h_ready[j & 1], (j >> 1) & 1);  // activation of chunk j is back in TMEM
         tc_fence_after_sync();
         const uint32_t a0 = tmem_base + kColH + (j & 1) * kChunk;
         for (int kb = 0; kb < 4; ++kb) {
-          const int s = rw.slot;
-          mbar_wait(&w_full[s], rw.phase());
+          const int s = slot;
+          mbar_wait(&w2_avail[s], (parity2 >> s) & 1u);
           tc_fence_after_sync();
           const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(s_ring + s * 2 * kUnitBytes));
 #pragma unroll
@@ -272,10 +287,11 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
             umma_ts_tf32(tmem_base + kColD2, a0 + kb * 32 + k * 8, b_desc + 2 * k, idesc,
                          (j | kb | k) ? 1u : 0u);
           umma_commit(&w_empty[s]);
-          rw.next();
+          parity2 ^= 1u << s;
+          if (++slot == kSuper) slot = 0;
         }
         umma_commit(&h_free[j & 1]);
-        if (j + 2 < kNChunk) rw.skip(4);  // the W1_{j+2} run
+        if (j + 2 < kNChunk) slot = (slot + 4) % kSuper;  // the W1_{j+2} run
       }
       umma_commit(d_full);
     }
