@@ -98,10 +98,10 @@ relpos_attn_kernel(const float* __restrict__ qkv, long long ld_qkv, const float*
       const int c0 = ks * 8 + 2 * t, c1 = c0 + 1;
       const float u0 = __ldg(bias_u + h * kD + c0), u1 = __ldg(bias_u + h * kD + c1);
       const float v0 = __ldg(bias_v + h * kD + c0), v1 = __ldg(bias_v + h * kD + c1);
-      const float q00 = r0 < T ? __ldg(qbase + (row_base + r0) * ld_qkv + c0) : 0.f;
-      const float q10 = r1 < T ? __ldg(qbase + (row_base + r1) * ld_qkv + c0) : 0.f;
-      const float q01 = r0 < T ? __ldg(qbase + (row_base + r0) * ld_qkv + c1) : 0.f;
-      const float q11 = r1 < T ? __ldg(qbase + (row_base + r1) * ld_qkv + c1) : 0.f;
+      const float q00 = r0 < T ? ld_act(qbase + (row_base + r0) * ld_qkv + c0) : 0.f;
+      const float q10 = r1 < T ? ld_act(qbase + (row_base + r1) * ld_qkv + c0) : 0.f;
+      const float q01 = r0 < T ? ld_act(qbase + (row_base + r0) * ld_qkv + c1) : 0.f;
+      const float q11 = r1 < T ? ld_act(qbase + (row_base + r1) * ld_qkv + c1) : 0.f;
       qu[ks][0] = tf32_bits(q00 + u0); qu[ks][1] = tf32_bits(q10 + u0);
       qu[ks][2] = tf32_bits(q01 + u1); qu[ks][3] = tf32_bits(q11 + u1);
       qv[ks][0] = tf32_bits(q00 + v0); qv[ks][1] = tf32_bits(q10 + v0);

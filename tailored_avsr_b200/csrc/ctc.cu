@@ -47,7 +47,7 @@ ctc_head_kernel(const float* __restrict__ hs, long long ldh, const float* __rest
       const int f = i / D, k = i % D;
       float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
       if (m0 + f < M)
-        x = __ldg(reinterpret_cast<const float4*>(hs + static_cast<long long>(m0 + f) * ldh + k));
+        x = ld_act4(reinterpret_cast<const float4*>(hs + static_cast<long long>(m0 + f) * ldh + k));
       *reinterpret_cast<float4*>(hw + i) = x;
     }
     __syncwarp();
@@ -196,8 +196,8 @@ ctc_loss_kernel(const float* __restrict__ logp, const int64_t* __restrict__ targ
   float pre0 = 0.f, pre1 = 0.f;
   auto fetch = [&](int t) {
     if (t >= 0 && t < Tb) {
-      if (lane < V) pre0 = __ldg(lp + static_cast<long long>(t) * V + lane);
-      if (lane + 32 < V) pre1 = __ldg(lp + static_cast<long long>(t) * V + lane + 32);
+      if (lane < V) pre0 = ld_act(lp + static_cast<long long>(t) * V + lane);
+      if (lane + 32 < V) pre1 = ld_act(lp + static_cast<long long>(t) * V + lane + 32);
     }
   };
   auto commit = [&](int buf) {

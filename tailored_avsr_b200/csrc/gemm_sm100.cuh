@@ -191,7 +191,7 @@ __device__ __forceinline__ void rowln_finish(const GemmParams& p, const float* s
     float resn[32];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float4 f = has_res ? __ldg(rp0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 f = has_res ? ld_act4(rp0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
       resn[4 * j] = f.x; resn[4 * j + 1] = f.y; resn[4 * j + 2] = f.z; resn[4 * j + 3] = f.w;
     }
     for (int c = 0; c < 8; ++c) {
@@ -203,7 +203,7 @@ __device__ __forceinline__ void rowln_finish(const GemmParams& p, const float* s
       if (c + 1 < 8) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 f = has_res ? __ldg(rp0 + (c + 1) * 8 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 f = has_res ? ld_act4(rp0 + (c + 1) * 8 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
           resn[4 * j] = f.x; resn[4 * j + 1] = f.y; resn[4 * j + 2] = f.z; resn[4 * j + 3] = f.w;
         }
       }

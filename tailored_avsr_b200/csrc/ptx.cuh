@@ -44,6 +44,28 @@ __device__ __forceinline__ void pdl_launch_dependents() {
 }
 __device__ __forceinline__ void pdl_wait() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  // The L1 invalidation that normally happens at a kernel-launch boundary took place when THIS
+  // grid was launched, i.e. possibly before the predecessor wrote its outputs: lines of an older
+  // tensor that lived at the same address may still sit in this SM's L1.  A gpu-scope fence
+  // invalidates L1 (CCTL.IVALL) so the loads below see the predecessor's data.
+  __threadfence();
+}
+
+// Loads of ACTIVATIONS (data produced by an earlier kernel).  Never use __ldg / ld.global.nc for
+// them: under programmatic dependent launch the producer may still be running when this kernel
+// starts, which breaks the "read-only for the lifetime of the kernel" contract of the
+// non-coherent path.  Weights (constant across the whole stream) may keep using __ldg.
+__device__ __forceinline__ float ld_act(const float* p) {
+  float v;
+  asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ld_act4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -29,7 +29,7 @@ layernorm_kernel(const float* __restrict__ x, long long ldx, int M, float eps,
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < kVec; ++i) {
-    v[i] = __ldg(xr + lane + 32 * i);
+    v[i] = ld_act4(xr + lane + 32 * i);
     sum += v[i].x + v[i].y + v[i].z + v[i].w;
   }
   const float inv_d = 1.0f / (128.0f * kVec);
@@ -77,7 +77,7 @@ csgu_stats_kernel(const float* __restrict__ h, long long ldh, int M, int Ch, flo
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < kVec; ++i) {
-    v[i] = __ldg(g + lane + 32 * i);
+    v[i] = ld_act4(g + lane + 32 * i);
     sum += v[i].x + v[i].y + v[i].z + v[i].w;
   }
   const float inv_d = 1.0f / (128.0f * kVec);
@@ -164,7 +164,7 @@ csgu_conv_kernel(const float* __restrict__ h, long long ldh, const float* __rest
     if (tb >= T) break;
     float rv[kGrp];          // carried half, loaded early so the latency hides behind the FMAs
 #pragma unroll
-    for (int o = 0; o < kGrp; ++o) rv[o] = tb + o < T ? __ldg(rcol + (row0 + tb + o) * ldh) : 0.f;
+    for (int o = 0; o < kGrp; ++o) rv[o] = tb + o < T ? ld_act(rcol + (row0 + tb + o) * ldh) : 0.f;
     float acc[kGrp];
 #pragma unroll
     for (int o = 0; o < kGrp; ++o) acc[o] = 0.f;
