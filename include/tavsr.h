@@ -205,10 +205,25 @@ int tavsr_merge_learned_ave_weights(const float* dots1, const float* dots2, cons
 
 /* ------------------------------------------------------------------------------------------------
  * CTC head: logits = hs . W^T + b in fp32 FMA (argmax must be bit-stable), then log-softmax /
- * softmax / argmax over V <= 64 (ctc.py:143,160-188).  Any of lp / prob / amax may be NULL.
+ * softmax / argmax over V <= 64 (ctc.py:143,160-188).  Any of logits / logp / prob / amax may be NULL.
  * ---------------------------------------------------------------------------------------------- */
 int tavsr_ctc_head(const float* hs, long long ldh, const float* w /* [V,D] */, const float* b,
-                   float* logp, float* prob, int64_t* amax, int M, int D, int V, void* stream);
+                   float* logits, float* logp, float* prob, int64_t* amax, int M, int D, int V,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Vocabulary residual  out = x + p . W^T + b,  p (M,V) posteriors, W (D,V):
+ *   - InterCTC self-conditioning  x + conditioning_layer(ctc.softmax(after_norm(x)))
+ *     (src/encoder/branchformer/encoder.py:393-399);
+ *   - InterCTCResidualModule      x + proj_2(softmax(proj_1(x)))
+ *     (src/ctc/interctc_residual_module.py:11-16).
+ * When xn != NULL it also receives LayerNorm(out; ln_g, ln_b, eps) — the next block's
+ * norm_ff_macaron, so the conditioned stream needs no extra pass.  D in {128,256,512}, V <= 64.
+ * ---------------------------------------------------------------------------------------------- */
+int tavsr_vocab_residual(const float* x, long long ldx, const float* p, const float* w /* [D,V] */,
+                         const float* b, float* out, long long ldo, const float* ln_g,
+                         const float* ln_b, float eps, float* xn, long long ldn, int M, int D, int V,
+                         void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * CTC loss, log domain, blank = 0 (torch.nn.CTCLoss(reduction="none", zero_infinity) at

@@ -64,6 +64,12 @@ CASES = {
     # conventional AV encoder: two independent stacks (configs/AVSR/conventional_...spanish.yaml)
     "av_conventional_small": dict(kind="conventional", cfg=_enc(num_blocks=2, input_layer=None),
                                   B=2, T=48, lens=[48, 31], vocab=37, Lmax=12, seed=17),
+    # dormant InterCTC path: taps after blocks 1 and 2 + self-conditioning (encoder.py:378-401);
+    # the model assigns conditioning_layer = Linear(V, d) (espnet_model.py:106-112)
+    "asr_interctc_cond": dict(kind="single", input_size=512,
+                              cfg=_enc(num_blocks=3, input_layer="linear", interctc_layer_idx=[1, 2],
+                                       interctc_use_conditioning=True),
+                              B=2, Tin=64, lens=[64, 39], vocab=41, Lmax=10, seed=19),
     # full-depth C1: 12 layers, B=8 x 10 s
     "asr_c1": dict(kind="single", input_size=80, cfg=_enc(), B=8, Tin=1001, lens=[1001] * 8,
                    vocab=41, Lmax=100, seed=1, stride_t=8, stride_d=4),

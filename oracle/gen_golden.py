@@ -35,6 +35,8 @@ def build_reference(ref, name):
                                       output_size=cfg["output_size"])
     ctc = ref.CTC(odim=c["vocab"], encoder_output_size=cfg["output_size"], dropout_rate=0.0,
                   ctc_type="builtin", reduce=True)
+    if cfg.get("interctc_use_conditioning", False):
+        enc.conditioning_layer = torch.nn.Linear(c["vocab"], cfg["output_size"])  # espnet_model.py:106-112
     enc.eval()
     ctc.eval()
     synth.fill_module(enc, seed=c["seed"], hot=c.get("hot", False))
@@ -49,8 +51,13 @@ def run_case(ref, name):
     out = {}
     with torch.no_grad():
         if c["kind"] == "single":
-            y, olens, _ = enc(inp["x"], inp["lens"])
-            streams = {"out": y}
+            y, olens, _ = enc(inp["x"], inp["lens"], ctc=ctc)
+            streams = {}
+            if isinstance(y, tuple):
+                y, inter = y
+                for idx, t in inter:
+                    streams[f"inter_{idx}"] = t
+            streams["out"] = y
             weights = [(getattr(l, "weight_global", None), getattr(l, "weight_local", None))
                        for l in enc.encoders]
         else:
@@ -92,14 +99,19 @@ def run_case(ref, name):
 def main():
     ref = reference_loader.load()
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    only = sys.argv[1:]  # optional: regenerate just the named cases
+    man = os.path.join(GOLDEN_DIR, "MANIFEST.json")
     meta = {"torch": torch.__version__, "cases": {}}
-    for name in cases.CASES:
+    if only and os.path.exists(man):
+        with open(man) as f:
+            meta = json.load(f)
+    for name in (only or cases.CASES):
         res = run_case(ref, name)
         np.savez_compressed(os.path.join(GOLDEN_DIR, f"{name}.npz"), **res)
         meta["cases"][name] = {"ctc_loss": float(res["ctc_loss"]), "n_params": int(res["n_params"]),
                                "out_shape": list(res["out"].shape)}
         print(name, meta["cases"][name], flush=True)
-    with open(os.path.join(GOLDEN_DIR, "MANIFEST.json"), "w") as f:
+    with open(man, "w") as f:
         json.dump(meta, f, indent=1)
 
 

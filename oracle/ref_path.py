@@ -182,7 +182,9 @@ def conv2d_subsample(x: torch.Tensor, mask: torch.Tensor, sd: SD, prefix: str) -
 def branchformer_encoder(xs: torch.Tensor, ilens: torch.Tensor, sd: SD, cfg: dict, prefix: str = ""
                          ) -> Tuple[torch.Tensor, torch.Tensor, List[Optional[Tuple]]]:
     """Eval-mode restatement of MyBranchformerEncoder.forward (encoder.py:324-412), plain loop
-    (:376), input_layer in {conv2d, linear, None}.  Returns (out, olens, per-layer merge weights)."""
+    (:376) or the InterCTC loop (:378-401) when cfg["interctc_layer_idx"] is set, input_layer in
+    {conv2d, linear, None}.  Returns (out, olens, per-layer merge weights); the tapped outputs are
+    left in cfg-independent form on the function attribute `last_taps` [(idx, tensor)]."""
     d = cfg.get("output_size", 256)
     n = cfg.get("num_blocks", 12)
     masks = make_valid_mask(ilens, xs.shape[1])
@@ -202,6 +204,8 @@ def branchformer_encoder(xs: torch.Tensor, ilens: torch.Tensor, sd: SD, cfg: dic
     cw = cfg.get("cgmlp_weight", 0.5)
     cw = [cw] * n if isinstance(cw, float) else list(cw)
     weights = []
+    taps = tuple(cfg.get("interctc_layer_idx", ()))
+    tap_outs = []
     for l in range(n):
         xs, w = branchformer_layer(
             xs, pos, masks, sd, f"{prefix}encoders.{l}", heads=cfg.get("attention_heads", 4),
@@ -209,6 +213,14 @@ def branchformer_encoder(xs: torch.Tensor, ilens: torch.Tensor, sd: SD, cfg: dic
             merge_method=cfg.get("merge_method", "learned_ave"), cgmlp_weight=cw[l],
             use_attn=cfg.get("use_attn", True), use_cgmlp=cfg.get("use_cgmlp", True))
         weights.append(w)
+        if (l + 1) in taps:
+            tap = layer_norm(xs, sd, prefix + "after_norm")  # :386-388
+            tap_outs.append((l + 1, tap))
+            if cfg.get("interctc_use_conditioning", False):  # :392-401
+                post = torch.softmax(F.linear(tap, sd["ctc.ctc_lo.weight"], sd["ctc.ctc_lo.bias"]), 2)
+                xs = xs + F.linear(post, sd[prefix + "conditioning_layer.weight"],
+                                   sd[prefix + "conditioning_layer.bias"])
+    branchformer_encoder.last_taps = tap_outs
     xs = layer_norm(xs, sd, prefix + "after_norm")
     return xs, masks.squeeze(1).sum(1), weights
 
@@ -282,6 +294,13 @@ def _encoder_with_mask(x_pos, masks, sd, cfg, prefix):
 # --------------------------------------------------------------------------------------------------
 # CTC (src/ctc/ctc.py)
 # --------------------------------------------------------------------------------------------------
+def interctc_residual(x: torch.Tensor, sd: SD, prefix: str = "") -> Tuple[torch.Tensor, torch.Tensor]:
+    """InterCTCResidualModule.forward (src/ctc/interctc_residual_module.py:11-16)."""
+    logits = F.linear(x, sd[prefix + "proj_1.weight"], sd[prefix + "proj_1.bias"])
+    y = x + F.linear(torch.softmax(logits, -1), sd[prefix + "proj_2.weight"], sd[prefix + "proj_2.bias"])
+    return y, logits
+
+
 def ctc_log_softmax(hs: torch.Tensor, sd: SD, prefix: str = "ctc_lo") -> torch.Tensor:
     """CTC.log_softmax (ctc.py:170-178)."""
     return F.log_softmax(F.linear(hs, sd[prefix + ".weight"], sd[prefix + ".bias"]), dim=2)

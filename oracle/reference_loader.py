@@ -28,12 +28,14 @@ def load():
     from types import SimpleNamespace
 
     from src.ctc.ctc import CTC
+    from src.ctc.interctc_residual_module import InterCTCResidualModule
     from src.encoder.audiovisual.conventional.encoder import ConventionalEncoder
     from src.encoder.audiovisual.tailored.encoder import TailoredEncoder
     from src.encoder.audiovisual.tailored.encoder_layer import TailoredEncoderLayer
     from src.encoder.branchformer.encoder import MyBranchformerEncoder
     from src.encoder.branchformer.encoder_layer import MyBranchformerEncoderLayer
-    return SimpleNamespace(CTC=CTC, ConventionalEncoder=ConventionalEncoder,
+    return SimpleNamespace(CTC=CTC, InterCTCResidualModule=InterCTCResidualModule,
+                           ConventionalEncoder=ConventionalEncoder,
                            TailoredEncoder=TailoredEncoder, TailoredEncoderLayer=TailoredEncoderLayer,
                            MyBranchformerEncoder=MyBranchformerEncoder,
                            MyBranchformerEncoderLayer=MyBranchformerEncoderLayer)

@@ -83,7 +83,10 @@ SIGNATURES = {
                                                 c_float, c_float, c_float, c_void_p, c_void_p,
                                                 c_int, c_int, c_void_p]),
     "tavsr_ctc_head": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,
-                               c_void_p, c_int, c_int, c_int, c_void_p]),
+                               c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "tavsr_vocab_residual": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_longlong, c_void_p, c_void_p, c_float, c_void_p, c_longlong,
+                                     c_int, c_int, c_int, c_void_p]),
     "tavsr_ctc_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "tavsr_ctc_loss": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_int, c_int,

@@ -22,8 +22,9 @@ constexpr int kVPad = 64;  // V <= 64 (EN 41, ES 37)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 ctc_head_kernel(const float* __restrict__ hs, long long ldh, const float* __restrict__ w,
-                const float* __restrict__ bias, float* __restrict__ logp, float* __restrict__ prob,
-                int64_t* __restrict__ amax, int M, int D, int V) {
+                const float* __restrict__ bias, float* __restrict__ logits,
+                float* __restrict__ logp, float* __restrict__ prob, int64_t* __restrict__ amax, int M,
+                int D, int V) {
   pdl_launch_dependents();
   extern __shared__ float sm[];
   float* Wt = sm;                       // [D][64]
@@ -90,6 +91,10 @@ ctc_head_kernel(const float* __restrict__ hs, long long ldh, const float* __rest
       const float e1 = lane + 32 < V ? expf(x1 - bv) : 0.f;
       const float se = warp_sum(e0 + e1);
       const float lse = bv + logf(se);
+      if (logits) {
+        if (lane < V) logits[static_cast<long long>(m) * V + lane] = x0;
+        if (lane + 32 < V) logits[static_cast<long long>(m) * V + lane + 32] = x1;
+      }
       if (logp) {
         if (lane < V) logp[static_cast<long long>(m) * V + lane] = x0 - lse;
         if (lane + 32 < V) logp[static_cast<long long>(m) * V + lane + 32] = x1 - lse;
@@ -100,6 +105,73 @@ ctc_head_kernel(const float* __restrict__ hs, long long ldh, const float* __rest
         if (lane + 32 < V) prob[static_cast<long long>(m) * V + lane + 32] = e1 * inv;
       }
       if (amax && lane == 0) amax[m] = bi;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Vocabulary residual: out = x + p . W^T + b with p (M,V) posteriors and W (D,V) — the InterCTC
+// self-conditioning update (encoder.py:393-399) and the second half of InterCTCResidualModule
+// (interctc_residual_module.py:14).  Optionally also the LayerNorm of the updated row (the next
+// block's norm_ff_macaron), so the conditioned stream needs no extra pass.  One warp per frame,
+// lane owns channels lane + 32 c; W^T is staged once per CTA.
+// ------------------------------------------------------------------------------------------------
+template <int kC>
+__global__ void __launch_bounds__(256)
+vocab_residual_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ p,
+                      const float* __restrict__ w, const float* __restrict__ bias,
+                      float* __restrict__ out, long long ldo, const float* __restrict__ ln_g,
+                      const float* __restrict__ ln_b, float eps, float* __restrict__ xn,
+                      long long ldn, int M, int V) {
+  pdl_launch_dependents();
+  constexpr int D = kC * 32;
+  extern __shared__ float sm[];
+  float* Wt = sm;  // [V][D]
+  for (int i = threadIdx.x; i < V * D; i += 256) {
+    const int v = i / D, d = i % D;
+    Wt[i] = __ldg(w + static_cast<long long>(d) * V + v);
+  }
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  float bb[kC], gg[kC], be[kC];
+#pragma unroll
+  for (int c = 0; c < kC; ++c) {
+    bb[c] = __ldg(bias + lane + 32 * c);
+    gg[c] = ln_g ? __ldg(ln_g + lane + 32 * c) : 1.f;
+    be[c] = ln_b ? __ldg(ln_b + lane + 32 * c) : 0.f;
+  }
+  __syncthreads();
+  pdl_wait();
+  for (int m = blockIdx.x * 8 + warp; m < M; m += gridDim.x * 8) {
+    const float p0 = lane < V ? ld_act(p + static_cast<long long>(m) * V + lane) : 0.f;
+    const float p1 = lane + 32 < V ? ld_act(p + static_cast<long long>(m) * V + lane + 32) : 0.f;
+    float acc[kC];
+#pragma unroll
+    for (int c = 0; c < kC; ++c) acc[c] = bb[c];
+    for (int v = 0; v < V; ++v) {
+      const float pv = __shfl_sync(0xffffffffu, v < 32 ? p0 : p1, v & 31);
+#pragma unroll
+      for (int c = 0; c < kC; ++c) acc[c] = fmaf(pv, Wt[v * D + lane + 32 * c], acc[c]);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < kC; ++c) {
+      acc[c] += ld_act(x + static_cast<long long>(m) * ldx + lane + 32 * c);
+      out[static_cast<long long>(m) * ldo + lane + 32 * c] = acc[c];
+      sum += acc[c];
+    }
+    if (xn) {
+      const float mean = warp_sum(sum) * (1.0f / D);
+      float var = 0.f;
+#pragma unroll
+      for (int c = 0; c < kC; ++c) {
+        const float d = acc[c] - mean;
+        var = fmaf(d, d, var);
+      }
+      const float rstd = rsqrtf(warp_sum(var) * (1.0f / D) + eps);
+#pragma unroll
+      for (int c = 0; c < kC; ++c)
+        xn[static_cast<long long>(m) * ldn + lane + 32 * c] = (acc[c] - mean) * rstd * gg[c] + be[c];
     }
   }
 }
@@ -422,8 +494,8 @@ ctc_prefix_kernel(const float* __restrict__ logp, const float* __restrict__ r_pr
 using namespace tavsr;
 
 extern "C" int tavsr_ctc_head(const float* hs, long long ldh, const float* w, const float* b,
-                              float* logp, float* prob, int64_t* amax, int M, int D, int V,
-                              void* stream) {
+                              float* logits, float* logp, float* prob, int64_t* amax, int M,
+                              int D, int V, void* stream) {
   TAVSR_REQUIRE(M > 0 && D > 0 && D % 4 == 0 && D <= 512, "ctc_head: bad D=%d", D);
   TAVSR_REQUIRE(V > 0 && V <= ctc::kVPad, "ctc_head: V=%d > 64 not built", V);
   TAVSR_REQUIRE(hs && w && b && ldh % 4 == 0, "ctc_head: bad arguments");
@@ -438,8 +510,39 @@ extern "C" int tavsr_ctc_head(const float* hs, long long ldh, const float* w, co
   const int groups = (M + 3) / 4;
   int grid = (groups + 7) / 8;
   if (grid > 2 * num_sms()) grid = 2 * num_sms();
-  TAVSR_CUDA_OK(launch_kernel(ctc::ctc_head_kernel, dim3(grid), dim3(256), smem, s, 0, hs, ldh, w, b, logp,
-                              prob, amax, M, D, V));
+  TAVSR_CUDA_OK(launch_kernel(ctc::ctc_head_kernel, dim3(grid), dim3(256), smem, s, 0, hs, ldh, w, b, logits,
+                              logp, prob, amax, M, D, V));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+extern "C" int tavsr_vocab_residual(const float* x, long long ldx, const float* p, const float* w,
+                                    const float* b, float* out, long long ldo, const float* ln_g,
+                                    const float* ln_b, float eps, float* xn, long long ldn, int M,
+                                    int D, int V, void* stream) {
+  TAVSR_REQUIRE(M > 0 && (D == 128 || D == 256 || D == 512), "vocab_residual: D=%d not built", D);
+  TAVSR_REQUIRE(V > 0 && V <= ctc::kVPad, "vocab_residual: V=%d > 64 not built", V);
+  TAVSR_REQUIRE(x && p && w && b && out, "vocab_residual: null pointer");
+  TAVSR_REQUIRE(!xn || (ln_g && ln_b), "vocab_residual: LayerNorm output needs gamma and beta");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int smem = V * D * 4;
+  int grid = (M + 7) / 8;
+  if (grid > 2 * num_sms()) grid = 2 * num_sms();
+#define TAVSR_VR_CASE(C)                                                                        \
+  do {                                                                                          \
+    static int configured = 0;                                                                  \
+    if (configured < smem) {                                                                    \
+      TAVSR_CUDA_OK(cudaFuncSetAttribute(ctc::vocab_residual_kernel<C>,                         \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));   \
+      configured = smem;                                                                        \
+    }                                                                                           \
+    TAVSR_CUDA_OK(launch_kernel(ctc::vocab_residual_kernel<C>, dim3(grid), dim3(256), smem, s, 0, x, \
+                                ldx, p, w, b, out, ldo, ln_g, ln_b, eps, xn, ldn, M, V));       \
+  } while (0)
+  if (D == 128) TAVSR_VR_CASE(4);
+  else if (D == 256) TAVSR_VR_CASE(8);
+  else TAVSR_VR_CASE(16);
+#undef TAVSR_VR_CASE
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }

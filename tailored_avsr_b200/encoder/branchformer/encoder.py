@@ -210,9 +210,11 @@ class MyBranchformerEncoder(AbsEncoder):
             xn = ops.layernorm(x, first_norm[0], first_norm[1], eps=1e-12)
         return x, xn, pos_emb, masks, B, T
 
-    def run_blocks(self, x, xn, pos_emb, lens, B, T, taps=(), stop_after: Optional[int] = None):
+    def run_blocks(self, x, xn, pos_emb, lens, B, T, taps=(), stop_after: Optional[int] = None,
+                   ctc=None):
         """The block stack on 2-D activations.  Returns (out, tap_outputs) where `out` already went
-        through after_norm when normalize_before."""
+        through after_norm when normalize_before.  With `interctc_use_conditioning` the tapped
+        posteriors are fed back, x += conditioning_layer(ctc.softmax(tap)) (encoder.py:393-401)."""
         pos = self._pos_proj_all(pos_emb)
         n = len(self.encoders)
         last = n - 1 if stop_after is None else min(stop_after, n - 1)
@@ -233,6 +235,11 @@ class MyBranchformerEncoder(AbsEncoder):
                 if self.normalize_before:
                     t_out = yn if i == last else ops.layernorm(y, after[0], after[1], eps=1e-12)
                 tap_outs.append((i + 1, t_out.view(B, T, -1)))
+                if self.interctc_use_conditioning:
+                    prob = ctc.softmax(t_out.view(B, T, -1))
+                    cl = self.conditioning_layer
+                    y, yn = ops.vocab_residual(y, prob.reshape(B * T, -1).contiguous(),
+                                               cl.weight.contiguous(), cl.bias, ln=next_norm)
             x, xn = y, yn
         out = xn if self.normalize_before else x
         return out, tap_outs
@@ -244,8 +251,9 @@ class MyBranchformerEncoder(AbsEncoder):
         x_in = xs_pad[0] if isinstance(xs_pad, tuple) else xs_pad
         engine.require_inference(self, x_in)
         if self.interctc_use_conditioning and len(self.interctc_layer_idx) > 0:
-            raise NotImplementedError("InterCTC self-conditioning is not built on the B200 path yet "
-                                      "(no shipped config enables it; interctc_weight is 0.0)")
+            if ctc is None or self.conditioning_layer is None:
+                raise ValueError("InterCTC self-conditioning needs the `ctc` module and an assigned "
+                                 "`conditioning_layer` (espnet_model.py:106-112)")
         Tin = x_in.size(1)
         dev = x_in.device
         # ~make_pad_mask(ilens)[:, None, :] built on the device: no .tolist() host sync (:345)
@@ -258,7 +266,7 @@ class MyBranchformerEncoder(AbsEncoder):
         if len(self.interctc_layer_idx) == 0 and max_layer is not None and 0 <= max_layer < len(self.encoders):
             stop = max_layer
         out, taps = self.run_blocks(x, xn, pos_emb, lens, B, T, taps=tuple(self.interctc_layer_idx),
-                                    stop_after=stop)
+                                    stop_after=stop, ctc=ctc)
         out = out.view(B, T, self._output_size)
         olens = masks.squeeze(1).sum(1)
         if len(taps) > 0:

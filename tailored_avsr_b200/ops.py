@@ -18,7 +18,7 @@ from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SWISH, DT_TF32, FfnArgs, Row
 __all__ = [
     "ACT_NONE", "ACT_SWISH", "ACT_GELU", "ACT_RELU",
     "gemm_bias_act", "gemm_rowln", "ffn_fused", "layernorm", "relpos_attn", "csgu", "merge_weights",
-    "ctc_head", "ctc_loss", "ctc_greedy", "ctc_prefix_score", "launch_count",
+    "ctc_head", "vocab_residual", "ctc_loss", "ctc_greedy", "ctc_prefix_score", "launch_count",
 ]
 
 
@@ -272,18 +272,42 @@ def merge_weights(dots1: torch.Tensor, dots2: torch.Tensor, lens: Optional[torch
 
 @_profiled
 def ctc_head(hs: torch.Tensor, w: torch.Tensor, b: torch.Tensor, want_logp: bool = True,
-             want_prob: bool = False, want_argmax: bool = False):
-    """(logp, prob, argmax) of ctc_lo(hs) over the vocabulary, fp32 FMA (tavsr_ctc_head)."""
+             want_prob: bool = False, want_argmax: bool = False, want_logits: bool = False):
+    """(logp, prob, argmax[, logits]) of ctc_lo(hs) over the vocabulary, fp32 FMA
+    (tavsr_ctc_head)."""
     _chk2d(hs, "hs")
     M, D = hs.shape
     V = w.shape[0]
     logp = torch.empty((M, V), device=hs.device, dtype=torch.float32) if want_logp else None
     prob = torch.empty((M, V), device=hs.device, dtype=torch.float32) if want_prob else None
     amax = torch.empty((M,), device=hs.device, dtype=torch.int64) if want_argmax else None
+    logits = torch.empty((M, V), device=hs.device, dtype=torch.float32) if want_logits else None
     check(_lib.load().tavsr_ctc_head(hs.data_ptr(), hs.stride(0), w.data_ptr(), b.data_ptr(),
-                                     _p(logp), _p(prob), _p(amax), M, D, V, _stream()),
+                                     _p(logits), _p(logp), _p(prob), _p(amax), M, D, V, _stream()),
           "tavsr_ctc_head")
+    if want_logits:
+        return logp, prob, amax, logits
     return logp, prob, amax
+
+
+@_profiled
+def vocab_residual(x: torch.Tensor, p: torch.Tensor, w: torch.Tensor, b: torch.Tensor,
+                   ln: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, eps: float = 1e-12):
+    """out = x + p @ w.T + b  (p (M,V) posteriors, w (D,V)); with `ln` also LayerNorm(out)
+    (tavsr_vocab_residual).  Returns (out, xn-or-None)."""
+    _chk2d(x, "x")
+    _chk2d(p, "p")
+    M, D = x.shape
+    V = p.shape[1]
+    if w.shape != (D, V) or not w.is_contiguous() or not p.is_contiguous():
+        raise ValueError("vocab_residual: w must be a contiguous (D,V) matrix, p contiguous (M,V)")
+    out = torch.empty((M, D), device=x.device, dtype=torch.float32)
+    xn = torch.empty((M, D), device=x.device, dtype=torch.float32) if ln is not None else None
+    check(_lib.load().tavsr_vocab_residual(
+        x.data_ptr(), x.stride(0), p.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(),
+        out.stride(0), _p(ln[0]) if ln else None, _p(ln[1]) if ln else None, eps, _p(xn),
+        xn.stride(0) if xn is not None else 0, M, D, V, _stream()), "tavsr_vocab_residual")
+    return out, xn
 
 
 @_profiled

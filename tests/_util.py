@@ -31,6 +31,8 @@ def build_dropin(name):
                                   output_size=cfg["output_size"])
     ctc = CTC(odim=c["vocab"], encoder_output_size=cfg["output_size"], dropout_rate=0.0,
               ctc_type="builtin", reduce=True)
+    if cfg.get("interctc_use_conditioning", False):
+        enc.conditioning_layer = torch.nn.Linear(c["vocab"], cfg["output_size"])
     enc.eval()
     ctc.eval()
     sd = synth.fill_module(enc, seed=c["seed"], hot=c.get("hot", False))
@@ -47,6 +49,8 @@ def run_oracle(name, sd):
         if c["kind"] == "single":
             y, olens, w = ref_path.branchformer_encoder(inp["x"], inp["lens"], sd, c["cfg"])
             res.update(out=y, olens=olens, weights=w)
+            for idx, t in ref_path.branchformer_encoder.last_taps:
+                res[f"inter_{idx}"] = t
         else:
             d = c["cfg"]["output_size"]
             T = c["T"]

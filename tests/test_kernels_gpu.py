@@ -361,3 +361,22 @@ def _ffn_case(ops, M, variant):
         v1 = _ln(v0, g0.double(), b0.double(), 1e-12)
         assert rel_fro(main, v1) < 3e-3, rel_fro(main, v1)
         assert rel_fro(oA, _ln(v1, gA.double(), bA.double(), 1e-12)) < 3e-3
+
+
+@pytest.mark.parametrize("M,D,V,ln", [(70, 256, 41, True), (9, 128, 64, False), (33, 512, 37, True)])
+def test_vocab_residual(M, D, V, ln):
+    ops = _ops()
+    g = torch.Generator().manual_seed(M + V)
+    x = torch.randn(M + 3, D, generator=g)[:M]
+    p = torch.randn(M, V, generator=g).softmax(-1)
+    w = torch.randn(D, V, generator=g)
+    b = torch.randn(D, generator=g)
+    gam, bet = 1 + 0.1 * torch.randn(D, generator=g), 0.1 * torch.randn(D, generator=g)
+    out, xn = ops.vocab_residual(x.to(DEV), p.to(DEV), w.to(DEV), b.to(DEV),
+                                 ln=(gam.to(DEV), bet.to(DEV)) if ln else None, eps=1e-12)
+    want = x + p @ w.t() + b
+    assert (out.cpu() - want).abs().max() < 1e-5 * max(1.0, float(want.abs().max()))
+    if ln:
+        assert (xn.cpu() - F.layer_norm(want, (D,), gam, bet, 1e-12)).abs().max() < 2e-5
+    else:
+        assert xn is None

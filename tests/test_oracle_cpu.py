@@ -29,10 +29,9 @@ def test_oracle_matches_reference_golden(name):
     c = cases.CASES[name]
     st, sdd = c.get("stride_t", 1), c.get("stride_d", 1)
     assert np.array_equal(res["olens"].numpy(), gold["olens"])
-    for key in ("out", "out_video"):
-        if key in gold:
-            mine = res[key][:, ::st, ::sdd].numpy()
-            assert np.allclose(mine, gold[key], rtol=1e-4, atol=1e-5), key
+    for key in [k for k in gold if k == "out" or k == "out_video" or k.startswith("inter_")]:
+        mine = res[key][:, ::st, ::sdd].numpy()
+        assert np.allclose(mine, gold[key], rtol=1e-4, atol=1e-5), key
     assert abs(float(res["ctc_loss"]) - float(gold["ctc_loss"])) <= 1e-5 * abs(float(gold["ctc_loss"]))
     assert np.allclose(res["ctc_loss_vec"].numpy(), gold["ctc_loss_vec"], rtol=1e-5, atol=1e-6)
     assert np.array_equal(res["argmax"].numpy().astype(np.int16), gold["argmax"])
@@ -44,7 +43,8 @@ def test_oracle_matches_reference_golden(name):
 
 
 @pytest.mark.skipif(not reference_loader.available(), reason="/root/reference not present")
-@pytest.mark.parametrize("name", ["asr_small", "asr_tailored_small", "av_tailored_small"])
+@pytest.mark.parametrize("name", ["asr_small", "asr_tailored_small", "av_tailored_small",
+                                  "asr_interctc_cond"])
 def test_oracle_matches_live_reference(name):
     """Where the reference tree exists, run it live (unmodified) and compare bit-for-bit-ish."""
     from oracle import gen_golden
@@ -54,6 +54,25 @@ def test_oracle_matches_live_reference(name):
     res = _util.run_oracle(name, sd)
     assert np.allclose(res["out"].numpy(), live["out"], rtol=1e-5, atol=1e-6)
     assert abs(float(res["ctc_loss"]) - float(live["ctc_loss"])) < 1e-4
+
+
+@pytest.mark.skipif(not reference_loader.available(), reason="/root/reference not present")
+def test_interctc_residual_restatement_vs_live_reference():
+    """src/ctc/interctc_residual_module.py run live == the oracle restatement; the drop-in class
+    has the same parameters."""
+    from oracle import ref_path, synth
+    from tailored_avsr_b200.ctc.interctc_residual_module import InterCTCResidualModule
+    ref = reference_loader.load()
+    m = ref.InterCTCResidualModule(256, 41).eval()
+    sd = synth.fill_module(m, seed=9)
+    x = synth.randn((3, 50, 256), 22) * 2.0
+    with torch.no_grad():
+        y, logits = m(x)
+    want_y, want_logits = ref_path.interctc_residual(x, sd)
+    assert torch.allclose(y, want_y, atol=1e-6) and torch.allclose(logits, want_logits, atol=1e-6)
+    mine = InterCTCResidualModule(256, 41)
+    assert {k: tuple(v.shape) for k, v in mine.state_dict().items()} == \
+        {k: tuple(v.shape) for k, v in m.state_dict().items()}
 
 
 def test_known_answer_parameter_counts():

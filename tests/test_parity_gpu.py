@@ -20,13 +20,18 @@ ENC_TOL = 1e-3
 DEV = "cuda"
 
 
-def _run_dropin(name, enc):
+def _run_dropin(name, enc, ctc=None):
     c = cases.CASES[name]
     inp = cases.make_inputs(name)
     with torch.no_grad():
         if c["kind"] == "single":
-            y, olens, _ = enc(inp["x"].to(DEV), inp["lens"].to(DEV))
-            return {"out": y, "olens": olens}
+            y, olens, _ = enc(inp["x"].to(DEV), inp["lens"].to(DEV), ctc=ctc)
+            res = {}
+            if isinstance(y, tuple):  # InterCTC taps (encoder.py:410-411)
+                y, inter = y
+                res.update({f"inter_{idx}": t for idx, t in inter})
+            res.update(out=y, olens=olens)
+            return res
         from oracle import ref_path
         d, T = c["cfg"]["output_size"], c["T"]
         pos = ref_path.rel_pos_emb(T, d).to(DEV)
@@ -40,12 +45,12 @@ def test_encoder_parity_vs_oracle_and_golden(name):
     enc, ctc, sd = _util.build_dropin(name)
     res = _util.run_oracle(name, sd)
     enc = enc.to(DEV)
-    got = _run_dropin(name, enc)
+    got = _run_dropin(name, enc, ctc.to(DEV))
     torch.cuda.synchronize()
     assert torch.equal(got["olens"].cpu().long(), res["olens"].long())
     lens = res["olens"]
-    for key in ("out", "out_video"):
-        if key in res:
+    for key in [k for k in res if k in ("out", "out_video") or k.startswith("inter_")]:
+        if True:
             mx, fro = _util.rel_errors(got[key], res[key], lens)
             print(f"{name}:{key}: max-rel {mx:.3e} fro {fro:.3e}")
             tol = cases.CASES[name].get("enc_tol", ENC_TOL)
@@ -165,3 +170,55 @@ def test_layer_module_standalone_matches_oracle():
     mx, fro = _util.rel_errors(y, want, lens)
     assert mx <= ENC_TOL and fro <= ENC_TOL, (mx, fro)
     assert pos_out.shape == (1, 2 * T - 1, d) and mask_out.shape == (B, 1, T)
+
+
+def test_prefix_scorer_beam_walk_matches_oracle():
+    """CTCPrefixScorer (asr_inference.py:142) driven like espnet's batch beam search: 4 decoding
+    steps, beam 3, device-resident state; every step's scores equal the oracle recursion."""
+    from oracle import ref_path, synth
+    from tailored_avsr_b200.ctc.ctc import CTC
+    from tailored_avsr_b200.ctc.prefix_scorer import CTCPrefixScorer
+    T, D, V = 37, 256, 41
+    eos = V - 1
+    ctc = CTC(odim=V, encoder_output_size=D, dropout_rate=0.0).eval()
+    sd = synth.fill_module(ctc, seed=5, prefix="ctc.")
+    x = synth.randn((T, D), 21) * 3.0
+    lp64 = ref_path.ctc_log_softmax(x[None], sd, "ctc.ctc_lo")[0].double().numpy()
+    scorer = CTCPrefixScorer(ctc=ctc.to(DEV), eos=eos)
+    scorer.batch_init_state(x.to(DEV))
+    beam = 3
+    hyps = [([], ref_path.ctc_prefix_init(lp64), 0.0)]          # oracle side: (prefix, r, log_psi)
+    states = [None]                                             # device side
+    sos = eos
+    for step in range(4):
+        y = torch.tensor([[sos] + h[0] for h in hyps], dtype=torch.int64, device=DEV)
+        score, new_state = scorer.batch_score_partial(y, None, states, x.to(DEV))
+        score = score.cpu().double().numpy()
+        cands = []
+        for i, (prefix, r, psi_prev) in enumerate(hyps):
+            want_r, want_psi = ref_path.ctc_prefix_score(lp64, r, prefix, 0, eos)
+            want = want_psi - psi_prev
+            ok = want_psi > -1e9
+            assert np.allclose(score[i][ok], want[ok], rtol=1e-4, atol=2e-3), (step, i)
+            assert (score[i][~ok] < -1e9).all()
+            for c in range(1, V - 1):
+                cands.append((want[c] + psi_prev, i, c, want_r[c], want_psi[c]))
+        cands.sort(key=lambda t: -t[0])
+        # force a repeated label into the beam to exercise the c == last branch
+        keep = cands[:beam - 1] + [next(t for t in cands if hyps[t[1]][0][-1:] == [t[2]])] \
+            if step > 0 else cands[:beam]
+        hyps = [(hyps[i][0] + [c], r, psi) for (_, i, c, r, psi) in keep]
+        states = [scorer.select_state(new_state, i, c) for (_, i, c, _, _) in keep]
+
+
+def test_interctc_residual_module_matches_oracle():
+    from oracle import ref_path, synth
+    from tailored_avsr_b200.ctc.interctc_residual_module import InterCTCResidualModule
+    m = InterCTCResidualModule(256, 41).eval()
+    sd = synth.fill_module(m, seed=9)
+    x = synth.randn((3, 50, 256), 22) * 2.0
+    want_y, want_logits = ref_path.interctc_residual(x, sd)
+    with torch.no_grad():
+        y, logits = m.to(DEV)(x.to(DEV))
+    assert (logits.cpu() - want_logits).abs().max() < 1e-4
+    assert (y.cpu() - want_y).abs().max() / want_y.abs().max() < 1e-5
