@@ -20,6 +20,9 @@
 
 namespace tavsr {
 extern std::atomic<long long> g_launches;
+int relpos_attn_tc_launch(const float* qkv, long long ld_qkv, const float* pos, long long ld_pos,
+                          const float* u, const float* v, const int32_t* lens, float* ctx,
+                          long long ld_ctx, int B, int T, int H, int round_out, cudaStream_t s);
 
 namespace attn {
 
@@ -274,6 +277,14 @@ extern "C" int tavsr_relpos_attn_fwd(const float* qkv, long long ld_qkv, const f
                     (reinterpret_cast<uintptr_t>(ctx) & 7) == 0,
                 "attn: misaligned pointer");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // tcgen05 / TMEM kernel (attention_sm100.cu) whenever TMA can address the operands;
+  // g_debug[8] = 1 forces the mma.sync kernel below.
+  if (g_debug[8] != 1 && ld_ctx % 4 == 0 && (reinterpret_cast<uintptr_t>(ctx) & 15) == 0) {
+    const int rc = relpos_attn_tc_launch(qkv, ld_qkv, pos, ld_pos, u, v, lens, ctx, ld_ctx, B, T, H,
+                                         round_out, s);
+    if (rc == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
+    return rc;
+  }
   const int smem = attn::kSmemFloats * 4;
   static bool configured = false;
   if (!configured) {

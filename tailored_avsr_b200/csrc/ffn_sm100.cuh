@@ -48,19 +48,6 @@ constexpr int kSmemBytes = 1024 + kXBytes + kRing * kUnitBytes + kParamFloats * 
 constexpr uint32_t kColD2 = 0, kColH = 256;
 }  // namespace ffn
 
-// D[tmem] (+)= A[tmem] . B[smem]^T : A operand read from tensor memory (lane == row, one 32-bit
-// column per K element).
-__device__ __forceinline__ void umma_ts_tf32(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
-                                             uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
-      "}\n" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 
 __device__ __forceinline__ long long globaltimer_ns() {
   long long t;
@@ -127,8 +114,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ffn::kThreadsV1, 1)
 ffn_fused_kernel(const __grid_constant__ FfnParams p) {
   using namespace ffn;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* s_x = smem;                       // 8 x 16 KB, later: peer partial rows (64 KB)
   uint8_t* s_ring = s_x + kXBytes;           // 6 x 16 KB, later: epilogue params + store staging
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + kRingV1 * kUnitBytes);
@@ -448,8 +434,7 @@ ffn_fused_pair_kernel(const __grid_constant__ Ffn2Params p) {
   constexpr int kRing2 = ffn2::kRing;
   constexpr int kHU = ffn2::kHalfUnit;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* s_x = smem;                       // 8 x 16 KB, later: peer partial rows (64 KB)
   uint8_t* s_ring = s_x + kXBytes;           // 10 x 8 KB, later: TMA-store staging
   float* s_b1 = reinterpret_cast<float*>(s_ring + kRing2 * kHU);

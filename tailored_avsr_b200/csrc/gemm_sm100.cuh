@@ -360,8 +360,7 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
   constexpr int kAccStages = Cfg::kAccStages;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* s_stage = smem;                                        // kStages * kStageBytes
   uint8_t* s_staging = s_stage + kStages * Cfg::kStageBytes;      // kEpiWarps * 8192
   float* s_param = reinterpret_cast<float*>(s_staging + Cfg::kStagingBytes);

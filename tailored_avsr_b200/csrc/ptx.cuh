@@ -13,6 +13,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// 1024-byte alignment of the dynamic shared window (SWIZZLE_128B atoms) WITHOUT a round trip
+// through an integer: `raw + offset` keeps the pointer provably in the shared address space, so
+// the compiler emits LDS/STS instead of generic LD/ST for everything derived from it.
+__device__ __forceinline__ uint8_t* align_smem_1024(uint8_t* raw) {
+  return raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
+}
+
 __device__ __forceinline__ uint32_t lane_id() {
   uint32_t l;
   asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));
@@ -245,6 +252,37 @@ __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64
         : "memory");
   }
 }
+
+// D[tmem] (+)= A[tmem] . B[smem]^T : A operand read from tensor memory (lane == row, one 32-bit
+// column per K element).
+__device__ __forceinline__ void umma_ts_tf32(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// Shared-memory descriptor for an MN-major operand tile with the 128-byte swizzle: rows of 128 B
+// run along MN (32 tf32 elements), 8 consecutive rows (= 8 K indices) form one 1024-byte atom
+// (a TMA box {32 elements of MN, K rows}).  `mn_atom_stride` is the byte distance between
+// successive 32-element MN blocks.  One tf32 MMA consumes K = 8 = exactly one atom along K, so
+// the K-group stride never comes into play; both offset fields carry the MN stride.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr,
+                                                            uint32_t mn_atom_stride) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((mn_atom_stride >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((mn_atom_stride >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+constexpr uint32_t kUmmaBMajorMN = 1u << 16;  // instruction-descriptor bit: B operand MN-major
 
 // Arrives (once) on `bar` when all previously issued tcgen05.mma of this thread have completed.
 // Implies tcgen05.fence::before_thread_sync.

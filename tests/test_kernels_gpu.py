@@ -156,7 +156,8 @@ def _rel_shift(x):
 
 
 @pytest.mark.parametrize("B,T,lens", [(2, 64, [64, 40]), (3, 100, [100, 1, 77]), (2, 250, [250, 130]),
-                                      (1, 17, [17]), (2, 130, [0, 130])])
+                                      (1, 17, [17]), (2, 130, [0, 130]), (1, 300, [300]),
+                                      (2, 515, [515, 260])])
 def test_relpos_attention(B, T, lens):
     ops = _ops()
     H, dk = 4, 64
@@ -180,6 +181,15 @@ def test_relpos_attention(B, T, lens):
     ref = (attn @ vv).transpose(1, 2).reshape(B * T, H * dk)
     assert rel_fro(out, ref) < 3e-3, rel_fro(out, ref)
     assert max_rel(out, ref) < 1e-2
+    # the mma.sync kernel stays available behind debug knob 8 and must agree too
+    from tailored_avsr_b200 import _lib
+    _lib.load().tavsr_debug_set(8, 1)
+    try:
+        out2 = ops.relpos_attn(qkv.to(DEV), pos.to(DEV), u.to(DEV), v.to(DEV), lens_t.to(DEV), B, T,
+                               H, round_out=False)
+    finally:
+        _lib.load().tavsr_debug_set(8, 0)
+    assert rel_fro(out2, ref) < 3e-3
 
 
 @pytest.mark.parametrize("B,T", [(2, 64), (3, 100), (2, 250), (1, 7)])
