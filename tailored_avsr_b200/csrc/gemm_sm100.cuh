@@ -95,19 +95,21 @@ __device__ __forceinline__ float apply_act(float x, int act_rt) {
   switch (act) {
     case ACT_SWISH: return __fdividef(x, 1.0f + __expf(-x));
     case ACT_GELU: {
-      // exact-erf GELU with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, i.e. at the fp32
-      // rounding level of the reference's erff) - 2 SFU ops + 8 FMA-pipe ops instead of erff's
-      // ~30-instruction branchy expansion; the epilogue warps are the bottleneck of this GEMM.
-      const float z = fabsf(x) * 0.70710678118654752440f;
-      const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-      float poly = fmaf(1.061405429f, t, -1.453152027f);
-      poly = fmaf(poly, t, 1.421413741f);
-      poly = fmaf(poly, t, -0.284496736f);
-      poly = fmaf(poly, t, 0.254829592f);
-      const float erfc_z = poly * t * __expf(-z * z);   // 1 - erf(z), z >= 0
-      // 0.5 * (1 + erf(x / sqrt 2)) without cancellation in the negative tail
-      const float cdf = x >= 0.f ? fmaf(-0.5f, erfc_z, 1.0f) : 0.5f * erfc_z;
-      return x * cdf;
+      // exact-erf GELU  x * Phi(x)  with the upper tail  Q(t) = 0.5 erfc(t / sqrt 2) = 2^R(t),
+      // R a degree-6 minimax fit of log2 Q on [0, 9] weighted by t Q(t) (tools/fit_gelu.py):
+      // |gelu - exact| <= 1.6e-7 max(1, |x|), i.e. the fp32 rounding level of the reference's erff,
+      // in 12 issue slots (1 SFU) instead of ~30 - the epilogue warps are the bottleneck of the
+      // channel_proj1 GEMM.  No cancellation in the negative tail: Phi(x) = Q(|x|) there.
+      const float t = fminf(fabsf(x), 9.0f);
+      float r = fmaf(2.904336725e-05f, t, -7.323304308e-04f);
+      r = fmaf(r, t, 7.953807712e-03f);
+      r = fmaf(r, t, -5.320513994e-02f);
+      r = fmaf(r, t, -4.589348137e-01f);
+      r = fmaf(r, t, -1.151144981e+00f);
+      r = fmaf(r, t, -9.999991059e-01f);
+      float qv;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(qv) : "f"(r));
+      return x * (x >= 0.f ? 1.0f - qv : qv);
     }
     case ACT_RELU: return fmaxf(x, 0.0f);
     default: return x;

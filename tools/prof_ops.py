@@ -35,6 +35,10 @@ if which in ("gemm_w1", "all"):
     x, w, b = rn(M, 256), rn(2048, 256) / 16, rn(2048)
     out = torch.empty(M, 2048, device=DEV)
     run(lambda: ops.gemm_bias_act(x, w, b, act=1, out=out))
+if which in ("gemm_gelu", "all"):
+    x, w, b = rn(M, 256), rn(2048, 256) / 16, rn(2048)
+    out = torch.empty(M, 2048, device=DEV)
+    run(lambda: ops.gemm_bias_act(x, w, b, act=2, out=out))
 if which in ("gemm_qkv", "all"):
     x, w, b = rn(M, 256), rn(768, 256) / 16, rn(768)
     out = torch.empty(M, 768, device=DEV)
