@@ -11,7 +11,7 @@ Python / launch overhead that otherwise dominates at B*T ~ 8k frames.
 """
 from __future__ import annotations
 
-from typing import Dict, Optional, Tuple
+from typing import Dict, Iterable, Iterator, Optional, Sequence, Tuple
 
 import torch
 
@@ -92,6 +92,60 @@ class EncoderCTCPipeline:
         entry = next(iter(self._graphs.values())) if key is None else self._graphs[key]
         entry["graph"].replay()
         return entry["out"]
+
+    @torch.no_grad()
+    def run_stream(self, batches: Iterable[Sequence[torch.Tensor]]) -> Iterator[dict]:
+        """Pipelined form of `run` for a stream of host batches (pinned memory): the host->device
+        copy of batch n+1 is issued on a copy stream before batch n is computed, so PCIe transfers
+        hide under the kernels.  Yields, in order, the same host-side dict as `run` (loss, tokens,
+        ntok on the host) plus `olens`; every batch still crosses PCIe and every result is read
+        back before the next one is yielded."""
+        dev = self.device
+        comp = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        copy = self._copy_stream
+
+        stages = self.__dict__.setdefault("_stages", {})
+        turn = [0]
+
+        def stage(batch):
+            # two persistent device staging sets per shape signature: no allocator traffic on the
+            # copy stream, and the set batch n+1 lands in is not the one batch n is read from
+            key = tuple((tuple(t.shape), t.dtype) for t in batch)
+            sets = stages.get(key)
+            if sets is None:
+                sets = [[torch.empty(t.shape, dtype=t.dtype, device=dev) for t in batch]
+                        for _ in range(2)]
+                stages[key] = sets
+            tens = sets[turn[0] & 1]
+            turn[0] += 1
+            copy.wait_stream(comp)  # the batch that last used this set has been consumed
+            with torch.cuda.stream(copy):
+                for d, t in zip(tens, batch):
+                    d.copy_(t, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            return tens, ev
+
+        it = iter(batches)
+        try:
+            nxt = stage(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            cur = nxt
+            try:
+                nxt = stage(next(it))
+            except StopIteration:
+                nxt = None
+            comp.wait_event(cur[1])
+            res = self.run_device(*cur[0])
+            out = {"olens": res["olens"], "loss": res["loss"].to("cpu")}
+            if self.greedy:
+                out["tokens"] = res["tokens"].to("cpu")
+                out["ntok"] = res["ntok"].to("cpu")
+            yield out
 
     @torch.no_grad()
     def run(self, feats, feats_lens, ys_pad, ys_lens) -> dict:

@@ -222,3 +222,31 @@ def test_interctc_residual_module_matches_oracle():
         y, logits = m.to(DEV)(x.to(DEV))
     assert (logits.cpu() - want_logits).abs().max() < 1e-4
     assert (y.cpu() - want_y).abs().max() / want_y.abs().max() < 1e-5
+
+
+def test_pipeline_run_stream_equals_blocking_run():
+    """EncoderCTCPipeline.run_stream (copy of batch n+1 overlapped with batch n, CUDA-graph replay)
+    returns, batch by batch, exactly what the blocking run() returns."""
+    from tailored_avsr_b200.pipeline import EncoderCTCPipeline
+    name = "vsr_small"
+    enc, ctc, _ = _util.build_dropin(name)
+    pipe = EncoderCTCPipeline(enc.to(DEV), ctc.to(DEV))
+    c = cases.CASES[name]
+    inp = cases.make_inputs(name)
+    batches = []
+    for k in range(4):
+        x = (inp["x"] * (1.0 + 0.1 * k)).pin_memory()
+        lens = inp["lens"].clone()
+        tl = cases.target_lens(name, lens)
+        ys = torch.roll(inp["ys_pad"], k, dims=1).contiguous()
+        batches.append((x, lens.pin_memory(), ys.pin_memory(), tl.pin_memory()))
+    want = []
+    for b in batches:
+        r = pipe.run(*b)
+        want.append((float(r["loss"]), r["tokens"].clone(), r["ntok"].clone()))
+    got = [(float(r["loss"]), r["tokens"].clone(), r["ntok"].clone()) for r in pipe.run_stream(batches)]
+    assert len(got) == len(want)
+    for (l0, t0, n0), (l1, t1, n1) in zip(want, got):
+        assert l0 == l1
+        assert torch.equal(t0, t1) and torch.equal(n0, n1)
+    assert len({w[0] for w in want}) == len(want)  # the batches really differ
