@@ -123,6 +123,16 @@ typedef struct tavsr_rowln_args {
    * pairs and recombined in the epilogue.  The kernel leaves the flag words zeroed again. */
   void* workspace;
   long long workspace_bytes;
+  /* Sequential dual mode (x2 != NULL and k1 > 0): the reduction axis is the concatenation of the
+   * two operands — x is [M,k1], x2 is [M,K-k1], w is [256,K] = [W1 | W2] — and
+   *   acc = rowscale1[seg]*(X.W1^T + segbias1) + rowscale2[seg]*(X2.W2^T + segbias2).
+   * This is the learned_ave / fixed_ave merge with the branch output projections folded into
+   * merge_proj (W1 = Wm.Wo, W2 = Wm.W_proj2; encoder_layer.py:208-209,220,291-293), so the
+   * attention context and the gated cgMLP activations feed the merge GEMM directly.
+   * k1 and K-k1 must be multiples of 32.  segbias1/2: [256] or NULL; not combinable with dots. */
+  int k1;
+  const float* segbias1;
+  const float* segbias2;
 } tavsr_rowln_args;
 
 int tavsr_gemm_rowln(const tavsr_rowln_args* args, void* stream);
@@ -198,6 +208,14 @@ int tavsr_csgu_fwd(const float* h, long long ldh, const float* norm_g, const flo
  *   s_K = softmax_{t < lens[b]}((dotsK[.,0] + pool_bK) / sqrt(size));  omega_K = sum_t s_K dotsK[.,1] + wproj_bK
  *   (w1, w2) = softmax(omega_1, omega_2)  -> weight_global / weight_local
  * ---------------------------------------------------------------------------------------------- */
+/* Row dots  out[m] = (a[m,:] . va, a[m,:] . vb)  for one or two (a2 may be NULL) activation
+ * matrices in one launch: the pooling_proj / weight_proj scores of the learned_ave merge
+ * (encoder_layer.py:243,258) taken on the attention context and the gated cgMLP activations with
+ * the branch output projections folded into the vectors (va = Wo^T a, ...).  out: [M,2]. */
+int tavsr_row_dots(const float* a1, long long ld1, int K1, const float* va1, const float* vb1,
+                   float* out1, const float* a2, long long ld2, int K2, const float* va2,
+                   const float* vb2, float* out2, int M, void* stream);
+
 int tavsr_merge_learned_ave_weights(const float* dots1, const float* dots2, const int32_t* lens,
                                     float pool_b1, float pool_b2, float wproj_b1, float wproj_b2,
                                     float inv_sqrt_size, float* w1, float* w2, int B, int T,

@@ -41,6 +41,7 @@ class RowLNArgs(Structure):
         ("eps", c_float),
         ("dot1", c_void_p), ("dot2", c_void_p), ("dots_out", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", c_longlong),
+        ("k1", c_int), ("segbias1", c_void_p), ("segbias2", c_void_p),
     ]
 
 
@@ -79,6 +80,8 @@ SIGNATURES = {
     "tavsr_csgu_fwd": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_longlong, c_void_p, c_int, c_int, c_int, c_int,
                                c_float, c_int, c_void_p]),
+    "tavsr_row_dots": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "tavsr_merge_learned_ave_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_float,
                                                 c_float, c_float, c_float, c_void_p, c_void_p,
                                                 c_int, c_int, c_void_p]),

@@ -259,6 +259,12 @@ extern "C" int tavsr_gemm_rowln(const tavsr_rowln_args* a, void* stream) {
   const bool dual = a->x2 != nullptr;
   TAVSR_REQUIRE(!dual || (a->rowscale1 && a->rowscale2 && a->rows_per_seg > 0),
                 "rowln: dual mode needs rowscale1/2 and rows_per_seg");
+  const bool seq = dual && a->k1 > 0;
+  TAVSR_REQUIRE(a->k1 == 0 || (dual && a->k1 % 32 == 0 && a->k1 < a->K && (a->K - a->k1) % 32 == 0),
+                "rowln: sequential dual mode needs x2 and k1, K-k1 multiples of 32 (k1=%d K=%d)",
+                a->k1, a->K);
+  TAVSR_REQUIRE(!(a->segbias1 || a->segbias2) || (seq && a->segbias1 && a->segbias2 && !a->dots_out),
+                "rowln: segbias1/2 come as a pair, only in sequential dual mode, without dots");
   GemmParams p;
   memset(&p, 0, sizeof(p));
   int rc;
@@ -280,8 +286,18 @@ extern "C" int tavsr_gemm_rowln(const tavsr_rowln_args* a, void* stream) {
     p.flags = static_cast<unsigned int*>(a->workspace);
     p.partial = reinterpret_cast<float*>(static_cast<char*>(a->workspace) + 4096);
   }
-  if ((rc = make_tmap_2d(&p.tmA, a->x, 4, false, a->M, a->K, a->ldx, 128, 32))) return rc;
-  if (dual && (rc = make_tmap_2d(&p.tmA2, a->x2, 4, false, a->M, a->K, a->ldx2, 128, 32))) return rc;
+  const int ka1 = seq ? a->k1 : a->K;
+  const int ka2 = seq ? a->K - a->k1 : a->K;
+  if (seq) {
+    p.seq_kb1 = a->k1 / 32;
+    if (a->segbias1) {
+      p.seg_bias = 1;
+      p.dot1 = a->segbias1;
+      p.dot2 = a->segbias2;
+    }
+  }
+  if ((rc = make_tmap_2d(&p.tmA, a->x, 4, false, a->M, ka1, a->ldx, 128, 32))) return rc;
+  if (dual && (rc = make_tmap_2d(&p.tmA2, a->x2, 4, false, a->M, ka2, a->ldx2, 128, 32))) return rc;
   if ((rc = make_tmap_2d(&p.tmB, a->w, 4, false, 256, a->K, a->ldw, 256 / ctas, 32))) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (ctas == 2) {

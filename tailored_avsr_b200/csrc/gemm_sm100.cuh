@@ -63,6 +63,12 @@ struct alignas(64) GemmParams {
   // accumulator to `partial`, the even unit adds it in its epilogue ----
   float* partial;          // [M_padded, 256] fp32 scratch
   unsigned int* flags;     // [num_m_tiles * kCtas * 4], zero between launches
+  // ---- sequential dual (kDual with seq_kb1 > 0): the reduction axis is the concatenation of the
+  // two operands, A = [A1 | A2], W = [W1 | W2]; k-blocks < seq_kb1 accumulate A1.W1^T into the
+  // first accumulator, the rest A2.W2^T into the second (merge with the branch output projections
+  // folded in).  seg_bias: dot1 / dot2 hold per-branch bias vectors scaled like the accumulators.
+  int seq_kb1;
+  int seg_bias;
 };
 
 template <bool kTf32, int kBlockN, int kMode, bool kDual, int kCtas>
@@ -218,6 +224,10 @@ __device__ __forceinline__ void rowln_finish(const GemmParams& p, const float* s
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           v[j] = w1 * __uint_as_float(r[j]) + w2 * __uint_as_float(r2[j]);
+        if (p.seg_bias) {  // per-branch biases, scaled like the branches (dot slots reused)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += w1 * s_d1[c * 32 + j] + w2 * s_d2[c * 32 + j];
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -439,18 +449,23 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* st = s_stage + s * Cfg::kStageBytes;
           uint8_t* sb = st + Cfg::kABytes * (kDual ? 2 : 1);
+          const bool seq = kDual && p.seq_kb1 > 0;   // one A tile per stage, picked by k-block
+          const bool second = seq && kb >= p.seq_kb1;
+          const CUtensorMap* tma_a = second ? &p.tmA2 : &p.tmA;
+          const int ka = (second ? kb - p.seq_kb1 : kb) * Cfg::kBlockK;
+          const uint32_t bytes = seq ? Cfg::kABytes + Cfg::kBBytes : Cfg::kStageBytes;
           if (kPair) {
             // the leader's barrier collects the bytes of both CTAs' loads
-            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes * 2);
-            tma_load_2d_2sm(st, &p.tmA, &full_bar[s], kb * Cfg::kBlockK, m_blk * Cfg::kBlockM);
-            if (kDual)
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], bytes * 2);
+            tma_load_2d_2sm(st, tma_a, &full_bar[s], ka, m_blk * Cfg::kBlockM);
+            if (kDual && !seq)
               tma_load_2d_2sm(st + Cfg::kABytes, &p.tmA2, &full_bar[s], kb * Cfg::kBlockK,
                               m_blk * Cfg::kBlockM);
             tma_load_2d_2sm(sb, &p.tmB, &full_bar[s], kb * Cfg::kBlockK, b_row0);
           } else {
-            mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
-            tma_load_2d(st, &p.tmA, &full_bar[s], kb * Cfg::kBlockK, m_blk * Cfg::kBlockM);
-            if (kDual)
+            mbar_arrive_expect_tx(&full_bar[s], bytes);
+            tma_load_2d(st, tma_a, &full_bar[s], ka, m_blk * Cfg::kBlockM);
+            if (kDual && !seq)
               tma_load_2d(st + Cfg::kABytes, &p.tmA2, &full_bar[s], kb * Cfg::kBlockK,
                           m_blk * Cfg::kBlockM);
             tma_load_2d(sb, &p.tmB, &full_bar[s], kb * Cfg::kBlockK, b_row0);
@@ -481,16 +496,22 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
           const uint64_t a_desc = umma_desc_kmajor_sw128(a_addr);
           const uint64_t b_desc = umma_desc_kmajor_sw128(b_addr);
           const uint64_t a2_desc = umma_desc_kmajor_sw128(a_addr + Cfg::kABytes);
+          const bool seq = kDual && p.seq_kb1 > 0;
+          const bool second = seq && kb >= p.seq_kb1;
+          const uint32_t dd = second ? d0 + kBlockN : d0;
+          const int kb_rel = second ? kb - p.seq_kb1 : kb;
 #pragma unroll
           for (int k = 0; k < Cfg::kBlockK / Cfg::kUmmaK; ++k) {
-            const uint32_t acc = (kb | k) ? 1u : 0u;
+            const uint32_t acc = (kb_rel | k) ? 1u : 0u;
             // advancing K inside the 128B swizzle row: +32 bytes == +2 in the (addr>>4) field
             if (kPair) {
-              umma_ss_2sm<kTf32>(d0, a_desc + 2 * k, b_desc + 2 * k, idesc, acc);
-              if (kDual) umma_ss_2sm<kTf32>(d0 + kBlockN, a2_desc + 2 * k, b_desc + 2 * k, idesc, acc);
+              umma_ss_2sm<kTf32>(dd, a_desc + 2 * k, b_desc + 2 * k, idesc, acc);
+              if (kDual && !seq)
+                umma_ss_2sm<kTf32>(d0 + kBlockN, a2_desc + 2 * k, b_desc + 2 * k, idesc, acc);
             } else {
-              umma_ss<kTf32>(d0, a_desc + 2 * k, b_desc + 2 * k, idesc, acc);
-              if (kDual) umma_ss<kTf32>(d0 + kBlockN, a2_desc + 2 * k, b_desc + 2 * k, idesc, acc);
+              umma_ss<kTf32>(dd, a_desc + 2 * k, b_desc + 2 * k, idesc, acc);
+              if (kDual && !seq)
+                umma_ss<kTf32>(d0 + kBlockN, a2_desc + 2 * k, b_desc + 2 * k, idesc, acc);
             }
           }
           // frees the smem slot (in both CTAs of a pair) once these MMAs retire

@@ -192,6 +192,50 @@ csgu_conv_kernel(const float* __restrict__ h, long long ldh, const float* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
+// Row dots: out[m] = (a[m,:] . va, a[m,:] . vb) for up to two activation matrices in one launch -
+// the pooling_proj / weight_proj scores of the learned_ave merge (encoder_layer.py:243,258) taken
+// directly on the attention context and the gated cgMLP activations, with the branch output
+// projections folded into va / vb.  One warp per row, 16-byte coalesced loads.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+row_dots_kernel(const float* __restrict__ a1, long long ld1, int K1, const float* __restrict__ va1,
+                const float* __restrict__ vb1, float2* __restrict__ out1,
+                const float* __restrict__ a2, long long ld2, int K2, const float* __restrict__ va2,
+                const float* __restrict__ vb2, float2* __restrict__ out2, int M) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int m = blockIdx.x * 8 + warp; m < M; m += gridDim.x * 8) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    const float4* r1 = reinterpret_cast<const float4*>(a1 + static_cast<long long>(m) * ld1);
+    for (int k = lane; k < K1 / 4; k += 32) {
+      const float4 x = ld_act4(r1 + k);
+      const float4 pa = __ldg(reinterpret_cast<const float4*>(va1) + k);
+      const float4 pb = __ldg(reinterpret_cast<const float4*>(vb1) + k);
+      s[0] += x.x * pa.x + x.y * pa.y + x.z * pa.z + x.w * pa.w;
+      s[1] += x.x * pb.x + x.y * pb.y + x.z * pb.z + x.w * pb.w;
+    }
+    if (a2 != nullptr) {
+      const float4* r2 = reinterpret_cast<const float4*>(a2 + static_cast<long long>(m) * ld2);
+      for (int k = lane; k < K2 / 4; k += 32) {
+        const float4 x = ld_act4(r2 + k);
+        const float4 pa = __ldg(reinterpret_cast<const float4*>(va2) + k);
+        const float4 pb = __ldg(reinterpret_cast<const float4*>(vb2) + k);
+        s[2] += x.x * pa.x + x.y * pa.y + x.z * pa.z + x.w * pa.w;
+        s[3] += x.x * pb.x + x.y * pb.y + x.z * pb.z + x.w * pb.w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s[i] = warp_sum(s[i]);
+    if (lane == 0) {
+      out1[m] = make_float2(s[0], s[1]);
+      if (a2 != nullptr) out2[m] = make_float2(s[2], s[3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // learned_ave merge weights: one warp per utterance.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
@@ -290,6 +334,23 @@ extern "C" int tavsr_csgu_fwd(const float* h, long long ldh, const float* norm_g
   TAVSR_CUDA_OK(launch_kernel(csgu_conv_kernel, grid2, dim3(kCh), 0, s, 0, h, ldh, norm_g, norm_b, conv_w,
                               conv_b, static_cast<const float2*>(st), out, ldo, T, Ch, round_out));
   g_launches.fetch_add(2, std::memory_order_relaxed);
+  return 0;
+}
+
+extern "C" int tavsr_row_dots(const float* a1, long long ld1, int K1, const float* va1,
+                              const float* vb1, float* out1, const float* a2, long long ld2, int K2,
+                              const float* va2, const float* vb2, float* out2, int M, void* stream) {
+  TAVSR_REQUIRE(M > 0 && a1 && va1 && vb1 && out1 && K1 > 0 && K1 % 4 == 0 && ld1 % 4 == 0,
+                "row_dots: bad first operand (K=%d)", K1);
+  TAVSR_REQUIRE(!a2 || (va2 && vb2 && out2 && K2 > 0 && K2 % 4 == 0 && ld2 % 4 == 0),
+                "row_dots: bad second operand (K=%d)", K2);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int grid = (M + 7) / 8;
+  if (grid > 8 * num_sms()) grid = 8 * num_sms();
+  TAVSR_CUDA_OK(launch_kernel(row_dots_kernel, dim3(grid), dim3(256), 0, s, 0, a1, ld1, K1, va1, vb1,
+                              reinterpret_cast<float2*>(out1), a2, ld2, K2, va2, vb2,
+                              reinterpret_cast<float2*>(out2), M));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
 

@@ -116,6 +116,77 @@ class MyBranchformerEncoderLayer(torch.nn.Module):
 
         learned = two and self.merge_method == "learned_ave"
         concat = two and self.merge_method == "concat"
+        x_b = new()
+        xf = new()
+        lnF = (self.norm_ff.weight, self.norm_ff.bias)
+        mp = self.merge_proj
+        if pos_proj is None and self.attn is not None:
+            raise NotImplementedError("attention without relative positional embedding "
+                                      "(abs_pos / selfattn) is not built on the B200 path")
+        fold = (engine.FOLD_MERGE and two and not concat and d == 256
+                and self.cgmlp.channel_proj2.weight.shape[1] % 32 == 0)
+        if fold:
+            # ---- merge with the branch output projections folded in (:208-209, 220, 227-309):
+            #   x + Wm (w1 (Wo ctx + bo) + w2 (W2 g + b2)) + bm
+            # = x + w1 ((Wm Wo) ctx + Wm bo) + w2 ((Wm W2) g + Wm b2) + bm
+            # and the pooling scores x1 . a = ctx . (Wo^T a) + bo . a, so x1 / x2 never exist.
+            lo, p2 = self.attn.linear_out, self.cgmlp.channel_proj2
+            f = self._packed.get(
+                "fold", [mp.weight, lo.weight, lo.bias, p2.weight, p2.bias],
+                lambda: (torch.cat([mp.weight.double() @ lo.weight.double(),
+                                    mp.weight.double() @ p2.weight.double()], 1).float().contiguous(),
+                         (mp.weight.double() @ lo.bias.double()).float().contiguous(),
+                         (mp.weight.double() @ p2.bias.double()).float().contiguous()))
+            ctx = engine.attention_ctx(xa, self.attn, pos_proj, lens, B, T, self._packed, "qkv")
+            u = engine.cgmlp_gated(xm, self.cgmlp, B, T, self._packed, "conv")
+            if learned:
+                pp1, wp1, pp2, wp2 = (self.pooling_proj1, self.weight_proj1, self.pooling_proj2,
+                                      self.weight_proj2)
+                fv = self._packed.get(
+                    "foldv", [lo.weight, lo.bias, p2.weight, p2.bias, pp1.weight, pp1.bias, wp1.weight,
+                              wp1.bias, pp2.weight, pp2.bias, wp2.weight, wp2.bias],
+                    lambda: dict(
+                        va1=(pp1.weight.double() @ lo.weight.double()).reshape(-1).float().contiguous(),
+                        vb1=(wp1.weight.double() @ lo.weight.double()).reshape(-1).float().contiguous(),
+                        va2=(pp2.weight.double() @ p2.weight.double()).reshape(-1).float().contiguous(),
+                        vb2=(wp2.weight.double() @ p2.weight.double()).reshape(-1).float().contiguous(),
+                        sc=[float(pp1.bias.double() + pp1.weight.double().reshape(-1) @ lo.bias.double()),
+                            float(pp2.bias.double() + pp2.weight.double().reshape(-1) @ p2.bias.double()),
+                            float(wp1.bias.double() + wp1.weight.double().reshape(-1) @ lo.bias.double()),
+                            float(wp2.bias.double() + wp2.weight.double().reshape(-1) @ p2.bias.double())]))
+                d1, d2 = ops.row_dots(ctx, fv["va1"], fv["vb1"], u, fv["va2"], fv["vb2"])
+                sc = fv["sc"]
+                w1, w2 = ops.merge_weights(d1, d2, lens, sc[0], sc[1], sc[2], sc[3], d, B, T)
+                self.weight_global = w1.view(B, 1, 1)
+                self.weight_local = w2.view(B, 1, 1)
+            else:
+                w1, w2 = self._packed.get(
+                    "fixedw" + str((B, str(dev))), [mp.weight],
+                    lambda: (torch.full((B,), 1.0 - self.cgmlp_weight, device=dev, dtype=torch.float32),
+                             torch.full((B,), float(self.cgmlp_weight), device=dev, dtype=torch.float32)))
+            ops.gemm_rowln(ctx, f[0], mp.bias, x2=u, k1=ctx.shape[1], segbias=(f[1], f[2]),
+                           rowscale=(w1, w2), rows_per_seg=T, residual=x_a, alpha=1.0, out_main=x_b,
+                           lnA=lnF, out_lnA=xf)
+        else:
+            self._run_branches_unfolded(xa, xm, x_a, x_b, xf, pos_proj, lens, B, T, learned, concat)
+
+        # ---- FFN + norm_final (+ the next block's first LayerNorm) ----
+        y = new()
+        yn = new() if next_norm is not None else None
+        engine.ffn_block(x_b, xf, self.feed_forward, out_main=y,
+                         ln0=(self.norm_final.weight, self.norm_final.bias),
+                         lnA=next_norm, out_lnA=yn, round_lnA=False)
+        return y, yn
+
+    def _run_branches_unfolded(self, xa, xm, x_a, x_b, xf, pos_proj, lens, B, T, learned, concat):
+        """Branch output projections as their own row-complete GEMMs, then merge (the layout of the
+        reference: encoder_layer.py:208-209, 220, 227-309).  Used for `concat`, single-branch
+        blocks and with TAVSR_FOLD_MERGE=0."""
+        d = self.size
+        M = B * T
+        dev = x_a.device
+        two = self.use_two_branches
+        new = lambda: torch.empty((M, d), device=dev, dtype=torch.float32)  # noqa: E731
         cat_buf = torch.empty((M, 2 * d), device=dev, dtype=torch.float32) if concat else None
         x1 = x2 = d1 = d2 = None
         if self.attn is not None:
@@ -141,8 +212,6 @@ class MyBranchformerEncoderLayer(torch.nn.Module):
                            out_main=x2, dots=dots, dots_out=d2)
 
         # ---- merge (:227-309) + norm_ff ----
-        x_b = new()
-        xf = new()
         lnF = (self.norm_ff.weight, self.norm_ff.bias)
         mp = self.merge_proj
         if two and self.merge_method in ("learned_ave", "fixed_ave"):
@@ -169,14 +238,6 @@ class MyBranchformerEncoderLayer(torch.nn.Module):
                                           "(use_attn/use_cgmlp=False) is not built on the B200 path")
             ops.gemm_rowln(xs, mp.weight, mp.bias, residual=x_a, alpha=1.0, out_main=x_b,
                            lnA=lnF, out_lnA=xf)
-
-        # ---- FFN + norm_final (+ the next block's first LayerNorm) ----
-        y = new()
-        yn = new() if next_norm is not None else None
-        engine.ffn_block(x_b, xf, self.feed_forward, out_main=y,
-                         ln0=(self.norm_final.weight, self.norm_final.bias),
-                         lnA=next_norm, out_lnA=yn, round_lnA=False)
-        return y, yn
 
     # ---------------------------------------------------------------------------------------
     def forward(self, x_input, mask, cache=None):

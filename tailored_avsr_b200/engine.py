@@ -33,6 +33,9 @@ from . import ops
 import os
 
 FFN_FUSED = os.environ.get("TAVSR_FFN_FUSED", "1") != "0"
+# fold attn.linear_out and cgmlp.channel_proj2 into merge_proj (two-branch learned_ave / fixed_ave
+# blocks): the merge GEMM then reads the attention context and the gated activations directly
+FOLD_MERGE = os.environ.get("TAVSR_FOLD_MERGE", "1") != "0"
 
 _ACT = {"swish": ops.ACT_SWISH, "relu": ops.ACT_RELU, "gelu": ops.ACT_GELU}
 

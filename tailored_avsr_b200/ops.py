@@ -18,7 +18,7 @@ from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SWISH, DT_TF32, FfnArgs, Row
 __all__ = [
     "ACT_NONE", "ACT_SWISH", "ACT_GELU", "ACT_RELU",
     "gemm_bias_act", "gemm_rowln", "ffn_fused", "layernorm", "relpos_attn", "csgu", "merge_weights",
-    "ctc_head", "vocab_residual", "ctc_loss", "ctc_greedy", "ctc_prefix_score", "launch_count",
+    "ctc_head", "vocab_residual", "row_dots", "ctc_loss", "ctc_greedy", "ctc_prefix_score", "launch_count",
 ]
 
 
@@ -152,8 +152,10 @@ def gemm_rowln(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = 
                out_lnB: Optional[torch.Tensor] = None, round_lnB: bool = False,
                eps: float = 1e-12,
                dots: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
-               dots_out: Optional[torch.Tensor] = None) -> None:
-    """Row-complete N=256 GEMM with fused residual / LayerNorm / row-dot epilogue (tavsr_gemm_rowln)."""
+               dots_out: Optional[torch.Tensor] = None, k1: int = 0,
+               segbias: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> None:
+    """Row-complete N=256 GEMM with fused residual / LayerNorm / row-dot epilogue (tavsr_gemm_rowln).
+    k1 > 0 selects the sequential dual mode: x (M,k1), x2 (M,K-k1), w (256,K) = [W1 | W2]."""
     _chk2d(x, "x")
     _chk2d(w, "w")
     a = RowLNArgs()
@@ -166,6 +168,11 @@ def gemm_rowln(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = 
         a.x2, a.ldx2 = x2.data_ptr(), x2.stride(0)
         a.rowscale1, a.rowscale2 = rowscale[0].data_ptr(), rowscale[1].data_ptr()
         a.rows_per_seg = rows_per_seg
+        if k1 > 0:
+            a.K = x.shape[1] + x2.shape[1]
+            a.k1 = k1
+            if segbias is not None:
+                a.segbias1, a.segbias2 = segbias[0].data_ptr(), segbias[1].data_ptr()
     a.w, a.ldw = w.data_ptr(), w.stride(0)
     if x2 is None and a.K >= 1024:
         ws = _splitk_workspace(x.device, a.M)
@@ -268,6 +275,22 @@ def merge_weights(dots1: torch.Tensor, dots2: torch.Tensor, lens: Optional[torch
         1.0 / math.sqrt(size), w1.data_ptr(), w2.data_ptr(), B, T, _stream()),
         "tavsr_merge_learned_ave_weights")
     return w1, w2
+
+
+@_profiled
+def row_dots(a1: torch.Tensor, va1: torch.Tensor, vb1: torch.Tensor,
+             a2: Optional[torch.Tensor] = None, va2: Optional[torch.Tensor] = None,
+             vb2: Optional[torch.Tensor] = None):
+    """(a1 @ [va1 vb1], a2 @ [va2 vb2]) as (M,2) tensors in one launch (tavsr_row_dots)."""
+    _chk2d(a1, "a1")
+    M = a1.shape[0]
+    o1 = torch.empty((M, 2), device=a1.device, dtype=torch.float32)
+    o2 = torch.empty((M, 2), device=a1.device, dtype=torch.float32) if a2 is not None else None
+    check(_lib.load().tavsr_row_dots(
+        a1.data_ptr(), a1.stride(0), a1.shape[1], va1.data_ptr(), vb1.data_ptr(), o1.data_ptr(),
+        _p(a2), a2.stride(0) if a2 is not None else 0, a2.shape[1] if a2 is not None else 0,
+        _p(va2), _p(vb2), _p(o2), M, _stream()), "tavsr_row_dots")
+    return o1, o2
 
 
 @_profiled

@@ -390,3 +390,48 @@ def test_vocab_residual(M, D, V, ln):
         assert (xn.cpu() - F.layer_norm(want, (D,), gam, bet, 1e-12)).abs().max() < 2e-5
     else:
         assert xn is None
+
+
+@pytest.mark.parametrize("B,T,K1,K2", [(5, 77, 256, 1024), (3, 250, 256, 1024), (2, 40, 64, 96)])
+def test_gemm_rowln_sequential_dual_folded_merge(B, T, K1, K2):
+    """Sequential dual mode: rowscale1*(X1.W1^T + c1) + rowscale2*(X2.W2^T + c2) over a concatenated
+    reduction axis (the merge GEMM with the branch output projections folded in)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(B * T + K2)
+    M = B * T
+    x1 = torch.randn(M, K1, generator=g).to(DEV)
+    x2 = torch.randn(M, K2, generator=g).to(DEV)
+    w = torch.cat([torch.randn(256, K1, generator=g) / math.sqrt(K1),
+                   torch.randn(256, K2, generator=g) / math.sqrt(K2)], 1).contiguous().to(DEV)
+    b, c1, c2 = [torch.randn(256, generator=g).to(DEV) for _ in range(3)]
+    res = torch.randn(M, 256, generator=g).to(DEV)
+    w1 = torch.rand(B, generator=g).to(DEV)
+    w2 = 1 - w1
+    gA, bA = torch.randn(256, generator=g).to(DEV), torch.randn(256, generator=g).to(DEV)
+    main = torch.empty(M, 256, device=DEV)
+    oA = torch.empty(M, 256, device=DEV)
+    ops.gemm_rowln(x1, w, b, x2=x2, k1=K1, segbias=(c1, c2), rowscale=(w1, w2), rows_per_seg=T,
+                   residual=res, alpha=1.0, out_main=main, lnA=(gA, bA), out_lnA=oA)
+    s1 = w1.double().repeat_interleave(T)[:, None]
+    s2 = w2.double().repeat_interleave(T)[:, None]
+    wd = w.double()
+    v = (res.double() + s1 * (x1.double() @ wd[:, :K1].t() + c1.double())
+         + s2 * (x2.double() @ wd[:, K1:].t() + c2.double()) + b.double())
+    assert rel_fro(main, v) < 2e-3
+    assert rel_fro(oA, _ln(v, gA.double(), bA.double(), 1e-12)) < 3e-3
+
+
+@pytest.mark.parametrize("M", [1, 333, 8000])
+def test_row_dots(M):
+    ops = _ops()
+    g = torch.Generator().manual_seed(M)
+    a1 = torch.randn(M, 256, generator=g).to(DEV)
+    a2 = torch.randn(M, 1024, generator=g).to(DEV)
+    v = [torch.randn(k, generator=g).to(DEV) for k in (256, 256, 1024, 1024)]
+    o1, o2 = ops.row_dots(a1, v[0], v[1], a2, v[2], v[3])
+    r1 = torch.stack([a1.double() @ v[0].double(), a1.double() @ v[1].double()], 1)
+    r2 = torch.stack([a2.double() @ v[2].double(), a2.double() @ v[3].double()], 1)
+    assert (o1.cpu().double() - r1.cpu()).abs().max() < 1e-4 * 16
+    assert (o2.cpu().double() - r2.cpu()).abs().max() < 1e-4 * 32
+    o1b, none = ops.row_dots(a1, v[0], v[1])
+    assert none is None and torch.equal(o1b, o1)
