@@ -206,26 +206,33 @@ row_dots_kernel(const float* __restrict__ a1, long long ld1, int K1, const float
   pdl_wait();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  for (int m = blockIdx.x * 8 + warp; m < M; m += gridDim.x * 8) {
-    float s[4] = {0.f, 0.f, 0.f, 0.f};
-    const float4* r1 = reinterpret_cast<const float4*>(a1 + static_cast<long long>(m) * ld1);
-    for (int k = lane; k < K1 / 4; k += 32) {
-      const float4 x = ld_act4(r1 + k);
-      const float4 pa = __ldg(reinterpret_cast<const float4*>(va1) + k);
-      const float4 pb = __ldg(reinterpret_cast<const float4*>(vb1) + k);
-      s[0] += x.x * pa.x + x.y * pa.y + x.z * pa.z + x.w * pa.w;
-      s[1] += x.x * pb.x + x.y * pb.y + x.z * pb.z + x.w * pb.w;
-    }
-    if (a2 != nullptr) {
-      const float4* r2 = reinterpret_cast<const float4*>(a2 + static_cast<long long>(m) * ld2);
-      for (int k = lane; k < K2 / 4; k += 32) {
-        const float4 x = ld_act4(r2 + k);
-        const float4 pa = __ldg(reinterpret_cast<const float4*>(va2) + k);
-        const float4 pb = __ldg(reinterpret_cast<const float4*>(vb2) + k);
-        s[2] += x.x * pa.x + x.y * pa.y + x.z * pa.z + x.w * pa.w;
-        s[3] += x.x * pb.x + x.y * pb.y + x.z * pb.z + x.w * pb.w;
+  // all loads of a row are issued before the first FMA (8 x 16 B per lane in flight): the kernel
+  // is a pure L2 -> register stream, so exposed load latency is the only thing that can slow it
+  auto dots2 = [&](const float* a, int K, const float* va, const float* vb, float& sa, float& sb) {
+    const float4* r = reinterpret_cast<const float4*>(a);
+    const float4* pa = reinterpret_cast<const float4*>(va);
+    const float4* pb = reinterpret_cast<const float4*>(vb);
+    const int n4 = K / 4;
+    for (int k0 = lane; k0 < n4; k0 += 256) {
+      float4 x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        x[j] = k0 + 32 * j < n4 ? ld_act4(r + k0 + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (k0 + 32 * j < n4) {
+          const float4 wa = __ldg(pa + k0 + 32 * j);
+          const float4 wb = __ldg(pb + k0 + 32 * j);
+          sa += x[j].x * wa.x + x[j].y * wa.y + x[j].z * wa.z + x[j].w * wa.w;
+          sb += x[j].x * wb.x + x[j].y * wb.y + x[j].z * wb.z + x[j].w * wb.w;
+        }
       }
     }
+  };
+  for (int m = blockIdx.x * 8 + warp; m < M; m += gridDim.x * 8) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    dots2(a1 + static_cast<long long>(m) * ld1, K1, va1, vb1, s[0], s[1]);
+    if (a2 != nullptr) dots2(a2 + static_cast<long long>(m) * ld2, K2, va2, vb2, s[2], s[3]);
 #pragma unroll
     for (int i = 0; i < 4; ++i) s[i] = warp_sum(s[i]);
     if (lane == 0) {
