@@ -224,6 +224,10 @@ def profile_step(pipe, batch_dev, peaks):
     ops.set_profiler(recs)
     try:
         with torch.no_grad():
+            # park the GPU behind a ~40 ms spin so the whole step (125 launches + their event pairs)
+            # is enqueued before the first kernel starts: the event deltas are then kernel
+            # durations, not host launch latency
+            torch.cuda._sleep(80_000_000)
             pipe._step(*batch_dev)
         torch.cuda.synchronize()
     finally:

@@ -132,12 +132,14 @@ struct WarpStager {
     const uint32_t lane = lane_id();
     if (lane == 0) tma_store_wait_read<1>();
     __syncwarp();
-    uint8_t* dst = base + buf * 4096 + lane * 128;
+    // explicit st.shared: the pointer travels through this struct, where the compiler may lose
+    // the address space and fall back to generic stores
+    const uint32_t dst = smem_u32(base) + buf * 4096 + lane * 128;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float4 f = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-      *reinterpret_cast<float4*>(dst + ((j ^ (lane & 7)) << 4)) = f;
-    }
+    for (int j = 0; j < 8; ++j)
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((j ^ (lane & 7)) << 4)),
+                   "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                   : "memory");
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
