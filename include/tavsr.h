@@ -65,6 +65,18 @@ int tavsr_gemm_bias_act(const void* x, long long ldx, const void* w, long long l
                         const float* bias, void* y, long long ldy, int M, int N, int K, int act,
                         int round_out, int dtype, void* stream);
 
+/* Same GEMM; additionally the epilogue emits per-row PARTIAL LayerNorm statistics of the stored
+ * output columns [stats_col0, N): stats_out[m * parts + p] = (mean, M2 = sum (y - mean)^2) over the
+ * p-th group of *stats_part_width consecutive columns (parts = (N - stats_col0) / width; the width
+ * is the library's tile choice, 64 or 128, returned through stats_part_width; size stats_out for
+ * width 64).  Consumed by tavsr_csgu_fwd_fused: the LayerNorm(Ch) statistics of the cgMLP gate half
+ * (espnet ConvolutionalSpatialGatingUnit.norm, reached from encoder_layer.py:220) cost no extra
+ * pass over the hidden activation. */
+int tavsr_gemm_bias_act_stats(const void* x, long long ldx, const void* w, long long ldw,
+                              const float* bias, void* y, long long ldy, int M, int N, int K,
+                              int act, int round_out, int dtype, float* stats_out, int stats_col0,
+                              int* stats_part_width, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Row-complete GEMM, N == 256 (the model width): one thread owns one output row, so everything that
  * follows the projection in the reference layer is fused into the epilogue:
@@ -189,6 +201,16 @@ int tavsr_layernorm(const float* x, long long ldx, int M, int D, float eps, cons
 int tavsr_relpos_attn_fwd(const float* qkv, long long ld_qkv, const float* pos, long long ld_pos,
                           const float* u, const float* v, const int32_t* lens, float* ctx,
                           long long ld_ctx, int B, int T, int H, int round_out, void* stream);
+/* Same kernel; additionally dots_out[(row * 2H + 2h + half)] = (ctx_part . dva_part, ctx_part .
+ * dvb_part) for the 32 context columns [64h + 32half, +32) of every row: the partial
+ * pooling_proj1 / weight_proj1 scores of the learned_ave merge (encoder_layer.py:243,258) with
+ * attn.linear_out folded into dva / dvb ([H*64] each, 16-byte aligned).  tavsr_merge_learned_ave_weights2
+ * sums the 2H parts. */
+int tavsr_relpos_attn_fwd_dots(const float* qkv, long long ld_qkv, const float* pos,
+                               long long ld_pos, const float* u, const float* v,
+                               const int32_t* lens, float* ctx, long long ld_ctx, int B, int T,
+                               int H, int round_out, const float* dva, const float* dvb,
+                               float* dots_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Convolutional spatial gating unit (espnet ConvolutionalSpatialGatingUnit.forward, reached through
@@ -201,6 +223,17 @@ int tavsr_csgu_fwd(const float* h, long long ldh, const float* norm_g, const flo
                    const float* conv_w /* [Ch,31] */, const float* conv_b, float* out,
                    long long ldo, float* stats, int B, int T, int Ch, int ksize, float eps,
                    int round_out, void* stream);
+/* Fused form for the two-branch block: LayerNorm statistics come as the partials written by
+ * tavsr_gemm_bias_act_stats (n_part parts of part_w channels, n_part * part_w == Ch, n_part <= 16),
+ * or, with stats_part == NULL, from the stand-alone statistics pass into the `stats` scratch;
+ * optionally emits per frame and 128-channel slab the partial dots of the OUTPUT with dva / dvb
+ * ([Ch] each): dots_out[(frame * (Ch/128) + slab)] = (a, b) - the pooling_proj2 / weight_proj2
+ * scores (encoder_layer.py:262,277) with channel_proj2 folded in. */
+int tavsr_csgu_fwd_fused(const float* h, long long ldh, const float* norm_g, const float* norm_b,
+                         const float* conv_w, const float* conv_b, float* out, long long ldo,
+                         float* stats, const float* stats_part, int n_part, int part_w, const float* dva,
+                         const float* dvb, float* dots_out, int B, int T, int Ch, int ksize,
+                         float eps, int round_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * learned_ave merge weights (encoder_layer.py:241-289).  dotsK[row] = (x_K . pooling_projK.weight,
@@ -220,6 +253,19 @@ int tavsr_merge_learned_ave_weights(const float* dots1, const float* dots2, cons
                                     float pool_b1, float pool_b2, float wproj_b1, float wproj_b2,
                                     float inv_sqrt_size, float* w1, float* w2, int B, int T,
                                     void* stream);
+/* General form: dotsK holds npK partial pairs per frame ([B*T, npK, 2], summed inside) and each
+ * branch has its own length array (lens2 == NULL: lens1) - the two modalities of
+ * AdaptiveAudioVisualFusion carry separate masks (adaptive_audiovisual_fusion.py:150-183). */
+int tavsr_merge_learned_ave_weights2(const float* dots1, int np1, const float* dots2, int np2,
+                                     const int32_t* lens1, const int32_t* lens2, float pool_b1,
+                                     float pool_b2, float wproj_b1, float wproj_b2,
+                                     float inv_sqrt_size, float* w1, float* w2, int B, int T,
+                                     void* stream);
+/* out[m,:] = w1[m / rows_per_seg] * a[m,:] + w2[m / rows_per_seg] * b[m,:]: the weighted modality
+ * average in front of the fusion FFN (adaptive_audiovisual_fusion.py:187-194).  D % 4 == 0. */
+int tavsr_scale_add_rows(const float* a, long long lda, const float* b, long long ldb,
+                         const float* w1, const float* w2, int rows_per_seg, float* out,
+                         long long ldo, int M, int D, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * CTC head: logits = hs . W^T + b in fp32 FMA (argmax must be bit-stable), then log-softmax /

@@ -68,6 +68,9 @@ SIGNATURES = {
     "tavsr_gemm_bias_act": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p,
                                     c_longlong, c_int, c_int, c_int, c_int, c_int, c_int,
                                     c_void_p]),
+    "tavsr_gemm_bias_act_stats": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p,
+                                          c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_int,
+                                          c_int, c_void_p, c_int, POINTER(c_int), c_void_p]),
     "tavsr_gemm_rowln": (c_int, [POINTER(RowLNArgs), c_void_p]),
     "tavsr_rowln_workspace_bytes": (c_size_t, [c_int]),
     "tavsr_ffn_fused": (c_int, [POINTER(FfnArgs), c_void_p]),
@@ -77,6 +80,20 @@ SIGNATURES = {
     "tavsr_relpos_attn_fwd": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int,
                                       c_int, c_int, c_void_p]),
+    "tavsr_relpos_attn_fwd_dots": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p,
+                                           c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int,
+                                           c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tavsr_csgu_fwd_fused": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_int, c_void_p,
+                                     c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
+                                     c_int, c_void_p]),
+    "tavsr_merge_learned_ave_weights2": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p,
+                                                 c_void_p, c_float, c_float, c_float, c_float,
+                                                 c_float, c_void_p, c_void_p, c_int, c_int,
+                                                 c_void_p]),
+    "tavsr_scale_add_rows": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p,
+                                     c_void_p, c_int, c_void_p, c_longlong, c_int, c_int,
+                                     c_void_p]),
     "tavsr_csgu_fwd": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_longlong, c_void_p, c_int, c_int, c_int, c_int,
                                c_float, c_int, c_void_p]),

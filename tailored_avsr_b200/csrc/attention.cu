@@ -22,7 +22,8 @@ namespace tavsr {
 extern std::atomic<long long> g_launches;
 int relpos_attn_tc_launch(const float* qkv, long long ld_qkv, const float* pos, long long ld_pos,
                           const float* u, const float* v, const int32_t* lens, float* ctx,
-                          long long ld_ctx, int B, int T, int H, int round_out, cudaStream_t s);
+                          long long ld_ctx, int B, int T, int H, int round_out, const float* dva,
+                          const float* dvb, float* dots_out, cudaStream_t s);
 
 namespace attn {
 
@@ -268,7 +269,19 @@ extern "C" int tavsr_relpos_attn_fwd(const float* qkv, long long ld_qkv, const f
                                      long long ld_pos, const float* u, const float* v,
                                      const int32_t* lens, float* ctx, long long ld_ctx, int B,
                                      int T, int H, int round_out, void* stream) {
+  return tavsr_relpos_attn_fwd_dots(qkv, ld_qkv, pos, ld_pos, u, v, lens, ctx, ld_ctx, B, T, H,
+                                    round_out, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int tavsr_relpos_attn_fwd_dots(const float* qkv, long long ld_qkv, const float* pos,
+                                          long long ld_pos, const float* u, const float* v,
+                                          const int32_t* lens, float* ctx, long long ld_ctx, int B,
+                                          int T, int H, int round_out, const float* dva,
+                                          const float* dvb, float* dots_out, void* stream) {
   TAVSR_REQUIRE(B > 0 && T > 0 && H > 0, "attn: bad shape B=%d T=%d H=%d", B, T, H);
+  TAVSR_REQUIRE(!dots_out || (dva && dvb && (reinterpret_cast<uintptr_t>(dva) & 15) == 0 &&
+                              (reinterpret_cast<uintptr_t>(dvb) & 15) == 0),
+                "attn: dots_out needs 16-byte aligned dva / dvb");
   TAVSR_REQUIRE(qkv && pos && u && v && ctx, "attn: null pointer");
   TAVSR_REQUIRE(ld_qkv % 4 == 0 && ld_pos % 4 == 0 && ld_ctx % 2 == 0,
                 "attn: pitches must be multiples of 4 (qkv, pos) / 2 (ctx)");
@@ -281,10 +294,12 @@ extern "C" int tavsr_relpos_attn_fwd(const float* qkv, long long ld_qkv, const f
   // g_debug[8] = 1 forces the mma.sync kernel below.
   if (g_debug[8] != 1 && ld_ctx % 4 == 0 && (reinterpret_cast<uintptr_t>(ctx) & 15) == 0) {
     const int rc = relpos_attn_tc_launch(qkv, ld_qkv, pos, ld_pos, u, v, lens, ctx, ld_ctx, B, T, H,
-                                         round_out, s);
+                                         round_out, dva, dvb, dots_out, s);
     if (rc == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
     return rc;
   }
+  TAVSR_REQUIRE(dots_out == nullptr, "attn: the fused row dots need the tcgen05 kernel "
+                                     "(16-byte aligned ctx with a pitch multiple of 4)");
   const int smem = attn::kSmemFloats * 4;
   static bool configured = false;
   if (!configured) {

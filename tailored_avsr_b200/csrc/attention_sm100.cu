@@ -66,6 +66,11 @@ struct Params {
   float* ctx;
   long long ld_ctx;
   int T, H, round_out;
+  // optional: partial row dots of the stored context with two (H*64)-vectors, one (a, b) pair per
+  // (head, 32-column half): dots_out[(row * 2H + 2h + half)] - the learned_ave pooling scores
+  const float* dva;
+  const float* dvb;
+  float2* dots_out;
   long long* dbg;  // optional phase timestamps (16 per CTA), tools/time_attn.py
 };
 
@@ -379,6 +384,9 @@ relpos_attn_tc_kernel(const __grid_constant__ Params p) {
       tmem_ld32(trow + (dbg == 1 ? kColS : kColO) + 32 * hf, ro);
       tmem_ld_wait();
       if (i < T) {
+        float da = 0.f, db = 0.f;
+        const float4* va4 = reinterpret_cast<const float4*>(p.dva + hcol + 32 * hf);
+        const float4* vb4 = reinterpret_cast<const float4*>(p.dvb + hcol + 32 * hf);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           float4 o = make_float4(__uint_as_float(ro[4 * e]) * inv, __uint_as_float(ro[4 * e + 1]) * inv,
@@ -387,11 +395,20 @@ relpos_attn_tc_kernel(const __grid_constant__ Params p) {
             o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
           }
           *reinterpret_cast<float4*>(out + 4 * e) = o;
+          if (p.dots_out != nullptr) {
+            const float4 a4 = __ldg(va4 + e), b4 = __ldg(vb4 + e);
+            da += o.x * a4.x + o.y * a4.y + o.z * a4.z + o.w * a4.w;
+            db += o.x * b4.x + o.y * b4.y + o.z * b4.z + o.w * b4.w;
+          }
         }
+        if (p.dots_out != nullptr)
+          p.dots_out[static_cast<long long>(row0 + i) * (2 * p.H) + 2 * h + hf] = make_float2(da, db);
       }
     } else if (i < T) {
       for (int e = 0; e < 8; ++e)
         *reinterpret_cast<float4*>(out + 4 * e) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.dots_out != nullptr)
+        p.dots_out[static_cast<long long>(row0 + i) * (2 * p.H) + 2 * h + hf] = make_float2(0.f, 0.f);
     }
   }
 
@@ -408,7 +425,8 @@ relpos_attn_tc_kernel(const __grid_constant__ Params p) {
 
 int relpos_attn_tc_launch(const float* qkv, long long ld_qkv, const float* pos, long long ld_pos,
                           const float* u, const float* v, const int32_t* lens, float* ctx,
-                          long long ld_ctx, int B, int T, int H, int round_out, cudaStream_t s) {
+                          long long ld_ctx, int B, int T, int H, int round_out, const float* dva,
+                          const float* dvb, float* dots_out, cudaStream_t s) {
   attn_tc::Params p;
   memset(&p, 0, sizeof(p));
   int rc;
@@ -425,6 +443,9 @@ int relpos_attn_tc_launch(const float* qkv, long long ld_qkv, const float* pos, 
   p.ld_ctx = ld_ctx;
   p.T = T;
   p.H = H;
+  p.dva = dva;
+  p.dvb = dvb;
+  p.dots_out = reinterpret_cast<float2*>(dots_out);
   p.dbg = reinterpret_cast<long long*>(g_debug_ptr);
   p.round_out = (round_out ? 1 : 0) | (g_debug[9] << 8);
   static bool configured = false;

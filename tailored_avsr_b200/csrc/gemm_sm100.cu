@@ -124,10 +124,10 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, bool is_bf16
 // ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
-template <bool kTf32, int kBlockN, int kMode, bool kDual, int kCtas, int kAct>
+template <bool kTf32, int kBlockN, int kMode, bool kDual, int kCtas, int kAct, bool kStats = false>
 static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<kTf32, kBlockN, kMode, kDual, kCtas>;
-  auto kern = gemm_sm100_kernel<kTf32, kBlockN, kMode, kDual, kCtas, kAct>;
+  auto kern = gemm_sm100_kernel<kTf32, kBlockN, kMode, kDual, kCtas, kAct, kStats>;
   static bool configured = false;
   if (!configured) {
     TAVSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -145,6 +145,11 @@ static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
 // Tiled GEMM dispatch over (tile width, CTA pairing, activation).
 template <int kBlockN, int kCtas>
 static int launch_tiled(const GemmParams& p, cudaStream_t s) {
+  if (p.stats_out != nullptr) {
+    // the partial-statistics epilogue is its own instantiation (run-time activation): the plain
+    // kernels keep the exact code they had without it
+    return launch_gemm<true, kBlockN, kModeTiled, false, kCtas, -1, true>(p, s);
+  }
   if constexpr (kCtas == 1) {
     return launch_gemm<true, kBlockN, kModeTiled, false, 1, -1>(p, s);
   } else {
@@ -177,6 +182,14 @@ extern "C" int tavsr_debug_set_ptr(void* p) {
 extern "C" int tavsr_gemm_bias_act(const void* x, long long ldx, const void* w, long long ldw,
                                    const float* bias, void* y, long long ldy, int M, int N, int K,
                                    int act, int round_out, int dtype, void* stream) {
+  return tavsr_gemm_bias_act_stats(x, ldx, w, ldw, bias, y, ldy, M, N, K, act, round_out, dtype,
+                                   nullptr, 0, nullptr, stream);
+}
+
+extern "C" int tavsr_gemm_bias_act_stats(const void* x, long long ldx, const void* w, long long ldw,
+                                         const float* bias, void* y, long long ldy, int M, int N,
+                                         int K, int act, int round_out, int dtype, float* stats_out,
+                                         int stats_col0, int* stats_part_width, void* stream) {
   TAVSR_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   TAVSR_REQUIRE(dtype == TAVSR_DT_TF32, "gemm: only TAVSR_DT_TF32 is built in this round");
   TAVSR_REQUIRE(K % 4 == 0 && N % 4 == 0, "gemm: K and N must be multiples of 4 (K=%d N=%d)", K, N);
@@ -199,6 +212,17 @@ extern "C" int tavsr_gemm_bias_act(const void* x, long long ldx, const void* w, 
   const int bn = (use128 && g_debug[2] != 256) ? 128 : 256;
   p.num_m_tiles = mt;
   p.num_n_tiles = (N + bn - 1) / bn;
+  if (stats_out != nullptr) {
+    const int pw = bn / 2;  // columns per epilogue warp == columns per statistics part
+    TAVSR_REQUIRE(stats_part_width != nullptr && stats_col0 >= 0 && stats_col0 < N &&
+                      stats_col0 % pw == 0 && N % pw == 0,
+                  "gemm: statistics columns [%d, %d) must be multiples of the part width %d",
+                  stats_col0, N, pw);
+    p.stats_out = reinterpret_cast<float2*>(stats_out);
+    p.stats_col0 = stats_col0;
+    p.stats_parts = (N - stats_col0) / pw;
+    *stats_part_width = pw;
+  }
   int rc;
   if ((rc = make_tmap_2d(&p.tmA, x, 4, false, M, K, ldx, 128, 32))) return rc;
   if ((rc = make_tmap_2d(&p.tmB, w, 4, false, N, K, ldw, bn / ctas, 32))) return rc;

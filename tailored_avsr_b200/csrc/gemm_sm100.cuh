@@ -69,6 +69,14 @@ struct alignas(64) GemmParams {
   // folded in).  seg_bias: dot1 / dot2 hold per-branch bias vectors scaled like the accumulators.
   int seq_kb1;
   int seg_bias;
+  // ---- Tiled mode: per-row partial LayerNorm statistics of the stored output columns
+  // [stats_col0, N): every epilogue warp owns kBlockN/2 columns of 32 rows and writes one
+  // (mean, M2 = sum (x - mean)^2) pair per row, stats_out[m * stats_parts + part].  The consumer
+  // (CSGU conv kernel) combines the parts, so the stand-alone statistics pass over the cgMLP
+  // hidden activation disappears.
+  float2* stats_out;
+  int stats_col0;
+  int stats_parts;
 };
 
 template <bool kTf32, int kBlockN, int kMode, bool kDual, int kCtas>
@@ -365,7 +373,7 @@ __device__ __forceinline__ void rowln_finish(const GemmParams& p, const float* s
     }
 }
 
-template <bool kTf32, int kBlockN, int kMode, bool kDual, int kCtas, int kAct>
+template <bool kTf32, int kBlockN, int kMode, bool kDual, int kCtas, int kAct, bool kStats = false>
 __global__ void __launch_bounds__(GemmCfg<kTf32, kBlockN, kMode, kDual, kCtas>::kThreads, 1)
 gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<kTf32, kBlockN, kMode, kDual, kCtas>;
@@ -549,6 +557,8 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
         const int col0 = half * (kBlockN / 2);
         uint32_t r[2][32];
         tmem_ld32(tacc + col0, r[0]);
+        const bool do_stats = kStats && p.stats_out != nullptr && n0 + col0 >= p.stats_col0;  // warp-uniform
+        float st_n = 0.f, st_mean = 0.f, st_m2 = 0.f;
 #pragma unroll
         for (int c = 0; c < kChunks; ++c) {
           const int col = col0 + c * 32;
@@ -586,8 +596,33 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
               x = apply_act<kAct>(x, p.act);
               v[j] = p.round_c ? round_tf32(x) : x;
             }
+            if (do_stats) {
+              // two-pass statistics of the 32 values in registers, merged into the running
+              // (count, mean, M2) of this row's part (Chan et al.)
+              float s = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) s += v[j];
+              const float mc = s * (1.0f / 32.0f);
+              float qd = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float dj = v[j] - mc;
+                qd = fmaf(dj, dj, qd);
+              }
+              const float delta = mc - st_mean;
+              const float tot = st_n + 32.0f;
+              st_mean = fmaf(delta, __fdividef(32.0f, tot), st_mean);
+              st_m2 += qd + delta * delta * __fdividef(st_n * 32.0f, tot);
+              st_n = tot;
+            }
             stager.store(&p.tmC, v, n0 + col, m0 + q * 32);
           }
+        }
+        if (do_stats) {
+          const int mrow = m0 + q * 32 + static_cast<int>(lane);
+          if (mrow < p.M)
+            p.stats_out[static_cast<long long>(mrow) * p.stats_parts +
+                        (n0 + col0 - p.stats_col0) / (kBlockN / 2)] = make_float2(st_mean, st_m2);
         }
       } else {
         // ---------------------------- row-complete epilogue ----------------------------------

@@ -67,6 +67,11 @@ __device__ __forceinline__ float ld_act(const float* p) {
   asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
 }
+__device__ __forceinline__ float2 ld_act2(const float2* p) {
+  float2 v;
+  asm volatile("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ float4 ld_act4(const float4* p) {
   float4 v;
   asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];"

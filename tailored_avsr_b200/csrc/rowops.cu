@@ -113,10 +113,37 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsr
                : "memory");
 }
 
+// sum over the 32 lanes of 32 per-lane values in 31 shuffles: afterwards v[0] of lane j holds the
+// warp total of value j (each step halves the values a lane carries and exchanges the other half)
+__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], uint32_t lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+// Optional fused inputs / outputs (the two-branch block path):
+//   stats_part != null : LayerNorm statistics arrive as n_part partial (mean, M2) pairs per frame,
+//                        each over part_w channels, written by the channel_proj1 GEMM epilogue
+//                        (Chan's parallel combination; no stand-alone statistics pass)
+//   dots_out != null   : per frame the partial dot products of this CTA's 128 output channels with
+//                        dva / dvb (the folded pooling_proj / weight_proj vectors of the learned_ave
+//                        merge, encoder_layer.py:243,258): dots_out[(frame * gridDim.x + slab)]
+template <bool kFused>
 __global__ void __launch_bounds__(kCh, 4)
 csgu_conv_kernel(const float* __restrict__ h, long long ldh, const float* __restrict__ norm_g,
                  const float* __restrict__ norm_b, const float* __restrict__ conv_w,
                  const float* __restrict__ conv_b, const float2* __restrict__ stats,
+                 const float2* __restrict__ stats_part, int n_part, int part_w, float eps,
+                 const float* __restrict__ dva, const float* __restrict__ dvb,
+                 float2* __restrict__ dots_out,
                  float* __restrict__ out, long long ldo, int T, int Ch, int round_out) {
   __shared__ __align__(16) float s_tile[kRows][kCh];
   __shared__ float2 s_ab[kRows];  // per frame: (rstd, -mean*rstd); (0,0) outside [0,T)
@@ -131,6 +158,11 @@ csgu_conv_kernel(const float* __restrict__ h, long long ldh, const float* __rest
     gam = __ldg(norm_g + c_early);
     bet = __ldg(norm_b + c_early);
     cb = __ldg(conv_b + c_early);
+  }
+  float dwa = 0.f, dwb = 0.f;
+  if (kFused && dots_out != nullptr && c_early < Ch) {
+    dwa = __ldg(dva + c_early);
+    dwb = __ldg(dvb + c_early);
   }
   pdl_wait();
   const int c0 = blockIdx.x * kCh;
@@ -149,7 +181,32 @@ csgu_conv_kernel(const float* __restrict__ h, long long ldh, const float* __rest
     const int t = t0 - kHalo + i;
     float2 ab = make_float2(0.f, 0.f);
     if (t >= 0 && t < T) {
-      const float2 st = stats[row0 + t];
+      float2 st;
+      if (kFused && stats_part != nullptr) {
+        // all partials of the frame are requested before the first use (n_part <= 16)
+        const float2* sp = stats_part + (row0 + t) * n_part;
+        float2 pq[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) pq[q] = q < n_part ? ld_act2(sp + q) : make_float2(0.f, 0.f);
+        float msum = 0.f, m2 = 0.f;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          msum += pq[q].x;
+          m2 += pq[q].y;
+        }
+        const float mean = msum / static_cast<float>(n_part);
+        float dev = 0.f;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const float dq = q < n_part ? pq[q].x - mean : 0.f;
+          dev = fmaf(dq, dq, dev);
+        }
+        const float var = (m2 + static_cast<float>(part_w) * dev) /
+                          (static_cast<float>(part_w) * static_cast<float>(n_part));
+        st = make_float2(mean, rsqrtf(var + eps));
+      } else {
+        st = stats[row0 + t];
+      }
       ab = make_float2(st.y, -st.x * st.y);
     }
     s_ab[i] = ab;
@@ -180,12 +237,43 @@ csgu_conv_kernel(const float* __restrict__ h, long long ldh, const float* __rest
         if (k >= 0 && k < kTaps) acc[o] = fmaf(w[k], xn, acc[o]);
       }
     }
+    if constexpr (!kFused) {
+#pragma unroll
+      for (int o = 0; o < kGrp; ++o) {
+        const int t = tb + o;
+        if (t < T) {
+          const float y = rv[o] * (acc[o] + cb);
+          out[(row0 + t) * ldo + c] = round_out ? round_tf32(y) : y;
+        }
+      }
+      continue;
+    }
+    float dv[2 * kGrp];
 #pragma unroll
     for (int o = 0; o < kGrp; ++o) {
       const int t = tb + o;
-      if (t < T) {
-        const float y = rv[o] * (acc[o] + cb);
-        out[(row0 + t) * ldo + c] = round_out ? round_tf32(y) : y;
+      float y = rv[o] * (acc[o] + cb);
+      y = round_out ? round_tf32(y) : y;
+      if (t < T) out[(row0 + t) * ldo + c] = y;
+      dv[2 * o] = y * dwa;
+      dv[2 * o + 1] = y * dwb;
+    }
+    if (dots_out != nullptr) {  // block-uniform
+      const uint32_t lane = threadIdx.x & 31;
+      const int wrp = threadIdx.x >> 5;
+      // the per-warp totals are exchanged through rows 0 / 1 of the gate tile: group g only reads
+      // rows >= 16 g, and every thread writes the column it alone has been reading, so the rows
+      // are dead by the time they are overwritten (two rows = double buffer, one barrier per group)
+      const int buf = (g0 / kGrp) & 1;
+      s_tile[buf][threadIdx.x] = warp_transpose_sum32(dv, lane);
+      __syncthreads();
+      if (wrp == 0) {
+        float tot = 0.f;
+#pragma unroll
+        for (int q = 0; q < kCh / 32; ++q) tot += s_tile[buf][q * 32 + lane];
+        const int t = tb + static_cast<int>(lane >> 1);
+        if (t < T)
+          reinterpret_cast<float*>(dots_out)[((row0 + t) * gridDim.x + blockIdx.x) * 2 + (lane & 1)] = tot;
       }
     }
   }
@@ -243,10 +331,68 @@ row_dots_kernel(const float* __restrict__ a1, long long ld1, int K1, const float
 }
 
 // ------------------------------------------------------------------------------------------------
-// learned_ave merge weights: one warp per utterance.
+// learned_ave merge weights: one warp per utterance.  dotsK holds npK partial (score, z) pairs per
+// frame (np = 1: the row dots of a row-complete GEMM / row_dots; np > 1: the partials the
+// attention and CSGU kernels emit per head half / channel slab), summed on the fly.  (A CTA per
+// utterance with block reductions measured 6 us SLOWER per launch inside the PDL-chained graph.)
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 sum_partials(const float2* d, int np) {
+  float2 acc = ld_act2(d);
+  for (int q = 1; q < np; ++q) {
+    const float2 v = ld_act2(d + q);
+    acc.x += v.x;
+    acc.y += v.y;
+  }
+  return acc;
+}
+
 __global__ void __launch_bounds__(128)
-merge_weights_kernel(const float2* __restrict__ dots1, const float2* __restrict__ dots2,
+merge_weights_kernel(const float2* __restrict__ dots1, int np1, const float2* __restrict__ dots2,
+                     int np2, const int32_t* __restrict__ lens1, const int32_t* __restrict__ lens2,
+                     float pool_b1, float pool_b2, float wproj_b1, float wproj_b2, float inv_sqrt,
+                     float* __restrict__ w1, float* __restrict__ w2, int B, int T) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const uint32_t lane = lane_id();
+  float omega[2];
+#pragma unroll
+  for (int br = 0; br < 2; ++br) {
+    const int32_t* lens = br == 0 ? lens1 : (lens2 ? lens2 : lens1);
+    int len = lens ? lens[b] : T;
+    len = len < 0 ? 0 : (len > T ? T : len);
+    const int np = br == 0 ? np1 : np2;
+    const float2* d = (br == 0 ? dots1 : dots2) + static_cast<long long>(b) * T * np;
+    const float pb = br == 0 ? pool_b1 : pool_b2;
+    float mx = -INFINITY;
+    for (int t = lane; t < len; t += 32)
+      mx = fmaxf(mx, (sum_partials(d + static_cast<long long>(t) * np, np).x + pb) * inv_sqrt);
+    mx = warp_max(mx);
+    float se = 0.f, sz = 0.f;
+    for (int t = lane; t < len; t += 32) {
+      const float2 v = sum_partials(d + static_cast<long long>(t) * np, np);
+      const float e = expf((v.x + pb) * inv_sqrt - mx);
+      se += e;
+      sz += e * v.y;
+    }
+    se = warp_sum(se);
+    sz = warp_sum(sz);
+    // len == 0: every score is masked, softmax-then-zero gives an all-zero pooling vector
+    omega[br] = (len > 0 ? sz / se : 0.f) + (br == 0 ? wproj_b1 : wproj_b2);
+  }
+  if (lane == 0) {
+    const float m = fmaxf(omega[0], omega[1]);
+    const float e0 = expf(omega[0] - m), e1 = expf(omega[1] - m);
+    w1[b] = e0 / (e0 + e1);
+    w2[b] = e1 / (e0 + e1);
+  }
+}
+
+// np == 1 and one length array: the hot two-branch block path, kept exactly as tuned (this
+// kernel sits alone on the critical path between the branches and the merge GEMM)
+__global__ void __launch_bounds__(128)
+merge_weights_plain_kernel(const float2* __restrict__ dots1, const float2* __restrict__ dots2,
                      const int32_t* __restrict__ lens, float pool_b1, float pool_b2, float wproj_b1,
                      float wproj_b2, float inv_sqrt, float* __restrict__ w1, float* __restrict__ w2,
                      int B, int T) {
@@ -285,6 +431,29 @@ merge_weights_kernel(const float2* __restrict__ dots1, const float2* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// out[m,:] = w1[m / rows_per_seg] * a[m,:] + w2[m / rows_per_seg] * b[m,:]   (the weighted modality
+// average in front of the fusion FFN, adaptive_audiovisual_fusion.py:187-194)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+scale_add_rows_kernel(const float* __restrict__ a, long long lda, const float* __restrict__ b,
+                      long long ldb, const float* __restrict__ w1, const float* __restrict__ w2,
+                      int rows_per_seg, float* __restrict__ out, long long ldo, int M, int D4) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long total = static_cast<long long>(M) * D4;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int m = static_cast<int>(idx / D4), q = static_cast<int>(idx % D4);
+    const int seg = m / rows_per_seg;
+    const float s1 = ld_act(w1 + seg), s2 = ld_act(w2 + seg);
+    const float4 x = ld_act4(reinterpret_cast<const float4*>(a + m * lda) + q);
+    const float4 y = ld_act4(reinterpret_cast<const float4*>(b + m * ldb) + q);
+    reinterpret_cast<float4*>(out + m * ldo)[q] =
+        make_float4(s1 * x.x + s2 * y.x, s1 * x.y + s2 * y.y, s1 * x.z + s2 * y.z, s1 * x.w + s2 * y.w);
+  }
+}
+
 }  // namespace tavsr
 
 using namespace tavsr;
@@ -317,31 +486,73 @@ extern "C" int tavsr_layernorm(const float* x, long long ldx, int M, int D, floa
   return 0;
 }
 
-extern "C" int tavsr_csgu_fwd(const float* h, long long ldh, const float* norm_g,
-                              const float* norm_b, const float* conv_w, const float* conv_b,
-                              float* out, long long ldo, float* stats, int B, int T, int Ch,
-                              int ksize, float eps, int round_out, void* stream) {
+static int csgu_launch(const float* h, long long ldh, const float* norm_g, const float* norm_b,
+                       const float* conv_w, const float* conv_b, float* out, long long ldo,
+                       float* stats, const float* stats_part, int n_part, int part_w,
+                       const float* dva, const float* dvb, float* dots_out, int B, int T, int Ch,
+                       int ksize, float eps, int round_out, void* stream) {
   TAVSR_REQUIRE(ksize == kTaps, "csgu: only kernel size 31 is built (got %d)", ksize);
   TAVSR_REQUIRE(B > 0 && T > 0 && Ch > 0 && Ch % 128 == 0 && Ch <= 2048, "csgu: bad shape");
-  TAVSR_REQUIRE(ldh % 4 == 0 && stats != nullptr, "csgu: bad pitch / missing stats scratch");
+  TAVSR_REQUIRE(ldh % 4 == 0 && (stats != nullptr || stats_part != nullptr),
+                "csgu: bad pitch / missing stats scratch");
+  TAVSR_REQUIRE(!stats_part || (n_part >= 1 && n_part <= 16 && n_part * part_w == Ch),
+                "csgu: partial statistics must tile the %d gate channels (n_part=%d, part_w=%d)",
+                Ch, n_part, part_w);
+  TAVSR_REQUIRE(!dots_out || (dva && dvb), "csgu: dots_out needs dva and dvb");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int M = B * T;
   const int grid1 = (M + 7) / 8;
   float2* st = reinterpret_cast<float2*>(stats);
-  switch (Ch / 128) {
-    case 1: TAVSR_CUDA_OK(launch_kernel(csgu_stats_kernel<1>, dim3(grid1), dim3(256), 0, s, 0, h, ldh, M, Ch, eps, st)); break;
-    case 2: TAVSR_CUDA_OK(launch_kernel(csgu_stats_kernel<2>, dim3(grid1), dim3(256), 0, s, 0, h, ldh, M, Ch, eps, st)); break;
-    case 4: TAVSR_CUDA_OK(launch_kernel(csgu_stats_kernel<4>, dim3(grid1), dim3(256), 0, s, 0, h, ldh, M, Ch, eps, st)); break;
-    case 8: TAVSR_CUDA_OK(launch_kernel(csgu_stats_kernel<8>, dim3(grid1), dim3(256), 0, s, 0, h, ldh, M, Ch, eps, st)); break;
-    case 16: TAVSR_CUDA_OK(launch_kernel(csgu_stats_kernel<16>, dim3(grid1), dim3(256), 0, s, 0, h, ldh, M, Ch, eps, st)); break;
-    default: return set_error(TAVSR_ERR_UNSUPPORTED, "csgu: Ch=%d not instantiated", Ch);
+  int launches = 1;
+  if (stats_part == nullptr) {
+    ++launches;
+    switch (Ch / 128) {
+      case 1: TAVSR_CUDA_OK(launch_kernel(csgu_stats_kernel<1>, dim3(grid1), dim3(256), 0, s, 0, h, ldh, M, Ch, eps, st)); break;
+      case 2: TAVSR_CUDA_OK(launch_kernel(csgu_stats_kernel<2>, dim3(grid1), dim3(256), 0, s, 0, h, ldh, M, Ch, eps, st)); break;
+      case 4: TAVSR_CUDA_OK(launch_kernel(csgu_stats_kernel<4>, dim3(grid1), dim3(256), 0, s, 0, h, ldh, M, Ch, eps, st)); break;
+      case 8: TAVSR_CUDA_OK(launch_kernel(csgu_stats_kernel<8>, dim3(grid1), dim3(256), 0, s, 0, h, ldh, M, Ch, eps, st)); break;
+      case 16: TAVSR_CUDA_OK(launch_kernel(csgu_stats_kernel<16>, dim3(grid1), dim3(256), 0, s, 0, h, ldh, M, Ch, eps, st)); break;
+      default: return set_error(TAVSR_ERR_UNSUPPORTED, "csgu: Ch=%d not instantiated", Ch);
+    }
+    TAVSR_CUDA_OK(cudaGetLastError());
   }
-  TAVSR_CUDA_OK(cudaGetLastError());
   dim3 grid2(Ch / kCh, (T + kSeg - 1) / kSeg, B);
-  TAVSR_CUDA_OK(launch_kernel(csgu_conv_kernel, grid2, dim3(kCh), 0, s, 0, h, ldh, norm_g, norm_b, conv_w,
-                              conv_b, static_cast<const float2*>(st), out, ldo, T, Ch, round_out));
-  g_launches.fetch_add(2, std::memory_order_relaxed);
+  if (stats_part != nullptr || dots_out != nullptr) {
+    TAVSR_CUDA_OK(launch_kernel(csgu_conv_kernel<true>, grid2, dim3(kCh), 0, s, 0, h, ldh, norm_g, norm_b,
+                                conv_w, conv_b, static_cast<const float2*>(st),
+                                reinterpret_cast<const float2*>(stats_part), n_part, part_w, eps, dva,
+                                dvb, reinterpret_cast<float2*>(dots_out), out, ldo, T, Ch, round_out));
+  } else {
+    TAVSR_CUDA_OK(launch_kernel(csgu_conv_kernel<false>, grid2, dim3(kCh), 0, s, 0, h, ldh, norm_g, norm_b,
+                                conv_w, conv_b, static_cast<const float2*>(st),
+                                static_cast<const float2*>(nullptr), 0, 0, eps,
+                                static_cast<const float*>(nullptr), static_cast<const float*>(nullptr),
+                                static_cast<float2*>(nullptr), out, ldo, T, Ch, round_out));
+  }
+  g_launches.fetch_add(launches, std::memory_order_relaxed);
   return 0;
+}
+
+extern "C" int tavsr_csgu_fwd(const float* h, long long ldh, const float* norm_g,
+                              const float* norm_b, const float* conv_w, const float* conv_b,
+                              float* out, long long ldo, float* stats, int B, int T, int Ch,
+                              int ksize, float eps, int round_out, void* stream) {
+  return csgu_launch(h, ldh, norm_g, norm_b, conv_w, conv_b, out, ldo, stats, nullptr, 0, 0, nullptr,
+                     nullptr, nullptr, B, T, Ch, ksize, eps, round_out, stream);
+}
+
+extern "C" int tavsr_csgu_fwd_fused(const float* h, long long ldh, const float* norm_g,
+                                    const float* norm_b, const float* conv_w, const float* conv_b,
+                                    float* out, long long ldo, float* stats,
+                                    const float* stats_part, int n_part, int part_w,
+                                    const float* dva, const float* dvb, float* dots_out, int B,
+                                    int T, int Ch, int ksize, float eps, int round_out,
+                                    void* stream) {
+  TAVSR_REQUIRE(stats_part != nullptr || stats != nullptr,
+                "csgu_fused: needs stats_part or a stats scratch");
+  return csgu_launch(h, ldh, norm_g, norm_b, conv_w, conv_b, out, ldo, stats_part ? nullptr : stats,
+                     stats_part, n_part, part_w, dva, dvb, dots_out, B, T, Ch, ksize, eps, round_out,
+                     stream);
 }
 
 extern "C" int tavsr_row_dots(const float* a1, long long ld1, int K1, const float* va1,
@@ -361,16 +572,50 @@ extern "C" int tavsr_row_dots(const float* a1, long long ld1, int K1, const floa
   return 0;
 }
 
+extern "C" int tavsr_merge_learned_ave_weights2(const float* dots1, int np1, const float* dots2,
+                                                int np2, const int32_t* lens1, const int32_t* lens2,
+                                                float pool_b1, float pool_b2, float wproj_b1,
+                                                float wproj_b2, float inv_sqrt_size, float* w1,
+                                                float* w2, int B, int T, void* stream) {
+  TAVSR_REQUIRE(B > 0 && T > 0 && dots1 && dots2 && w1 && w2 && np1 >= 1 && np2 >= 1,
+                "merge_weights: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (np1 == 1 && np2 == 1 && lens2 == nullptr) {
+    TAVSR_CUDA_OK(launch_kernel(merge_weights_plain_kernel, dim3((B + 3) / 4), dim3(128), 0, s, 0,
+                                reinterpret_cast<const float2*>(dots1),
+                                reinterpret_cast<const float2*>(dots2), lens1, pool_b1, pool_b2,
+                                wproj_b1, wproj_b2, inv_sqrt_size, w1, w2, B, T));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+  }
+  TAVSR_CUDA_OK(launch_kernel(merge_weights_kernel, dim3((B + 3) / 4), dim3(128), 0, s, 0,
+                              reinterpret_cast<const float2*>(dots1), np1,
+                              reinterpret_cast<const float2*>(dots2), np2, lens1, lens2, pool_b1,
+                              pool_b2, wproj_b1, wproj_b2, inv_sqrt_size, w1, w2, B, T));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
 extern "C" int tavsr_merge_learned_ave_weights(const float* dots1, const float* dots2,
                                                const int32_t* lens, float pool_b1, float pool_b2,
                                                float wproj_b1, float wproj_b2, float inv_sqrt_size,
                                                float* w1, float* w2, int B, int T, void* stream) {
-  TAVSR_REQUIRE(B > 0 && T > 0 && dots1 && dots2 && w1 && w2, "merge_weights: bad arguments");
+  return tavsr_merge_learned_ave_weights2(dots1, 1, dots2, 1, lens, nullptr, pool_b1, pool_b2,
+                                          wproj_b1, wproj_b2, inv_sqrt_size, w1, w2, B, T, stream);
+}
+
+extern "C" int tavsr_scale_add_rows(const float* a, long long lda, const float* b, long long ldb,
+                                    const float* w1, const float* w2, int rows_per_seg, float* out,
+                                    long long ldo, int M, int D, void* stream) {
+  TAVSR_REQUIRE(M > 0 && D > 0 && D % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && ldo % 4 == 0 &&
+                    rows_per_seg > 0 && a && b && w1 && w2 && out,
+                "scale_add_rows: bad arguments (M=%d D=%d)", M, D);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  TAVSR_CUDA_OK(launch_kernel(merge_weights_kernel, dim3((B + 3) / 4), dim3(128), 0, s, 0,
-                              reinterpret_cast<const float2*>(dots1),
-                              reinterpret_cast<const float2*>(dots2), lens, pool_b1, pool_b2,
-                              wproj_b1, wproj_b2, inv_sqrt_size, w1, w2, B, T));
+  const long long total = static_cast<long long>(M) * (D / 4);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 8ll * num_sms()) blocks = 8ll * num_sms();
+  TAVSR_CUDA_OK(launch_kernel(scale_add_rows_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0,
+                              s, 0, a, lda, b, ldb, w1, w2, rows_per_seg, out, ldo, M, D / 4));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }

@@ -137,8 +137,7 @@ class MyBranchformerEncoderLayer(torch.nn.Module):
                                     mp.weight.double() @ p2.weight.double()], 1).float().contiguous(),
                          (mp.weight.double() @ lo.bias.double()).float().contiguous(),
                          (mp.weight.double() @ p2.bias.double()).float().contiguous()))
-            ctx = engine.attention_ctx(xa, self.attn, pos_proj, lens, B, T, self._packed, "qkv")
-            u = engine.cgmlp_gated(xm, self.cgmlp, B, T, self._packed, "conv")
+            fv = None
             if learned:
                 pp1, wp1, pp2, wp2 = (self.pooling_proj1, self.weight_proj1, self.pooling_proj2,
                                       self.weight_proj2)
@@ -154,9 +153,27 @@ class MyBranchformerEncoderLayer(torch.nn.Module):
                             float(pp2.bias.double() + pp2.weight.double().reshape(-1) @ p2.bias.double()),
                             float(wp1.bias.double() + wp1.weight.double().reshape(-1) @ lo.bias.double()),
                             float(wp2.bias.double() + wp2.weight.double().reshape(-1) @ p2.bias.double())]))
-                d1, d2 = ops.row_dots(ctx, fv["va1"], fv["vb1"], u, fv["va2"], fv["vb2"])
+            fused_dots = learned and engine.FUSE_DOTS
+            # the two branches are independent until the merge: the cgMLP chain runs on a side
+            # stream (captured as a fork / join in the CUDA graph) so its kernels fill the SMs the
+            # attention kernel's second wave and the persistent GEMMs' tails leave idle
+            with engine.branch_fork(dev) as side:
+                with side:
+                    u = engine.cgmlp_gated(xm, self.cgmlp, B, T, self._packed, "conv",
+                                           dots=(fv["va2"], fv["vb2"]) if fused_dots else None)
+                ctx = engine.attention_ctx(xa, self.attn, pos_proj, lens, B, T, self._packed, "qkv",
+                                           dots=(fv["va1"], fv["vb1"]) if fused_dots else None)
+            if learned:
                 sc = fv["sc"]
-                w1, w2 = ops.merge_weights(d1, d2, lens, sc[0], sc[1], sc[2], sc[3], d, B, T)
+                if fused_dots:
+                    # the pooling / weight scores came out of the attention and CSGU epilogues as
+                    # partial dots (per head half / per 128-channel slab)
+                    (u, d2), (ctx, d1) = u, ctx
+                    w1, w2 = ops.merge_weights2(d1, d1.shape[1], d2, d2.shape[1], lens, None,
+                                                sc[0], sc[1], sc[2], sc[3], d, B, T)
+                else:
+                    d1, d2 = ops.row_dots(ctx, fv["va1"], fv["vb1"], u, fv["va2"], fv["vb2"])
+                    w1, w2 = ops.merge_weights(d1, d2, lens, sc[0], sc[1], sc[2], sc[3], d, B, T)
                 self.weight_global = w1.view(B, 1, 1)
                 self.weight_local = w2.view(B, 1, 1)
             else:

@@ -37,6 +37,51 @@ FFN_FUSED = os.environ.get("TAVSR_FFN_FUSED", "1") != "0"
 # blocks): the merge GEMM then reads the attention context and the gated activations directly
 FOLD_MERGE = os.environ.get("TAVSR_FOLD_MERGE", "1") != "0"
 
+# run the attention and cgMLP branches of a two-branch block on two streams.  MEASURED (C2, graph
+# replay): 3.786 vs 3.789 ms per step - every kernel of the block already fills the GPU (persistent
+# GEMMs, 1 CTA/SM attention), so the branches serialise anyway; opt-in.
+BRANCH_FORK = os.environ.get("TAVSR_BRANCH_FORK", "0") != "0"
+_SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+class branch_fork:
+    """`with branch_fork(dev) as side:` — inside, `with side:` runs launches on a side stream that
+    was made to wait for everything enqueued on the current stream so far; leaving the outer block
+    makes the current stream wait for the side stream (fork / join; under CUDA-graph capture the
+    two chains become parallel graph branches).  Tensors produced on the side stream are only
+    consumed after the join, and every later fork waits for the consumers first, so the caching
+    allocator's per-stream reuse stays ordered."""
+
+    def __init__(self, device, enabled=None):
+        self.device = device
+        self.side = None
+        self.enabled = BRANCH_FORK if enabled is None else enabled
+
+    def __enter__(self):
+        if not self.enabled:
+            return _NullCtx()
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        side = _SIDE_STREAMS.get(idx)
+        if side is None:
+            side = _SIDE_STREAMS[idx] = torch.cuda.Stream(device=self.device)
+        self.side = side
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        return torch.cuda.stream(side)
+
+    def __exit__(self, *exc):
+        if self.side is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.side)
+        return False
+
+
 _ACT = {"swish": ops.ACT_SWISH, "relu": ops.ACT_RELU, "gelu": ops.ACT_GELU}
 
 
@@ -119,13 +164,14 @@ def qkv_weights(attn, cache: PackedCache, key: str):
         torch.cat([attn.linear_q.bias, attn.linear_k.bias, attn.linear_v.bias], 0).contiguous()))
 
 
-def attention_ctx(xa, attn, pos_proj, lens, B, T, cache: PackedCache, key: str):
-    """Fused QKV projection + rel-pos attention; returns ctx (B*T, d)."""
+def attention_ctx(xa, attn, pos_proj, lens, B, T, cache: PackedCache, key: str, dots=None):
+    """Fused QKV projection + rel-pos attention; returns ctx (B*T, d), or (ctx, partial row dots
+    (B*T, 2h, 2)) when `dots=(va, vb)` asks the attention epilogue for the learned_ave scores."""
     wqkv, bqkv = qkv_weights(attn, cache, key)
     qkv = ops.gemm_bias_act(xa, wqkv, bqkv)
     u = attn.pos_bias_u.reshape(-1)
     v = attn.pos_bias_v.reshape(-1)
-    return ops.relpos_attn(qkv, pos_proj, u, v, lens, B, T, attn.h)
+    return ops.relpos_attn(qkv, pos_proj, u, v, lens, B, T, attn.h, dots=dots)
 
 
 def pos_projection(attn, pos_emb: torch.Tensor):
@@ -133,14 +179,40 @@ def pos_projection(attn, pos_emb: torch.Tensor):
     return ops.gemm_bias_act(pos_emb.reshape(-1, pos_emb.shape[-1]), attn.linear_pos.weight, None)
 
 
-def cgmlp_gated(xm, cgmlp, B, T, cache: PackedCache, key: str):
-    """channel_proj1 + GELU + CSGU; returns u (B*T, C/2) ready for channel_proj2."""
+# LayerNorm statistics of the CSGU gate half from the channel_proj1 GEMM epilogue (no stand-alone
+# statistics kernel) and the learned_ave row dots from the attention / CSGU epilogues (no row_dots
+# kernel)
+# MEASURED (C2, CUDA-graph replay): both fusions LOSE inside the PDL-chained graph - the two small
+# kernels they remove mostly overlap their neighbours there, while the extra epilogue work and the
+# partial-summing merge-weights kernel sit on the critical path (3.86 ms -> 3.99-4.03 ms per step) -
+# so they are opt-in; the ncu launch list (cold, serialised) shows the opposite, -18 us per block.
+FUSE_STATS = os.environ.get("TAVSR_FUSE_STATS", "0") != "0"
+FUSE_DOTS = os.environ.get("TAVSR_FUSE_DOTS", "0") != "0"
+
+
+def cgmlp_gated(xm, cgmlp, B, T, cache: PackedCache, key: str, dots=None):
+    """channel_proj1 + GELU + CSGU; returns u (B*T, C/2) ready for channel_proj2, or
+    (u, partial row dots (B*T, C/256, 2)) when `dots=(va, vb)` is given."""
     if cgmlp.csgu.linear is not None or cgmlp.csgu.gate_activation != "identity":
         raise NotImplementedError("use_linear_after_conv / non-identity gate_activation are not "
                                   "built on the B200 path (no shipped config uses them)")
     lin = cgmlp.channel_proj1[0]
-    g = ops.gemm_bias_act(xm, lin.weight, lin.bias, act=ops.ACT_GELU)
     conv = cgmlp.csgu.conv
     cw = cache.get(key, [conv.weight], lambda: conv.weight.reshape(conv.weight.shape[0], -1).contiguous())
-    return ops.csgu(g, cgmlp.csgu.norm.weight, cgmlp.csgu.norm.bias, cw, conv.bias, B, T,
-                    eps=cgmlp.csgu.norm.eps)
+    Ch = lin.weight.shape[0] // 2
+    if FUSE_STATS and Ch % 128 == 0 and Ch // 64 <= 16:
+        g, st, n_part, pw = ops.gemm_bias_act_stats(xm, lin.weight, lin.bias, ops.ACT_GELU, Ch)
+        u, d = ops.csgu_fused(g, cgmlp.csgu.norm.weight, cgmlp.csgu.norm.bias, cw, conv.bias, B, T,
+                              st, n_part, pw, eps=cgmlp.csgu.norm.eps, dots=dots)
+        return u if dots is None else (u, d)
+    if dots is not None and Ch % 128 == 0:
+        g = ops.gemm_bias_act(xm, lin.weight, lin.bias, act=ops.ACT_GELU)
+        return ops.csgu_fused(g, cgmlp.csgu.norm.weight, cgmlp.csgu.norm.bias, cw, conv.bias, B, T,
+                              None, 0, 0, eps=cgmlp.csgu.norm.eps, dots=dots)
+    g = ops.gemm_bias_act(xm, lin.weight, lin.bias, act=ops.ACT_GELU)
+    u = ops.csgu(g, cgmlp.csgu.norm.weight, cgmlp.csgu.norm.bias, cw, conv.bias, B, T,
+                 eps=cgmlp.csgu.norm.eps)
+    if dots is None:
+        return u
+    d, _ = ops.row_dots(u, dots[0], dots[1])
+    return u, d.view(-1, 1, 2)

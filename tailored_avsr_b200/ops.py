@@ -17,7 +17,7 @@ from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SWISH, DT_TF32, FfnArgs, Row
 
 __all__ = [
     "ACT_NONE", "ACT_SWISH", "ACT_GELU", "ACT_RELU",
-    "gemm_bias_act", "gemm_rowln", "ffn_fused", "layernorm", "relpos_attn", "csgu", "merge_weights",
+    "gemm_bias_act", "gemm_bias_act_stats", "csgu_fused", "merge_weights2", "scale_add_rows", "gemm_rowln", "ffn_fused", "layernorm", "relpos_attn", "csgu", "merge_weights",
     "ctc_head", "vocab_residual", "row_dots", "ctc_loss", "ctc_greedy", "ctc_prefix_score", "launch_count",
 ]
 
@@ -104,6 +104,29 @@ def gemm_bias_act(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]
                                   out.data_ptr(), out.stride(0), M, N, K, act, int(round_out),
                                   DT_TF32, _stream()), "tavsr_gemm_bias_act")
     return out
+
+
+@_profiled
+def gemm_bias_act_stats(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: int,
+                        stats_col0: int, out: Optional[torch.Tensor] = None):
+    """gemm_bias_act whose epilogue also emits partial LayerNorm statistics (mean, M2) of the
+    output columns [stats_col0, N) (tavsr_gemm_bias_act_stats).  Returns
+    (out, stats_part (M, n_part, 2), n_part, part_width)."""
+    _chk2d(x, "x")
+    _chk2d(w, "w")
+    M, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), device=x.device, dtype=torch.float32)
+    _chk2d(out, "out")
+    stats = torch.empty((M * ((N - stats_col0) // 64) * 2,), device=x.device, dtype=torch.float32)
+    width = ctypes.c_int(0)
+    check(_lib.load().tavsr_gemm_bias_act_stats(
+        x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), _p(bias), out.data_ptr(),
+        out.stride(0), M, N, K, act, 0, DT_TF32, stats.data_ptr(), stats_col0, ctypes.byref(width),
+        _stream()), "tavsr_gemm_bias_act_stats")
+    n_part = (N - stats_col0) // width.value
+    return out, stats, n_part, width.value
 
 
 def _fill_rowln(a: RowLNArgs, M: int, bias, residual, alpha, ln0, eps0, out_main, round_main, lnA,
@@ -229,17 +252,27 @@ def layernorm(x: torch.Tensor, gA: torch.Tensor, bA: torch.Tensor, eps: float = 
 @_profiled
 def relpos_attn(qkv: torch.Tensor, pos: torch.Tensor, u: torch.Tensor, v: torch.Tensor,
                 lens: Optional[torch.Tensor], B: int, T: int, H: int, round_out: bool = True,
-                out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """ctx = rel-pos MHSA(qkv) for (B*T, 3*H*64) fused projections (tavsr_relpos_attn_fwd)."""
+                out: Optional[torch.Tensor] = None,
+                dots: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+    """ctx = rel-pos MHSA(qkv) for (B*T, 3*H*64) fused projections (tavsr_relpos_attn_fwd).
+    With `dots=(va, vb)` also returns the partial row dots of ctx with the two (H*64)-vectors,
+    (B*T, 2H, 2) (tavsr_relpos_attn_fwd_dots)."""
     _chk2d(qkv, "qkv")
     _chk2d(pos, "pos")
     if out is None:
         out = torch.empty((B * T, H * 64), device=qkv.device, dtype=torch.float32)
-    check(_lib.load().tavsr_relpos_attn_fwd(qkv.data_ptr(), qkv.stride(0), pos.data_ptr(),
-                                            pos.stride(0), u.data_ptr(), v.data_ptr(), _p(lens),
-                                            out.data_ptr(), out.stride(0), B, T, H,
-                                            int(round_out), _stream()), "tavsr_relpos_attn_fwd")
-    return out
+    if dots is None:
+        check(_lib.load().tavsr_relpos_attn_fwd(qkv.data_ptr(), qkv.stride(0), pos.data_ptr(),
+                                                pos.stride(0), u.data_ptr(), v.data_ptr(), _p(lens),
+                                                out.data_ptr(), out.stride(0), B, T, H,
+                                                int(round_out), _stream()), "tavsr_relpos_attn_fwd")
+        return out
+    dout = torch.empty((B * T, 2 * H, 2), device=qkv.device, dtype=torch.float32)
+    check(_lib.load().tavsr_relpos_attn_fwd_dots(
+        qkv.data_ptr(), qkv.stride(0), pos.data_ptr(), pos.stride(0), u.data_ptr(), v.data_ptr(),
+        _p(lens), out.data_ptr(), out.stride(0), B, T, H, int(round_out), dots[0].data_ptr(),
+        dots[1].data_ptr(), dout.data_ptr(), _stream()), "tavsr_relpos_attn_fwd_dots")
+    return out, dout
 
 
 @_profiled
@@ -258,6 +291,63 @@ def csgu(h: torch.Tensor, norm_g: torch.Tensor, norm_b: torch.Tensor, conv_w: to
                                      norm_b.data_ptr(), conv_w.data_ptr(), conv_b.data_ptr(),
                                      out.data_ptr(), out.stride(0), stats.data_ptr(), B, T, Ch,
                                      ksize, eps, int(round_out), _stream()), "tavsr_csgu_fwd")
+    return out
+
+
+@_profiled
+def csgu_fused(h: torch.Tensor, norm_g: torch.Tensor, norm_b: torch.Tensor, conv_w: torch.Tensor,
+               conv_b: torch.Tensor, B: int, T: int, stats_part: Optional[torch.Tensor],
+               n_part: int, part_w: int, eps: float = 1e-12, round_out: bool = True,
+               dots: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+    """csgu() with the LayerNorm statistics taken from the partials of gemm_bias_act_stats
+    (stats_part=None: stand-alone statistics pass) and, with `dots=(va, vb)`, the partial row dots
+    of the output, (B*T, Ch/128, 2) (tavsr_csgu_fwd_fused).  Returns (out, dots-or-None)."""
+    _chk2d(h, "h")
+    Ch = h.shape[1] // 2
+    out = torch.empty((B * T, Ch), device=h.device, dtype=torch.float32)
+    stats = None
+    if stats_part is None:
+        stats = torch.empty((B * T, 2), device=h.device, dtype=torch.float32)
+    dout = None
+    if dots is not None:
+        dout = torch.empty((B * T, Ch // 128, 2), device=h.device, dtype=torch.float32)
+    ksize = conv_w.shape[-1]
+    check(_lib.load().tavsr_csgu_fwd_fused(
+        h.data_ptr(), h.stride(0), norm_g.data_ptr(), norm_b.data_ptr(), conv_w.data_ptr(),
+        conv_b.data_ptr(), out.data_ptr(), out.stride(0), _p(stats), _p(stats_part), n_part, part_w,
+        _p(dots[0]) if dots else None, _p(dots[1]) if dots else None, _p(dout), B, T, Ch, ksize, eps,
+        int(round_out), _stream()), "tavsr_csgu_fwd_fused")
+    return out, dout
+
+
+@_profiled
+def merge_weights2(dots1: torch.Tensor, np1: int, dots2: torch.Tensor, np2: int,
+                   lens1: Optional[torch.Tensor], lens2: Optional[torch.Tensor], pool_b1: float,
+                   pool_b2: float, wproj_b1: float, wproj_b2: float, size: int, B: int, T: int):
+    """learned_ave weights from partial row dots, one length array per branch
+    (tavsr_merge_learned_ave_weights2)."""
+    w1 = torch.empty((B,), device=dots1.device, dtype=torch.float32)
+    w2 = torch.empty((B,), device=dots1.device, dtype=torch.float32)
+    check(_lib.load().tavsr_merge_learned_ave_weights2(
+        dots1.data_ptr(), np1, dots2.data_ptr(), np2, _p(lens1), _p(lens2), pool_b1, pool_b2,
+        wproj_b1, wproj_b2, 1.0 / math.sqrt(size), w1.data_ptr(), w2.data_ptr(), B, T, _stream()),
+        "tavsr_merge_learned_ave_weights2")
+    return w1, w2
+
+
+@_profiled
+def scale_add_rows(a: torch.Tensor, b: torch.Tensor, w1: torch.Tensor, w2: torch.Tensor,
+                   rows_per_seg: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[m] = w1[m // rows_per_seg] * a[m] + w2[m // rows_per_seg] * b[m] (tavsr_scale_add_rows)."""
+    _chk2d(a, "a")
+    _chk2d(b, "b")
+    M, D = a.shape
+    if out is None:
+        out = torch.empty((M, D), device=a.device, dtype=torch.float32)
+    check(_lib.load().tavsr_scale_add_rows(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0),
+                                           w1.data_ptr(), w2.data_ptr(), rows_per_seg,
+                                           out.data_ptr(), out.stride(0), M, D, _stream()),
+          "tavsr_scale_add_rows")
     return out
 
 

@@ -435,3 +435,108 @@ def test_row_dots(M):
     assert (o2.cpu().double() - r2.cpu()).abs().max() < 1e-4 * 32
     o1b, none = ops.row_dots(a1, v[0], v[1])
     assert none is None and torch.equal(o1b, o1)
+
+
+@pytest.mark.parametrize("M,N,K,col0", [(8000, 2048, 256, 1024), (300, 2048, 256, 1024),
+                                        (1000, 512, 256, 256), (130, 256, 64, 0)])
+def test_gemm_bias_act_stats_partials(M, N, K, col0):
+    """Partial (mean, M2) pairs from the GEMM epilogue combine to the LayerNorm statistics of the
+    stored output columns [col0, N)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(M + N)
+    x = torch.randn(M, K, generator=g).to(DEV)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV)
+    b = (torch.randn(N, generator=g) + 0.5).to(DEV)
+    y, st, n_part, pw = ops.gemm_bias_act_stats(x, w, b, ops.ACT_GELU, col0)
+    y_plain = ops.gemm_bias_act(x, w, b, act=ops.ACT_GELU)
+    assert torch.equal(y, y_plain)
+    assert n_part * pw == N - col0
+    part = st[: M * n_part * 2].view(M, n_part, 2).double().cpu()
+    mean = part[..., 0].mean(dim=1)
+    m2 = part[..., 1].sum(dim=1) + pw * ((part[..., 0] - mean[:, None]) ** 2).sum(dim=1)
+    var = m2 / (N - col0)
+    yd = y[:, col0:].double().cpu()
+    assert float((mean - yd.mean(dim=1)).abs().max()) < 1e-6
+    assert max_rel(var, yd.var(dim=1, unbiased=False)) < 1e-5
+
+
+@pytest.mark.parametrize("B,T", [(2, 64), (3, 100), (2, 250), (1, 7)])
+@pytest.mark.parametrize("pw", [64, 128])
+def test_csgu_fused_matches_csgu_and_emits_dots(B, T, pw):
+    ops = _ops()
+    Ch = 1024
+    g = torch.Generator().manual_seed(B * T + pw)
+    h = (torch.randn(B * T, 2 * Ch, generator=g) + 0.3).to(DEV)
+    ng, nb = torch.randn(Ch, generator=g).to(DEV), torch.randn(Ch, generator=g).to(DEV)
+    cw = (torch.randn(Ch, 31, generator=g) * 0.2).to(DEV)
+    cb = torch.randn(Ch, generator=g).to(DEV)
+    va, vb = torch.randn(Ch, generator=g).to(DEV), torch.randn(Ch, generator=g).to(DEV)
+    ref = ops.csgu(h, ng, nb, cw, cb, B, T, round_out=False)
+    n_part = Ch // pw
+    gp = h[:, Ch:].double().view(B * T, n_part, pw)
+    pm = gp.mean(dim=2)
+    part = torch.stack([pm, ((gp - pm[..., None]) ** 2).sum(dim=2)], dim=-1).float().contiguous()
+    out, dots = ops.csgu_fused(h, ng, nb, cw, cb, B, T, part, n_part, pw, round_out=False,
+                               dots=(va, vb))
+    assert max_rel(out, ref) < 1e-5, max_rel(out, ref)
+    want = torch.stack([ref.double() @ va.double(), ref.double() @ vb.double()], dim=-1)
+    got = dots.double().sum(dim=1)
+    assert dots.shape == (B * T, Ch // 128, 2)
+    assert max_rel(got, want) < 1e-5, max_rel(got, want)
+    out2, none = ops.csgu_fused(h, ng, nb, cw, cb, B, T, part, n_part, pw, round_out=False)
+    assert none is None and torch.equal(out2, out)
+
+
+@pytest.mark.parametrize("B,T,lens", [(2, 64, [64, 40]), (2, 250, [250, 130]), (2, 130, [0, 130])])
+def test_relpos_attention_fused_dots(B, T, lens):
+    ops = _ops()
+    H, dk = 4, 64
+    g = torch.Generator().manual_seed(T + 1)
+    qkv = torch.randn(B * T, 3 * H * dk, generator=g).to(DEV)
+    pos = torch.randn(2 * T - 1, H * dk, generator=g).to(DEV)
+    u = (torch.randn(H * dk, generator=g) * 0.5).to(DEV)
+    v = (torch.randn(H * dk, generator=g) * 0.5).to(DEV)
+    va, vb = torch.randn(H * dk, generator=g).to(DEV), torch.randn(H * dk, generator=g).to(DEV)
+    lens_t = torch.tensor(lens, dtype=torch.int32).to(DEV)
+    ref = ops.relpos_attn(qkv, pos, u, v, lens_t, B, T, H)
+    out, dots = ops.relpos_attn(qkv, pos, u, v, lens_t, B, T, H, dots=(va, vb))
+    assert torch.equal(out, ref)
+    assert dots.shape == (B * T, 2 * H, 2)
+    want = torch.stack([ref.double() @ va.double(), ref.double() @ vb.double()], dim=-1)
+    assert max_rel(dots.double().sum(dim=1), want) < 1e-5
+
+
+def test_merge_weights2_partials_and_two_length_arrays():
+    ops = _ops()
+    B, T = 5, 300
+    g = torch.Generator().manual_seed(5)
+    np1, np2 = 8, 3
+    d1 = torch.randn(B * T, np1, 2, generator=g) * 1.5
+    d2 = torch.randn(B * T, np2, 2, generator=g) * 2.5
+    l1 = torch.tensor([300, 1, 145, 0, 299], dtype=torch.int32)
+    l2 = torch.tensor([300, 300, 20, 7, 0], dtype=torch.int32)
+    pb1, pb2, wb1, wb2 = 0.3, -0.2, 0.1, 0.7
+    w1, w2 = ops.merge_weights2(d1.to(DEV), np1, d2.to(DEV), np2, l1.to(DEV), l2.to(DEV), pb1, pb2,
+                                wb1, wb2, 256, B, T)
+    om = []
+    for d, pb, wb, lens in ((d1, pb1, wb1, l1), (d2, pb2, wb2, l2)):
+        dd = d.double().sum(dim=1).view(B, T, 2)
+        sc = (dd[..., 0] + pb) / 16.0
+        mask = torch.arange(T)[None, :] >= lens[:, None].long()
+        sc = sc.masked_fill(mask, torch.finfo(torch.float32).min)
+        s = torch.softmax(sc, dim=-1).masked_fill(mask, 0.0)
+        om.append((s * dd[..., 1]).sum(-1) + wb)
+    ref = torch.softmax(torch.stack(om, dim=-1), dim=-1)
+    assert max_rel(w1, ref[:, 0]) < 1e-5
+    assert max_rel(w2, ref[:, 1]) < 1e-5
+
+
+def test_scale_add_rows():
+    ops = _ops()
+    B, T, D = 3, 77, 256
+    g = torch.Generator().manual_seed(9)
+    a, b = torch.randn(B * T, D, generator=g).to(DEV), torch.randn(B * T, D, generator=g).to(DEV)
+    w1, w2 = torch.rand(B, generator=g).to(DEV), torch.rand(B, generator=g).to(DEV)
+    out = ops.scale_add_rows(a, b, w1, w2, T)
+    ref = w1.repeat_interleave(T)[:, None] * a + w2.repeat_interleave(T)[:, None] * b
+    assert max_rel(out, ref) < 1e-6
