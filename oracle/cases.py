@@ -64,6 +64,44 @@ CASES = {
     # conventional AV encoder: two independent stacks (configs/AVSR/conventional_...spanish.yaml)
     "av_conventional_small": dict(kind="conventional", cfg=_enc(num_blocks=2, input_layer=None),
                                   B=2, T=48, lens=[48, 31], vocab=37, Lmax=12, seed=17),
+    # AdaptiveAudioVisualFusion behind the AV encoders: learned_ave fusion of
+    # the two streams with DIFFERENT audio / video masks, CTC on the fused output
+    # (avsr_espnet_model.py:467,678)
+    "av_fusion_tailored": dict(kind="tailored",
+                               cfg=dict(BASE_TAILORED, num_blocks=3,
+                                        acoustic_use_attn=[True, False, True],
+                                        visual_use_attn=[False, True, True]),
+                               fusion=dict(merge_method="learned_ave"),
+                               B=3, T=72, lens=[72, 50, 33], lens_video=[72, 41, 33], vocab=37, Lmax=14,
+                               seed=21),
+    "av_fusion_conventional": dict(kind="conventional", cfg=_enc(num_blocks=2, input_layer=None),
+                                   fusion=dict(merge_method="learned_ave"),
+                                   B=2, T=48, lens=[48, 31], lens_video=[48, 25], vocab=37, Lmax=12,
+                                   seed=22),
+    "av_fusion_fixed": dict(kind="tailored",
+                            cfg=dict(BASE_TAILORED, num_blocks=2, acoustic_use_attn=[False, True],
+                                     visual_use_attn=[True, True]),
+                            fusion=dict(merge_method="fixed_ave", acoustic_weight=0.3),
+                            B=2, T=40, lens=[40, 22], vocab=37, Lmax=9, seed=23),
+    # audio-visual InterCTC: fused taps after blocks 1 and 2 + conditioning of both streams on the
+    # fused posteriors (tailored/encoder.py:270-318)
+    "av_tailored_interctc": dict(kind="tailored",
+                                 cfg=dict(BASE_TAILORED, num_blocks=3,
+                                          acoustic_use_attn=[False, True, True],
+                                          visual_use_attn=[True, False, True],
+                                          interctc_layer_idx=[1, 2], interctc_use_conditioning=True,
+                                          audiovisual_interctc_conditioning=True),
+                                 fusion=dict(merge_method="learned_ave"),
+                                 B=2, T=56, lens=[56, 35], lens_video=[56, 30], vocab=37, Lmax=11,
+                                 seed=24),
+    "av_tailored_interctc_sep": dict(kind="tailored",
+                                     cfg=dict(BASE_TAILORED, num_blocks=2,
+                                              acoustic_use_attn=[True, True],
+                                              visual_use_attn=[False, True],
+                                              interctc_layer_idx=[1], interctc_use_conditioning=True,
+                                              audiovisual_interctc_conditioning=False),
+                                     fusion=dict(merge_method="learned_ave"),
+                                     B=2, T=44, lens=[44, 28], vocab=37, Lmax=9, seed=25),
     # dormant InterCTC path: taps after blocks 1 and 2 + self-conditioning (encoder.py:378-401);
     # the model assigns conditioning_layer = Linear(V, d) (espnet_model.py:106-112)
     "asr_interctc_cond": dict(kind="single", input_size=512,
@@ -101,8 +139,23 @@ def make_inputs(name: str):
         for b, l in enumerate(c["lens"]):
             v[b, l:] = -1.0 * (d ** 0.5)
         out["audio"], out["video"] = a, v
+        out["lens_video"] = torch.tensor(c.get("lens_video", c["lens"]), dtype=torch.int64)
     out["ys_pad"] = synth.rand_targets(c["B"], c["Lmax"], c["vocab"], s + 1)
     return out
+
+
+FUSION_DEFAULTS = dict(input_size=256, output_size=256, hidden_units=2048,
+                       audiovisual_layer_type="upsampling_positionwise", merge_method="learned_ave",
+                       activation_type="swish", acoustic_weight=0.5, dropout_rate=0.1,
+                       acoustic_branch_drop_rate=0.0)
+
+
+def fusion_kwargs(name: str):
+    """Constructor kwargs of the case's AdaptiveAudioVisualFusion, or None."""
+    c = CASES[name]
+    if "fusion" not in c:
+        return None
+    return dict(FUSION_DEFAULTS, **c["fusion"])
 
 
 def target_lens(name: str, olens: torch.Tensor) -> torch.Tensor:

@@ -41,13 +41,19 @@ def build_reference(ref, name):
     ctc.eval()
     synth.fill_module(enc, seed=c["seed"], hot=c.get("hot", False))
     synth.fill_module(ctc, seed=c["seed"], prefix="ctc.", hot=c.get("hot", False))
-    return enc, ctc
+    fk = cases.fusion_kwargs(name)
+    if fk is not None:
+        fusion = ref.AdaptiveAudioVisualFusion(**fk)
+        fusion.eval()
+        synth.fill_module(fusion, seed=c["seed"], prefix="fusion.")
+        return enc, ctc, fusion
+    return enc, ctc, None
 
 
 def run_case(ref, name):
     c = cases.CASES[name]
     inp = cases.make_inputs(name)
-    enc, ctc = build_reference(ref, name)
+    enc, ctc, fusion = build_reference(ref, name)
     out = {}
     with torch.no_grad():
         if c["kind"] == "single":
@@ -65,15 +71,29 @@ def run_case(ref, name):
             T = c["T"]
             pos = rel_pos_emb(T, d)
             mask = make_valid_mask(inp["lens"], T)
-            ya, _, yv, _, _ = enc((inp["audio"], pos), mask, (inp["video"], pos), mask)
-            streams = {"out": ya, "out_video": yv}
+            mask_v = make_valid_mask(inp["lens_video"], T)
+            ya, _, yv, _, _ = enc((inp["audio"], pos), mask, (inp["video"], pos), mask_v, ctc=ctc,
+                                  audiovisual_fusion=fusion)
+            streams = {}
+            if isinstance(ya, tuple):
+                ya, inter = ya
+                for idx, t in inter:
+                    streams[f"inter_{idx}"] = t
+            streams.update({"out": ya, "out_video": yv})
             olens = inp["lens"]
+            if fusion is not None:
+                # avsr_espnet_model.py:467: the fused stream is what CTC sees
+                fused, olens = fusion(ya, mask, yv, mask_v)
+                streams["fused"] = fused
+                aw = fusion.acoustic_weight
+                out["acoustic_weight"] = (aw.flatten().numpy() if torch.is_tensor(aw)
+                                          else np.array([aw], dtype=np.float32))
             if c["kind"] == "conventional":
                 weights = [(getattr(l, "weight_global", None), getattr(l, "weight_local", None))
                            for l in enc.acoustic_encoder.encoders]
             else:
                 weights = []
-        y = streams["out"]
+        y = streams.get("fused", streams["out"])
         tl = cases.target_lens(name, olens)
         loss = ctc(y, olens, inp["ys_pad"], tl)
         ctc.reduce = False

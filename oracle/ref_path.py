@@ -248,17 +248,62 @@ def tailored_layer(audio, video, pos_a, pos_v, mask_a, mask_v, sd: SD, prefix: s
     return outs[0], outs[1]
 
 
-def tailored_encoder(audio, pos_a, mask_a, video, pos_v, mask_v, sd: SD, cfg: dict, prefix: str = ""):
-    """Eval-mode restatement of TailoredEncoder.forward (tailored/encoder.py:221-332), no InterCTC."""
+def adaptive_av_fusion(audio, mask_a, video, mask_v, sd: SD, prefix: str = "fusion.", *,
+                       merge_method: str = "learned_ave", acoustic_weight: float = 0.5,
+                       act: str = "swish"):
+    """Eval-mode restatement of AdaptiveAudioVisualFusion.forward
+    (src/audiovisual_fusion/adaptive_audiovisual_fusion.py:113-211): per-modality masked softmax
+    pooling over time -> 2-way softmax -> weighted average -> position-wise FFN (no residual, no
+    pre-norm) -> norm_final.  Returns (fused, olens, acoustic_weight (B,1,1) or float)."""
+    if merge_method == "learned_ave":
+        wa = _pool_weight(audio, mask_a, sd, prefix + "acoustic_pooling_proj", prefix + "acoustic_weight_proj")
+        wv = _pool_weight(video, mask_v, sd, prefix + "visual_pooling_proj", prefix + "visual_weight_proj")
+        mw = torch.softmax(torch.cat([wa, wv], dim=-1), dim=-1).unsqueeze(-1).unsqueeze(-1)
+        w_a, w_v = mw[:, 0], mw[:, 1]
+    elif merge_method == "fixed_ave":
+        w_a, w_v = acoustic_weight, 1.0 - acoustic_weight
+    else:
+        raise NotImplementedError(merge_method)
+    z = feed_forward(w_a * audio + w_v * video, sd, prefix + "audiovisual_layer", act)
+    fused = layer_norm(z, sd, prefix + "norm_final")
+    olens = torch.logical_or(mask_a, mask_v).squeeze(1).sum(1)
+    return fused, olens, w_a
+
+
+def tailored_encoder(audio, pos_a, mask_a, video, pos_v, mask_v, sd: SD, cfg: dict, prefix: str = "",
+                     fusion=None, ctc_softmax=None):
+    """Eval-mode restatement of TailoredEncoder.forward (tailored/encoder.py:221-332).  With
+    `interctc_layer_idx` in cfg, `fusion(a, mask_a, v, mask_v) -> fused` produces the tapped
+    audio-visual outputs (:270-289) and `ctc_softmax` the conditioning posteriors (:291-318).
+    Returns (audio, video) or (audio, video, taps)."""
     audio = audio + sd[prefix + "modality_encoding.weight"][0]
     video = video + sd[prefix + "modality_encoding.weight"][1]
+    idx = list(cfg.get("interctc_layer_idx", []) or [])
+    taps = []
     for l in range(cfg.get("num_blocks", 12)):
         audio, video = tailored_layer(
             audio, video, pos_a, pos_v, mask_a, mask_v, sd, f"{prefix}encoders.{l}",
             a_attn=cfg["acoustic_use_attn"][l], v_attn=cfg["visual_use_attn"][l],
             heads=cfg.get("attention_heads", 4), kernel=cfg.get("cgmlp_conv_kernel", 31),
             act=cfg.get("ffn_activation_type", "swish"))
-    return layer_norm(audio, sd, prefix + "after_norm"), layer_norm(video, sd, prefix + "after_norm")
+        if l + 1 in idx:
+            ea = layer_norm(audio, sd, prefix + "after_norm")
+            ev = layer_norm(video, sd, prefix + "after_norm")
+            eav = fusion(ea, mask_a, ev, mask_v)
+            taps.append((l + 1, eav))
+            if cfg.get("interctc_use_conditioning", False):
+                if cfg.get("audiovisual_interctc_conditioning", False):
+                    ca = cv = ctc_softmax(eav)
+                else:
+                    ca, cv = ctc_softmax(ea), ctc_softmax(ev)
+                cw, cb = sd[prefix + "conditioning_layer.weight"], sd[prefix + "conditioning_layer.bias"]
+                audio = audio + F.linear(ca, cw, cb)
+                video = video + F.linear(cv, cw, cb)
+    a_out = layer_norm(audio, sd, prefix + "after_norm")
+    v_out = layer_norm(video, sd, prefix + "after_norm")
+    if idx:
+        return a_out, v_out, taps
+    return a_out, v_out
 
 
 def conventional_encoder(audio, pos_a, mask_a, video, pos_v, mask_v, sd: SD, cfg_a: dict, cfg_v: dict,

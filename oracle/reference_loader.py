@@ -27,6 +27,7 @@ def load():
             sys.path.insert(0, p)
     from types import SimpleNamespace
 
+    from src.audiovisual_fusion.adaptive_audiovisual_fusion import AdaptiveAudioVisualFusion
     from src.ctc.ctc import CTC
     from src.ctc.interctc_residual_module import InterCTCResidualModule
     from src.encoder.audiovisual.conventional.encoder import ConventionalEncoder
@@ -34,7 +35,7 @@ def load():
     from src.encoder.audiovisual.tailored.encoder_layer import TailoredEncoderLayer
     from src.encoder.branchformer.encoder import MyBranchformerEncoder
     from src.encoder.branchformer.encoder_layer import MyBranchformerEncoderLayer
-    return SimpleNamespace(CTC=CTC, InterCTCResidualModule=InterCTCResidualModule,
+    return SimpleNamespace(CTC=CTC, AdaptiveAudioVisualFusion=AdaptiveAudioVisualFusion, InterCTCResidualModule=InterCTCResidualModule,
                            ConventionalEncoder=ConventionalEncoder,
                            TailoredEncoder=TailoredEncoder, TailoredEncoderLayer=TailoredEncoderLayer,
                            MyBranchformerEncoder=MyBranchformerEncoder,

@@ -144,9 +144,14 @@ class TailoredEncoder(AudioVisualAbsEncoder):
     def forward(self, audio_pad, audio_masks, video_pad, video_masks, prev_states=None, ctc=None,
                 audiovisual_fusion=None):
         """Same contract as the reference forward (tailored/encoder.py:221-249)."""
-        if len(self.interctc_layer_idx) > 0:
-            raise NotImplementedError("audio-visual InterCTC taps go through the fusion module, a "
-                                      "'next' row of the scope table; not built on the B200 path yet")
+        taps_on = len(self.interctc_layer_idx) > 0
+        if taps_on:
+            if audiovisual_fusion is None or not hasattr(audiovisual_fusion, "run"):
+                raise ValueError("audio-visual InterCTC taps need the B200 `audiovisual_fusion` "
+                                 "module (tailored/encoder.py:280-286)")
+            if self.interctc_use_conditioning and (ctc is None or self.conditioning_layer is None):
+                raise ValueError("InterCTC self-conditioning needs the `ctc` module and an assigned "
+                                 "`conditioning_layer` (avsr_espnet_model.py)")
         audio, a_pos = audio_pad if isinstance(audio_pad, tuple) else (audio_pad, None)
         video, v_pos = video_pad if isinstance(video_pad, tuple) else (video_pad, None)
         engine.require_inference(self, audio, video)
@@ -165,6 +170,7 @@ class TailoredEncoder(AudioVisualAbsEncoder):
         pa = self._pos_proj_all(a_pos, "acoustic")
         pv = self._pos_proj_all(v_pos, "visual")
         n = len(self.encoders)
+        inter = []
         after = (self.after_norm.weight, self.after_norm.bias) if self.normalize_before else None
         for i, layer in enumerate(self.encoders):
             layer._check_supported()
@@ -174,5 +180,26 @@ class TailoredEncoder(AudioVisualAbsEncoder):
             else:
                 next_norm = after
             x, xn = layer.run(x, xn, pa.get(i), pv.get(i), la, lv, B, T, next_norm=next_norm)
+            if taps_on and (i + 1) in self.interctc_layer_idx:
+                # intermediate outputs are normalised too (:275-278), fused (:280-286), and with
+                # conditioning the posteriors are fed back into BOTH streams (:291-318)
+                if self.normalize_before:
+                    t_out = xn if i + 1 == n else ops.layernorm(x, after[0], after[1], eps=1e-12)
+                else:
+                    t_out = x
+                fused = audiovisual_fusion.run(t_out[:M], t_out[M:], la, lv, B, T)
+                inter.append((i + 1, fused.view(B, T, d)))
+                if self.interctc_use_conditioning:
+                    cl = self.conditioning_layer
+                    if self.audiovisual_interctc_conditioning:
+                        p_av = ctc.softmax(fused.view(B, T, d)).reshape(M, -1)
+                        prob = torch.cat([p_av, p_av], 0)
+                    else:
+                        prob = ctc.softmax(t_out.view(2 * B, T, d)).reshape(2 * M, -1)
+                    x, xn = ops.vocab_residual(x, prob.contiguous(), cl.weight.contiguous(), cl.bias,
+                                               ln=next_norm)
         out = xn if self.normalize_before else x
-        return out[:M].view(B, T, d), audio_masks, out[M:].view(B, T, d), video_masks, None
+        a_out = out[:M].view(B, T, d)
+        if inter:
+            return (a_out, inter), audio_masks, out[M:].view(B, T, d), video_masks, None
+        return a_out, audio_masks, out[M:].view(B, T, d), video_masks, None

@@ -140,18 +140,18 @@ def lens_from_mask(mask: Optional[torch.Tensor], B: int, T: int, device) -> torc
 
 
 def ffn_block(x, xn, ff, *, out_main, ln0=None, lnA=None, out_lnA=None, round_lnA=False,
-              lnB=None, out_lnB=None, eps0=1e-12):
-    """x + 0.5 * W2 act(W1 xn + b1) + b2 with the trailing LayerNorms fused.  One kernel with the
-    hidden activation kept on chip when the shapes are the built ones (256 -> 2048 -> 256),
-    otherwise (or with TAVSR_FFN_FUSED=0) the two-GEMM sequence."""
+              lnB=None, out_lnB=None, eps0=1e-12, alpha=0.5):
+    """x + alpha * (W2 act(W1 xn + b1) + b2) with the trailing LayerNorms fused (x may be None: no
+    residual).  One kernel with the hidden activation kept on chip when the shapes are the built
+    ones (256 -> 2048 -> 256), otherwise (or with TAVSR_FFN_FUSED=0) the two-GEMM sequence."""
     if FFN_FUSED and tuple(ff.w_1.weight.shape) == (2048, 256):
         ops.ffn_fused(xn, ff.w_1.weight, ff.w_1.bias, ff.w_2.weight, ff.w_2.bias,
-                      act_code(ff.activation_type), residual=x, alpha=0.5, ln0=ln0, eps0=eps0,
+                      act_code(ff.activation_type), residual=x, alpha=alpha, ln0=ln0, eps0=eps0,
                       out_main=out_main, lnA=lnA, out_lnA=out_lnA, round_lnA=round_lnA,
                       lnB=lnB, out_lnB=out_lnB)
         return
     h = ops.gemm_bias_act(xn, ff.w_1.weight, ff.w_1.bias, act=act_code(ff.activation_type))
-    ops.gemm_rowln(h, ff.w_2.weight, ff.w_2.bias, residual=x, alpha=0.5, ln0=ln0, eps0=eps0,
+    ops.gemm_rowln(h, ff.w_2.weight, ff.w_2.bias, residual=x, alpha=alpha, ln0=ln0, eps0=eps0,
                    out_main=out_main, lnA=lnA, out_lnA=out_lnA, round_lnA=round_lnA,
                    lnB=lnB, out_lnB=out_lnB)
 

@@ -11,6 +11,7 @@ and `avsr_main.py`, the YAML configs and checkpoints run unchanged (INTEGRATION.
 """
 from __future__ import annotations
 
+from .audiovisual_fusion.adaptive_audiovisual_fusion import AdaptiveAudioVisualFusion
 from .ctc.ctc import CTC
 from .encoder.audiovisual.conventional.encoder import ConventionalEncoder
 from .encoder.audiovisual.tailored.encoder import TailoredEncoder
@@ -35,4 +36,6 @@ def install_avsr(namespace: dict) -> None:
     classes = _classes(namespace["encoder_choices"])
     classes["tailored"] = TailoredEncoder
     classes["conventional"] = ConventionalEncoder
+    # src/tasks/avsr.py:165-172: audiovisual_fusion_choices, key "adaptive"
+    _classes(namespace["audiovisual_fusion_choices"])["adaptive"] = AdaptiveAudioVisualFusion
     namespace["CTC"] = CTC

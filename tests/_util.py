@@ -37,7 +37,21 @@ def build_dropin(name):
     ctc.eval()
     sd = synth.fill_module(enc, seed=c["seed"], hot=c.get("hot", False))
     sd.update(synth.fill_module(ctc, seed=c["seed"], prefix="ctc.", hot=c.get("hot", False)))
+    fusion = build_fusion(name)
+    if fusion is not None:
+        sd.update(synth.fill_module(fusion, seed=c["seed"], prefix="fusion."))
+        enc.test_fusion = [fusion]  # in a list: not registered as a sub-module of the encoder
     return enc, ctc, sd
+
+
+def build_fusion(name):
+    """The case's AdaptiveAudioVisualFusion drop-in (CPU, weights not filled yet), or None."""
+    from tailored_avsr_b200.audiovisual_fusion.adaptive_audiovisual_fusion import \
+        AdaptiveAudioVisualFusion
+    fk = cases.fusion_kwargs(name)
+    if fk is None:
+        return None
+    return AdaptiveAudioVisualFusion(**fk).eval()
 
 
 def run_oracle(name, sd):
@@ -56,21 +70,40 @@ def run_oracle(name, sd):
             T = c["T"]
             pos = ref_path.rel_pos_emb(T, d)
             mask = ref_path.make_valid_mask(inp["lens"], T)
+            mask_v = ref_path.make_valid_mask(inp["lens_video"], T)
+            fk = cases.fusion_kwargs(name)
+            fuse = None
+            if fk is not None:
+                def fuse(a_, ma_, v_, mv_):
+                    return ref_path.adaptive_av_fusion(
+                        a_, ma_, v_, mv_, sd, "fusion.", merge_method=fk["merge_method"],
+                        acoustic_weight=fk["acoustic_weight"], act=fk["activation_type"])
             if c["kind"] == "tailored":
-                a, v = ref_path.tailored_encoder(inp["audio"], pos, mask, inp["video"], pos, mask, sd,
-                                                 c["cfg"])
+                r = ref_path.tailored_encoder(
+                    inp["audio"], pos, mask, inp["video"], pos, mask_v, sd, c["cfg"],
+                    fusion=(lambda *a_: fuse(*a_)[0]) if fuse else None,
+                    ctc_softmax=lambda h: ref_path.ctc_log_softmax(h, sd, "ctc.ctc_lo").exp())
+                a, v = r[0], r[1]
+                for idx, t in (r[2] if len(r) > 2 else []):
+                    res[f"inter_{idx}"] = t
                 w = []
             else:
                 a, v, w, _ = ref_path.conventional_encoder(inp["audio"], pos, mask, inp["video"], pos,
-                                                           mask, sd, c["cfg"], c["cfg"])
+                                                           mask_v, sd, c["cfg"], c["cfg"])
             res.update(out=a, out_video=v, olens=inp["lens"], weights=w)
+            res["lens_video"] = inp["lens_video"]
+            if fuse is not None:
+                fused, folens, aw = fuse(a, mask, v, mask_v)
+                res.update(fused=fused, olens=folens, lens_audio=inp["lens"], acoustic_weight=aw)
+        # the CTC input: the fused stream when a fusion module sits behind the encoder
+        res["hs"] = res.get("fused", res["out"])
         tl = cases.target_lens(name, res["olens"])
         res["tlens"] = tl
-        res["ctc_loss"] = ref_path.ctc_loss(res["out"], res["olens"], inp["ys_pad"], tl, sd, "ctc.ctc_lo")
-        res["ctc_loss_vec"] = ref_path.ctc_loss(res["out"], res["olens"], inp["ys_pad"], tl, sd,
+        res["ctc_loss"] = ref_path.ctc_loss(res["hs"], res["olens"], inp["ys_pad"], tl, sd, "ctc.ctc_lo")
+        res["ctc_loss_vec"] = ref_path.ctc_loss(res["hs"], res["olens"], inp["ys_pad"], tl, sd,
                                                 "ctc.ctc_lo", reduce=False)
         res["argmax"] = torch.argmax(torch.nn.functional.linear(
-            res["out"], sd["ctc.ctc_lo.weight"], sd["ctc.ctc_lo.bias"]), dim=2)
+            res["hs"], sd["ctc.ctc_lo.weight"], sd["ctc.ctc_lo.bias"]), dim=2)
     res["inputs"] = inp
     return res
 

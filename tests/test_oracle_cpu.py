@@ -29,22 +29,26 @@ def test_oracle_matches_reference_golden(name):
     c = cases.CASES[name]
     st, sdd = c.get("stride_t", 1), c.get("stride_d", 1)
     assert np.array_equal(res["olens"].numpy(), gold["olens"])
-    for key in [k for k in gold if k == "out" or k == "out_video" or k.startswith("inter_")]:
+    for key in [k for k in gold if k in ("out", "out_video", "fused") or k.startswith("inter_")]:
         mine = res[key][:, ::st, ::sdd].numpy()
         assert np.allclose(mine, gold[key], rtol=1e-4, atol=1e-5), key
+    if "acoustic_weight" in gold:
+        aw = res["acoustic_weight"]
+        aw = aw.flatten().numpy() if torch.is_tensor(aw) else np.array([aw], dtype=np.float32)
+        assert np.allclose(aw, gold["acoustic_weight"], rtol=1e-4, atol=1e-6)
     assert abs(float(res["ctc_loss"]) - float(gold["ctc_loss"])) <= 1e-5 * abs(float(gold["ctc_loss"]))
     assert np.allclose(res["ctc_loss_vec"].numpy(), gold["ctc_loss_vec"], rtol=1e-5, atol=1e-6)
     assert np.array_equal(res["argmax"].numpy().astype(np.int16), gold["argmax"])
     if "weight_global" in gold and res["weights"]:
         wg = np.stack([w[0].flatten().numpy() for w in res["weights"] if w is not None])
         assert np.allclose(wg, gold["weight_global"], rtol=1e-4, atol=1e-6)
-    n_params = sum(v.numel() for k, v in sd.items() if not k.startswith("ctc."))
+    n_params = sum(v.numel() for k, v in sd.items() if not k.startswith(("ctc.", "fusion.")))
     assert n_params == int(gold["n_params"])
 
 
 @pytest.mark.skipif(not reference_loader.available(), reason="/root/reference not present")
 @pytest.mark.parametrize("name", ["asr_small", "asr_tailored_small", "av_tailored_small",
-                                  "asr_interctc_cond"])
+                                  "asr_interctc_cond", "av_fusion_tailored", "av_tailored_interctc"])
 def test_oracle_matches_live_reference(name):
     """Where the reference tree exists, run it live (unmodified) and compare bit-for-bit-ish."""
     from oracle import gen_golden
@@ -53,6 +57,8 @@ def test_oracle_matches_live_reference(name):
     _, _, sd = _util.build_dropin(name)
     res = _util.run_oracle(name, sd)
     assert np.allclose(res["out"].numpy(), live["out"], rtol=1e-5, atol=1e-6)
+    if "fused" in live:
+        assert np.allclose(res["fused"].numpy(), live["fused"], rtol=1e-4, atol=1e-5)
     assert abs(float(res["ctc_loss"]) - float(live["ctc_loss"])) < 1e-4
 
 
@@ -94,7 +100,7 @@ def test_state_dict_layout_equals_reference(name):
     """Same keys and shapes as the reference modules, strict load in both directions."""
     from oracle import gen_golden
     ref = reference_loader.load()
-    theirs, their_ctc = gen_golden.build_reference(ref, name)
+    theirs, their_ctc, their_fusion = gen_golden.build_reference(ref, name)
     mine, my_ctc, _ = _util.build_dropin(name)
     a = {k: tuple(v.shape) for k, v in mine.state_dict().items()}
     b = {k: tuple(v.shape) for k, v in theirs.state_dict().items()}
@@ -102,6 +108,16 @@ def test_state_dict_layout_equals_reference(name):
     theirs.load_state_dict(mine.state_dict(), strict=True)
     mine.load_state_dict(theirs.state_dict(), strict=True)
     my_ctc.load_state_dict(their_ctc.state_dict(), strict=True)
+    if their_fusion is not None:
+        # AdaptiveAudioVisualFusion: same parameter names / shapes, strict load both ways, and the
+        # reference's abstract base is honoured (avsr.py:165-172 type-checks the registry entry)
+        my_fusion = mine.test_fusion[0]
+        fa = {k: tuple(v.shape) for k, v in my_fusion.state_dict().items()}
+        fb = {k: tuple(v.shape) for k, v in their_fusion.state_dict().items()}
+        assert fa == fb
+        their_fusion.load_state_dict(my_fusion.state_dict(), strict=True)
+        my_fusion.load_state_dict(their_fusion.state_dict(), strict=True)
+        assert my_fusion.output_size() == their_fusion.output_size()
 
 
 @pytest.mark.skipif(not reference_loader.available(), reason="/root/reference not present")

@@ -36,8 +36,20 @@ def _run_dropin(name, enc, ctc=None):
         d, T = c["cfg"]["output_size"], c["T"]
         pos = ref_path.rel_pos_emb(T, d).to(DEV)
         mask = ref_path.make_valid_mask(inp["lens"], T).to(DEV)
-        ya, _, yv, _, _ = enc((inp["audio"].to(DEV), pos), mask, (inp["video"].to(DEV), pos), mask)
-        return {"out": ya, "out_video": yv, "olens": inp["lens"]}
+        mask_v = ref_path.make_valid_mask(inp["lens_video"], T).to(DEV)
+        fusion = enc.test_fusion[0].to(DEV) if hasattr(enc, "test_fusion") else None
+        ya, _, yv, _, _ = enc((inp["audio"].to(DEV), pos), mask, (inp["video"].to(DEV), pos), mask_v,
+                              ctc=ctc, audiovisual_fusion=fusion)
+        res = {}
+        if isinstance(ya, tuple):  # audio-visual InterCTC taps (tailored/encoder.py:329-330)
+            ya, inter = ya
+            res.update({f"inter_{idx}": t for idx, t in inter})
+        res.update({"out": ya, "out_video": yv, "olens": inp["lens"]})
+        if fusion is not None:
+            # avsr_espnet_model.py:467: the fused stream and its lengths feed CTC
+            res["fused"], res["olens"] = fusion(ya, mask, yv, mask_v)
+            res["acoustic_weight"] = fusion.acoustic_weight
+        return res
 
 
 @pytest.mark.parametrize("name", list(cases.CASES))
@@ -49,9 +61,12 @@ def test_encoder_parity_vs_oracle_and_golden(name):
     torch.cuda.synchronize()
     assert torch.equal(got["olens"].cpu().long(), res["olens"].long())
     lens = res["olens"]
-    for key in [k for k in res if k in ("out", "out_video") or k.startswith("inter_")]:
+    for key in [k for k in res if k in ("out", "out_video", "fused") or k.startswith("inter_")]:
         if True:
-            mx, fro = _util.rel_errors(got[key], res[key], lens)
+            # valid frames per stream: audio / video keep their own lengths, the fused stream and
+            # its taps are valid wherever either modality is (logical_or of the masks)
+            klens = {"out": res.get("lens_audio", lens), "out_video": res.get("lens_video", lens)}.get(key, lens)
+            mx, fro = _util.rel_errors(got[key], res[key], klens)
             print(f"{name}:{key}: max-rel {mx:.3e} fro {fro:.3e}")
             tol = cases.CASES[name].get("enc_tol", ENC_TOL)
             assert mx <= tol and fro <= tol, (name, key, mx, fro)
@@ -59,11 +74,16 @@ def test_encoder_parity_vs_oracle_and_golden(name):
     gold = _util.load_golden(name)
     c = cases.CASES[name]
     st, sdd = c.get("stride_t", 1), c.get("stride_d", 1)
-    g = torch.from_numpy(gold["out"])
-    mine = got["out"].cpu()[:, ::st, ::sdd]
+    gkey = "fused" if "fused" in gold else "out"
+    g = torch.from_numpy(gold[gkey])
+    mine = got[gkey].cpu()[:, ::st, ::sdd]
     glens = (lens + st - 1) // st
     mx, fro = _util.rel_errors(mine, g, glens)
     assert mx <= 2 * tol and fro <= tol, (name, "golden", mx, fro)
+    if "acoustic_weight" in gold:
+        aw = got["acoustic_weight"]
+        aw = aw.flatten().cpu().numpy() if torch.is_tensor(aw) else np.array([aw], dtype=np.float32)
+        assert np.allclose(aw, gold["acoustic_weight"], atol=2e-3)
     # learned_ave merge weights published on the layers (study_branches.py:44-45)
     if c["kind"] == "single" and c["cfg"]["merge_method"] == "learned_ave":
         wg = torch.stack([l.weight_global.flatten().cpu() for l in enc.encoders])
@@ -77,7 +97,7 @@ def test_ctc_parity_given_identical_hs(name):
     res = _util.run_oracle(name, sd)
     gold = _util.load_golden(name)
     ctc = ctc.to(DEV)
-    hs = res["out"].to(DEV)
+    hs = res["hs"].to(DEV)
     inp = res["inputs"]
     with torch.no_grad():
         loss = ctc(hs, res["olens"].to(DEV), inp["ys_pad"].to(DEV), res["tlens"].to(DEV))
@@ -96,11 +116,11 @@ def test_ctc_parity_given_identical_hs(name):
     assert torch.equal(amax.cpu(), res["argmax"])
     assert np.array_equal(amax.cpu().numpy().astype(np.int16), gold["argmax"])
     from oracle import ref_path
-    ref_lp = ref_path.ctc_log_softmax(res["out"], sd, "ctc.ctc_lo")
+    ref_lp = ref_path.ctc_log_softmax(res["hs"], sd, "ctc.ctc_lo")
     assert (logp.cpu() - ref_lp).abs().max() < 2e-5
     assert (prob.cpu() - ref_lp.exp()).abs().max() < 2e-6
-    assert toks == ref_path.ctc_greedy(res["out"], sd, "ctc.ctc_lo")
-    assert toks_len == ref_path.ctc_greedy(res["out"], sd, "ctc.ctc_lo", lens=res["olens"])
+    assert toks == ref_path.ctc_greedy(res["hs"], sd, "ctc.ctc_lo")
+    assert toks_len == ref_path.ctc_greedy(res["hs"], sd, "ctc.ctc_lo", lens=res["olens"])
 
 
 def test_ctc_training_gradients_match_torch():
