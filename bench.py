@@ -38,24 +38,122 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = dict(name="C2", B=32, T=250, feat=512, vocab=41, Lmax=100, layers=12)
 METRIC = "branchformer_encoder_ctc_valid_frames_per_sec"
 UNIT = "frames/s"
+
+# SURVEY.md §8d workloads.  B = utterances PER GPU, T = encoder frames.  C2 is the bench line
+# (BASELINE.json configs[1]); the others are selected with --workload for the sweep / parity-size
+# measurements (tools/sweep.py), never silently.
+WORKLOADS = {
+    "C1": dict(kind="single", front="conv2d", B=8, T=249, feat=80, vocab=41, Lmax=100,
+               desc="ASR audio-only, conv2d front end on (B, 4T+5, 80) log-mel"),
+    "C2": dict(kind="single", front="linear", B=32, T=250, feat=512, vocab=41, Lmax=100,
+               desc="VSR video-only, linear front end on (B, T, 512) post-frontend features"),
+    "C3": dict(kind="conventional", B=8, T=250, vocab=37, Lmax=100,
+               desc="AVSR conventional: two 12-block stacks + AdaptiveAudioVisualFusion, "
+                    "(B, T, 256) block inputs per stream"),
+    "C4": dict(kind="tailored", B=32, T=500, vocab=37, Lmax=166, ragged=True,
+               desc="AVSR tailored: heterogeneous per-layer branches "
+                    "(configs/AVSR/tailored_transformer+ctc_spanish.yaml:79-80), padded "
+                    "variable-length batch, AdaptiveAudioVisualFusion"),
+}
+WORKLOAD = dict(WORKLOADS["C2"], name="C2", layers=12)
+
+
+def select_workload(args):
+    global WORKLOAD
+    w = dict(WORKLOADS[args.workload], name=args.workload, layers=12)
+    if args.batch:
+        w["B"] = args.batch
+    if args.T:
+        w["T"] = args.T
+        if w["name"] == "C4":
+            w["Lmax"] = max(1, args.T // 3)
+    WORKLOAD = w
+    return w
 
 
 def enc_cfg():
     from oracle import cases
-    return dict(cases.BASE_ENC, input_layer="linear")
+    w = WORKLOAD
+    if w["kind"] == "single":
+        return dict(cases.BASE_ENC, input_layer=w["front"])
+    if w["kind"] == "conventional":
+        return dict(cases.BASE_ENC, input_layer=None)
+    return dict(cases.BASE_TAILORED)
+
+
+def flops_per_frame():
+    """Algorithmic FLOP per valid frame, 12 blocks; AV workloads count both
+    streams plus the fusion FFN."""
+    w = WORKLOAD
+    T = w["T"]
+    if w["kind"] == "single":
+        return 2.0 * 12 * (3243008 + 768 * T)
+    if w["kind"] == "conventional":
+        return 2.0 * (2 * 12 * (3243008 + 768 * T) + 2 * 256 * 2048)
+    cfg = enc_cfg()
+    mac = 0
+    for l in range(12):
+        for use_attn in (cfg["acoustic_use_attn"][l], cfg["visual_use_attn"][l]):
+            mac += (2359296 + 768 * T) if use_attn else 2915328
+    return 2.0 * (mac + 2 * 256 * 2048)
+
+
+def build_modules():
+    """(encoder, fusion-or-None, ctc) drop-in modules on the CPU with the seeded synthetic weights,
+    plus the flat state dict the CPU oracle reads."""
+    from oracle import cases, synth
+    from tailored_avsr_b200.audiovisual_fusion.adaptive_audiovisual_fusion import AdaptiveAudioVisualFusion
+    from tailored_avsr_b200.ctc.ctc import CTC
+    from tailored_avsr_b200.encoder.audiovisual.conventional.encoder import ConventionalEncoder
+    from tailored_avsr_b200.encoder.audiovisual.tailored.encoder import TailoredEncoder
+    from tailored_avsr_b200.encoder.branchformer.encoder import MyBranchformerEncoder
+    w = WORKLOAD
+    cfg = enc_cfg()
+    fusion = None
+    if w["kind"] == "single":
+        enc = MyBranchformerEncoder(input_size=w["feat"], **cfg)
+    elif w["kind"] == "conventional":
+        sub = {k: v for k, v in cfg.items() if k != "output_size"}
+        enc = ConventionalEncoder(input_size=256,
+                                  acoustic_encoder_conf=dict(sub, encoder_class_type="branchformer"),
+                                  visual_encoder_conf=dict(sub, encoder_class_type="branchformer"),
+                                  output_size=256)
+    else:
+        enc = TailoredEncoder(embed_pos_enc_layer_type="rel_pos", embed_rel_pos_type="latest", **cfg)
+    ctc = CTC(odim=w["vocab"], encoder_output_size=256, dropout_rate=0.0)
+    sd = synth.fill_module(enc, seed=0)
+    sd.update(synth.fill_module(ctc, seed=0, prefix="ctc."))
+    if w["kind"] != "single":
+        fusion = AdaptiveAudioVisualFusion(**cases.FUSION_DEFAULTS)
+        sd.update(synth.fill_module(fusion, seed=0, prefix="fusion."))
+    return enc, fusion, ctc, sd
 
 
 def make_batch(rank: int):
+    """Host tensors of one step, in the positional order of the pipeline's run()."""
     from oracle import synth
     w = WORKLOAD
-    feats = synth.randn((w["B"], w["T"], w["feat"]), 3 + 100 * rank)
-    lens = torch.full((w["B"],), w["T"], dtype=torch.int64)
-    ys = synth.rand_targets(w["B"], w["Lmax"], w["vocab"], 4 + 100 * rank)
-    ylens = torch.full((w["B"],), w["Lmax"], dtype=torch.int64)
-    return feats, lens, ys, ylens
+    B, T = w["B"], w["T"]
+    ys = synth.rand_targets(B, w["Lmax"], w["vocab"], 4 + 100 * rank)
+    if w["kind"] == "single":
+        Tin = T if w["front"] == "linear" else 4 * T + 5
+        feats = synth.randn((B, Tin, w["feat"]), 3 + 100 * rank)
+        lens = torch.full((B,), Tin, dtype=torch.int64)
+        ylens = torch.full((B,), w["Lmax"], dtype=torch.int64)
+        return [feats, lens, ys, ylens], B * T
+    a = synth.randn((B, T, 256), 4 + 100 * rank) * 4.0
+    v = synth.randn((B, T, 256), 5 + 100 * rank) * 4.0
+    if w.get("ragged"):
+        lens = synth.rand_lens(B, T, 6 + 100 * rank)
+        for b in range(B):
+            v[b, int(lens[b]):] = -16.0  # the AV alignment pad (-1 before x sqrt(d))
+        ylens = (lens // 3).clamp(1, w["Lmax"])
+    else:
+        lens = torch.full((B,), T, dtype=torch.int64)
+        ylens = torch.full((B,), w["Lmax"], dtype=torch.int64)
+    return [a, v, lens, lens.clone(), ys, ylens], int(lens.sum())
 
 
 def load_peaks():
@@ -125,22 +223,32 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 def cpu_oracle_arm(steps: int, warmup: int, sample_B: int):
     """Times the CPU oracle port on `sample_B` utterances of the workload per step."""
-    from oracle import ref_path, synth
-    from tailored_avsr_b200.ctc.ctc import CTC
-    from tailored_avsr_b200.encoder.branchformer.encoder import MyBranchformerEncoder
+    from oracle import cases, ref_path
     w = WORKLOAD
     torch.set_num_threads(os.cpu_count() or 1)
     cfg = enc_cfg()
-    enc = MyBranchformerEncoder(input_size=w["feat"], **cfg)  # parameter container only (CPU)
-    ctc = CTC(odim=w["vocab"], encoder_output_size=256)
-    sd = synth.fill_module(enc, seed=0)
-    sd.update(synth.fill_module(ctc, seed=0, prefix="ctc."))
-    feats, lens, ys, ylens = make_batch(0)
-    feats, lens, ys, ylens = feats[:sample_B], lens[:sample_B], ys[:sample_B], ylens[:sample_B]
+    _, _, _, sd = build_modules()  # parameter containers only (CPU)
+    batch, _ = make_batch(0)
+    batch = [t[:sample_B] for t in batch]
 
     def step():
         with torch.no_grad():
-            out, olens, _ = ref_path.branchformer_encoder(feats, lens, sd, cfg)
+            if w["kind"] == "single":
+                feats, lens, ys, ylens = batch
+                out, olens, _ = ref_path.branchformer_encoder(feats, lens, sd, cfg)
+            else:
+                a, v, la, lv, ys, ylens = batch
+                T = a.shape[1]
+                pos = ref_path.rel_pos_emb(T, 256)
+                ma, mv = ref_path.make_valid_mask(la, T), ref_path.make_valid_mask(lv, T)
+                if w["kind"] == "tailored":
+                    ya, yv = ref_path.tailored_encoder(a, pos, ma, v, pos, mv, sd, cfg)
+                else:
+                    ya, yv, _, _ = ref_path.conventional_encoder(a, pos, ma, v, pos, mv, sd, cfg, cfg)
+                fk = cases.FUSION_DEFAULTS
+                out, olens, _ = ref_path.adaptive_av_fusion(ya, ma, yv, mv, sd, "fusion.",
+                                                            merge_method=fk["merge_method"],
+                                                            act=fk["activation_type"])
             loss = ref_path.ctc_loss(out, olens, ys, ylens, sd, "ctc.ctc_lo")
             toks = ref_path.ctc_greedy(out, sd, "ctc.ctc_lo")
         return float(loss), toks, int(olens.sum())
@@ -159,18 +267,18 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    sample_B = 8
+    sample_B = min(8, WORKLOAD["B"])
     steps = max(1, min(args.steps, 10))
     warm = max(1, min(args.warmup, 2))
     fps, ms, cores = cpu_oracle_arm(steps, warm, sample_B)
-    sample = (f"{sample_B} of the {WORKLOAD['B']} utterances of the C2 batch per step "
+    sample = (f"{sample_B} of the {WORKLOAD['B']} utterances of the {WORKLOAD['name']} batch per step "
               f"({sample_B}x{WORKLOAD['T']} frames), {steps} steps after {warm} warm-up, fp32, "
               f"torch {torch.__version__} with {cores} threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2", "batch": sample_B, "T": WORKLOAD["T"], "feat": WORKLOAD["feat"],
+        "config": {"workload": WORKLOAD["name"], "batch": sample_B, "T": WORKLOAD["T"],
                    "layers": 12, "note": "CPU oracle port of the reference path (espnet not "
                                          "installable: reference modules cannot run on the box)"},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -280,25 +388,21 @@ def run_gpu_arm(args):
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)
 
-    from oracle import synth
     from tailored_avsr_b200 import ops
-    from tailored_avsr_b200.ctc.ctc import CTC
-    from tailored_avsr_b200.encoder.branchformer.encoder import MyBranchformerEncoder
-    from tailored_avsr_b200.pipeline import EncoderCTCPipeline
+    from tailored_avsr_b200.pipeline import AVEncoderCTCPipeline, EncoderCTCPipeline
 
     w = WORKLOAD
     peaks, peak_src = load_peaks()
-    enc = MyBranchformerEncoder(input_size=w["feat"], **enc_cfg())
-    ctc = CTC(odim=w["vocab"], encoder_output_size=256, dropout_rate=0.0)
-    synth.fill_module(enc, seed=0)
-    synth.fill_module(ctc, seed=0, prefix="ctc.")
+    enc, fusion, ctc, _ = build_modules()
     enc, ctc = enc.to(dev).eval(), ctc.to(dev).eval()
-    pipe = EncoderCTCPipeline(enc, ctc, use_cuda_graph=not args.no_graph)
+    if fusion is None:
+        pipe = EncoderCTCPipeline(enc, ctc, use_cuda_graph=not args.no_graph)
+    else:
+        pipe = AVEncoderCTCPipeline(enc, fusion.to(dev).eval(), ctc, use_cuda_graph=not args.no_graph)
 
-    feats, lens, ys, ylens = make_batch(rank)
-    host = [t.pin_memory() for t in (feats, lens, ys, ylens)]
+    host, frames_per_step = make_batch(rank)
+    host = [t.pin_memory() for t in host]
     batch_dev = [t.to(dev) for t in host]
-    frames_per_step = int(lens.sum())  # linear front end: olens == ilens
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
     # ---- warm-up (also captures the CUDA graph) ----
@@ -386,20 +490,23 @@ def run_gpu_arm(args):
     if rank == 0:
         roof, shares, prof_total_ms = profile_step(pipe, batch_dev, peaks)
         roof["peak_source"] = peak_src
-        sample_B = 8
+        sample_B = min(8, w["B"])
         fps_cpu, ms_cpu, cores = cpu_oracle_arm(2, 1, sample_B) if world == 1 and not args.no_cpu else (None, None, None)
         h2d = sum(t_.numel() * t_.element_size() for t_ in host)
         d2h = 4 + w["B"] * w["T"] * 8 + w["B"] * 4
-        flops_per_frame = 2.0 * 12 * (3243008 + 768 * w["T"])
+        fpf = flops_per_frame()
         value = total_frames / (dev_ms * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
             "data": "synthetic",
-            "config": {"workload": "C2", "batch_per_gpu": w["B"], "T": w["T"], "feat": w["feat"],
-                       "layers": 12, "vocab": w["vocab"], "target_len": w["Lmax"],
-                       "step": "encoder fwd + CTC loss + greedy decode",
+            "config": {"workload": w["name"], "batch_per_gpu": w["B"], "T": w["T"],
+                       "feat": w.get("feat", 256), "layers": 12, "vocab": w["vocab"],
+                       "target_len": w["Lmax"], "what": w["desc"],
+                       "valid_frames_per_step_per_gpu": frames_per_step,
+                       "step": "encoder fwd" + ("" if w["kind"] == "single" else " + AV fusion")
+                               + " + CTC loss + greedy decode",
                        "cuda_graph": not args.no_graph,
                        "l2": "256 MB memset between steps (outside the per-step event pairs)",
                        "timing": "CUDA events per step, summed over steps, max over ranks",
@@ -417,8 +524,9 @@ def run_gpu_arm(args):
             "roofline": roof,
             "kernel_time_shares": shares,
             "eager_step_kernel_ms": prof_total_ms,
-            "model_tflops": value * flops_per_frame / 1e12,
-            "model_frac_of_bf16_sustained": value * flops_per_frame / 1e12 / peaks["bf16_tflops_sustained"],
+            "model_tflops": value * fpf / 1e12,
+            "model_tflops_per_gpu": value * fpf / 1e12 / world,
+            "model_frac_of_bf16_sustained": value * fpf / 1e12 / world / peaks["bf16_tflops_sustained"],
             "loss": loss_ref,
         }
         if fps_cpu is not None:
@@ -443,7 +551,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of graph replay")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS),
+                    help="SURVEY.md §8d workload (default: the bench line, C2)")
+    ap.add_argument("--batch", type=int, default=0, help="utterances per GPU (sweep)")
+    ap.add_argument("--T", type=int, default=0, help="encoder frames per utterance (sweep)")
     args = ap.parse_args()
+    select_workload(args)
     if args.impl == "reference":
         return run_reference_arm(args)
     if not torch.cuda.is_available():

@@ -268,6 +268,18 @@ int tavsr_scale_add_rows(const float* a, long long lda, const float* b, long lon
                          long long ldo, int M, int D, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Conv2dSubsampling front end (espnet Conv2dSubsampling inside the encoder module,
+ * encoder.py:149-155): writes the im2col operand of the second 3x3 stride-2 convolution with the
+ * first convolution + ReLU evaluated on the fly,
+ *   A[(b, t2, f2), (i*3+j)*C + c] = relu(conv1)[b, c, 2 t2 + i, 2 f2 + j],
+ * T2 = ((Tin-1)/2-1)/2, F2 = ((F-1)/2-1)/2, A is [B*T2*F2, 9*C] row-major.  The second convolution
+ * is tavsr_gemm_bias_act(A, W2r, b2, RELU) with W2r[c2, (i*3+j)*C + c1] = w2[c2, c1, i, j].
+ *   x [B, Tin, F] contiguous;  w1 [C, 9] (= conv.0.weight flattened);  b1 [C].
+ * ---------------------------------------------------------------------------------------------- */
+int tavsr_conv2d_sub_im2col(const float* x, int B, int Tin, int F, const float* w1,
+                            const float* b1, int C, float* A, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * CTC head: logits = hs . W^T + b in fp32 FMA (argmax must be bit-stable), then log-softmax /
  * softmax / argmax over V <= 64 (ctc.py:143,160-188).  Any of logits / logp / prob / amax may be NULL.
  * ---------------------------------------------------------------------------------------------- */

@@ -102,6 +102,14 @@ CASES = {
                                               audiovisual_interctc_conditioning=False),
                                      fusion=dict(merge_method="learned_ave"),
                                      B=2, T=44, lens=[44, 28], vocab=37, Lmax=9, seed=25),
+    # conventional AV encoder, layer-zipped InterCTC path with per-stream conditioning
+    # (conventional/encoder.py:152-199)
+    "av_conventional_interctc": dict(kind="conventional", cfg=_enc(num_blocks=2, input_layer=None),
+                                     wrap=dict(interctc_layer_idx=[1], interctc_use_conditioning=True,
+                                               audiovisual_interctc_conditioning=False),
+                                     fusion=dict(merge_method="learned_ave"),
+                                     B=2, T=40, lens=[40, 26], lens_video=[40, 21], vocab=37, Lmax=9,
+                                     seed=26),
     # dormant InterCTC path: taps after blocks 1 and 2 + self-conditioning (encoder.py:378-401);
     # the model assigns conditioning_layer = Linear(V, d) (espnet_model.py:106-112)
     "asr_interctc_cond": dict(kind="single", input_size=512,

@@ -32,10 +32,10 @@ def build_reference(ref, name):
         a = dict(sub, encoder_class_type="branchformer")
         v = dict(sub, encoder_class_type="branchformer")
         enc = ref.ConventionalEncoder(input_size=256, acoustic_encoder_conf=a, visual_encoder_conf=v,
-                                      output_size=cfg["output_size"])
+                                      output_size=cfg["output_size"], **c.get("wrap", {}))
     ctc = ref.CTC(odim=c["vocab"], encoder_output_size=cfg["output_size"], dropout_rate=0.0,
                   ctc_type="builtin", reduce=True)
-    if cfg.get("interctc_use_conditioning", False):
+    if cfg.get("interctc_use_conditioning", False) or c.get("wrap", {}).get("interctc_use_conditioning", False):
         enc.conditioning_layer = torch.nn.Linear(c["vocab"], cfg["output_size"])  # espnet_model.py:106-112
     enc.eval()
     ctc.eval()

@@ -320,6 +320,41 @@ def conventional_encoder(audio, pos_a, mask_a, video, pos_v, mask_v, sd: SD, cfg
     return a, v, wa, wv
 
 
+def conventional_encoder_interctc(audio, pos_a, mask_a, video, pos_v, mask_v, sd: SD, cfg: dict,
+                                  wrap: dict, fusion, ctc_softmax, prefix: str = ""):
+    """Layer-zipped ConventionalEncoder.forward with audio-visual InterCTC taps
+    (conventional/encoder.py:152-199).  `wrap` holds the wrapper's interctc_layer_idx /
+    interctc_use_conditioning / audiovisual_interctc_conditioning.  Returns (audio, video, taps)."""
+    n = cfg.get("num_blocks", 12)
+    cw = cfg.get("cgmlp_weight", 0.5)
+    cw = [cw] * n if isinstance(cw, float) else list(cw)
+    xs = [audio, video]
+    taps = []
+    for l in range(n):
+        for k, (pos, mask, tag) in enumerate(((pos_a, mask_a, "acoustic_encoder."),
+                                              (pos_v, mask_v, "visual_encoder."))):
+            xs[k], _ = branchformer_layer(
+                xs[k], pos, mask, sd, f"{prefix}{tag}encoders.{l}", heads=cfg.get("attention_heads", 4),
+                kernel=cfg.get("cgmlp_conv_kernel", 31), act=cfg.get("ffn_activation_type", "relu"),
+                merge_method=cfg.get("merge_method", "learned_ave"), cgmlp_weight=cw[l],
+                use_attn=cfg.get("use_attn", True), use_cgmlp=cfg.get("use_cgmlp", True))
+        if l + 1 in wrap["interctc_layer_idx"]:
+            ea = layer_norm(xs[0], sd, prefix + "acoustic_encoder.after_norm")
+            ev = layer_norm(xs[1], sd, prefix + "visual_encoder.after_norm")
+            eav = fusion(ea, mask_a, ev, mask_v)
+            taps.append((l + 1, eav))
+            if wrap.get("interctc_use_conditioning", False):
+                if wrap.get("audiovisual_interctc_conditioning", False):
+                    ca_ = cv_ = ctc_softmax(eav)
+                else:
+                    ca_, cv_ = ctc_softmax(ea), ctc_softmax(ev)
+                w_, b_ = sd[prefix + "conditioning_layer.weight"], sd[prefix + "conditioning_layer.bias"]
+                xs[0] = xs[0] + F.linear(ca_, w_, b_)
+                xs[1] = xs[1] + F.linear(cv_, w_, b_)
+    return (layer_norm(xs[0], sd, prefix + "acoustic_encoder.after_norm"),
+            layer_norm(xs[1], sd, prefix + "visual_encoder.after_norm"), taps)
+
+
 def _encoder_with_mask(x_pos, masks, sd, cfg, prefix):
     xs, pos = x_pos
     n = cfg.get("num_blocks", 12)

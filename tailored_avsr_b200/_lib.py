@@ -102,6 +102,8 @@ SIGNATURES = {
     "tavsr_merge_learned_ave_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_float,
                                                 c_float, c_float, c_float, c_void_p, c_void_p,
                                                 c_int, c_int, c_void_p]),
+    "tavsr_conv2d_sub_im2col": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                                        c_void_p, c_void_p]),
     "tavsr_ctc_head": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "tavsr_vocab_residual": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,

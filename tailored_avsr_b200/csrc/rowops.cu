@@ -454,6 +454,51 @@ scale_add_rows_kernel(const float* __restrict__ a, long long lda, const float* _
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Conv2dSubsampling front end (espnet Conv2dSubsampling, reached from encoder.py:149-155):
+//   conv1 = relu(Conv2d(1, C, 3, stride 2)(x)),  conv2 = relu(Conv2d(C, C, 3, stride 2)(conv1)).
+// This kernel evaluates conv1 ON THE FLY (9 FMAs per value) while writing the im2col operand of
+// conv2, so the (B, C, T1, F1) intermediate never exists:
+//   A[(b, t2, f2), (i*3 + j) * C + c] = conv1[b, c, 2 t2 + i, 2 f2 + j]
+// conv2 is then one tcgen05 GEMM  relu(A . W2r^T + b2)  with W2r[c2, (i*3+j)*C + c1] = w2[c2,c1,i,j],
+// whose (B*T2, F2*C) channels-last output feeds the 4864 -> 256 projection with permuted columns.
+// CTA = one (b, t2); thread = conv1 channel c: every store is a coalesced C*4-byte run.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+conv2d_sub_im2col_kernel(const float* __restrict__ x, int Tin, int F, const float* __restrict__ w1,
+                         const float* __restrict__ b1, int C, int T2, int F2,
+                         float* __restrict__ A) {
+  extern __shared__ float s_x[];  // 7 input rows x F
+  pdl_launch_dependents();
+  const int b = blockIdx.x / T2, t2 = blockIdx.x % T2;
+  pdl_wait();
+  const float* xb = x + (static_cast<long long>(b) * Tin + 4 * t2) * F;
+  for (int i = threadIdx.x; i < 7 * F; i += blockDim.x) s_x[i] = ld_act(xb + i);  // rows 4t2..4t2+6
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float w[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) w[k] = __ldg(w1 + c * 9 + k);
+    const float bias = __ldg(b1 + c);
+    float* arow = A + (static_cast<long long>(b) * T2 + t2) * F2 * 9 * C + c;
+    for (int f2 = 0; f2 < F2; ++f2) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const float* xp = s_x + (2 * i) * F + 4 * f2 + 2 * j;
+          float v = bias;
+#pragma unroll
+          for (int pp = 0; pp < 3; ++pp)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) v = fmaf(w[pp * 3 + q], xp[pp * F + q], v);
+          arow[(static_cast<long long>(f2) * 9 + i * 3 + j) * C] = fmaxf(v, 0.f);
+        }
+      }
+    }
+  }
+}
+
 }  // namespace tavsr
 
 using namespace tavsr;
@@ -616,6 +661,19 @@ extern "C" int tavsr_scale_add_rows(const float* a, long long lda, const float* 
   if (blocks > 8ll * num_sms()) blocks = 8ll * num_sms();
   TAVSR_CUDA_OK(launch_kernel(scale_add_rows_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0,
                               s, 0, a, lda, b, ldb, w1, w2, rows_per_seg, out, ldo, M, D / 4));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+extern "C" int tavsr_conv2d_sub_im2col(const float* x, int B, int Tin, int F, const float* w1,
+                                       const float* b1, int C, float* A, void* stream) {
+  TAVSR_REQUIRE(B > 0 && Tin >= 7 && F >= 7 && C > 0 && x && w1 && b1 && A,
+                "conv2d_sub: bad arguments (B=%d Tin=%d F=%d C=%d)", B, Tin, F, C);
+  const int T2 = ((Tin - 1) / 2 - 1) / 2, F2 = ((F - 1) / 2 - 1) / 2;
+  TAVSR_REQUIRE(T2 >= 1 && F2 >= 1 && 7 * F * 4 <= 48 * 1024, "conv2d_sub: unsupported shape");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  TAVSR_CUDA_OK(launch_kernel(conv2d_sub_im2col_kernel, dim3(B * T2), dim3(256),
+                              static_cast<size_t>(7 * F * 4), s, 0, x, Tin, F, w1, b1, C, T2, F2, A));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }

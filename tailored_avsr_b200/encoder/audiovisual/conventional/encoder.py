@@ -87,12 +87,12 @@ class ConventionalEncoder(AudioVisualAbsEncoder):
     def forward(self, audio_pad, audio_masks, video_pad, video_masks, prev_states=None, ctc=None,
                 audiovisual_fusion=None):
         """Same contract as the reference forward (conventional/encoder.py:116-144)."""
-        if len(self.interctc_layer_idx) > 0:
-            raise NotImplementedError("audio-visual InterCTC taps go through the fusion module, a "
-                                      "'next' row of the scope table; not built on the B200 path yet")
         a0 = audio_pad[0] if isinstance(audio_pad, tuple) else audio_pad
         v0 = video_pad[0] if isinstance(video_pad, tuple) else video_pad
         engine.require_inference(self, a0, v0)
+        if len(self.interctc_layer_idx) > 0:
+            return self._forward_interctc(audio_pad, audio_masks, video_pad, video_masks, ctc,
+                                          audiovisual_fusion)
         cur = torch.cuda.current_stream(a0.device)
         if self._side_stream is None or self._side_stream.device != a0.device:
             self._side_stream = torch.cuda.Stream(device=a0.device)
@@ -104,3 +104,59 @@ class ConventionalEncoder(AudioVisualAbsEncoder):
             video_out.record_stream(cur)
         cur.wait_stream(side)
         return audio_out, audio_masks, video_out, video_masks, None
+
+    def _forward_interctc(self, audio_pad, audio_masks, video_pad, video_masks, ctc, fusion):
+        """Layer-zipped form with audio-visual InterCTC taps (conventional/encoder.py:152-199): after
+        the tapped blocks both streams are normalised, fused, and (with conditioning) get the CTC
+        posteriors added back through `conditioning_layer`."""
+        from .... import ops
+        if fusion is None or not hasattr(fusion, "run"):
+            raise ValueError("audio-visual InterCTC taps need the B200 `audiovisual_fusion` module "
+                             "(conventional/encoder.py:171-177)")
+        if self.interctc_use_conditioning and (ctc is None or self.conditioning_layer is None):
+            raise ValueError("InterCTC self-conditioning needs the `ctc` module and an assigned "
+                             "`conditioning_layer`")
+        st = []
+        for enc, x_pad, masks in ((self.acoustic_encoder, audio_pad, audio_masks),
+                                  (self.visual_encoder, video_pad, video_masks)):
+            xs, pos_emb = x_pad if isinstance(x_pad, tuple) else (x_pad, None)
+            if pos_emb is None:
+                raise NotImplementedError("the conventional AV encoder expects (x, pos_emb) inputs")
+            first = enc.encoders[0]
+            x, xn, pos_emb, masks, B, T = enc._embed(
+                (xs, pos_emb), masks, (first.norm_ff_macaron.weight, first.norm_ff_macaron.bias))
+            st.append(dict(enc=enc, x=x, xn=xn, pos=enc._pos_proj_all(pos_emb),
+                           lens=engine.lens_from_mask(masks, B, T, x.device)))
+        d = self.output_size()
+        n = len(self.acoustic_encoder.encoders)
+        inter = []
+        for i in range(n):
+            for s_ in st:
+                enc = s_["enc"]
+                layer = enc.encoders[i]
+                layer._check_supported()
+                if i + 1 < n:
+                    nxt = enc.encoders[i + 1]
+                    s_["next_norm"] = (nxt.norm_ff_macaron.weight, nxt.norm_ff_macaron.bias)
+                else:
+                    s_["next_norm"] = ((enc.after_norm.weight, enc.after_norm.bias)
+                                       if enc.normalize_before else None)
+                s_["x"], s_["xn"] = layer.run(s_["x"], s_["xn"], s_["pos"].get(i), s_["lens"], B, T,
+                                              next_norm=s_["next_norm"])
+            if (i + 1) in self.interctc_layer_idx:
+                taps = []
+                for s_ in st:
+                    enc = s_["enc"]
+                    taps.append(ops.layernorm(s_["x"], enc.after_norm.weight, enc.after_norm.bias, eps=1e-12)
+                                if enc.normalize_before else s_["x"])
+                fused = fusion.run(taps[0], taps[1], st[0]["lens"], st[1]["lens"], B, T)
+                inter.append((i + 1, fused.view(B, T, d)))
+                if self.interctc_use_conditioning:
+                    cl = self.conditioning_layer
+                    for s_, tap in zip(st, taps):
+                        src = fused if self.audiovisual_interctc_conditioning else tap
+                        prob = ctc.softmax(src.view(B, T, d)).reshape(B * T, -1).contiguous()
+                        s_["x"], s_["xn"] = ops.vocab_residual(s_["x"], prob, cl.weight.contiguous(),
+                                                               cl.bias, ln=s_["next_norm"])
+        outs = [(s_["xn"] if s_["enc"].normalize_before else s_["x"]).view(B, T, d) for s_ in st]
+        return (outs[0], inter), audio_masks, outs[1], video_masks, None

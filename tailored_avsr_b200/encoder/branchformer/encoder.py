@@ -173,18 +173,33 @@ class MyBranchformerEncoder(AbsEncoder):
                     f"has {xs_pad.size(1)} frames and is too short for subsampling "
                     + f"(it needs more than {limit_size} frames), return empty results",
                     xs_pad.size(1), limit_size)
-            # the two stride-2 3x3 convolutions stay on cuDNN (pre-encoder
-            # "next" row); the 4864->256 projection, the sqrt(d) scale and the first LayerNorm are
-            # one row-complete tcgen05 GEMM.
+            # conv1 + ReLU are evaluated inside the im2col writer, conv2 + ReLU is one tcgen05 GEMM
+            # over K = 9 C, and the 4864 -> 256 projection, the sqrt(d) scale and the first
+            # LayerNorm are one row-complete GEMM on the channels-last result (weights permuted
+            # once): no cuDNN / ATen arithmetic on the path.  TAVSR_CUDNN_EMBED=1 keeps the former
+            # cuDNN convolutions as a cross-check.
             conv = self.embed.conv
-            h = F.relu(F.conv2d(xs_pad.unsqueeze(1), conv[0].weight, conv[0].bias, stride=2))
-            h = F.relu(F.conv2d(h, conv[2].weight, conv[2].bias, stride=2))
-            B, C, T, Fd = h.shape
-            h2 = h.transpose(1, 2).contiguous().view(B * T, C * Fd)
             lin = self.embed.out[0]
-            x = torch.empty((B * T, d), device=h.device, dtype=torch.float32)
+            B, Tin, Fin = xs_pad.shape
+            C = conv[0].weight.shape[0]
+            T, Fd = ((Tin - 1) // 2 - 1) // 2, ((Fin - 1) // 2 - 1) // 2
+            x = torch.empty((B * T, d), device=xs_pad.device, dtype=torch.float32)
             xn = torch.empty_like(x)
-            ops.gemm_rowln(h2, lin.weight, lin.bias, alpha=math.sqrt(d), out_main=x,
+            if engine.CUDNN_EMBED:
+                h = F.relu(F.conv2d(xs_pad.unsqueeze(1), conv[0].weight, conv[0].bias, stride=2))
+                h = F.relu(F.conv2d(h, conv[2].weight, conv[2].bias, stride=2))
+                h2 = h.transpose(1, 2).contiguous().view(B * T, C * Fd)
+                w_lin = lin.weight
+            else:
+                pk = self._packed.get(
+                    "conv2d", [conv[0].weight, conv[2].weight, lin.weight],
+                    lambda: (conv[0].weight.reshape(C, 9).contiguous(),
+                             conv[2].weight.permute(0, 2, 3, 1).reshape(C, 9 * C).contiguous(),
+                             lin.weight.view(-1, C, Fd).permute(0, 2, 1).reshape(-1, Fd * C).contiguous()))
+                a_mat = ops.conv2d_sub_im2col(xs_pad.contiguous().float(), pk[0], conv[0].bias)
+                h2 = ops.gemm_bias_act(a_mat, pk[1], conv[2].bias, act=ops.ACT_RELU).view(B * T, Fd * C)
+                w_lin = pk[2]
+            ops.gemm_rowln(h2, w_lin, lin.bias, alpha=math.sqrt(d), out_main=x,
                            lnA=first_norm, out_lnA=xn)
             masks = masks[:, :, :-2:2][:, :, :-2:2]
             pos_emb = self.embed.out[1].pos_emb(T, x.device)

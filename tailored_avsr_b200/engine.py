@@ -82,6 +82,9 @@ class branch_fork:
         return False
 
 
+# Conv2dSubsampling on cuDNN instead of the im2col + tcgen05 path (cross-check knob)
+CUDNN_EMBED = os.environ.get("TAVSR_CUDNN_EMBED", "0") != "0"
+
 _ACT = {"swish": ops.ACT_SWISH, "relu": ops.ACT_RELU, "gelu": ops.ACT_GELU}
 
 

@@ -17,7 +17,7 @@ from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SWISH, DT_TF32, FfnArgs, Row
 
 __all__ = [
     "ACT_NONE", "ACT_SWISH", "ACT_GELU", "ACT_RELU",
-    "gemm_bias_act", "gemm_bias_act_stats", "csgu_fused", "merge_weights2", "scale_add_rows", "gemm_rowln", "ffn_fused", "layernorm", "relpos_attn", "csgu", "merge_weights",
+    "gemm_bias_act", "conv2d_sub_im2col", "gemm_bias_act_stats", "csgu_fused", "merge_weights2", "scale_add_rows", "gemm_rowln", "ffn_fused", "layernorm", "relpos_attn", "csgu", "merge_weights",
     "ctc_head", "vocab_residual", "row_dots", "ctc_loss", "ctc_greedy", "ctc_prefix_score", "launch_count",
 ]
 
@@ -381,6 +381,21 @@ def row_dots(a1: torch.Tensor, va1: torch.Tensor, vb1: torch.Tensor,
         _p(a2), a2.stride(0) if a2 is not None else 0, a2.shape[1] if a2 is not None else 0,
         _p(va2), _p(vb2), _p(o2), M, _stream()), "tavsr_row_dots")
     return o1, o2
+
+
+@_profiled
+def conv2d_sub_im2col(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor) -> torch.Tensor:
+    """im2col operand of the second Conv2dSubsampling convolution with conv1 + ReLU evaluated on
+    the fly: x (B, Tin, F) -> A (B*T2*F2, 9*C) (tavsr_conv2d_sub_im2col)."""
+    if not x.is_cuda or x.dtype != torch.float32 or not x.is_contiguous():
+        raise _lib.TavsrError("conv2d_sub_im2col: x must be a contiguous fp32 CUDA tensor")
+    B, Tin, F = x.shape
+    C = w1.shape[0]
+    T2, F2 = ((Tin - 1) // 2 - 1) // 2, ((F - 1) // 2 - 1) // 2
+    A = torch.empty((B * T2 * F2, 9 * C), device=x.device, dtype=torch.float32)
+    check(_lib.load().tavsr_conv2d_sub_im2col(x.data_ptr(), B, Tin, F, w1.data_ptr(), b1.data_ptr(),
+                                              C, A.data_ptr(), _stream()), "tavsr_conv2d_sub_im2col")
+    return A
 
 
 @_profiled

@@ -45,44 +45,38 @@ class EncoderCTCPipeline:
             res["tokens"], res["ntok"] = self.ctc.greedy(out)
         return res
 
-    def _capture(self, key, feats, feats_lens, ys_pad, ys_lens):
-        static_in = {
-            "feats": torch.empty_like(feats), "feats_lens": torch.empty_like(feats_lens),
-            "ys_pad": torch.empty_like(ys_pad), "ys_lens": torch.empty_like(ys_lens)}
-        for k, v in (("feats", feats), ("feats_lens", feats_lens), ("ys_pad", ys_pad),
-                     ("ys_lens", ys_lens)):
-            static_in[k].copy_(v)
+    def _capture(self, key, *tensors):
+        static_in = [torch.empty_like(t) for t in tensors]
+        for s_, t in zip(static_in, tensors):
+            s_.copy_(t)
         # warm-up on a side stream: fills the weight-pack caches, the TMA descriptor cache and
         # the function attributes before capture
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side), torch.no_grad():
             for _ in range(2):
-                self._step(**static_in)
+                self._step(*static_in)
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
         with torch.no_grad(), torch.cuda.graph(graph):
-            static_out = self._step(**static_in)
+            static_out = self._step(*static_in)
         entry = {"graph": graph, "in": static_in, "out": static_out}
         self._graphs[key] = entry
         return entry
 
     @torch.no_grad()
-    def run_device(self, feats, feats_lens, ys_pad, ys_lens) -> dict:
+    def run_device(self, *tensors) -> dict:
         """Device tensors in, device tensors out (results alias static buffers when graphs are on:
         consume or clone them before the next call)."""
         if not self.use_cuda_graph:
-            return self._step(feats, feats_lens, ys_pad, ys_lens)
-        key = (tuple(feats.shape), feats.dtype, tuple(ys_pad.shape))
+            return self._step(*tensors)
+        key = tuple((tuple(t.shape), t.dtype) for t in tensors)
         entry = self._graphs.get(key)
         if entry is None:
-            entry = self._capture(key, feats, feats_lens, ys_pad, ys_lens)
-        si = entry["in"]
-        si["feats"].copy_(feats, non_blocking=True)
-        si["feats_lens"].copy_(feats_lens, non_blocking=True)
-        si["ys_pad"].copy_(ys_pad, non_blocking=True)
-        si["ys_lens"].copy_(ys_lens, non_blocking=True)
+            entry = self._capture(key, *tensors)
+        for s_, t in zip(entry["in"], tensors):
+            s_.copy_(t, non_blocking=True)
         entry["graph"].replay()
         return entry["out"]
 
@@ -148,18 +142,47 @@ class EncoderCTCPipeline:
             yield out
 
     @torch.no_grad()
-    def run(self, feats, feats_lens, ys_pad, ys_lens) -> dict:
-        """Host or device tensors in; returns host-side loss (float tensor), token lists lengths
-        and the device encoder output.  Host inputs should be pinned for an asynchronous copy."""
+    def run(self, *tensors) -> dict:
+        """Host or device tensors in (feats, feats_lens, ys_pad, ys_lens for the single-stream
+        pipeline); returns host-side loss (float tensor), token lists lengths and the device
+        encoder output.  Host inputs should be pinned for an asynchronous copy."""
         dev = self.device
-        f = feats.to(dev, non_blocking=True)
-        fl = feats_lens.to(dev, non_blocking=True)
-        yp = ys_pad.to(dev, non_blocking=True)
-        yl = ys_lens.to(dev, non_blocking=True)
-        res = self.run_device(f, fl, yp, yl)
+        res = self.run_device(*[t.to(dev, non_blocking=True) for t in tensors])
         out = {"encoder_out": res["encoder_out"], "olens": res["olens"],
                "loss": res["loss"].to("cpu", non_blocking=False)}
         if self.greedy:
             out["tokens"] = res["tokens"].to("cpu")
             out["ntok"] = res["ntok"].to("cpu")
         return out
+
+
+class AVEncoderCTCPipeline(EncoderCTCPipeline):
+    """Audio-visual form: `run(audio, video, lens_audio, lens_video, ys_pad, ys_lens)` with the two
+    time-aligned (B, T, d) streams as they enter the encoder blocks (post-embed, x sqrt(d) applied:
+    src/models/avsr_espnet_model.py:427-448).  One step = TailoredEncoder / ConventionalEncoder ->
+    AdaptiveAudioVisualFusion -> CTC loss + greedy decode (avsr_espnet_model.py:451-467, 678-683).
+    The key-padding masks and the relative positional table are built on the device."""
+
+    def __init__(self, encoder, fusion, ctc, use_cuda_graph: bool = True, greedy: bool = True):
+        super().__init__(encoder, ctc, use_cuda_graph=use_cuda_graph, greedy=greedy)
+        from .espnet_compat import RelPositionalEncoding
+        self.fusion = fusion.eval()
+        self._pos = RelPositionalEncoding(encoder.output_size(), 0.0)
+
+    def _step(self, audio, video, lens_a, lens_v, ys_pad, ys_lens):
+        B, T, _ = audio.shape
+        dev = audio.device
+        ar = torch.arange(T, device=dev)[None, :]
+        mask_a = (ar < lens_a[:, None]).unsqueeze(1)
+        mask_v = (ar < lens_v[:, None]).unsqueeze(1)
+        pos = self._pos.pos_emb(T, dev)
+        ya, _, yv, _, _ = self.encoder((audio, pos), mask_a, (video, pos), mask_v, ctc=self.ctc,
+                                       audiovisual_fusion=self.fusion)
+        if isinstance(ya, tuple):
+            ya = ya[0]
+        fused, olens = self.fusion(ya, mask_a, yv, mask_v)
+        if self.greedy:
+            loss, tokens, ntok = self.ctc.loss_and_greedy(fused, olens, ys_pad, ys_lens)
+            return {"encoder_out": fused, "olens": olens, "loss": loss, "tokens": tokens, "ntok": ntok}
+        return {"encoder_out": fused, "olens": olens,
+                "loss": self.ctc(fused, olens, ys_pad, ys_lens)}

@@ -28,10 +28,10 @@ def build_dropin(name):
         enc = ConventionalEncoder(input_size=256,
                                   acoustic_encoder_conf=dict(sub, encoder_class_type="branchformer"),
                                   visual_encoder_conf=dict(sub, encoder_class_type="branchformer"),
-                                  output_size=cfg["output_size"])
+                                  output_size=cfg["output_size"], **c.get("wrap", {}))
     ctc = CTC(odim=c["vocab"], encoder_output_size=cfg["output_size"], dropout_rate=0.0,
               ctc_type="builtin", reduce=True)
-    if cfg.get("interctc_use_conditioning", False):
+    if cfg.get("interctc_use_conditioning", False) or c.get("wrap", {}).get("interctc_use_conditioning", False):
         enc.conditioning_layer = torch.nn.Linear(c["vocab"], cfg["output_size"])
     enc.eval()
     ctc.eval()
@@ -85,6 +85,14 @@ def run_oracle(name, sd):
                     ctc_softmax=lambda h: ref_path.ctc_log_softmax(h, sd, "ctc.ctc_lo").exp())
                 a, v = r[0], r[1]
                 for idx, t in (r[2] if len(r) > 2 else []):
+                    res[f"inter_{idx}"] = t
+                w = []
+            elif c.get("wrap", {}).get("interctc_layer_idx"):
+                a, v, taps = ref_path.conventional_encoder_interctc(
+                    inp["audio"], pos, mask, inp["video"], pos, mask_v, sd, c["cfg"], c["wrap"],
+                    fusion=lambda *a_: fuse(*a_)[0],
+                    ctc_softmax=lambda h: ref_path.ctc_log_softmax(h, sd, "ctc.ctc_lo").exp())
+                for idx, t in taps:
                     res[f"inter_{idx}"] = t
                 w = []
             else:

@@ -540,3 +540,30 @@ def test_scale_add_rows():
     out = ops.scale_add_rows(a, b, w1, w2, T)
     ref = w1.repeat_interleave(T)[:, None] * a + w2.repeat_interleave(T)[:, None] * b
     assert max_rel(out, ref) < 1e-6
+
+
+@pytest.mark.parametrize("B,Tin,Fin", [(2, 203, 80), (1, 7, 80), (3, 64, 40)])
+def test_conv2d_subsampling_im2col_plus_gemm(B, Tin, Fin):
+    """conv1 (on the fly) + im2col + tcgen05 GEMM == espnet Conv2dSubsampling's two stride-2
+    3x3 convolutions with ReLU, in channels-last layout."""
+    ops = _ops()
+    C = 256
+    g = torch.Generator().manual_seed(Tin)
+    x = torch.randn(B, Tin, Fin, generator=g)
+    w1 = torch.randn(C, 1, 3, 3, generator=g) / 3
+    b1 = torch.randn(C, generator=g) * 0.1
+    w2 = torch.randn(C, C, 3, 3, generator=g) / math.sqrt(9 * C)
+    b2 = torch.randn(C, generator=g) * 0.1
+    a = ops.conv2d_sub_im2col(x.to(DEV), w1.reshape(C, 9).contiguous().to(DEV), b1.to(DEV))
+    h1 = F.relu(F.conv2d(x.double().unsqueeze(1), w1.double(), b1.double(), stride=2))
+    T2, F2 = ((Tin - 1) // 2 - 1) // 2, ((Fin - 1) // 2 - 1) // 2
+    # im2col of the fp64 conv1 output in the (i, j, c) column order
+    cols = F.unfold(h1, kernel_size=3, stride=2)                      # (B, C*9, T2*F2), (c, i, j)
+    cols = cols.view(B, C, 9, T2 * F2).permute(0, 3, 2, 1).reshape(B * T2 * F2, 9 * C)
+    assert a.shape == cols.shape
+    assert max_rel(a, cols) < 1e-5
+    w2r = w2.permute(0, 2, 3, 1).reshape(C, 9 * C).contiguous()
+    out = ops.gemm_bias_act(a, w2r.to(DEV), b2.to(DEV), act=ops.ACT_RELU)
+    ref = F.relu(F.conv2d(h1, w2.double(), b2.double(), stride=2))    # (B, C, T2, F2)
+    ref = ref.permute(0, 2, 3, 1).reshape(B * T2 * F2, C)
+    assert rel_fro(out, ref) < 2e-3, rel_fro(out, ref)

@@ -1,5 +1,4 @@
-p() { python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$1', round(d['value']), round(d['ms_per_step'],4), round(d['e2e']['value']))"; }
-python -m pytest tests/test_kernels_gpu.py -x -q 2>&1 | tail -2
-(cd _ab_old && python bench.py --no-cpu 2>&1 | tail -1 | p old)
-python bench.py --no-cpu 2>&1 | tail -1 | p new_default
-TAVSR_BRANCH_FORK=0 python bench.py --no-cpu 2>&1 | tail -1 | p new_nofork
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+p() { python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$1', round(d['value']), round(d['ms_per_step'],4), round(d['e2e']['value']), d['gpu_launches_per_step'])"; }
+python bench.py --no-cpu --workload C1 2>&1 | tail -1 | p C1_im2col
+TAVSR_CUDNN_EMBED=1 python bench.py --no-cpu --workload C1 2>&1 | tail -1 | p C1_cudnn

@@ -1,0 +1,70 @@
+"""Throughput sweep (inference part): encoder + CTC valid frames/s over
+T x batch for one workload, device-resident CUDA-graph replay, CUDA-event timed with an L2 flush
+between steps (same timing rules as bench.py, whose builders it reuses).  One JSON line per point.
+
+  python tools/sweep.py --workload C2 --T 250,500,1000,1500 --batch 1,8,32,128,256 [--steps 10]
+"""
+import argparse
+import json
+import os
+import sys
+import types
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="C2", choices=sorted(bench.WORKLOADS))
+    ap.add_argument("--T", default="250,500,1000,1500")
+    ap.add_argument("--batch", default="1,8,32,128,256")
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--max-rows", type=int, default=400000, help="skip points with B*T above this")
+    a = ap.parse_args()
+    from tailored_avsr_b200.pipeline import AVEncoderCTCPipeline, EncoderCTCPipeline
+    dev = torch.device("cuda", 0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    mods = None
+    for T in [int(x) for x in a.T.split(",")]:
+        for B in [int(x) for x in a.batch.split(",")]:
+            if B * T > a.max_rows:
+                continue
+            bench.select_workload(types.SimpleNamespace(workload=a.workload, batch=B, T=T))
+            if mods is None:  # weights do not depend on (B, T)
+                enc, fusion, ctc, _ = bench.build_modules()
+                mods = (enc.to(dev).eval(), fusion.to(dev).eval() if fusion is not None else None,
+                        ctc.to(dev).eval())
+            enc, fusion, ctc = mods
+            pipe = (EncoderCTCPipeline(enc, ctc) if fusion is None
+                    else AVEncoderCTCPipeline(enc, fusion, ctc))
+            host, frames = bench.make_batch(0)
+            batch_dev = [t.to(dev) for t in host]
+            for _ in range(a.warmup):
+                res = pipe.run_device(*batch_dev)
+            torch.cuda.synchronize()
+            evs = []
+            for _ in range(a.steps):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                pipe.replay_static()
+                e1.record()
+                evs.append((e0, e1))
+            torch.cuda.synchronize()
+            ms = sum(x.elapsed_time(y) for x, y in evs) / a.steps
+            fps = frames / (ms * 1e-3)
+            print(json.dumps({"workload": a.workload, "B": B, "T": T, "valid_frames": frames,
+                              "ms_per_step": round(ms, 4), "frames_per_s": round(fps),
+                              "model_tflops": round(fps * bench.flops_per_frame() / 1e12, 1),
+                              "loss": float(res["loss"]), "dtype": "tf32", "n_gpus": 1}), flush=True)
+            del pipe, batch_dev, res
+            torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
