@@ -332,6 +332,136 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
   }
   cluster_sync_all();  // both CTAs' MMAs are done -> both s_x regions may be overwritten
   FFN_STAMP(3);
+  if (p.ep.rowwarp_epilogue) {
+    // ---- warp-per-row epilogue.  The thread-per-row form below keeps 64 threads per SM busy on a
+    // serial chain (1 KB-strided residual loads, up to five TMEM passes); here the partial
+    // accumulators leave TMEM once - rows this CTA finishes into its own smem, the other 64 rows
+    // into the peer's - and then all eight warps finish rows with coalesced global accesses and
+    // shuffle reductions (lane = 8 consecutive columns).
+    uint8_t* s_own = s_x + 64 * 1024;  // [64 rows][1 KB], 16-byte chunks XOR-swizzled by row & 7
+    if (warp >= 4) {
+      const int q = warp & 3;
+      const uint32_t td2 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kColD2;
+      const int row_local = (q & 1) * 32 + static_cast<int>(lane);
+      const bool mine = static_cast<uint32_t>(q >> 1) == rank;
+      const uint32_t base = mine ? smem_u32(s_own) + row_local * 1024
+                                 : mapa_cluster(smem_u32(s_x) + row_local * 1024, rank ^ 1u);
+      for (int c = 0; c < 8; ++c) {
+        uint32_t r[32];
+        tmem_ld32(td2 + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t dst = base + (((c * 8 + i) ^ (row_local & 7)) << 4);
+          const float4 f = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                       __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+          if (mine)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(f.x), "f"(f.y),
+                         "f"(f.z), "f"(f.w) : "memory");
+          else
+            st_cluster_v4(dst, f);
+        }
+      }
+    }
+    cluster_sync_all();  // release/acquire: own rows in s_own, the peer's partials of them in s_x
+    FFN_STAMP(4);
+    const GemmParams& e = p.ep;
+    const bool has_ln0 = e.ln0_g != nullptr, has_lnA = e.lnA_g != nullptr, has_lnB = e.lnB_g != nullptr;
+    const int col = 8 * static_cast<int>(lane);
+    auto ld8 = [&](const float* src, float (&dst)[8]) {
+      const float4 a = *reinterpret_cast<const float4*>(src);
+      const float4 b = *reinterpret_cast<const float4*>(src + 4);
+      dst[0] = a.x; dst[1] = a.y; dst[2] = a.z; dst[3] = a.w;
+      dst[4] = b.x; dst[5] = b.y; dst[6] = b.z; dst[7] = b.w;
+    };
+    float bias[8];
+    ld8(s_param + col, bias);
+    for (int r = warp; r < 64; r += kThreadsV1 / 32) {
+      const int m = m0 + static_cast<int>(rank) * 64 + r;
+      if (m >= e.M) break;  // warp-uniform; rows only grow
+      float v[8];
+      {
+        const uint32_t sw0 = static_cast<uint32_t>(((2 * lane) ^ (r & 7)) << 4);
+        const uint32_t sw1 = static_cast<uint32_t>(((2 * lane + 1) ^ (r & 7)) << 4);
+        const float4 o0 = *reinterpret_cast<const float4*>(s_own + r * 1024 + sw0);
+        const float4 o1 = *reinterpret_cast<const float4*>(s_own + r * 1024 + sw1);
+        const float4 q0 = *reinterpret_cast<const float4*>(s_x + r * 1024 + sw0);
+        const float4 q1 = *reinterpret_cast<const float4*>(s_x + r * 1024 + sw1);
+        float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+        if (e.residual != nullptr) {
+          const float4* rp = reinterpret_cast<const float4*>(e.residual + static_cast<long long>(m) * e.ldr + col);
+          r0 = ld_act4(rp);
+          r1 = ld_act4(rp + 1);
+        }
+        v[0] = r0.x + e.alpha * (o0.x + q0.x + bias[0]);
+        v[1] = r0.y + e.alpha * (o0.y + q0.y + bias[1]);
+        v[2] = r0.z + e.alpha * (o0.z + q0.z + bias[2]);
+        v[3] = r0.w + e.alpha * (o0.w + q0.w + bias[3]);
+        v[4] = r1.x + e.alpha * (o1.x + q1.x + bias[4]);
+        v[5] = r1.y + e.alpha * (o1.y + q1.y + bias[5]);
+        v[6] = r1.z + e.alpha * (o1.z + q1.z + bias[6]);
+        v[7] = r1.w + e.alpha * (o1.w + q1.w + bias[7]);
+      }
+      auto stats = [&](float eps, float& mean, float& rstd) {  // two-pass, like torch's LayerNorm
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += v[k];
+        mean = warp_sum(s) * (1.0f / 256.0f);
+        float ss = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float dk = v[k] - mean;
+          ss = fmaf(dk, dk, ss);
+        }
+        rstd = rsqrtf(warp_sum(ss) * (1.0f / 256.0f) + eps);
+      };
+      auto emit = [&](float* out, long long ld, const float* g, const float* b, float mean, float rstd,
+                      bool affine, bool rnd) {
+        float y[8];
+        if (affine) {
+          float gg[8], bb[8];
+          ld8(g + col, gg);
+          ld8(b + col, bb);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) y[k] = (v[k] - mean) * rstd * gg[k] + bb[k];
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) y[k] = v[k];
+        }
+        if (rnd) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) y[k] = round_tf32(y[k]);
+        }
+        float4* op = reinterpret_cast<float4*>(out + static_cast<long long>(m) * ld + col);
+        op[0] = make_float4(y[0], y[1], y[2], y[3]);
+        op[1] = make_float4(y[4], y[5], y[6], y[7]);
+      };
+      float mean = 0.f, rstd = 1.f;
+      if (has_ln0) {  // v1 = LN0(v0) replaces v0 (norm_final)
+        stats(e.eps0, mean, rstd);
+        float gg[8], bb[8];
+        ld8(s_param + 256 + col, gg);
+        ld8(s_param + 512 + col, bb);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = (v[k] - mean) * rstd * gg[k] + bb[k];
+      }
+      if (e.has_main) emit(e.out_main, e.ld_main, nullptr, nullptr, 0.f, 1.f, false, e.round_c != 0);
+      if (has_lnA || has_lnB) {
+        stats(e.eps, mean, rstd);
+        if (has_lnA) emit(e.out_lnA, e.ld_lnA, s_param + 768, s_param + 1024, mean, rstd, true, e.round_lnA != 0);
+        if (has_lnB) emit(e.out_lnB, e.ld_lnB, s_param + 1280, s_param + 1536, mean, rstd, true, e.round_lnB != 0);
+      }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    FFN_STAMP(5);
+    tc_fence_after_sync();
+    if (warp == 1) {
+      __syncwarp();
+      tmem_dealloc(tmem_base, 512);
+    }
+    return;
+  }
   if (warp >= 4) {
     const int q = warp & 3;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;

@@ -259,6 +259,10 @@ int fill_rowln_epilogue(GemmParams& p, const tavsr_rowln_args* a, const char* wh
   p.dot1 = a->dot1; p.dot2 = a->dot2; p.dots_out = a->dots_out;
   p.eps = a->eps;
   p.eps0 = a->eps0;
+  p.out_main = a->out_main; p.ld_main = a->ld_main;
+  p.out_lnA = a->out_lnA; p.ld_lnA = a->ld_lnA;
+  p.out_lnB = a->out_lnB; p.ld_lnB = a->ld_lnB;
+  p.rowwarp_epilogue = g_debug[11] == 0 && a->dots_out == nullptr;
   int rc;
   if (a->out_main &&
       (rc = make_tmap_2d(&p.tmC, a->out_main, 4, false, a->M, 256, a->ld_main, 32, 32, false)))

@@ -77,6 +77,14 @@ struct alignas(64) GemmParams {
   float2* stats_out;
   int stats_col0;
   int stats_parts;
+  // ---- raw output pointers (the fused FFN's warp-per-row epilogue stores directly, coalesced) ----
+  float* out_main;
+  long long ld_main;
+  float* out_lnA;
+  long long ld_lnA;
+  float* out_lnB;
+  long long ld_lnB;
+  int rowwarp_epilogue;  // fused FFN: 1 = warp-per-row epilogue (default), 0 = thread-per-row
 };
 
 template <bool kTf32, int kBlockN, int kMode, bool kDual, int kCtas>
