@@ -323,6 +323,17 @@ def op_cost(name, shapes, extra):
     return 0.0, 0.0
 
 
+# ncu --set full, C2 shapes, per launch (profiles/r01b_ncu_full_c2_summary.csv): read + write bytes
+NCU_TRAFFIC = {
+    "ffn_fused[(8000, 256), (2048, 256)]": (20.68 + 0.02) * 1e6,
+    "gemm_rowln[(8000, 256), (256, 1280)]+dual": (50.53 + 0.95) * 1e6,
+    "relpos_attn[(8000, 768), (499, 256)]": (25.17 + 0.01) * 1e6,
+    "csgu[(8000, 2048), (1024,)]": (65.77 + 4.66 + 32.77 + 0.01) * 1e6,
+    "gemm_bias_act[(8000, 256), (2048, 256)]": (10.38 + 9.40) * 1e6,
+    "gemm_bias_act[(8000, 256), (768, 256)]": (9.02 + 0.00) * 1e6,
+}
+
+
 def profile_step(pipe, batch_dev, peaks):
     """One eager step with CUDA events around every op: per-op-group time shares + roofline of the
     dominant group."""
@@ -369,6 +380,13 @@ def profile_step(pipe, batch_dev, peaks):
         peak = peaks["hbm_gbs"]
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None}
+    # DRAM traffic per launch of that kernel from the committed ncu --set full capture (cold-cache
+    # replay, C2 shapes): dram__bytes_read.sum + dram__bytes_write.sum, bytes
+    traffic = NCU_TRAFFIC.get(top_key)
+    if traffic is not None:
+        roof["traffic"] = traffic
+        roof["traffic_source"] = "profiles/r01b_ncu_full_c2_summary.csv"
+        roof["algorithmic_bytes"] = top["bytes"]
     roof["kernel"] = top_key
     roof["avg_launch_us"] = avg_s * 1e6
     roof["share_of_step"] = top["ms"] / total if total > 0 else None

@@ -124,10 +124,11 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, bool is_bf16
 // ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
-template <bool kTf32, int kBlockN, int kMode, bool kDual, int kCtas, int kAct, bool kStats = false>
+template <bool kTf32, int kBlockN, int kMode, bool kDual, int kCtas, int kAct, bool kStats = false,
+          bool kSeq = false>
 static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<kTf32, kBlockN, kMode, kDual, kCtas>;
-  auto kern = gemm_sm100_kernel<kTf32, kBlockN, kMode, kDual, kCtas, kAct, kStats>;
+  using Cfg = GemmCfg<kTf32, kBlockN, kMode, kDual, kCtas, kSeq>;
+  auto kern = gemm_sm100_kernel<kTf32, kBlockN, kMode, kDual, kCtas, kAct, kStats, kSeq>;
   static bool configured = false;
   if (!configured) {
     TAVSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -329,9 +330,11 @@ extern "C" int tavsr_gemm_rowln(const tavsr_rowln_args* a, void* stream) {
   if ((rc = make_tmap_2d(&p.tmB, a->w, 4, false, 256, a->K, a->ldw, 256 / ctas, 32))) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (ctas == 2) {
+    if (seq) return launch_gemm<true, 256, kModeRowLN, true, 2, 0, false, true>(p, s);
     if (dual) return launch_gemm<true, 256, kModeRowLN, true, 2, 0>(p, s);
     return launch_gemm<true, 256, kModeRowLN, false, 2, 0>(p, s);
   }
+  if (seq) return launch_gemm<true, 256, kModeRowLN, true, 1, 0, false, true>(p, s);
   if (dual) return launch_gemm<true, 256, kModeRowLN, true, 1, 0>(p, s);
   return launch_gemm<true, 256, kModeRowLN, false, 1, 0>(p, s);
 }

@@ -87,7 +87,7 @@ struct alignas(64) GemmParams {
   int rowwarp_epilogue;  // fused FFN: 1 = warp-per-row epilogue (default), 0 = thread-per-row
 };
 
-template <bool kTf32, int kBlockN, int kMode, bool kDual, int kCtas>
+template <bool kTf32, int kBlockN, int kMode, bool kDual, int kCtas, bool kSeq = false>
 struct GemmCfg {
   static constexpr int kBlockM = 128;               // rows per CTA (a CTA pair covers 256)
   static constexpr int kElemBytes = kTf32 ? 4 : 2;
@@ -96,7 +96,11 @@ struct GemmCfg {
   static constexpr int kABytes = kBlockM * 128;
   static constexpr int kBRows = kBlockN / kCtas;    // B rows held by this CTA (half in a pair)
   static constexpr int kBBytes = kBRows * 128;
-  static constexpr int kStageBytes = kABytes * (kDual ? 2 : 1) + kBBytes;
+  // a stage holds two A tiles only in the parallel dual mode; the sequential dual mode (kSeq)
+  // streams ONE A tile per k-block, so its stages are as small - and its ring as deep - as the
+  // single-operand kernel's
+  static constexpr int kATiles = (kDual && !kSeq) ? 2 : 1;
+  static constexpr int kStageBytes = kABytes * kATiles + kBBytes;
   static constexpr int kAccCols = kBlockN * (kDual ? 2 : 1);
   static constexpr int kAccStages = (512 / kAccCols) >= 2 ? 2 : 1;
   static constexpr int kEpiWarps = kMode == kModeTiled ? 8 : 4;
@@ -222,7 +226,9 @@ __device__ __forceinline__ void rowln_finish(const GemmParams& p, const float* s
     }
     for (int c = 0; c < 8; ++c) {
       uint32_t r[32];
+      uint32_t r2[kDual ? 32 : 1];
       tmem_ld32(tacc + c * 32, r);
+      if constexpr (kDual) tmem_ld32(tacc + 256 + c * 32, r2);  // both loads in flight, one wait
       float res[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) res[j] = resn[j];
@@ -235,10 +241,7 @@ __device__ __forceinline__ void rowln_finish(const GemmParams& p, const float* s
       }
       tmem_ld_wait();
       float v[32];
-      if (kDual) {
-        uint32_t r2[32];
-        tmem_ld32(tacc + 256 + c * 32, r2);
-        tmem_ld_wait();
+      if constexpr (kDual) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           v[j] = w1 * __uint_as_float(r[j]) + w2 * __uint_as_float(r2[j]);
@@ -381,10 +384,12 @@ __device__ __forceinline__ void rowln_finish(const GemmParams& p, const float* s
     }
 }
 
-template <bool kTf32, int kBlockN, int kMode, bool kDual, int kCtas, int kAct, bool kStats = false>
-__global__ void __launch_bounds__(GemmCfg<kTf32, kBlockN, kMode, kDual, kCtas>::kThreads, 1)
+template <bool kTf32, int kBlockN, int kMode, bool kDual, int kCtas, int kAct, bool kStats = false,
+          bool kSeq = false>
+__global__ void __launch_bounds__(GemmCfg<kTf32, kBlockN, kMode, kDual, kCtas, kSeq>::kThreads, 1)
 gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<kTf32, kBlockN, kMode, kDual, kCtas>;
+  using Cfg = GemmCfg<kTf32, kBlockN, kMode, kDual, kCtas, kSeq>;
+  static_assert(!kSeq || kDual, "the sequential mode is a dual mode");
   constexpr bool kPair = kCtas == 2;
   constexpr int kStages = Cfg::kStages;
   constexpr int kAccStages = Cfg::kAccStages;
@@ -466,8 +471,8 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
         for (int kb = kb_beg; kb < kb_beg + kb_cnt; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* st = s_stage + s * Cfg::kStageBytes;
-          uint8_t* sb = st + Cfg::kABytes * (kDual ? 2 : 1);
-          const bool seq = kDual && p.seq_kb1 > 0;   // one A tile per stage, picked by k-block
+          uint8_t* sb = st + Cfg::kABytes * Cfg::kATiles;
+          constexpr bool seq = kSeq;   // one A tile per stage, picked by k-block
           const bool second = seq && kb >= p.seq_kb1;
           const CUtensorMap* tma_a = second ? &p.tmA2 : &p.tmA;
           const int ka = (second ? kb - p.seq_kb1 : kb) * Cfg::kBlockK;
@@ -510,11 +515,11 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after_sync();
           const uint32_t a_addr = smem_u32(s_stage + s * Cfg::kStageBytes);
-          const uint32_t b_addr = a_addr + Cfg::kABytes * (kDual ? 2 : 1);
+          const uint32_t b_addr = a_addr + Cfg::kABytes * Cfg::kATiles;
           const uint64_t a_desc = umma_desc_kmajor_sw128(a_addr);
           const uint64_t b_desc = umma_desc_kmajor_sw128(b_addr);
           const uint64_t a2_desc = umma_desc_kmajor_sw128(a_addr + Cfg::kABytes);
-          const bool seq = kDual && p.seq_kb1 > 0;
+          constexpr bool seq = kSeq;
           const bool second = seq && kb >= p.seq_kb1;
           const uint32_t dd = second ? d0 + kBlockN : d0;
           const int kb_rel = second ? kb - p.seq_kb1 : kb;
