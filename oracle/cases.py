@@ -123,6 +123,15 @@ CASES = {
     # larger branch outputs than default init); parity tolerance stated separately (3e-3)
     "asr_c1_hot": dict(kind="single", input_size=80, cfg=_enc(), B=2, Tin=1001, lens=[1001, 801],
                        vocab=41, Lmax=100, seed=2, stride_t=8, stride_d=4, hot=True, enc_tol=3e-3),
+    # the longest sequence of the C5 sweep (T = 1500: 12 key tiles per attention row, 24 conv
+    # segments) on a ragged pair, and the shortest ones (T = 5 < conv half-width 15; B = 1)
+    "vsr_long1500": dict(kind="single", input_size=512, cfg=_enc(num_blocks=2, input_layer="linear"),
+                         B=2, Tin=1500, lens=[1500, 777], vocab=41, Lmax=100, seed=31,
+                         stride_t=4, stride_d=4),
+    "vsr_tiny": dict(kind="single", input_size=512, cfg=_enc(num_blocks=2, input_layer="linear"),
+                     B=1, Tin=5, lens=[5], vocab=41, Lmax=3, seed=32),
+    "asr_shortest": dict(kind="single", input_size=80, cfg=_enc(num_blocks=2), B=2, Tin=23,
+                         lens=[23, 9], vocab=41, Lmax=2, seed=33),
     # full-depth ragged VSR-like (C2/C4 flavour): padded variable-length batch, garbage in the pad
     "vsr_ragged12": dict(kind="single", input_size=512, cfg=_enc(input_layer="linear"), B=4, Tin=120,
                          lens=[120, 95, 64, 48], vocab=41, Lmax=30, seed=18, stride_t=4, stride_d=4),
