@@ -318,6 +318,17 @@ int tavsr_ctc_loss(const float* logp, const int64_t* targets, long long ld_targe
                    float gscale, void* alpha_ws, int B, int T, int V, int Lmax, int zero_infinity,
                    void* stream);
 
+/* Backward of the CTC head logits = hs . W^T + b (ctc.py:143) given dlogits [M,V] (the `grad` of
+ * tavsr_ctc_loss), scaled per utterance by row_scale[m / rows_per_seg] (the upstream d total / d
+ * nll_b; NULL = 1):  dhs [M,D] = g . W,  dw [V,D] = g^T . hs,  db [V] = sum_m g.  D == 256, V <= 64.
+ * `workspace` (tavsr_ctc_head_bwd_workspace_bytes) holds per-CTA partials: no atomics, results are
+ * bit-reproducible.  Outputs are overwritten, not accumulated. */
+size_t tavsr_ctc_head_bwd_workspace_bytes(int M);
+int tavsr_ctc_head_bwd(const float* dlogits, const float* row_scale, int rows_per_seg,
+                       const float* hs, long long ldh, const float* w, float* dhs, long long ldd,
+                       float* dw, float* db, void* workspace, long long workspace_bytes, int M,
+                       int D, int V, void* stream);
+
 /* Greedy CTC decode: collapse repeats of `amax` and drop blank (espnet_model.py:590-592,
  * maskctc_model.py:287-291).  lens == NULL collapses over all T frames (what _calc_ctc_loss does).
  * tokens [B,T] padded with -1, ntok [B]. */

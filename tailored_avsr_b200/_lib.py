@@ -113,6 +113,10 @@ SIGNATURES = {
     "tavsr_ctc_loss": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                c_void_p]),
+    "tavsr_ctc_head_bwd_workspace_bytes": (c_size_t, [c_int]),
+    "tavsr_ctc_head_bwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_longlong, c_void_p, c_void_p,
+                                   c_longlong, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int,
+                                   c_int, c_void_p]),
     "tavsr_ctc_greedy": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                  c_void_p]),
     "tavsr_ctc_prefix_score": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

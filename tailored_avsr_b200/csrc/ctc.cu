@@ -488,6 +488,88 @@ ctc_prefix_kernel(const float* __restrict__ logp, const float* __restrict__ r_pr
   score[idx] = psi - psi_prev[hy];
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Backward of the CTC head  logits = hs . W^T + b  (ctc.py:143: ctc_lo) given d loss / d logits
+// from ctc_loss_kernel:   d hs = g . W,   d W = g^T . hs,   d b = sum_m g   with g = dlogits scaled
+// per utterance by the upstream gradient (d total / d nll_b).  fp32 FMA like the forward head.
+// CTA = 64 rows x all D = 256 columns (thread = column): W's column and the V partial sums of d W
+// live in registers, the scaled g rows are broadcast from shared memory; per-CTA partials of d W /
+// d b go to a workspace that ctc_head_bwd_reduce_kernel sums (deterministic, no atomics).
+// ------------------------------------------------------------------------------------------------
+constexpr int kBwdRows = 64;
+
+__global__ void __launch_bounds__(256)
+ctc_head_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ row_scale,
+                    int rows_per_seg, const float* __restrict__ hs, long long ldh,
+                    const float* __restrict__ w, float* __restrict__ dhs, long long ldd,
+                    float* __restrict__ part_w, float* __restrict__ part_b, int M, int V) {
+  __shared__ float s_g[kBwdRows][kVPad];
+  pdl_launch_dependents();
+  const int t = threadIdx.x;  // column of hs / W
+  constexpr int D = 256;
+  float wcol[kVPad], acc[kVPad];
+#pragma unroll
+  for (int v = 0; v < kVPad; ++v) {
+    wcol[v] = v < V ? __ldg(w + static_cast<long long>(v) * D + t) : 0.f;
+    acc[v] = 0.f;
+  }
+  pdl_wait();
+  const int m0 = blockIdx.x * kBwdRows;
+  for (int i = t; i < kBwdRows * kVPad; i += 256) {
+    const int r = i / kVPad, v = i % kVPad;
+    const int m = m0 + r;
+    float g = 0.f;
+    if (m < M && v < V) {
+      g = ld_act(dlogits + static_cast<long long>(m) * V + v);
+      if (row_scale != nullptr) g *= ld_act(row_scale + m / rows_per_seg);
+    }
+    s_g[r][v] = g;
+  }
+  __syncthreads();
+  for (int r = 0; r < kBwdRows; ++r) {
+    const int m = m0 + r;
+    if (m >= M) break;
+    const float h = ld_act(hs + static_cast<long long>(m) * ldh + t);
+    float dh = 0.f;
+#pragma unroll
+    for (int v = 0; v < kVPad; ++v) {
+      if (v < V) {
+        const float g = s_g[r][v];
+        acc[v] = fmaf(g, h, acc[v]);
+        dh = fmaf(g, wcol[v], dh);
+      }
+    }
+    dhs[static_cast<long long>(m) * ldd + t] = dh;
+  }
+  float* pw = part_w + static_cast<long long>(blockIdx.x) * kVPad * D;
+#pragma unroll
+  for (int v = 0; v < kVPad; ++v)
+    if (v < V) pw[v * D + t] = acc[v];
+  if (t < kVPad) {
+    float sb = 0.f;
+    for (int r = 0; r < kBwdRows; ++r) sb += s_g[r][t];
+    part_b[blockIdx.x * kVPad + t] = sb;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ctc_head_bwd_reduce_kernel(const float* __restrict__ part_w, const float* __restrict__ part_b,
+                           int nblk, float* __restrict__ dw, float* __restrict__ db, int V) {
+  pdl_launch_dependents();
+  pdl_wait();
+  constexpr int D = 256;
+  const int v = blockIdx.x, t = threadIdx.x;
+  float s = 0.f;
+  for (int b = 0; b < nblk; ++b) s += ld_act(part_w + (static_cast<long long>(b) * kVPad + v) * D + t);
+  dw[v * D + t] = s;
+  if (t == 0) {
+    float sb = 0.f;
+    for (int b = 0; b < nblk; ++b) sb += ld_act(part_b + b * kVPad + v);
+    db[v] = sb;
+  }
+}
+
 }  // namespace ctc
 }  // namespace tavsr
 
@@ -603,5 +685,33 @@ extern "C" int tavsr_ctc_prefix_score(const float* logp, const float* r_prev, co
                               r_prev, last, plen, psi_prev, r_new, score, T, Tvalid, V, nhyp, blank,
                               eos));
   g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+extern "C" size_t tavsr_ctc_head_bwd_workspace_bytes(int M) {
+  const size_t nblk = (static_cast<size_t>(M) + ctc::kBwdRows - 1) / ctc::kBwdRows;
+  return nblk * ctc::kVPad * (256 + 1) * sizeof(float);
+}
+
+extern "C" int tavsr_ctc_head_bwd(const float* dlogits, const float* row_scale, int rows_per_seg,
+                                  const float* hs, long long ldh, const float* w, float* dhs,
+                                  long long ldd, float* dw, float* db, void* workspace,
+                                  long long workspace_bytes, int M, int D, int V, void* stream) {
+  TAVSR_REQUIRE(M > 0 && D == 256 && V > 0 && V <= ctc::kVPad,
+                "ctc_head_bwd: built for D == 256, V <= 64 (M=%d D=%d V=%d)", M, D, V);
+  TAVSR_REQUIRE(dlogits && hs && w && dhs && dw && db && workspace, "ctc_head_bwd: null pointer");
+  TAVSR_REQUIRE(!row_scale || rows_per_seg > 0, "ctc_head_bwd: row_scale needs rows_per_seg");
+  TAVSR_REQUIRE(static_cast<size_t>(workspace_bytes) >= tavsr_ctc_head_bwd_workspace_bytes(M),
+                "ctc_head_bwd: workspace too small");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int nblk = (M + ctc::kBwdRows - 1) / ctc::kBwdRows;
+  float* part_w = static_cast<float*>(workspace);
+  float* part_b = part_w + static_cast<size_t>(nblk) * ctc::kVPad * 256;
+  TAVSR_CUDA_OK(launch_kernel(ctc::ctc_head_bwd_kernel, dim3(nblk), dim3(256), 0, s, 0, dlogits,
+                              row_scale, rows_per_seg, hs, ldh, w, dhs, ldd, part_w, part_b, M, V));
+  TAVSR_CUDA_OK(launch_kernel(ctc::ctc_head_bwd_reduce_kernel, dim3(V), dim3(256), 0, s, 0,
+                              static_cast<const float*>(part_w), static_cast<const float*>(part_b),
+                              nblk, dw, db, V));
+  g_launches.fetch_add(2, std::memory_order_relaxed);
   return 0;
 }

@@ -12,23 +12,26 @@ import torch.nn.functional as F
 from .. import ops
 
 
-class _CTCLossFn(torch.autograd.Function):
-    """loss_b = nll_b; backward uses the gradient w.r.t. the LOGITS produced by the same kernel
-    launch (softmax - occupancy), chained through ctc_lo by autograd."""
+class _CTCHeadLossFn(torch.autograd.Function):
+    """nll_b = CTC(log_softmax(hs . W^T + b)) with every step on the CUDA path: the head and the
+    forward-backward recursion in forward (the loss kernel also emits d nll_b / d logits =
+    softmax - occupancy), the head's backward (d hs, d W, d b) in backward."""
 
     @staticmethod
-    def forward(ctx, logits, logp, targets, hlens, tlens, zero_infinity):
-        want_grad = logits.requires_grad
-        nll, grad = ops.ctc_loss(logp, targets, hlens, tlens, want_grad=want_grad, gscale=1.0,
-                                 zero_infinity=zero_infinity)
-        if want_grad:
-            ctx.save_for_backward(grad)
+    def forward(ctx, hs2d, weight, bias, targets, hlens, tlens, B, T, zero_infinity):
+        logp, _, _ = ops.ctc_head(hs2d, weight, bias, want_logp=True)
+        nll, grad = ops.ctc_loss(logp.view(B, T, -1), targets, hlens, tlens, want_grad=True,
+                                 gscale=1.0, zero_infinity=zero_infinity)
+        ctx.save_for_backward(grad, hs2d, weight)
+        ctx.T = T
         return nll
 
     @staticmethod
     def backward(ctx, gout):
-        (grad,) = ctx.saved_tensors
-        return grad * gout.view(-1, 1, 1), None, None, None, None, None
+        grad, hs2d, weight = ctx.saved_tensors
+        dhs, dw, db = ops.ctc_head_bwd(grad, hs2d, weight.contiguous(),
+                                       row_scale=gout.contiguous().float(), rows_per_seg=ctx.T)
+        return dhs, dw, db, None, None, None, None, None, None
 
 
 class CTC(torch.nn.Module):
@@ -82,10 +85,11 @@ class CTC(torch.nn.Module):
         tl = ys_lens.to(dev).to(torch.int32)
         needs_grad = torch.is_grad_enabled() and (hs.requires_grad or self.ctc_lo.weight.requires_grad)
         if needs_grad:
-            # training: logits through autograd (ctc_lo), loss + d/dlogits from the CUDA kernel
-            logits = self.ctc_lo(hs)
-            logp = torch.log_softmax(logits.detach(), dim=2).contiguous()
-            nll = _CTCLossFn.apply(logits, logp, targets, hl, tl, self.zero_infinity)
+            # training: head + loss + their backward all on the CUDA path (no ATen arithmetic)
+            D = hs.shape[-1]
+            hs2d = hs.reshape(B * T, D).contiguous().float()
+            nll = _CTCHeadLossFn.apply(hs2d, self.ctc_lo.weight, self.ctc_lo.bias, targets, hl, tl,
+                                       B, T, self.zero_infinity)
         else:
             (logp, _, _), _, _ = self._head(hs, logp=True)
             nll, _ = ops.ctc_loss(logp.view(B, T, -1), targets, hl, tl, zero_infinity=self.zero_infinity)

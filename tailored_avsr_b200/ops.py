@@ -18,7 +18,7 @@ from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SWISH, DT_TF32, FfnArgs, Row
 __all__ = [
     "ACT_NONE", "ACT_SWISH", "ACT_GELU", "ACT_RELU",
     "gemm_bias_act", "conv2d_sub_im2col", "gemm_bias_act_stats", "csgu_fused", "merge_weights2", "scale_add_rows", "gemm_rowln", "ffn_fused", "layernorm", "relpos_attn", "csgu", "merge_weights",
-    "ctc_head", "vocab_residual", "row_dots", "ctc_loss", "ctc_greedy", "ctc_prefix_score", "launch_count",
+    "ctc_head", "ctc_head_bwd", "vocab_residual", "row_dots", "ctc_loss", "ctc_greedy", "ctc_prefix_score", "launch_count",
 ]
 
 
@@ -456,6 +456,30 @@ def ctc_loss(logp: torch.Tensor, targets: torch.Tensor, hlens: torch.Tensor, tle
                              _p(ws), B, T, V, Lmax, int(zero_infinity), _stream()),
           "tavsr_ctc_loss")
     return nll, grad
+
+
+@_profiled
+def ctc_head_bwd(dlogits: torch.Tensor, hs: torch.Tensor, w: torch.Tensor,
+                 row_scale: Optional[torch.Tensor] = None, rows_per_seg: int = 0):
+    """Backward of the CTC head: (dhs (M,D), dw (V,D), db (V,)) from dlogits (M,V), optionally
+    scaled per utterance (tavsr_ctc_head_bwd)."""
+    _chk2d(hs, "hs")
+    M, D = hs.shape
+    V = w.shape[0]
+    dl = dlogits.reshape(M, V)
+    if not dl.is_contiguous() or not w.is_contiguous():
+        raise _lib.TavsrError("ctc_head_bwd: dlogits and w must be contiguous")
+    lib = _lib.load()
+    dhs = torch.empty((M, D), device=hs.device, dtype=torch.float32)
+    dw = torch.empty((V, D), device=hs.device, dtype=torch.float32)
+    db = torch.empty((V,), device=hs.device, dtype=torch.float32)
+    ws = torch.empty((int(lib.tavsr_ctc_head_bwd_workspace_bytes(M)) // 4,), device=hs.device,
+                     dtype=torch.float32)
+    check(lib.tavsr_ctc_head_bwd(dl.data_ptr(), _p(row_scale), rows_per_seg, hs.data_ptr(),
+                                 hs.stride(0), w.data_ptr(), dhs.data_ptr(), dhs.stride(0),
+                                 dw.data_ptr(), db.data_ptr(), ws.data_ptr(), ws.numel() * 4, M, D, V,
+                                 _stream()), "tavsr_ctc_head_bwd")
+    return dhs, dw, db
 
 
 @_profiled

@@ -62,3 +62,51 @@ def test_two_rank_gloo_loss_and_gather_match_single_process():
         ret = mgr.dict()
         mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
         assert ret.get("loss_ok") and ret.get("toks_ok") and ret.get("max_ok"), dict(ret)
+
+
+def _grad_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        B, T, D, V, L = 6, 30, 16, 11, 7
+        lens = torch.tensor([30, 25, 28, 21, 30, 12])
+        hs = synth.randn((B, T, D), 5)
+        ys = synth.rand_targets(B, L, V, 8)
+        ylens = torch.tensor([7, 5, 7, 6, 7, 3])
+        torch.manual_seed(0)
+        lo = torch.nn.Linear(D, V)
+        extra = torch.nn.Parameter(torch.zeros(3))      # never used: contributes zeros
+
+        def loss_of(idx):
+            sd = {"ctc_lo.weight": lo.weight, "ctc_lo.bias": lo.bias}
+            vec = ref_path.ctc_loss(hs[idx], lens[idx], ys[idx], ylens[idx], sd, reduce=False) * len(idx)
+            return vec.sum() / B                          # normalised by the GLOBAL batch
+
+        mine = torch.tensor(parallel.shard_utterances(lens.tolist(), world, rank))
+        loss_of(mine).backward()
+        # tiny buckets: weight (176 floats) and bias / extra land in different collectives
+        red = parallel.GradBucketReducer([lo.weight, lo.bias, extra], bucket_mb=0.0005)
+        n = red.reduce()
+        got_w, got_b = lo.weight.grad.clone(), lo.bias.grad.clone()
+        lo.zero_grad()
+        loss_of(torch.arange(B)).backward()
+        if rank == 0:
+            ret["n_collectives"] = n
+            ret["w_ok"] = bool(torch.allclose(got_w, lo.weight.grad, rtol=1e-5, atol=1e-6))
+            ret["b_ok"] = bool(torch.allclose(got_b, lo.bias.grad, rtol=1e-5, atol=1e-6))
+            ret["extra_ok"] = bool(extra.grad is not None and float(extra.grad.abs().sum()) == 0.0)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_bucketed_gradient_allreduce_equals_full_batch_gradient():
+    """Sum of the per-rank gradients (loss normalised by the global batch) == full-batch gradient;
+    buckets are formed in reverse parameter order and every rank launches the same collectives."""
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_grad_worker, args=(world, port, ret), nprocs=world, join=True)
+        assert ret.get("w_ok") and ret.get("b_ok") and ret.get("extra_ok"), dict(ret)
+        assert ret.get("n_collectives") >= 2, dict(ret)
