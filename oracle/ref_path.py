@@ -372,6 +372,48 @@ def _encoder_with_mask(x_pos, masks, sd, cfg, prefix):
 
 
 # --------------------------------------------------------------------------------------------------
+# AVSR embedding layers (src/embedding_for_avsr/default.py) + the model's temporal alignment
+# --------------------------------------------------------------------------------------------------
+def avsr_embed_layer(xs: torch.Tensor, ilens: torch.Tensor, sd: SD, prefix: str, input_layer: str):
+    """DefaultEmbeddingLayerForAVSR.apply_embed_layer (default.py:139-153), eval mode.
+    conv2d = espnet Conv2dSubsamplingWOPosEnc (two 3x3 stride-2 convs + ReLU, Linear, no pos-enc);
+    linear = Linear + torch LayerNorm (eps 1e-5).  Returns (x (B,T,d), masks (B,1,T))."""
+    masks = make_valid_mask(ilens, xs.shape[1])
+    if input_layer == "conv2d":
+        h = F.relu(F.conv2d(xs.unsqueeze(1), sd[prefix + "embed.conv.0.weight"],
+                            sd[prefix + "embed.conv.0.bias"], stride=2))
+        h = F.relu(F.conv2d(h, sd[prefix + "embed.conv.2.weight"], sd[prefix + "embed.conv.2.bias"],
+                            stride=2))
+        b, c, t, f = h.shape
+        x = F.linear(h.transpose(1, 2).contiguous().view(b, t, c * f), sd[prefix + "embed.out.weight"],
+                     sd[prefix + "embed.out.bias"])
+        return x, masks[:, :, :-2:2][:, :, :-2:2]
+    if input_layer == "linear":
+        x = F.linear(xs, sd[prefix + "embed.0.weight"], sd[prefix + "embed.0.bias"])
+        x = F.layer_norm(x, (x.shape[-1],), sd[prefix + "embed.1.weight"], sd[prefix + "embed.1.bias"], 1e-5)
+        return x, masks
+    raise NotImplementedError(input_layer)
+
+
+def audiovisual_alignment(a, ma, v, mv, ignore_id: float = -1.0):
+    """ESPnetAVSRModel.audiovisual_alignment (src/models/avsr_espnet_model.py:512-541): the shorter
+    stream is padded with ignore_id (masks with False) up to the longer one."""
+    pad = a.shape[1] - v.shape[1]
+    if pad < 0:
+        a = F.pad(a, (0, 0, 0, -pad, 0, 0), value=ignore_id)
+        ma = F.pad(ma, (0, -pad), value=False)
+    elif pad > 0:
+        v = F.pad(v, (0, 0, 0, pad, 0, 0), value=ignore_id)
+        mv = F.pad(mv, (0, pad), value=False)
+    return a, ma, v, mv
+
+
+def rel_pos_enc(x: torch.Tensor):
+    """espnet RelPositionalEncoding.forward in eval: (x * sqrt(d), pos_emb (1, 2T-1, d))."""
+    return x * math.sqrt(x.shape[-1]), rel_pos_emb(x.shape[1], x.shape[-1])
+
+
+# --------------------------------------------------------------------------------------------------
 # CTC (src/ctc/ctc.py)
 # --------------------------------------------------------------------------------------------------
 def interctc_residual(x: torch.Tensor, sd: SD, prefix: str = "") -> Tuple[torch.Tensor, torch.Tensor]:

@@ -13,6 +13,7 @@ from __future__ import annotations
 
 from .audiovisual_fusion.adaptive_audiovisual_fusion import AdaptiveAudioVisualFusion
 from .ctc.ctc import CTC
+from .embedding_for_avsr.default import DefaultEmbeddingLayerForAVSR
 from .encoder.audiovisual.conventional.encoder import ConventionalEncoder
 from .encoder.audiovisual.tailored.encoder import TailoredEncoder
 from .encoder.branchformer.encoder import MyBranchformerEncoder
@@ -38,4 +39,7 @@ def install_avsr(namespace: dict) -> None:
     classes["conventional"] = ConventionalEncoder
     # src/tasks/avsr.py:165-172: audiovisual_fusion_choices, key "adaptive"
     _classes(namespace["audiovisual_fusion_choices"])["adaptive"] = AdaptiveAudioVisualFusion
+    # src/tasks/avsr.py:140-155: acoustic_embed_choices / visual_embed_choices, key "default"
+    _classes(namespace["acoustic_embed_choices"])["default"] = DefaultEmbeddingLayerForAVSR
+    _classes(namespace["visual_embed_choices"])["default"] = DefaultEmbeddingLayerForAVSR
     namespace["CTC"] = CTC
