@@ -163,19 +163,47 @@ class AVEncoderCTCPipeline(EncoderCTCPipeline):
     AdaptiveAudioVisualFusion -> CTC loss + greedy decode (avsr_espnet_model.py:451-467, 678-683).
     The key-padding masks and the relative positional table are built on the device."""
 
-    def __init__(self, encoder, fusion, ctc, use_cuda_graph: bool = True, greedy: bool = True):
+    def __init__(self, encoder, fusion, ctc, use_cuda_graph: bool = True, greedy: bool = True,
+                 acoustic_embed=None, visual_embed=None, ignore_id: float = -1.0):
+        """With `acoustic_embed` / `visual_embed` (DefaultEmbeddingLayerForAVSR) the inputs are the
+        raw per-modality features and their lengths, and the step starts where the model's encode()
+        does: embed -> temporal alignment (pad with ignore_id) -> positional encoding
+        (avsr_espnet_model.py:427-448)."""
         super().__init__(encoder, ctc, use_cuda_graph=use_cuda_graph, greedy=greedy)
         from .espnet_compat import RelPositionalEncoding
         self.fusion = fusion.eval()
         self._pos = RelPositionalEncoding(encoder.output_size(), 0.0)
+        assert (acoustic_embed is None) == (visual_embed is None), "pass both embeds or neither"
+        self.acoustic_embed = acoustic_embed.eval() if acoustic_embed is not None else None
+        self.visual_embed = visual_embed.eval() if visual_embed is not None else None
+        self.ignore_id = ignore_id
+
+    def _embed(self, audio, video, lens_a, lens_v):
+        """Raw features -> aligned, position-encoded block inputs and masks."""
+        import torch.nn.functional as F
+        a, ma = self.acoustic_embed.apply_embed_layer(audio, lens_a)
+        v, mv = self.visual_embed.apply_embed_layer(video, lens_v)
+        pad = a.shape[1] - v.shape[1]   # static per input shape: the CUDA graph key covers it
+        if pad < 0:
+            a = F.pad(a, (0, 0, 0, -pad, 0, 0), value=self.ignore_id)
+            ma = F.pad(ma, (0, -pad), value=False)
+        elif pad > 0:
+            v = F.pad(v, (0, 0, 0, pad, 0, 0), value=self.ignore_id)
+            mv = F.pad(mv, (0, pad), value=False)
+        (a, pos), (v, _) = self.acoustic_embed.apply_pos_enc(a), self.visual_embed.apply_pos_enc(v)
+        return a, v, ma, mv, pos
 
     def _step(self, audio, video, lens_a, lens_v, ys_pad, ys_lens):
-        B, T, _ = audio.shape
         dev = audio.device
-        ar = torch.arange(T, device=dev)[None, :]
-        mask_a = (ar < lens_a[:, None]).unsqueeze(1)
-        mask_v = (ar < lens_v[:, None]).unsqueeze(1)
-        pos = self._pos.pos_emb(T, dev)
+        if self.acoustic_embed is not None:
+            audio, video, mask_a, mask_v, pos = self._embed(audio, video, lens_a, lens_v)
+            B, T, _ = audio.shape
+        else:
+            B, T, _ = audio.shape
+            ar = torch.arange(T, device=dev)[None, :]
+            mask_a = (ar < lens_a[:, None]).unsqueeze(1)
+            mask_v = (ar < lens_v[:, None]).unsqueeze(1)
+            pos = self._pos.pos_emb(T, dev)
         ya, _, yv, _, _ = self.encoder((audio, pos), mask_a, (video, pos), mask_v, ctc=self.ctc,
                                        audiovisual_fusion=self.fusion)
         if isinstance(ya, tuple):

@@ -87,3 +87,50 @@ def test_embed_refuses_cpu_tensors():
     ae, _, _ = _build()
     with pytest.raises(Exception):
         ae.apply_embed_layer(torch.zeros(1, 23, 80), torch.tensor([23]))
+
+
+@pytest.mark.gpu
+def test_av_pipeline_from_raw_features_matches_oracle_composition():
+    """The whole AVSR encode() call stack on the B200 path (embed -> align -> pos-enc -> tailored
+    encoder -> fusion -> CTC loss + greedy), CUDA-graph replay included, against the oracle."""
+    import copy
+
+    from oracle import cases
+    from tailored_avsr_b200.audiovisual_fusion.adaptive_audiovisual_fusion import AdaptiveAudioVisualFusion
+    from tailored_avsr_b200.ctc.ctc import CTC
+    from tailored_avsr_b200.encoder.audiovisual.tailored.encoder import TailoredEncoder
+    from tailored_avsr_b200.pipeline import AVEncoderCTCPipeline
+    ae, ve, sd = _build()
+    cfg = dict(copy.deepcopy(cases.BASE_TAILORED), num_blocks=2, acoustic_use_attn=[True, False],
+               visual_use_attn=[False, True])
+    enc = TailoredEncoder(embed_pos_enc_layer_type="rel_pos", embed_rel_pos_type="latest", **cfg).eval()
+    fusion = AdaptiveAudioVisualFusion(**cases.FUSION_DEFAULTS).eval()
+    ctc = CTC(odim=37, encoder_output_size=256, dropout_rate=0.0).eval()
+    sd.update(synth.fill_module(enc, seed=7))
+    sd.update(synth.fill_module(fusion, seed=7, prefix="fusion."))
+    sd.update(synth.fill_module(ctc, seed=7, prefix="ctc."))
+    xa, la, xv, lv = gen_golden_embed.inputs()
+    ys = synth.rand_targets(3, 10, 37, 3)
+    yl = torch.tensor([10, 7, 4])
+    # oracle composition
+    o = _oracle(sd)
+    with torch.no_grad():
+        wa, wv = ref_path.tailored_encoder(o["audio_in"], o["pos"], o["audio_mask_aligned"], o["video_in"],
+                                           o["pos"], o["video_mask_aligned"], sd, cfg)
+        fused, olens, _ = ref_path.adaptive_av_fusion(wa, o["audio_mask_aligned"], wv,
+                                                      o["video_mask_aligned"], sd, "fusion.")
+        want_loss = float(ref_path.ctc_loss(fused, olens, ys, yl, sd, "ctc.ctc_lo"))
+    pipe = AVEncoderCTCPipeline(enc.cuda(), fusion.cuda(), ctc.cuda(), acoustic_embed=ae.cuda(),
+                                visual_embed=ve.cuda())
+    dev_in = [t.cuda() for t in (xa, xv, la, lv, ys, yl)]
+    pipe.run_device(*dev_in)                 # captures the graph
+    res = pipe.run_device(*dev_in)           # replay
+    torch.cuda.synchronize()
+    got = res["encoder_out"].cpu()
+    assert torch.equal(res["olens"].cpu().long(), olens.long())
+    err = 0.0
+    for b in range(3):
+        n = int(olens[b])
+        err = max(err, float((got[b, :n] - fused[b, :n]).abs().max() / fused.abs().max()))
+    assert err <= 1e-3, err
+    assert abs(float(res["loss"]) - want_loss) <= 2e-3 * abs(want_loss)   # loss on OUR encoder output
