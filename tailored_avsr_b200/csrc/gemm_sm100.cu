@@ -192,8 +192,14 @@ extern "C" int tavsr_gemm_bias_act_stats(const void* x, long long ldx, const voi
                                          int K, int act, int round_out, int dtype, float* stats_out,
                                          int stats_col0, int* stats_part_width, void* stream) {
   TAVSR_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
-  TAVSR_REQUIRE(dtype == TAVSR_DT_TF32, "gemm: only TAVSR_DT_TF32 is built in this round");
-  TAVSR_REQUIRE(K % 4 == 0 && N % 4 == 0, "gemm: K and N must be multiples of 4 (K=%d N=%d)", K, N);
+  TAVSR_REQUIRE(dtype == TAVSR_DT_TF32 || dtype == TAVSR_DT_BF16,
+                "gemm: dtype must be TAVSR_DT_TF32 or TAVSR_DT_BF16 (bf16 operands, fp32 output)");
+  const bool bf16 = dtype == TAVSR_DT_BF16;
+  const int eb = bf16 ? 2 : 4;  // operand element bytes; a 128-byte swizzle row holds 128 / eb
+  TAVSR_REQUIRE(K % (16 / eb) == 0 && N % 4 == 0,
+                "gemm: K must be a multiple of %d and N of 4 (K=%d N=%d)", 16 / eb, K, N);
+  TAVSR_REQUIRE(!bf16 || (stats_out == nullptr && !round_out),
+                "gemm: the bf16-operand kernel has no statistics epilogue / TF32 output rounding");
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K;
@@ -225,10 +231,17 @@ extern "C" int tavsr_gemm_bias_act_stats(const void* x, long long ldx, const voi
     *stats_part_width = pw;
   }
   int rc;
-  if ((rc = make_tmap_2d(&p.tmA, x, 4, false, M, K, ldx, 128, 32))) return rc;
-  if ((rc = make_tmap_2d(&p.tmB, w, 4, false, N, K, ldw, bn / ctas, 32))) return rc;
+  if ((rc = make_tmap_2d(&p.tmA, x, eb, bf16, M, K, ldx, 128, 128 / eb))) return rc;
+  if ((rc = make_tmap_2d(&p.tmB, w, eb, bf16, N, K, ldw, bn / ctas, 128 / eb))) return rc;
   if ((rc = make_tmap_2d(&p.tmC, y, 4, false, M, N, ldy, 32, 32, false))) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (bf16) {
+    // kind::f16 MMAs on bf16 operands (128 x N x 16 per instruction, twice the TF32 rate at half
+    // the operand bytes), fp32 accumulate and fp32 output: the first brick of the bf16 mode
+    TAVSR_REQUIRE(ctas == 2, "gemm: the bf16-operand kernel is built for CTA pairs");
+    return bn == 128 ? launch_gemm<false, 128, kModeTiled, false, 2, -1>(p, s)
+                     : launch_gemm<false, 256, kModeTiled, false, 2, -1>(p, s);
+  }
   if (ctas == 2) return bn == 128 ? launch_tiled<128, 2>(p, s) : launch_tiled<256, 2>(p, s);
   return bn == 128 ? launch_tiled<128, 1>(p, s) : launch_tiled<256, 1>(p, s);
 }

@@ -13,7 +13,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SWISH, DT_TF32, FfnArgs, RowLNArgs, check
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SWISH, DT_BF16, DT_TF32, FfnArgs, RowLNArgs, check
 
 __all__ = [
     "ACT_NONE", "ACT_SWISH", "ACT_GELU", "ACT_RELU",
@@ -91,9 +91,11 @@ def launch_count() -> int:
 @_profiled
 def gemm_bias_act(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: int = ACT_NONE,
                   round_out: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out = act(x @ w.T + bias) on the tcgen05 GEMM (tavsr_gemm_bias_act)."""
-    _chk2d(x, "x")
-    _chk2d(w, "w")
+    """out = act(x @ w.T + bias) on the tcgen05 GEMM (tavsr_gemm_bias_act).  fp32 operands run as
+    TF32; bf16 operands (both) run kind::f16 MMAs with fp32 accumulate and fp32 output."""
+    bf16 = x.dtype == torch.bfloat16
+    _chk2d(x, "x", x.dtype if bf16 else torch.float32)
+    _chk2d(w, "w", torch.bfloat16 if bf16 else torch.float32)
     M, K = x.shape
     N = w.shape[0]
     if out is None:
@@ -102,7 +104,7 @@ def gemm_bias_act(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]
     lib = _lib.load()
     check(lib.tavsr_gemm_bias_act(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), _p(bias),
                                   out.data_ptr(), out.stride(0), M, N, K, act, int(round_out),
-                                  DT_TF32, _stream()), "tavsr_gemm_bias_act")
+                                  DT_BF16 if bf16 else DT_TF32, _stream()), "tavsr_gemm_bias_act")
     return out
 
 

@@ -567,3 +567,23 @@ def test_conv2d_subsampling_im2col_plus_gemm(B, Tin, Fin):
     ref = F.relu(F.conv2d(h1, w2.double(), b2.double(), stride=2))    # (B, C, T2, F2)
     ref = ref.permute(0, 2, 3, 1).reshape(B * T2 * F2, C)
     assert rel_fro(out, ref) < 2e-3, rel_fro(out, ref)
+
+
+@pytest.mark.parametrize("M,N,K", [(8000, 2048, 256), (8000, 768, 256), (300, 256, 1024), (77, 48, 64)])
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_gemm_bias_act_bf16_operands(M, N, K, act):
+    """TAVSR_DT_BF16: bf16 operands, fp32 accumulate and output - exact up to fp32 summation order
+    against an fp64 product of the same bf16 values."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(M + N + K + act)
+    x = torch.randn(M, K, generator=g).to(DEV).to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV).to(torch.bfloat16)
+    b = torch.randn(N, generator=g).to(DEV)
+    y = ops.gemm_bias_act(x, w, b, act=act)
+    assert y.dtype == torch.float32
+    ref = x.double() @ w.double().t() + b.double()
+    if act == 1:
+        ref = ref * torch.sigmoid(ref)
+    elif act == 2:
+        ref = F.gelu(ref)
+    assert rel_fro(y, ref) < 2e-5, rel_fro(y, ref)
