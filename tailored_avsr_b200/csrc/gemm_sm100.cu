@@ -125,10 +125,10 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, bool is_bf16
 // launch helpers
 // ------------------------------------------------------------------------------------------------
 template <bool kTf32, int kBlockN, int kMode, bool kDual, int kCtas, int kAct, bool kStats = false,
-          bool kSeq = false>
+          bool kSeq = false, bool kWideEpi = false>
 static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<kTf32, kBlockN, kMode, kDual, kCtas, kSeq>;
-  auto kern = gemm_sm100_kernel<kTf32, kBlockN, kMode, kDual, kCtas, kAct, kStats, kSeq>;
+  using Cfg = GemmCfg<kTf32, kBlockN, kMode, kDual, kCtas, kSeq, kWideEpi>;
+  auto kern = gemm_sm100_kernel<kTf32, kBlockN, kMode, kDual, kCtas, kAct, kStats, kSeq, kWideEpi>;
   static bool configured = false;
   if (!configured) {
     TAVSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -241,6 +241,19 @@ extern "C" int tavsr_gemm_bias_act_stats(const void* x, long long ldx, const voi
     TAVSR_REQUIRE(ctas == 2, "gemm: the bf16-operand kernel is built for CTA pairs");
     return bn == 128 ? launch_gemm<false, 128, kModeTiled, false, 2, -1>(p, s)
                      : launch_gemm<false, 256, kModeTiled, false, 2, -1>(p, s);
+  }
+  // 16-warp epilogue (GemmCfg::kWideEpi) for the CTA-pair kernels: +3.7 % on the C2 step with the
+  // 256-wide tiles.  g_debug[13] = 1 falls back to 8 warps; g_debug[14] = 1 also widens 128-wide tiles.
+  if (ctas == 2 && g_debug[13] == 0 && stats_out == nullptr && (bn == 256 || g_debug[14] == 1)) {
+#define TAVSR_WIDE(BN)                                                                                \
+    switch (p.act) {                                                                                  \
+      case ACT_NONE: return launch_gemm<true, BN, kModeTiled, false, 2, ACT_NONE, false, false, true>(p, s);   \
+      case ACT_SWISH: return launch_gemm<true, BN, kModeTiled, false, 2, ACT_SWISH, false, false, true>(p, s); \
+      case ACT_GELU: return launch_gemm<true, BN, kModeTiled, false, 2, ACT_GELU, false, false, true>(p, s);   \
+      default: return launch_gemm<true, BN, kModeTiled, false, 2, -1, false, false, true>(p, s);      \
+    }
+    if (bn == 256) { TAVSR_WIDE(256) } else { TAVSR_WIDE(128) }
+#undef TAVSR_WIDE
   }
   if (ctas == 2) return bn == 128 ? launch_tiled<128, 2>(p, s) : launch_tiled<256, 2>(p, s);
   return bn == 128 ? launch_tiled<128, 1>(p, s) : launch_tiled<256, 1>(p, s);

@@ -87,7 +87,12 @@ struct alignas(64) GemmParams {
   int rowwarp_epilogue;  // fused FFN: 1 = warp-per-row epilogue (default), 0 = thread-per-row
 };
 
-template <bool kTf32, int kBlockN, int kMode, bool kDual, int kCtas, bool kSeq = false>
+// kWideEpi (tiled mode): 16 epilogue warps (four per TMEM lane quadrant, a quarter of the tile's
+// columns each) instead of 8.  The K = 256 projections are bound by their epilogue, and ncu shows it
+// latency-bound rather than issue-bound (8 epilogue warps: 39 % issue-active, stalls on the first
+// use of each TMEM / bias load and on fixed-latency dependencies), so more warps per scheduler.
+template <bool kTf32, int kBlockN, int kMode, bool kDual, int kCtas, bool kSeq = false,
+          bool kWideEpi = false>
 struct GemmCfg {
   static constexpr int kBlockM = 128;               // rows per CTA (a CTA pair covers 256)
   static constexpr int kElemBytes = kTf32 ? 4 : 2;
@@ -103,9 +108,11 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes * kATiles + kBBytes;
   static constexpr int kAccCols = kBlockN * (kDual ? 2 : 1);
   static constexpr int kAccStages = (512 / kAccCols) >= 2 ? 2 : 1;
-  static constexpr int kEpiWarps = kMode == kModeTiled ? 8 : 4;
+  static constexpr int kEpiWarps = kMode == kModeTiled ? (kWideEpi ? 16 : 8) : 4;
   static constexpr int kThreads = 64 + 32 * kEpiWarps;
-  static constexpr int kStagingBytes = kEpiWarps * 2 * 4096;
+  static constexpr int kStageBufs = kWideEpi ? 1 : 2;  // 16 warps: single-buffered store staging
+  static constexpr int kStagingBytes = kEpiWarps * kStageBufs * 4096;
+  static constexpr int kEpiParts = kEpiWarps / 4;      // column slices of a tile (one per warp of a quadrant)
   // params staged in smem: bias[2][kBlockN] (tiled) or 9 x 256 floats (rowln)
   static constexpr int kParamFloats = kMode == kModeTiled ? 2 * kBlockN : 9 * 256;
   static constexpr int kFixedBytes = 1024 /*align slack*/ + kStagingBytes + kParamFloats * 4 + 256;
@@ -145,12 +152,15 @@ __device__ __forceinline__ float apply_act(float x, int act_rt) {
 // Write one 32-float row chunk into a per-warp staging box (32 rows x 128 B, 128B-swizzled so that
 // it matches a TMA store with CU_TENSOR_MAP_SWIZZLE_128B) and issue the TMA store.
 struct WarpStager {
-  uint8_t* base;  // 2 x 4096 B, 1024-aligned
+  uint8_t* base;  // nbuf x 4096 B, 1024-aligned
   int buf;
+  int nbuf = 2;
   __device__ __forceinline__ void store(const CUtensorMap* tm, const float (&v)[32], int col0,
                                         int row0) {
     const uint32_t lane = lane_id();
-    if (lane == 0) tma_store_wait_read<1>();
+    if (lane == 0) {
+      if (nbuf == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+    }
     __syncwarp();
     // explicit st.shared: the pointer travels through this struct, where the compiler may lose
     // the address space and fall back to generic stores
@@ -166,7 +176,7 @@ struct WarpStager {
       tma_store_2d(tm, base + buf * 4096, col0, row0);
       tma_store_commit();
     }
-    buf ^= 1;
+    if (nbuf == 2) buf ^= 1;
   }
   __device__ __forceinline__ void drain() {
     if (lane_id() == 0) tma_store_wait_all<0>();
@@ -385,10 +395,11 @@ __device__ __forceinline__ void rowln_finish(const GemmParams& p, const float* s
 }
 
 template <bool kTf32, int kBlockN, int kMode, bool kDual, int kCtas, int kAct, bool kStats = false,
-          bool kSeq = false>
-__global__ void __launch_bounds__(GemmCfg<kTf32, kBlockN, kMode, kDual, kCtas, kSeq>::kThreads, 1)
+          bool kSeq = false, bool kWideEpi = false>
+__global__ void __launch_bounds__(GemmCfg<kTf32, kBlockN, kMode, kDual, kCtas, kSeq, kWideEpi>::kThreads, 1)
 gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<kTf32, kBlockN, kMode, kDual, kCtas, kSeq>;
+  using Cfg = GemmCfg<kTf32, kBlockN, kMode, kDual, kCtas, kSeq, kWideEpi>;
+  static_assert(!kWideEpi || (kMode == kModeTiled && !kStats), "wide epilogue: tiled mode");
   static_assert(!kSeq || kDual, "the sequential mode is a dual mode");
   constexpr bool kPair = kCtas == 2;
   constexpr int kStages = Cfg::kStages;
@@ -551,7 +562,7 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
     const int ew = warp - 2;          // 0 .. kEpiWarps-1
     const int q = warp & 3;           // TMEM lane quadrant this warp may access
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    WarpStager stager{s_staging + ew * 8192, 0};
+    WarpStager stager{s_staging + ew * Cfg::kStageBufs * 4096, 0, Cfg::kStageBufs};
     int as = 0;
     uint32_t aph = 0;
     int it = 0;
@@ -565,9 +576,9 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
       if constexpr (kMode == kModeTiled) {
         mbar_wait(&tfull_bar[as], aph);
         tc_fence_after_sync();
-        const int half = ew >> 2;
-        constexpr int kChunks = kBlockN / 64;  // 32-col chunks per warp (half the tile)
-        const int col0 = half * (kBlockN / 2);
+        const int half = ew >> 2;              // column slice of this warp (0 .. kEpiParts-1)
+        constexpr int kChunks = kBlockN / 32 / Cfg::kEpiParts;  // 32-col chunks per warp
+        const int col0 = half * (kBlockN / Cfg::kEpiParts);
         uint32_t r[2][32];
         tmem_ld32(tacc + col0, r[0]);
         const bool do_stats = kStats && p.stats_out != nullptr && n0 + col0 >= p.stats_col0;  // warp-uniform
