@@ -56,7 +56,7 @@ __device__ __forceinline__ long long globaltimer_ns() {
 }
 #define FFN_STAMP(slot)                                                              \
   do {                                                                               \
-    if (p.dbg != nullptr && (threadIdx.x == (blockDim.x == 256 ? 128 : 64)))           \
+    if (p.dbg != nullptr && (threadIdx.x == (blockDim.x >= 256 ? 128 : 64)))           \
       p.dbg[static_cast<long long>(blockIdx.x) * 8 + (slot)] = globaltimer_ns();     \
   } while (0)
 
@@ -86,7 +86,8 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t addr, float4 v) {
 // is walked identically by the producer and both issuers.
 // ------------------------------------------------------------------------------------------------
 namespace ffn {
-constexpr int kThreadsV1 = 256;
+constexpr int kActWarpsV1 = 8;                     // activation warps: two per TMEM lane quadrant
+constexpr int kThreadsV1 = 128 + 32 * kActWarpsV1;  // + TMA, GEMM1, GEMM2 issuer warps and an idle one
 constexpr int kRingV1 = 6;
 constexpr int kSmemBytesV1 = 1024 + kXBytes + kRingV1 * kUnitBytes + 512;
 
@@ -147,7 +148,7 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
     mbar_init(x_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&h_full[i], 1);
-      mbar_init(&h_ready[i], 4);
+      mbar_init(&h_ready[i], kActWarpsV1);
       mbar_init(&h_free[i], 1);
     }
     mbar_init(d_full, 1);
@@ -283,7 +284,13 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
     }
   } else if (warp >= 4) {
     // =============================== activation warps =======================================
+    // Eight warps: quadrant q = warp & 3, and the two warps of a quadrant split the chunk's four
+    // 32-column groups.  The activation sits between GEMM1_j and GEMM2_j on the tensor pipe's
+    // critical path (the pipe idles while a lone warp per quadrant walks 128 columns), so its
+    // latency is halved rather than its instruction count.
     const int q = warp & 3;  // TMEM lane quadrant
+    const int part = (warp - 4) >> 2;
+    constexpr int kGroupsPerWarp = 4 / (kActWarpsV1 / 4);
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     for (int j = 0; j < kNChunk; ++j) {
       mbar_wait(&h_full[j & 1], (j >> 1) & 1);
@@ -293,7 +300,8 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
       const uint32_t th = tmem_base + lane_off + kColH + (j & 1) * kChunk;
       const float4* b1p = reinterpret_cast<const float4*>(p.b1 + hid0 + j * kChunk);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < kGroupsPerWarp; ++cc) {
+        const int c = part * kGroupsPerWarp + cc;
         uint32_t r[32];
         tmem_ld32(th + c * 32, r);
         float bb[32];
@@ -339,7 +347,7 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
     // into the peer's - and then all eight warps finish rows with coalesced global accesses and
     // shuffle reductions (lane = 8 consecutive columns).
     uint8_t* s_own = s_x + 64 * 1024;  // [64 rows][1 KB], 16-byte chunks XOR-swizzled by row & 7
-    if (warp >= 4) {
+    if (warp >= 4 && warp < 8) {
       const int q = warp & 3;
       const uint32_t td2 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kColD2;
       const int row_local = (q & 1) * 32 + static_cast<int>(lane);
@@ -462,7 +470,7 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
     }
     return;
   }
-  if (warp >= 4) {
+  if (warp >= 4 && warp < 8) {
     const int q = warp & 3;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t td2 = tmem_base + lane_off + kColD2;
@@ -485,7 +493,7 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
   }
   cluster_sync_all();  // release/acquire: the peer's rows are visible in s_x
   FFN_STAMP(4);
-  if (warp >= 4) {
+  if (warp >= 4 && warp < 8) {
     const int q = warp & 3;
     if (static_cast<uint32_t>(q >> 1) == rank) {
       const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
