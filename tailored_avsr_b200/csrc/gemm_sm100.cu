@@ -356,9 +356,16 @@ extern "C" int tavsr_gemm_rowln(const tavsr_rowln_args* a, void* stream) {
   if ((rc = make_tmap_2d(&p.tmB, a->w, 4, false, 256, a->K, a->ldw, 256 / ctas, 32))) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (ctas == 2) {
-    if (seq) return launch_gemm<true, 256, kModeRowLN, true, 2, 0, false, true>(p, s);
+    // g_debug[15] = 1: two epilogue warps per TMEM lane quadrant (rowln_finish2), never with
+    // split-K.  Opt-in: measured SLOWER on the C2 step (3.28 vs 3.19 ms) - unlike the tiled GEMM and
+    // the FFN activation, the four LayerNorm partial-sum exchanges and the single-buffered store
+    // staging cost more than the halved per-thread chain saves.
+    const bool wide = g_debug[15] == 1 && p.num_n_tiles == 1;
+    if (seq) return wide ? launch_gemm<true, 256, kModeRowLN, true, 2, 0, false, true, true>(p, s)
+                         : launch_gemm<true, 256, kModeRowLN, true, 2, 0, false, true>(p, s);
     if (dual) return launch_gemm<true, 256, kModeRowLN, true, 2, 0>(p, s);
-    return launch_gemm<true, 256, kModeRowLN, false, 2, 0>(p, s);
+    return wide ? launch_gemm<true, 256, kModeRowLN, false, 2, 0, false, false, true>(p, s)
+                : launch_gemm<true, 256, kModeRowLN, false, 2, 0>(p, s);
   }
   if (seq) return launch_gemm<true, 256, kModeRowLN, true, 1, 0, false, true>(p, s);
   if (dual) return launch_gemm<true, 256, kModeRowLN, true, 1, 0>(p, s);
