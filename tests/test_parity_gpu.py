@@ -270,3 +270,22 @@ def test_pipeline_run_stream_equals_blocking_run():
         assert l0 == l1
         assert torch.equal(t0, t1) and torch.equal(n0, n1)
     assert len({w[0] for w in want}) == len(want)  # the batches really differ
+
+
+@pytest.mark.parametrize("knob", [11, 13, 15])
+def test_alternative_epilogue_paths_keep_parity(knob):
+    """The opt-out / opt-in epilogue variants behind the debug knobs stay correct: 11 = thread-per-row
+    FFN epilogue, 13 = 8-warp tiled GEMM epilogue, 15 = two-warps-per-quadrant RowLN epilogue."""
+    from tailored_avsr_b200 import _lib
+    name = "vsr_small"
+    enc, ctc, sd = _util.build_dropin(name)
+    res = _util.run_oracle(name, sd)
+    lib = _lib.load()
+    lib.tavsr_debug_set(knob, 1)
+    try:
+        got = _run_dropin(name, enc.to(DEV), ctc.to(DEV))
+        torch.cuda.synchronize()
+    finally:
+        lib.tavsr_debug_set(knob, 0)
+    mx, fro = _util.rel_errors(got["out"], res["out"], res["olens"])
+    assert mx <= ENC_TOL and fro <= ENC_TOL, (knob, mx, fro)
