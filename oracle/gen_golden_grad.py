@@ -1,0 +1,54 @@
+"""TEST INFRASTRUCTURE: golden GRADIENTS of the hot path for the training rows of SURVEY.md §8
+(encoder backward, not built yet): the REAL reference modules (eval mode: dropout and stochastic
+depth are identities, the arithmetic is the training arithmetic) run live over oracle/espnet_shim
+with autograd on, loss = CTC loss of the case; per parameter the gradient's L2 norm, its sum and
+a strided sample are stored.  The functional port (oracle/ref_path.py, plain differentiable torch)
+must reproduce them (tests/test_oracle_cpu.py), which pins the oracle the backward kernels will
+be checked against.  Run in the build container:  python -m oracle.gen_golden_grad"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import cases, gen_golden, reference_loader  # noqa: E402
+
+CASES = ["vsr_small", "asr_tailored_small"]
+
+
+def summarize(named_grads):
+    out = {}
+    for name, g in named_grads:
+        g = g.detach().double().reshape(-1)
+        out["norm/" + name] = np.array(float(g.norm()))
+        out["sum/" + name] = np.array(float(g.sum()))
+        out["sample/" + name] = g[:: max(1, g.numel() // 16)][:16].numpy()
+    return out
+
+
+def main():
+    ref = reference_loader.load()
+    for name in CASES:
+        c = cases.CASES[name]
+        inp = cases.make_inputs(name)
+        enc, ctc, _ = gen_golden.build_reference(ref, name)
+        x = inp["x"].clone().requires_grad_(True)
+        y, olens, _ = enc(x, inp["lens"])
+        tl = cases.target_lens(name, olens)
+        loss = ctc(y, olens, inp["ys_pad"], tl)
+        loss.backward()
+        grads = [("enc." + n, p.grad) for n, p in enc.named_parameters() if p.grad is not None]
+        grads += [("ctc." + n, p.grad) for n, p in ctc.named_parameters()]
+        grads.append(("input", x.grad))
+        out = summarize(grads)
+        out["loss"] = np.array(float(loss))
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", f"grad_{name}.npz"), **out)
+        print(name, float(loss), len(grads), "gradients")
+
+
+if __name__ == "__main__":
+    main()

@@ -242,3 +242,37 @@ def test_constructor_errors_match_reference_behaviour():
         MyBranchformerEncoder(input_size=80, **dict(cases.BASE_ENC, cgmlp_weight=[0.5] * 3))
     with pytest.raises(ValueError):
         CTC(41, 256, ctc_type="bogus")
+
+
+@pytest.mark.parametrize("name", ["vsr_small", "asr_tailored_small"])
+def test_oracle_port_gradients_match_reference_golden(name):
+    """Training rows of SURVEY.md §8 (encoder backward, not built yet): autograd through the
+    functional oracle port reproduces the gradients of the REAL reference modules
+    (oracle/gen_golden_grad.py) for every parameter and for the input - the oracle the backward
+    kernels will be checked against is pinned before they exist."""
+    gold = dict(np.load(os.path.join(_util.GOLDEN_DIR, f"grad_{name}.npz")))
+    _, _, sd = _util.build_dropin(name)
+    c = cases.CASES[name]
+    inp = cases.make_inputs(name)
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    x = inp["x"].clone().requires_grad_(True)
+    y, olens, _ = ref_path.branchformer_encoder(x, inp["lens"], leaf, c["cfg"])
+    tl = cases.target_lens(name, olens)
+    loss = ref_path.ctc_loss(y, olens, inp["ys_pad"], tl, leaf, "ctc.ctc_lo")
+    loss.backward()
+    assert abs(float(loss) - float(gold["loss"])) <= 1e-5 * abs(float(gold["loss"]))
+    names = sorted(k[len("norm/"):] for k in gold if k.startswith("norm/"))
+    assert len(names) > 90
+    for n in names:
+        if n == "input":
+            g = x.grad
+        elif n.startswith("enc."):
+            g = leaf[n[4:]].grad
+        else:
+            g = leaf[n].grad
+        assert g is not None, n
+        g = g.detach().double().reshape(-1)
+        norm = float(gold["norm/" + n])
+        assert abs(float(g.norm()) - norm) <= 2e-3 * norm + 1e-9, (n, float(g.norm()), norm)
+        sample = g[:: max(1, g.numel() // 16)][:16].numpy()
+        assert np.allclose(sample, gold["sample/" + n], rtol=5e-3, atol=2e-3 * norm / max(1.0, g.numel() ** 0.5) + 1e-9), n

@@ -110,3 +110,11 @@ def test_two_rank_gloo_bucketed_gradient_allreduce_equals_full_batch_gradient():
         mp.spawn(_grad_worker, args=(world, port, ret), nprocs=world, join=True)
         assert ret.get("w_ok") and ret.get("b_ok") and ret.get("extra_ok"), dict(ret)
         assert ret.get("n_collectives") >= 2, dict(ret)
+
+
+def test_grad_bucket_reducer_buckets_in_reverse_parameter_order():
+    ps = [torch.nn.Parameter(torch.zeros(n)) for n in (10, 300, 5, 200)]
+    frozen = torch.nn.Parameter(torch.zeros(7), requires_grad=False)
+    r = parallel.GradBucketReducer(ps + [frozen], bucket_mb=300 * 4 / (1 << 20))
+    assert [[p.numel() for p in b] for b in r.buckets] == [[200, 5], [300], [10]]
+    assert r.reduce() == 0          # no process group: nothing to do, gradients untouched
