@@ -329,6 +329,41 @@ int tavsr_ctc_head_bwd(const float* dlogits, const float* row_scale, int rows_pe
                        float* dw, float* db, void* workspace, long long workspace_bytes, int M,
                        int D, int V, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Backward building blocks for the encoder (training): transcriptions of
+ * oracle/bwd_formulas.py (verified against autograd on the CPU), checked on the GPU in
+ * tests/test_backward_gpu.py.  No product module calls them yet (attention / merge backward and
+ * the training-forward orchestration are missing).  All fp32, no atomics (two-stage reductions
+ * through caller-provided workspaces).
+ *   tavsr_transpose_2d    out[c][r] = in[r][c]           (wgrad operands, W^T for dgrad)
+ *   tavsr_col_sums        out[c] = sum_r a[r][c] (* b[r][c] when b != NULL)     (bias gradients)
+ *   tavsr_act_bwd         dz = dh * act'(z), act = TAVSR_ACT_*   (Swish / exact GELU / ReLU)
+ *   tavsr_layernorm_bwd   dx = LN_bwd(x; gamma, dy) (+ dres), dgamma | dbeta into one [2, D] buffer
+ *                         (dbeta == dgamma + D); D in {256, 512, 1024}; statistics recomputed
+ *   tavsr_csgu_conv_bwd   CSGU backward up to the LayerNorm: given h = [r | g], the forward's
+ *                         (mean, rstd) `stats` and du, writes dr into dh[:, :Ch], dn = d LN(g) into
+ *                         `dn`, and dconv_w [Ch,31], dconv_b [Ch]; the gate half of dh is then
+ *                         tavsr_layernorm_bwd(x = h + Ch, dy = dn, dx = dh + Ch, D = Ch)
+ * ---------------------------------------------------------------------------------------------- */
+int tavsr_transpose_2d(const float* in, long long ld_in, float* out, long long ld_out, int R, int C,
+                       void* stream);
+size_t tavsr_col_sums_workspace_bytes(int R, int C);
+int tavsr_col_sums(const float* a, long long lda, const float* b, long long ldb, float* out,
+                   void* workspace, long long workspace_bytes, int R, int C, void* stream);
+int tavsr_act_bwd(const float* z, long long ldz, const float* dh, long long ldh, float* dz,
+                  long long ldd, int M, int C, int act, void* stream);
+size_t tavsr_layernorm_bwd_workspace_bytes(int M, int D);
+int tavsr_layernorm_bwd(const float* x, long long ldx, const float* gamma, const float* dy,
+                        long long ldy, const float* dres, long long ldr, float* dx, long long ldd,
+                        float* dgamma, float* dbeta, void* workspace, long long workspace_bytes,
+                        int M, int D, float eps, void* stream);
+size_t tavsr_csgu_bwd_workspace_bytes(int B, int T, int Ch);
+int tavsr_csgu_conv_bwd(const float* h, long long ldh, const float* norm_g, const float* norm_b,
+                        const float* conv_w, const float* conv_b, const float* stats,
+                        const float* du, long long ldu, float* dh, long long lddh, float* dn,
+                        long long lddn, float* dconv_w, float* dconv_b, void* workspace,
+                        long long workspace_bytes, int B, int T, int Ch, int ksize, void* stream);
+
 /* Greedy CTC decode: collapse repeats of `amax` and drop blank (espnet_model.py:590-592,
  * maskctc_model.py:287-291).  lens == NULL collapses over all T frames (what _calc_ctc_loss does).
  * tokens [B,T] padded with -1, ntok [B]. */

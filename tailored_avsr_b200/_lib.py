@@ -117,6 +117,21 @@ SIGNATURES = {
     "tavsr_ctc_head_bwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_longlong, c_void_p, c_void_p,
                                    c_longlong, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int,
                                    c_int, c_void_p]),
+    "tavsr_transpose_2d": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_void_p]),
+    "tavsr_col_sums_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "tavsr_col_sums": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p,
+                               c_longlong, c_int, c_int, c_void_p]),
+    "tavsr_act_bwd": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int,
+                              c_int, c_int, c_void_p]),
+    "tavsr_layernorm_bwd_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "tavsr_layernorm_bwd": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_void_p,
+                                    c_longlong, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p,
+                                    c_longlong, c_int, c_int, c_float, c_void_p]),
+    "tavsr_csgu_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "tavsr_csgu_conv_bwd": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_longlong, c_void_p, c_longlong, c_void_p,
+                                    c_longlong, c_void_p, c_void_p, c_void_p, c_longlong, c_int,
+                                    c_int, c_int, c_int, c_void_p]),
     "tavsr_ctc_greedy": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                  c_void_p]),
     "tavsr_ctc_prefix_score": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -1,0 +1,409 @@
+// Backward building blocks for the encoder.
+//
+// These kernels transcribe the autograd-free formulas of oracle/bwd_formulas.py (verified against
+// torch.autograd on the CPU, tests/test_bwd_formulas_cpu.py) and are checked against them on the
+// GPU (tests/test_backward_gpu.py).  No module of the product path calls them yet: the attention
+// and merge backward kernels and the training-forward orchestration are still missing.
+//
+// All of them are memory-bound fp32 row kernels (coalesced along the channel axis, warp-shuffle or
+// two-stage reductions, no atomics: results are bit-reproducible).  The GEMM-shaped parts of the
+// backward (dgrad dX = dY.W, wgrad dW = dY^T.X) reuse the tcgen05 GEMM: tavsr_gemm_bias_act with a
+// transposed weight copy, resp. with both operands transposed by tavsr_transpose_2d.
+#include <atomic>
+
+#include "host.h"
+#include "ptx.cuh"
+
+namespace tavsr {
+extern std::atomic<long long> g_launches;
+
+namespace bwd {
+
+// ------------------------------------------------------------------------------------------------
+// out[c][r] = in[r][c]  (32 x 32 tiles through shared memory, both sides coalesced)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+transpose_kernel(const float* __restrict__ in, long long ld_in, float* __restrict__ out,
+                 long long ld_out, int R, int C) {
+  __shared__ float tile[32][33];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + tx;
+    tile[j][tx] = (r < R && c < C) ? ld_act(in + static_cast<long long>(r) * ld_in + c) : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, r = r0 + tx;
+    if (c < C && r < R) out[static_cast<long long>(c) * ld_out + r] = tile[tx][j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Column sums, two stages:  part[blk][c] = sum over the CTA's rows of a[r][c] (* b[r][c]),
+// then out[c] = sum_blk part[blk][c].  (bias gradients; LayerNorm d gamma with b = x_hat.)
+// ------------------------------------------------------------------------------------------------
+constexpr int kColRows = 256;  // rows per CTA
+
+__global__ void __launch_bounds__(128)
+col_sums_partial_kernel(const float* __restrict__ a, long long lda, const float* __restrict__ b,
+                        long long ldb, float* __restrict__ part, int R, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  const int r0 = blockIdx.y * kColRows;
+  if (c >= C) return;
+  const int r1 = r0 + kColRows < R ? r0 + kColRows : R;
+  float s = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    float v = ld_act(a + static_cast<long long>(r) * lda + c);
+    if (b != nullptr) v *= ld_act(b + static_cast<long long>(r) * ldb + c);
+    s += v;
+  }
+  part[static_cast<long long>(blockIdx.y) * C + c] = s;
+}
+
+__global__ void __launch_bounds__(128)
+col_sums_reduce_kernel(const float* __restrict__ part, int nblk, float* __restrict__ out, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int b = 0; b < nblk; ++b) s += ld_act(part + static_cast<long long>(b) * C + c);
+  out[c] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dz = dh * act'(z)   (Swish: s (1 + z (1 - s)); exact-erf GELU: Phi(z) + z phi(z); ReLU: z > 0)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float act_grad(float z, int act) {
+  switch (act) {
+    case 1: {  // swish
+      const float s = 1.0f / (1.0f + __expf(-z));
+      return s * (1.0f + z * (1.0f - s));
+    }
+    case 2: {  // gelu
+      const float phi = 0.3989422804014327f * __expf(-0.5f * z * z);
+      const float Phi = 0.5f * (1.0f + erff(z * 0.7071067811865476f));
+      return Phi + z * phi;
+    }
+    case 3: return z > 0.f ? 1.0f : 0.f;
+    default: return 1.0f;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+act_bwd_kernel(const float* __restrict__ z, long long ldz, const float* __restrict__ dh,
+               long long ldh, float* __restrict__ dz, long long ldd, int M, int C4, int act) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long total = static_cast<long long>(M) * C4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int m = static_cast<int>(i / C4), q = static_cast<int>(i % C4);
+    const float4 zz = ld_act4(reinterpret_cast<const float4*>(z + m * ldz) + q);
+    const float4 g = ld_act4(reinterpret_cast<const float4*>(dh + m * ldh) + q);
+    reinterpret_cast<float4*>(dz + m * ldd)[q] =
+        make_float4(g.x * act_grad(zz.x, act), g.y * act_grad(zz.y, act),
+                    g.z * act_grad(zz.z, act), g.w * act_grad(zz.w, act));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward, one warp per row (D = 128 * kVec), rows of a CTA = 8 warps x kLnRowsPerWarp:
+//   x_hat = (x - mu) rstd;  g = dy * gamma;  dx = rstd (g - mean(g) - x_hat mean(g x_hat)) [+ dres]
+//   per-warp partials of d gamma = sum dy x_hat and d beta = sum dy -> part[warp slot][2][D]
+// (reduced by col_sums_reduce_kernel over 2 D columns).  Statistics are recomputed two-pass.
+// ------------------------------------------------------------------------------------------------
+constexpr int kLnRowsPerWarp = 8;
+
+template <int kVec>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
+                     const float* __restrict__ dy, long long ldy, const float* __restrict__ dres,
+                     long long ldr, float* __restrict__ dx, long long ldd,
+                     float* __restrict__ part, int M, float eps) {
+  constexpr int D = 128 * kVec;
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  float4 gam[kVec];
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) gam[i] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
+  pdl_wait();
+  float4 ag[kVec], ab[kVec];
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int row_beg = (blockIdx.x * 8 + warp) * kLnRowsPerWarp;
+  if (row_beg >= M) return;  // whole warp idle: its partial slot does not exist
+  for (int rr = 0; rr < kLnRowsPerWarp; ++rr) {
+    const int row = row_beg + rr;
+    if (row >= M) break;
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * ldx);
+    const float4* yr = reinterpret_cast<const float4*>(dy + static_cast<long long>(row) * ldy);
+    float4 xv[kVec], gv[kVec];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+      xv[i] = ld_act4(xr + lane + 32 * i);
+      gv[i] = ld_act4(yr + lane + 32 * i);
+      sum += xv[i].x + xv[i].y + xv[i].z + xv[i].w;
+    }
+    const float inv_d = 1.0f / static_cast<float>(D);
+    const float mean = warp_sum(sum) * inv_d;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+      xv[i].x -= mean; xv[i].y -= mean; xv[i].z -= mean; xv[i].w -= mean;
+      ss += xv[i].x * xv[i].x + xv[i].y * xv[i].y + xv[i].z * xv[i].z + xv[i].w * xv[i].w;
+    }
+    const float rstd = rsqrtf(warp_sum(ss) * inv_d + eps);
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+      // x_hat in xv, dy in gv -> accumulate parameter gradients, then g = dy * gamma in gv
+      xv[i].x *= rstd; xv[i].y *= rstd; xv[i].z *= rstd; xv[i].w *= rstd;
+      ag[i].x += gv[i].x * xv[i].x; ag[i].y += gv[i].y * xv[i].y;
+      ag[i].z += gv[i].z * xv[i].z; ag[i].w += gv[i].w * xv[i].w;
+      ab[i].x += gv[i].x; ab[i].y += gv[i].y; ab[i].z += gv[i].z; ab[i].w += gv[i].w;
+      gv[i].x *= gam[i].x; gv[i].y *= gam[i].y; gv[i].z *= gam[i].z; gv[i].w *= gam[i].w;
+      sg += gv[i].x + gv[i].y + gv[i].z + gv[i].w;
+      sgx += gv[i].x * xv[i].x + gv[i].y * xv[i].y + gv[i].z * xv[i].z + gv[i].w * xv[i].w;
+    }
+    const float mg = warp_sum(sg) * inv_d, mgx = warp_sum(sgx) * inv_d;
+    float4* dr = reinterpret_cast<float4*>(dx + static_cast<long long>(row) * ldd);
+    const float4* rs = dres ? reinterpret_cast<const float4*>(dres + static_cast<long long>(row) * ldr)
+                            : nullptr;
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+      float4 o;
+      o.x = rstd * (gv[i].x - mg - xv[i].x * mgx);
+      o.y = rstd * (gv[i].y - mg - xv[i].y * mgx);
+      o.z = rstd * (gv[i].z - mg - xv[i].z * mgx);
+      o.w = rstd * (gv[i].w - mg - xv[i].w * mgx);
+      if (rs != nullptr) {
+        const float4 r4 = ld_act4(rs + lane + 32 * i);
+        o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+      }
+      dr[lane + 32 * i] = o;
+    }
+  }
+  // per-WARP partials of d gamma | d beta: part[(cta * 8 + warp)][2][D], summed by the reduce kernel
+  float4* pg = reinterpret_cast<float4*>(part + static_cast<long long>(blockIdx.x * 8 + warp) * 2 * D);
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) {
+    pg[lane + 32 * i] = ag[i];
+    pg[D / 4 + lane + 32 * i] = ab[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CSGU backward, convolution part.  Forward: h = [r | g], n = LN(g), c = dwconv_k(n) + cb, u = r c.
+// Given du:   dr = du c;   dc = du r;   dn[t] = sum_j w[j] dc[t - j + half];
+//             d w[j] = sum_t dc[t] n[t + j - half];   d cb = sum_t dc[t].
+// (The LayerNorm part, dg = LN_bwd(g; dn), is layernorm_bwd_kernel on the gate half of h.)
+// CTA = 128 channels x kSeg frames of one utterance; the n tile and the dc tile (kSeg + 2 half
+// rows each) live in shared memory; thread = channel.  dr goes to dh[:, :C], dn to its own buffer;
+// per-CTA partials of d w (k taps) and d cb go to part[cta][C-slab][32] (slot 31 = d cb).
+// ------------------------------------------------------------------------------------------------
+constexpr int kTaps = 31, kHalo = 15, kSeg = 64, kCh = 128, kRows = kSeg + 2 * kHalo;
+
+__global__ void __launch_bounds__(kCh)
+csgu_conv_bwd_kernel(const float* __restrict__ h, long long ldh, const float* __restrict__ norm_g,
+                     const float* __restrict__ norm_b, const float* __restrict__ conv_w,
+                     const float* __restrict__ conv_b, const float2* __restrict__ stats,
+                     const float* __restrict__ du, long long ldu, float* __restrict__ dh,
+                     long long lddh, float* __restrict__ dn, long long lddn,
+                     float* __restrict__ part, int T, int Ch) {
+  extern __shared__ float s_mem[];
+  float* s_n = s_mem;                    // [kRows][kCh]  LN(g), exactly 0 outside [0, T)
+  float* s_dc = s_mem + kRows * kCh;     // [kRows][kCh]  du * r, 0 outside [0, T)
+  pdl_launch_dependents();
+  const int c = blockIdx.x * kCh + threadIdx.x;
+  float w[kTaps];
+#pragma unroll
+  for (int k = 0; k < kTaps; ++k) w[k] = __ldg(conv_w + static_cast<long long>(c) * kTaps + k);
+  const float gam = __ldg(norm_g + c), bet = __ldg(norm_b + c), cb = __ldg(conv_b + c);
+  pdl_wait();
+  const int t0 = blockIdx.y * kSeg;
+  const int b = blockIdx.z;
+  const long long row0 = static_cast<long long>(b) * T;
+  for (int r = 0; r < kRows; ++r) {
+    const int t = t0 - kHalo + r;
+    float nv = 0.f, dcv = 0.f;
+    if (t >= 0 && t < T) {
+      const float2 st = stats[row0 + t];
+      const float g = ld_act(h + (row0 + t) * ldh + Ch + c);
+      nv = (g - st.x) * st.y * gam + bet;
+      dcv = ld_act(du + (row0 + t) * ldu + c) * ld_act(h + (row0 + t) * ldh + c);
+    }
+    s_n[r * kCh + threadIdx.x] = nv;
+    s_dc[r * kCh + threadIdx.x] = dcv;
+  }
+  // every thread only reads the column it wrote: no barrier needed
+  float dw[kTaps];
+#pragma unroll
+  for (int k = 0; k < kTaps; ++k) dw[k] = 0.f;
+  float dcb = 0.f;
+  for (int o = 0; o < kSeg; ++o) {
+    const int t = t0 + o;
+    if (t >= T) break;
+    const int rc = o + kHalo;  // tile row of frame t
+    float conv = cb, dnv = 0.f;
+    const float dct = s_dc[rc * kCh + threadIdx.x];
+#pragma unroll
+    for (int k = 0; k < kTaps; ++k) {
+      const float nk = s_n[(rc + k - kHalo) * kCh + threadIdx.x];
+      conv = fmaf(w[k], nk, conv);                                        // c[t]
+      dnv = fmaf(w[k], s_dc[(rc - k + kHalo) * kCh + threadIdx.x], dnv);  // dn[t]
+      dw[k] = fmaf(dct, nk, dw[k]);                                       // d w[k]
+    }
+    dcb += dct;
+    dh[(row0 + t) * lddh + c] = ld_act(du + (row0 + t) * ldu + c) * conv;  // dr
+    dn[(row0 + t) * lddn + c] = dnv;
+  }
+  float* pp = part + ((static_cast<long long>(b) * gridDim.y + blockIdx.y) * Ch + c) * 32;
+#pragma unroll
+  for (int k = 0; k < kTaps; ++k) pp[k] = dw[k];
+  pp[31] = dcb;
+}
+
+// sums the per-CTA partials: out_w[c][k] (k < 31), out_b[c]
+__global__ void __launch_bounds__(256)
+csgu_conv_bwd_reduce_kernel(const float* __restrict__ part, int nblk, int Ch,
+                            float* __restrict__ dconv_w, float* __restrict__ dconv_b) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int i = blockIdx.x * 256 + threadIdx.x;  // (c, slot)
+  if (i >= Ch * 32) return;
+  float s = 0.f;
+  for (int b = 0; b < nblk; ++b) s += ld_act(part + static_cast<long long>(b) * Ch * 32 + i);
+  const int c = i >> 5, k = i & 31;
+  if (k < kTaps) dconv_w[c * kTaps + k] = s; else dconv_b[c] = s;
+}
+
+}  // namespace bwd
+}  // namespace tavsr
+
+using namespace tavsr;
+
+extern "C" int tavsr_transpose_2d(const float* in, long long ld_in, float* out, long long ld_out,
+                                  int R, int C, void* stream) {
+  TAVSR_REQUIRE(R > 0 && C > 0 && in && out && ld_in >= C && ld_out >= R, "transpose: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  TAVSR_CUDA_OK(launch_kernel(bwd::transpose_kernel, dim3((C + 31) / 32, (R + 31) / 32), dim3(256), 0,
+                              s, 0, in, ld_in, out, ld_out, R, C));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+extern "C" size_t tavsr_col_sums_workspace_bytes(int R, int C) {
+  return static_cast<size_t>((R + bwd::kColRows - 1) / bwd::kColRows) * C * sizeof(float);
+}
+
+extern "C" int tavsr_col_sums(const float* a, long long lda, const float* b, long long ldb,
+                              float* out, void* workspace, long long workspace_bytes, int R, int C,
+                              void* stream) {
+  TAVSR_REQUIRE(R > 0 && C > 0 && a && out && workspace, "col_sums: bad arguments");
+  TAVSR_REQUIRE(static_cast<size_t>(workspace_bytes) >= tavsr_col_sums_workspace_bytes(R, C),
+                "col_sums: workspace too small");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int nblk = (R + bwd::kColRows - 1) / bwd::kColRows;
+  float* part = static_cast<float*>(workspace);
+  TAVSR_CUDA_OK(launch_kernel(bwd::col_sums_partial_kernel, dim3((C + 127) / 128, nblk), dim3(128), 0,
+                              s, 0, a, lda, b, ldb, part, R, C));
+  TAVSR_CUDA_OK(launch_kernel(bwd::col_sums_reduce_kernel, dim3((C + 127) / 128), dim3(128), 0, s, 0,
+                              static_cast<const float*>(part), nblk, out, C));
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  return 0;
+}
+
+extern "C" int tavsr_act_bwd(const float* z, long long ldz, const float* dh, long long ldh,
+                             float* dz, long long ldd, int M, int C, int act, void* stream) {
+  TAVSR_REQUIRE(M > 0 && C > 0 && C % 4 == 0 && ldz % 4 == 0 && ldh % 4 == 0 && ldd % 4 == 0 && z &&
+                    dh && dz && act >= 0 && act <= 3,
+                "act_bwd: bad arguments (M=%d C=%d act=%d)", M, C, act);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long total = static_cast<long long>(M) * (C / 4);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 8ll * num_sms()) blocks = 8ll * num_sms();
+  TAVSR_CUDA_OK(launch_kernel(bwd::act_bwd_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, s,
+                              0, z, ldz, dh, ldh, dz, ldd, M, C / 4, act));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+extern "C" size_t tavsr_layernorm_bwd_workspace_bytes(int M, int D) {
+  const size_t slots = (static_cast<size_t>(M) + bwd::kLnRowsPerWarp - 1) / bwd::kLnRowsPerWarp;
+  return slots * 2 * D * sizeof(float);
+}
+
+extern "C" int tavsr_layernorm_bwd(const float* x, long long ldx, const float* gamma,
+                                   const float* dy, long long ldy, const float* dres, long long ldr,
+                                   float* dx, long long ldd, float* dgamma, float* dbeta,
+                                   void* workspace, long long workspace_bytes, int M, int D,
+                                   float eps, void* stream) {
+  TAVSR_REQUIRE(M > 0 && (D == 256 || D == 512 || D == 1024) && x && gamma && dy && dx && dgamma &&
+                    dbeta && workspace,
+                "layernorm_bwd: built for D in {256, 512, 1024} (M=%d D=%d)", M, D);
+  TAVSR_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0 && ldd % 4 == 0 && (!dres || ldr % 4 == 0) &&
+                    dgamma + D == dbeta,
+                "layernorm_bwd: pitches must be multiples of 4 and dgamma / dbeta one [2, D] buffer");
+  TAVSR_REQUIRE(static_cast<size_t>(workspace_bytes) >= tavsr_layernorm_bwd_workspace_bytes(M, D),
+                "layernorm_bwd: workspace too small");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int rows_per_cta = 8 * bwd::kLnRowsPerWarp;
+  const int nblk = (M + rows_per_cta - 1) / rows_per_cta;
+  float* part = static_cast<float*>(workspace);
+#define TAVSR_LNB(V)                                                                                 \
+  TAVSR_CUDA_OK(launch_kernel(bwd::layernorm_bwd_kernel<V>, dim3(nblk), dim3(256), 0, s, 0, x, ldx,  \
+                              gamma, dy, ldy, dres, ldr, dx, ldd, part, M, eps))
+  if (D == 256) TAVSR_LNB(2); else if (D == 512) TAVSR_LNB(4); else TAVSR_LNB(8);
+#undef TAVSR_LNB
+  // [nblk][2 D] partials -> dgamma | dbeta (contiguous [2, D])
+  const int slots = (M + bwd::kLnRowsPerWarp - 1) / bwd::kLnRowsPerWarp;
+  TAVSR_CUDA_OK(launch_kernel(bwd::col_sums_reduce_kernel, dim3((2 * D + 127) / 128), dim3(128), 0, s, 0,
+                              static_cast<const float*>(part), slots, dgamma, 2 * D));
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  return 0;
+}
+
+extern "C" size_t tavsr_csgu_bwd_workspace_bytes(int B, int T, int Ch) {
+  const size_t nseg = (static_cast<size_t>(T) + bwd::kSeg - 1) / bwd::kSeg;
+  return static_cast<size_t>(B) * nseg * Ch * 32 * sizeof(float);
+}
+
+extern "C" int tavsr_csgu_conv_bwd(const float* h, long long ldh, const float* norm_g,
+                                   const float* norm_b, const float* conv_w, const float* conv_b,
+                                   const float* stats, const float* du, long long ldu, float* dh,
+                                   long long lddh, float* dn, long long lddn, float* dconv_w,
+                                   float* dconv_b, void* workspace, long long workspace_bytes, int B,
+                                   int T, int Ch, int ksize, void* stream) {
+  TAVSR_REQUIRE(ksize == bwd::kTaps, "csgu_bwd: only kernel size 31 is built (got %d)", ksize);
+  TAVSR_REQUIRE(B > 0 && T > 0 && Ch > 0 && Ch % 128 == 0 && h && norm_g && norm_b && conv_w &&
+                    conv_b && stats && du && dh && dn && dconv_w && dconv_b && workspace,
+                "csgu_bwd: bad arguments");
+  TAVSR_REQUIRE(static_cast<size_t>(workspace_bytes) >= tavsr_csgu_bwd_workspace_bytes(B, T, Ch),
+                "csgu_bwd: workspace too small");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int smem = 2 * bwd::kRows * bwd::kCh * 4;
+  static bool configured = false;
+  if (!configured) {
+    TAVSR_CUDA_OK(cudaFuncSetAttribute(bwd::csgu_conv_bwd_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int nseg = (T + bwd::kSeg - 1) / bwd::kSeg;
+  float* part = static_cast<float*>(workspace);
+  TAVSR_CUDA_OK(launch_kernel(bwd::csgu_conv_bwd_kernel, dim3(Ch / bwd::kCh, nseg, B), dim3(bwd::kCh),
+                              static_cast<size_t>(smem), s, 0, h, ldh, norm_g, norm_b, conv_w, conv_b,
+                              reinterpret_cast<const float2*>(stats), du, ldu, dh, lddh, dn, lddn, part,
+                              T, Ch));
+  TAVSR_CUDA_OK(launch_kernel(bwd::csgu_conv_bwd_reduce_kernel, dim3((Ch * 32 + 255) / 256), dim3(256), 0,
+                              s, 0, static_cast<const float*>(part), B * nseg, Ch, dconv_w, dconv_b));
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  return 0;
+}

@@ -1,0 +1,90 @@
+"""Tensor-level wrappers over the backward building blocks of the C ABI (include/tavsr.h,
+csrc/backward.cu; GPU-tested in tests/test_backward_gpu.py).  Not used by any product module yet:
+the attention / merge backward kernels and the training-forward orchestration are the next
+round's work; the arithmetic is fixed by oracle/bwd_formulas.py."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import check
+from .ops import _chk2d, _p, _stream
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty((max(1, int(nbytes)) + 3) // 4, dtype=torch.float32, device=device)
+
+
+def transpose_2d(x: torch.Tensor) -> torch.Tensor:
+    _chk2d(x, "x")
+    R, C = x.shape
+    out = torch.empty((C, R), device=x.device, dtype=torch.float32)
+    check(_lib.load().tavsr_transpose_2d(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), R, C,
+                                         _stream()), "tavsr_transpose_2d")
+    return out
+
+
+def col_sums(a: torch.Tensor, b: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _chk2d(a, "a")
+    R, C = a.shape
+    lib = _lib.load()
+    out = torch.empty((C,), device=a.device, dtype=torch.float32)
+    ws = _ws(lib.tavsr_col_sums_workspace_bytes(R, C), a.device)
+    check(lib.tavsr_col_sums(a.data_ptr(), a.stride(0), _p(b), b.stride(0) if b is not None else 0,
+                             out.data_ptr(), ws.data_ptr(), ws.numel() * 4, R, C, _stream()),
+          "tavsr_col_sums")
+    return out
+
+
+def act_bwd(z: torch.Tensor, dh: torch.Tensor, act: int) -> torch.Tensor:
+    _chk2d(z, "z")
+    _chk2d(dh, "dh")
+    M, C = z.shape
+    dz = torch.empty((M, C), device=z.device, dtype=torch.float32)
+    check(_lib.load().tavsr_act_bwd(z.data_ptr(), z.stride(0), dh.data_ptr(), dh.stride(0),
+                                    dz.data_ptr(), dz.stride(0), M, C, act, _stream()), "tavsr_act_bwd")
+    return dz
+
+
+def layernorm_bwd(x: torch.Tensor, gamma: torch.Tensor, dy: torch.Tensor, eps: float = 1e-12,
+                  dres: Optional[torch.Tensor] = None, dx: Optional[torch.Tensor] = None):
+    """Returns (dx, dgamma, dbeta); x / dy / dx may be strided row views (e.g. the gate half of h)."""
+    _chk2d(x, "x")
+    _chk2d(dy, "dy")
+    M, D = x.shape
+    lib = _lib.load()
+    if dx is None:
+        dx = torch.empty((M, D), device=x.device, dtype=torch.float32)
+    gb = torch.empty((2, D), device=x.device, dtype=torch.float32)
+    ws = _ws(lib.tavsr_layernorm_bwd_workspace_bytes(M, D), x.device)
+    check(lib.tavsr_layernorm_bwd(x.data_ptr(), x.stride(0), gamma.data_ptr(), dy.data_ptr(),
+                                  dy.stride(0), _p(dres), dres.stride(0) if dres is not None else 0,
+                                  dx.data_ptr(), dx.stride(0), gb[0].data_ptr(), gb[1].data_ptr(),
+                                  ws.data_ptr(), ws.numel() * 4, M, D, eps, _stream()),
+          "tavsr_layernorm_bwd")
+    return dx, gb[0], gb[1]
+
+
+def csgu_bwd(h: torch.Tensor, norm_g: torch.Tensor, norm_b: torch.Tensor, conv_w: torch.Tensor,
+             conv_b: torch.Tensor, stats: torch.Tensor, du: torch.Tensor, B: int, T: int,
+             eps: float = 1e-12):
+    """Full CSGU backward: (dh (B*T, 2Ch), dnorm_g, dnorm_b, dconv_w (Ch,31), dconv_b).  `stats` is
+    the forward's (mean, rstd) per frame (tavsr_csgu_fwd's scratch)."""
+    _chk2d(h, "h")
+    _chk2d(du, "du")
+    Ch = h.shape[1] // 2
+    lib = _lib.load()
+    dh = torch.empty_like(h)
+    dn = torch.empty((B * T, Ch), device=h.device, dtype=torch.float32)
+    dcw = torch.empty((Ch, conv_w.shape[-1]), device=h.device, dtype=torch.float32)
+    dcb = torch.empty((Ch,), device=h.device, dtype=torch.float32)
+    ws = _ws(lib.tavsr_csgu_bwd_workspace_bytes(B, T, Ch), h.device)
+    check(lib.tavsr_csgu_conv_bwd(h.data_ptr(), h.stride(0), norm_g.data_ptr(), norm_b.data_ptr(),
+                                  conv_w.data_ptr(), conv_b.data_ptr(), stats.data_ptr(), du.data_ptr(),
+                                  du.stride(0), dh.data_ptr(), dh.stride(0), dn.data_ptr(), dn.stride(0),
+                                  dcw.data_ptr(), dcb.data_ptr(), ws.data_ptr(), ws.numel() * 4, B, T, Ch,
+                                  conv_w.shape[-1], _stream()), "tavsr_csgu_conv_bwd")
+    _, dng, dnb = layernorm_bwd(h[:, Ch:], norm_g, dn, eps=eps, dx=dh[:, Ch:])
+    return dh, dng, dnb, dcw, dcb
