@@ -130,3 +130,34 @@ def test_learned_ave_merge_bwd_matches_autograd_through_the_port():
         assert _close(db, leaf[f"l.weight_proj{tag}.weight"].grad.reshape(-1), 1e-8)
         assert _close(dc.reshape(1), leaf[f"l.pooling_proj{tag}.bias"].grad, 1e-8)
         assert _close(de.reshape(1), leaf[f"l.weight_proj{tag}.bias"].grad, 1e-8)
+
+
+def test_whole_block_manual_backward_matches_autograd():
+    """The hand-composed backward of one two-branch learned_ave block (oracle/manual_backward.py:
+    saved tensors, residual joins, merge split) equals autograd on ref_path.branchformer_layer for
+    the input and for every one of the block's parameters."""
+    from oracle import manual_backward, synth
+    from tailored_avsr_b200.encoder.branchformer.encoder import MyBranchformerEncoder
+    from oracle import cases
+    cfg = dict(cases.BASE_ENC, num_blocks=1, input_layer=None, output_size=32, attention_heads=2,
+               linear_units=48, cgmlp_linear_units=64, cgmlp_conv_kernel=31)
+    enc = MyBranchformerEncoder(input_size=32, **cfg)
+    sd = {k_: v_.double() for k_, v_ in synth.fill_module(enc, seed=3).items()}
+    B, T, D = 2, 19, 32
+    lens = torch.tensor([19, 11])
+    mask = ref_path.make_valid_mask(lens, T)
+    pos = ref_path.rel_pos_emb(T, D).double()
+    x = torch.randn(B, T, D, dtype=D64)
+    dy = torch.randn(B, T, D, dtype=D64)
+    leaf = {k_: v_.clone().requires_grad_(True) for k_, v_ in sd.items()}
+    xg = x.clone().requires_grad_(True)
+    y_ref, _ = ref_path.branchformer_layer(xg, pos, mask, leaf, "encoders.0", heads=2, kernel=31)
+    y_ref.backward(dy)
+    y, dx, grads = manual_backward.layer_forward_backward(x, pos, mask, sd, "encoders.0", dy, heads=2)
+    assert _close(y, y_ref.detach(), 1e-9)
+    assert _close(dx, xg.grad, 1e-7)
+    block = [k_ for k_ in sd if k_.startswith("encoders.0.")]
+    assert len(block) >= 40
+    for k_ in block:
+        assert k_ in grads, k_
+        assert _close(grads[k_].reshape(leaf[k_].grad.shape), leaf[k_].grad, 1e-7), k_
