@@ -146,3 +146,70 @@ def learned_ave_merge_bwd(x1, x2, lens, a1, c1, b1, e1, a2, c2, b2, e2, dm_or_w:
         dc = dsc.sum()
         outs.append((dx, da, dc, db, de))
     return outs
+
+
+def relpos_attn_core_fwd_stats(q, k, v, p, u, vb, lens):
+    """Forward of the attention core returning what a flash-style backward keeps: the output o and
+    the per-row log-sum-exp L (natural log, of the scaled masked scores)."""
+    B, H, T, d = q.shape
+    scale = 1.0 / math.sqrt(d)
+    qu = q + u[None, :, None, :]
+    qv = q + vb[None, :, None, :]
+    idx = (T - 1 - torch.arange(T).unsqueeze(1) + torch.arange(T).unsqueeze(0))
+    s = (qu @ k.transpose(-2, -1) + (qv @ p.transpose(-2, -1)[None]).gather(-1, idx.expand(B, H, T, T))) * scale
+    inv = (torch.arange(T)[None, :] >= lens[:, None])[:, None, None, :]
+    s = s.masked_fill(inv, float("-inf"))
+    lse = torch.logsumexp(s, dim=-1)                                     # -inf for all-masked rows
+    P = torch.nan_to_num(torch.exp(s - lse.unsqueeze(-1)))
+    return P @ v, lse
+
+
+def relpos_attn_core_bwd_tiled(q, k, v, p, u, vb, lens, do, o, lse, tq: int = 4, tk: int = 4):
+    """The same gradients as relpos_attn_core_bwd computed the way a tiled (flash-style, tensor-core)
+    kernel will: loop over (query tile, key tile) pairs, recompute the scores of the pair from Q, K
+    and the BAND of relative positions the pair touches - band column c of the pair (i0, j0) is
+    relative-position row rbase + c with rbase = T - tq - i0 + j0, exactly the forward kernel's
+    indexing (attention_sm100.cu) - take P = exp(s - L_i) from the saved row log-sum-exp, use
+    D_i = sum_d do_i o_i instead of a row reduction over P dP, and accumulate
+    dq (per query tile), dk / dv (per key tile) and dp (per band row)."""
+    B, H, T, d = q.shape
+    scale = 1.0 / math.sqrt(d)
+    qu = q + u[None, :, None, :]
+    qv = q + vb[None, :, None, :]
+    Drow = (do * o).sum(-1)                                              # (B,H,T)
+    dqu = torch.zeros_like(q)
+    dqv = torch.zeros_like(q)
+    dk = torch.zeros_like(k)
+    dv = torch.zeros_like(v)
+    dp = torch.zeros_like(p)
+    nband = tq + tk - 1
+    for i0 in range(0, T, tq):
+        i1 = min(i0 + tq, T)
+        for j0 in range(0, T, tk):
+            j1 = min(j0 + tk, T)
+            rbase = T - tq - i0 + j0                                     # band column 0 <-> row rbase
+            rows = torch.arange(rbase, rbase + nband).clamp(0, 2 * T - 2)
+            band = p[:, rows, :]                                         # (H, nband, d)
+            S = qu[:, :, i0:i1] @ k[:, :, j0:j1].transpose(-2, -1)       # (B,H,ti,tj)
+            R = qv[:, :, i0:i1] @ band.transpose(-2, -1)[None]           # (B,H,ti,nband)
+            # rel-shift inside the pair: key jj of query ii sits at band column (tq - 1 - ii) + jj
+            ii = torch.arange(i1 - i0).unsqueeze(1)
+            jj = torch.arange(j1 - j0).unsqueeze(0)
+            col = (tq - 1 - ii + jj)                                     # (ti,tj)
+            s = (S + R.gather(-1, col.expand(B, H, i1 - i0, j1 - j0))) * scale
+            keys = torch.arange(j0, j1)
+            masked = (keys[None, :] >= lens[:, None])[:, None, None, :]
+            L = lse[:, :, i0:i1].unsqueeze(-1)
+            Pt = torch.where(masked | torch.isinf(L), torch.zeros_like(s), torch.exp(s - L))
+            dv[:, :, j0:j1] += Pt.transpose(-2, -1) @ do[:, :, i0:i1]
+            dP = do[:, :, i0:i1] @ v[:, :, j0:j1].transpose(-2, -1)
+            dS = Pt * (dP - Drow[:, :, i0:i1].unsqueeze(-1)) * scale
+            dqu[:, :, i0:i1] += dS @ k[:, :, j0:j1]
+            dk[:, :, j0:j1] += dS.transpose(-2, -1) @ qu[:, :, i0:i1]
+            dR = torch.zeros_like(R)
+            dR.scatter_add_(-1, col.expand(B, H, i1 - i0, j1 - j0), dS)
+            dqv[:, :, i0:i1] += dR @ band[None]
+            contrib = (dR.transpose(-2, -1) @ qv[:, :, i0:i1]).sum(0)    # (H, nband, d)
+            inside = (torch.arange(rbase, rbase + nband) >= 0) & (torch.arange(rbase, rbase + nband) <= 2 * T - 2)
+            dp.index_add_(1, rows[inside], contrib[:, inside])
+    return dqu + dqv, dk, dv, dp, dqu.sum((0, 2)), dqv.sum((0, 2))

@@ -161,3 +161,20 @@ def test_whole_block_manual_backward_matches_autograd():
     for k_ in block:
         assert k_ in grads, k_
         assert _close(grads[k_].reshape(leaf[k_].grad.shape), leaf[k_].grad, 1e-7), k_
+
+
+def test_tiled_attention_backward_with_band_indexing_equals_the_dense_formula():
+    """Flash-style backward over (query tile, key tile) pairs with the forward kernel's band
+    indexing (rbase = T - tq - i0 + j0), saved log-sum-exp and D_i = do_i . o_i equals the dense
+    formula - ragged T (not a multiple of the tiles), masked keys and an empty utterance included."""
+    B, H, T, d = 3, 2, 11, 4
+    lens = torch.tensor([11, 6, 0])
+    q, k, v, do = (torch.randn(B, H, T, d, dtype=D64) for _ in range(4))
+    p = torch.randn(H, 2 * T - 1, d, dtype=D64)
+    u, vb = torch.randn(H, d, dtype=D64) * 0.3, torch.randn(H, d, dtype=D64) * 0.3
+    dense = bw.relpos_attn_core_bwd(q, k, v, p, u, vb, lens, do)
+    o, lse = bw.relpos_attn_core_fwd_stats(q, k, v, p, u, vb, lens)
+    for tq, tk in ((4, 4), (4, 8), (16, 16)):
+        tiled = bw.relpos_attn_core_bwd_tiled(q, k, v, p, u, vb, lens, do, o, lse, tq=tq, tk=tk)
+        for a, b in zip(tiled, dense):
+            assert _close(a, b, 1e-9), (tq, tk)
