@@ -161,3 +161,40 @@ def layer_forward_backward(x, pos_emb, mask, sd: SD, prefix: str, dy, heads: int
     dxn0 = _ffn_bwd(xn0, z1, h1, 0.5 * dx_a, sd, P + ".feed_forward_macaron", g)
     dx = dx_a + _ln_bwd(x, dxn0, sd, P + ".norm_ff_macaron", g)
     return y, dx, g
+
+
+def encoder_forward_backward(xs, ilens, sd: SD, cfg: dict, dout_fn):
+    """Whole single-stream encoder (linear front end, two-branch learned_ave blocks, swish FFN):
+    forward, then the backward chained by hand through after_norm, the blocks in reverse (each
+    block's backward is layer_forward_backward on its saved input) and the embed (Linear +
+    LayerNorm(1e-5) + x sqrt(d)).  `dout_fn(out, olens)` returns d loss / d out (the CTC backward,
+    which already exists as a CUDA kernel).  Returns (out, grads incl. "input")."""
+    assert cfg.get("input_layer") == "linear" and cfg.get("merge_method", "learned_ave") == "learned_ave"
+    d = cfg.get("output_size", 256)
+    n = cfg.get("num_blocks", 12)
+    heads = cfg.get("attention_heads", 4)
+    T = xs.shape[1]
+    masks = ref_path.make_valid_mask(ilens, T)
+    e0 = F.linear(xs, sd["embed.0.weight"], sd["embed.0.bias"])
+    e1 = F.layer_norm(e0, (d,), sd["embed.1.weight"], sd["embed.1.bias"], 1e-5)
+    x = e1 * math.sqrt(d)
+    pos = ref_path.rel_pos_emb(T, d).to(xs.dtype)
+    block_in = []
+    for l in range(n):
+        block_in.append(x)
+        x, _ = ref_path.branchformer_layer(x, pos, masks, sd, f"encoders.{l}", heads=heads,
+                                           kernel=cfg.get("cgmlp_conv_kernel", 31), act="swish")
+    out = _ln(x, sd, "after_norm")
+    g: Dict[str, torch.Tensor] = {}
+    dx = _ln_bwd(x, dout_fn(out, masks.squeeze(1).sum(1)), sd, "after_norm", g)
+    for l in reversed(range(n)):
+        _, dx, gl = layer_forward_backward(block_in[l], pos, masks, sd, f"encoders.{l}", dx, heads=heads)
+        for k_, v_ in gl.items():
+            _acc(g, k_, v_)
+    de1 = dx * math.sqrt(d)
+    de0 = _ln_bwd(e0, de1, sd, "embed.1", g, eps=1e-5)
+    dxs, dw, db = bw.linear_bwd(xs, sd["embed.0.weight"], de0)
+    _acc(g, "embed.0.weight", dw)
+    _acc(g, "embed.0.bias", db)
+    g["input"] = dxs
+    return out, g

@@ -178,3 +178,44 @@ def test_tiled_attention_backward_with_band_indexing_equals_the_dense_formula():
         tiled = bw.relpos_attn_core_bwd_tiled(q, k, v, p, u, vb, lens, do, o, lse, tq=tq, tk=tk)
         for a, b in zip(tiled, dense):
             assert _close(a, b, 1e-9), (tq, tk)
+
+
+def test_whole_encoder_manual_backward_matches_the_live_reference_gradients():
+    """Embed + 2 blocks + after_norm chained by hand (oracle/manual_backward.py) with the CTC
+    gradient on top reproduce the gradients of the REAL reference modules (tests/golden/
+    grad_vsr_small.npz, oracle/gen_golden_grad.py) for the input and every encoder parameter."""
+    import os
+
+    import numpy as np
+    from oracle import cases, manual_backward
+    from . import _util
+    name = "vsr_small"
+    gold = dict(np.load(os.path.join(_util.GOLDEN_DIR, f"grad_{name}.npz")))
+    _, _, sd32 = _util.build_dropin(name)
+    sd = {k_: v_.double() for k_, v_ in sd32.items()}
+    c = cases.CASES[name]
+    inp = cases.make_inputs(name)
+
+    def dout_fn(out, olens):
+        o = out.detach().clone().requires_grad_(True)
+        tl = cases.target_lens(name, olens)
+        ref_path.ctc_loss(o, olens, inp["ys_pad"], tl, sd, "ctc.ctc_lo").backward()
+        return o.grad
+
+    _, grads = manual_backward.encoder_forward_backward(inp["x"].double(), inp["lens"], sd, c["cfg"], dout_fn)
+    names = [k_[len("norm/"):] for k_ in gold if k_.startswith("norm/") and not k_.startswith("norm/ctc.")]
+    assert len(names) > 90
+    for n_ in names:
+        key = "input" if n_ == "input" else n_[len("enc."):]
+        assert key in grads, key
+        gflat = grads[key].reshape(-1)
+        norm = float(gold["norm/" + n_])
+        if norm < 1e-7:
+            # mathematically zero gradient (attn.linear_k.bias shifts every key's score of a query
+            # by the same amount: the softmax does not see it); the reference's value is fp32 noise
+            assert float(gflat.norm()) < 1e-7, n_
+            continue
+        assert abs(float(gflat.norm()) - norm) <= 2e-3 * norm + 1e-9, (n_, float(gflat.norm()), norm)
+        sample = gflat[:: max(1, gflat.numel() // 16)][:16].numpy()
+        assert np.allclose(sample, gold["sample/" + n_], rtol=5e-3,
+                           atol=2e-3 * norm / max(1.0, gflat.numel() ** 0.5) + 1e-9), n_
