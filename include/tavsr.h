@@ -364,6 +364,21 @@ int tavsr_csgu_conv_bwd(const float* h, long long ldh, const float* norm_g, cons
                         long long lddn, float* dconv_w, float* dconv_b, void* workspace,
                         long long workspace_bytes, int B, int T, int Ch, int ksize, void* stream);
 
+/* learned_ave merge backward (encoder_layer.py:241-291 up to m = w1 x1 + w2 x2), D == 256,
+ * T <= 2048.  EXPERIMENTAL: written after the round's GPU budget was spent, NOT yet run on a GPU
+ * (its test needs TAVSR_TEST_BWD_WIP=1).  Given dm = d loss / d m: dx1, dx2 and
+ * grads = [da1 | db1 | da2 | db2] (4 x 256: pooling_projK.weight, weight_projK.weight) followed by
+ * [dc1, de1, dc2, de2] (their biases), 1028 floats.  aK / bK are the pooling_projK / weight_projK
+ * weight vectors, cK / eK their biases.  Arithmetic: oracle/bwd_formulas.py::learned_ave_merge_bwd. */
+size_t tavsr_merge_learned_ave_bwd_workspace_bytes(int B);
+int tavsr_merge_learned_ave_bwd(const float* x1, long long ld1, const float* x2, long long ld2,
+                                const float* dm, long long ldm, const int32_t* lens,
+                                const float* a1, float c1, const float* b1, float e1,
+                                const float* a2, float c2, const float* b2, float e2, float* dx1,
+                                long long ldd1, float* dx2, long long ldd2, float* grads,
+                                void* workspace, long long workspace_bytes, int B, int T, int D,
+                                void* stream);
+
 /* Greedy CTC decode: collapse repeats of `amax` and drop blank (espnet_model.py:590-592,
  * maskctc_model.py:287-291).  lens == NULL collapses over all T frames (what _calc_ctc_loss does).
  * tokens [B,T] padded with -1, ntok [B]. */

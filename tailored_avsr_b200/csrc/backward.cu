@@ -285,6 +285,204 @@ csgu_conv_bwd_reduce_kernel(const float* __restrict__ part, int nblk, int Ch,
   if (k < kTaps) dconv_w[c * kTaps + k] = s; else dconv_b[c] = s;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// learned_ave merge backward (oracle/bwd_formulas.py::learned_ave_merge_bwd), one CTA of 256 threads
+// per utterance, D == 256.  NOT YET RUN ON A GPU (written after the round's GPU budget was spent):
+// its test is gated behind TAVSR_TEST_BWD_WIP=1.
+//   forward:  score_i[t] = (x_i[t].a_i + c_i)/sqrt(D) (t < len), s_i = softmax_t, pooled_i = sum_t
+//             s_i[t] x_i[t], omega_i = pooled_i.b_i + e_i, w = softmax(omega), m = w1 x1 + w2 x2
+//   given dm: dw_i = sum_{t,d} dm x_i (ALL T frames: the sum m is dense), domega = w (dw - w.dw),
+//             dpool_i = domega_i b_i, ds_i[t] = x_i[t].dpool_i, dsc_i = s_i (ds_i - s_i.ds_i)/sqrt(D)
+//             dx_i[t] = w_i dm[t] + s_i[t] dpool_i + dsc_i[t] a_i
+//             da_i = sum_t dsc_i[t] x_i[t], dc_i = sum_t dsc_i[t], db_i = domega_i pooled_i, de_i = domega_i
+// Row dots run warp-per-row, column accumulations thread-per-column (coalesced either way).
+// Per-utterance parameter-gradient partials: part[b][4][D] = (da1, db1, da2, db2), part_s[b][4] =
+// (dc1, de1, dc2, de2); the caller reduces them over b with tavsr_col_sums' reduce kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMergeT = 2048;  // frames per utterance held in shared memory
+
+__device__ __forceinline__ float block_sum_256(float v, float* s_red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r += s_red[i];
+  return r;
+}
+__device__ __forceinline__ float block_max_256(float v, float* s_red) {
+  v = warp_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = s_red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) r = fmaxf(r, s_red[i]);
+  return r;
+}
+
+struct MergeBwdParams {
+  const float* x1; const float* x2; const float* dm;
+  long long ld1, ld2, ldm;
+  const int32_t* lens;
+  const float* a1; const float* b1; const float* a2; const float* b2;  // [D] vectors
+  float c1, e1, c2, e2;                                                // scalars (biases)
+  float* dx1; float* dx2;
+  long long ldd1, ldd2;
+  float* part;    // [B][4][D]
+  float* part_s;  // [B][4]
+  int T;
+};
+
+__global__ void __launch_bounds__(256)
+merge_learned_ave_bwd_kernel(const MergeBwdParams p) {
+  constexpr int D = 256;
+  extern __shared__ float s_mem[];
+  float* s_s = s_mem;                  // [2][T]  scores -> softmax weights s_i[t]
+  float* s_d = s_mem + 2 * p.T;        // [2][T]  ds_i[t] -> dsc_i[t]
+  __shared__ float s_vec[4][D];        // a1, a2 -> later dpool1, dpool2 in rows 2, 3
+  __shared__ float s_red[8];
+  pdl_launch_dependents();
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t lane = lane_id();
+  const int T = p.T;
+  s_vec[0][tid] = __ldg(p.a1 + tid);
+  s_vec[1][tid] = __ldg(p.a2 + tid);
+  const float bb1 = __ldg(p.b1 + tid), bb2 = __ldg(p.b2 + tid);
+  pdl_wait();
+  int len = p.lens ? p.lens[b] : T;
+  len = len < 0 ? 0 : (len > T ? T : len);
+  const long long row0 = static_cast<long long>(b) * T;
+  const float rs = rsqrtf(static_cast<float>(D));
+  __syncthreads();
+  // ---- phase 1 (warp per row): scores and the dense dw_i = sum dm . x_i ----
+  float dw1 = 0.f, dw2 = 0.f;
+  for (int t = warp; t < T; t += 8) {
+    const float4* r1 = reinterpret_cast<const float4*>(p.x1 + (row0 + t) * p.ld1);
+    const float4* r2 = reinterpret_cast<const float4*>(p.x2 + (row0 + t) * p.ld2);
+    const float4* rm = reinterpret_cast<const float4*>(p.dm + (row0 + t) * p.ldm);
+    float sa1 = 0.f, sa2 = 0.f, sm1 = 0.f, sm2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float4 v1 = ld_act4(r1 + lane + 32 * i), v2 = ld_act4(r2 + lane + 32 * i);
+      const float4 g = ld_act4(rm + lane + 32 * i);
+      const float4 w1 = *reinterpret_cast<const float4*>(&s_vec[0][4 * (lane + 32 * i)]);
+      const float4 w2 = *reinterpret_cast<const float4*>(&s_vec[1][4 * (lane + 32 * i)]);
+      sa1 += v1.x * w1.x + v1.y * w1.y + v1.z * w1.z + v1.w * w1.w;
+      sa2 += v2.x * w2.x + v2.y * w2.y + v2.z * w2.z + v2.w * w2.w;
+      sm1 += v1.x * g.x + v1.y * g.y + v1.z * g.z + v1.w * g.w;
+      sm2 += v2.x * g.x + v2.y * g.y + v2.z * g.z + v2.w * g.w;
+    }
+    sa1 = warp_sum(sa1); sa2 = warp_sum(sa2);
+    dw1 += warp_sum(sm1); dw2 += warp_sum(sm2);   // identical in every lane of the warp
+    if (lane == 0) {
+      s_s[t] = (sa1 + p.c1) * rs;
+      s_s[T + t] = (sa2 + p.c2) * rs;
+    }
+  }
+  // one lane per warp carries the warp's dw partial into the block sums
+  dw1 = block_sum_256(lane == 0 ? dw1 : 0.f, s_red);
+  dw2 = block_sum_256(lane == 0 ? dw2 : 0.f, s_red);
+  // ---- phase 2: masked softmax over t < len for both branches ----
+  float se[2];
+#pragma unroll
+  for (int br = 0; br < 2; ++br) {
+    float* sc = s_s + br * T;
+    float mx = -INFINITY;
+    for (int t = tid; t < len; t += 256) mx = fmaxf(mx, sc[t]);
+    mx = block_max_256(mx, s_red);
+    float sum = 0.f;
+    for (int t = tid; t < T; t += 256) {
+      const float e = t < len ? expf(sc[t] - mx) : 0.f;
+      sc[t] = e;
+      sum += e;
+    }
+    se[br] = block_sum_256(sum, s_red);
+    const float inv = len > 0 ? 1.0f / se[br] : 0.f;
+    for (int t = tid; t < T; t += 256) sc[t] *= inv;
+  }
+  __syncthreads();
+  // ---- phase 3 (thread per column): pooled_i[d], omega, w, domega, dpool ----
+  float pool1 = 0.f, pool2 = 0.f;
+  for (int t = 0; t < len; ++t) {
+    pool1 = fmaf(s_s[t], ld_act(p.x1 + (row0 + t) * p.ld1 + tid), pool1);
+    pool2 = fmaf(s_s[T + t], ld_act(p.x2 + (row0 + t) * p.ld2 + tid), pool2);
+  }
+  const float om1 = block_sum_256(pool1 * bb1, s_red) + p.e1;
+  const float om2 = block_sum_256(pool2 * bb2, s_red) + p.e2;
+  const float mo = fmaxf(om1, om2);
+  const float e1 = expf(om1 - mo), e2 = expf(om2 - mo);
+  const float w1 = e1 / (e1 + e2), w2 = e2 / (e1 + e2);
+  const float wd = w1 * dw1 + w2 * dw2;
+  const float dom1 = w1 * (dw1 - wd), dom2 = w2 * (dw2 - wd);
+  const float dp1 = dom1 * bb1, dp2 = dom2 * bb2;   // dpool_i[d]
+  s_vec[2][tid] = dp1;
+  s_vec[3][tid] = dp2;
+  float* pp = p.part + static_cast<long long>(b) * 4 * D;
+  pp[1 * D + tid] = dom1 * pool1;  // db1
+  pp[3 * D + tid] = dom2 * pool2;  // db2
+  __syncthreads();
+  // ---- phase 4 (warp per row): ds_i[t] = x_i[t] . dpool_i ----
+  for (int t = warp; t < len; t += 8) {
+    const float4* r1 = reinterpret_cast<const float4*>(p.x1 + (row0 + t) * p.ld1);
+    const float4* r2 = reinterpret_cast<const float4*>(p.x2 + (row0 + t) * p.ld2);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float4 v1 = ld_act4(r1 + lane + 32 * i), v2 = ld_act4(r2 + lane + 32 * i);
+      const float4 q1 = *reinterpret_cast<const float4*>(&s_vec[2][4 * (lane + 32 * i)]);
+      const float4 q2 = *reinterpret_cast<const float4*>(&s_vec[3][4 * (lane + 32 * i)]);
+      s1 += v1.x * q1.x + v1.y * q1.y + v1.z * q1.z + v1.w * q1.w;
+      s2 += v2.x * q2.x + v2.y * q2.y + v2.z * q2.z + v2.w * q2.w;
+    }
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (lane == 0) { s_d[t] = s1; s_d[T + t] = s2; }
+  }
+  __syncthreads();
+  // ---- phase 5: dsc_i[t] = s_i[t] (ds_i[t] - sum_t s_i ds_i) / sqrt(D); dc_i = sum_t dsc_i[t] ----
+  float dcs[2];
+#pragma unroll
+  for (int br = 0; br < 2; ++br) {
+    float acc = 0.f;
+    for (int t = tid; t < len; t += 256) acc += s_s[br * T + t] * s_d[br * T + t];
+    const float sds = block_sum_256(acc, s_red);
+    float dc = 0.f;
+    for (int t = tid; t < T; t += 256) {
+      const float v = t < len ? s_s[br * T + t] * (s_d[br * T + t] - sds) * rs : 0.f;
+      s_d[br * T + t] = v;
+      dc += v;
+    }
+    dcs[br] = block_sum_256(dc, s_red);
+  }
+  __syncthreads();
+  // ---- phase 6 (thread per column): dx_i and da_i ----
+  const float av1 = s_vec[0][tid], av2 = s_vec[1][tid];
+  float da1 = 0.f, da2 = 0.f;
+  for (int t = 0; t < T; ++t) {
+    const float g = ld_act(p.dm + (row0 + t) * p.ldm + tid);
+    float o1 = w1 * g, o2 = w2 * g;
+    if (t < len) {
+      const float v1 = ld_act(p.x1 + (row0 + t) * p.ld1 + tid);
+      const float v2 = ld_act(p.x2 + (row0 + t) * p.ld2 + tid);
+      const float k1 = s_d[t], k2 = s_d[T + t];
+      o1 += s_s[t] * dp1 + k1 * av1;
+      o2 += s_s[T + t] * dp2 + k2 * av2;
+      da1 = fmaf(k1, v1, da1);
+      da2 = fmaf(k2, v2, da2);
+    }
+    p.dx1[(row0 + t) * p.ldd1 + tid] = o1;
+    p.dx2[(row0 + t) * p.ldd2 + tid] = o2;
+  }
+  pp[0 * D + tid] = da1;
+  pp[2 * D + tid] = da2;
+  if (tid == 0) {
+    float* ps = p.part_s + b * 4;
+    ps[0] = dcs[0]; ps[1] = dom1; ps[2] = dcs[1]; ps[3] = dom2;
+  }
+}
+
 }  // namespace bwd
 }  // namespace tavsr
 
@@ -405,5 +603,52 @@ extern "C" int tavsr_csgu_conv_bwd(const float* h, long long ldh, const float* n
   TAVSR_CUDA_OK(launch_kernel(bwd::csgu_conv_bwd_reduce_kernel, dim3((Ch * 32 + 255) / 256), dim3(256), 0,
                               s, 0, static_cast<const float*>(part), B * nseg, Ch, dconv_w, dconv_b));
   g_launches.fetch_add(2, std::memory_order_relaxed);
+  return 0;
+}
+
+extern "C" size_t tavsr_merge_learned_ave_bwd_workspace_bytes(int B) {
+  return static_cast<size_t>(B) * (4 * 256 + 4) * sizeof(float);
+}
+
+// EXPERIMENTAL, not yet run on a GPU (see the kernel's header comment).
+// grads: [4][256] = (da1, db1, da2, db2) then [4] = (dc1, de1, dc2, de2), i.e. 1028 floats.
+extern "C" int tavsr_merge_learned_ave_bwd(const float* x1, long long ld1, const float* x2,
+                                           long long ld2, const float* dm, long long ldm,
+                                           const int32_t* lens, const float* a1, float c1,
+                                           const float* b1, float e1, const float* a2, float c2,
+                                           const float* b2, float e2, float* dx1, long long ldd1,
+                                           float* dx2, long long ldd2, float* grads, void* workspace,
+                                           long long workspace_bytes, int B, int T, int D,
+                                           void* stream) {
+  TAVSR_REQUIRE(B > 0 && T > 0 && T <= bwd::kMergeT && D == 256,
+                "merge_bwd: built for D == 256, T <= %d (B=%d T=%d D=%d)", bwd::kMergeT, B, T, D);
+  TAVSR_REQUIRE(x1 && x2 && dm && a1 && b1 && a2 && b2 && dx1 && dx2 && grads && workspace,
+                "merge_bwd: null pointer");
+  TAVSR_REQUIRE(ld1 % 4 == 0 && ld2 % 4 == 0 && ldm % 4 == 0, "merge_bwd: pitches must be multiples of 4");
+  TAVSR_REQUIRE(static_cast<size_t>(workspace_bytes) >= tavsr_merge_learned_ave_bwd_workspace_bytes(B),
+                "merge_bwd: workspace too small");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  bwd::MergeBwdParams p;
+  p.x1 = x1; p.x2 = x2; p.dm = dm; p.ld1 = ld1; p.ld2 = ld2; p.ldm = ldm; p.lens = lens;
+  p.a1 = a1; p.b1 = b1; p.a2 = a2; p.b2 = b2; p.c1 = c1; p.e1 = e1; p.c2 = c2; p.e2 = e2;
+  p.dx1 = dx1; p.dx2 = dx2; p.ldd1 = ldd1; p.ldd2 = ldd2;
+  p.part = static_cast<float*>(workspace);
+  p.part_s = p.part + static_cast<size_t>(B) * 4 * 256;
+  p.T = T;
+  const int smem = 4 * T * 4;
+  static int configured = 0;
+  if (configured < smem) {
+    TAVSR_CUDA_OK(cudaFuncSetAttribute(bwd::merge_learned_ave_bwd_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  TAVSR_CUDA_OK(launch_kernel(bwd::merge_learned_ave_bwd_kernel, dim3(B), dim3(256),
+                              static_cast<size_t>(smem), s, 0, p));
+  // reduce the per-utterance partials over b: [B][1024] -> grads[0:1024], [B][4] -> grads[1024:1028]
+  TAVSR_CUDA_OK(launch_kernel(bwd::col_sums_reduce_kernel, dim3(8), dim3(128), 0, s, 0,
+                              static_cast<const float*>(p.part), B, grads, 1024));
+  TAVSR_CUDA_OK(launch_kernel(bwd::col_sums_reduce_kernel, dim3(1), dim3(128), 0, s, 0,
+                              static_cast<const float*>(p.part_s), B, grads + 1024, 4));
+  g_launches.fetch_add(3, std::memory_order_relaxed);
   return 0;
 }
