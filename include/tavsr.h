@@ -41,9 +41,18 @@ extern "C" {
 #define TAVSR_ACT_GELU 2
 #define TAVSR_ACT_RELU 3
 
-/* operand dtype of the tensor-core GEMMs */
+/* `dtype` arguments: operand storage of the tensor-core products in the low byte, OR-ed with flags
+ * saying which OUTPUTS are stored as bf16 (only with bf16 operands: outputs that feed the next
+ * tensor-core product are bf16, the residual stream / encoder output stay fp32).
+ * "tf32x3" (fp32-class accuracy on the TF32 pipe) is composed by the caller: tavsr_split_tf32
+ * writes [hi | hi | lo] / [hi | lo | hi] operand triples and the product runs as a TF32 GEMM over
+ * the tripled reduction axis (a_hi.b_hi + a_hi.b_lo + a_lo.b_hi). */
 #define TAVSR_DT_TF32 0 /* fp32 storage, kind::tf32 */
 #define TAVSR_DT_BF16 1 /* bf16 storage, kind::f16  */
+#define TAVSR_DT_MASK 0xff
+#define TAVSR_DT_OUT_BF16 0x100 /* main output (y / out_main / ctx / u) stored as bf16 */
+#define TAVSR_DT_LNA_BF16 0x200 /* out_lnA stored as bf16 */
+#define TAVSR_DT_LNB_BF16 0x400 /* out_lnB stored as bf16 */
 
 int tavsr_version(void);
 const char* tavsr_last_error(void);
@@ -59,23 +68,13 @@ long long tavsr_launch_count(void);
  * encoder_layer.py:194,314), cgMLP channel_proj1 + GELU (encoder_layer.py:220), fused
  * linear_q|k|v (encoder_layer.py:208), linear_pos.
  * round_out != 0 rounds Y to TF32 (legal when Y only feeds further tensor-core products).
- * Requirements: K % 4 == 0, N % 4 == 0, ld* % 4 == 0 (16-byte TMA strides), 16-byte aligned bases.
+ * dtype: TAVSR_DT_TF32 (fp32 x / w / y) or TAVSR_DT_BF16 (bf16 x / w; y fp32, or bf16 with
+ * TAVSR_DT_OUT_BF16).  Requirements: 16-byte row pitches and bases (K % 4 / N % 4 elements in
+ * fp32, % 8 in bf16).
  * ---------------------------------------------------------------------------------------------- */
 int tavsr_gemm_bias_act(const void* x, long long ldx, const void* w, long long ldw,
                         const float* bias, void* y, long long ldy, int M, int N, int K, int act,
                         int round_out, int dtype, void* stream);
-
-/* Same GEMM; additionally the epilogue emits per-row PARTIAL LayerNorm statistics of the stored
- * output columns [stats_col0, N): stats_out[m * parts + p] = (mean, M2 = sum (y - mean)^2) over the
- * p-th group of *stats_part_width consecutive columns (parts = (N - stats_col0) / width; the width
- * is the library's tile choice, 64 or 128, returned through stats_part_width; size stats_out for
- * width 64).  Consumed by tavsr_csgu_fwd_fused: the LayerNorm(Ch) statistics of the cgMLP gate half
- * (espnet ConvolutionalSpatialGatingUnit.norm, reached from encoder_layer.py:220) cost no extra
- * pass over the hidden activation. */
-int tavsr_gemm_bias_act_stats(const void* x, long long ldx, const void* w, long long ldw,
-                              const float* bias, void* y, long long ldy, int M, int N, int K,
-                              int act, int round_out, int dtype, float* stats_out, int stats_col0,
-                              int* stats_part_width, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Row-complete GEMM, N == 256 (the model width): one thread owns one output row, so everything that
@@ -95,7 +94,7 @@ int tavsr_gemm_bias_act_stats(const void* x, long long ldx, const void* w, long 
 typedef struct tavsr_rowln_args {
   int struct_size; /* sizeof(tavsr_rowln_args), for forward compatibility */
   int M, K;        /* N is 256 */
-  int dtype;       /* TAVSR_DT_* */
+  int dtype;       /* TAVSR_DT_* operand type | TAVSR_DT_{OUT,LNA,LNB}_BF16 output flags */
   const void* x;
   long long ldx;
   const void* x2; /* second operand (merge) or NULL */
@@ -112,17 +111,17 @@ typedef struct tavsr_rowln_args {
   const float* ln0_g;
   const float* ln0_b;
   float eps0;
-  float* out_main;
+  void* out_main; /* fp32, or bf16 with TAVSR_DT_OUT_BF16 */
   long long ld_main;
   int round_main;
   const float* lnA_g;
   const float* lnA_b;
-  float* out_lnA;
+  void* out_lnA; /* fp32, or bf16 with TAVSR_DT_LNA_BF16 */
   long long ld_lnA;
   int round_lnA;
   const float* lnB_g;
   const float* lnB_b;
-  float* out_lnB;
+  void* out_lnB; /* fp32, or bf16 with TAVSR_DT_LNB_BF16 */
   long long ld_lnB;
   int round_lnB;
   float eps;
@@ -141,7 +140,8 @@ typedef struct tavsr_rowln_args {
    * This is the learned_ave / fixed_ave merge with the branch output projections folded into
    * merge_proj (W1 = Wm.Wo, W2 = Wm.W_proj2; encoder_layer.py:208-209,220,291-293), so the
    * attention context and the gated cgMLP activations feed the merge GEMM directly.
-   * k1 and K-k1 must be multiples of 32.  segbias1/2: [256] or NULL; not combinable with dots. */
+   * k1 and K-k1 must be multiples of 32 (64 in bf16).  segbias1/2: [256] or NULL; not combinable
+   * with dots.  The bf16 kernel has the sequential dual mode only. */
   int k1;
   const float* segbias1;
   const float* segbias2;
@@ -157,7 +157,9 @@ size_t tavsr_rowln_workspace_bytes(int M);
  *   acc = act(xn . W1^T + b1) . W2^T            hidden = 2048 stays in TMEM / shared memory
  *   then exactly the tavsr_gemm_rowln epilogue on acc (ep.bias = b2, ep.residual, ep.alpha, ep.ln0,
  *   ep.out_main, ep.lnA/lnB ...).  ep.x / ep.w / ep.K / ep.x2 / ep.workspace are ignored.
- * Built for model width 256 and hidden width 2048 (every shipped config).
+ * Built for model width 256 and hidden width 2048 (every shipped config).  ep.dtype selects tf32
+ * (fp32 xn / w1 / w2, TF32 hidden in TMEM) or bf16 (bf16 xn / w1 / w2, packed bf16 hidden in TMEM);
+ * ep.dots_out is not supported here.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct tavsr_ffn_args {
   int struct_size; /* sizeof(tavsr_ffn_args) */
@@ -183,8 +185,9 @@ int tavsr_ffn_fused(const tavsr_ffn_args* args, void* stream);
  * RelPositionalEncoding).
  * ---------------------------------------------------------------------------------------------- */
 int tavsr_layernorm(const float* x, long long ldx, int M, int D, float eps, const float* gA,
-                    const float* bA, float* outA, long long ldA, int roundA, const float* gB,
-                    const float* bB, float* outB, long long ldB, int roundB, float scale,
+                    const float* bA, void* outA, long long ldA, int roundA, const float* gB,
+                    const float* bB, void* outB, long long ldB, int roundB, float scale,
+                    int dtype /* TAVSR_DT_LNA_BF16 / TAVSR_DT_LNB_BF16: bf16 outputs */,
                     void* stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -196,21 +199,14 @@ int tavsr_layernorm(const float* x, long long ldx, int M, int D, float eps, cons
  *   u, v  [H*64]          pos_bias_u / pos_bias_v
  *   lens  [B] int32       valid keys per utterance (mask.sum); keys >= lens[b] get probability 0
  *   ctx   [B*T, ld_ctx]   softmax(((q+u)k^T + rel_shift((q+v)p^T)) / 8) v, heads concatenated
- * d_k is fixed to 64.
+ * d_k is fixed to 64.  dtype: TAVSR_DT_TF32 (fp32 qkv / pos / ctx) or
+ * TAVSR_DT_BF16 | TAVSR_DT_OUT_BF16 (bf16 qkv / pos / ctx; scores, softmax and the output
+ * accumulation stay fp32).  All pitches and bases 16-byte aligned.
  * ---------------------------------------------------------------------------------------------- */
-int tavsr_relpos_attn_fwd(const float* qkv, long long ld_qkv, const float* pos, long long ld_pos,
-                          const float* u, const float* v, const int32_t* lens, float* ctx,
-                          long long ld_ctx, int B, int T, int H, int round_out, void* stream);
-/* Same kernel; additionally dots_out[(row * 2H + 2h + half)] = (ctx_part . dva_part, ctx_part .
- * dvb_part) for the 32 context columns [64h + 32half, +32) of every row: the partial
- * pooling_proj1 / weight_proj1 scores of the learned_ave merge (encoder_layer.py:243,258) with
- * attn.linear_out folded into dva / dvb ([H*64] each, 16-byte aligned).  tavsr_merge_learned_ave_weights2
- * sums the 2H parts. */
-int tavsr_relpos_attn_fwd_dots(const float* qkv, long long ld_qkv, const float* pos,
-                               long long ld_pos, const float* u, const float* v,
-                               const int32_t* lens, float* ctx, long long ld_ctx, int B, int T,
-                               int H, int round_out, const float* dva, const float* dvb,
-                               float* dots_out, void* stream);
+int tavsr_relpos_attn_fwd(const void* qkv, long long ld_qkv, const void* pos, long long ld_pos,
+                          const float* u, const float* v, const int32_t* lens, void* ctx,
+                          long long ld_ctx, int B, int T, int H, int round_out, int dtype,
+                          void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Convolutional spatial gating unit (espnet ConvolutionalSpatialGatingUnit.forward, reached through
@@ -218,22 +214,13 @@ int tavsr_relpos_attn_fwd_dots(const float* qkv, long long ld_qkv, const float* 
  *   out = r * (dwconv_k(LayerNorm_Ch(g)) + conv_bias),  zero padding (k-1)/2 on the normalised
  * sequence at t<0 and t>=T, the key-padding mask is NOT applied (espnet ignores it).
  *   stats [B*T,2] scratch (mean, rstd).  Kernel size must be 31.
+ * dtype: TAVSR_DT_TF32 (fp32 h / out) or TAVSR_DT_BF16 | TAVSR_DT_OUT_BF16 (bf16 h / out;
+ * LayerNorm statistics, the convolution and the gate product stay fp32).
  * ---------------------------------------------------------------------------------------------- */
-int tavsr_csgu_fwd(const float* h, long long ldh, const float* norm_g, const float* norm_b,
-                   const float* conv_w /* [Ch,31] */, const float* conv_b, float* out,
+int tavsr_csgu_fwd(const void* h, long long ldh, const float* norm_g, const float* norm_b,
+                   const float* conv_w /* [Ch,31] */, const float* conv_b, void* out,
                    long long ldo, float* stats, int B, int T, int Ch, int ksize, float eps,
-                   int round_out, void* stream);
-/* Fused form for the two-branch block: LayerNorm statistics come as the partials written by
- * tavsr_gemm_bias_act_stats (n_part parts of part_w channels, n_part * part_w == Ch, n_part <= 16),
- * or, with stats_part == NULL, from the stand-alone statistics pass into the `stats` scratch;
- * optionally emits per frame and 128-channel slab the partial dots of the OUTPUT with dva / dvb
- * ([Ch] each): dots_out[(frame * (Ch/128) + slab)] = (a, b) - the pooling_proj2 / weight_proj2
- * scores (encoder_layer.py:262,277) with channel_proj2 folded in. */
-int tavsr_csgu_fwd_fused(const float* h, long long ldh, const float* norm_g, const float* norm_b,
-                         const float* conv_w, const float* conv_b, float* out, long long ldo,
-                         float* stats, const float* stats_part, int n_part, int part_w, const float* dva,
-                         const float* dvb, float* dots_out, int B, int T, int Ch, int ksize,
-                         float eps, int round_out, void* stream);
+                   int round_out, int dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * learned_ave merge weights (encoder_layer.py:241-289).  dotsK[row] = (x_K . pooling_projK.weight,
@@ -245,9 +232,10 @@ int tavsr_csgu_fwd_fused(const float* h, long long ldh, const float* norm_g, con
  * matrices in one launch: the pooling_proj / weight_proj scores of the learned_ave merge
  * (encoder_layer.py:243,258) taken on the attention context and the gated cgMLP activations with
  * the branch output projections folded into the vectors (va = Wo^T a, ...).  out: [M,2]. */
-int tavsr_row_dots(const float* a1, long long ld1, int K1, const float* va1, const float* vb1,
-                   float* out1, const float* a2, long long ld2, int K2, const float* va2,
-                   const float* vb2, float* out2, int M, void* stream);
+int tavsr_row_dots(const void* a1, long long ld1, int K1, const float* va1, const float* vb1,
+                   float* out1, const void* a2, long long ld2, int K2, const float* va2,
+                   const float* vb2, float* out2, int M, int dtype /* a1 / a2 fp32 or bf16 */,
+                   void* stream);
 
 int tavsr_merge_learned_ave_weights(const float* dots1, const float* dots2, const int32_t* lens,
                                     float pool_b1, float pool_b2, float wproj_b1, float wproj_b2,
@@ -264,8 +252,19 @@ int tavsr_merge_learned_ave_weights2(const float* dots1, int np1, const float* d
 /* out[m,:] = w1[m / rows_per_seg] * a[m,:] + w2[m / rows_per_seg] * b[m,:]: the weighted modality
  * average in front of the fusion FFN (adaptive_audiovisual_fusion.py:187-194).  D % 4 == 0. */
 int tavsr_scale_add_rows(const float* a, long long lda, const float* b, long long ldb,
-                         const float* w1, const float* w2, int rows_per_seg, float* out,
-                         long long ldo, int M, int D, void* stream);
+                         const float* w1, const float* w2, int rows_per_seg, void* out,
+                         long long ldo, int M, int D,
+                         int dtype /* TAVSR_DT_OUT_BF16: out stored as bf16 (w = (1, 0): a cast) */,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 3xTF32 operand split (the "tf32x3" compute mode): out is [M, 3K],
+ *   pattern 0 (activations): [hi | hi | lo],   pattern 1 (weights): [hi | lo | hi],
+ * hi = tf32(x), lo = x - hi.  tavsr_gemm_bias_act / tavsr_gemm_rowln over the tripled reduction
+ * axis then compute a_hi.b_hi + a_hi.b_lo + a_lo.b_hi with fp32 accumulation.
+ * ---------------------------------------------------------------------------------------------- */
+int tavsr_split_tf32(const float* in, long long ld, float* out, long long ldo, int M, int K,
+                     int pattern, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Conv2dSubsampling front end (espnet Conv2dSubsampling inside the encoder module,
@@ -277,7 +276,8 @@ int tavsr_scale_add_rows(const float* a, long long lda, const float* b, long lon
  *   x [B, Tin, F] contiguous;  w1 [C, 9] (= conv.0.weight flattened);  b1 [C].
  * ---------------------------------------------------------------------------------------------- */
 int tavsr_conv2d_sub_im2col(const float* x, int B, int Tin, int F, const float* w1,
-                            const float* b1, int C, float* A, void* stream);
+                            const float* b1, int C, void* A,
+                            int dtype /* TAVSR_DT_OUT_BF16: A stored as bf16 */, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * CTC head: logits = hs . W^T + b in fp32 FMA (argmax must be bit-stable), then log-softmax /
@@ -298,8 +298,8 @@ int tavsr_ctc_head(const float* hs, long long ldh, const float* w /* [V,D] */, c
  * ---------------------------------------------------------------------------------------------- */
 int tavsr_vocab_residual(const float* x, long long ldx, const float* p, const float* w /* [D,V] */,
                          const float* b, float* out, long long ldo, const float* ln_g,
-                         const float* ln_b, float eps, float* xn, long long ldn, int M, int D, int V,
-                         void* stream);
+                         const float* ln_b, float eps, void* xn, long long ldn, int M, int D, int V,
+                         int dtype /* TAVSR_DT_LNA_BF16: xn stored as bf16 */, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * CTC loss, log domain, blank = 0 (torch.nn.CTCLoss(reduction="none", zero_infinity) at

@@ -116,6 +116,10 @@ CASES = {
                               cfg=_enc(num_blocks=3, input_layer="linear", interctc_layer_idx=[1, 2],
                                        interctc_use_conditioning=True),
                               B=2, Tin=64, lens=[64, 39], vocab=41, Lmax=10, seed=19),
+    # dormant early-exit path: forward(..., max_layer=1) runs blocks 0 and 1 of three, then
+    # after_norm (encoder.py:370-374)
+    "vsr_max_layer": dict(kind="single", input_size=512, cfg=_enc(num_blocks=3, input_layer="linear"),
+                          B=2, Tin=58, lens=[58, 37], vocab=41, Lmax=9, seed=34, max_layer=1),
     # full-depth C1: 12 layers, B=8 x 10 s
     "asr_c1": dict(kind="single", input_size=80, cfg=_enc(), B=8, Tin=1001, lens=[1001] * 8,
                    vocab=41, Lmax=100, seed=1, stride_t=8, stride_d=4),

@@ -57,7 +57,7 @@ def run_case(ref, name):
     out = {}
     with torch.no_grad():
         if c["kind"] == "single":
-            y, olens, _ = enc(inp["x"], inp["lens"], ctc=ctc)
+            y, olens, _ = enc(inp["x"], inp["lens"], ctc=ctc, max_layer=c.get("max_layer"))
             streams = {}
             if isinstance(y, tuple):
                 y, inter = y

@@ -179,11 +179,13 @@ def conv2d_subsample(x: torch.Tensor, mask: torch.Tensor, sd: SD, prefix: str) -
     return h, mask[:, :, :-2:2][:, :, :-2:2]
 
 
-def branchformer_encoder(xs: torch.Tensor, ilens: torch.Tensor, sd: SD, cfg: dict, prefix: str = ""
+def branchformer_encoder(xs: torch.Tensor, ilens: torch.Tensor, sd: SD, cfg: dict, prefix: str = "",
+                         max_layer: Optional[int] = None
                          ) -> Tuple[torch.Tensor, torch.Tensor, List[Optional[Tuple]]]:
     """Eval-mode restatement of MyBranchformerEncoder.forward (encoder.py:324-412), plain loop
     (:376) or the InterCTC loop (:378-401) when cfg["interctc_layer_idx"] is set, input_layer in
-    {conv2d, linear, None}.  Returns (out, olens, per-layer merge weights); the tapped outputs are
+    {conv2d, linear, None}; `max_layer` is the early exit of :370-374 (only without InterCTC taps:
+    blocks 0..max_layer run, then after_norm).  Returns (out, olens, per-layer merge weights); the tapped outputs are
     left in cfg-independent form on the function attribute `last_taps` [(idx, tensor)]."""
     d = cfg.get("output_size", 256)
     n = cfg.get("num_blocks", 12)
@@ -213,6 +215,8 @@ def branchformer_encoder(xs: torch.Tensor, ilens: torch.Tensor, sd: SD, cfg: dic
             merge_method=cfg.get("merge_method", "learned_ave"), cgmlp_weight=cw[l],
             use_attn=cfg.get("use_attn", True), use_cgmlp=cfg.get("use_cgmlp", True))
         weights.append(w)
+        if not taps and max_layer is not None and 0 <= max_layer < n and l >= max_layer:
+            break  # encoder.py:373-374
         if (l + 1) in taps:
             tap = layer_norm(xs, sd, prefix + "after_norm")  # :386-388
             tap_outs.append((l + 1, tap))

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_PKG_DIR, "libtavsr_sm100.so")
 
 ACT_NONE, ACT_SWISH, ACT_GELU, ACT_RELU = 0, 1, 2, 3
 DT_TF32, DT_BF16 = 0, 1
+DT_OUT_BF16, DT_LNA_BF16, DT_LNB_BF16 = 0x100, 0x200, 0x400
 
 
 class TavsrError(RuntimeError):
@@ -68,47 +69,40 @@ SIGNATURES = {
     "tavsr_gemm_bias_act": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p,
                                     c_longlong, c_int, c_int, c_int, c_int, c_int, c_int,
                                     c_void_p]),
-    "tavsr_gemm_bias_act_stats": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p,
-                                          c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_int,
-                                          c_int, c_void_p, c_int, POINTER(c_int), c_void_p]),
     "tavsr_gemm_rowln": (c_int, [POINTER(RowLNArgs), c_void_p]),
     "tavsr_rowln_workspace_bytes": (c_size_t, [c_int]),
     "tavsr_ffn_fused": (c_int, [POINTER(FfnArgs), c_void_p]),
     "tavsr_layernorm": (c_int, [c_void_p, c_longlong, c_int, c_int, c_float, c_void_p, c_void_p,
                                 c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_void_p,
-                                c_longlong, c_int, c_float, c_void_p]),
+                                c_longlong, c_int, c_float, c_int, c_void_p]),
     "tavsr_relpos_attn_fwd": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int,
-                                      c_int, c_int, c_void_p]),
-    "tavsr_relpos_attn_fwd_dots": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p,
-                                           c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int,
-                                           c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "tavsr_csgu_fwd_fused": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,
-                                     c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_int, c_void_p,
-                                     c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
-                                     c_int, c_void_p]),
+                                      c_int, c_int, c_int, c_void_p]),
     "tavsr_merge_learned_ave_weights2": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p,
                                                  c_void_p, c_float, c_float, c_float, c_float,
                                                  c_float, c_void_p, c_void_p, c_int, c_int,
                                                  c_void_p]),
     "tavsr_scale_add_rows": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p,
-                                     c_void_p, c_int, c_void_p, c_longlong, c_int, c_int,
+                                     c_void_p, c_int, c_void_p, c_longlong, c_int, c_int, c_int,
                                      c_void_p]),
     "tavsr_csgu_fwd": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_longlong, c_void_p, c_int, c_int, c_int, c_int,
-                               c_float, c_int, c_void_p]),
+                               c_float, c_int, c_int, c_void_p]),
     "tavsr_row_dots": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                               c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+                               c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                               c_void_p]),
     "tavsr_merge_learned_ave_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_float,
                                                 c_float, c_float, c_float, c_void_p, c_void_p,
                                                 c_int, c_int, c_void_p]),
+    "tavsr_split_tf32": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_int,
+                                 c_void_p]),
     "tavsr_conv2d_sub_im2col": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
-                                        c_void_p, c_void_p]),
+                                        c_void_p, c_int, c_void_p]),
     "tavsr_ctc_head": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "tavsr_vocab_residual": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_longlong, c_void_p, c_void_p, c_float, c_void_p, c_longlong,
-                                     c_int, c_int, c_int, c_void_p]),
+                                     c_int, c_int, c_int, c_int, c_void_p]),
     "tavsr_ctc_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "tavsr_ctc_loss": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_int, c_int,

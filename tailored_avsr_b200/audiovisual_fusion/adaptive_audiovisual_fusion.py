@@ -94,11 +94,13 @@ class AdaptiveAudioVisualFusion(AudioVisualFusionAbsModule):
                 lambda: (torch.full((B,), float(self.acoustic_weight), device=dev, dtype=torch.float32),
                          torch.full((B,), 1.0 - float(self.acoustic_weight), device=dev,
                                     dtype=torch.float32)))
-        z = ops.scale_add_rows(audio2d, video2d, w_a, w_v, T)
+        # the weighted average only feeds the fusion FFN: operand storage
+        z = ops.scale_add_rows(audio2d, video2d, w_a, w_v, T, out_dtype=engine.act_dtype())
         out = torch.empty((B * T, d), device=dev, dtype=torch.float32)
         # audiovisual_layer + norm_final: the FFN kernel without residual, norm_final as its LN0
         engine.ffn_block(None, z, self.audiovisual_layer, out_main=out, alpha=1.0,
-                         ln0=(self.norm_final.weight, self.norm_final.bias))
+                         ln0=(self.norm_final.weight, self.norm_final.bias), cache=self._packed,
+                         key="avffn")
         return out
 
     def forward(self, audio_pad, audio_masks, video_pad, video_masks, cache=None):

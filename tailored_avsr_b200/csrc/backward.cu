@@ -588,12 +588,10 @@ extern "C" int tavsr_csgu_conv_bwd(const float* h, long long ldh, const float* n
                 "csgu_bwd: workspace too small");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int smem = 2 * bwd::kRows * bwd::kCh * 4;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (first_use_on_device(configured))
     TAVSR_CUDA_OK(cudaFuncSetAttribute(bwd::csgu_conv_bwd_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
   const int nseg = (T + bwd::kSeg - 1) / bwd::kSeg;
   float* part = static_cast<float*>(workspace);
   TAVSR_CUDA_OK(launch_kernel(bwd::csgu_conv_bwd_kernel, dim3(Ch / bwd::kCh, nseg, B), dim3(bwd::kCh),
@@ -636,11 +634,10 @@ extern "C" int tavsr_merge_learned_ave_bwd(const float* x1, long long ld1, const
   p.part_s = p.part + static_cast<size_t>(B) * 4 * 256;
   p.T = T;
   const int smem = 4 * T * 4;
-  static int configured = 0;
-  if (configured < smem) {
+  static PerDeviceMax configured;
+  if (configured.raise(smem)) {
     TAVSR_CUDA_OK(cudaFuncSetAttribute(bwd::merge_learned_ave_bwd_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = smem;
   }
   TAVSR_CUDA_OK(launch_kernel(bwd::merge_learned_ave_bwd_kernel, dim3(B), dim3(256),
                               static_cast<size_t>(smem), s, 0, p));

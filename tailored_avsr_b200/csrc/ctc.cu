@@ -121,8 +121,8 @@ __global__ void __launch_bounds__(256)
 vocab_residual_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ p,
                       const float* __restrict__ w, const float* __restrict__ bias,
                       float* __restrict__ out, long long ldo, const float* __restrict__ ln_g,
-                      const float* __restrict__ ln_b, float eps, float* __restrict__ xn,
-                      long long ldn, int M, int V) {
+                      const float* __restrict__ ln_b, float eps, void* __restrict__ xn,
+                      long long ldn, int M, int V, int xn_bf16) {
   pdl_launch_dependents();
   constexpr int D = kC * 32;
   extern __shared__ float sm[];
@@ -170,8 +170,12 @@ vocab_residual_kernel(const float* __restrict__ x, long long ldx, const float* _
       }
       const float rstd = rsqrtf(warp_sum(var) * (1.0f / D) + eps);
 #pragma unroll
-      for (int c = 0; c < kC; ++c)
-        xn[static_cast<long long>(m) * ldn + lane + 32 * c] = (acc[c] - mean) * rstd * gg[c] + be[c];
+      for (int c = 0; c < kC; ++c) {
+        const float y = (acc[c] - mean) * rstd * gg[c] + be[c];
+        const long long o = static_cast<long long>(m) * ldn + lane + 32 * c;
+        if (xn_bf16) static_cast<uint16_t*>(xn)[o] = static_cast<uint16_t>(pack_bf16x2(y, 0.f) & 0xFFFFu);
+        else static_cast<float*>(xn)[o] = y;
+      }
     }
   }
 }
@@ -583,11 +587,10 @@ extern "C" int tavsr_ctc_head(const float* hs, long long ldh, const float* w, co
   TAVSR_REQUIRE(hs && w && b && ldh % 4 == 0, "ctc_head: bad arguments");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int smem = (D * ctc::kVPad + 8 * 4 * D) * 4;
-  static int configured = 0;
-  if (configured < smem) {
+  static PerDeviceMax configured;
+  if (configured.raise(smem)) {
     TAVSR_CUDA_OK(cudaFuncSetAttribute(ctc::ctc_head_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = smem;
   }
   const int groups = (M + 3) / 4;
   int grid = (groups + 7) / 8;
@@ -600,8 +603,9 @@ extern "C" int tavsr_ctc_head(const float* hs, long long ldh, const float* w, co
 
 extern "C" int tavsr_vocab_residual(const float* x, long long ldx, const float* p, const float* w,
                                     const float* b, float* out, long long ldo, const float* ln_g,
-                                    const float* ln_b, float eps, float* xn, long long ldn, int M,
-                                    int D, int V, void* stream) {
+                                    const float* ln_b, float eps, void* xn, long long ldn, int M,
+                                    int D, int V, int dtype, void* stream) {
+  const int xn_bf16 = (dtype & TAVSR_DT_LNA_BF16) ? 1 : 0;
   TAVSR_REQUIRE(M > 0 && (D == 128 || D == 256 || D == 512), "vocab_residual: D=%d not built", D);
   TAVSR_REQUIRE(V > 0 && V <= ctc::kVPad, "vocab_residual: V=%d > 64 not built", V);
   TAVSR_REQUIRE(x && p && w && b && out, "vocab_residual: null pointer");
@@ -612,14 +616,13 @@ extern "C" int tavsr_vocab_residual(const float* x, long long ldx, const float* 
   if (grid > 2 * num_sms()) grid = 2 * num_sms();
 #define TAVSR_VR_CASE(C)                                                                        \
   do {                                                                                          \
-    static int configured = 0;                                                                  \
-    if (configured < smem) {                                                                    \
+    static PerDeviceMax configured;                                                                  \
+    if (configured.raise(smem)) {                                                                    \
       TAVSR_CUDA_OK(cudaFuncSetAttribute(ctc::vocab_residual_kernel<C>,                         \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));   \
-      configured = smem;                                                                        \
     }                                                                                           \
     TAVSR_CUDA_OK(launch_kernel(ctc::vocab_residual_kernel<C>, dim3(grid), dim3(256), smem, s, 0, x, \
-                                ldx, p, w, b, out, ldo, ln_g, ln_b, eps, xn, ldn, M, V));       \
+                                ldx, p, w, b, out, ldo, ln_g, ln_b, eps, xn, ldn, M, V, xn_bf16)); \
   } while (0)
   if (D == 128) TAVSR_VR_CASE(4);
   else if (D == 256) TAVSR_VR_CASE(8);

@@ -124,17 +124,15 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, bool is_bf16
 // ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
-template <bool kTf32, int kBlockN, int kMode, bool kDual, int kCtas, int kAct, bool kStats = false,
-          bool kSeq = false, bool kWideEpi = false>
+template <bool kTf32, int kBlockN, int kMode, bool kDual, int kCtas, int kAct, bool kSeq = false,
+          bool kWideEpi = false>
 static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<kTf32, kBlockN, kMode, kDual, kCtas, kSeq, kWideEpi>;
-  auto kern = gemm_sm100_kernel<kTf32, kBlockN, kMode, kDual, kCtas, kAct, kStats, kSeq, kWideEpi>;
-  static bool configured = false;
-  if (!configured) {
+  auto kern = gemm_sm100_kernel<kTf32, kBlockN, kMode, kDual, kCtas, kAct, kSeq, kWideEpi>;
+  static unsigned long long configured = 0;  // one bit per device ordinal
+  if (first_use_on_device(configured))
     TAVSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes));
-    configured = true;
-  }
   const int units = p.num_m_tiles * p.num_n_tiles;
   const int max_units = num_sms() / kCtas;
   const int grid = (units < max_units ? units : max_units) * kCtas;
@@ -143,23 +141,14 @@ static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
   return 0;
 }
 
-// Tiled GEMM dispatch over (tile width, CTA pairing, activation).
-template <int kBlockN, int kCtas>
+// Tiled GEMM dispatch over (operand type, tile width, epilogue width, activation): CTA pairs only.
+template <bool kTf32, int kBlockN, bool kWide>
 static int launch_tiled(const GemmParams& p, cudaStream_t s) {
-  if (p.stats_out != nullptr) {
-    // the partial-statistics epilogue is its own instantiation (run-time activation): the plain
-    // kernels keep the exact code they had without it
-    return launch_gemm<true, kBlockN, kModeTiled, false, kCtas, -1, true>(p, s);
-  }
-  if constexpr (kCtas == 1) {
-    return launch_gemm<true, kBlockN, kModeTiled, false, 1, -1>(p, s);
-  } else {
   switch (p.act) {
-    case ACT_NONE: return launch_gemm<true, kBlockN, kModeTiled, false, kCtas, ACT_NONE>(p, s);
-    case ACT_SWISH: return launch_gemm<true, kBlockN, kModeTiled, false, kCtas, ACT_SWISH>(p, s);
-    case ACT_GELU: return launch_gemm<true, kBlockN, kModeTiled, false, kCtas, ACT_GELU>(p, s);
-    default: return launch_gemm<true, kBlockN, kModeTiled, false, kCtas, -1>(p, s);
-  }
+    case ACT_NONE: return launch_gemm<kTf32, kBlockN, kModeTiled, false, 2, ACT_NONE, false, kWide>(p, s);
+    case ACT_SWISH: return launch_gemm<kTf32, kBlockN, kModeTiled, false, 2, ACT_SWISH, false, kWide>(p, s);
+    case ACT_GELU: return launch_gemm<kTf32, kBlockN, kModeTiled, false, 2, ACT_GELU, false, kWide>(p, s);
+    default: return launch_gemm<kTf32, kBlockN, kModeTiled, false, 2, -1, false, kWide>(p, s);
   }
 }
 
@@ -183,32 +172,28 @@ extern "C" int tavsr_debug_set_ptr(void* p) {
 extern "C" int tavsr_gemm_bias_act(const void* x, long long ldx, const void* w, long long ldw,
                                    const float* bias, void* y, long long ldy, int M, int N, int K,
                                    int act, int round_out, int dtype, void* stream) {
-  return tavsr_gemm_bias_act_stats(x, ldx, w, ldw, bias, y, ldy, M, N, K, act, round_out, dtype,
-                                   nullptr, 0, nullptr, stream);
-}
-
-extern "C" int tavsr_gemm_bias_act_stats(const void* x, long long ldx, const void* w, long long ldw,
-                                         const float* bias, void* y, long long ldy, int M, int N,
-                                         int K, int act, int round_out, int dtype, float* stats_out,
-                                         int stats_col0, int* stats_part_width, void* stream) {
   TAVSR_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
-  TAVSR_REQUIRE(dtype == TAVSR_DT_TF32 || dtype == TAVSR_DT_BF16,
-                "gemm: dtype must be TAVSR_DT_TF32 or TAVSR_DT_BF16 (bf16 operands, fp32 output)");
-  const bool bf16 = dtype == TAVSR_DT_BF16;
+  const int op = dtype & TAVSR_DT_MASK;
+  TAVSR_REQUIRE(op == TAVSR_DT_TF32 || op == TAVSR_DT_BF16,
+                "gemm: operand dtype must be TAVSR_DT_TF32 or TAVSR_DT_BF16 (tf32x3 is composed by "
+                "the caller from tavsr_split_tf32 + a K-tripled TF32 product)");
+  const bool bf16 = op == TAVSR_DT_BF16;
+  const bool out_bf16 = (dtype & TAVSR_DT_OUT_BF16) != 0;
+  TAVSR_REQUIRE(bf16 || !out_bf16, "gemm: bf16 output only with bf16 operands");
   const int eb = bf16 ? 2 : 4;  // operand element bytes; a 128-byte swizzle row holds 128 / eb
-  TAVSR_REQUIRE(K % (16 / eb) == 0 && N % 4 == 0,
-                "gemm: K must be a multiple of %d and N of 4 (K=%d N=%d)", 16 / eb, K, N);
-  TAVSR_REQUIRE(!bf16 || (stats_out == nullptr && !round_out),
-                "gemm: the bf16-operand kernel has no statistics epilogue / TF32 output rounding");
+  TAVSR_REQUIRE(K % (16 / eb) == 0 && N % (out_bf16 ? 8 : 4) == 0,
+                "gemm: K must be a multiple of %d and N of %d (K=%d N=%d)", 16 / eb,
+                out_bf16 ? 8 : 4, K, N);
+  TAVSR_REQUIRE(!bf16 || !round_out, "gemm: TF32 output rounding is a tf32-mode option");
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K;
   p.bias = bias; p.act = act; p.round_c = round_out;
-  // CTA pairing (cta_group::2): a pair covers 256 rows and shares the B tile, which halves the
-  // per-SM weight traffic and makes room for a deeper pipeline.  g_debug[3] = 1 forces 1-CTA.
-  const int ctas = g_debug[3] == 1 ? 1 : 2;
-  const int rows_per_unit = 128 * ctas;
-  const int mt = (M + rows_per_unit - 1) / rows_per_unit;
+  p.c_bf16 = out_bf16;
+  // CTA pairs (cta_group::2): a pair covers 256 rows and shares the B tile, which halves the
+  // per-SM weight traffic and makes room for a deeper pipeline.
+  const int ctas = 2;
+  const int mt = (M + 255) / 256;
   const int slots = num_sms() / ctas;
   // tile-width heuristic: fewer waves wins (a 128-wide tile costs about half a 256-wide one)
   const int t256 = mt * ((N + 255) / 256), t128 = mt * ((N + 127) / 128);
@@ -219,44 +204,24 @@ extern "C" int tavsr_gemm_bias_act_stats(const void* x, long long ldx, const voi
   const int bn = (use128 && g_debug[2] != 256) ? 128 : 256;
   p.num_m_tiles = mt;
   p.num_n_tiles = (N + bn - 1) / bn;
-  if (stats_out != nullptr) {
-    const int pw = bn / 2;  // columns per epilogue warp == columns per statistics part
-    TAVSR_REQUIRE(stats_part_width != nullptr && stats_col0 >= 0 && stats_col0 < N &&
-                      stats_col0 % pw == 0 && N % pw == 0,
-                  "gemm: statistics columns [%d, %d) must be multiples of the part width %d",
-                  stats_col0, N, pw);
-    p.stats_out = reinterpret_cast<float2*>(stats_out);
-    p.stats_col0 = stats_col0;
-    p.stats_parts = (N - stats_col0) / pw;
-    *stats_part_width = pw;
-  }
   int rc;
   if ((rc = make_tmap_2d(&p.tmA, x, eb, bf16, M, K, ldx, 128, 128 / eb))) return rc;
   if ((rc = make_tmap_2d(&p.tmB, w, eb, bf16, N, K, ldw, bn / ctas, 128 / eb))) return rc;
-  if ((rc = make_tmap_2d(&p.tmC, y, 4, false, M, N, ldy, 32, 32, false))) return rc;
+  if (out_bf16) {
+    if ((rc = make_tmap_2d(&p.tmC, y, 2, true, M, N, ldy, 32, 64, false))) return rc;
+  } else {
+    if ((rc = make_tmap_2d(&p.tmC, y, 4, false, M, N, ldy, 32, 32, false))) return rc;
+  }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // 16-warp epilogue (GemmCfg::kWideEpi) on the 256-wide tiles: the K = 256 projections are bound
+  // by their epilogue's latency (+3.7 % on the C2 step).  g_debug[13] = 1 falls back to 8 warps.
+  const bool wide = bn == 256 && g_debug[13] == 0;
   if (bf16) {
-    // kind::f16 MMAs on bf16 operands (128 x N x 16 per instruction, twice the TF32 rate at half
-    // the operand bytes), fp32 accumulate and fp32 output: the first brick of the bf16 mode
-    TAVSR_REQUIRE(ctas == 2, "gemm: the bf16-operand kernel is built for CTA pairs");
-    return bn == 128 ? launch_gemm<false, 128, kModeTiled, false, 2, -1>(p, s)
-                     : launch_gemm<false, 256, kModeTiled, false, 2, -1>(p, s);
+    if (bn == 128) return launch_tiled<false, 128, false>(p, s);
+    return wide ? launch_tiled<false, 256, true>(p, s) : launch_tiled<false, 256, false>(p, s);
   }
-  // 16-warp epilogue (GemmCfg::kWideEpi) for the CTA-pair kernels: +3.7 % on the C2 step with the
-  // 256-wide tiles.  g_debug[13] = 1 falls back to 8 warps; g_debug[14] = 1 also widens 128-wide tiles.
-  if (ctas == 2 && g_debug[13] == 0 && stats_out == nullptr && (bn == 256 || g_debug[14] == 1)) {
-#define TAVSR_WIDE(BN)                                                                                \
-    switch (p.act) {                                                                                  \
-      case ACT_NONE: return launch_gemm<true, BN, kModeTiled, false, 2, ACT_NONE, false, false, true>(p, s);   \
-      case ACT_SWISH: return launch_gemm<true, BN, kModeTiled, false, 2, ACT_SWISH, false, false, true>(p, s); \
-      case ACT_GELU: return launch_gemm<true, BN, kModeTiled, false, 2, ACT_GELU, false, false, true>(p, s);   \
-      default: return launch_gemm<true, BN, kModeTiled, false, 2, -1, false, false, true>(p, s);      \
-    }
-    if (bn == 256) { TAVSR_WIDE(256) } else { TAVSR_WIDE(128) }
-#undef TAVSR_WIDE
-  }
-  if (ctas == 2) return bn == 128 ? launch_tiled<128, 2>(p, s) : launch_tiled<256, 2>(p, s);
-  return bn == 128 ? launch_tiled<128, 1>(p, s) : launch_tiled<256, 1>(p, s);
+  if (bn == 128) return launch_tiled<true, 128, false>(p, s);
+  return wide ? launch_tiled<true, 256, true>(p, s) : launch_tiled<true, 256, false>(p, s);
 }
 
 extern "C" size_t tavsr_rowln_workspace_bytes(int M) {
@@ -274,6 +239,9 @@ int fill_rowln_epilogue(GemmParams& p, const tavsr_rowln_args* a, const char* wh
                 "%s: LayerNorm stages need gamma, beta and an output", who);
   TAVSR_REQUIRE(!a->dots_out || (a->dot1 && a->dot2), "%s: dots_out needs dot1 and dot2", who);
   TAVSR_REQUIRE(!a->residual || a->ldr % 4 == 0, "%s: residual pitch must be a multiple of 4", who);
+  const bool bf16 = (a->dtype & TAVSR_DT_MASK) == TAVSR_DT_BF16;
+  TAVSR_REQUIRE(bf16 || !(a->dtype & (TAVSR_DT_OUT_BF16 | TAVSR_DT_LNA_BF16 | TAVSR_DT_LNB_BF16)),
+                "%s: bf16 outputs only with bf16 operands", who);
   p.M = a->M; p.N = 256;
   p.bias = a->bias;
   p.act = ACT_NONE;
@@ -289,17 +257,17 @@ int fill_rowln_epilogue(GemmParams& p, const tavsr_rowln_args* a, const char* wh
   p.out_main = a->out_main; p.ld_main = a->ld_main;
   p.out_lnA = a->out_lnA; p.ld_lnA = a->ld_lnA;
   p.out_lnB = a->out_lnB; p.ld_lnB = a->ld_lnB;
-  p.rowwarp_epilogue = g_debug[11] == 0 && a->dots_out == nullptr;
+  p.c_bf16 = (a->dtype & TAVSR_DT_OUT_BF16) != 0;
+  p.lnA_bf16 = (a->dtype & TAVSR_DT_LNA_BF16) != 0;
+  p.lnB_bf16 = (a->dtype & TAVSR_DT_LNB_BF16) != 0;
+  auto out_map = [&](CUtensorMap* tm, void* ptr, long long ld, bool as_bf16) {
+    return as_bf16 ? make_tmap_2d(tm, ptr, 2, true, a->M, 256, ld, 32, 64, false)
+                   : make_tmap_2d(tm, ptr, 4, false, a->M, 256, ld, 32, 32, false);
+  };
   int rc;
-  if (a->out_main &&
-      (rc = make_tmap_2d(&p.tmC, a->out_main, 4, false, a->M, 256, a->ld_main, 32, 32, false)))
-    return rc;
-  if (a->lnA_g &&
-      (rc = make_tmap_2d(&p.tmLnA, a->out_lnA, 4, false, a->M, 256, a->ld_lnA, 32, 32, false)))
-    return rc;
-  if (a->lnB_g &&
-      (rc = make_tmap_2d(&p.tmLnB, a->out_lnB, 4, false, a->M, 256, a->ld_lnB, 32, 32, false)))
-    return rc;
+  if (a->out_main && (rc = out_map(&p.tmC, a->out_main, a->ld_main, p.c_bf16))) return rc;
+  if (a->lnA_g && (rc = out_map(&p.tmLnA, a->out_lnA, a->ld_lnA, p.lnA_bf16))) return rc;
+  if (a->lnB_g && (rc = out_map(&p.tmLnB, a->out_lnB, a->ld_lnB, p.lnB_bf16))) return rc;
   return 0;
 }
 }  // namespace tavsr
@@ -308,23 +276,29 @@ extern "C" int tavsr_gemm_rowln(const tavsr_rowln_args* a, void* stream) {
   TAVSR_REQUIRE(a != nullptr && a->struct_size == static_cast<int>(sizeof(tavsr_rowln_args)),
                 "rowln: bad args struct (size %d, expected %d)", a ? a->struct_size : -1,
                 static_cast<int>(sizeof(tavsr_rowln_args)));
-  TAVSR_REQUIRE(a->M > 0 && a->K > 0 && a->K % 4 == 0, "rowln: bad shape M=%d K=%d", a->M, a->K);
-  TAVSR_REQUIRE(a->dtype == TAVSR_DT_TF32, "rowln: only TAVSR_DT_TF32 is built in this round");
+  const int op = a->dtype & TAVSR_DT_MASK;
+  TAVSR_REQUIRE(op == TAVSR_DT_TF32 || op == TAVSR_DT_BF16,
+                "rowln: operand dtype must be TAVSR_DT_TF32 or TAVSR_DT_BF16");
+  const bool bf16 = op == TAVSR_DT_BF16;
+  const int eb = bf16 ? 2 : 4;
+  const int bk = 128 / eb;  // elements per 128-byte k-block
+  TAVSR_REQUIRE(a->M > 0 && a->K > 0 && a->K % (16 / eb) == 0, "rowln: bad shape M=%d K=%d", a->M, a->K);
   TAVSR_REQUIRE(a->x && a->w, "rowln: x and w are required");
   const bool dual = a->x2 != nullptr;
   TAVSR_REQUIRE(!dual || (a->rowscale1 && a->rowscale2 && a->rows_per_seg > 0),
                 "rowln: dual mode needs rowscale1/2 and rows_per_seg");
   const bool seq = dual && a->k1 > 0;
-  TAVSR_REQUIRE(a->k1 == 0 || (dual && a->k1 % 32 == 0 && a->k1 < a->K && (a->K - a->k1) % 32 == 0),
-                "rowln: sequential dual mode needs x2 and k1, K-k1 multiples of 32 (k1=%d K=%d)",
+  TAVSR_REQUIRE(a->k1 == 0 || (dual && a->k1 % bk == 0 && a->k1 < a->K && (a->K - a->k1) % bk == 0),
+                "rowln: sequential dual mode needs x2 and k1, K-k1 multiples of %d (k1=%d K=%d)", bk,
                 a->k1, a->K);
   TAVSR_REQUIRE(!(a->segbias1 || a->segbias2) || (seq && a->segbias1 && a->segbias2 && !a->dots_out),
                 "rowln: segbias1/2 come as a pair, only in sequential dual mode, without dots");
+  TAVSR_REQUIRE(!bf16 || !dual || seq, "rowln: the bf16 kernel has the sequential dual mode only");
   GemmParams p;
   memset(&p, 0, sizeof(p));
   int rc;
   if ((rc = fill_rowln_epilogue(p, a, "rowln"))) return rc;
-  const int ctas = g_debug[3] == 1 ? 1 : 2;
+  const int ctas = 2;
   p.K = a->K;
   p.num_m_tiles = (a->M + 128 * ctas - 1) / (128 * ctas);
   p.num_n_tiles = 1;
@@ -332,8 +306,8 @@ extern "C" int tavsr_gemm_rowln(const tavsr_rowln_args* a, void* stream) {
   // split-K over two CTA pairs when the row tiles alone would leave >= half of the SMs idle
   // (measured slower than the unsplit kernel at M = 8000 in round 1 - the fused FFN kernel is the
   // real fix for K = 2048 - so it is opt-in: g_debug[4] = 1)
-  if (!dual && ctas == 2 && a->workspace != nullptr && g_debug[4] == 1 && a->K >= 1024 &&
-      a->K % 64 == 0 && 2 * p.num_m_tiles <= num_sms() / 2 &&
+  if (!dual && a->workspace != nullptr && g_debug[4] == 1 && a->K >= 1024 &&
+      a->K % (2 * bk) == 0 && 2 * p.num_m_tiles <= num_sms() / 2 &&
       static_cast<size_t>(a->workspace_bytes) >= tavsr_rowln_workspace_bytes(a->M)) {
     p.num_n_tiles = 2;
     // flag words live at a FIXED offset (start of the scratch) so that calls with different M
@@ -344,30 +318,22 @@ extern "C" int tavsr_gemm_rowln(const tavsr_rowln_args* a, void* stream) {
   const int ka1 = seq ? a->k1 : a->K;
   const int ka2 = seq ? a->K - a->k1 : a->K;
   if (seq) {
-    p.seq_kb1 = a->k1 / 32;
+    p.seq_kb1 = a->k1 / bk;
     if (a->segbias1) {
       p.seg_bias = 1;
       p.dot1 = a->segbias1;
       p.dot2 = a->segbias2;
     }
   }
-  if ((rc = make_tmap_2d(&p.tmA, a->x, 4, false, a->M, ka1, a->ldx, 128, 32))) return rc;
-  if (dual && (rc = make_tmap_2d(&p.tmA2, a->x2, 4, false, a->M, ka2, a->ldx2, 128, 32))) return rc;
-  if ((rc = make_tmap_2d(&p.tmB, a->w, 4, false, 256, a->K, a->ldw, 256 / ctas, 32))) return rc;
+  if ((rc = make_tmap_2d(&p.tmA, a->x, eb, bf16, a->M, ka1, a->ldx, 128, bk))) return rc;
+  if (dual && (rc = make_tmap_2d(&p.tmA2, a->x2, eb, bf16, a->M, ka2, a->ldx2, 128, bk))) return rc;
+  if ((rc = make_tmap_2d(&p.tmB, a->w, eb, bf16, 256, a->K, a->ldw, 256 / ctas, bk))) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (ctas == 2) {
-    // g_debug[15] = 1: two epilogue warps per TMEM lane quadrant (rowln_finish2), never with
-    // split-K.  Opt-in: measured SLOWER on the C2 step (3.28 vs 3.19 ms) - unlike the tiled GEMM and
-    // the FFN activation, the four LayerNorm partial-sum exchanges and the single-buffered store
-    // staging cost more than the halved per-thread chain saves.
-    const bool wide = g_debug[15] == 1 && p.num_n_tiles == 1;
-    if (seq) return wide ? launch_gemm<true, 256, kModeRowLN, true, 2, 0, false, true, true>(p, s)
-                         : launch_gemm<true, 256, kModeRowLN, true, 2, 0, false, true>(p, s);
-    if (dual) return launch_gemm<true, 256, kModeRowLN, true, 2, 0>(p, s);
-    return wide ? launch_gemm<true, 256, kModeRowLN, false, 2, 0, false, false, true>(p, s)
-                : launch_gemm<true, 256, kModeRowLN, false, 2, 0>(p, s);
+  if (bf16) {
+    if (seq) return launch_gemm<false, 256, kModeRowLN, true, 2, 0, true>(p, s);
+    return launch_gemm<false, 256, kModeRowLN, false, 2, 0>(p, s);
   }
-  if (seq) return launch_gemm<true, 256, kModeRowLN, true, 1, 0, false, true>(p, s);
-  if (dual) return launch_gemm<true, 256, kModeRowLN, true, 1, 0>(p, s);
-  return launch_gemm<true, 256, kModeRowLN, false, 1, 0>(p, s);
+  if (seq) return launch_gemm<true, 256, kModeRowLN, true, 2, 0, true>(p, s);
+  if (dual) return launch_gemm<true, 256, kModeRowLN, true, 2, 0>(p, s);
+  return launch_gemm<true, 256, kModeRowLN, false, 2, 0>(p, s);
 }

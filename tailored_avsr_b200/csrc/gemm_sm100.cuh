@@ -69,22 +69,16 @@ struct alignas(64) GemmParams {
   // folded in).  seg_bias: dot1 / dot2 hold per-branch bias vectors scaled like the accumulators.
   int seq_kb1;
   int seg_bias;
-  // ---- Tiled mode: per-row partial LayerNorm statistics of the stored output columns
-  // [stats_col0, N): every epilogue warp owns kBlockN/2 columns of 32 rows and writes one
-  // (mean, M2 = sum (x - mean)^2) pair per row, stats_out[m * stats_parts + part].  The consumer
-  // (CSGU conv kernel) combines the parts, so the stand-alone statistics pass over the cgMLP
-  // hidden activation disappears.
-  float2* stats_out;
-  int stats_col0;
-  int stats_parts;
   // ---- raw output pointers (the fused FFN's warp-per-row epilogue stores directly, coalesced) ----
-  float* out_main;
+  void* out_main;
   long long ld_main;
-  float* out_lnA;
+  void* out_lnA;
   long long ld_lnA;
-  float* out_lnB;
+  void* out_lnB;
   long long ld_lnB;
-  int rowwarp_epilogue;  // fused FFN: 1 = warp-per-row epilogue (default), 0 = thread-per-row
+  // ---- bf16 mode (kTf32 == false): which outputs are stored as bf16 (tensor-core operands of the
+  // next kernel) instead of fp32 (residual stream, encoder output) ----
+  int c_bf16, lnA_bf16, lnB_bf16;
 };
 
 // kWideEpi (tiled mode): 16 epilogue warps (four per TMEM lane quadrant, a quarter of the tile's
@@ -108,18 +102,15 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes * kATiles + kBBytes;
   static constexpr int kAccCols = kBlockN * (kDual ? 2 : 1);
   static constexpr int kAccStages = (512 / kAccCols) >= 2 ? 2 : 1;
-  static constexpr int kEpiWarps = kMode == kModeTiled ? (kWideEpi ? 16 : 8) : (kWideEpi ? 8 : 4);
+  static constexpr int kEpiWarps = kMode == kModeTiled ? (kWideEpi ? 16 : 8) : 4;
   static constexpr int kThreads = 64 + 32 * kEpiWarps;
   static constexpr int kStageBufs = kWideEpi ? 1 : 2;  // 16 warps: single-buffered store staging
+  static_assert(kMode == kModeTiled || !kWideEpi, "the wide epilogue is a tiled-mode variant");
   static constexpr int kStagingBytes = kEpiWarps * kStageBufs * 4096;
   static constexpr int kEpiParts = kEpiWarps / 4;      // column slices of a tile (one per warp of a quadrant)
   // params staged in smem: bias[2][kBlockN] (tiled) or 9 x 256 floats (rowln)
   static constexpr int kParamFloats = kMode == kModeTiled ? 2 * kBlockN : 9 * 256;
-  // RowLN with two warps per TMEM lane quadrant: LayerNorm partial sums cross between the two
-  // warps of a row through [2 tile parities][6 slots][128 rows][2 parts] floats
-  static constexpr int kXchFloats = (kMode == kModeRowLN && kWideEpi) ? 2 * 6 * 128 * 2 : 0;
-  static constexpr int kFixedBytes =
-      1024 /*align slack*/ + kStagingBytes + (kParamFloats + kXchFloats) * 4 + 256;
+  static constexpr int kFixedBytes = 1024 /*align slack*/ + kStagingBytes + kParamFloats * 4 + 256;
   static constexpr int kStagesFit = (227 * 1024 - kFixedBytes) / kStageBytes;
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
   static constexpr int kSmemBytes = kFixedBytes + kStages * kStageBytes;
@@ -182,11 +173,70 @@ struct WarpStager {
     }
     if (nbuf == 2) buf ^= 1;
   }
+  // ---- explicit-buffer forms (bf16 mode) ----
+  // fp32 box into buffer b
+  __device__ __forceinline__ void store_at(int b, const CUtensorMap* tm, const float (&v)[32],
+                                           int col0, int row0) {
+    const uint32_t lane = lane_id();
+    if (lane == 0) tma_store_wait_read<0>();
+    __syncwarp();
+    const uint32_t dst = smem_u32(base) + b * 4096 + lane * 128;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((j ^ (lane & 7)) << 4)),
+                   "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                   : "memory");
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tm, base + b * 4096, col0, row0);
+      tma_store_commit();
+    }
+  }
+  // A bf16 box is 32 rows x 64 columns (128 B rows): 32 fp32 values per lane fill HALF a row
+  // (16-byte chunks 4*half .. 4*half+3, XOR-swizzled like the TMA map expects).  `pending` = how
+  // many earlier bulk groups may still be reading OTHER buffers when half 0 claims buffer b.
+  template <int kPending>
+  __device__ __forceinline__ void put_bf16(int b, const float (&v)[32], int half) {
+    const uint32_t lane = lane_id();
+    if (half == 0) {
+      if (lane == 0) tma_store_wait_read<kPending>();
+      __syncwarp();
+    }
+    const uint32_t dst = smem_u32(base) + b * 4096 + lane * 128;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(
+                       dst + (((4 * half + j) ^ (lane & 7)) << 4)),
+                   "r"(pack_bf16x2(v[8 * j], v[8 * j + 1])), "r"(pack_bf16x2(v[8 * j + 2], v[8 * j + 3])),
+                   "r"(pack_bf16x2(v[8 * j + 4], v[8 * j + 5])), "r"(pack_bf16x2(v[8 * j + 6], v[8 * j + 7]))
+                   : "memory");
+  }
+  __device__ __forceinline__ void flush_bf16(int b, const CUtensorMap* tm, int col0, int row0) {
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane_id() == 0) {
+      tma_store_2d(tm, base + b * 4096, col0, row0);
+      tma_store_commit();
+    }
+  }
   __device__ __forceinline__ void drain() {
     if (lane_id() == 0) tma_store_wait_all<0>();
     __syncwarp();
   }
 };
+
+// One 32-column chunk `c` (0..7) of an N = 256 row-complete output: fp32 boxes go out per chunk,
+// bf16 boxes per chunk PAIR (64 columns).  `b` = staging buffer (0 / 1) reserved for this output.
+__device__ __forceinline__ void rowln_emit(WarpStager& stager, int b, const CUtensorMap* tm,
+                                           bool as_bf16, const float (&v)[32], int c, int row0) {
+  if (as_bf16) {
+    stager.put_bf16<0>(b, v, c & 1);
+    if (c & 1) stager.flush_bf16(b, tm, (c - 1) * 32, row0);
+  } else {
+    stager.store_at(b, tm, v, c * 32, row0);
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 // Row-complete epilogue math, shared by the RowLN GEMM and the fused FFN kernel.  The calling warp
@@ -197,7 +247,7 @@ struct WarpStager {
 // Values round-trip TMEM between passes (tcgen05.st), statistics are two-pass (mean, then centred
 // second moment) like torch's LayerNorm.
 // ------------------------------------------------------------------------------------------------
-template <bool kDual>
+template <bool kDual, bool kBf16 = false>
 __device__ __forceinline__ void rowln_finish(const GemmParams& p, const float* s_param,
                                              uint32_t tacc, int row0, uint32_t lane,
                                              WarpStager& stager, const float* part_row) {
@@ -299,7 +349,8 @@ __device__ __forceinline__ void rowln_finish(const GemmParams& p, const float* s
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
           }
-          stager.store(&p.tmC, v, c * 32, row0);
+          if constexpr (kBf16) rowln_emit(stager, 0, &p.tmC, p.c_bf16 != 0, v, c, row0);
+          else stager.store(&p.tmC, v, c * 32, row0);
         }
       }
     }
@@ -346,7 +397,8 @@ __device__ __forceinline__ void rowln_finish(const GemmParams& p, const float* s
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
             }
-            stager.store(&p.tmC, v, c * 32, row0);
+            if constexpr (kBf16) rowln_emit(stager, 0, &p.tmC, p.c_bf16 != 0, v, c, row0);
+          else stager.store(&p.tmC, v, c * 32, row0);
           }
         }
         tmem_st_wait();
@@ -379,7 +431,8 @@ __device__ __forceinline__ void rowln_finish(const GemmParams& p, const float* s
                   (__uint_as_float(r[j]) - mean) * rstd * s_gA[c * 32 + j] + s_bA[c * 32 + j];
               v[j] = p.round_lnA ? round_tf32(y) : y;
             }
-            stager.store(&p.tmLnA, v, c * 32, row0);
+            if constexpr (kBf16) rowln_emit(stager, 0, &p.tmLnA, p.lnA_bf16 != 0, v, c, row0);
+            else stager.store(&p.tmLnA, v, c * 32, row0);
           }
           if (has_lnB) {
 #pragma unroll
@@ -388,7 +441,8 @@ __device__ __forceinline__ void rowln_finish(const GemmParams& p, const float* s
                   (__uint_as_float(r[j]) - mean) * rstd * s_gB[c * 32 + j] + s_bB[c * 32 + j];
               v[j] = p.round_lnB ? round_tf32(y) : y;
             }
-            stager.store(&p.tmLnB, v, c * 32, row0);
+            if constexpr (kBf16) rowln_emit(stager, 1, &p.tmLnB, p.lnB_bf16 != 0, v, c, row0);
+            else stager.store(&p.tmLnB, v, c * 32, row0);
           }
         }
       }
@@ -398,219 +452,11 @@ __device__ __forceinline__ void rowln_finish(const GemmParams& p, const float* s
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// rowln_finish with TWO warps per TMEM lane quadrant (RowLN GEMM, kWideEpi): the calling warp owns
-// rows row0 .. row0+31 and the column half [128 part, 128 part + 128); LayerNorm partial sums and
-// the row dots cross to the partner warp through `xch` behind a 64-thread named barrier.  Same
-// arithmetic as rowln_finish; the per-thread serial chain is half as long.  No split-K.
-// ------------------------------------------------------------------------------------------------
-template <bool kDual>
-__device__ __forceinline__ void rowln_finish2(const GemmParams& p, const float* s_param,
-                                              uint32_t tacc, int row0, uint32_t lane,
-                                              WarpStager& stager, int part, float* xch,
-                                              int row_in_cta, uint32_t bar_id) {
-  const float* s_bias = s_param;
-  const float* s_g0 = s_param + 256;
-  const float* s_b0 = s_param + 512;
-  const float* s_gA = s_param + 768;
-  const float* s_bA = s_param + 1024;
-  const float* s_gB = s_param + 1280;
-  const float* s_bB = s_param + 1536;
-  const float* s_d1 = s_param + 1792;
-  const float* s_d2 = s_param + 2048;
-  const int m = row0 + static_cast<int>(lane);
-  const bool valid = m < p.M;
-  const bool has_ln0 = p.ln0_g != nullptr;
-  const bool has_lnA = p.lnA_g != nullptr;
-  const bool has_lnB = p.lnB_g != nullptr;
-  const bool any_ln = has_ln0 || has_lnA || has_lnB;
-  const bool has_dots = p.dots_out != nullptr;
-  const int c_beg = part * 4, c_end = c_beg + 4;
-  // every thread of both warps runs the same sequence of exchanges (the conditions are kernel-
-  // uniform), so the barrier counts always match
-  auto exchange = [&](int slot, float mine) -> float {
-    float* cell = xch + (slot * 128 + row_in_cta) * 2;
-    cell[part] = mine;
-    named_bar_sync(bar_id, 64);
-    return mine + cell[part ^ 1];
-  };
-  float w1 = 1.0f, w2 = 0.0f;
-  if (kDual) {
-    const int seg = (valid ? m : p.M - 1) / p.rows_per_seg;
-    w1 = p.rowscale1[seg];
-    w2 = p.rowscale2[seg];
-  }
-  // PASS A: v0 = residual + alpha * (combine(acc) + bias) over this warp's four chunks
-  float sum = 0.0f, dd1 = 0.0f, dd2 = 0.0f;
-  const bool has_res = p.residual != nullptr && valid;
-  const float4* rp0 = reinterpret_cast<const float4*>(
-      p.residual + (has_res ? static_cast<long long>(m) * p.ldr : 0));
-  float resn[32];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float4 f = has_res ? ld_act4(rp0 + c_beg * 8 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-    resn[4 * j] = f.x; resn[4 * j + 1] = f.y; resn[4 * j + 2] = f.z; resn[4 * j + 3] = f.w;
-  }
-  for (int c = c_beg; c < c_end; ++c) {
-    uint32_t r[32];
-    uint32_t r2[kDual ? 32 : 1];
-    tmem_ld32(tacc + c * 32, r);
-    if constexpr (kDual) tmem_ld32(tacc + 256 + c * 32, r2);
-    float res[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) res[j] = resn[j];
-    if (c + 1 < c_end) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 f = has_res ? ld_act4(rp0 + (c + 1) * 8 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-        resn[4 * j] = f.x; resn[4 * j + 1] = f.y; resn[4 * j + 2] = f.z; resn[4 * j + 3] = f.w;
-      }
-    }
-    tmem_ld_wait();
-    float v[32];
-    if constexpr (kDual) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        v[j] = w1 * __uint_as_float(r[j]) + w2 * __uint_as_float(r2[j]);
-      if (p.seg_bias) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += w1 * s_d1[c * 32 + j] + w2 * s_d2[c * 32 + j];
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-    }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      v[j] = res[j] + p.alpha * (v[j] + s_bias[c * 32 + j]);
-      sum += v[j];
-    }
-    if (any_ln) {
-      uint32_t w[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(v[j]);
-      tmem_st32(tacc + c * 32, w);
-    }
-    if (!has_ln0) {
-      if (has_dots) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          dd1 += v[j] * s_d1[c * 32 + j];
-          dd2 += v[j] * s_d2[c * 32 + j];
-        }
-      }
-      if (p.has_main) {
-        if (p.round_c) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
-        }
-        stager.store(&p.tmC, v, c * 32, row0);
-      }
-    }
-  }
-  if (any_ln) {
-    tmem_st_wait();
-    float mean = exchange(0, sum) * (1.0f / 256.0f);
-    // PASS B: centred second moment of v0
-    float ss = 0.0f;
-    for (int c = c_beg; c < c_end; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tacc + c * 32, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float d = __uint_as_float(r[j]) - mean;
-        ss += d * d;
-      }
-    }
-    float rstd = rsqrtf(exchange(1, ss) * (1.0f / 256.0f) + (has_ln0 ? p.eps0 : p.eps));
-    if (has_ln0) {
-      // PASS C: v1 = LN0(v0) -> TMEM, main output, dots, new sum
-      float sum1 = 0.0f;
-      for (int c = c_beg; c < c_end; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tacc + c * 32, r);
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          v[j] = (__uint_as_float(r[j]) - mean) * rstd * s_g0[c * 32 + j] + s_b0[c * 32 + j];
-          sum1 += v[j];
-          r[j] = __float_as_uint(v[j]);
-        }
-        tmem_st32(tacc + c * 32, r);
-        if (has_dots) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            dd1 += v[j] * s_d1[c * 32 + j];
-            dd2 += v[j] * s_d2[c * 32 + j];
-          }
-        }
-        if (p.has_main) {
-          if (p.round_c) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
-          }
-          stager.store(&p.tmC, v, c * 32, row0);
-        }
-      }
-      tmem_st_wait();
-      mean = exchange(2, sum1) * (1.0f / 256.0f);
-      // PASS D: centred second moment of v1
-      ss = 0.0f;
-      for (int c = c_beg; c < c_end; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tacc + c * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float d = __uint_as_float(r[j]) - mean;
-          ss += d * d;
-        }
-      }
-      rstd = rsqrtf(exchange(3, ss) * (1.0f / 256.0f) + p.eps);
-    }
-    // PASS E: LayerNorm outputs of v1
-    if (has_lnA || has_lnB) {
-      for (int c = c_beg; c < c_end; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tacc + c * 32, r);
-        tmem_ld_wait();
-        float v[32];
-        if (has_lnA) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float y =
-                (__uint_as_float(r[j]) - mean) * rstd * s_gA[c * 32 + j] + s_bA[c * 32 + j];
-            v[j] = p.round_lnA ? round_tf32(y) : y;
-          }
-          stager.store(&p.tmLnA, v, c * 32, row0);
-        }
-        if (has_lnB) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float y =
-                (__uint_as_float(r[j]) - mean) * rstd * s_gB[c * 32 + j] + s_bB[c * 32 + j];
-            v[j] = p.round_lnB ? round_tf32(y) : y;
-          }
-          stager.store(&p.tmLnB, v, c * 32, row0);
-        }
-      }
-    }
-  }
-  if (has_dots) {
-    dd1 = exchange(4, dd1);
-    dd2 = exchange(5, dd2);
-    if (part == 0 && valid) reinterpret_cast<float2*>(p.dots_out)[m] = make_float2(dd1, dd2);
-  }
-}
-
-template <bool kTf32, int kBlockN, int kMode, bool kDual, int kCtas, int kAct, bool kStats = false,
-          bool kSeq = false, bool kWideEpi = false>
+template <bool kTf32, int kBlockN, int kMode, bool kDual, int kCtas, int kAct, bool kSeq = false,
+          bool kWideEpi = false>
 __global__ void __launch_bounds__(GemmCfg<kTf32, kBlockN, kMode, kDual, kCtas, kSeq, kWideEpi>::kThreads, 1)
 gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<kTf32, kBlockN, kMode, kDual, kCtas, kSeq, kWideEpi>;
-  static_assert(!kWideEpi || !kStats, "wide epilogue: no statistics epilogue");
   static_assert(!kSeq || kDual, "the sequential mode is a dual mode");
   constexpr bool kPair = kCtas == 2;
   constexpr int kStages = Cfg::kStages;
@@ -621,8 +467,7 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
   uint8_t* s_stage = smem;                                        // kStages * kStageBytes
   uint8_t* s_staging = s_stage + kStages * Cfg::kStageBytes;      // kEpiWarps * 8192
   float* s_param = reinterpret_cast<float*>(s_staging + Cfg::kStagingBytes);
-  float* s_xch = s_param + Cfg::kParamFloats;
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_xch + Cfg::kXchFloats);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_param + Cfg::kParamFloats);
   uint64_t* full_bar = s_bar;                  // [kStages]
   uint64_t* empty_bar = s_bar + kStages;       // [kStages]
   uint64_t* tfull_bar = s_bar + 2 * kStages;   // [kAccStages]
@@ -793,12 +638,12 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
         const int col0 = half * (kBlockN / Cfg::kEpiParts);
         uint32_t r[2][32];
         tmem_ld32(tacc + col0, r[0]);
-        const bool do_stats = kStats && p.stats_out != nullptr && n0 + col0 >= p.stats_col0;  // warp-uniform
-        float st_n = 0.f, st_mean = 0.f, st_m2 = 0.f;
 #pragma unroll
         for (int c = 0; c < kChunks; ++c) {
           const int col = col0 + c * 32;
-          const bool live = n0 + col < p.N;  // warp-uniform
+          // warp-uniform; a bf16 box covers a 64-column pair, stored when its first half is live
+          // (columns past N are clipped by the TMA store)
+          const bool live = (!kTf32 && p.c_bf16) ? (n0 + (col & ~63) < p.N) : (n0 + col < p.N);
           // bias: uniform (same address in every lane) 16-byte loads served by L1
           float bv[32];
           if (p.bias != nullptr && n0 + col + 32 <= p.N) {
@@ -832,33 +677,17 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
               x = apply_act<kAct>(x, p.act);
               v[j] = p.round_c ? round_tf32(x) : x;
             }
-            if (do_stats) {
-              // two-pass statistics of the 32 values in registers, merged into the running
-              // (count, mean, M2) of this row's part (Chan et al.)
-              float s = 0.f;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) s += v[j];
-              const float mc = s * (1.0f / 32.0f);
-              float qd = 0.f;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float dj = v[j] - mc;
-                qd = fmaf(dj, dj, qd);
+            if (!kTf32 && p.c_bf16) {
+              static_assert(kTf32 || kChunks % 2 == 0, "bf16 boxes need an even number of chunks per warp");
+              stager.template put_bf16<Cfg::kStageBufs - 1>(stager.buf, v, c & 1);
+              if (c & 1) {
+                stager.flush_bf16(stager.buf, &p.tmC, n0 + col - 32, m0 + q * 32);
+                if (Cfg::kStageBufs == 2) stager.buf ^= 1;
               }
-              const float delta = mc - st_mean;
-              const float tot = st_n + 32.0f;
-              st_mean = fmaf(delta, __fdividef(32.0f, tot), st_mean);
-              st_m2 += qd + delta * delta * __fdividef(st_n * 32.0f, tot);
-              st_n = tot;
+            } else {
+              stager.store(&p.tmC, v, n0 + col, m0 + q * 32);
             }
-            stager.store(&p.tmC, v, n0 + col, m0 + q * 32);
           }
-        }
-        if (do_stats) {
-          const int mrow = m0 + q * 32 + static_cast<int>(lane);
-          if (mrow < p.M)
-            p.stats_out[static_cast<long long>(mrow) * p.stats_parts +
-                        (n0 + col0 - p.stats_col0) / (kBlockN / 2)] = make_float2(st_mean, st_m2);
         }
       } else {
         // ---------------------------- row-complete epilogue ----------------------------------
@@ -866,17 +695,6 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
         mbar_wait(&tfull_bar[as], aph);
         tc_fence_after_sync();
 
-        if constexpr (kWideEpi) {
-          // two warps per quadrant, 128 columns each (the host never combines this with split-K)
-          rowln_finish2<kDual>(p, s_param, tacc, m0 + q * 32, lane, stager, ew >> 2,
-                               s_xch + (it & 1) * (6 * 128 * 2), q * 32 + static_cast<int>(lane),
-                               1u + static_cast<uint32_t>(q));
-          tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) { if (kPair) mbar_arrive_leader(&tempty_bar[as]); else mbar_arrive(&tempty_bar[as]); }
-          if (++as == kAccStages) { as = 0; aph ^= 1; }
-          continue;
-        }
         const bool splitk = p.num_n_tiles == 2;
         unsigned int* flag =
             splitk ? p.flags + ((static_cast<long long>(m_blk) * 4 + q)) : nullptr;
@@ -919,7 +737,7 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
           __syncwarp();
         }
         const float* part_row = splitk ? p.partial + static_cast<long long>(m) * 256 : nullptr;
-        rowln_finish<kDual>(p, s_param, tacc, m0 + q * 32, lane, stager, part_row);
+        rowln_finish<kDual, !kTf32>(p, s_param, tacc, m0 + q * 32, lane, stager, part_row);
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) { if (kPair) mbar_arrive_leader(&tempty_bar[as]); else mbar_arrive(&tempty_bar[as]); }

@@ -50,6 +50,30 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, bool is_bf16
 
 int num_sms();
 
+// Function attributes (MaxDynamicSharedMemorySize) are per device: `mask` keeps one bit per device
+// ordinal, the caller sets the attribute when this returns true.
+inline bool first_use_on_device(unsigned long long& mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
+}
+
+// Same for attributes whose value grows with the problem (dynamic shared memory sized by T / V / D):
+// returns true when device `dev`'s recorded size is below `bytes` (and records it).
+struct PerDeviceMax {
+  int v[64] = {0};
+  bool raise(int bytes) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (v[dev & 63] >= bytes) return false;
+    v[dev & 63] = bytes;
+    return true;
+  }
+};
+
 // Uniform launch path: optional thread-block cluster, optional programmatic dependent launch
 // (g_debug[7] == 0 enables PDL; set it to 1 to fall back to plain stream-ordered launches).
 template <typename... KArgs, typename... Args>

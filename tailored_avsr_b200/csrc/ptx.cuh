@@ -272,6 +272,40 @@ __device__ __forceinline__ void umma_ts_tf32(uint32_t d_tmem, uint32_t a_tmem, u
       : "memory");
 }
 
+// D[tmem] (+)= A[tmem] . B[smem]^T, kind::f16 with bf16 operands: the A operand sits in tensor memory
+// as PACKED pairs - lane == row, 32-bit column j holds (A[row][2j] in the low half, A[row][2j+1] in
+// the high half) - so one K = 16 instruction reads 8 columns (verified on hardware by
+// tools/umma_probe.cu, variants 3 / 4 / 6).
+__device__ __forceinline__ void umma_ts_f16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// Shared-memory descriptor for an MN-major bf16 operand tile with the 128-byte swizzle, exactly
+// what a TMA box {64 elements of MN, K rows} writes: a row of 128 B holds 64 consecutive MN
+// elements of one K index, 8 consecutive rows (K indices) form a 1024-byte atom.
+//   LBO = byte distance between successive 64-element MN atoms (the stride between two boxes),
+//   SBO = byte distance between successive 8-row K atoms (1024 for a dense box).
+// One kind::f16 MMA consumes K = 16 = two atoms along K: advance the start address by 2048 B per
+// K step.  (tools/umma_probe.cu variants 1 / 2 / 5 pin this encoding on hardware.)
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128_b16(uint32_t smem_addr, uint32_t lbo,
+                                                                uint32_t sbo = 1024) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
 // Shared-memory descriptor for an MN-major operand tile with the 128-byte swizzle: rows of 128 B
 // run along MN (32 tf32 elements), 8 consecutive rows (= 8 K indices) form one 1024-byte atom
 // (a TMA box {32 elements of MN, K rows}).  `mn_atom_stride` is the byte distance between
@@ -427,6 +461,14 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
@@ -439,6 +481,34 @@ __device__ __forceinline__ float round_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
+}
+
+// Two fp32 -> one packed bf16x2 word (round to nearest even): `lo` in bits [0,16), `hi` in [16,32).
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+// coherent 16-byte / 8-byte / 4-byte loads of packed bf16 ACTIVATIONS (see ld_act)
+__device__ __forceinline__ uint4 ld_act_u4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint2 ld_act_u2(const void* p) {
+  uint2 v;
+  asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ unsigned short ld_act_u16(const void* p) {
+  unsigned short v;
+  asm volatile("ld.global.u16 %0, [%1];" : "=h"(v) : "l"(p));
+  return v;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

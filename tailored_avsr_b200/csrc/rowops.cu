@@ -2,6 +2,7 @@
 // (LayerNorm statistics + depthwise conv k=31 over time + gate multiply) and the learned_ave merge
 // weights.  All are coalesced along the channel dimension and use warp-shuffle reductions.
 #include <atomic>
+#include <type_traits>
 
 #include "host.h"
 #include "ptx.cuh"
@@ -16,9 +17,9 @@ template <int kVec>  // number of float4 per lane: D = 128 * kVec
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, long long ldx, int M, float eps,
                  const float* __restrict__ gA, const float* __restrict__ bA,
-                 float* __restrict__ outA, long long ldA, int roundA,
+                 void* __restrict__ outA, long long ldA, int roundA,
                  const float* __restrict__ gB, const float* __restrict__ bB,
-                 float* __restrict__ outB, long long ldB, int roundB, float scale) {
+                 void* __restrict__ outB, long long ldB, int roundB, float scale, int bf16_mask) {
   pdl_launch_dependents();
   pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -41,8 +42,9 @@ layernorm_kernel(const float* __restrict__ x, long long ldx, int M, float eps,
     ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
   }
   const float rstd = rsqrtf(warp_sum(ss) * inv_d + eps);
-  auto emit = [&](const float* g, const float* b, float* out, long long ld, int rnd) {
-    float4* o = reinterpret_cast<float4*>(out + static_cast<long long>(row) * ld);
+  auto emit = [&](const float* g, const float* b, void* out, long long ld, int rnd, bool as_bf16) {
+    float4* o = reinterpret_cast<float4*>(static_cast<float*>(out) + static_cast<long long>(row) * ld);
+    uint2* ob = reinterpret_cast<uint2*>(static_cast<uint16_t*>(out) + static_cast<long long>(row) * ld);
 #pragma unroll
     for (int i = 0; i < kVec; ++i) {
       const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + lane + 32 * i);
@@ -52,32 +54,52 @@ layernorm_kernel(const float* __restrict__ x, long long ldx, int M, float eps,
       y.y = (v[i].y * rstd * gg.y + bb.y) * scale;
       y.z = (v[i].z * rstd * gg.z + bb.z) * scale;
       y.w = (v[i].w * rstd * gg.w + bb.w) * scale;
+      if (as_bf16) {
+        ob[lane + 32 * i] = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+        continue;
+      }
       if (rnd) { y.x = round_tf32(y.x); y.y = round_tf32(y.y); y.z = round_tf32(y.z); y.w = round_tf32(y.w); }
       o[lane + 32 * i] = y;
     }
   };
-  if (outA) emit(gA, bA, outA, ldA, roundA);
-  if (outB) emit(gB, bB, outB, ldB, roundB);
+  if (outA) emit(gA, bA, outA, ldA, roundA, (bf16_mask & 1) != 0);
+  if (outB) emit(gB, bB, outB, ldB, roundB, (bf16_mask & 2) != 0);
+}
+
+// 4 consecutive activation elements as float4, fp32 or bf16 storage (index in units of 4 elements)
+template <bool kBf16>
+__device__ __forceinline__ float4 ld_act_vec4(const void* base, long long idx4) {
+  if constexpr (kBf16) {
+    const uint2 w = ld_act_u2(static_cast<const uint2*>(base) + idx4);
+    return make_float4(bf16_lo(w.x), bf16_hi(w.x), bf16_lo(w.y), bf16_hi(w.y));
+  } else {
+    return ld_act4(static_cast<const float4*>(base) + idx4);
+  }
+}
+template <bool kBf16>
+__device__ __forceinline__ const void* elem_ptr(const void* base, long long elem) {
+  return kBf16 ? static_cast<const void*>(static_cast<const uint16_t*>(base) + elem)
+               : static_cast<const void*>(static_cast<const float*>(base) + elem);
 }
 
 // ------------------------------------------------------------------------------------------------
 // CSGU pass 1: LayerNorm statistics of the gate half, one warp per frame.
 // ------------------------------------------------------------------------------------------------
-template <int kVec>  // Ch = 128 * kVec
+template <int kVec, bool kBf16>  // Ch = 128 * kVec
 __global__ void __launch_bounds__(256)
-csgu_stats_kernel(const float* __restrict__ h, long long ldh, int M, int Ch, float eps,
+csgu_stats_kernel(const void* __restrict__ h, long long ldh, int M, int Ch, float eps,
                   float2* __restrict__ stats) {
   pdl_launch_dependents();
   pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const uint32_t lane = lane_id();
-  const float4* g = reinterpret_cast<const float4*>(h + static_cast<long long>(row) * ldh + Ch);
+  const void* g = elem_ptr<kBf16>(h, static_cast<long long>(row) * ldh + Ch);
   float4 v[kVec];
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < kVec; ++i) {
-    v[i] = ld_act4(g + lane + 32 * i);
+    v[i] = ld_act_vec4<kBf16>(g, lane + 32 * i);
     sum += v[i].x + v[i].y + v[i].z + v[i].w;
   }
   const float inv_d = 1.0f / (128.0f * kVec);
@@ -113,39 +135,17 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsr
                : "memory");
 }
 
-// sum over the 32 lanes of 32 per-lane values in 31 shuffles: afterwards v[0] of lane j holds the
-// warp total of value j (each step halves the values a lane carries and exchanges the other half)
-__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], uint32_t lane) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool up = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < off; ++i) {
-      const float send = up ? v[i] : v[i + off];
-      const float keep = up ? v[i + off] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  return v[0];
-}
-
-// Optional fused inputs / outputs (the two-branch block path):
-//   stats_part != null : LayerNorm statistics arrive as n_part partial (mean, M2) pairs per frame,
-//                        each over part_w channels, written by the channel_proj1 GEMM epilogue
-//                        (Chan's parallel combination; no stand-alone statistics pass)
-//   dots_out != null   : per frame the partial dot products of this CTA's 128 output channels with
-//                        dva / dvb (the folded pooling_proj / weight_proj vectors of the learned_ave
-//                        merge, encoder_layer.py:243,258): dots_out[(frame * gridDim.x + slab)]
-template <bool kFused>
+// kBf16: h and out are bf16 (the gate tile sits in shared memory as bf16, 24 KB instead of 47 KB);
+// LayerNorm, the convolution and the gate product stay fp32.
+template <bool kBf16>
 __global__ void __launch_bounds__(kCh, 4)
-csgu_conv_kernel(const float* __restrict__ h, long long ldh, const float* __restrict__ norm_g,
+csgu_conv_kernel(const void* __restrict__ h, long long ldh, const float* __restrict__ norm_g,
                  const float* __restrict__ norm_b, const float* __restrict__ conv_w,
                  const float* __restrict__ conv_b, const float2* __restrict__ stats,
-                 const float2* __restrict__ stats_part, int n_part, int part_w, float eps,
-                 const float* __restrict__ dva, const float* __restrict__ dvb,
-                 float2* __restrict__ dots_out,
-                 float* __restrict__ out, long long ldo, int T, int Ch, int round_out) {
-  __shared__ __align__(16) float s_tile[kRows][kCh];
+                 void* __restrict__ out, long long ldo, int T, int Ch, int round_out) {
+  using elem_t = typename std::conditional<kBf16, uint16_t, float>::type;
+  constexpr int kPer16 = 16 / static_cast<int>(sizeof(elem_t));  // elements per 16-byte request
+  __shared__ __align__(16) elem_t s_tile[kRows][kCh];
   __shared__ float2 s_ab[kRows];  // per frame: (rstd, -mean*rstd); (0,0) outside [0,T)
   pdl_launch_dependents();
   // weights first (not produced by the predecessor), then wait for the gate activations / stats
@@ -159,60 +159,32 @@ csgu_conv_kernel(const float* __restrict__ h, long long ldh, const float* __rest
     bet = __ldg(norm_b + c_early);
     cb = __ldg(conv_b + c_early);
   }
-  float dwa = 0.f, dwb = 0.f;
-  if (kFused && dots_out != nullptr && c_early < Ch) {
-    dwa = __ldg(dva + c_early);
-    dwb = __ldg(dvb + c_early);
-  }
   pdl_wait();
   const int c0 = blockIdx.x * kCh;
   const int t0 = blockIdx.y * kSeg;
   const int b = blockIdx.z;
   const long long row0 = static_cast<long long>(b) * T;
-  const float* gbase = h + Ch + c0;
-  for (int idx = threadIdx.x; idx < kRows * (kCh / 4); idx += kCh) {
-    const int r = idx / (kCh / 4), q = idx % (kCh / 4);
+  const elem_t* hb = static_cast<const elem_t*>(h);
+  const elem_t* gbase = hb + Ch + c0;
+  for (int idx = threadIdx.x; idx < kRows * (kCh / kPer16); idx += kCh) {
+    const int r = idx / (kCh / kPer16), q = idx % (kCh / kPer16);
     const int t = t0 - kHalo + r;
     const bool ok = t >= 0 && t < T;
-    cp_async16_zfill(&s_tile[r][q * 4], gbase + (row0 + (ok ? t : 0)) * ldh + q * 4, ok);
+    cp_async16_zfill(&s_tile[r][q * kPer16], gbase + (row0 + (ok ? t : 0)) * ldh + q * kPer16, ok);
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
   for (int i = threadIdx.x; i < kRows; i += kCh) {
     const int t = t0 - kHalo + i;
     float2 ab = make_float2(0.f, 0.f);
     if (t >= 0 && t < T) {
-      float2 st;
-      if (kFused && stats_part != nullptr) {
-        // all partials of the frame are requested before the first use (n_part <= 16)
-        const float2* sp = stats_part + (row0 + t) * n_part;
-        float2 pq[16];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) pq[q] = q < n_part ? ld_act2(sp + q) : make_float2(0.f, 0.f);
-        float msum = 0.f, m2 = 0.f;
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          msum += pq[q].x;
-          m2 += pq[q].y;
-        }
-        const float mean = msum / static_cast<float>(n_part);
-        float dev = 0.f;
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const float dq = q < n_part ? pq[q].x - mean : 0.f;
-          dev = fmaf(dq, dq, dev);
-        }
-        const float var = (m2 + static_cast<float>(part_w) * dev) /
-                          (static_cast<float>(part_w) * static_cast<float>(n_part));
-        st = make_float2(mean, rsqrtf(var + eps));
-      } else {
-        st = stats[row0 + t];
-      }
+      const float2 st = stats[row0 + t];
       ab = make_float2(st.y, -st.x * st.y);
     }
     s_ab[i] = ab;
   }
   const int c = c0 + threadIdx.x;
-  const float* rcol = h + c;
+  const elem_t* rcol = hb + c;
+  elem_t* ocol = static_cast<elem_t*>(out) + c;
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
@@ -221,15 +193,23 @@ csgu_conv_kernel(const float* __restrict__ h, long long ldh, const float* __rest
     if (tb >= T) break;
     float rv[kGrp];          // carried half, loaded early so the latency hides behind the FMAs
 #pragma unroll
-    for (int o = 0; o < kGrp; ++o) rv[o] = tb + o < T ? ld_act(rcol + (row0 + tb + o) * ldh) : 0.f;
+    for (int o = 0; o < kGrp; ++o) {
+      if constexpr (kBf16)
+        rv[o] = tb + o < T ? __uint_as_float(static_cast<uint32_t>(ld_act_u16(rcol + (row0 + tb + o) * ldh)) << 16) : 0.f;
+      else
+        rv[o] = tb + o < T ? ld_act(rcol + (row0 + tb + o) * ldh) : 0.f;
+    }
     float acc[kGrp];
 #pragma unroll
     for (int o = 0; o < kGrp; ++o) acc[o] = 0.f;
 #pragma unroll
     for (int ii = 0; ii < kGrp + kTaps - 1; ++ii) {
       const float2 ab = s_ab[g0 + ii];
+      float xv;
+      if constexpr (kBf16) xv = __uint_as_float(static_cast<uint32_t>(s_tile[g0 + ii][threadIdx.x]) << 16);
+      else xv = s_tile[g0 + ii][threadIdx.x];
       // LN(g) = (x - mean) * rstd * gamma + beta; exactly 0 outside [0,T) (conv zero padding)
-      const float xh = fmaf(s_tile[g0 + ii][threadIdx.x], ab.x, ab.y);
+      const float xh = fmaf(xv, ab.x, ab.y);
       const float xn = ab.x != 0.f ? fmaf(xh, gam, bet) : 0.f;
 #pragma unroll
       for (int o = 0; o < kGrp; ++o) {
@@ -237,43 +217,16 @@ csgu_conv_kernel(const float* __restrict__ h, long long ldh, const float* __rest
         if (k >= 0 && k < kTaps) acc[o] = fmaf(w[k], xn, acc[o]);
       }
     }
-    if constexpr (!kFused) {
-#pragma unroll
-      for (int o = 0; o < kGrp; ++o) {
-        const int t = tb + o;
-        if (t < T) {
-          const float y = rv[o] * (acc[o] + cb);
-          out[(row0 + t) * ldo + c] = round_out ? round_tf32(y) : y;
-        }
-      }
-      continue;
-    }
-    float dv[2 * kGrp];
 #pragma unroll
     for (int o = 0; o < kGrp; ++o) {
       const int t = tb + o;
-      float y = rv[o] * (acc[o] + cb);
-      y = round_out ? round_tf32(y) : y;
-      if (t < T) out[(row0 + t) * ldo + c] = y;
-      dv[2 * o] = y * dwa;
-      dv[2 * o + 1] = y * dwb;
-    }
-    if (dots_out != nullptr) {  // block-uniform
-      const uint32_t lane = threadIdx.x & 31;
-      const int wrp = threadIdx.x >> 5;
-      // the per-warp totals are exchanged through rows 0 / 1 of the gate tile: group g only reads
-      // rows >= 16 g, and every thread writes the column it alone has been reading, so the rows
-      // are dead by the time they are overwritten (two rows = double buffer, one barrier per group)
-      const int buf = (g0 / kGrp) & 1;
-      s_tile[buf][threadIdx.x] = warp_transpose_sum32(dv, lane);
-      __syncthreads();
-      if (wrp == 0) {
-        float tot = 0.f;
-#pragma unroll
-        for (int q = 0; q < kCh / 32; ++q) tot += s_tile[buf][q * 32 + lane];
-        const int t = tb + static_cast<int>(lane >> 1);
-        if (t < T)
-          reinterpret_cast<float*>(dots_out)[((row0 + t) * gridDim.x + blockIdx.x) * 2 + (lane & 1)] = tot;
+      if (t < T) {
+        const float y = rv[o] * (acc[o] + cb);
+        if constexpr (kBf16) {
+          ocol[(row0 + t) * ldo] = static_cast<uint16_t>(pack_bf16x2(y, 0.f) & 0xFFFFu);
+        } else {
+          ocol[(row0 + t) * ldo] = round_out ? round_tf32(y) : y;
+        }
       }
     }
   }
@@ -285,19 +238,19 @@ csgu_conv_kernel(const float* __restrict__ h, long long ldh, const float* __rest
 // directly on the attention context and the gated cgMLP activations, with the branch output
 // projections folded into va / vb.  One warp per row, 16-byte coalesced loads.
 // ------------------------------------------------------------------------------------------------
+template <bool kBf16>
 __global__ void __launch_bounds__(256)
-row_dots_kernel(const float* __restrict__ a1, long long ld1, int K1, const float* __restrict__ va1,
+row_dots_kernel(const void* __restrict__ a1, long long ld1, int K1, const float* __restrict__ va1,
                 const float* __restrict__ vb1, float2* __restrict__ out1,
-                const float* __restrict__ a2, long long ld2, int K2, const float* __restrict__ va2,
+                const void* __restrict__ a2, long long ld2, int K2, const float* __restrict__ va2,
                 const float* __restrict__ vb2, float2* __restrict__ out2, int M) {
   pdl_launch_dependents();
   pdl_wait();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  // all loads of a row are issued before the first FMA (8 x 16 B per lane in flight): the kernel
+  // all loads of a row are issued before the first FMA (8 requests per lane in flight): the kernel
   // is a pure L2 -> register stream, so exposed load latency is the only thing that can slow it
-  auto dots2 = [&](const float* a, int K, const float* va, const float* vb, float& sa, float& sb) {
-    const float4* r = reinterpret_cast<const float4*>(a);
+  auto dots2 = [&](const void* a, int K, const float* va, const float* vb, float& sa, float& sb) {
     const float4* pa = reinterpret_cast<const float4*>(va);
     const float4* pb = reinterpret_cast<const float4*>(vb);
     const int n4 = K / 4;
@@ -305,7 +258,7 @@ row_dots_kernel(const float* __restrict__ a1, long long ld1, int K1, const float
       float4 x[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        x[j] = k0 + 32 * j < n4 ? ld_act4(r + k0 + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        x[j] = k0 + 32 * j < n4 ? ld_act_vec4<kBf16>(a, k0 + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         if (k0 + 32 * j < n4) {
@@ -319,8 +272,8 @@ row_dots_kernel(const float* __restrict__ a1, long long ld1, int K1, const float
   };
   for (int m = blockIdx.x * 8 + warp; m < M; m += gridDim.x * 8) {
     float s[4] = {0.f, 0.f, 0.f, 0.f};
-    dots2(a1 + static_cast<long long>(m) * ld1, K1, va1, vb1, s[0], s[1]);
-    if (a2 != nullptr) dots2(a2 + static_cast<long long>(m) * ld2, K2, va2, vb2, s[2], s[3]);
+    dots2(elem_ptr<kBf16>(a1, static_cast<long long>(m) * ld1), K1, va1, vb1, s[0], s[1]);
+    if (a2 != nullptr) dots2(elem_ptr<kBf16>(a2, static_cast<long long>(m) * ld2), K2, va2, vb2, s[2], s[3]);
 #pragma unroll
     for (int i = 0; i < 4; ++i) s[i] = warp_sum(s[i]);
     if (lane == 0) {
@@ -435,10 +388,11 @@ merge_weights_plain_kernel(const float2* __restrict__ dots1, const float2* __res
 // out[m,:] = w1[m / rows_per_seg] * a[m,:] + w2[m / rows_per_seg] * b[m,:]   (the weighted modality
 // average in front of the fusion FFN, adaptive_audiovisual_fusion.py:187-194)
 // ------------------------------------------------------------------------------------------------
+template <bool kOutBf16>
 __global__ void __launch_bounds__(256)
 scale_add_rows_kernel(const float* __restrict__ a, long long lda, const float* __restrict__ b,
                       long long ldb, const float* __restrict__ w1, const float* __restrict__ w2,
-                      int rows_per_seg, float* __restrict__ out, long long ldo, int M, int D4) {
+                      int rows_per_seg, void* __restrict__ out, long long ldo, int M, int D4) {
   pdl_launch_dependents();
   pdl_wait();
   const long long total = static_cast<long long>(M) * D4;
@@ -449,8 +403,38 @@ scale_add_rows_kernel(const float* __restrict__ a, long long lda, const float* _
     const float s1 = ld_act(w1 + seg), s2 = ld_act(w2 + seg);
     const float4 x = ld_act4(reinterpret_cast<const float4*>(a + m * lda) + q);
     const float4 y = ld_act4(reinterpret_cast<const float4*>(b + m * ldb) + q);
-    reinterpret_cast<float4*>(out + m * ldo)[q] =
+    const float4 r =
         make_float4(s1 * x.x + s2 * y.x, s1 * x.y + s2 * y.y, s1 * x.z + s2 * y.z, s1 * x.w + s2 * y.w);
+    if constexpr (kOutBf16)
+      reinterpret_cast<uint2*>(static_cast<uint16_t*>(out) + m * ldo)[q] =
+          make_uint2(pack_bf16x2(r.x, r.y), pack_bf16x2(r.z, r.w));
+    else
+      reinterpret_cast<float4*>(static_cast<float*>(out) + m * ldo)[q] = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3xTF32 operand split ("tf32x3" mode): x = hi + lo with hi = tf32(x), lo = x - hi (exact in fp32;
+// TMA rounds it to TF32 on load).  The product  a.b ~ a_hi b_hi + a_hi b_lo + a_lo b_hi  then runs as
+// ONE TF32 GEMM over a tripled reduction axis: activations are written as [hi | hi | lo] (pattern
+// 0), weights as [hi | lo | hi] (pattern 1), K -> 3K.  Error ~2^-21 instead of 2^-11 per product.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+split_tf32_kernel(const float* __restrict__ in, long long ld, float* __restrict__ out, long long ldo,
+                  int M, int K4, int pattern) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long total = static_cast<long long>(M) * K4;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int m = static_cast<int>(idx / K4), q = static_cast<int>(idx % K4);
+    const float4 x = ld_act4(reinterpret_cast<const float4*>(in + m * ld) + q);
+    const float4 hi = make_float4(round_tf32(x.x), round_tf32(x.y), round_tf32(x.z), round_tf32(x.w));
+    const float4 lo = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+    float4* o = reinterpret_cast<float4*>(out + m * ldo);
+    o[q] = hi;
+    o[K4 + q] = pattern == 0 ? hi : lo;
+    o[2 * K4 + q] = pattern == 0 ? lo : hi;
   }
 }
 
@@ -464,10 +448,12 @@ scale_add_rows_kernel(const float* __restrict__ a, long long lda, const float* _
 // whose (B*T2, F2*C) channels-last output feeds the 4864 -> 256 projection with permuted columns.
 // CTA = one (b, t2); thread = conv1 channel c: every store is a coalesced C*4-byte run.
 // ------------------------------------------------------------------------------------------------
+template <bool kBf16>
 __global__ void __launch_bounds__(256)
 conv2d_sub_im2col_kernel(const float* __restrict__ x, int Tin, int F, const float* __restrict__ w1,
                          const float* __restrict__ b1, int C, int T2, int F2,
-                         float* __restrict__ A) {
+                         void* __restrict__ A) {
+  using elem_t = typename std::conditional<kBf16, uint16_t, float>::type;
   extern __shared__ float s_x[];  // 7 input rows x F
   pdl_launch_dependents();
   const int b = blockIdx.x / T2, t2 = blockIdx.x % T2;
@@ -480,7 +466,7 @@ conv2d_sub_im2col_kernel(const float* __restrict__ x, int Tin, int F, const floa
 #pragma unroll
     for (int k = 0; k < 9; ++k) w[k] = __ldg(w1 + c * 9 + k);
     const float bias = __ldg(b1 + c);
-    float* arow = A + (static_cast<long long>(b) * T2 + t2) * F2 * 9 * C + c;
+    elem_t* arow = static_cast<elem_t*>(A) + (static_cast<long long>(b) * T2 + t2) * F2 * 9 * C + c;
     for (int f2 = 0; f2 < F2; ++f2) {
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
@@ -492,7 +478,11 @@ conv2d_sub_im2col_kernel(const float* __restrict__ x, int Tin, int F, const floa
           for (int pp = 0; pp < 3; ++pp)
 #pragma unroll
             for (int q = 0; q < 3; ++q) v = fmaf(w[pp * 3 + q], xp[pp * F + q], v);
-          arow[(static_cast<long long>(f2) * 9 + i * 3 + j) * C] = fmaxf(v, 0.f);
+          if constexpr (kBf16)
+            arow[(static_cast<long long>(f2) * 9 + i * 3 + j) * C] =
+                static_cast<uint16_t>(pack_bf16x2(fmaxf(v, 0.f), 0.f) & 0xFFFFu);
+          else
+            arow[(static_cast<long long>(f2) * 9 + i * 3 + j) * C] = fmaxf(v, 0.f);
         }
       }
     }
@@ -504,9 +494,10 @@ conv2d_sub_im2col_kernel(const float* __restrict__ x, int Tin, int F, const floa
 using namespace tavsr;
 
 extern "C" int tavsr_layernorm(const float* x, long long ldx, int M, int D, float eps,
-                               const float* gA, const float* bA, float* outA, long long ldA,
-                               int roundA, const float* gB, const float* bB, float* outB,
-                               long long ldB, int roundB, float scale, void* stream) {
+                               const float* gA, const float* bA, void* outA, long long ldA,
+                               int roundA, const float* gB, const float* bB, void* outB,
+                               long long ldB, int roundB, float scale, int dtype, void* stream) {
+  const int bf16_mask = ((dtype & TAVSR_DT_LNA_BF16) ? 1 : 0) | ((dtype & TAVSR_DT_LNB_BF16) ? 2 : 0);
   TAVSR_REQUIRE(M > 0 && D > 0 && D % 128 == 0 && D <= 2048, "layernorm: D=%d unsupported", D);
   TAVSR_REQUIRE(ldx % 4 == 0 && (!outA || ldA % 4 == 0) && (!outB || ldB % 4 == 0),
                 "layernorm: pitches must be multiples of 4");
@@ -517,7 +508,8 @@ extern "C" int tavsr_layernorm(const float* x, long long ldx, int M, int D, floa
 #define TAVSR_LN_CASE(V)                                                                          \
   case V:                                                                                         \
     TAVSR_CUDA_OK(launch_kernel(layernorm_kernel<V>, dim3(grid), dim3(256), 0, s, 0, x, ldx, M, eps, \
-                                gA, bA, outA, ldA, roundA, gB, bB, outB, ldB, roundB, scale));    \
+                                gA, bA, outA, ldA, roundA, gB, bB, outB, ldB, roundB, scale,      \
+                                bf16_mask));                                                      \
     break;
   switch (D / 128) {
     TAVSR_LN_CASE(1) TAVSR_LN_CASE(2) TAVSR_LN_CASE(3) TAVSR_LN_CASE(4) TAVSR_LN_CASE(6)
@@ -531,88 +523,70 @@ extern "C" int tavsr_layernorm(const float* x, long long ldx, int M, int D, floa
   return 0;
 }
 
-static int csgu_launch(const float* h, long long ldh, const float* norm_g, const float* norm_b,
-                       const float* conv_w, const float* conv_b, float* out, long long ldo,
-                       float* stats, const float* stats_part, int n_part, int part_w,
-                       const float* dva, const float* dvb, float* dots_out, int B, int T, int Ch,
-                       int ksize, float eps, int round_out, void* stream) {
-  TAVSR_REQUIRE(ksize == kTaps, "csgu: only kernel size 31 is built (got %d)", ksize);
-  TAVSR_REQUIRE(B > 0 && T > 0 && Ch > 0 && Ch % 128 == 0 && Ch <= 2048, "csgu: bad shape");
-  TAVSR_REQUIRE(ldh % 4 == 0 && (stats != nullptr || stats_part != nullptr),
-                "csgu: bad pitch / missing stats scratch");
-  TAVSR_REQUIRE(!stats_part || (n_part >= 1 && n_part <= 16 && n_part * part_w == Ch),
-                "csgu: partial statistics must tile the %d gate channels (n_part=%d, part_w=%d)",
-                Ch, n_part, part_w);
-  TAVSR_REQUIRE(!dots_out || (dva && dvb), "csgu: dots_out needs dva and dvb");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
+template <bool kBf16>
+static int csgu_launch(const void* h, long long ldh, const float* norm_g, const float* norm_b,
+                       const float* conv_w, const float* conv_b, void* out, long long ldo,
+                       float* stats, int B, int T, int Ch, float eps, int round_out, cudaStream_t s) {
   const int M = B * T;
   const int grid1 = (M + 7) / 8;
   float2* st = reinterpret_cast<float2*>(stats);
-  int launches = 1;
-  if (stats_part == nullptr) {
-    ++launches;
-    switch (Ch / 128) {
-      case 1: TAVSR_CUDA_OK(launch_kernel(csgu_stats_kernel<1>, dim3(grid1), dim3(256), 0, s, 0, h, ldh, M, Ch, eps, st)); break;
-      case 2: TAVSR_CUDA_OK(launch_kernel(csgu_stats_kernel<2>, dim3(grid1), dim3(256), 0, s, 0, h, ldh, M, Ch, eps, st)); break;
-      case 4: TAVSR_CUDA_OK(launch_kernel(csgu_stats_kernel<4>, dim3(grid1), dim3(256), 0, s, 0, h, ldh, M, Ch, eps, st)); break;
-      case 8: TAVSR_CUDA_OK(launch_kernel(csgu_stats_kernel<8>, dim3(grid1), dim3(256), 0, s, 0, h, ldh, M, Ch, eps, st)); break;
-      case 16: TAVSR_CUDA_OK(launch_kernel(csgu_stats_kernel<16>, dim3(grid1), dim3(256), 0, s, 0, h, ldh, M, Ch, eps, st)); break;
-      default: return set_error(TAVSR_ERR_UNSUPPORTED, "csgu: Ch=%d not instantiated", Ch);
-    }
-    TAVSR_CUDA_OK(cudaGetLastError());
+#define TAVSR_STATS_CASE(V)                                                                        \
+  case V:                                                                                          \
+    TAVSR_CUDA_OK(launch_kernel(csgu_stats_kernel<V, kBf16>, dim3(grid1), dim3(256), 0, s, 0, h,   \
+                                ldh, M, Ch, eps, st));                                             \
+    break;
+  switch (Ch / 128) {
+    TAVSR_STATS_CASE(1) TAVSR_STATS_CASE(2) TAVSR_STATS_CASE(4) TAVSR_STATS_CASE(8) TAVSR_STATS_CASE(16)
+    default: return set_error(TAVSR_ERR_UNSUPPORTED, "csgu: Ch=%d not instantiated", Ch);
   }
+#undef TAVSR_STATS_CASE
   dim3 grid2(Ch / kCh, (T + kSeg - 1) / kSeg, B);
-  if (stats_part != nullptr || dots_out != nullptr) {
-    TAVSR_CUDA_OK(launch_kernel(csgu_conv_kernel<true>, grid2, dim3(kCh), 0, s, 0, h, ldh, norm_g, norm_b,
-                                conv_w, conv_b, static_cast<const float2*>(st),
-                                reinterpret_cast<const float2*>(stats_part), n_part, part_w, eps, dva,
-                                dvb, reinterpret_cast<float2*>(dots_out), out, ldo, T, Ch, round_out));
-  } else {
-    TAVSR_CUDA_OK(launch_kernel(csgu_conv_kernel<false>, grid2, dim3(kCh), 0, s, 0, h, ldh, norm_g, norm_b,
-                                conv_w, conv_b, static_cast<const float2*>(st),
-                                static_cast<const float2*>(nullptr), 0, 0, eps,
-                                static_cast<const float*>(nullptr), static_cast<const float*>(nullptr),
-                                static_cast<float2*>(nullptr), out, ldo, T, Ch, round_out));
-  }
-  g_launches.fetch_add(launches, std::memory_order_relaxed);
+  TAVSR_CUDA_OK(launch_kernel(csgu_conv_kernel<kBf16>, grid2, dim3(kCh), 0, s, 0, h, ldh, norm_g, norm_b,
+                              conv_w, conv_b, static_cast<const float2*>(st), out, ldo, T, Ch,
+                              round_out));
+  g_launches.fetch_add(2, std::memory_order_relaxed);
   return 0;
 }
 
-extern "C" int tavsr_csgu_fwd(const float* h, long long ldh, const float* norm_g,
+extern "C" int tavsr_csgu_fwd(const void* h, long long ldh, const float* norm_g,
                               const float* norm_b, const float* conv_w, const float* conv_b,
-                              float* out, long long ldo, float* stats, int B, int T, int Ch,
-                              int ksize, float eps, int round_out, void* stream) {
-  return csgu_launch(h, ldh, norm_g, norm_b, conv_w, conv_b, out, ldo, stats, nullptr, 0, 0, nullptr,
-                     nullptr, nullptr, B, T, Ch, ksize, eps, round_out, stream);
+                              void* out, long long ldo, float* stats, int B, int T, int Ch,
+                              int ksize, float eps, int round_out, int dtype, void* stream) {
+  TAVSR_REQUIRE(ksize == kTaps, "csgu: only kernel size 31 is built (got %d)", ksize);
+  TAVSR_REQUIRE(B > 0 && T > 0 && Ch > 0 && Ch % 128 == 0 && Ch <= 2048, "csgu: bad shape");
+  const int op = dtype & TAVSR_DT_MASK;
+  TAVSR_REQUIRE(op == TAVSR_DT_TF32 || (op == TAVSR_DT_BF16 && (dtype & TAVSR_DT_OUT_BF16)),
+                "csgu: dtype is TAVSR_DT_TF32 (fp32 h / out) or TAVSR_DT_BF16 | TAVSR_DT_OUT_BF16");
+  const bool bf16 = op == TAVSR_DT_BF16;
+  TAVSR_REQUIRE(ldh % (bf16 ? 8 : 4) == 0 && stats != nullptr, "csgu: bad pitch / missing stats scratch");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return bf16 ? csgu_launch<true>(h, ldh, norm_g, norm_b, conv_w, conv_b, out, ldo, stats, B, T, Ch,
+                                  eps, round_out, s)
+              : csgu_launch<false>(h, ldh, norm_g, norm_b, conv_w, conv_b, out, ldo, stats, B, T, Ch,
+                                   eps, round_out, s);
 }
 
-extern "C" int tavsr_csgu_fwd_fused(const float* h, long long ldh, const float* norm_g,
-                                    const float* norm_b, const float* conv_w, const float* conv_b,
-                                    float* out, long long ldo, float* stats,
-                                    const float* stats_part, int n_part, int part_w,
-                                    const float* dva, const float* dvb, float* dots_out, int B,
-                                    int T, int Ch, int ksize, float eps, int round_out,
-                                    void* stream) {
-  TAVSR_REQUIRE(stats_part != nullptr || stats != nullptr,
-                "csgu_fused: needs stats_part or a stats scratch");
-  return csgu_launch(h, ldh, norm_g, norm_b, conv_w, conv_b, out, ldo, stats_part ? nullptr : stats,
-                     stats_part, n_part, part_w, dva, dvb, dots_out, B, T, Ch, ksize, eps, round_out,
-                     stream);
-}
-
-extern "C" int tavsr_row_dots(const float* a1, long long ld1, int K1, const float* va1,
-                              const float* vb1, float* out1, const float* a2, long long ld2, int K2,
-                              const float* va2, const float* vb2, float* out2, int M, void* stream) {
-  TAVSR_REQUIRE(M > 0 && a1 && va1 && vb1 && out1 && K1 > 0 && K1 % 4 == 0 && ld1 % 4 == 0,
+extern "C" int tavsr_row_dots(const void* a1, long long ld1, int K1, const float* va1,
+                              const float* vb1, float* out1, const void* a2, long long ld2, int K2,
+                              const float* va2, const float* vb2, float* out2, int M, int dtype,
+                              void* stream) {
+  const bool bf16 = (dtype & TAVSR_DT_MASK) == TAVSR_DT_BF16;
+  const int al = bf16 ? 8 : 4;
+  TAVSR_REQUIRE(M > 0 && a1 && va1 && vb1 && out1 && K1 > 0 && K1 % 4 == 0 && ld1 % al == 0,
                 "row_dots: bad first operand (K=%d)", K1);
-  TAVSR_REQUIRE(!a2 || (va2 && vb2 && out2 && K2 > 0 && K2 % 4 == 0 && ld2 % 4 == 0),
+  TAVSR_REQUIRE(!a2 || (va2 && vb2 && out2 && K2 > 0 && K2 % 4 == 0 && ld2 % al == 0),
                 "row_dots: bad second operand (K=%d)", K2);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int grid = (M + 7) / 8;
   if (grid > 8 * num_sms()) grid = 8 * num_sms();
-  TAVSR_CUDA_OK(launch_kernel(row_dots_kernel, dim3(grid), dim3(256), 0, s, 0, a1, ld1, K1, va1, vb1,
-                              reinterpret_cast<float2*>(out1), a2, ld2, K2, va2, vb2,
-                              reinterpret_cast<float2*>(out2), M));
+  if (bf16)
+    TAVSR_CUDA_OK(launch_kernel(row_dots_kernel<true>, dim3(grid), dim3(256), 0, s, 0, a1, ld1, K1, va1,
+                                vb1, reinterpret_cast<float2*>(out1), a2, ld2, K2, va2, vb2,
+                                reinterpret_cast<float2*>(out2), M));
+  else
+    TAVSR_CUDA_OK(launch_kernel(row_dots_kernel<false>, dim3(grid), dim3(256), 0, s, 0, a1, ld1, K1, va1,
+                                vb1, reinterpret_cast<float2*>(out1), a2, ld2, K2, va2, vb2,
+                                reinterpret_cast<float2*>(out2), M));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
@@ -650,8 +624,8 @@ extern "C" int tavsr_merge_learned_ave_weights(const float* dots1, const float* 
 }
 
 extern "C" int tavsr_scale_add_rows(const float* a, long long lda, const float* b, long long ldb,
-                                    const float* w1, const float* w2, int rows_per_seg, float* out,
-                                    long long ldo, int M, int D, void* stream) {
+                                    const float* w1, const float* w2, int rows_per_seg, void* out,
+                                    long long ldo, int M, int D, int dtype, void* stream) {
   TAVSR_REQUIRE(M > 0 && D > 0 && D % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && ldo % 4 == 0 &&
                     rows_per_seg > 0 && a && b && w1 && w2 && out,
                 "scale_add_rows: bad arguments (M=%d D=%d)", M, D);
@@ -659,21 +633,46 @@ extern "C" int tavsr_scale_add_rows(const float* a, long long lda, const float* 
   const long long total = static_cast<long long>(M) * (D / 4);
   long long blocks = (total + 255) / 256;
   if (blocks > 8ll * num_sms()) blocks = 8ll * num_sms();
-  TAVSR_CUDA_OK(launch_kernel(scale_add_rows_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0,
-                              s, 0, a, lda, b, ldb, w1, w2, rows_per_seg, out, ldo, M, D / 4));
+  if (dtype & TAVSR_DT_OUT_BF16)
+    TAVSR_CUDA_OK(launch_kernel(scale_add_rows_kernel<true>, dim3(static_cast<unsigned>(blocks)),
+                                dim3(256), 0, s, 0, a, lda, b, ldb, w1, w2, rows_per_seg, out, ldo, M,
+                                D / 4));
+  else
+    TAVSR_CUDA_OK(launch_kernel(scale_add_rows_kernel<false>, dim3(static_cast<unsigned>(blocks)),
+                                dim3(256), 0, s, 0, a, lda, b, ldb, w1, w2, rows_per_seg, out, ldo, M,
+                                D / 4));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+extern "C" int tavsr_split_tf32(const float* in, long long ld, float* out, long long ldo, int M,
+                                int K, int pattern, void* stream) {
+  TAVSR_REQUIRE(M > 0 && K > 0 && K % 4 == 0 && ld % 4 == 0 && ldo % 4 == 0 && in && out &&
+                    (pattern == 0 || pattern == 1),
+                "split_tf32: bad arguments (M=%d K=%d pattern=%d)", M, K, pattern);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long total = static_cast<long long>(M) * (K / 4);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 8ll * num_sms()) blocks = 8ll * num_sms();
+  TAVSR_CUDA_OK(launch_kernel(split_tf32_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, s, 0,
+                              in, ld, out, ldo, M, K / 4, pattern));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
 
 extern "C" int tavsr_conv2d_sub_im2col(const float* x, int B, int Tin, int F, const float* w1,
-                                       const float* b1, int C, float* A, void* stream) {
+                                       const float* b1, int C, void* A, int dtype, void* stream) {
   TAVSR_REQUIRE(B > 0 && Tin >= 7 && F >= 7 && C > 0 && x && w1 && b1 && A,
                 "conv2d_sub: bad arguments (B=%d Tin=%d F=%d C=%d)", B, Tin, F, C);
   const int T2 = ((Tin - 1) / 2 - 1) / 2, F2 = ((F - 1) / 2 - 1) / 2;
   TAVSR_REQUIRE(T2 >= 1 && F2 >= 1 && 7 * F * 4 <= 48 * 1024, "conv2d_sub: unsupported shape");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  TAVSR_CUDA_OK(launch_kernel(conv2d_sub_im2col_kernel, dim3(B * T2), dim3(256),
-                              static_cast<size_t>(7 * F * 4), s, 0, x, Tin, F, w1, b1, C, T2, F2, A));
+  if (dtype & TAVSR_DT_OUT_BF16)
+    TAVSR_CUDA_OK(launch_kernel(conv2d_sub_im2col_kernel<true>, dim3(B * T2), dim3(256),
+                                static_cast<size_t>(7 * F * 4), s, 0, x, Tin, F, w1, b1, C, T2, F2, A));
+  else
+    TAVSR_CUDA_OK(launch_kernel(conv2d_sub_im2col_kernel<false>, dim3(B * T2), dim3(256),
+                                static_cast<size_t>(7 * F * 4), s, 0, x, Tin, F, w1, b1, C, T2, F2, A));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }

@@ -77,14 +77,26 @@ class CTCPrefixScorer:
 
     def score_partial(self, y: torch.Tensor, ids: Optional[torch.Tensor], state: Any,
                       x: torch.Tensor):
-        """Single-hypothesis form: y (ylen,), state from init_state/select_state."""
-        score, (r_new, psi_new) = self.batch_score_partial(
-            y.unsqueeze(0), None if ids is None else ids.unsqueeze(0), [state], x)
-        return score[0], (r_new, psi_new)
+        """Single-hypothesis form used by espnet's non-batch `BeamSearch` (the path
+        asr_inference.py:276-303 falls back to): y (ylen,), state from init_state / select_state.
+        Like espnet's scorer it returns ONE SCORE PER ENTRY OF `ids` (not a full-V vector -
+        BeamSearch does `weighted_scores[part_ids] += w * part_scores`) and a state indexed by the
+        position in `ids`: (r (len(ids), T, 2), log_psi (len(ids),))."""
+        score, (r_new, psi_new) = self.batch_score_partial(y.unsqueeze(0), None, [state], x)
+        if ids is None:
+            ids = torch.arange(score.shape[1], device=score.device)
+        idx = ids.to(score.device).long()
+        return score[0, idx], (r_new[0][:, idx, :].permute(1, 0, 2), psi_new[0, idx])
 
     def select_state(self, state, i: int, new_id: Optional[int] = None):
-        """State of hypothesis i extended by token new_id (views into the step's device buffers)."""
+        """Three-argument form (BatchBeamSearch): state = what batch_score_partial returned,
+        i = hypothesis, new_id = the token it is extended by.  Two-argument form (BeamSearch):
+        state = what score_partial returned, i = position of the chosen token in its `ids`.
+        Both return the (r (T,2), log_psi) state of the extended hypothesis (views into the
+        step's device buffers)."""
+        if state is None:
+            return None
         r_new, psi_new = state
-        if new_id is None:  # already a selected state
-            return state
+        if new_id is None:
+            return r_new[i], psi_new[i]
         return r_new[i, :, new_id, :], psi_new[i, new_id]

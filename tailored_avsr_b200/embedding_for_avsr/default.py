@@ -95,21 +95,25 @@ class DefaultEmbeddingLayerForAVSR(EmbeddingForAVSRAbsLayer):
                 lambda: (conv[0].weight.reshape(C, 9).contiguous(),
                          conv[2].weight.permute(0, 2, 3, 1).reshape(C, 9 * C).contiguous(),
                          lin.weight.view(-1, C, Fd).permute(0, 2, 1).reshape(-1, Fd * C).contiguous()))
-            a_mat = ops.conv2d_sub_im2col(xs_pad.contiguous().float(), pk[0], conv[0].bias)
-            h2 = ops.gemm_bias_act(a_mat, pk[1], conv[2].bias, act=ops.ACT_RELU).view(B * T, Fd * C)
+            adt = engine.act_dtype()
+            a_mat = ops.conv2d_sub_im2col(xs_pad.contiguous().float(), pk[0], conv[0].bias, out_dtype=adt)
+            h2 = engine.linear(a_mat, pk[1], conv[2].bias, self._packed, "conv2", act=ops.ACT_RELU,
+                               out_dtype=adt).view(B * T, Fd * C)
             x = torch.empty((B * T, d), device=dev, dtype=torch.float32)
-            ops.gemm_rowln(h2, pk[2], lin.bias, out_main=x)
+            engine.linear_rowln(h2, pk[2], lin.bias, self._packed, "embout", out_main=x)
             return x.view(B, T, d), masks[:, :, :-2:2][:, :, :-2:2]
         B, T, Fin = xs_pad.shape
-        x2 = xs_pad.reshape(B * T, Fin).contiguous().float()
         if self.embed is None:
             return xs_pad, masks
+        x2 = engine.operand(xs_pad.reshape(B * T, Fin).contiguous().float())
         x = torch.empty((B * T, d), device=dev, dtype=torch.float32)
         if isinstance(self.embed, torch.nn.Sequential):
             lin, ln = self.embed[0], self.embed[1]
-            ops.gemm_rowln(x2, lin.weight, lin.bias, ln0=(ln.weight, ln.bias), eps0=ln.eps, out_main=x)
+            engine.linear_rowln(x2, lin.weight, lin.bias, self._packed, "embin",
+                                ln0=(ln.weight, ln.bias), eps0=ln.eps, out_main=x)
         else:
-            ops.gemm_rowln(x2, self.embed.weight, self.embed.bias, out_main=x)
+            engine.linear_rowln(x2, self.embed.weight, self.embed.bias, self._packed, "embin",
+                                out_main=x)
         return x.view(B, T, d), masks
 
     def apply_pos_enc(self, xs_pad: torch.Tensor):

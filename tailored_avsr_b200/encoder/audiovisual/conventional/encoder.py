@@ -141,8 +141,9 @@ class ConventionalEncoder(AudioVisualAbsEncoder):
                 else:
                     s_["next_norm"] = ((enc.after_norm.weight, enc.after_norm.bias)
                                        if enc.normalize_before else None)
+                s_["nn_dtype"] = torch.float32 if i + 1 == n else None   # after_norm: fp32 output
                 s_["x"], s_["xn"] = layer.run(s_["x"], s_["xn"], s_["pos"].get(i), s_["lens"], B, T,
-                                              next_norm=s_["next_norm"])
+                                              next_norm=s_["next_norm"], next_norm_dtype=s_["nn_dtype"])
             if (i + 1) in self.interctc_layer_idx:
                 taps = []
                 for s_ in st:
@@ -156,7 +157,8 @@ class ConventionalEncoder(AudioVisualAbsEncoder):
                     for s_, tap in zip(st, taps):
                         src = fused if self.audiovisual_interctc_conditioning else tap
                         prob = ctc.softmax(src.view(B, T, d)).reshape(B * T, -1).contiguous()
-                        s_["x"], s_["xn"] = ops.vocab_residual(s_["x"], prob, cl.weight.contiguous(),
-                                                               cl.bias, ln=s_["next_norm"])
+                        s_["x"], s_["xn"] = ops.vocab_residual(
+                            s_["x"], prob, cl.weight.contiguous(), cl.bias, ln=s_["next_norm"],
+                            ln_dtype=s_["nn_dtype"] or engine.act_dtype())
         outs = [(s_["xn"] if s_["enc"].normalize_before else s_["x"]).view(B, T, d) for s_ in st]
         return (outs[0], inter), audio_masks, outs[1], video_masks, None

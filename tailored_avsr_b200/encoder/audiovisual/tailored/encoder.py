@@ -138,7 +138,9 @@ class TailoredEncoder(AudioVisualAbsEncoder):
         d = self._output_size
         ws = [a.linear_pos.weight for _, a in layers]
         wcat = self._packed.get("wpos_" + tag, ws, lambda: torch.cat(ws, 0).contiguous())
-        p_all = ops.gemm_bias_act(pos_emb.reshape(-1, d).contiguous().float(), wcat, None)
+        pe = engine.operand(pos_emb.reshape(-1, d).contiguous().float())
+        p_all = engine.linear(pe, wcat, None, self._packed, "wpos_" + tag + ".w",
+                              out_dtype=engine.act_dtype())
         return {i: p_all[:, k * d:(k + 1) * d] for k, (i, _) in enumerate(layers)}
 
     def forward(self, audio_pad, audio_masks, video_pad, video_masks, prev_states=None, ctc=None,
@@ -164,7 +166,8 @@ class TailoredEncoder(AudioVisualAbsEncoder):
         # modality encoding (:251-263) while stacking the two streams into one (2*B*T, d) matrix
         x = torch.cat([(audio + me[0]).reshape(M, d), (video + me[1]).reshape(M, d)], 0).contiguous().float()
         first = self.encoders[0]
-        xn = ops.layernorm(x, first.norm_ff_macaron.weight, first.norm_ff_macaron.bias, eps=1e-12)
+        xn = ops.layernorm(x, first.norm_ff_macaron.weight, first.norm_ff_macaron.bias, eps=1e-12,
+                           out_dtype=engine.act_dtype())
         la = engine.lens_from_mask(audio_masks, B, T, x.device)
         lv = engine.lens_from_mask(video_masks, B, T, x.device)
         pa = self._pos_proj_all(a_pos, "acoustic")
@@ -179,7 +182,10 @@ class TailoredEncoder(AudioVisualAbsEncoder):
                 next_norm = (nxt.norm_ff_macaron.weight, nxt.norm_ff_macaron.bias)
             else:
                 next_norm = after
-            x, xn = layer.run(x, xn, pa.get(i), pv.get(i), la, lv, B, T, next_norm=next_norm)
+            # the last block's trailing LayerNorm is after_norm: the fp32 encoder output
+            nn_dtype = torch.float32 if i + 1 == n else None
+            x, xn = layer.run(x, xn, pa.get(i), pv.get(i), la, lv, B, T, next_norm=next_norm,
+                              next_norm_dtype=nn_dtype)
             if taps_on and (i + 1) in self.interctc_layer_idx:
                 # intermediate outputs are normalised too (:275-278), fused (:280-286), and with
                 # conditioning the posteriors are fed back into BOTH streams (:291-318)
@@ -197,7 +203,7 @@ class TailoredEncoder(AudioVisualAbsEncoder):
                     else:
                         prob = ctc.softmax(t_out.view(2 * B, T, d)).reshape(2 * M, -1)
                     x, xn = ops.vocab_residual(x, prob.contiguous(), cl.weight.contiguous(), cl.bias,
-                                               ln=next_norm)
+                                               ln=next_norm, ln_dtype=nn_dtype or engine.act_dtype())
         out = xn if self.normalize_before else x
         a_out = out[:M].view(B, T, d)
         if inter:

@@ -55,29 +55,37 @@ class TailoredEncoderLayer(torch.nn.Module):
                                    f"None: {a}, {c}.")
             if a is None and c is None:
                 raise NotImplementedError(f"{tag} stream without a tailored module is not built")
+            if a is not None and (a.d_k != 64 or a.h * a.d_k != self.size):
+                raise NotImplementedError(
+                    f"the B200 attention kernel is built for head width d_k = 64; {tag} attention "
+                    f"has h={a.h}, d_k={a.d_k}")
         if self.training and (self.dropout.p > 0 or self.stochastic_depth_rate > 0):
             raise NotImplementedError("training-mode dropout / stochastic depth are not built on "
                                       "the B200 path yet; use .eval()")
 
-    def run(self, x, xn, pos_proj_a, pos_proj_v, lens_a, lens_v, B, T, next_norm=None):
+    def run(self, x, xn, pos_proj_a, pos_proj_v, lens_a, lens_v, B, T, next_norm=None,
+            next_norm_dtype=None):
         """Core on 2-D activations holding BOTH streams stacked: rows [0, B*T) audio,
-        [B*T, 2*B*T) video.  x: block input, xn: norm_ff_macaron(x).  Returns (y, yn)."""
+        [B*T, 2*B*T) video.  x: block input (fp32), xn: norm_ff_macaron(x) in operand storage.
+        Returns (y, yn); yn is stored as `next_norm_dtype` (default: operand storage)."""
         d = self.size
         M = B * T
         dev = x.device
-        new2 = lambda: torch.empty((2 * M, d), device=dev, dtype=torch.float32)  # noqa: E731
+        adt = engine.act_dtype()
+        new2 = lambda dt=torch.float32: torch.empty((2 * M, d), device=dev, dtype=dt)  # noqa: E731
         # shared macaron FFN over both streams; per-stream branch norms differ -> plain output, then
         # the stream-specific LayerNorm is fused as lnA of two half-height launches below.
         x_a = new2()
-        xb_in = new2()  # per-stream branch input (its own LayerNorm)
+        xb_in = new2(adt)  # per-stream branch input (its own LayerNorm)
         for s, tag in enumerate(("acoustic", "visual")):
             norm = getattr(self, f"{tag}_norm_mha", None) if getattr(self, f"{tag}_attn") is not None \
                 else getattr(self, f"{tag}_norm_cgmlp")
             sl = slice(s * M, (s + 1) * M)
             engine.ffn_block(x[sl], xn[sl], self.feed_forward_macaron, out_main=x_a[sl],
-                             lnA=(norm.weight, norm.bias), out_lnA=xb_in[sl])
+                             lnA=(norm.weight, norm.bias), out_lnA=xb_in[sl], cache=self._packed,
+                             key="ffm")
         x_b = new2()
-        xf = new2()
+        xf = new2(adt)
         lnF = (self.norm_ff.weight, self.norm_ff.bias)
         for s, (tag, pos_proj, lens) in enumerate((("acoustic", pos_proj_a, lens_a),
                                                    ("visual", pos_proj_v, lens_v))):
@@ -89,18 +97,20 @@ class TailoredEncoderLayer(torch.nn.Module):
                                               "not built on the B200 path")
                 ctx = engine.attention_ctx(xb_in[sl], attn, pos_proj, lens, B, T, self._packed,
                                            f"{tag}_qkv")
-                ops.gemm_rowln(ctx, attn.linear_out.weight, attn.linear_out.bias, residual=x_a[sl],
-                               alpha=1.0, out_main=x_b[sl], lnA=lnF, out_lnA=xf[sl])
+                engine.linear_rowln(ctx, attn.linear_out.weight, attn.linear_out.bias, self._packed,
+                                    f"{tag}_lo", residual=x_a[sl], alpha=1.0, out_main=x_b[sl],
+                                    lnA=lnF, out_lnA=xf[sl])
             else:
                 cg = getattr(self, f"{tag}_cgmlp")
                 u = engine.cgmlp_gated(xb_in[sl], cg, B, T, self._packed, f"{tag}_conv")
-                ops.gemm_rowln(u, cg.channel_proj2.weight, cg.channel_proj2.bias, residual=x_a[sl],
-                               alpha=1.0, out_main=x_b[sl], lnA=lnF, out_lnA=xf[sl])
+                engine.linear_rowln(u, cg.channel_proj2.weight, cg.channel_proj2.bias, self._packed,
+                                    f"{tag}_p2", residual=x_a[sl], alpha=1.0, out_main=x_b[sl],
+                                    lnA=lnF, out_lnA=xf[sl])
         y = new2()
-        yn = new2() if next_norm is not None else None
+        yn = new2(next_norm_dtype or adt) if next_norm is not None else None
         engine.ffn_block(x_b, xf, self.feed_forward, out_main=y,
                          ln0=(self.norm_final.weight, self.norm_final.bias),
-                         lnA=next_norm, out_lnA=yn)
+                         lnA=next_norm, out_lnA=yn, cache=self._packed, key="ff")
         return y, yn
 
     def forward(self, audio_input, audio_masks, video_input, video_masks, cache=None):
@@ -117,14 +127,15 @@ class TailoredEncoderLayer(torch.nn.Module):
         B, T, d = audio.shape
         M = B * T
         x = torch.cat([audio.reshape(M, d), video.reshape(M, d)], 0).contiguous().float()
-        xn = ops.layernorm(x, self.norm_ff_macaron.weight, self.norm_ff_macaron.bias, eps=1e-12)
+        xn = ops.layernorm(x, self.norm_ff_macaron.weight, self.norm_ff_macaron.bias, eps=1e-12,
+                           out_dtype=engine.act_dtype())
         la = engine.lens_from_mask(audio_masks, B, T, x.device)
         lv = engine.lens_from_mask(video_masks, B, T, x.device)
         pa = pv = None
         if self.acoustic_attn is not None and audio_pos is not None:
-            pa = engine.pos_projection(self.acoustic_attn, audio_pos.float())
+            pa = engine.pos_projection(self.acoustic_attn, audio_pos.float(), self._packed)
         if self.visual_attn is not None and video_pos is not None:
-            pv = engine.pos_projection(self.visual_attn, video_pos.float())
+            pv = engine.pos_projection(self.visual_attn, video_pos.float(), self._packed)
         y, _ = self.run(x, xn, pa, pv, la, lv, B, T)
         a_out, v_out = y[:M].view(B, T, d), y[M:].view(B, T, d)
         a_ret = (a_out, audio_pos) if audio_pos is not None else a_out

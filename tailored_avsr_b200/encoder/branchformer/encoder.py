@@ -160,12 +160,15 @@ class MyBranchformerEncoder(AbsEncoder):
         d = self._output_size
         ws = [a.linear_pos.weight for _, a in attn_layers]
         wcat = self._packed.get("wpos", ws, lambda: torch.cat(ws, 0).contiguous())
-        p_all = ops.gemm_bias_act(pos_emb.reshape(-1, d).contiguous().float(), wcat, None)
+        pe = engine.operand(pos_emb.reshape(-1, d).contiguous().float())
+        p_all = engine.linear(pe, wcat, None, self._packed, "wpos.w", out_dtype=engine.act_dtype())
         return {i: p_all[:, k * d:(k + 1) * d] for k, (i, _) in enumerate(attn_layers)}
 
     def _embed(self, xs_pad: torch.Tensor, masks: torch.Tensor, first_norm):
-        """Input layer + x*sqrt(d) + first LayerNorm.  Returns (x2d, xn2d, pos_emb, masks, B, T)."""
+        """Input layer + x*sqrt(d) + first LayerNorm.  Returns (x2d, xn2d, pos_emb, masks, B, T);
+        x2d is the fp32 residual stream, xn2d the first block's LayerNorm in operand storage."""
         d = self._output_size
+        adt = engine.act_dtype()
         if isinstance(self.embed, Conv2dSubsampling):
             short_status, limit_size = check_short_utt(self.embed, xs_pad.size(1))
             if short_status:
@@ -184,11 +187,11 @@ class MyBranchformerEncoder(AbsEncoder):
             C = conv[0].weight.shape[0]
             T, Fd = ((Tin - 1) // 2 - 1) // 2, ((Fin - 1) // 2 - 1) // 2
             x = torch.empty((B * T, d), device=xs_pad.device, dtype=torch.float32)
-            xn = torch.empty_like(x)
+            xn = torch.empty((B * T, d), device=xs_pad.device, dtype=adt)
             if engine.CUDNN_EMBED:
                 h = F.relu(F.conv2d(xs_pad.unsqueeze(1), conv[0].weight, conv[0].bias, stride=2))
                 h = F.relu(F.conv2d(h, conv[2].weight, conv[2].bias, stride=2))
-                h2 = h.transpose(1, 2).contiguous().view(B * T, C * Fd)
+                h2 = engine.operand(h.transpose(1, 2).contiguous().view(B * T, C * Fd))
                 w_lin = lin.weight
             else:
                 pk = self._packed.get(
@@ -196,11 +199,13 @@ class MyBranchformerEncoder(AbsEncoder):
                     lambda: (conv[0].weight.reshape(C, 9).contiguous(),
                              conv[2].weight.permute(0, 2, 3, 1).reshape(C, 9 * C).contiguous(),
                              lin.weight.view(-1, C, Fd).permute(0, 2, 1).reshape(-1, Fd * C).contiguous()))
-                a_mat = ops.conv2d_sub_im2col(xs_pad.contiguous().float(), pk[0], conv[0].bias)
-                h2 = ops.gemm_bias_act(a_mat, pk[1], conv[2].bias, act=ops.ACT_RELU).view(B * T, Fd * C)
+                a_mat = ops.conv2d_sub_im2col(xs_pad.contiguous().float(), pk[0], conv[0].bias,
+                                              out_dtype=adt)
+                h2 = engine.linear(a_mat, pk[1], conv[2].bias, self._packed, "conv2", act=ops.ACT_RELU,
+                                   out_dtype=adt).view(B * T, Fd * C)
                 w_lin = pk[2]
-            ops.gemm_rowln(h2, w_lin, lin.bias, alpha=math.sqrt(d), out_main=x,
-                           lnA=first_norm, out_lnA=xn)
+            engine.linear_rowln(h2, w_lin, lin.bias, self._packed, "embout", alpha=math.sqrt(d),
+                                out_main=x, lnA=first_norm, out_lnA=xn)
             masks = masks[:, :, :-2:2][:, :, :-2:2]
             pos_emb = self.embed.out[1].pos_emb(T, x.device)
         elif self.embed is not None:
@@ -210,9 +215,10 @@ class MyBranchformerEncoder(AbsEncoder):
             g16, b16 = self._packed.get("embln", [ln.weight, ln.bias],
                                         lambda: ((ln.weight * sc).contiguous(), (ln.bias * sc).contiguous()))
             x = torch.empty((B * T, d), device=xs_pad.device, dtype=torch.float32)
-            xn = torch.empty_like(x)
-            ops.gemm_rowln(xs_pad.reshape(B * T, Fd).contiguous().float(), lin.weight, lin.bias,
-                           ln0=(g16, b16), eps0=ln.eps, out_main=x, lnA=first_norm, out_lnA=xn)
+            xn = torch.empty((B * T, d), device=xs_pad.device, dtype=adt)
+            xin = engine.operand(xs_pad.reshape(B * T, Fd).contiguous().float())
+            engine.linear_rowln(xin, lin.weight, lin.bias, self._packed, "embin",
+                                ln0=(g16, b16), eps0=ln.eps, out_main=x, lnA=first_norm, out_lnA=xn)
             pos_emb = self.embed[3].pos_emb(T, x.device)
         else:
             if isinstance(xs_pad, tuple):
@@ -222,7 +228,7 @@ class MyBranchformerEncoder(AbsEncoder):
                                           "pass (conventional/encoder.py:149)")
             B, T, _ = xs.shape
             x = xs.reshape(B * T, d).contiguous().float()
-            xn = ops.layernorm(x, first_norm[0], first_norm[1], eps=1e-12)
+            xn = ops.layernorm(x, first_norm[0], first_norm[1], eps=1e-12, out_dtype=adt)
         return x, xn, pos_emb, masks, B, T
 
     def run_blocks(self, x, xn, pos_emb, lens, B, T, taps=(), stop_after: Optional[int] = None,
@@ -244,7 +250,10 @@ class MyBranchformerEncoder(AbsEncoder):
                 next_norm = (nxt.norm_ff_macaron.weight, nxt.norm_ff_macaron.bias)
             else:
                 next_norm = after
-            y, yn = layer.run(x, xn, pos.get(i), lens, B, T, next_norm=next_norm)
+            # the last block's trailing LayerNorm is after_norm, i.e. the fp32 encoder output
+            nn_dtype = torch.float32 if i == last else None
+            y, yn = layer.run(x, xn, pos.get(i), lens, B, T, next_norm=next_norm,
+                              next_norm_dtype=nn_dtype)
             if (i + 1) in taps:
                 t_out = y
                 if self.normalize_before:
@@ -254,7 +263,8 @@ class MyBranchformerEncoder(AbsEncoder):
                     prob = ctc.softmax(t_out.view(B, T, -1))
                     cl = self.conditioning_layer
                     y, yn = ops.vocab_residual(y, prob.reshape(B * T, -1).contiguous(),
-                                               cl.weight.contiguous(), cl.bias, ln=next_norm)
+                                               cl.weight.contiguous(), cl.bias, ln=next_norm,
+                                               ln_dtype=nn_dtype or engine.act_dtype())
             x, xn = y, yn
         out = xn if self.normalize_before else x
         return out, tap_outs

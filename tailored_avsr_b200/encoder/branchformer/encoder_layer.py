@@ -83,6 +83,10 @@ class MyBranchformerEncoderLayer(torch.nn.Module):
     def _check_supported(self):
         if self.size != 256:
             raise NotImplementedError("the B200 row-complete GEMM epilogue is built for size=256")
+        if self.attn is not None and (self.attn.d_k != 64 or self.attn.h * self.attn.d_k != self.size):
+            raise NotImplementedError(
+                f"the B200 attention kernel is built for head width d_k = 64 (attention_heads = "
+                f"size / 64); got h={self.attn.h}, d_k={self.attn.d_k}")
         if self.feed_forward_macaron is None or self.feed_forward is None:
             raise NotImplementedError("macaron=False / missing FFN is not built (the reference "
                                       "itself crashes at encoder_layer.py:193 without macaron)")
@@ -92,39 +96,44 @@ class MyBranchformerEncoderLayer(torch.nn.Module):
                                       "not built on the B200 path yet; use .eval()")
 
     def run(self, x: torch.Tensor, xn: torch.Tensor, pos_proj: Optional[torch.Tensor],
-            lens: torch.Tensor, B: int, T: int, next_norm=None, next_norm_round: bool = True):
+            lens: torch.Tensor, B: int, T: int, next_norm=None, next_norm_dtype=None):
         """Core of the block on 2-D activations.
 
-        x: (B*T, d) block input; xn: LN_ff_macaron(x); pos_proj: linear_pos(pos_emb) (2T-1, d) with
-        any row pitch.  Returns (y, yn): y = block output, yn = next_norm(y) or None.
+        x: (B*T, d) block input (fp32 residual stream); xn: LN_ff_macaron(x) in operand storage
+        (fp32, or bf16 in bf16 mode); pos_proj: linear_pos(pos_emb) (2T-1, d) with any row pitch.
+        Returns (y, yn): y = block output (fp32), yn = next_norm(y) or None, stored as
+        `next_norm_dtype` (default: operand storage; the encoder asks for fp32 when next_norm is
+        its after_norm, i.e. the encoder output).
         """
         d = self.size
         M = B * T
         dev = x.device
-        new = lambda: torch.empty((M, d), device=dev, dtype=torch.float32)  # noqa: E731
+        adt = engine.act_dtype()
+        new = lambda dt=torch.float32: torch.empty((M, d), device=dev, dtype=dt)  # noqa: E731
         x_a = new()
         two = self.use_two_branches
-        xa = new() if self.attn is not None else None
-        xm = new() if self.cgmlp is not None else None
+        xa = new(adt) if self.attn is not None else None
+        xm = new(adt) if self.cgmlp is not None else None
         lnA = (self.norm_mha.weight, self.norm_mha.bias) if self.attn is not None else None
         lnB = (self.norm_mlp.weight, self.norm_mlp.bias) if self.cgmlp is not None else None
         if lnA is None:  # cgMLP-only block: use slot A for norm_mlp
-            engine.ffn_block(x, xn, self.feed_forward_macaron, out_main=x_a, lnA=lnB, out_lnA=xm)
+            engine.ffn_block(x, xn, self.feed_forward_macaron, out_main=x_a, lnA=lnB, out_lnA=xm,
+                             cache=self._packed, key="ffm")
         else:
             engine.ffn_block(x, xn, self.feed_forward_macaron, out_main=x_a, lnA=lnA, out_lnA=xa,
-                             lnB=lnB, out_lnB=xm)
+                             lnB=lnB, out_lnB=xm, cache=self._packed, key="ffm")
 
         learned = two and self.merge_method == "learned_ave"
         concat = two and self.merge_method == "concat"
         x_b = new()
-        xf = new()
+        xf = new(adt)
         lnF = (self.norm_ff.weight, self.norm_ff.bias)
         mp = self.merge_proj
         if pos_proj is None and self.attn is not None:
             raise NotImplementedError("attention without relative positional embedding "
                                       "(abs_pos / selfattn) is not built on the B200 path")
         fold = (engine.FOLD_MERGE and two and not concat and d == 256
-                and self.cgmlp.channel_proj2.weight.shape[1] % 32 == 0)
+                and self.cgmlp.channel_proj2.weight.shape[1] % 64 == 0)
         if fold:
             # ---- merge with the branch output projections folded in (:208-209, 220, 227-309):
             #   x + Wm (w1 (Wo ctx + bo) + w2 (W2 g + b2)) + bm
@@ -133,8 +142,8 @@ class MyBranchformerEncoderLayer(torch.nn.Module):
             lo, p2 = self.attn.linear_out, self.cgmlp.channel_proj2
             f = self._packed.get(
                 "fold", [mp.weight, lo.weight, lo.bias, p2.weight, p2.bias],
-                lambda: (torch.cat([mp.weight.double() @ lo.weight.double(),
-                                    mp.weight.double() @ p2.weight.double()], 1).float().contiguous(),
+                lambda: (mp.weight.double() @ lo.weight.double(),
+                         mp.weight.double() @ p2.weight.double(),
                          (mp.weight.double() @ lo.bias.double()).float().contiguous(),
                          (mp.weight.double() @ p2.bias.double()).float().contiguous()))
             fv = None
@@ -153,27 +162,16 @@ class MyBranchformerEncoderLayer(torch.nn.Module):
                             float(pp2.bias.double() + pp2.weight.double().reshape(-1) @ p2.bias.double()),
                             float(wp1.bias.double() + wp1.weight.double().reshape(-1) @ lo.bias.double()),
                             float(wp2.bias.double() + wp2.weight.double().reshape(-1) @ p2.bias.double())]))
-            fused_dots = learned and engine.FUSE_DOTS
-            # the two branches are independent until the merge: the cgMLP chain runs on a side
-            # stream (captured as a fork / join in the CUDA graph) so its kernels fill the SMs the
-            # attention kernel's second wave and the persistent GEMMs' tails leave idle
+            # the two branches are independent until the merge: with TAVSR_BRANCH_FORK=1 the cgMLP
+            # chain runs on a side stream (a fork / join in the CUDA graph)
             with engine.branch_fork(dev) as side:
                 with side:
-                    u = engine.cgmlp_gated(xm, self.cgmlp, B, T, self._packed, "conv",
-                                           dots=(fv["va2"], fv["vb2"]) if fused_dots else None)
-                ctx = engine.attention_ctx(xa, self.attn, pos_proj, lens, B, T, self._packed, "qkv",
-                                           dots=(fv["va1"], fv["vb1"]) if fused_dots else None)
+                    u = engine.cgmlp_gated(xm, self.cgmlp, B, T, self._packed, "conv")
+                ctx = engine.attention_ctx(xa, self.attn, pos_proj, lens, B, T, self._packed, "qkv")
             if learned:
                 sc = fv["sc"]
-                if fused_dots:
-                    # the pooling / weight scores came out of the attention and CSGU epilogues as
-                    # partial dots (per head half / per 128-channel slab)
-                    (u, d2), (ctx, d1) = u, ctx
-                    w1, w2 = ops.merge_weights2(d1, d1.shape[1], d2, d2.shape[1], lens, None,
-                                                sc[0], sc[1], sc[2], sc[3], d, B, T)
-                else:
-                    d1, d2 = ops.row_dots(ctx, fv["va1"], fv["vb1"], u, fv["va2"], fv["vb2"])
-                    w1, w2 = ops.merge_weights(d1, d2, lens, sc[0], sc[1], sc[2], sc[3], d, B, T)
+                d1, d2 = ops.row_dots(ctx, fv["va1"], fv["vb1"], u, fv["va2"], fv["vb2"])
+                w1, w2 = ops.merge_weights(d1, d2, lens, sc[0], sc[1], sc[2], sc[3], d, B, T)
                 self.weight_global = w1.view(B, 1, 1)
                 self.weight_local = w2.view(B, 1, 1)
             else:
@@ -181,7 +179,17 @@ class MyBranchformerEncoderLayer(torch.nn.Module):
                     "fixedw" + str((B, str(dev))), [mp.weight],
                     lambda: (torch.full((B,), 1.0 - self.cgmlp_weight, device=dev, dtype=torch.float32),
                              torch.full((B,), float(self.cgmlp_weight), device=dev, dtype=torch.float32)))
-            ops.gemm_rowln(ctx, f[0], mp.bias, x2=u, k1=ctx.shape[1], segbias=(f[1], f[2]),
+            mode = engine.compute_dtype()
+            if mode == "tf32x3":
+                wf = self._packed.get("foldw:x3", [f[0], f[1]], lambda: torch.cat(
+                    [ops.split_tf32(f[0].float().contiguous(), "w"),
+                     ops.split_tf32(f[1].float().contiguous(), "w")], 1).contiguous())
+                xc, xu = ops.split_tf32(ctx, "x"), ops.split_tf32(u, "x")
+            else:
+                wf = self._packed.get("foldw:" + mode, [f[0], f[1]], lambda: torch.cat(
+                    [f[0], f[1]], 1).to(adt).contiguous())
+                xc, xu = ctx, u
+            ops.gemm_rowln(xc, wf, mp.bias, x2=xu, k1=xc.shape[1], segbias=(f[2], f[3]),
                            rowscale=(w1, w2), rows_per_seg=T, residual=x_a, alpha=1.0, out_main=x_b,
                            lnA=lnF, out_lnA=xf)
         else:
@@ -189,10 +197,10 @@ class MyBranchformerEncoderLayer(torch.nn.Module):
 
         # ---- FFN + norm_final (+ the next block's first LayerNorm) ----
         y = new()
-        yn = new() if next_norm is not None else None
+        yn = new(next_norm_dtype or adt) if next_norm is not None else None
         engine.ffn_block(x_b, xf, self.feed_forward, out_main=y,
                          ln0=(self.norm_final.weight, self.norm_final.bias),
-                         lnA=next_norm, out_lnA=yn, round_lnA=False)
+                         lnA=next_norm, out_lnA=yn, round_lnA=False, cache=self._packed, key="ff")
         return y, yn
 
     def _run_branches_unfolded(self, xa, xm, x_a, x_b, xf, pos_proj, lens, B, T, learned, concat):
@@ -203,30 +211,34 @@ class MyBranchformerEncoderLayer(torch.nn.Module):
         M = B * T
         dev = x_a.device
         two = self.use_two_branches
-        new = lambda: torch.empty((M, d), device=dev, dtype=torch.float32)  # noqa: E731
-        cat_buf = torch.empty((M, 2 * d), device=dev, dtype=torch.float32) if concat else None
+        adt = engine.act_dtype()
+        # x1 / x2 only feed the merge projection: operand storage
+        new = lambda: torch.empty((M, d), device=dev, dtype=adt)  # noqa: E731
+        cat_buf = torch.empty((M, 2 * d), device=dev, dtype=adt) if two else None
         x1 = x2 = d1 = d2 = None
         if self.attn is not None:
             if pos_proj is None:
                 raise NotImplementedError("attention without relative positional embedding "
                                           "(abs_pos / selfattn) is not built on the B200 path")
             ctx = engine.attention_ctx(xa, self.attn, pos_proj, lens, B, T, self._packed, "qkv")
-            x1 = cat_buf[:, :d] if concat else new()
+            x1 = cat_buf[:, :d] if two else new()
             dots = None
             if learned:
                 d1 = torch.empty((M, 2), device=dev, dtype=torch.float32)
                 dots = (self.pooling_proj1.weight.reshape(-1), self.weight_proj1.weight.reshape(-1))
-            ops.gemm_rowln(ctx, self.attn.linear_out.weight, self.attn.linear_out.bias,
-                           out_main=x1, dots=dots, dots_out=d1)
+            lo = self.attn.linear_out
+            engine.linear_rowln(ctx, lo.weight, lo.bias, self._packed, "lo", out_main=x1, dots=dots,
+                                dots_out=d1)
         if self.cgmlp is not None:
             u = engine.cgmlp_gated(xm, self.cgmlp, B, T, self._packed, "conv")
-            x2 = cat_buf[:, d:] if concat else new()
+            x2 = cat_buf[:, d:] if two else new()
             dots = None
             if learned:
                 d2 = torch.empty((M, 2), device=dev, dtype=torch.float32)
                 dots = (self.pooling_proj2.weight.reshape(-1), self.weight_proj2.weight.reshape(-1))
-            ops.gemm_rowln(u, self.cgmlp.channel_proj2.weight, self.cgmlp.channel_proj2.bias,
-                           out_main=x2, dots=dots, dots_out=d2)
+            p2 = self.cgmlp.channel_proj2
+            engine.linear_rowln(u, p2.weight, p2.bias, self._packed, "p2", out_main=x2, dots=dots,
+                                dots_out=d2)
 
         # ---- merge (:227-309) + norm_ff ----
         lnF = (self.norm_ff.weight, self.norm_ff.bias)
@@ -243,18 +255,28 @@ class MyBranchformerEncoderLayer(torch.nn.Module):
             else:
                 w1 = torch.full((B,), 1.0 - self.cgmlp_weight, device=dev, dtype=torch.float32)
                 w2 = torch.full((B,), float(self.cgmlp_weight), device=dev, dtype=torch.float32)
-            ops.gemm_rowln(x1, mp.weight, mp.bias, x2=x2, rowscale=(w1, w2), rows_per_seg=T,
-                           residual=x_a, alpha=1.0, out_main=x_b, lnA=lnF, out_lnA=xf)
+            # (w1 x1 + w2 x2) Wm^T as the sequential dual product over [x1 | x2] . [Wm | Wm]^T
+            mode = engine.compute_dtype()
+            if mode == "tf32x3":
+                wmm = self._packed.get("mp2:x3", [mp.weight], lambda: torch.cat(
+                    [ops.split_tf32(mp.weight.detach(), "w")] * 2, 1).contiguous())
+                xa1, xa2 = ops.split_tf32(x1.contiguous(), "x"), ops.split_tf32(x2.contiguous(), "x")
+            else:
+                wmm = self._packed.get("mp2:" + mode, [mp.weight], lambda: torch.cat(
+                    [mp.weight.detach(), mp.weight.detach()], 1).to(adt).contiguous())
+                xa1, xa2 = x1, x2
+            ops.gemm_rowln(xa1, wmm, mp.bias, x2=xa2, k1=xa1.shape[1], rowscale=(w1, w2),
+                           rows_per_seg=T, residual=x_a, alpha=1.0, out_main=x_b, lnA=lnF, out_lnA=xf)
         elif concat:
-            ops.gemm_rowln(cat_buf, mp.weight, mp.bias, residual=x_a, alpha=1.0, out_main=x_b,
-                           lnA=lnF, out_lnA=xf)
+            engine.linear_rowln(cat_buf, mp.weight, mp.bias, self._packed, "mp", residual=x_a,
+                                alpha=1.0, out_main=x_b, lnA=lnF, out_lnA=xf)
         else:
             xs = x2 if self.attn is None else x1
             if isinstance(mp, torch.nn.Identity):
                 raise NotImplementedError("single-branch block built with merge_proj=Identity "
                                           "(use_attn/use_cgmlp=False) is not built on the B200 path")
-            ops.gemm_rowln(xs, mp.weight, mp.bias, residual=x_a, alpha=1.0, out_main=x_b,
-                           lnA=lnF, out_lnA=xf)
+            engine.linear_rowln(xs, mp.weight, mp.bias, self._packed, "mp", residual=x_a, alpha=1.0,
+                                out_main=x_b, lnA=lnF, out_lnA=xf)
 
     # ---------------------------------------------------------------------------------------
     def forward(self, x_input, mask, cache=None):
@@ -271,10 +293,11 @@ class MyBranchformerEncoderLayer(torch.nn.Module):
         B, T, d = x.shape
         x2 = x.reshape(B * T, d).contiguous().float()
         lens = engine.lens_from_mask(mask, B, T, x.device)
-        xn = ops.layernorm(x2, self.norm_ff_macaron.weight, self.norm_ff_macaron.bias, eps=1e-12)
+        xn = ops.layernorm(x2, self.norm_ff_macaron.weight, self.norm_ff_macaron.bias, eps=1e-12,
+                           out_dtype=engine.act_dtype())
         pos_proj = None
         if pos_emb is not None and self.attn is not None:
-            pos_proj = engine.pos_projection(self.attn, pos_emb.float())
+            pos_proj = engine.pos_projection(self.attn, pos_emb.float(), self._packed)
         y, _ = self.run(x2, xn, pos_proj, lens, B, T)
         y = y.view(B, T, d)
         if pos_emb is not None:

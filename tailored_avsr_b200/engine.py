@@ -1,8 +1,17 @@
 """Kernel sequencing for one Branchformer block on the B200 path.
 
 The layer modules own the parameters; this file turns them into launch sequences of the C-ABI
-kernels (ops.py).  All activations are 2-D row-major (B*T, C) fp32 tensors ("tf32 mode": operands
-are rounded to TF32 by TMA on load, accumulation and every non-GEMM step stay fp32).
+kernels (ops.py).  All activations are 2-D row-major (B*T, C) tensors.  Compute modes
+(`set_compute_dtype`, env TAVSR_DTYPE):
+  "tf32"   (default) fp32 storage everywhere, operands rounded to TF32 by TMA on load;
+  "tf32x3" as tf32, but the dense projections run as three-term split TF32 products
+           (a_hi b_hi + a_hi b_lo + a_lo b_hi over a tripled reduction axis): fp32-class accuracy
+           on the TF32 pipe, the parity fallback for checkpoints whose statistics eat the TF32 margin;
+  "bf16"   every tensor-core operand is stored as bf16 by the kernel that produces it (LayerNorm
+           outputs, qkv, ctx, the GELU'd cgMLP hidden, the CSGU output) and weights are converted
+           once per parameter version; the residual stream, LayerNorm statistics, softmax, the
+           CSGU arithmetic, the encoder output and the whole CTC scorer stay fp32.
+Accumulation is fp32 in every mode.
 
 Fusion map of one two-branch `learned_ave` block (reference encoder_layer.py:153-321):
 
@@ -87,6 +96,54 @@ CUDNN_EMBED = os.environ.get("TAVSR_CUDNN_EMBED", "0") != "0"
 
 _ACT = {"swish": ops.ACT_SWISH, "relu": ops.ACT_RELU, "gelu": ops.ACT_GELU}
 
+_MODES = ("tf32", "tf32x3", "bf16")
+_DTYPE = os.environ.get("TAVSR_DTYPE", "tf32")
+if _DTYPE not in _MODES:
+    raise ValueError(f"TAVSR_DTYPE={_DTYPE!r}: expected one of {_MODES}")
+
+
+def set_compute_dtype(mode: str) -> None:
+    """Select the compute mode of every B200 module in this process (see the module docstring).
+    Captured CUDA graphs key on it, derived-weight caches hold one entry per mode."""
+    global _DTYPE
+    if mode not in _MODES:
+        raise ValueError(f"compute dtype {mode!r}: expected one of {_MODES}")
+    _DTYPE = mode
+
+
+def compute_dtype() -> str:
+    return _DTYPE
+
+
+class use_compute_dtype:
+    """`with use_compute_dtype("bf16"): ...` (tests, benches)."""
+
+    def __init__(self, mode: str):
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev = _DTYPE
+        set_compute_dtype(self.mode)
+        return self
+
+    def __exit__(self, *exc):
+        set_compute_dtype(self.prev)
+        return False
+
+
+def is_bf16() -> bool:
+    return _DTYPE == "bf16"
+
+
+def act_dtype() -> torch.dtype:
+    """Storage type of tensors that only feed tensor-core products."""
+    return torch.bfloat16 if _DTYPE == "bf16" else torch.float32
+
+
+def operand(x: torch.Tensor) -> torch.Tensor:
+    """Activation entering the path from outside (features, pos_emb) in operand storage."""
+    return ops.cast_bf16(x) if _DTYPE == "bf16" and x.dtype != torch.bfloat16 else x
+
 
 def act_code(name: str) -> int:
     if name not in _ACT:
@@ -108,6 +165,16 @@ class PackedCache:
             return t._version
         except RuntimeError:  # inference tensors do not track versions
             return -1
+
+    def clear(self) -> None:
+        self._store.clear()
+
+    def weight(self, key: str, w: torch.Tensor) -> torch.Tensor:
+        """Operand form of a weight matrix in the current compute mode: the parameter itself
+        (tf32: TMA rounds on load) or a bf16 copy made once per parameter version."""
+        if _DTYPE != "bf16":
+            return w
+        return self.get(key + ":bf16", [w], lambda: w.detach().to(torch.bfloat16).contiguous())
 
     def get(self, key: str, sources, build):
         sig = tuple((s.data_ptr(), self._version(s), s.device) for s in sources)
@@ -143,20 +210,50 @@ def lens_from_mask(mask: Optional[torch.Tensor], B: int, T: int, device) -> torc
 
 
 def ffn_block(x, xn, ff, *, out_main, ln0=None, lnA=None, out_lnA=None, round_lnA=False,
-              lnB=None, out_lnB=None, eps0=1e-12, alpha=0.5):
+              lnB=None, out_lnB=None, eps0=1e-12, alpha=0.5, cache: Optional[PackedCache] = None,
+              key: str = "ffn"):
     """x + alpha * (W2 act(W1 xn + b1) + b2) with the trailing LayerNorms fused (x may be None: no
     residual).  One kernel with the hidden activation kept on chip when the shapes are the built
-    ones (256 -> 2048 -> 256), otherwise (or with TAVSR_FFN_FUSED=0) the two-GEMM sequence."""
-    if FFN_FUSED and tuple(ff.w_1.weight.shape) == (2048, 256):
-        ops.ffn_fused(xn, ff.w_1.weight, ff.w_1.bias, ff.w_2.weight, ff.w_2.bias,
+    ones (256 -> 2048 -> 256), otherwise (or with TAVSR_FFN_FUSED=0, or in tf32x3 mode) the
+    two-GEMM sequence.  Output storage types follow the tensors passed in."""
+    cache = cache if cache is not None else _ffn_cache(ff)
+    w1 = cache.weight(key + ".w1", ff.w_1.weight)
+    w2 = cache.weight(key + ".w2", ff.w_2.weight)
+    if FFN_FUSED and _DTYPE != "tf32x3" and tuple(ff.w_1.weight.shape) == (2048, 256):
+        ops.ffn_fused(xn, w1, ff.w_1.bias, w2, ff.w_2.bias,
                       act_code(ff.activation_type), residual=x, alpha=alpha, ln0=ln0, eps0=eps0,
                       out_main=out_main, lnA=lnA, out_lnA=out_lnA, round_lnA=round_lnA,
                       lnB=lnB, out_lnB=out_lnB)
         return
-    h = ops.gemm_bias_act(xn, ff.w_1.weight, ff.w_1.bias, act=act_code(ff.activation_type))
-    ops.gemm_rowln(h, ff.w_2.weight, ff.w_2.bias, residual=x, alpha=alpha, ln0=ln0, eps0=eps0,
-                   out_main=out_main, lnA=lnA, out_lnA=out_lnA, round_lnA=round_lnA,
-                   lnB=lnB, out_lnB=out_lnB)
+    h = linear(xn, ff.w_1.weight, ff.w_1.bias, cache, key + ".w1", act=act_code(ff.activation_type),
+               out_dtype=act_dtype())
+    linear_rowln(h, ff.w_2.weight, ff.w_2.bias, cache, key + ".w2", residual=x, alpha=alpha, ln0=ln0,
+                 eps0=eps0, out_main=out_main, lnA=lnA, out_lnA=out_lnA, round_lnA=round_lnA,
+                 lnB=lnB, out_lnB=out_lnB)
+
+
+def _ffn_cache(ff) -> PackedCache:
+    c = ff.__dict__.get("_tavsr_packed")
+    if c is None:
+        c = ff.__dict__["_tavsr_packed"] = PackedCache()
+    return c
+
+
+def linear(x, w, bias, cache: PackedCache, key: str, act: int = ops.ACT_NONE, out_dtype=None):
+    """act(x W^T + b) in the current compute mode (tiled tcgen05 GEMM)."""
+    if _DTYPE == "tf32x3":
+        w3 = cache.get(key + ":x3", [w], lambda: ops.split_tf32(w.detach(), "w"))
+        return ops.gemm_bias_act(ops.split_tf32(x, "x"), w3, bias, act=act)
+    return ops.gemm_bias_act(x, cache.weight(key, w), bias, act=act, out_dtype=out_dtype)
+
+
+def linear_rowln(x, w, bias, cache: PackedCache, key: str, **kw):
+    """Row-complete (N = 256) projection with the fused residual / LayerNorm epilogue in the current
+    compute mode (single-operand form)."""
+    if _DTYPE == "tf32x3":
+        w3 = cache.get(key + ":x3", [w], lambda: ops.split_tf32(w.detach(), "w"))
+        return ops.gemm_rowln(ops.split_tf32(x, "x"), w3, bias, **kw)
+    return ops.gemm_rowln(x, cache.weight(key, w), bias, **kw)
 
 
 def qkv_weights(attn, cache: PackedCache, key: str):
@@ -167,55 +264,30 @@ def qkv_weights(attn, cache: PackedCache, key: str):
         torch.cat([attn.linear_q.bias, attn.linear_k.bias, attn.linear_v.bias], 0).contiguous()))
 
 
-def attention_ctx(xa, attn, pos_proj, lens, B, T, cache: PackedCache, key: str, dots=None):
-    """Fused QKV projection + rel-pos attention; returns ctx (B*T, d), or (ctx, partial row dots
-    (B*T, 2h, 2)) when `dots=(va, vb)` asks the attention epilogue for the learned_ave scores."""
+def attention_ctx(xa, attn, pos_proj, lens, B, T, cache: PackedCache, key: str):
+    """Fused QKV projection + rel-pos attention; returns ctx (B*T, d) in operand storage."""
     wqkv, bqkv = qkv_weights(attn, cache, key)
-    qkv = ops.gemm_bias_act(xa, wqkv, bqkv)
+    qkv = linear(xa, wqkv, bqkv, cache, key + ".w", out_dtype=act_dtype())
     u = attn.pos_bias_u.reshape(-1)
     v = attn.pos_bias_v.reshape(-1)
-    return ops.relpos_attn(qkv, pos_proj, u, v, lens, B, T, attn.h, dots=dots)
+    return ops.relpos_attn(qkv, pos_proj, u, v, lens, B, T, attn.h)
 
 
-def pos_projection(attn, pos_emb: torch.Tensor):
+def pos_projection(attn, pos_emb: torch.Tensor, cache: Optional[PackedCache] = None):
     """linear_pos(pos_emb): (2T-1, d).  Batch independent."""
-    return ops.gemm_bias_act(pos_emb.reshape(-1, pos_emb.shape[-1]), attn.linear_pos.weight, None)
+    cache = cache if cache is not None else PackedCache()
+    pe = operand(pos_emb.reshape(-1, pos_emb.shape[-1]).contiguous().float())
+    return linear(pe, attn.linear_pos.weight, None, cache, f"wpos1_{id(attn)}", out_dtype=act_dtype())
 
 
-# LayerNorm statistics of the CSGU gate half from the channel_proj1 GEMM epilogue (no stand-alone
-# statistics kernel) and the learned_ave row dots from the attention / CSGU epilogues (no row_dots
-# kernel)
-# MEASURED (C2, CUDA-graph replay): both fusions LOSE inside the PDL-chained graph - the two small
-# kernels they remove mostly overlap their neighbours there, while the extra epilogue work and the
-# partial-summing merge-weights kernel sit on the critical path (3.86 ms -> 3.99-4.03 ms per step) -
-# so they are opt-in; the ncu launch list (cold, serialised) shows the opposite, -18 us per block.
-FUSE_STATS = os.environ.get("TAVSR_FUSE_STATS", "0") != "0"
-FUSE_DOTS = os.environ.get("TAVSR_FUSE_DOTS", "0") != "0"
-
-
-def cgmlp_gated(xm, cgmlp, B, T, cache: PackedCache, key: str, dots=None):
-    """channel_proj1 + GELU + CSGU; returns u (B*T, C/2) ready for channel_proj2, or
-    (u, partial row dots (B*T, C/256, 2)) when `dots=(va, vb)` is given."""
+def cgmlp_gated(xm, cgmlp, B, T, cache: PackedCache, key: str):
+    """channel_proj1 + GELU + CSGU; returns u (B*T, C/2) ready for channel_proj2."""
     if cgmlp.csgu.linear is not None or cgmlp.csgu.gate_activation != "identity":
         raise NotImplementedError("use_linear_after_conv / non-identity gate_activation are not "
                                   "built on the B200 path (no shipped config uses them)")
     lin = cgmlp.channel_proj1[0]
     conv = cgmlp.csgu.conv
     cw = cache.get(key, [conv.weight], lambda: conv.weight.reshape(conv.weight.shape[0], -1).contiguous())
-    Ch = lin.weight.shape[0] // 2
-    if FUSE_STATS and Ch % 128 == 0 and Ch // 64 <= 16:
-        g, st, n_part, pw = ops.gemm_bias_act_stats(xm, lin.weight, lin.bias, ops.ACT_GELU, Ch)
-        u, d = ops.csgu_fused(g, cgmlp.csgu.norm.weight, cgmlp.csgu.norm.bias, cw, conv.bias, B, T,
-                              st, n_part, pw, eps=cgmlp.csgu.norm.eps, dots=dots)
-        return u if dots is None else (u, d)
-    if dots is not None and Ch % 128 == 0:
-        g = ops.gemm_bias_act(xm, lin.weight, lin.bias, act=ops.ACT_GELU)
-        return ops.csgu_fused(g, cgmlp.csgu.norm.weight, cgmlp.csgu.norm.bias, cw, conv.bias, B, T,
-                              None, 0, 0, eps=cgmlp.csgu.norm.eps, dots=dots)
-    g = ops.gemm_bias_act(xm, lin.weight, lin.bias, act=ops.ACT_GELU)
-    u = ops.csgu(g, cgmlp.csgu.norm.weight, cgmlp.csgu.norm.bias, cw, conv.bias, B, T,
-                 eps=cgmlp.csgu.norm.eps)
-    if dots is None:
-        return u
-    d, _ = ops.row_dots(u, dots[0], dots[1])
-    return u, d.view(-1, 1, 2)
+    g = linear(xm, lin.weight, lin.bias, cache, key + ".p1", act=ops.ACT_GELU, out_dtype=act_dtype())
+    return ops.csgu(g, cgmlp.csgu.norm.weight, cgmlp.csgu.norm.bias, cw, conv.bias, B, T,
+                    eps=cgmlp.csgu.norm.eps)

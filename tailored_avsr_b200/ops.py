@@ -13,11 +13,12 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SWISH, DT_BF16, DT_TF32, FfnArgs, RowLNArgs, check
+from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, ACT_SWISH, DT_BF16, DT_LNA_BF16, DT_LNB_BF16,
+                   DT_OUT_BF16, DT_TF32, FfnArgs, RowLNArgs, check)
 
 __all__ = [
     "ACT_NONE", "ACT_SWISH", "ACT_GELU", "ACT_RELU",
-    "gemm_bias_act", "conv2d_sub_im2col", "gemm_bias_act_stats", "csgu_fused", "merge_weights2", "scale_add_rows", "gemm_rowln", "ffn_fused", "layernorm", "relpos_attn", "csgu", "merge_weights",
+    "gemm_bias_act", "conv2d_sub_im2col", "merge_weights2", "scale_add_rows", "cast_bf16", "split_tf32", "gemm_rowln", "ffn_fused", "layernorm", "relpos_attn", "csgu", "merge_weights",
     "ctc_head", "ctc_head_bwd", "vocab_residual", "row_dots", "ctc_loss", "ctc_greedy", "ctc_prefix_score", "launch_count",
 ]
 
@@ -37,6 +38,12 @@ def _profiled(fn):
 
     @functools.wraps(fn)
     def wrapper(*args, **kwargs):
+        # launch on the device (and its current stream) that owns the operands, not on whatever
+        # device happens to be current
+        t0 = next((a for a in args if torch.is_tensor(a) and a.is_cuda), None)
+        if t0 is not None and t0.device.index != torch.cuda.current_device():
+            with torch.cuda.device(t0.device):
+                return wrapper(*args, **kwargs)
         if _PROFILE is None:
             return fn(*args, **kwargs)
         e0 = torch.cuda.Event(enable_timing=True)
@@ -61,12 +68,28 @@ def _p(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+_ACT_DTYPES = (torch.float32, torch.bfloat16)
+
+
 def _chk2d(t: torch.Tensor, name: str, dtype=torch.float32) -> None:
+    """dtype=None accepts either activation storage type (fp32 / bf16)."""
     if not t.is_cuda:
         raise _lib.TavsrError(f"{name} must be a CUDA tensor (no CPU fallback exists)")
-    if t.dtype != dtype or t.dim() != 2 or t.stride(1) != 1:
-        raise _lib.TavsrError(f"{name} must be 2-D {dtype} with unit inner stride, got "
+    ok = t.dtype in _ACT_DTYPES if dtype is None else t.dtype == dtype
+    if not ok or t.dim() != 2 or t.stride(1) != 1:
+        raise _lib.TavsrError(f"{name} must be 2-D {dtype or 'fp32/bf16'} with unit inner stride, got "
                               f"{tuple(t.shape)} {t.dtype} strides {t.stride()}")
+
+
+def _is_bf16(t: Optional[torch.Tensor]) -> bool:
+    return t is not None and t.dtype == torch.bfloat16
+
+
+def _chk_k(w: torch.Tensor, K: int, who: str) -> None:
+    """The kernels take the reduction length from the activation operand: a weight of another
+    width would be read out of bounds, so refuse it here."""
+    if w.shape[1] != K:
+        raise _lib.TavsrError(f"{who}: weight reduction width {w.shape[1]} != activation width {K}")
 
 
 _SPLITK_WS = {}  # (device index, stream handle) -> zero-initialised split-K scratch
@@ -90,52 +113,36 @@ def launch_count() -> int:
 
 @_profiled
 def gemm_bias_act(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: int = ACT_NONE,
-                  round_out: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                  round_out: bool = False, out: Optional[torch.Tensor] = None,
+                  out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
     """out = act(x @ w.T + bias) on the tcgen05 GEMM (tavsr_gemm_bias_act).  fp32 operands run as
-    TF32; bf16 operands (both) run kind::f16 MMAs with fp32 accumulate and fp32 output."""
+    TF32; bf16 operands (both) run kind::f16 MMAs with fp32 accumulate and an fp32 or bf16 output
+    (`out_dtype`, default fp32, or the dtype of `out`)."""
     bf16 = x.dtype == torch.bfloat16
     _chk2d(x, "x", x.dtype if bf16 else torch.float32)
     _chk2d(w, "w", torch.bfloat16 if bf16 else torch.float32)
     M, K = x.shape
     N = w.shape[0]
+    _chk_k(w, K, "gemm_bias_act")
     if out is None:
-        out = torch.empty((M, N), device=x.device, dtype=torch.float32)
-    _chk2d(out, "out")
+        out = torch.empty((M, N), device=x.device, dtype=out_dtype or torch.float32)
+    _chk2d(out, "out", None)
+    if out.dtype == torch.bfloat16 and not bf16:
+        raise _lib.TavsrError("gemm_bias_act: a bf16 output needs bf16 operands")
+    dt = (DT_BF16 if bf16 else DT_TF32) | (DT_OUT_BF16 if out.dtype == torch.bfloat16 else 0)
     lib = _lib.load()
     check(lib.tavsr_gemm_bias_act(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), _p(bias),
                                   out.data_ptr(), out.stride(0), M, N, K, act, int(round_out),
-                                  DT_BF16 if bf16 else DT_TF32, _stream()), "tavsr_gemm_bias_act")
+                                  dt, _stream()), "tavsr_gemm_bias_act")
     return out
-
-
-@_profiled
-def gemm_bias_act_stats(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: int,
-                        stats_col0: int, out: Optional[torch.Tensor] = None):
-    """gemm_bias_act whose epilogue also emits partial LayerNorm statistics (mean, M2) of the
-    output columns [stats_col0, N) (tavsr_gemm_bias_act_stats).  Returns
-    (out, stats_part (M, n_part, 2), n_part, part_width)."""
-    _chk2d(x, "x")
-    _chk2d(w, "w")
-    M, K = x.shape
-    N = w.shape[0]
-    if out is None:
-        out = torch.empty((M, N), device=x.device, dtype=torch.float32)
-    _chk2d(out, "out")
-    stats = torch.empty((M * ((N - stats_col0) // 64) * 2,), device=x.device, dtype=torch.float32)
-    width = ctypes.c_int(0)
-    check(_lib.load().tavsr_gemm_bias_act_stats(
-        x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), _p(bias), out.data_ptr(),
-        out.stride(0), M, N, K, act, 0, DT_TF32, stats.data_ptr(), stats_col0, ctypes.byref(width),
-        _stream()), "tavsr_gemm_bias_act_stats")
-    n_part = (N - stats_col0) // width.value
-    return out, stats, n_part, width.value
 
 
 def _fill_rowln(a: RowLNArgs, M: int, bias, residual, alpha, ln0, eps0, out_main, round_main, lnA,
                 out_lnA, round_lnA, lnB, out_lnB, round_lnB, eps, dots, dots_out) -> None:
     a.struct_size = ctypes.sizeof(RowLNArgs)
     a.M = M
-    a.dtype = DT_TF32
+    a.dtype = ((DT_OUT_BF16 if _is_bf16(out_main) else 0) | (DT_LNA_BF16 if _is_bf16(out_lnA) else 0)
+               | (DT_LNB_BF16 if _is_bf16(out_lnB) else 0))   # the caller ORs in the operand type
     a.bias = _p(bias)
     if residual is not None:
         _chk2d(residual, "residual")
@@ -145,16 +152,16 @@ def _fill_rowln(a: RowLNArgs, M: int, bias, residual, alpha, ln0, eps0, out_main
         a.ln0_g, a.ln0_b = ln0[0].data_ptr(), ln0[1].data_ptr()
     a.eps0 = eps0
     if out_main is not None:
-        _chk2d(out_main, "out_main")
+        _chk2d(out_main, "out_main", None)
         a.out_main, a.ld_main = out_main.data_ptr(), out_main.stride(0)
     a.round_main = int(round_main)
     if lnA is not None:
-        _chk2d(out_lnA, "out_lnA")
+        _chk2d(out_lnA, "out_lnA", None)
         a.lnA_g, a.lnA_b = lnA[0].data_ptr(), lnA[1].data_ptr()
         a.out_lnA, a.ld_lnA = out_lnA.data_ptr(), out_lnA.stride(0)
     a.round_lnA = int(round_lnA)
     if lnB is not None:
-        _chk2d(out_lnB, "out_lnB")
+        _chk2d(out_lnB, "out_lnB", None)
         a.lnB_g, a.lnB_b = lnB[0].data_ptr(), lnB[1].data_ptr()
         a.out_lnB, a.ld_lnB = out_lnB.data_ptr(), out_lnB.stride(0)
     a.round_lnB = int(round_lnB)
@@ -181,15 +188,16 @@ def gemm_rowln(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = 
                segbias: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> None:
     """Row-complete N=256 GEMM with fused residual / LayerNorm / row-dot epilogue (tavsr_gemm_rowln).
     k1 > 0 selects the sequential dual mode: x (M,k1), x2 (M,K-k1), w (256,K) = [W1 | W2]."""
-    _chk2d(x, "x")
-    _chk2d(w, "w")
+    _chk2d(x, "x", None)
+    _chk2d(w, "w", x.dtype)
     a = RowLNArgs()
     _fill_rowln(a, x.shape[0], bias, residual, alpha, ln0, eps0, out_main, round_main, lnA, out_lnA,
                 round_lnA, lnB, out_lnB, round_lnB, eps, dots, dots_out)
+    a.dtype |= DT_BF16 if _is_bf16(x) else DT_TF32
     a.K = x.shape[1]
     a.x, a.ldx = x.data_ptr(), x.stride(0)
     if x2 is not None:
-        _chk2d(x2, "x2")
+        _chk2d(x2, "x2", x.dtype)
         a.x2, a.ldx2 = x2.data_ptr(), x2.stride(0)
         a.rowscale1, a.rowscale2 = rowscale[0].data_ptr(), rowscale[1].data_ptr()
         a.rows_per_seg = rows_per_seg
@@ -199,6 +207,14 @@ def gemm_rowln(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = 
             if segbias is not None:
                 a.segbias1, a.segbias2 = segbias[0].data_ptr(), segbias[1].data_ptr()
     a.w, a.ldw = w.data_ptr(), w.stride(0)
+    if w.shape[0] != 256:
+        raise _lib.TavsrError(f"gemm_rowln: the row-complete epilogue is built for N = 256, got {w.shape[0]}")
+    if x2 is not None and k1 == 0:
+        _chk_k(w, x.shape[1], "gemm_rowln")
+        if x2.shape[1] != x.shape[1]:
+            raise _lib.TavsrError("gemm_rowln: dual operands must have equal widths")
+    else:
+        _chk_k(w, a.K, "gemm_rowln")
     if x2 is None and a.K >= 1024:
         ws = _splitk_workspace(x.device, a.M)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
@@ -218,9 +234,13 @@ def ffn_fused(xn: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Te
               eps: float = 1e-12) -> None:
     """residual + alpha * (act(xn @ w1.T + b1) @ w2.T + b2) with the row-complete LayerNorm epilogue;
     the hidden activation stays on chip (tavsr_ffn_fused)."""
-    _chk2d(xn, "xn")
-    _chk2d(w1, "w1")
-    _chk2d(w2, "w2")
+    _chk2d(xn, "xn", None)
+    _chk2d(w1, "w1", xn.dtype)
+    _chk2d(w2, "w2", xn.dtype)
+    _chk_k(w1, xn.shape[1], "ffn_fused (w1)")
+    _chk_k(w2, w1.shape[0], "ffn_fused (w2)")
+    if xn.shape[1] != 256 or w2.shape[0] != 256:
+        raise _lib.TavsrError("ffn_fused: built for model width 256")
     a = FfnArgs()
     a.struct_size = ctypes.sizeof(FfnArgs)
     a.hidden = w1.shape[0]
@@ -231,6 +251,7 @@ def ffn_fused(xn: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Te
     a.w2, a.ldw2 = w2.data_ptr(), w2.stride(0)
     _fill_rowln(a.ep, xn.shape[0], b2, residual, alpha, ln0, eps0, out_main, round_main, lnA, out_lnA,
                 round_lnA, lnB, out_lnB, round_lnB, eps, None, None)
+    a.ep.dtype |= DT_BF16 if _is_bf16(xn) else DT_TF32
     check(_lib.load().tavsr_ffn_fused(ctypes.byref(a), _stream()), "tavsr_ffn_fused")
 
 
@@ -238,88 +259,64 @@ def ffn_fused(xn: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Te
 def layernorm(x: torch.Tensor, gA: torch.Tensor, bA: torch.Tensor, eps: float = 1e-12,
               round_out: bool = False, scale: float = 1.0, out: Optional[torch.Tensor] = None,
               gB: Optional[torch.Tensor] = None, bB: Optional[torch.Tensor] = None,
-              outB: Optional[torch.Tensor] = None, roundB: bool = False) -> torch.Tensor:
+              outB: Optional[torch.Tensor] = None, roundB: bool = False,
+              out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """LayerNorm of fp32 rows into an fp32 or bf16 output (`out_dtype` / the dtype of `out`)."""
     _chk2d(x, "x")
     M, D = x.shape
     if out is None:
-        out = torch.empty((M, D), device=x.device, dtype=torch.float32)
+        out = torch.empty((M, D), device=x.device, dtype=out_dtype or torch.float32)
+    dt = (DT_LNA_BF16 if _is_bf16(out) else 0) | (DT_LNB_BF16 if _is_bf16(outB) else 0)
     check(_lib.load().tavsr_layernorm(x.data_ptr(), x.stride(0), M, D, eps, gA.data_ptr(),
                                       bA.data_ptr(), out.data_ptr(), out.stride(0), int(round_out),
                                       _p(gB), _p(bB), _p(outB),
                                       outB.stride(0) if outB is not None else 0, int(roundB),
-                                      scale, _stream()), "tavsr_layernorm")
+                                      scale, dt, _stream()), "tavsr_layernorm")
     return out
 
 
 @_profiled
 def relpos_attn(qkv: torch.Tensor, pos: torch.Tensor, u: torch.Tensor, v: torch.Tensor,
                 lens: Optional[torch.Tensor], B: int, T: int, H: int, round_out: bool = True,
-                out: Optional[torch.Tensor] = None,
-                dots: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
-    """ctx = rel-pos MHSA(qkv) for (B*T, 3*H*64) fused projections (tavsr_relpos_attn_fwd).
-    With `dots=(va, vb)` also returns the partial row dots of ctx with the two (H*64)-vectors,
-    (B*T, 2H, 2) (tavsr_relpos_attn_fwd_dots)."""
-    _chk2d(qkv, "qkv")
-    _chk2d(pos, "pos")
+                out: Optional[torch.Tensor] = None):
+    """ctx = rel-pos MHSA(qkv) for (B*T, 3*H*64) fused projections (tavsr_relpos_attn_fwd); fp32
+    qkv / pos -> fp32 ctx on TF32 MMAs, bf16 qkv / pos -> bf16 ctx on kind::f16 MMAs."""
+    _chk2d(qkv, "qkv", None)
+    _chk2d(pos, "pos", qkv.dtype)
+    if qkv.shape != (B * T, 3 * H * 64) or pos.shape != (2 * T - 1, H * 64) or u.numel() != H * 64 \
+            or v.numel() != H * 64:
+        raise _lib.TavsrError(
+            f"relpos_attn: the attention kernel is built for head width d_k = 64: expected qkv "
+            f"({B * T}, {3 * H * 64}), pos ({2 * T - 1}, {H * 64}), u / v of {H * 64} values, got "
+            f"{tuple(qkv.shape)}, {tuple(pos.shape)}, {u.numel()}, {v.numel()}")
     if out is None:
-        out = torch.empty((B * T, H * 64), device=qkv.device, dtype=torch.float32)
-    if dots is None:
-        check(_lib.load().tavsr_relpos_attn_fwd(qkv.data_ptr(), qkv.stride(0), pos.data_ptr(),
-                                                pos.stride(0), u.data_ptr(), v.data_ptr(), _p(lens),
-                                                out.data_ptr(), out.stride(0), B, T, H,
-                                                int(round_out), _stream()), "tavsr_relpos_attn_fwd")
-        return out
-    dout = torch.empty((B * T, 2 * H, 2), device=qkv.device, dtype=torch.float32)
-    check(_lib.load().tavsr_relpos_attn_fwd_dots(
-        qkv.data_ptr(), qkv.stride(0), pos.data_ptr(), pos.stride(0), u.data_ptr(), v.data_ptr(),
-        _p(lens), out.data_ptr(), out.stride(0), B, T, H, int(round_out), dots[0].data_ptr(),
-        dots[1].data_ptr(), dout.data_ptr(), _stream()), "tavsr_relpos_attn_fwd_dots")
-    return out, dout
+        out = torch.empty((B * T, H * 64), device=qkv.device, dtype=qkv.dtype)
+    dt = (DT_BF16 | DT_OUT_BF16) if _is_bf16(qkv) else DT_TF32
+    check(_lib.load().tavsr_relpos_attn_fwd(qkv.data_ptr(), qkv.stride(0), pos.data_ptr(),
+                                            pos.stride(0), u.data_ptr(), v.data_ptr(), _p(lens),
+                                            out.data_ptr(), out.stride(0), B, T, H,
+                                            int(round_out), dt, _stream()), "tavsr_relpos_attn_fwd")
+    return out
 
 
 @_profiled
 def csgu(h: torch.Tensor, norm_g: torch.Tensor, norm_b: torch.Tensor, conv_w: torch.Tensor,
          conv_b: torch.Tensor, B: int, T: int, eps: float = 1e-12, round_out: bool = True,
          out: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out = r * (dwconv31(LN(g)) + b) for h = [r | g] (tavsr_csgu_fwd)."""
-    _chk2d(h, "h")
+    """out = r * (dwconv31(LN(g)) + b) for h = [r | g] (tavsr_csgu_fwd); h / out fp32 or bf16."""
+    _chk2d(h, "h", None)
     Ch = h.shape[1] // 2
     if out is None:
-        out = torch.empty((B * T, Ch), device=h.device, dtype=torch.float32)
+        out = torch.empty((B * T, Ch), device=h.device, dtype=h.dtype)
     if stats is None:
         stats = torch.empty((B * T, 2), device=h.device, dtype=torch.float32)
     ksize = conv_w.shape[-1]
+    dt = (DT_BF16 | DT_OUT_BF16) if _is_bf16(h) else DT_TF32
     check(_lib.load().tavsr_csgu_fwd(h.data_ptr(), h.stride(0), norm_g.data_ptr(),
                                      norm_b.data_ptr(), conv_w.data_ptr(), conv_b.data_ptr(),
                                      out.data_ptr(), out.stride(0), stats.data_ptr(), B, T, Ch,
-                                     ksize, eps, int(round_out), _stream()), "tavsr_csgu_fwd")
+                                     ksize, eps, int(round_out), dt, _stream()), "tavsr_csgu_fwd")
     return out
-
-
-@_profiled
-def csgu_fused(h: torch.Tensor, norm_g: torch.Tensor, norm_b: torch.Tensor, conv_w: torch.Tensor,
-               conv_b: torch.Tensor, B: int, T: int, stats_part: Optional[torch.Tensor],
-               n_part: int, part_w: int, eps: float = 1e-12, round_out: bool = True,
-               dots: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
-    """csgu() with the LayerNorm statistics taken from the partials of gemm_bias_act_stats
-    (stats_part=None: stand-alone statistics pass) and, with `dots=(va, vb)`, the partial row dots
-    of the output, (B*T, Ch/128, 2) (tavsr_csgu_fwd_fused).  Returns (out, dots-or-None)."""
-    _chk2d(h, "h")
-    Ch = h.shape[1] // 2
-    out = torch.empty((B * T, Ch), device=h.device, dtype=torch.float32)
-    stats = None
-    if stats_part is None:
-        stats = torch.empty((B * T, 2), device=h.device, dtype=torch.float32)
-    dout = None
-    if dots is not None:
-        dout = torch.empty((B * T, Ch // 128, 2), device=h.device, dtype=torch.float32)
-    ksize = conv_w.shape[-1]
-    check(_lib.load().tavsr_csgu_fwd_fused(
-        h.data_ptr(), h.stride(0), norm_g.data_ptr(), norm_b.data_ptr(), conv_w.data_ptr(),
-        conv_b.data_ptr(), out.data_ptr(), out.stride(0), _p(stats), _p(stats_part), n_part, part_w,
-        _p(dots[0]) if dots else None, _p(dots[1]) if dots else None, _p(dout), B, T, Ch, ksize, eps,
-        int(round_out), _stream()), "tavsr_csgu_fwd_fused")
-    return out, dout
 
 
 @_profiled
@@ -339,18 +336,47 @@ def merge_weights2(dots1: torch.Tensor, np1: int, dots2: torch.Tensor, np2: int,
 
 @_profiled
 def scale_add_rows(a: torch.Tensor, b: torch.Tensor, w1: torch.Tensor, w2: torch.Tensor,
-                   rows_per_seg: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out[m] = w1[m // rows_per_seg] * a[m] + w2[m // rows_per_seg] * b[m] (tavsr_scale_add_rows)."""
+                   rows_per_seg: int, out: Optional[torch.Tensor] = None,
+                   out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """out[m] = w1[m // rows_per_seg] * a[m] + w2[m // rows_per_seg] * b[m] (tavsr_scale_add_rows);
+    fp32 inputs, fp32 or bf16 output."""
     _chk2d(a, "a")
     _chk2d(b, "b")
     M, D = a.shape
     if out is None:
-        out = torch.empty((M, D), device=a.device, dtype=torch.float32)
+        out = torch.empty((M, D), device=a.device, dtype=out_dtype or torch.float32)
     check(_lib.load().tavsr_scale_add_rows(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0),
                                            w1.data_ptr(), w2.data_ptr(), rows_per_seg,
-                                           out.data_ptr(), out.stride(0), M, D, _stream()),
+                                           out.data_ptr(), out.stride(0), M, D,
+                                           DT_OUT_BF16 if _is_bf16(out) else 0, _stream()),
           "tavsr_scale_add_rows")
     return out
+
+
+@_profiled
+def split_tf32(x: torch.Tensor, kind: str) -> torch.Tensor:
+    """3xTF32 operand triple (tavsr_split_tf32): kind "x" -> [hi | hi | lo], "w" -> [hi | lo | hi],
+    (M, K) fp32 -> (M, 3K) fp32."""
+    _chk2d(x, "x")
+    M, K = x.shape
+    out = torch.empty((M, 3 * K), device=x.device, dtype=torch.float32)
+    check(_lib.load().tavsr_split_tf32(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), M, K,
+                                       0 if kind == "x" else 1, _stream()), "tavsr_split_tf32")
+    return out
+
+
+_CAST_SCALARS = {}
+
+
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    """fp32 (M, D) -> bf16 copy on our own kernel (scale_add_rows with weights (1, 0)): the operand
+    form of tensors that enter the bf16 path from outside (input features, pos_emb)."""
+    if x.dtype == torch.bfloat16:
+        return x
+    sc = _CAST_SCALARS.get(x.device)
+    if sc is None:
+        sc = _CAST_SCALARS[x.device] = (torch.ones(1, device=x.device), torch.zeros(1, device=x.device))
+    return scale_add_rows(x, x, sc[0], sc[1], max(1, x.shape[0]), out_dtype=torch.bfloat16)
 
 
 @_profiled
@@ -373,20 +399,24 @@ def merge_weights(dots1: torch.Tensor, dots2: torch.Tensor, lens: Optional[torch
 def row_dots(a1: torch.Tensor, va1: torch.Tensor, vb1: torch.Tensor,
              a2: Optional[torch.Tensor] = None, va2: Optional[torch.Tensor] = None,
              vb2: Optional[torch.Tensor] = None):
-    """(a1 @ [va1 vb1], a2 @ [va2 vb2]) as (M,2) tensors in one launch (tavsr_row_dots)."""
-    _chk2d(a1, "a1")
+    """(a1 @ [va1 vb1], a2 @ [va2 vb2]) as (M,2) tensors in one launch (tavsr_row_dots); a1 / a2
+    fp32 or bf16 (both the same), vectors fp32."""
+    _chk2d(a1, "a1", None)
+    if a2 is not None:
+        _chk2d(a2, "a2", a1.dtype)
     M = a1.shape[0]
     o1 = torch.empty((M, 2), device=a1.device, dtype=torch.float32)
     o2 = torch.empty((M, 2), device=a1.device, dtype=torch.float32) if a2 is not None else None
     check(_lib.load().tavsr_row_dots(
         a1.data_ptr(), a1.stride(0), a1.shape[1], va1.data_ptr(), vb1.data_ptr(), o1.data_ptr(),
         _p(a2), a2.stride(0) if a2 is not None else 0, a2.shape[1] if a2 is not None else 0,
-        _p(va2), _p(vb2), _p(o2), M, _stream()), "tavsr_row_dots")
+        _p(va2), _p(vb2), _p(o2), M, DT_BF16 if _is_bf16(a1) else DT_TF32, _stream()), "tavsr_row_dots")
     return o1, o2
 
 
 @_profiled
-def conv2d_sub_im2col(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor) -> torch.Tensor:
+def conv2d_sub_im2col(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor,
+                      out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
     """im2col operand of the second Conv2dSubsampling convolution with conv1 + ReLU evaluated on
     the fly: x (B, Tin, F) -> A (B*T2*F2, 9*C) (tavsr_conv2d_sub_im2col)."""
     if not x.is_cuda or x.dtype != torch.float32 or not x.is_contiguous():
@@ -394,9 +424,10 @@ def conv2d_sub_im2col(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor) -> to
     B, Tin, F = x.shape
     C = w1.shape[0]
     T2, F2 = ((Tin - 1) // 2 - 1) // 2, ((F - 1) // 2 - 1) // 2
-    A = torch.empty((B * T2 * F2, 9 * C), device=x.device, dtype=torch.float32)
+    A = torch.empty((B * T2 * F2, 9 * C), device=x.device, dtype=out_dtype)
     check(_lib.load().tavsr_conv2d_sub_im2col(x.data_ptr(), B, Tin, F, w1.data_ptr(), b1.data_ptr(),
-                                              C, A.data_ptr(), _stream()), "tavsr_conv2d_sub_im2col")
+                                              C, A.data_ptr(), DT_OUT_BF16 if _is_bf16(A) else 0,
+                                              _stream()), "tavsr_conv2d_sub_im2col")
     return A
 
 
@@ -422,7 +453,8 @@ def ctc_head(hs: torch.Tensor, w: torch.Tensor, b: torch.Tensor, want_logp: bool
 
 @_profiled
 def vocab_residual(x: torch.Tensor, p: torch.Tensor, w: torch.Tensor, b: torch.Tensor,
-                   ln: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, eps: float = 1e-12):
+                   ln: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, eps: float = 1e-12,
+                   ln_dtype: torch.dtype = torch.float32):
     """out = x + p @ w.T + b  (p (M,V) posteriors, w (D,V)); with `ln` also LayerNorm(out)
     (tavsr_vocab_residual).  Returns (out, xn-or-None)."""
     _chk2d(x, "x")
@@ -432,11 +464,12 @@ def vocab_residual(x: torch.Tensor, p: torch.Tensor, w: torch.Tensor, b: torch.T
     if w.shape != (D, V) or not w.is_contiguous() or not p.is_contiguous():
         raise ValueError("vocab_residual: w must be a contiguous (D,V) matrix, p contiguous (M,V)")
     out = torch.empty((M, D), device=x.device, dtype=torch.float32)
-    xn = torch.empty((M, D), device=x.device, dtype=torch.float32) if ln is not None else None
+    xn = torch.empty((M, D), device=x.device, dtype=ln_dtype) if ln is not None else None
     check(_lib.load().tavsr_vocab_residual(
         x.data_ptr(), x.stride(0), p.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(),
         out.stride(0), _p(ln[0]) if ln else None, _p(ln[1]) if ln else None, eps, _p(xn),
-        xn.stride(0) if xn is not None else 0, M, D, V, _stream()), "tavsr_vocab_residual")
+        xn.stride(0) if xn is not None else 0, M, D, V, DT_LNA_BF16 if _is_bf16(xn) else 0,
+        _stream()), "tavsr_vocab_residual")
     return out, xn
 
 

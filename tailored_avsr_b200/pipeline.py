@@ -24,6 +24,7 @@ class EncoderCTCPipeline:
         self.use_cuda_graph = use_cuda_graph
         self.greedy = greedy
         self._graphs: Dict[Tuple, dict] = {}
+        self._param_sig = None
         p = next(encoder.parameters())
         if not p.is_cuda:
             raise RuntimeError("EncoderCTCPipeline needs the modules on a CUDA device "
@@ -31,6 +32,46 @@ class EncoderCTCPipeline:
         self.device = p.device
 
     # ---------------------------------------------------------------------------------------
+    def _modules(self):
+        return [m for m in (self.encoder, self.ctc, getattr(self, "fusion", None),
+                            getattr(self, "acoustic_embed", None), getattr(self, "visual_embed", None))
+                if m is not None]
+
+    def _parameter_signature(self) -> tuple:
+        """In-place version counters of every parameter and buffer the captured graphs read.  A
+        CUDA graph bakes in derived tensors (fused QKV weight, folded merge weights, permuted conv
+        weights) and host scalars taken from the parameters at capture time, so a replay after
+        `load_state_dict` / an optimizer step would mix new raw parameters with stale derived
+        ones: the signature is checked before every replay (one attribute read per tensor, ~30 us)
+        and the graphs are re-captured when it changed.  Writes through `.data`
+        (`p.data.copy_()`) do not bump the version counter and replacing parameter OBJECTS
+        (`module.to()`, `load_state_dict(assign=True)`) is not seen either - call `invalidate()`
+        after those."""
+        tens = self.__dict__.get("_sig_tensors")
+        if tens is None:
+            tens = []
+            for m in self._modules():
+                tens += list(m.parameters()) + list(m.buffers())
+            self._sig_tensors = tens
+            self._sig_ptrs = tuple(t.data_ptr() for t in tens)
+        try:
+            return (self._sig_ptrs,) + tuple([t._version for t in tens])
+        except RuntimeError:   # inference tensors do not track versions
+            return (self._sig_ptrs,)
+
+    def invalidate(self) -> None:
+        """Drop every captured graph and derived-weight cache (call after writing parameters
+        through `.data` or any other path that does not bump the tensors' version counters)."""
+        from .engine import PackedCache
+        self._graphs.clear()
+        self._param_sig = None
+        self.__dict__.pop("_sig_tensors", None)
+        for m in self._modules():
+            for sub in m.modules():
+                pk = getattr(sub, "_packed", None)
+                if isinstance(pk, PackedCache):
+                    pk.clear()
+
     def _step(self, feats, feats_lens, ys_pad, ys_lens):
         out, olens, _ = self.encoder(feats, feats_lens)
         if isinstance(out, tuple):
@@ -71,7 +112,12 @@ class EncoderCTCPipeline:
         consume or clone them before the next call)."""
         if not self.use_cuda_graph:
             return self._step(*tensors)
-        key = tuple((tuple(t.shape), t.dtype) for t in tensors)
+        from .engine import compute_dtype
+        key = tuple((tuple(t.shape), t.dtype) for t in tensors) + (compute_dtype(),)
+        sig = self._parameter_signature()
+        if sig != self._param_sig:
+            self._graphs.clear()       # parameters changed since capture: derived tensors are stale
+            self._param_sig = sig
         entry = self._graphs.get(key)
         if entry is None:
             entry = self._capture(key, *tensors)

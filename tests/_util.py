@@ -61,7 +61,8 @@ def run_oracle(name, sd):
     res = {}
     with torch.no_grad():
         if c["kind"] == "single":
-            y, olens, w = ref_path.branchformer_encoder(inp["x"], inp["lens"], sd, c["cfg"])
+            y, olens, w = ref_path.branchformer_encoder(inp["x"], inp["lens"], sd, c["cfg"],
+                                                        max_layer=c.get("max_layer"))
             res.update(out=y, olens=olens, weights=w)
             for idx, t in ref_path.branchformer_encoder.last_taps:
                 res[f"inter_{idx}"] = t

@@ -1,10 +1,16 @@
 """Parity of the CUDA drop-in (through the C ABI) against the CPU oracle on the same seeded inputs
 and against the golden vectors of the real reference (tests/golden, oracle/gen_golden.py).
 
-Tolerances (BASELINE.json north_star), tf32 mode = fp32 storage, TF32 tensor-core
-operands, fp32 accumulate:
-  * encoder outputs: max|y-ref|/max|ref| <= 1e-3 and ||y-ref||_F/||ref||_F <= 1e-3 over valid frames
-  * CTC loss given identical hs_pad: relative error <= 1e-4
+Tolerances (BASELINE.json north_star), stated ONCE per compute mode in ENC_TOL:
+  * encoder outputs, max|y-ref|/max|ref| and ||y-ref||_F/||ref||_F over valid frames, against the
+    fp32 oracle AND the golden vectors of the real reference:
+      tf32   (fp32 storage, TF32 tensor-core operands, fp32 accumulate)            <= 1e-3
+      tf32x3 (three-term split TF32 products for the dense projections)           <= 1e-3, also on
+             the "hot weights" stress case the single-pass tf32 mode only meets at 3e-3
+      bf16   (bf16 operands AND bf16 storage of operand-only tensors, fp32 residual stream /
+             statistics / softmax / accumulation)                                  <= 5e-3
+             (SURVEY.md §7 budget for this form: 1.5e-3 .. 1e-2; never looser than its 2e-2)
+  * CTC loss given identical hs_pad: relative error <= 1e-4 (every mode: the scorer is fp32)
   * greedy CTC token sequences given identical hs_pad: exact
 """
 import numpy as np
@@ -16,8 +22,26 @@ from oracle import cases
 from . import _util
 
 pytestmark = pytest.mark.gpu
-ENC_TOL = 1e-3
+ENC_TOL = {"tf32": 1e-3, "tf32x3": 1e-3, "bf16": 5e-3}
+# merge weights (softmax of pooled scores) published per layer: absolute tolerance per mode
+WG_TOL = {"tf32": 2e-3, "tf32x3": 2e-3, "bf16": 1e-2}
 DEV = "cuda"
+# tf32x3 runs the K-tripled products: a representative subset incl. the stress case
+X3_CASES = ["asr_small", "vsr_small", "asr_tailored_small", "concat_small", "av_tailored_small",
+            "av_fusion_conventional", "asr_interctc_cond", "asr_c1_hot"]
+MODE_CASES = ([("tf32", n) for n in cases.CASES] + [("bf16", n) for n in cases.CASES]
+              + [("tf32x3", n) for n in X3_CASES])
+
+
+def _tol(mode, name):
+    """The mode's tolerance; the single-pass tf32 mode states the hot-weights stress case
+    separately (enc_tol), tf32x3 and bf16 do not need to."""
+    c = cases.CASES[name]
+    if mode == "tf32":
+        return c.get("enc_tol", ENC_TOL[mode])
+    if mode == "bf16" and c.get("hot", False):
+        return 3 * ENC_TOL[mode]   # 1.7x larger branch outputs: stated separately, like tf32's 3x
+    return ENC_TOL[mode]
 
 
 def _run_dropin(name, enc, ctc=None):
@@ -25,7 +49,8 @@ def _run_dropin(name, enc, ctc=None):
     inp = cases.make_inputs(name)
     with torch.no_grad():
         if c["kind"] == "single":
-            y, olens, _ = enc(inp["x"].to(DEV), inp["lens"].to(DEV), ctc=ctc)
+            y, olens, _ = enc(inp["x"].to(DEV), inp["lens"].to(DEV), ctc=ctc,
+                              max_layer=c.get("max_layer"))
             res = {}
             if isinstance(y, tuple):  # InterCTC taps (encoder.py:410-411)
                 y, inter = y
@@ -52,13 +77,16 @@ def _run_dropin(name, enc, ctc=None):
         return res
 
 
-@pytest.mark.parametrize("name", list(cases.CASES))
-def test_encoder_parity_vs_oracle_and_golden(name):
+@pytest.mark.parametrize("mode,name", MODE_CASES)
+def test_encoder_parity_vs_oracle_and_golden(mode, name):
+    from tailored_avsr_b200 import engine
     enc, ctc, sd = _util.build_dropin(name)
     res = _util.run_oracle(name, sd)
     enc = enc.to(DEV)
-    got = _run_dropin(name, enc, ctc.to(DEV))
+    with engine.use_compute_dtype(mode):
+        got = _run_dropin(name, enc, ctc.to(DEV))
     torch.cuda.synchronize()
+    tol = _tol(mode, name)
     assert torch.equal(got["olens"].cpu().long(), res["olens"].long())
     lens = res["olens"]
     for key in [k for k in res if k in ("out", "out_video", "fused") or k.startswith("inter_")]:
@@ -67,9 +95,8 @@ def test_encoder_parity_vs_oracle_and_golden(name):
             # its taps are valid wherever either modality is (logical_or of the masks)
             klens = {"out": res.get("lens_audio", lens), "out_video": res.get("lens_video", lens)}.get(key, lens)
             mx, fro = _util.rel_errors(got[key], res[key], klens)
-            print(f"{name}:{key}: max-rel {mx:.3e} fro {fro:.3e}")
-            tol = cases.CASES[name].get("enc_tol", ENC_TOL)
-            assert mx <= tol and fro <= tol, (name, key, mx, fro)
+            print(f"PARITY {mode} {name}:{key}: max-rel {mx:.3e} fro {fro:.3e} (tol {tol:.0e})")
+            assert mx <= tol and fro <= tol, (mode, name, key, mx, fro)
     # golden vectors of the real reference (strided for the 12-layer cases)
     gold = _util.load_golden(name)
     c = cases.CASES[name]
@@ -79,16 +106,16 @@ def test_encoder_parity_vs_oracle_and_golden(name):
     mine = got[gkey].cpu()[:, ::st, ::sdd]
     glens = (lens + st - 1) // st
     mx, fro = _util.rel_errors(mine, g, glens)
-    assert mx <= 2 * tol and fro <= tol, (name, "golden", mx, fro)
+    assert mx <= tol and fro <= tol, (mode, name, "golden", mx, fro)
     if "acoustic_weight" in gold:
         aw = got["acoustic_weight"]
         aw = aw.flatten().cpu().numpy() if torch.is_tensor(aw) else np.array([aw], dtype=np.float32)
-        assert np.allclose(aw, gold["acoustic_weight"], atol=2e-3)
+        assert np.allclose(aw, gold["acoustic_weight"], atol=WG_TOL[mode])
     # learned_ave merge weights published on the layers (study_branches.py:44-45)
     if c["kind"] == "single" and c["cfg"]["merge_method"] == "learned_ave":
         wg = torch.stack([l.weight_global.flatten().cpu() for l in enc.encoders])
         assert wg.shape == tuple(gold["weight_global"].shape)
-        assert np.allclose(wg.numpy(), gold["weight_global"], atol=2e-3)
+        assert np.allclose(wg.numpy(), gold["weight_global"], atol=WG_TOL[mode])
 
 
 @pytest.mark.parametrize("name", list(cases.CASES))
@@ -188,7 +215,7 @@ def test_layer_module_standalone_matches_oracle():
         (y, pos_out), mask_out = layer((x.to(DEV), pos.to(DEV)), mask.to(DEV))
         want, _ = ref_path.branchformer_layer(x, pos, mask, sd, "encoders.1", merge_method="concat")
     mx, fro = _util.rel_errors(y, want, lens)
-    assert mx <= ENC_TOL and fro <= ENC_TOL, (mx, fro)
+    assert mx <= ENC_TOL["tf32"] and fro <= ENC_TOL["tf32"], (mx, fro)
     assert pos_out.shape == (1, 2 * T - 1, d) and mask_out.shape == (B, 1, T)
 
 
@@ -272,20 +299,67 @@ def test_pipeline_run_stream_equals_blocking_run():
     assert len({w[0] for w in want}) == len(want)  # the batches really differ
 
 
-@pytest.mark.parametrize("knob", [11, 13, 15])
-def test_alternative_epilogue_paths_keep_parity(knob):
-    """The opt-out / opt-in epilogue variants behind the debug knobs stay correct: 11 = thread-per-row
-    FFN epilogue, 13 = 8-warp tiled GEMM epilogue, 15 = two-warps-per-quadrant RowLN epilogue."""
-    from tailored_avsr_b200 import _lib
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+def test_eight_warp_tiled_epilogue_keeps_parity(mode):
+    """Debug knob 13 (8 instead of 16 epilogue warps on the 256-wide tiled GEMM) stays correct."""
+    from tailored_avsr_b200 import _lib, engine
     name = "vsr_small"
     enc, ctc, sd = _util.build_dropin(name)
     res = _util.run_oracle(name, sd)
     lib = _lib.load()
-    lib.tavsr_debug_set(knob, 1)
+    lib.tavsr_debug_set(13, 1)
     try:
-        got = _run_dropin(name, enc.to(DEV), ctc.to(DEV))
+        with engine.use_compute_dtype(mode):
+            got = _run_dropin(name, enc.to(DEV), ctc.to(DEV))
         torch.cuda.synchronize()
     finally:
-        lib.tavsr_debug_set(knob, 0)
+        lib.tavsr_debug_set(13, 0)
     mx, fro = _util.rel_errors(got["out"], res["out"], res["olens"])
-    assert mx <= ENC_TOL and fro <= ENC_TOL, (knob, mx, fro)
+    assert mx <= ENC_TOL[mode] and fro <= ENC_TOL[mode], (mode, mx, fro)
+
+
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+def test_unfolded_and_unfused_kernel_sequences_keep_parity(mode, monkeypatch):
+    """The two-GEMM FFN (TAVSR_FFN_FUSED=0) and the separate branch output projections
+    (TAVSR_FOLD_MERGE=0) - the sequences the training forward uses - match the oracle too."""
+    from tailored_avsr_b200 import engine
+    monkeypatch.setattr(engine, "FFN_FUSED", False)
+    monkeypatch.setattr(engine, "FOLD_MERGE", False)
+    for name in ("vsr_small", "fixed_ave_small"):
+        enc, ctc, sd = _util.build_dropin(name)
+        res = _util.run_oracle(name, sd)
+        with engine.use_compute_dtype(mode):
+            got = _run_dropin(name, enc.to(DEV), ctc.to(DEV))
+        mx, fro = _util.rel_errors(got["out"], res["out"], res["olens"])
+        assert mx <= ENC_TOL[mode] and fro <= ENC_TOL[mode], (mode, name, mx, fro)
+
+
+def test_pipeline_recaptures_after_parameter_update_and_per_compute_mode():
+    """The CUDA graphs bake in derived weights: an in-place parameter update (load_state_dict, an
+    optimizer step) must trigger a re-capture, `.data` writes need invalidate(), and each compute
+    mode owns its graph."""
+    from tailored_avsr_b200 import engine
+    from tailored_avsr_b200.pipeline import EncoderCTCPipeline
+    name = "vsr_small"
+    enc, ctc, sd = _util.build_dropin(name)
+    pipe = EncoderCTCPipeline(enc.to(DEV), ctc.to(DEV))
+    inp = cases.make_inputs(name)
+    tl = cases.target_lens(name, inp["lens"])
+    args = (inp["x"].to(DEV), inp["lens"].to(DEV), inp["ys_pad"].to(DEV), tl.to(DEV))
+    l0 = float(pipe.run(*args)["loss"])
+    assert float(pipe.run(*args)["loss"]) == l0
+    new_sd = {k: v * 1.05 if k.endswith("merge_proj.weight") else v for k, v in enc.state_dict().items()}
+    enc.load_state_dict(new_sd)                       # copy_ bumps the version counters
+    l1 = float(pipe.run(*args)["loss"])
+    assert l1 != l0
+    fresh = EncoderCTCPipeline(enc, ctc, use_cuda_graph=False)
+    assert abs(float(fresh.run(*args)["loss"]) - l1) <= 1e-5 * abs(l1)
+    with torch.no_grad():
+        enc.encoders[0].merge_proj.weight.data.mul_(1.0 / 1.05)   # invisible to version counters
+    pipe.invalidate()
+    l2 = float(pipe.run(*args)["loss"])
+    assert abs(l2 - float(fresh.run(*args)["loss"])) <= 1e-5 * abs(l2) and l2 != l1
+    with engine.use_compute_dtype("bf16"):
+        lb = float(pipe.run(*args)["loss"])
+    assert lb != l2 and abs(lb - l2) <= 2e-2 * abs(l2)
+    assert float(pipe.run(*args)["loss"]) == l2
