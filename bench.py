@@ -406,8 +406,9 @@ def run_gpu_arm(args):
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)
 
-    from tailored_avsr_b200 import ops
+    from tailored_avsr_b200 import engine, ops
     from tailored_avsr_b200.pipeline import AVEncoderCTCPipeline, EncoderCTCPipeline
+    engine.set_compute_dtype(args.dtype)
 
     w = WORKLOAD
     peaks, peak_src = load_peaks()
@@ -517,7 +518,7 @@ def run_gpu_arm(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
             "data": "synthetic",
             "config": {"workload": w["name"], "batch_per_gpu": w["B"], "T": w["T"],
                        "feat": w.get("feat", 256), "layers": 12, "vocab": w["vocab"],
@@ -573,6 +574,8 @@ def main():
                     help="SURVEY.md §8d workload (default: the bench line, C2)")
     ap.add_argument("--batch", type=int, default=0, help="utterances per GPU (sweep)")
     ap.add_argument("--T", type=int, default=0, help="encoder frames per utterance (sweep)")
+    ap.add_argument("--dtype", default="tf32", choices=["tf32", "tf32x3", "bf16"],
+                    help="compute mode (tailored_avsr_b200.engine): operand storage of the tensor-core products")
     args = ap.parse_args()
     select_workload(args)
     if args.impl == "reference":

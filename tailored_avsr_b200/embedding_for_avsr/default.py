@@ -97,10 +97,14 @@ class DefaultEmbeddingLayerForAVSR(EmbeddingForAVSRAbsLayer):
                          lin.weight.view(-1, C, Fd).permute(0, 2, 1).reshape(-1, Fd * C).contiguous()))
             adt = engine.act_dtype()
             a_mat = ops.conv2d_sub_im2col(xs_pad.contiguous().float(), pk[0], conv[0].bias, out_dtype=adt)
+            # conv2 output fp32, last projection on TF32 operands: see encoder.py::_embed
             h2 = engine.linear(a_mat, pk[1], conv[2].bias, self._packed, "conv2", act=ops.ACT_RELU,
-                               out_dtype=adt).view(B * T, Fd * C)
+                               out_dtype=torch.float32).view(B * T, Fd * C)
             x = torch.empty((B * T, d), device=dev, dtype=torch.float32)
-            engine.linear_rowln(h2, pk[2], lin.bias, self._packed, "embout", out_main=x)
+            if engine.compute_dtype() == "tf32x3":
+                engine.linear_rowln(h2, pk[2], lin.bias, self._packed, "embout", out_main=x)
+            else:
+                ops.gemm_rowln(h2, pk[2], lin.bias, out_main=x)
             return x.view(B, T, d), masks[:, :, :-2:2][:, :, :-2:2]
         B, T, Fin = xs_pad.shape
         if self.embed is None:

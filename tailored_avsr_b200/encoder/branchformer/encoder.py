@@ -199,13 +199,21 @@ class MyBranchformerEncoder(AbsEncoder):
                     lambda: (conv[0].weight.reshape(C, 9).contiguous(),
                              conv[2].weight.permute(0, 2, 3, 1).reshape(C, 9 * C).contiguous(),
                              lin.weight.view(-1, C, Fd).permute(0, 2, 1).reshape(-1, Fd * C).contiguous()))
+                # bf16 mode: the im2col operand (the big tensor: 9 C values per conv2 input) and the
+                # conv2 weights are bf16, but conv2's output stays fp32 and the 4864 -> 256
+                # projection that PRODUCES the residual stream runs on TF32 operands - an error
+                # made here rides the residual path through every block unattenuated
                 a_mat = ops.conv2d_sub_im2col(xs_pad.contiguous().float(), pk[0], conv[0].bias,
                                               out_dtype=adt)
                 h2 = engine.linear(a_mat, pk[1], conv[2].bias, self._packed, "conv2", act=ops.ACT_RELU,
-                                   out_dtype=adt).view(B * T, Fd * C)
+                                   out_dtype=torch.float32).view(B * T, Fd * C)
                 w_lin = pk[2]
-            engine.linear_rowln(h2, w_lin, lin.bias, self._packed, "embout", alpha=math.sqrt(d),
-                                out_main=x, lnA=first_norm, out_lnA=xn)
+            if engine.compute_dtype() == "tf32x3":
+                engine.linear_rowln(h2, w_lin, lin.bias, self._packed, "embout", alpha=math.sqrt(d),
+                                    out_main=x, lnA=first_norm, out_lnA=xn)
+            else:
+                ops.gemm_rowln(h2.float() if h2.dtype != torch.float32 else h2, w_lin, lin.bias,
+                               alpha=math.sqrt(d), out_main=x, lnA=first_norm, out_lnA=xn)
             masks = masks[:, :, :-2:2][:, :, :-2:2]
             pos_emb = self.embed.out[1].pos_emb(T, x.device)
         elif self.embed is not None:

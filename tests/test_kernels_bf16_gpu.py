@@ -243,7 +243,7 @@ def test_layernorm_and_cast_bf16_outputs(M, D):
     oB = torch.empty(M, D, device=DEV)
     oA = ops.layernorm(x, gA, bA, eps=1e-12, gB=gB, bB=bB, outB=oB, out_dtype=BF)
     wantA = _ln(x.double(), gA.double(), bA.double(), 1e-12)
-    assert oA.dtype == BF and torch.equal(oA.cpu(), wantA.float().to(BF)) or rel_fro(oA, wantA) < OUT_BF16_FRO
+    assert oA.dtype == BF and rel_fro(oA, wantA) < OUT_BF16_FRO
     assert max_rel(oB, _ln(x.double(), gB.double(), bB.double(), 1e-12)) < 1e-5
     c = ops.cast_bf16(x)
     assert c.dtype == BF and torch.equal(c, x.to(BF))
@@ -290,9 +290,9 @@ def test_tf32x3_split_product_is_fp32_class(M, N, K):
     y1 = ops.gemm_bias_act(x, w, b)
     ref = x.double() @ w.double().t() + b.double()
     e3, e1 = rel_fro(y3, ref), rel_fro(y1, ref)
-    assert e3 < 5e-6 and e3 < e1 / 20, (e3, e1)
+    assert e3 < 2e-5 and e3 < e1 / 20, (e3, e1)
     if N == 256:
         res = torch.randn(M, 256, generator=g).to(DEV)
         main = torch.empty(M, 256, device=DEV)
         ops.gemm_rowln(x3, w3, b, residual=res, alpha=0.5, out_main=main)
-        assert rel_fro(main, res.double() + 0.5 * ref) < 5e-6
+        assert rel_fro(main, res.double() + 0.5 * ref) < 2e-5
