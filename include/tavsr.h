@@ -206,7 +206,22 @@ int tavsr_layernorm(const float* x, long long ldx, int M, int D, float eps, cons
 int tavsr_relpos_attn_fwd(const void* qkv, long long ld_qkv, const void* pos, long long ld_pos,
                           const float* u, const float* v, const int32_t* lens, void* ctx,
                           long long ld_ctx, int B, int T, int H, int round_out, int dtype,
+                          float* lse /* optional [B,H,T]: base-2 log-sum-exp of the scaled scores,
+                                        kept by the training forward for tavsr_relpos_attn_bwd */,
                           void* stream);
+
+/* Backward of the attention core (training).  Given dctx = d loss / d ctx, the forward's qkv, pos,
+ * u, v, lens, ctx and lse (fp32), writes the k and v blocks of dqkv [B*T, 3*H*64] and ACCUMULATES
+ * (fp32 atomics; zero them first) the two parts of d q into dq_ac / dq_bd [B*T, H*64]
+ * (d q = dq_ac + dq_bd; d pos_bias_u = column sums of dq_ac, d pos_bias_v = column sums of dq_bd)
+ * and d linear_pos(pos_emb) into dpos [2T-1, H*64] (summed over utterances).  Probabilities are
+ * recomputed from lse: nothing of size T x T is stored.  Arithmetic:
+ * oracle/bwd_formulas.py::relpos_attn_core_bwd (verified against autograd). */
+int tavsr_relpos_attn_bwd(const float* qkv, long long ld_qkv, const float* pos, long long ld_pos,
+                          const float* u, const float* v, const int32_t* lens, const float* ctx,
+                          long long ld_ctx, const float* dctx, long long ld_dctx, const float* lse,
+                          float* dqkv, long long ld_dqkv, float* dq_ac, float* dq_bd, float* dpos,
+                          int B, int T, int H, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Convolutional spatial gating unit (espnet ConvolutionalSpatialGatingUnit.forward, reached through
@@ -350,6 +365,9 @@ int tavsr_transpose_2d(const float* in, long long ld_in, float* out, long long l
 size_t tavsr_col_sums_workspace_bytes(int R, int C);
 int tavsr_col_sums(const float* a, long long lda, const float* b, long long ldb, float* out,
                    void* workspace, long long workspace_bytes, int R, int C, void* stream);
+/* h = act(z) (* mask when mask != NULL: a dropout keep-mask pre-scaled by 1/(1-p)) */
+int tavsr_act_fwd(const float* z, long long ldz, const float* mask, long long ldm, float* h,
+                  long long ldh, int M, int C, int act, void* stream);
 int tavsr_act_bwd(const float* z, long long ldz, const float* dh, long long ldh, float* dz,
                   long long ldd, int M, int C, int act, void* stream);
 size_t tavsr_layernorm_bwd_workspace_bytes(int M, int D);

@@ -15,7 +15,7 @@ from concurrent.futures import ThreadPoolExecutor
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libtavsr_sm100.so")
-SOURCES = ["gemm_sm100.cu", "ffn_sm100.cu", "rowops.cu", "attention_sm100.cu", "ctc.cu",
+SOURCES = ["gemm_sm100.cu", "ffn_sm100.cu", "rowops.cu", "attention_sm100.cu", "attention_bwd.cu", "ctc.cu",
            "backward.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -80,6 +80,7 @@ struct Params {
   void* ctx;       // fp32 (tf32 mode) or bf16
   long long ld_ctx;
   int T, H, round_out;
+  float* lse;      // optional [B, H, T]: base-2 log-sum-exp of the scaled scores (training forward)
   long long* dbg;  // optional phase timestamps (16 per CTA), tools/time_attn.py
 };
 
@@ -485,7 +486,10 @@ relpos_attn_tc_kernel(const __grid_constant__ Params p) {
       float* s_sum = s_xch + (n_kv & 1) * 256;  // slot not in use by the last tile's maxima
       s_sum[hf * 128 + row] = l_run;
       named_bar_sync(1, 256);
-      inv = 1.0f / (l_run + s_sum[(hf ^ 1) * 128 + row]);
+      const float l_tot = l_run + s_sum[(hf ^ 1) * 128 + row];
+      inv = 1.0f / l_tot;
+      if (p.lse != nullptr && hf == 0 && i < T)
+        p.lse[(static_cast<long long>(b) * p.H + h) * T + i] = m_run + log2f(l_tot);
       mbar_wait(o_done, (n_kv - 1) & 1);
       tc_fence_after_sync();
       ATTN_STAMP(13);
@@ -494,6 +498,7 @@ relpos_attn_tc_kernel(const __grid_constant__ Params p) {
     } else {
 #pragma unroll
       for (int e = 0; e < 32; ++e) ro[e] = 0u;   // empty utterance: zero context
+      if (p.lse != nullptr && hf == 0 && i < T) p.lse[(static_cast<long long>(b) * p.H + h) * T + i] = 0.f;
     }
     if (i < T) {
       if constexpr (kBf16) {
@@ -536,7 +541,8 @@ relpos_attn_tc_kernel(const __grid_constant__ Params p) {
 template <bool kBf16>
 static int relpos_attn_launch(const void* qkv, long long ld_qkv, const void* pos, long long ld_pos,
                               const float* u, const float* v, const int32_t* lens, void* ctx,
-                              long long ld_ctx, int B, int T, int H, int round_out, cudaStream_t s) {
+                              long long ld_ctx, int B, int T, int H, int round_out, float* lse,
+                              cudaStream_t s) {
   using C = attn_tc::Cfg<kBf16>;
   attn_tc::Params p;
   memset(&p, 0, sizeof(p));
@@ -555,6 +561,7 @@ static int relpos_attn_launch(const void* qkv, long long ld_qkv, const void* pos
   p.ld_ctx = ld_ctx;
   p.T = T;
   p.H = H;
+  p.lse = lse;
   p.dbg = reinterpret_cast<long long*>(g_debug_ptr);
   p.round_out = round_out ? 1 : 0;
   auto kern = attn_tc::relpos_attn_tc_kernel<kBf16>;
@@ -575,7 +582,8 @@ using namespace tavsr;
 extern "C" int tavsr_relpos_attn_fwd(const void* qkv, long long ld_qkv, const void* pos,
                                      long long ld_pos, const float* u, const float* v,
                                      const int32_t* lens, void* ctx, long long ld_ctx, int B,
-                                     int T, int H, int round_out, int dtype, void* stream) {
+                                     int T, int H, int round_out, int dtype, float* lse,
+                                     void* stream) {
   TAVSR_REQUIRE(B > 0 && T > 0 && H > 0, "attn: bad shape B=%d T=%d H=%d", B, T, H);
   TAVSR_REQUIRE(qkv && pos && u && v && ctx, "attn: null pointer");
   const int op = dtype & TAVSR_DT_MASK;
@@ -591,7 +599,7 @@ extern "C" int tavsr_relpos_attn_fwd(const void* qkv, long long ld_qkv, const vo
                 "attn: operands must be 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return bf16 ? relpos_attn_launch<true>(qkv, ld_qkv, pos, ld_pos, u, v, lens, ctx, ld_ctx, B, T, H,
-                                         round_out, s)
+                                         round_out, lse, s)
               : relpos_attn_launch<false>(qkv, ld_qkv, pos, ld_pos, u, v, lens, ctx, ld_ctx, B, T, H,
-                                          round_out, s);
+                                          round_out, lse, s);
 }

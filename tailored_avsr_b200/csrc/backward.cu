@@ -24,7 +24,7 @@ namespace bwd {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 transpose_kernel(const float* __restrict__ in, long long ld_in, float* __restrict__ out,
-                 long long ld_out, int R, int C) {
+                 long long ld_out, int R, int C, int Rpad) {
   __shared__ float tile[32][33];
   pdl_launch_dependents();
   pdl_wait();
@@ -37,7 +37,8 @@ transpose_kernel(const float* __restrict__ in, long long ld_in, float* __restric
   __syncthreads();
   for (int j = ty; j < 32; j += 8) {
     const int c = c0 + j, r = r0 + tx;
-    if (c < C && r < R) out[static_cast<long long>(c) * ld_out + r] = tile[tx][j];
+    // columns [R, Rpad) of the output are written as zeros: a wgrad product reduces over them
+    if (c < C && r < Rpad) out[static_cast<long long>(c) * ld_out + r] = tile[tx][j];
   }
 }
 
@@ -92,6 +93,37 @@ __device__ __forceinline__ float act_grad(float z, int act) {
     }
     case 3: return z > 0.f ? 1.0f : 0.f;
     default: return 1.0f;
+  }
+}
+
+__device__ __forceinline__ float act_val(float z, int act) {
+  switch (act) {
+    case 1: return z / (1.0f + __expf(-z));
+    case 2: return 0.5f * z * (1.0f + erff(z * 0.7071067811865476f));
+    case 3: return fmaxf(z, 0.f);
+    default: return z;
+  }
+}
+
+// h = act(z) [* mask]: the training forward keeps the pre-activation z (the backward needs it) and
+// re-evaluates h where a weight gradient reads it; `mask` (optional, same shape) carries a dropout
+// keep-mask already scaled by 1 / (1 - p)
+__global__ void __launch_bounds__(256)
+act_fwd_kernel(const float* __restrict__ z, long long ldz, const float* __restrict__ mask,
+               long long ldm, float* __restrict__ h, long long ldh, int M, int C4, int act) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long total = static_cast<long long>(M) * C4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int m = static_cast<int>(i / C4), q = static_cast<int>(i % C4);
+    const float4 zz = ld_act4(reinterpret_cast<const float4*>(z + m * ldz) + q);
+    float4 r = make_float4(act_val(zz.x, act), act_val(zz.y, act), act_val(zz.z, act), act_val(zz.w, act));
+    if (mask != nullptr) {
+      const float4 k = ld_act4(reinterpret_cast<const float4*>(mask + m * ldm) + q);
+      r.x *= k.x; r.y *= k.y; r.z *= k.z; r.w *= k.w;
+    }
+    reinterpret_cast<float4*>(h + m * ldh)[q] = r;
   }
 }
 
@@ -492,8 +524,10 @@ extern "C" int tavsr_transpose_2d(const float* in, long long ld_in, float* out, 
                                   int R, int C, void* stream) {
   TAVSR_REQUIRE(R > 0 && C > 0 && in && out && ld_in >= C && ld_out >= R, "transpose: bad arguments");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // the tail of every output row up to the next multiple of 4 (within the pitch) is zero-filled
+  const int Rpad = static_cast<int>(ld_out < ((R + 3) / 4) * 4 ? ld_out : ((R + 3) / 4) * 4);
   TAVSR_CUDA_OK(launch_kernel(bwd::transpose_kernel, dim3((C + 31) / 32, (R + 31) / 32), dim3(256), 0,
-                              s, 0, in, ld_in, out, ld_out, R, C));
+                              s, 0, in, ld_in, out, ld_out, R, C, Rpad));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
@@ -516,6 +550,21 @@ extern "C" int tavsr_col_sums(const float* a, long long lda, const float* b, lon
   TAVSR_CUDA_OK(launch_kernel(bwd::col_sums_reduce_kernel, dim3((C + 127) / 128), dim3(128), 0, s, 0,
                               static_cast<const float*>(part), nblk, out, C));
   g_launches.fetch_add(2, std::memory_order_relaxed);
+  return 0;
+}
+
+extern "C" int tavsr_act_fwd(const float* z, long long ldz, const float* mask, long long ldm, float* h,
+                             long long ldh, int M, int C, int act, void* stream) {
+  TAVSR_REQUIRE(M > 0 && C > 0 && C % 4 == 0 && ldz % 4 == 0 && ldh % 4 == 0 && z && h && act >= 0 &&
+                    act <= 3 && (!mask || ldm % 4 == 0),
+                "act_fwd: bad arguments (M=%d C=%d act=%d)", M, C, act);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long total = static_cast<long long>(M) * (C / 4);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 8ll * num_sms()) blocks = 8ll * num_sms();
+  TAVSR_CUDA_OK(launch_kernel(bwd::act_fwd_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, s,
+                              0, z, ldz, mask, ldm, h, ldh, M, C / 4, act));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
 

@@ -211,9 +211,13 @@ class MyBranchformerEncoder(AbsEncoder):
             if engine.compute_dtype() == "tf32x3":
                 engine.linear_rowln(h2, w_lin, lin.bias, self._packed, "embout", alpha=math.sqrt(d),
                                     out_main=x, lnA=first_norm, out_lnA=xn)
-            else:
+            elif adt == torch.float32:
+                ops.gemm_rowln(h2, w_lin, lin.bias, alpha=math.sqrt(d), out_main=x, lnA=first_norm,
+                               out_lnA=xn)
+            else:   # the TF32 row-complete kernel stores fp32 only: LayerNorm -> bf16 as its own pass
                 ops.gemm_rowln(h2.float() if h2.dtype != torch.float32 else h2, w_lin, lin.bias,
-                               alpha=math.sqrt(d), out_main=x, lnA=first_norm, out_lnA=xn)
+                               alpha=math.sqrt(d), out_main=x)
+                ops.layernorm(x, first_norm[0], first_norm[1], eps=1e-12, out=xn)
             masks = masks[:, :, :-2:2][:, :, :-2:2]
             pos_emb = self.embed.out[1].pos_emb(T, x.device)
         elif self.embed is not None:

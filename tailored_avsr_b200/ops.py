@@ -278,9 +278,10 @@ def layernorm(x: torch.Tensor, gA: torch.Tensor, bA: torch.Tensor, eps: float = 
 @_profiled
 def relpos_attn(qkv: torch.Tensor, pos: torch.Tensor, u: torch.Tensor, v: torch.Tensor,
                 lens: Optional[torch.Tensor], B: int, T: int, H: int, round_out: bool = True,
-                out: Optional[torch.Tensor] = None):
+                out: Optional[torch.Tensor] = None, lse: Optional[torch.Tensor] = None):
     """ctx = rel-pos MHSA(qkv) for (B*T, 3*H*64) fused projections (tavsr_relpos_attn_fwd); fp32
-    qkv / pos -> fp32 ctx on TF32 MMAs, bf16 qkv / pos -> bf16 ctx on kind::f16 MMAs."""
+    qkv / pos -> fp32 ctx on TF32 MMAs, bf16 qkv / pos -> bf16 ctx on kind::f16 MMAs.  `lse`
+    (B, H, T) fp32, optional: receives the per-row log-sum-exp the backward recomputes P from."""
     _chk2d(qkv, "qkv", None)
     _chk2d(pos, "pos", qkv.dtype)
     if qkv.shape != (B * T, 3 * H * 64) or pos.shape != (2 * T - 1, H * 64) or u.numel() != H * 64 \
@@ -295,7 +296,8 @@ def relpos_attn(qkv: torch.Tensor, pos: torch.Tensor, u: torch.Tensor, v: torch.
     check(_lib.load().tavsr_relpos_attn_fwd(qkv.data_ptr(), qkv.stride(0), pos.data_ptr(),
                                             pos.stride(0), u.data_ptr(), v.data_ptr(), _p(lens),
                                             out.data_ptr(), out.stride(0), B, T, H,
-                                            int(round_out), dt, _stream()), "tavsr_relpos_attn_fwd")
+                                            int(round_out), dt, _p(lse), _stream()),
+          "tavsr_relpos_attn_fwd")
     return out
 
 
@@ -368,14 +370,20 @@ def split_tf32(x: torch.Tensor, kind: str) -> torch.Tensor:
 _CAST_SCALARS = {}
 
 
+def _cast_scalars(device):
+    """Device scalars (1, 0) used as scale_add_rows weights."""
+    sc = _CAST_SCALARS.get(device)
+    if sc is None:
+        sc = _CAST_SCALARS[device] = (torch.ones(1, device=device), torch.zeros(1, device=device))
+    return sc
+
+
 def cast_bf16(x: torch.Tensor) -> torch.Tensor:
     """fp32 (M, D) -> bf16 copy on our own kernel (scale_add_rows with weights (1, 0)): the operand
     form of tensors that enter the bf16 path from outside (input features, pos_emb)."""
     if x.dtype == torch.bfloat16:
         return x
-    sc = _CAST_SCALARS.get(x.device)
-    if sc is None:
-        sc = _CAST_SCALARS[x.device] = (torch.ones(1, device=x.device), torch.zeros(1, device=x.device))
+    sc = _cast_scalars(x.device)
     return scale_add_rows(x, x, sc[0], sc[1], max(1, x.shape[0]), out_dtype=torch.bfloat16)
 
 

@@ -1,7 +1,6 @@
-"""Tensor-level wrappers over the backward building blocks of the C ABI (include/tavsr.h,
-csrc/backward.cu; GPU-tested in tests/test_backward_gpu.py).  Not used by any product module yet:
-the attention / merge backward kernels and the training-forward orchestration are the next
-round's work; the arithmetic is fixed by oracle/bwd_formulas.py."""
+"""Tensor-level wrappers over the backward kernels of the C ABI (include/tavsr.h, csrc/backward.cu,
+csrc/attention_bwd.cu; GPU-tested in tests/test_backward_gpu.py).  training.py composes them into
+the autograd nodes of the encoder; the arithmetic is fixed by oracle/bwd_formulas.py."""
 from __future__ import annotations
 
 from typing import Optional
@@ -17,13 +16,76 @@ def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty((max(1, int(nbytes)) + 3) // 4, dtype=torch.float32, device=device)
 
 
-def transpose_2d(x: torch.Tensor) -> torch.Tensor:
+def transpose_2d(x: torch.Tensor, pad: bool = False) -> torch.Tensor:
+    """out[c][r] = x[r][c].  With `pad` the output rows are padded with zeros to a multiple of 4
+    columns (the operand form of a wgrad product, whose reduction axis is the row count of x)."""
     _chk2d(x, "x")
     R, C = x.shape
-    out = torch.empty((C, R), device=x.device, dtype=torch.float32)
+    Rp = (R + 3) // 4 * 4 if pad else R
+    out = torch.empty((C, Rp), device=x.device, dtype=torch.float32)
     check(_lib.load().tavsr_transpose_2d(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), R, C,
                                          _stream()), "tavsr_transpose_2d")
     return out
+
+
+def act_fwd(z: torch.Tensor, act: int, mask: Optional[torch.Tensor] = None,
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """h = act(z) (* mask): the training forward keeps z and evaluates h separately."""
+    _chk2d(z, "z")
+    M, C = z.shape
+    if out is None:
+        out = torch.empty((M, C), device=z.device, dtype=torch.float32)
+    check(_lib.load().tavsr_act_fwd(z.data_ptr(), z.stride(0), _p(mask),
+                                    mask.stride(0) if mask is not None else 0, out.data_ptr(),
+                                    out.stride(0), M, C, act, _stream()), "tavsr_act_fwd")
+    return out
+
+
+def linear_bwd(x_in: torch.Tensor, w: torch.Tensor, dy: torch.Tensor, need_dx: bool = True,
+               need_dw: bool = True, wT: Optional[torch.Tensor] = None):
+    """Backward of y = x_in W^T + b on the tcgen05 GEMM (TF32 operands, fp32 accumulate):
+         dx = dy W            = gemm(dy, (W^T) as the (K, N) weight operand)
+         dW = dy^T x_in       = gemm(dy^T (N, M), x_in^T (K, M)): reduction over the M rows
+         db = column sums of dy
+    Both products want K-major operands, hence the transposed copies (a 32 x 32 tile transpose
+    kernel; the bf16 path can read MN-major operands directly and will not need them).
+    Returns (dx or None, dW or None, db or None)."""
+    from . import ops
+    dx = dw = db = None
+    if need_dx:
+        if wT is None:
+            wT = transpose_2d(w.contiguous() if w.stride(1) != 1 else w)
+        dx = ops.gemm_bias_act(dy, wT, None)
+    if need_dw:
+        dyT = transpose_2d(dy, pad=True)
+        xT = transpose_2d(x_in, pad=True)
+        dw = ops.gemm_bias_act(dyT, xT, None)
+        db = col_sums(dy)
+    return dx, dw, db
+
+
+def relpos_attn_bwd(qkv: torch.Tensor, pos: torch.Tensor, u: torch.Tensor, v: torch.Tensor,
+                    lens: Optional[torch.Tensor], ctx: torch.Tensor, dctx: torch.Tensor,
+                    lse: torch.Tensor, B: int, T: int, H: int):
+    """Backward of ops.relpos_attn (tavsr_relpos_attn_bwd).  Returns (dqkv (B*T, 3*H*64), dpos
+    (2T-1, H*64), du (H*64,), dv (H*64,)): d q = the two accumulated parts summed into dqkv's q
+    block, the pos_bias gradients are the column sums of the parts."""
+    from . import ops
+    for t, n in ((qkv, "qkv"), (pos, "pos"), (ctx, "ctx"), (dctx, "dctx")):
+        _chk2d(t, n)
+    M, HD = B * T, H * 64
+    dev = qkv.device
+    dqkv = torch.empty((M, 3 * HD), device=dev, dtype=torch.float32)
+    acc = torch.zeros((2 * M + 2 * T - 1, HD), device=dev, dtype=torch.float32)   # one memset
+    dq_ac, dq_bd, dpos = acc[:M], acc[M:2 * M], acc[2 * M:]
+    check(_lib.load().tavsr_relpos_attn_bwd(
+        qkv.data_ptr(), qkv.stride(0), pos.data_ptr(), pos.stride(0), u.data_ptr(), v.data_ptr(),
+        _p(lens), ctx.data_ptr(), ctx.stride(0), dctx.data_ptr(), dctx.stride(0), lse.data_ptr(),
+        dqkv.data_ptr(), dqkv.stride(0), dq_ac.data_ptr(), dq_bd.data_ptr(), dpos.data_ptr(), B, T, H,
+        _stream()), "tavsr_relpos_attn_bwd")
+    one = ops._cast_scalars(dev)[0]
+    ops.scale_add_rows(dq_ac, dq_bd, one, one, M, out=dqkv[:, :HD])
+    return dqkv, dpos, col_sums(dq_ac), col_sums(dq_bd)
 
 
 def col_sums(a: torch.Tensor, b: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -93,8 +155,7 @@ def csgu_bwd(h: torch.Tensor, norm_g: torch.Tensor, norm_b: torch.Tensor, conv_w
 def merge_learned_ave_bwd(x1: torch.Tensor, x2: torch.Tensor, dm: torch.Tensor, lens: torch.Tensor,
                           a1: torch.Tensor, c1: float, b1: torch.Tensor, e1: float,
                           a2: torch.Tensor, c2: float, b2: torch.Tensor, e2: float, B: int, T: int):
-    """EXPERIMENTAL (not yet run on a GPU).  Returns (dx1, dx2, grads (1028,)): see
-    tavsr_merge_learned_ave_bwd in include/tavsr.h."""
+    """Returns (dx1, dx2, grads (1028,)): see tavsr_merge_learned_ave_bwd in include/tavsr.h."""
     _chk2d(x1, "x1")
     _chk2d(x2, "x2")
     _chk2d(dm, "dm")

@@ -76,9 +76,6 @@ def test_csgu_bwd(B, T):
     assert _rel(dcw, want[3].reshape(Ch, 31)) < 5e-5 and _rel(dcb, want[4]) < 5e-5
 
 
-@pytest.mark.skipif(os.environ.get("TAVSR_TEST_BWD_WIP", "0") != "1",
-                    reason="merge backward kernel written after the GPU budget was spent: not yet "
-                           "run on a GPU (set TAVSR_TEST_BWD_WIP=1; first thing to do next round)")
 def test_merge_learned_ave_bwd():
     from oracle import bwd_formulas as bw
     from tailored_avsr_b200 import ops_backward as ob
@@ -101,3 +98,64 @@ def test_merge_learned_ave_bwd():
         assert _rel(got, want) < 5e-5
     for got, want in ((gr[1024], wc1), (gr[1025], we1), (gr[1026], wc2), (gr[1027], we2)):
         assert abs(float(got) - float(want)) <= 5e-5 * max(1.0, abs(float(want)))
+
+
+@pytest.mark.parametrize("B,T,lens", [(2, 64, [64, 40]), (3, 100, [100, 1, 77]), (2, 250, [250, 130]),
+                                      (2, 130, [0, 130]), (1, 17, [17])])
+def test_relpos_attention_bwd(B, T, lens):
+    """tavsr_relpos_attn_bwd (P recomputed from the forward's log-sum-exp, fp32 FMA tiles, atomics for
+    the d q parts and d pos) against the autograd-verified dense formula in fp64."""
+    from oracle import bwd_formulas as bw
+    from tailored_avsr_b200 import ops, ops_backward as ob
+    H, dk = 4, 64
+    g = torch.Generator().manual_seed(T + B)
+    qkv = torch.randn(B * T, 3 * H * dk, generator=g)
+    pos = torch.randn(2 * T - 1, H * dk, generator=g)
+    u = torch.randn(H * dk, generator=g) * 0.5
+    v = torch.randn(H * dk, generator=g) * 0.5
+    dctx = torch.randn(B * T, H * dk, generator=g)
+    lens_t = torch.tensor(lens, dtype=torch.int32)
+    lse = torch.empty(B, H, T, device=DEV)
+    ctx = ops.relpos_attn(qkv.to(DEV), pos.to(DEV), u.to(DEV), v.to(DEV), lens_t.to(DEV), B, T, H,
+                          round_out=False, lse=lse)
+    dqkv, dpos, du, dv = ob.relpos_attn_bwd(qkv.to(DEV), pos.to(DEV), u.to(DEV), v.to(DEV),
+                                            lens_t.to(DEV), ctx, dctx.to(DEV), lse, B, T, H)
+    torch.cuda.synchronize()
+    split = lambda t: t.double().view(B, T, H, dk).transpose(1, 2)            # noqa: E731
+    q, k, vv = [split(t) for t in qkv.split(H * dk, dim=1)]
+    p = pos.double().view(2 * T - 1, H, dk).transpose(0, 1)
+    wq, wk, wv, wp, wu, wvb = bw.relpos_attn_core_bwd(q, k, vv, p, u.double().view(H, dk),
+                                                      v.double().view(H, dk), lens_t.long(), split(dctx))
+    unsplit = lambda t: t.transpose(1, 2).reshape(B * T, H * dk)             # noqa: E731
+    gq, gk, gv = dqkv.split(H * dk, dim=1)
+    tol = 5e-3   # the forward's scores / lse are TF32, the recomputation is fp32
+    assert _rel(gv, unsplit(wv)) < tol, _rel(gv, unsplit(wv))
+    assert _rel(gk, unsplit(wk)) < tol, _rel(gk, unsplit(wk))
+    assert _rel(gq, unsplit(wq)) < tol, _rel(gq, unsplit(wq))
+    assert _rel(dpos, wp.transpose(0, 1).reshape(2 * T - 1, H * dk)) < tol
+    assert _rel(du, wu.reshape(-1)) < tol and _rel(dv, wvb.reshape(-1)) < tol
+
+
+@pytest.mark.parametrize("M,N,K", [(8000, 2048, 256), (385, 256, 1024), (1000, 768, 256)])
+def test_linear_bwd_on_the_tcgen05_gemm(M, N, K):
+    from tailored_avsr_b200 import ops_backward as ob
+    g = torch.Generator().manual_seed(M + N)
+    x = torch.randn(M, K, generator=g).to(DEV)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    dy = torch.randn(M, N, generator=g).to(DEV)
+    dx, dw, db = ob.linear_bwd(x, w, dy)
+    assert _rel(dx, dy.double() @ w.double()) < 2e-3
+    assert _rel(dw, dy.double().t() @ x.double()) < 2e-3
+    assert _rel(db, dy.double().sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("act", [1, 2, 3])
+def test_act_fwd_with_and_without_mask(act):
+    from tailored_avsr_b200 import ops_backward as ob
+    g = torch.Generator().manual_seed(act)
+    z = torch.randn(333, 512, generator=g).to(DEV) * 2
+    mask = (torch.rand(333, 512, generator=g) > 0.1).float().to(DEV) / 0.9
+    zd = z.double()
+    want = {1: zd * torch.sigmoid(zd), 2: torch.nn.functional.gelu(zd), 3: torch.relu(zd)}[act]
+    assert _rel(ob.act_fwd(z, act), want) < 1e-6
+    assert _rel(ob.act_fwd(z, act, mask=mask), want * mask.double()) < 1e-6
