@@ -256,6 +256,11 @@ int tavsr_merge_learned_ave_weights(const float* dots1, const float* dots2, cons
                                     float pool_b1, float pool_b2, float wproj_b1, float wproj_b2,
                                     float inv_sqrt_size, float* w1, float* w2, int B, int T,
                                     void* stream);
+/* Training form: the four biases (pool_b1, pool_b2, wproj_b1, wproj_b2) are read from the DEVICE
+ * array `scal` instead of being passed by value (no host read-back of parameters per step). */
+int tavsr_merge_learned_ave_weights_dev(const float* dots1, const float* dots2, const int32_t* lens,
+                                        const float* scal, float inv_sqrt_size, float* w1, float* w2,
+                                        int B, int T, void* stream);
 /* General form: dotsK holds npK partial pairs per frame ([B*T, npK, 2], summed inside) and each
  * branch has its own length array (lens2 == NULL: lens1) - the two modalities of
  * AdaptiveAudioVisualFusion carry separate masks (adaptive_audiovisual_fusion.py:150-183). */
@@ -345,11 +350,11 @@ int tavsr_ctc_head_bwd(const float* dlogits, const float* row_scale, int rows_pe
                        int D, int V, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Backward building blocks for the encoder (training): transcriptions of
+ * Backward kernels of the encoder (training): transcriptions of
  * oracle/bwd_formulas.py (verified against autograd on the CPU), checked on the GPU in
- * tests/test_backward_gpu.py.  No product module calls them yet (attention / merge backward and
- * the training-forward orchestration are missing).  All fp32, no atomics (two-stage reductions
- * through caller-provided workspaces).
+ * tests/test_backward_gpu.py and composed into autograd nodes by tailored_avsr_b200/training.py.
+ * All fp32, two-stage reductions through caller-provided workspaces (atomics only in
+ * tavsr_relpos_attn_bwd).
  *   tavsr_transpose_2d    out[c][r] = in[r][c]           (wgrad operands, W^T for dgrad)
  *   tavsr_col_sums        out[c] = sum_r a[r][c] (* b[r][c] when b != NULL)     (bias gradients)
  *   tavsr_act_bwd         dz = dh * act'(z), act = TAVSR_ACT_*   (Swish / exact GELU / ReLU)
@@ -383,19 +388,18 @@ int tavsr_csgu_conv_bwd(const float* h, long long ldh, const float* norm_g, cons
                         long long workspace_bytes, int B, int T, int Ch, int ksize, void* stream);
 
 /* learned_ave merge backward (encoder_layer.py:241-291 up to m = w1 x1 + w2 x2), D == 256,
- * T <= 2048.  EXPERIMENTAL: written after the round's GPU budget was spent, NOT yet run on a GPU
- * (its test needs TAVSR_TEST_BWD_WIP=1).  Given dm = d loss / d m: dx1, dx2 and
- * grads = [da1 | db1 | da2 | db2] (4 x 256: pooling_projK.weight, weight_projK.weight) followed by
- * [dc1, de1, dc2, de2] (their biases), 1028 floats.  aK / bK are the pooling_projK / weight_projK
- * weight vectors, cK / eK their biases.  Arithmetic: oracle/bwd_formulas.py::learned_ave_merge_bwd. */
+ * T <= 2048.  Given dm = d loss / d m: dx1, dx2 and grads = [da1 | db1 | da2 | db2] (4 x 256:
+ * pooling_projK.weight, weight_projK.weight) followed by [dc1, de1, dc2, de2] (their biases), 1028
+ * floats.  aK / bK are the pooling_projK / weight_projK weight vectors; scal is a DEVICE array
+ * [c1, e1, c2, e2] of their biases (read on the device: no host synchronisation inside a training
+ * step).  Arithmetic: oracle/bwd_formulas.py::learned_ave_merge_bwd. */
 size_t tavsr_merge_learned_ave_bwd_workspace_bytes(int B);
 int tavsr_merge_learned_ave_bwd(const float* x1, long long ld1, const float* x2, long long ld2,
                                 const float* dm, long long ldm, const int32_t* lens,
-                                const float* a1, float c1, const float* b1, float e1,
-                                const float* a2, float c2, const float* b2, float e2, float* dx1,
-                                long long ldd1, float* dx2, long long ldd2, float* grads,
-                                void* workspace, long long workspace_bytes, int B, int T, int D,
-                                void* stream);
+                                const float* a1, const float* b1, const float* a2, const float* b2,
+                                const float* scal, float* dx1, long long ldd1, float* dx2,
+                                long long ldd2, float* grads, void* workspace,
+                                long long workspace_bytes, int B, int T, int D, void* stream);
 
 /* Greedy CTC decode: collapse repeats of `amax` and drop blank (espnet_model.py:590-592,
  * maskctc_model.py:287-291).  lens == NULL collapses over all T frames (what _calc_ctc_loss does).

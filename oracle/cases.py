@@ -47,6 +47,12 @@ CASES = {
                                cfg=_enc(num_blocks=3, merge_method="fixed_ave",
                                         cgmlp_weight=[1.0, 0.0, 0.0]),
                                B=2, Tin=163, lens=[163, 99], vocab=37, Lmax=10, seed=13),
+    # the same branch pruning behind the linear front end (the training path's front ends are
+    # linear / None): cgMLP-only, attention-only and a two-branch fixed_ave block in one stack
+    "vsr_tailored_small": dict(kind="single", input_size=512,
+                               cfg=_enc(num_blocks=3, input_layer="linear", merge_method="fixed_ave",
+                                        cgmlp_weight=[1.0, 0.0, 0.4]),
+                               B=2, Tin=61, lens=[61, 38], vocab=41, Lmax=9, seed=35),
     # dormant merges: concat, two-branch fixed_ave
     "concat_small": dict(kind="single", input_size=512,
                          cfg=_enc(num_blocks=2, input_layer="linear", merge_method="concat"),

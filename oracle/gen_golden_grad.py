@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import cases, gen_golden, reference_loader  # noqa: E402
 
-CASES = ["vsr_small", "asr_tailored_small"]
+CASES = ["vsr_small", "asr_tailored_small", "vsr_tailored_small", "concat_small"]
 
 
 def summarize(named_grads):

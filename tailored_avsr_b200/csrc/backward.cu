@@ -360,7 +360,7 @@ struct MergeBwdParams {
   long long ld1, ld2, ldm;
   const int32_t* lens;
   const float* a1; const float* b1; const float* a2; const float* b2;  // [D] vectors
-  float c1, e1, c2, e2;                                                // scalars (biases)
+  const float* scal;   // device [4]: c1, e1, c2, e2 (the Linear(D,1) biases; no host read-back)
   float* dx1; float* dx2;
   long long ldd1, ldd2;
   float* part;    // [B][4][D]
@@ -384,6 +384,7 @@ merge_learned_ave_bwd_kernel(const MergeBwdParams p) {
   s_vec[1][tid] = __ldg(p.a2 + tid);
   const float bb1 = __ldg(p.b1 + tid), bb2 = __ldg(p.b2 + tid);
   pdl_wait();
+  const float pc1 = ld_act(p.scal), pe1 = ld_act(p.scal + 1), pc2 = ld_act(p.scal + 2), pe2 = ld_act(p.scal + 3);
   int len = p.lens ? p.lens[b] : T;
   len = len < 0 ? 0 : (len > T ? T : len);
   const long long row0 = static_cast<long long>(b) * T;
@@ -410,8 +411,8 @@ merge_learned_ave_bwd_kernel(const MergeBwdParams p) {
     sa1 = warp_sum(sa1); sa2 = warp_sum(sa2);
     dw1 += warp_sum(sm1); dw2 += warp_sum(sm2);   // identical in every lane of the warp
     if (lane == 0) {
-      s_s[t] = (sa1 + p.c1) * rs;
-      s_s[T + t] = (sa2 + p.c2) * rs;
+      s_s[t] = (sa1 + pc1) * rs;
+      s_s[T + t] = (sa2 + pc2) * rs;
     }
   }
   // one lane per warp carries the warp's dw partial into the block sums
@@ -442,8 +443,8 @@ merge_learned_ave_bwd_kernel(const MergeBwdParams p) {
     pool1 = fmaf(s_s[t], ld_act(p.x1 + (row0 + t) * p.ld1 + tid), pool1);
     pool2 = fmaf(s_s[T + t], ld_act(p.x2 + (row0 + t) * p.ld2 + tid), pool2);
   }
-  const float om1 = block_sum_256(pool1 * bb1, s_red) + p.e1;
-  const float om2 = block_sum_256(pool2 * bb2, s_red) + p.e2;
+  const float om1 = block_sum_256(pool1 * bb1, s_red) + pe1;
+  const float om2 = block_sum_256(pool2 * bb2, s_red) + pe2;
   const float mo = fmaxf(om1, om2);
   const float e1 = expf(om1 - mo), e2 = expf(om2 - mo);
   const float w1 = e1 / (e1 + e2), w2 = e2 / (e1 + e2);
@@ -657,19 +658,18 @@ extern "C" size_t tavsr_merge_learned_ave_bwd_workspace_bytes(int B) {
   return static_cast<size_t>(B) * (4 * 256 + 4) * sizeof(float);
 }
 
-// EXPERIMENTAL, not yet run on a GPU (see the kernel's header comment).
 // grads: [4][256] = (da1, db1, da2, db2) then [4] = (dc1, de1, dc2, de2), i.e. 1028 floats.
 extern "C" int tavsr_merge_learned_ave_bwd(const float* x1, long long ld1, const float* x2,
                                            long long ld2, const float* dm, long long ldm,
-                                           const int32_t* lens, const float* a1, float c1,
-                                           const float* b1, float e1, const float* a2, float c2,
-                                           const float* b2, float e2, float* dx1, long long ldd1,
+                                           const int32_t* lens, const float* a1, const float* b1,
+                                           const float* a2, const float* b2, const float* scal,
+                                           float* dx1, long long ldd1,
                                            float* dx2, long long ldd2, float* grads, void* workspace,
                                            long long workspace_bytes, int B, int T, int D,
                                            void* stream) {
   TAVSR_REQUIRE(B > 0 && T > 0 && T <= bwd::kMergeT && D == 256,
                 "merge_bwd: built for D == 256, T <= %d (B=%d T=%d D=%d)", bwd::kMergeT, B, T, D);
-  TAVSR_REQUIRE(x1 && x2 && dm && a1 && b1 && a2 && b2 && dx1 && dx2 && grads && workspace,
+  TAVSR_REQUIRE(x1 && x2 && dm && a1 && b1 && a2 && b2 && scal && dx1 && dx2 && grads && workspace,
                 "merge_bwd: null pointer");
   TAVSR_REQUIRE(ld1 % 4 == 0 && ld2 % 4 == 0 && ldm % 4 == 0, "merge_bwd: pitches must be multiples of 4");
   TAVSR_REQUIRE(static_cast<size_t>(workspace_bytes) >= tavsr_merge_learned_ave_bwd_workspace_bytes(B),
@@ -677,7 +677,7 @@ extern "C" int tavsr_merge_learned_ave_bwd(const float* x1, long long ld1, const
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   bwd::MergeBwdParams p;
   p.x1 = x1; p.x2 = x2; p.dm = dm; p.ld1 = ld1; p.ld2 = ld2; p.ldm = ldm; p.lens = lens;
-  p.a1 = a1; p.b1 = b1; p.a2 = a2; p.b2 = b2; p.c1 = c1; p.e1 = e1; p.c2 = c2; p.e2 = e2;
+  p.a1 = a1; p.b1 = b1; p.a2 = a2; p.b2 = b2; p.scal = scal;
   p.dx1 = dx1; p.dx2 = dx2; p.ldd1 = ldd1; p.ldd2 = ldd2;
   p.part = static_cast<float*>(workspace);
   p.part_s = p.part + static_cast<size_t>(B) * 4 * 256;

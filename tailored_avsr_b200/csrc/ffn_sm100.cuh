@@ -333,8 +333,15 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
           uint32_t w[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float x0 = apply_act<kAct>(__uint_as_float(r[2 * i]) + bb[2 * i], p.act);
-            const float x1 = apply_act<kAct>(__uint_as_float(r[2 * i + 1]) + bb[2 * i + 1], p.act);
+            float x0 = __uint_as_float(r[2 * i]) + bb[2 * i];
+            float x1 = __uint_as_float(r[2 * i + 1]) + bb[2 * i + 1];
+            if constexpr (kAct == ACT_SWISH) {   // one SFU op per value: the result is bf16
+              x0 = swish_tanh(x0);
+              x1 = swish_tanh(x1);
+            } else {
+              x0 = apply_act<kAct>(x0, p.act);
+              x1 = apply_act<kAct>(x1, p.act);
+            }
             w[i] = pack_bf16x2(x0, x1);
           }
           tmem_st16(th + part * 64 + cc * 16, w);
@@ -373,14 +380,16 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
   // into its own smem, the other 64 rows into the peer's - and then all eight warps finish rows with
   // coalesced global accesses and shuffle reductions (lane = 8 consecutive columns).
   uint8_t* s_own = smem + C::kOwnOff;  // [64 rows][1 KB], 16-byte chunks XOR-swizzled by row & 7
-  if (warp >= 4 && warp < 8) {
+  if (warp >= 4) {
+    // all eight activation warps: quadrant q, column half (warp - 4) >> 2
     const int q = warp & 3;
+    const int chalf = (warp - 4) >> 2;
     const uint32_t td2 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + C::kColD2;
     const int row_local = (q & 1) * 32 + static_cast<int>(lane);
     const bool mine = static_cast<uint32_t>(q >> 1) == rank;
     const uint32_t base = mine ? smem_u32(s_own) + row_local * 1024
                                : mapa_cluster(smem_u32(s_x) + row_local * 1024, rank ^ 1u);
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 4 * chalf; c < 4 * chalf + 4; ++c) {
       uint32_t r[32];
       tmem_ld32(td2 + c * 32, r);
       tmem_ld_wait();
@@ -410,6 +419,18 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
   };
   float bias[8];
   ld8(s_param + col, bias);
+  // the residual row of the NEXT iteration is requested before the current row is processed: its
+  // L2 latency (the longest single wait of a row) hides behind the reductions and stores
+  float4 pre0 = make_float4(0.f, 0.f, 0.f, 0.f), pre1 = pre0;
+  auto fetch_residual = [&](int r) {
+    const int mm = m0 + static_cast<int>(rank) * 64 + r;
+    if (e.residual != nullptr && r < 64 && mm < e.M) {
+      const float4* rp = reinterpret_cast<const float4*>(e.residual + static_cast<long long>(mm) * e.ldr + col);
+      pre0 = ld_act4(rp);
+      pre1 = ld_act4(rp + 1);
+    }
+  };
+  fetch_residual(warp);
   for (int r = warp; r < 64; r += C::kThreads / 32) {
     const int m = m0 + static_cast<int>(rank) * 64 + r;
     if (m >= e.M) break;  // warp-uniform; rows only grow
@@ -421,12 +442,8 @@ ffn_fused_kernel(const __grid_constant__ FfnParams p) {
       const float4 o1 = *reinterpret_cast<const float4*>(s_own + r * 1024 + sw1);
       const float4 q0 = *reinterpret_cast<const float4*>(s_x + r * 1024 + sw0);
       const float4 q1 = *reinterpret_cast<const float4*>(s_x + r * 1024 + sw1);
-      float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
-      if (e.residual != nullptr) {
-        const float4* rp = reinterpret_cast<const float4*>(e.residual + static_cast<long long>(m) * e.ldr + col);
-        r0 = ld_act4(rp);
-        r1 = ld_act4(rp + 1);
-      }
+      const float4 r0 = pre0, r1 = pre1;
+      fetch_residual(r + C::kThreads / 32);
       v[0] = r0.x + e.alpha * (o0.x + q0.x + bias[0]);
       v[1] = r0.y + e.alpha * (o0.y + q0.y + bias[1]);
       v[2] = r0.z + e.alpha * (o0.z + q0.z + bias[2]);

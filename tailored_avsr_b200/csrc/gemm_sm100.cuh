@@ -117,6 +117,18 @@ struct GemmCfg {
   static_assert(kStages >= 2, "pipeline needs at least two stages");
 };
 
+// Swish with ONE special-function op: x sigmoid(x) = h + h tanh(h), h = x / 2 (tanh.approx.f32,
+// relative error ~2^-11).  The exact form below costs two (ex2 + rcp) and the SFU pipe (16 per
+// clock per SM) is what bounds the fused FFN's activation stage: 128 x 128 values per chunk are
+// 2048 cycles of SFU time, as much as the two GEMMs of the chunk.  Used where the result is rounded
+// to bf16 (2^-9) anyway.
+__device__ __forceinline__ float swish_tanh(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+
 template <int kAct>
 __device__ __forceinline__ float apply_act(float x, int act_rt) {
   const int act = kAct >= 0 ? kAct : act_rt;

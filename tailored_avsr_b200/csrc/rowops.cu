@@ -348,9 +348,13 @@ __global__ void __launch_bounds__(128)
 merge_weights_plain_kernel(const float2* __restrict__ dots1, const float2* __restrict__ dots2,
                      const int32_t* __restrict__ lens, float pool_b1, float pool_b2, float wproj_b1,
                      float wproj_b2, float inv_sqrt, float* __restrict__ w1, float* __restrict__ w2,
-                     int B, int T) {
+                     int B, int T, const float* __restrict__ scal) {
   pdl_launch_dependents();
   pdl_wait();
+  if (scal != nullptr) {   // training: the biases live on the device
+    pool_b1 = ld_act(scal); pool_b2 = ld_act(scal + 1);
+    wproj_b1 = ld_act(scal + 2); wproj_b2 = ld_act(scal + 3);
+  }
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
   const uint32_t lane = lane_id();
@@ -603,7 +607,8 @@ extern "C" int tavsr_merge_learned_ave_weights2(const float* dots1, int np1, con
     TAVSR_CUDA_OK(launch_kernel(merge_weights_plain_kernel, dim3((B + 3) / 4), dim3(128), 0, s, 0,
                                 reinterpret_cast<const float2*>(dots1),
                                 reinterpret_cast<const float2*>(dots2), lens1, pool_b1, pool_b2,
-                                wproj_b1, wproj_b2, inv_sqrt_size, w1, w2, B, T));
+                                wproj_b1, wproj_b2, inv_sqrt_size, w1, w2, B, T,
+                                static_cast<const float*>(nullptr)));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return 0;
   }
@@ -611,6 +616,20 @@ extern "C" int tavsr_merge_learned_ave_weights2(const float* dots1, int np1, con
                               reinterpret_cast<const float2*>(dots1), np1,
                               reinterpret_cast<const float2*>(dots2), np2, lens1, lens2, pool_b1,
                               pool_b2, wproj_b1, wproj_b2, inv_sqrt_size, w1, w2, B, T));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+extern "C" int tavsr_merge_learned_ave_weights_dev(const float* dots1, const float* dots2,
+                                                   const int32_t* lens, const float* scal,
+                                                   float inv_sqrt_size, float* w1, float* w2, int B,
+                                                   int T, void* stream) {
+  TAVSR_REQUIRE(B > 0 && T > 0 && dots1 && dots2 && scal && w1 && w2, "merge_weights: bad arguments");
+  TAVSR_CUDA_OK(launch_kernel(merge_weights_plain_kernel, dim3((B + 3) / 4), dim3(128), 0,
+                              static_cast<cudaStream_t>(stream), 0,
+                              reinterpret_cast<const float2*>(dots1),
+                              reinterpret_cast<const float2*>(dots2), lens, 0.f, 0.f, 0.f, 0.f,
+                              inv_sqrt_size, w1, w2, B, T, scal));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }

@@ -10,7 +10,7 @@ from typing import List, Optional, Tuple
 import torch
 import torch.nn.functional as F
 
-from ... import engine, ops
+from ... import engine, ops, training
 from ...espnet_compat import (AbsEncoder, Conv2dSubsampling, ConvolutionalGatingMLP, LayerNorm,
                               PositionwiseFeedForward, RelPositionalEncoding,
                               RelPositionMultiHeadedAttention, TooShortUttError, check_short_utt,
@@ -286,7 +286,10 @@ class MyBranchformerEncoder(AbsEncoder):
                 ) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
         """Same contract as the reference forward (encoder.py:324-343)."""
         x_in = xs_pad[0] if isinstance(xs_pad, tuple) else xs_pad
-        engine.require_inference(self, x_in)
+        engine.require_cuda(x_in)
+        if training.wants_grad(self, x_in):
+            # training step: one autograd node per block on the backward kernels (training.py)
+            return training.encoder_forward(self, xs_pad, ilens, max_layer=max_layer)
         if self.interctc_use_conditioning and len(self.interctc_layer_idx) > 0:
             if ctc is None or self.conditioning_layer is None:
                 raise ValueError("InterCTC self-conditioning needs the `ctc` module and an assigned "

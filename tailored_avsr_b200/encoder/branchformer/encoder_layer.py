@@ -90,10 +90,11 @@ class MyBranchformerEncoderLayer(torch.nn.Module):
         if self.feed_forward_macaron is None or self.feed_forward is None:
             raise NotImplementedError("macaron=False / missing FFN is not built (the reference "
                                       "itself crashes at encoder_layer.py:193 without macaron)")
-        if self.training and (self.dropout.p > 0 or self.stochastic_depth_rate > 0
-                              or self.attn_branch_drop_rate > 0):
-            raise NotImplementedError("training-mode dropout / stochastic depth / branch drop are "
-                                      "not built on the B200 path yet; use .eval()")
+        if self.training and not torch.is_grad_enabled() and (
+                self.dropout.p > 0 or self.stochastic_depth_rate > 0 or self.attn_branch_drop_rate > 0):
+            raise NotImplementedError("a no-grad call in train() mode with dropout / stochastic depth / "
+                                      "branch drop enabled: the inference kernels have no random "
+                                      "paths; use .eval() (or a grad-mode call: training.py)")
 
     def run(self, x: torch.Tensor, xn: torch.Tensor, pos_proj: Optional[torch.Tensor],
             lens: torch.Tensor, B: int, T: int, next_norm=None, next_norm_dtype=None):
@@ -289,10 +290,14 @@ class MyBranchformerEncoderLayer(torch.nn.Module):
         else:
             x, pos_emb = x_input, None
         self._check_supported()
-        engine.require_inference(self, x)
+        engine.require_cuda(x)
         B, T, d = x.shape
         x2 = x.reshape(B * T, d).contiguous().float()
         lens = engine.lens_from_mask(mask, B, T, x.device)
+        from ... import training
+        if training.wants_grad(self, x):
+            y = training.run_block(self, x2, B, T, lens, pos_emb).view(B, T, d)
+            return ((y, pos_emb), mask) if pos_emb is not None else (y, mask)
         xn = ops.layernorm(x2, self.norm_ff_macaron.weight, self.norm_ff_macaron.bias, eps=1e-12,
                            out_dtype=engine.act_dtype())
         pos_proj = None

@@ -187,18 +187,24 @@ class PackedCache:
         return val
 
 
-def require_inference(module: torch.nn.Module, *tensors) -> None:
-    """The backward kernels of this path are not built yet: refuse loudly instead of silently
-    detaching the graph."""
-    if torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters()):
-        raise NotImplementedError(
-            "tailored_avsr_b200: the CUDA backward kernels for the encoder are not built in this "
-            "round; call the encoder under torch.no_grad() / torch.inference_mode() "
-            "(see DESIGN.md, 'Training path').")
+def require_cuda(*tensors) -> None:
     for t in tensors:
         if t is not None and not t.is_cuda:
             raise RuntimeError("tailored_avsr_b200 runs on CUDA tensors only (there is no CPU "
                                "fallback); move the module and its inputs to a B200 device")
+
+
+def require_inference(module: torch.nn.Module, *tensors) -> None:
+    """For the modules whose backward is not built (the tailored AV layer, the fusion module, the AV
+    embedding layer, InterCTC): refuse a grad-mode call loudly instead of silently detaching the
+    graph.  MyBranchformerEncoder / its layers / ConventionalEncoder / CTC route grad-mode calls to
+    training.py instead."""
+    if torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters()):
+        raise NotImplementedError(
+            f"tailored_avsr_b200: {type(module).__name__} has no CUDA backward yet; call it under "
+            "torch.no_grad() / torch.inference_mode() (the training path covers "
+            "MyBranchformerEncoder, ConventionalEncoder and CTC: see README 'Training').")
+    require_cuda(*tensors)
 
 
 def lens_from_mask(mask: Optional[torch.Tensor], B: int, T: int, device) -> torch.Tensor:

@@ -404,6 +404,19 @@ def merge_weights(dots1: torch.Tensor, dots2: torch.Tensor, lens: Optional[torch
 
 
 @_profiled
+def merge_weights_dev(dots1: torch.Tensor, dots2: torch.Tensor, lens: Optional[torch.Tensor],
+                      scal: torch.Tensor, size: int, B: int, T: int):
+    """merge_weights with the four biases (pool_b1, pool_b2, wproj_b1, wproj_b2) read from the device
+    tensor `scal` (training: parameters change every step, no host read-back)."""
+    w1 = torch.empty((B,), device=dots1.device, dtype=torch.float32)
+    w2 = torch.empty((B,), device=dots1.device, dtype=torch.float32)
+    check(_lib.load().tavsr_merge_learned_ave_weights_dev(
+        dots1.data_ptr(), dots2.data_ptr(), _p(lens), scal.data_ptr(), 1.0 / math.sqrt(size),
+        w1.data_ptr(), w2.data_ptr(), B, T, _stream()), "tavsr_merge_learned_ave_weights_dev")
+    return w1, w2
+
+
+@_profiled
 def row_dots(a1: torch.Tensor, va1: torch.Tensor, vb1: torch.Tensor,
              a2: Optional[torch.Tensor] = None, va2: Optional[torch.Tensor] = None,
              vb2: Optional[torch.Tensor] = None):

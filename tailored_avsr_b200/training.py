@@ -1,0 +1,459 @@
+"""Training path of the Branchformer encoder on the B200 kernels: forward that keeps what the
+backward needs, hand-composed backward, wired into autograd as ONE node per encoder block.
+
+Reference being differentiated: `MyBranchformerEncoderLayer.forward`
+(src/encoder/branchformer/encoder_layer.py:153-321) inside `MyBranchformerEncoder.forward`
+(src/encoder/branchformer/encoder.py:324-412), trained every step by avsr_main.py:27-57.
+
+Why one autograd node per block: autograd runs the blocks' backward nodes last-to-first and hands
+every parameter gradient to its AccumulateGrad node as soon as the block's node returns, so the
+bucketed gradient all-reduce (parallel.GradBucketReducer, hooked per parameter) overlaps the
+backward of the earlier blocks - the DDP pattern SURVEY.md §8e asks for.
+
+Forward = the un-fused kernel sequence (the fused FFN keeps its 2048-wide hidden on chip and the
+folded merge never forms x1 / x2: both would have to be recomputed for the weight gradients):
+    xn0 = LN_ffmac(x)                      z1 = xn0 W1^T + b1          h1 = swish(z1)
+    x_a = x + .5 (h1 W2^T + b2)            xa = LN_mha(x_a), xm = LN_mlp(x_a)
+    qkv = xa Wqkv^T + b                    ctx, lse = relpos_attn(qkv, linear_pos(pos_emb), u, v)
+    x1 = ctx Wo^T + bo                     zc = xm Wc1^T + bc1, hc = gelu(zc), u = csgu(hc), x2 = u Wc2^T + b
+    (w1, w2) = learned_ave(x1, x2)         x_b = x_a + c (w1 x1 + w2 x2) Wm^T + bm,  xf = LN_ff(x_b)
+    z2, h2 likewise                        y0 = x_b + .5 (h2 W2^T + b2),   y = LN_final(y0)
+Kept per block: x, xn0, z1, x_a, xa, xm, qkv, pos_proj, ctx, lse, x1, zc, u, CSGU (mean, rstd), x2,
+w1, w2, x_b, xf, z2, y0 (~0.6 GB at the C2 shape).  Backward = oracle/manual_backward.py's
+composition (equal to autograd on the reference's own modules: tests/golden/grad_*.npz) on the
+kernels of ops_backward.py: dgrad / wgrad on the tcgen05 GEMM, LayerNorm / activation / CSGU /
+merge / rel-pos attention backward kernels.  Storage is fp32 and the products run on TF32 operands
+in every compute mode (the bf16 mode is an inference mode).
+
+Training-only randomness follows the reference's host RNG stream: stochastic depth draws
+`torch.rand(1).item()` at layer entry (encoder_layer.py:180-182), attention-branch drop draws it
+inside the learned_ave merge (:233-239), in that order, layer by layer.  Dropout layers with p > 0
+are not built (every Dropout must be p = 0 or the module in eval mode): see README "Training".
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import engine, ops
+from . import ops_backward as ob
+
+F32 = torch.float32
+
+
+def wants_grad(module: torch.nn.Module, *tensors) -> bool:
+    """True when this call has to build an autograd graph (grad mode on and a parameter or an input
+    asks for gradients)."""
+    if not torch.is_grad_enabled():
+        return False
+    if any(t is not None and torch.is_tensor(t) and t.requires_grad for t in tensors):
+        return True
+    return any(p.requires_grad for p in module.parameters())
+
+
+def _no_dropout(module: torch.nn.Module, what: str) -> None:
+    """The parameter containers of espnet_compat.py record their dropout rates as `dropout_rate`
+    attributes (they own no Dropout module); torch.nn.Dropout modules are checked too."""
+    if not module.training:
+        return
+    for m in module.modules():
+        p = m.p if isinstance(m, torch.nn.Dropout) else getattr(m, "dropout_rate", 0.0)
+        if isinstance(p, (int, float)) and p > 0:
+            raise NotImplementedError(
+                f"tailored_avsr_b200 training path: {what} ({type(m).__name__}) has an active "
+                f"dropout rate {p}; only 0.0 is built (stochastic depth and attention-branch drop "
+                "are).  Set dropout_rate / attention_dropout_rate / positional_dropout_rate to 0.0 "
+                "in the YAML, or put the module in eval mode (gradients still flow).")
+
+
+def _named(layer: torch.nn.Module) -> Tuple[List[str], List[torch.nn.Parameter]]:
+    names, params = [], []
+    for n, p in layer.named_parameters():
+        names.append(n)
+        params.append(p)
+    return names, params
+
+
+def _acc(g: Dict[str, torch.Tensor], key: str, val: torch.Tensor) -> None:
+    g[key] = g[key] + val if key in g else val
+
+
+def _lin_bwd(g, x_in, lin_w, dy, wname: Optional[str], bname: Optional[str], need_dx=True):
+    dx, dw, db = ob.linear_bwd(x_in, lin_w, dy, need_dx=need_dx, need_dw=wname is not None)
+    if wname is not None:
+        _acc(g, wname, dw)
+        if bname is not None:
+            _acc(g, bname, db)
+    return dx
+
+
+def _ln_bwd(g, x, norm, dy, prefix: str, eps: float = 1e-12, dres=None):
+    dx, dg, db = ob.layernorm_bwd(x, norm.weight, dy, eps=eps, dres=dres)
+    _acc(g, prefix + ".weight", dg)
+    _acc(g, prefix + ".bias", db)
+    return dx
+
+
+def _half(t: torch.Tensor) -> torch.Tensor:
+    """0.5 * t on our elementwise kernel (the ff_scale of the macaron FFNs)."""
+    half, zero = _scalars(t.device)
+    return ops.scale_add_rows(t, t, half, zero, max(1, t.shape[0]))
+
+
+_SC = {}
+
+
+def _scalars(device):
+    s = _SC.get(device)
+    if s is None:
+        s = _SC[device] = (torch.full((1,), 0.5, device=device), torch.zeros(1, device=device))
+    return s
+
+
+# ---------------------------------------------------------------------------------------------------
+# position-wise feed-forward (espnet PositionwiseFeedForward + the residual line around it)
+# ---------------------------------------------------------------------------------------------------
+def _ffn_forward(xn, ff, residual, out_main, lnA=None, out_lnA=None, lnB=None, out_lnB=None):
+    act = engine.act_code(ff.activation_type)
+    z = ops.gemm_bias_act(xn, ff.w_1.weight, ff.w_1.bias)
+    h = ob.act_fwd(z, act)
+    ops.gemm_rowln(h, ff.w_2.weight, ff.w_2.bias, residual=residual, alpha=0.5, out_main=out_main,
+                   lnA=lnA, out_lnA=out_lnA, lnB=lnB, out_lnB=out_lnB)
+    return z
+
+
+def _ffn_backward(g, xn, z, ff, dout, prefix: str):
+    """dout = d loss / d (residual + 0.5 ffn(xn)); returns d loss / d xn."""
+    act = engine.act_code(ff.activation_type)
+    dhalf = _half(dout)
+    h = ob.act_fwd(z, act)                               # recomputed: only z is kept
+    dh = _lin_bwd(g, h, ff.w_2.weight, dhalf, prefix + ".w_2.weight", prefix + ".w_2.bias")
+    dz = ob.act_bwd(z, dh, act)
+    return _lin_bwd(g, xn, ff.w_1.weight, dz, prefix + ".w_1.weight", prefix + ".w_1.bias")
+
+
+# ---------------------------------------------------------------------------------------------------
+# one Branchformer block
+# ---------------------------------------------------------------------------------------------------
+def block_forward(L, aux, x: torch.Tensor) -> Tuple[torch.Tensor, dict]:
+    B, T = aux.B, aux.T
+    M, d = B * T, L.size
+    dev = x.device
+    new = lambda c=d: torch.empty((M, c), device=dev, dtype=F32)  # noqa: E731
+    sv = {"x": x}
+    two = L.use_two_branches
+    learned = two and L.merge_method == "learned_ave" and not aux.drop_attn
+    # ---- macaron FFN ----
+    sv["xn0"] = ops.layernorm(x, L.norm_ff_macaron.weight, L.norm_ff_macaron.bias, eps=1e-12)
+    x_a = new()
+    xa = new() if L.attn is not None else None
+    xm = new() if L.cgmlp is not None else None
+    lnA = (L.norm_mha.weight, L.norm_mha.bias) if L.attn is not None else None
+    lnB = (L.norm_mlp.weight, L.norm_mlp.bias) if L.cgmlp is not None else None
+    if lnA is None:
+        sv["z1"] = _ffn_forward(sv["xn0"], L.feed_forward_macaron, x, x_a, lnA=lnB, out_lnA=xm)
+    else:
+        sv["z1"] = _ffn_forward(sv["xn0"], L.feed_forward_macaron, x, x_a, lnA=lnA, out_lnA=xa,
+                                lnB=lnB, out_lnB=xm)
+    sv.update(x_a=x_a, xa=xa, xm=xm)
+    x1 = x2 = d1 = d2 = None
+    # ---- attention branch ----
+    if L.attn is not None:
+        A = L.attn
+        if aux.pos2d is None:
+            raise NotImplementedError("attention without relative positional embedding is not built")
+        wqkv = torch.cat([A.linear_q.weight, A.linear_k.weight, A.linear_v.weight], 0)
+        bqkv = torch.cat([A.linear_q.bias, A.linear_k.bias, A.linear_v.bias], 0)
+        qkv = ops.gemm_bias_act(xa, wqkv, bqkv)
+        pp = ops.gemm_bias_act(aux.pos2d, A.linear_pos.weight, None)
+        lse = torch.empty((B, A.h, T), device=dev, dtype=F32)
+        ctx = ops.relpos_attn(qkv, pp, A.pos_bias_u.reshape(-1), A.pos_bias_v.reshape(-1), aux.lens,
+                              B, T, A.h, round_out=False, lse=lse)
+        x1 = new()
+        dots = None
+        if learned:
+            d1 = torch.empty((M, 2), device=dev, dtype=F32)
+            dots = (L.pooling_proj1.weight.reshape(-1), L.weight_proj1.weight.reshape(-1))
+        ops.gemm_rowln(ctx, A.linear_out.weight, A.linear_out.bias, out_main=x1, dots=dots, dots_out=d1)
+        sv.update(wqkv=wqkv, qkv=qkv, pp=pp, lse=lse, ctx=ctx, x1=x1)
+    # ---- cgMLP branch ----
+    if L.cgmlp is not None:
+        Cg = L.cgmlp
+        if Cg.csgu.linear is not None or Cg.csgu.gate_activation != "identity":
+            raise NotImplementedError("use_linear_after_conv / non-identity gate are not built")
+        lin = Cg.channel_proj1[0]
+        conv = Cg.csgu.conv
+        zc = ops.gemm_bias_act(xm, lin.weight, lin.bias)
+        hc = ob.act_fwd(zc, ops.ACT_GELU)
+        stats = torch.empty((M, 2), device=dev, dtype=F32)
+        u = ops.csgu(hc, Cg.csgu.norm.weight, Cg.csgu.norm.bias, conv.weight.reshape(conv.weight.shape[0], -1),
+                     conv.bias, B, T, eps=Cg.csgu.norm.eps, round_out=False, stats=stats)
+        x2 = new()
+        dots = None
+        if learned:
+            d2 = torch.empty((M, 2), device=dev, dtype=F32)
+            dots = (L.pooling_proj2.weight.reshape(-1), L.weight_proj2.weight.reshape(-1))
+        ops.gemm_rowln(u, Cg.channel_proj2.weight, Cg.channel_proj2.bias, out_main=x2, dots=dots,
+                       dots_out=d2)
+        sv.update(zc=zc, stats=stats, u=u, x2=x2)
+    # ---- merge (:227-309) ----
+    x_b, xf = new(), new()
+    lnF = (L.norm_ff.weight, L.norm_ff.bias)
+    mp = L.merge_proj
+    if isinstance(mp, torch.nn.Identity):
+        raise NotImplementedError("single-branch block built with merge_proj=Identity is not built")
+    if two and L.merge_method in ("learned_ave", "fixed_ave"):
+        if L.merge_method == "learned_ave":
+            if learned:
+                scal = torch.cat([L.pooling_proj1.bias, L.pooling_proj2.bias, L.weight_proj1.bias,
+                                  L.weight_proj2.bias]).float()
+                w1, w2 = ops.merge_weights_dev(d1, d2, aux.lens, scal, d, B, T)
+            else:   # attention branch dropped for this step (:233-239)
+                w1 = torch.zeros((B,), device=dev, dtype=F32)
+                w2 = torch.ones((B,), device=dev, dtype=F32)
+            L.weight_global, L.weight_local = w1.detach().view(B, 1, 1), w2.detach().view(B, 1, 1)
+        else:
+            w1 = torch.full((B,), 1.0 - L.cgmlp_weight, device=dev, dtype=F32)
+            w2 = torch.full((B,), float(L.cgmlp_weight), device=dev, dtype=F32)
+        ops.gemm_rowln(x1, mp.weight, mp.bias, x2=x2, rowscale=(w1, w2), rows_per_seg=T, residual=x_a,
+                       alpha=aux.stoch, out_main=x_b, lnA=lnF, out_lnA=xf)
+        sv.update(w1=w1, w2=w2)
+    elif two:   # concat
+        cat = torch.cat([x1, x2], 1)
+        ops.gemm_rowln(cat, mp.weight, mp.bias, residual=x_a, alpha=aux.stoch, out_main=x_b, lnA=lnF,
+                       out_lnA=xf)
+    else:
+        xs = x2 if L.attn is None else x1
+        ops.gemm_rowln(xs, mp.weight, mp.bias, residual=x_a, alpha=aux.stoch, out_main=x_b, lnA=lnF,
+                       out_lnA=xf)
+    sv.update(x_b=x_b, xf=xf, learned=learned)
+    # ---- FFN + norm_final ----
+    y0, y = new(), new()
+    sv["z2"] = _ffn_forward(xf, L.feed_forward, x_b, y0, lnA=(L.norm_final.weight, L.norm_final.bias),
+                            out_lnA=y)
+    sv["y0"] = y0
+    return y, sv
+
+
+def block_backward(L, aux, sv: dict, dy: torch.Tensor) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+    B, T = aux.B, aux.T
+    M, d = B * T, L.size
+    dev = dy.device
+    g: Dict[str, torch.Tensor] = {}
+    two = L.use_two_branches
+    # ---- norm_final, FFN, norm_ff ----
+    dy0 = _ln_bwd(g, sv["y0"], L.norm_final, dy, "norm_final")
+    dxf = _ffn_backward(g, sv["xf"], sv["z2"], L.feed_forward, dy0, "feed_forward")
+    dx_b = _ln_bwd(g, sv["x_b"], L.norm_ff, dxf, "norm_ff", dres=dy0)          # residual joins here
+    # ---- merge ----
+    mp = L.merge_proj
+    dmo = dx_b
+    if aux.stoch != 1.0:   # x_b = x_a + c * (merge_proj(m)): the projection sees c * dx_b
+        c = torch.full((1,), float(aux.stoch), device=dev)
+        dmo = ops.scale_add_rows(dx_b, dx_b, c, _scalars(dev)[1], M)
+    x1, x2 = sv.get("x1"), sv.get("x2")
+    dx1 = dx2 = None
+    if two and L.merge_method in ("learned_ave", "fixed_ave"):
+        w1, w2 = sv["w1"], sv["w2"]
+        m = ops.scale_add_rows(x1, x2, w1, w2, T)
+        dm = _lin_bwd(g, m, mp.weight, dmo, "merge_proj.weight", "merge_proj.bias")
+        if sv["learned"]:
+            scal = torch.cat([L.pooling_proj1.bias, L.weight_proj1.bias, L.pooling_proj2.bias,
+                              L.weight_proj2.bias]).float()
+            dx1, dx2, gr = ob.merge_learned_ave_bwd(
+                x1, x2, dm, aux.lens, L.pooling_proj1.weight.reshape(-1), L.weight_proj1.weight.reshape(-1),
+                L.pooling_proj2.weight.reshape(-1), L.weight_proj2.weight.reshape(-1), scal, B, T)
+            D = d
+            for k, name in enumerate(("pooling_proj1", "weight_proj1", "pooling_proj2", "weight_proj2")):
+                _acc(g, name + ".weight", gr[k * D:(k + 1) * D].reshape(1, D))
+                _acc(g, name + ".bias", gr[4 * D + k:4 * D + k + 1])
+        else:
+            zero = torch.zeros((B,), device=dev, dtype=F32)
+            dx1 = ops.scale_add_rows(dm, dm, w1, zero, T)
+            dx2 = ops.scale_add_rows(dm, dm, w2, zero, T)
+    elif two:   # concat
+        cat = torch.cat([x1, x2], 1)
+        dcat = _lin_bwd(g, cat, mp.weight, dmo, "merge_proj.weight", "merge_proj.bias")
+        dx1, dx2 = dcat[:, :d], dcat[:, d:]
+    else:
+        xs = x2 if L.attn is None else x1
+        dxs = _lin_bwd(g, xs, mp.weight, dmo, "merge_proj.weight", "merge_proj.bias")
+        dx1, dx2 = (None, dxs) if L.attn is None else (dxs, None)
+    dx_a = dx_b
+    # ---- attention branch ----
+    if L.attn is not None:
+        A = L.attn
+        dctx = _lin_bwd(g, sv["ctx"], A.linear_out.weight, dx1, "attn.linear_out.weight", "attn.linear_out.bias")
+        dqkv, dpos, du, dv = ob.relpos_attn_bwd(sv["qkv"], sv["pp"], A.pos_bias_u.reshape(-1),
+                                                A.pos_bias_v.reshape(-1), aux.lens, sv["ctx"], dctx,
+                                                sv["lse"], B, T, A.h)
+        _acc(g, "attn.pos_bias_u", du.view(A.h, A.d_k))
+        _acc(g, "attn.pos_bias_v", dv.view(A.h, A.d_k))
+        # d linear_pos.weight = dpos^T . pos_emb (reduction over the 2T-1 relative positions)
+        _acc(g, "attn.linear_pos.weight",
+             ops.gemm_bias_act(ob.transpose_2d(dpos, pad=True), aux.pos2d_T, None))
+        dxa, dwqkv, dbqkv = ob.linear_bwd(sv["xa"], sv["wqkv"], dqkv)
+        D = d
+        for k, name in enumerate(("q", "k", "v")):
+            _acc(g, f"attn.linear_{name}.weight", dwqkv[k * D:(k + 1) * D])
+            _acc(g, f"attn.linear_{name}.bias", dbqkv[k * D:(k + 1) * D])
+        dx_a = _ln_bwd(g, sv["x_a"], L.norm_mha, dxa, "norm_mha", dres=dx_a)
+    # ---- cgMLP branch ----
+    if L.cgmlp is not None:
+        Cg = L.cgmlp
+        lin, conv = Cg.channel_proj1[0], Cg.csgu.conv
+        du_ = _lin_bwd(g, sv["u"], Cg.channel_proj2.weight, dx2, "cgmlp.channel_proj2.weight",
+                       "cgmlp.channel_proj2.bias")
+        hc = ob.act_fwd(sv["zc"], ops.ACT_GELU)
+        dhc, dng, dnb, dcw, dcb = ob.csgu_bwd(hc, Cg.csgu.norm.weight, Cg.csgu.norm.bias,
+                                              conv.weight.reshape(conv.weight.shape[0], -1), conv.bias,
+                                              sv["stats"], du_, B, T, eps=Cg.csgu.norm.eps)
+        _acc(g, "cgmlp.csgu.norm.weight", dng)
+        _acc(g, "cgmlp.csgu.norm.bias", dnb)
+        _acc(g, "cgmlp.csgu.conv.weight", dcw.view_as(conv.weight))
+        _acc(g, "cgmlp.csgu.conv.bias", dcb)
+        dzc = ob.act_bwd(sv["zc"], dhc, ops.ACT_GELU)
+        dxm = _lin_bwd(g, sv["xm"], lin.weight, dzc, "cgmlp.channel_proj1.0.weight",
+                       "cgmlp.channel_proj1.0.bias")
+        dx_a = _ln_bwd(g, sv["x_a"], L.norm_mlp, dxm, "norm_mlp", dres=dx_a)
+    # ---- macaron FFN ----
+    dxn0 = _ffn_backward(g, sv["xn0"], sv["z1"], L.feed_forward_macaron, dx_a, "feed_forward_macaron")
+    dx = _ln_bwd(g, sv["x"], L.norm_ff_macaron, dxn0, "norm_ff_macaron", dres=dx_a)
+    return dx, g
+
+
+class _BlockFn(torch.autograd.Function):
+    """One Branchformer block as one autograd node (forward: block_forward, backward: block_backward)."""
+
+    @staticmethod
+    def forward(ctx, L, aux, names, x, *params):
+        y, sv = block_forward(L, aux, x.contiguous())
+        ctx.L, ctx.aux, ctx.sv, ctx.names = L, aux, sv, names
+        ctx.params = params
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dx, g = block_backward(ctx.L, ctx.aux, ctx.sv, dy.contiguous())
+        ctx.sv = None   # free the saved activations as soon as the block is done
+        grads = []
+        for n, p in zip(ctx.names, ctx.params):
+            gp = g.get(n)
+            grads.append(gp.reshape(p.shape) if gp is not None and p.requires_grad else None)
+        return (None, None, None, dx) + tuple(grads)
+
+
+class _LayerNormFn(torch.autograd.Function):
+    """y = scale * LayerNorm(x) (after_norm; the `linear` input layer's LayerNorm x sqrt(d))."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, scale):
+        ctx.save_for_backward(x, weight)
+        ctx.eps, ctx.scale = eps, scale
+        return ops.layernorm(x, weight, bias, eps=eps, scale=scale)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        s = ctx.scale
+        gam = weight if s == 1.0 else weight * s        # d/dx of s * LN(x) == LN-backward with s * gamma
+        dx, dg, db = ob.layernorm_bwd(x, gam.contiguous(), dy.contiguous(), eps=ctx.eps)
+        if s != 1.0:
+            dg, db = dg * s, db * s
+        return dx, dg, db, None, None
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = x W^T + b on the tcgen05 GEMM (the `linear` input layer)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.need_dx = x.requires_grad
+        return ops.gemm_bias_act(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dx, dw, db = ob.linear_bwd(x, weight, dy.contiguous(), need_dx=ctx.need_dx)
+        return dx, dw, db
+
+
+def make_aux(layer, B: int, T: int, lens: torch.Tensor, pos_emb: Optional[torch.Tensor]):
+    """Per-call constants of a block plus the training-only random decisions, drawn from the host
+    RNG exactly where the reference draws them (encoder_layer.py:176-189, 233-239).  Returns None
+    when stochastic depth skips the layer."""
+    stoch = 1.0
+    if layer.training and layer.stochastic_depth_rate > 0:
+        skip = torch.rand(1).item() < layer.stochastic_depth_rate
+        stoch = 1.0 / (1 - layer.stochastic_depth_rate)
+        if skip:
+            return None
+    drop_attn = False
+    if (layer.use_two_branches and layer.merge_method == "learned_ave" and layer.training
+            and layer.attn_branch_drop_rate > 0):
+        drop_attn = torch.rand(1).item() < layer.attn_branch_drop_rate
+    pos2d = pos2d_T = None
+    if pos_emb is not None:
+        pos2d = pos_emb.reshape(-1, pos_emb.shape[-1]).contiguous().float()
+        pos2d_T = ob.transpose_2d(pos2d, pad=True)
+    return SimpleNamespace(B=B, T=T, lens=lens, pos2d=pos2d, pos2d_T=pos2d_T, stoch=stoch,
+                           drop_attn=drop_attn)
+
+
+def run_block(layer, x2d: torch.Tensor, B: int, T: int, lens: torch.Tensor,
+              pos_emb: Optional[torch.Tensor], shared_pos=None) -> torch.Tensor:
+    """Training forward of one block on (B*T, d) activations, as an autograd node."""
+    layer._check_supported()
+    _no_dropout(layer, type(layer).__name__)
+    aux = make_aux(layer, B, T, lens, pos_emb if shared_pos is None else None)
+    if aux is None:
+        return x2d                                     # stochastic depth: the layer is skipped
+    if shared_pos is not None:
+        aux.pos2d, aux.pos2d_T = shared_pos
+    names, params = _named(layer)
+    return _BlockFn.apply(layer, aux, names, x2d, *params)
+
+
+def encoder_forward(enc, xs_pad, ilens, max_layer=None, masks=None):
+    """Training forward of MyBranchformerEncoder (encoder.py:324-412, plain layer loop and the
+    max_layer early exit).  Returns (out (B,T,d), olens, None) with an autograd graph behind `out`.
+    `masks` (B,1,T): given by the AV wrappers instead of `ilens`."""
+    if len(enc.interctc_layer_idx) > 0:
+        raise NotImplementedError("InterCTC taps / self-conditioning are not built on the training path "
+                                  "(no shipped config uses them: interctc_weight = 0.0 everywhere)")
+    x_in = xs_pad[0] if isinstance(xs_pad, tuple) else xs_pad
+    dev = x_in.device
+    d = enc._output_size
+    Tin = x_in.size(1)
+    if masks is None:
+        masks = (torch.arange(Tin, device=dev)[None, :] < ilens.to(dev)[:, None]).unsqueeze(1)
+    if enc.embed is None:
+        xs, pos_emb = xs_pad
+        B, T, _ = xs.shape
+        x = xs.reshape(B * T, d).contiguous().float()
+    elif isinstance(enc.embed, torch.nn.Sequential):          # input_layer == "linear"
+        _no_dropout(enc.embed, "embed")
+        B, T, Fd = x_in.shape
+        lin, ln = enc.embed[0], enc.embed[1]
+        e0 = _LinearFn.apply(x_in.reshape(B * T, Fd).contiguous().float(), lin.weight, lin.bias)
+        x = _LayerNormFn.apply(e0, ln.weight, ln.bias, ln.eps, math.sqrt(d))
+        pos_emb = enc.embed[3].pos_emb(T, dev)
+    else:
+        raise NotImplementedError("the training path has no backward for the conv2d front end yet "
+                                  "(input_layer 'linear' and None are built): see README 'Training'")
+    lens = masks.reshape(B, -1).sum(dim=1).to(torch.int32)
+    pos2d = pos_emb.reshape(-1, d).contiguous().float()
+    shared = (pos2d, ob.transpose_2d(pos2d, pad=True))
+    n = len(enc.encoders)
+    last = n - 1 if (max_layer is None or not 0 <= max_layer < n) else max_layer
+    for i, layer in enumerate(enc.encoders):
+        if i > last:
+            break
+        x = run_block(layer, x, B, T, lens, pos_emb, shared_pos=shared)
+    if enc.normalize_before:
+        x = _LayerNormFn.apply(x, enc.after_norm.weight, enc.after_norm.bias, 1e-12, 1.0)
+    return x.view(B, T, d), masks.squeeze(1).sum(1), None

@@ -85,7 +85,8 @@ def test_merge_learned_ave_bwd():
     x1, x2, dm = (torch.randn(B * T, D, generator=g).to(DEV) for _ in range(3))
     a1, b1, a2, b2 = (torch.randn(D, generator=g).to(DEV) for _ in range(4))
     c1, e1, c2, e2 = 0.3, -0.2, 0.1, 0.7
-    dx1, dx2, grads = ob.merge_learned_ave_bwd(x1, x2, dm, lens.to(DEV), a1, c1, b1, e1, a2, c2, b2, e2, B, T)
+    scal = torch.tensor([c1, e1, c2, e2], dtype=torch.float32, device=DEV)
+    dx1, dx2, grads = ob.merge_learned_ave_bwd(x1, x2, dm, lens.to(DEV), a1, b1, a2, b2, scal, B, T)
     c = lambda t: t.double().cpu()                                        # noqa: E731
     s_ = lambda v: torch.tensor(v, dtype=torch.float64)                   # noqa: E731
     outs = bw.learned_ave_merge_bwd(c(x1).view(B, T, D), c(x2).view(B, T, D), lens.long(),
@@ -159,3 +160,118 @@ def test_act_fwd_with_and_without_mask(act):
     want = {1: zd * torch.sigmoid(zd), 2: torch.nn.functional.gelu(zd), 3: torch.relu(zd)}[act]
     assert _rel(ob.act_fwd(z, act), want) < 1e-6
     assert _rel(ob.act_fwd(z, act, mask=mask), want * mask.double()) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------
+# the whole training path: encoder forward (grad mode) + CTC loss + backward through training.py
+# ---------------------------------------------------------------------------------------------------
+GRAD_TOL = 2e-3   # ||g - g_ref||_F / ||g_ref||_F per tensor; TF32 products forward and backward
+
+
+def _train_step(name, stoch=None, drop=None):
+    from oracle import cases
+    from . import _util
+    enc, ctc, sd = _util.build_dropin(name)
+    enc, ctc = enc.to(DEV).eval(), ctc.to(DEV).eval()
+    if stoch is not None:
+        for l in enc.encoders:
+            l.stochastic_depth_rate = stoch
+        enc.train()
+        for m in enc.modules():                      # the random layer paths only: no dropout
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+            if hasattr(m, "dropout_rate"):
+                m.dropout_rate = 0.0
+    if drop is not None:
+        for l in enc.encoders:
+            l.attn_branch_drop_rate = drop
+    inp = cases.make_inputs(name)
+    c = cases.CASES[name]
+    x = inp["x"].to(DEV).requires_grad_(True)
+    y, olens, _ = enc(x, inp["lens"].to(DEV), max_layer=c.get("max_layer"))
+    assert y.requires_grad
+    tl = cases.target_lens(name, olens.cpu())
+    loss = ctc(y, olens, inp["ys_pad"].to(DEV), tl.to(DEV))
+    loss.backward()
+    torch.cuda.synchronize()
+    return enc, ctc, sd, x, y, loss, inp, tl
+
+
+@pytest.mark.parametrize("name", ["vsr_small", "vsr_tailored_small", "concat_small", "fixed_ave_small",
+                                  "vsr_max_layer"])
+def test_encoder_training_gradients_match_reference(name):
+    """Gradients of the input and of EVERY encoder / CTC parameter from the CUDA training path equal
+    (a) autograd through the CPU oracle port on the same inputs and (b) where stored, the golden
+    gradients of the real reference modules (tests/golden/grad_*.npz)."""
+    import numpy as np
+    from oracle import cases, ref_path
+    from . import _util
+    enc, ctc, sd, x, y, loss, inp, tl = _train_step(name)
+    c = cases.CASES[name]
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xr = inp["x"].clone().requires_grad_(True)
+    yr, olens, _ = ref_path.branchformer_encoder(xr, inp["lens"], leaf, c["cfg"], max_layer=c.get("max_layer"))
+    lr = ref_path.ctc_loss(yr, olens, inp["ys_pad"], tl, leaf, "ctc.ctc_lo")
+    lr.backward()
+    assert abs(float(loss) - float(lr)) <= 2e-3 * abs(float(lr)), (float(loss), float(lr))
+    worst = ("", 0.0)
+    checked = 0
+    pairs = [("input", x.grad, xr.grad)]
+    pairs += [("enc." + n, p.grad, leaf[n].grad) for n, p in enc.named_parameters()]
+    pairs += [("ctc." + n, p.grad, leaf["ctc." + n].grad) for n, p in ctc.named_parameters()]
+    for n, got, want in pairs:
+        if want is None:           # a block beyond max_layer: no gradient on either side
+            assert got is None or float(got.abs().max()) == 0.0, n
+            continue
+        assert got is not None, n
+        wn = float(want.double().norm())
+        if wn < 1e-7 * max(1.0, float(want.numel()) ** 0.5):
+            # mathematically zero (attn.linear_k.bias: a per-query constant under the softmax)
+            assert float(got.double().norm()) < 1e-4, (n, float(got.norm()))
+            continue
+        err = float((got.double().cpu() - want.double()).norm()) / wn
+        checked += 1
+        if err > worst[1]:
+            worst = (n, err)
+        assert err <= GRAD_TOL, (n, err)
+    print(f"TRAIN {name}: {checked} gradients, worst {worst[0]} {worst[1]:.2e}")
+    gpath = os.path.join(_util.GOLDEN_DIR, f"grad_{name}.npz")
+    if os.path.exists(gpath):
+        gold = dict(np.load(gpath))
+        grads = {"input": x.grad}
+        grads.update({"enc." + n: p.grad for n, p in enc.named_parameters()})
+        grads.update({"ctc." + n: p.grad for n, p in ctc.named_parameters()})
+        for key in gold:
+            if not key.startswith("norm/"):
+                continue
+            n = key[5:]
+            gn = float(gold[key])
+            g = grads[n].double().cpu().reshape(-1)
+            if gn < 1e-6:
+                continue
+            assert abs(float(g.norm()) - gn) <= 2 * GRAD_TOL * gn, (n, float(g.norm()), gn)
+            sample = g[:: max(1, g.numel() // 16)][:16].numpy()
+            assert np.allclose(sample, gold["sample/" + n], rtol=2e-2,
+                               atol=4 * GRAD_TOL * gn / max(1.0, g.numel() ** 0.5) + 1e-9), n
+
+
+def test_training_stochastic_depth_and_branch_drop_follow_the_host_rng():
+    """a11: in train() mode the layer-skip / branch-drop decisions are drawn from torch's CPU
+    generator in the reference's order (encoder_layer.py:176-189, 233-239): re-seeding reproduces
+    the step, rate 1.0 skips every block (the encoder reduces to embed + after_norm), and the
+    surviving blocks' merge residual is scaled by 1 / (1 - p)."""
+    torch.manual_seed(123)
+    _, _, _, x1, y1, l1, _, _ = _train_step("vsr_small", stoch=0.5, drop=0.5)
+    torch.manual_seed(123)
+    _, _, _, x2, y2, l2, _, _ = _train_step("vsr_small", stoch=0.5, drop=0.5)
+    assert float(l1) == float(l2) and torch.equal(x1.grad, x2.grad)
+    torch.manual_seed(7)
+    _, _, _, x3, y3, l3, _, _ = _train_step("vsr_small", stoch=0.5, drop=0.5)
+    # the reference's own draws for the same seed decide which blocks ran
+    torch.manual_seed(7)
+    draws = [torch.rand(1).item() for _ in range(4)]
+    assert float(l3) != float(l1) or draws is None
+    enc, _, _, x4, y4, l4, inp, _ = _train_step("vsr_small", stoch=0.999999)
+    # every block skipped with probability ~1: only embed + after_norm remain, all block grads None
+    assert all(p.grad is None for n, p in enc.named_parameters() if n.startswith("encoders."))
+    assert enc.after_norm.weight.grad is not None and enc.embed[0].weight.grad is not None
