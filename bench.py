@@ -20,7 +20,17 @@ e2e        = same metric through EncoderCTCPipeline.run_stream() with pinned HOS
 roofline   = dominant kernel group of the step (CUDA events around every op of one eager step).
 cpu_baseline / --impl reference = the CPU oracle port (oracle/ref_path.py; the reference's own
              modules cannot travel to the GPU box: espnet is not installable) on the
-             host cores with all threads, on a bounded sample of the same workload.
+             host cores with all threads, on the FULL batch of the same workload (median of the steps).
+train      = (extra object of the same line) a training step of the same workload: encoder forward
+             in grad mode (training.py: one autograd node per block) + CTC loss normalised by the
+             GLOBAL batch + backward + bucketed gradient all-reduce (parallel.GradBucketReducer,
+             launched from gradient hooks DURING backward) + no optimizer; the exposed (not
+             overlapped) all-reduce time is reported.  `--mode train` makes it the headline value.
+strong     = (extra object) strong scaling: a FIXED global batch of 64 utterances split over the N
+             ranks (the inference step of the same workload).
+gpu_eager_baseline = (N = 1, informational) the plain-PyTorch port of the reference path
+             (oracle/ref_path.py) run eagerly on the same B200, fp32 and TF32-allowed, i.e. the
+             cuBLAS / ATen-composed path BASELINE.md §3 names as the bar to beat.
 """
 from __future__ import annotations
 
@@ -222,7 +232,8 @@ class ClockSampler:
 
 # --------------------------------------------------------------------------------------------------
 def cpu_oracle_arm(steps: int, warmup: int, sample_B: int):
-    """Times the CPU oracle port on `sample_B` utterances of the workload per step."""
+    """Times the CPU oracle port on `sample_B` utterances of the workload per step; returns
+    (frames/s from the MEDIAN step, median ms per step, threads)."""
     from oracle import cases, ref_path
     w = WORKLOAD
     torch.set_num_threads(os.cpu_count() or 1)
@@ -255,32 +266,40 @@ def cpu_oracle_arm(steps: int, warmup: int, sample_B: int):
 
     for _ in range(warmup):
         step()
-    t0 = time.perf_counter()
-    frames = 0
+    times, frames = [], 0
     for _ in range(steps):
-        frames += step()[2]
-    dt = time.perf_counter() - t0
-    return frames / dt, dt / steps * 1e3, torch.get_num_threads()
+        t0 = time.perf_counter()
+        frames = step()[2]
+        times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    return frames / med, med * 1e3, torch.get_num_threads()
+
+
+CPU_STEPS, CPU_WARMUP = 5, 1   # the cpu_baseline leg of the GPU arm (full batch, median)
 
 
 def run_reference_arm(args):
+    """--impl reference: the CPU oracle port on the FULL batch of the workload (the GPU arm's
+    config), args.steps steps after args.warmup warm-ups (capped so the run stays within minutes:
+    a C2 step takes ~1 s on 16 cores), value from the median step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    sample_B = min(8, WORKLOAD["B"])
-    steps = max(1, min(args.steps, 10))
-    warm = max(1, min(args.warmup, 2))
+    sample_B = WORKLOAD["B"]
+    steps = max(1, min(args.steps, 30))
+    warm = max(1, min(args.warmup, 5))
     fps, ms, cores = cpu_oracle_arm(steps, warm, sample_B)
-    sample = (f"{sample_B} of the {WORKLOAD['B']} utterances of the {WORKLOAD['name']} batch per step "
-              f"({sample_B}x{WORKLOAD['T']} frames), {steps} steps after {warm} warm-up, fp32, "
-              f"torch {torch.__version__} with {cores} threads")
+    sample = (f"the full {WORKLOAD['name']} batch per step ({sample_B}x{WORKLOAD['T']} frames), median of "
+              f"{steps} steps after {warm} warm-up, fp32, torch {torch.__version__} with {cores} threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD["name"], "batch": sample_B, "T": WORKLOAD["T"],
-                   "layers": 12, "note": "CPU oracle port of the reference path (espnet not "
-                                         "installable: reference modules cannot run on the box)"},
+        "config": {"workload": WORKLOAD["name"], "batch_per_gpu": sample_B, "T": WORKLOAD["T"],
+                   "feat": WORKLOAD.get("feat", 256), "layers": 12, "vocab": WORKLOAD["vocab"],
+                   "target_len": WORKLOAD["Lmax"],
+                   "note": "CPU oracle port of the reference path (espnet not installable: the "
+                           "reference's own modules cannot run on the box); rank 0 only"},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -290,29 +309,33 @@ def run_reference_arm(args):
 
 
 # --------------------------------------------------------------------------------------------------
-def op_cost(name, shapes, extra):
-    """(algorithmic flops, algorithmic bytes) of one op call from its tensor shapes."""
+def op_cost(name, shapes, extra, eb=4):
+    """(algorithmic flops, algorithmic bytes) of one op call from its tensor shapes; eb = bytes per
+    element of the operand-only tensors (4 in tf32 mode, 2 in bf16 mode), the residual stream and
+    the encoder output are fp32 in every mode."""
     if name == "gemm_bias_act":
         (M, K), (N, _) = shapes[0], shapes[1]
-        return 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N)
+        return 2.0 * M * N * K, eb * (M * K + N * K + M * N)
     if name == "gemm_rowln":
         (M, K), (N, _) = shapes[0], shapes[1]
         dual = 2 if "x2" in extra else 1
-        outs = 1 + ("lnA" in extra) + ("lnB" in extra) + ("residual" in extra)
-        return 2.0 * M * N * K * dual, 4.0 * (dual * M * K + N * K + outs * M * N)
+        outs = ("lnA" in extra) + ("lnB" in extra)
+        return 2.0 * M * N * K * dual, eb * (dual * M * K + N * K + outs * M * N) + 4.0 * M * N * (
+            1 + ("residual" in extra))
     if name == "ffn_fused":
         M = shapes[0][0]
         H, D = shapes[1]
-        # algorithmic bytes: xn + residual in, up to 3 row outputs, weights once
-        return 4.0 * M * H * D, 4.0 * (M * D * 5 + 2 * H * D)
+        # algorithmic bytes: xn in, up to 2 LayerNorm outputs (operand storage); residual in and
+        # the main output (fp32); weights once
+        return 4.0 * M * H * D, eb * (M * D * 3 + 2 * H * D) + 4.0 * M * D * 2
     if name == "relpos_attn":
         M, C = shapes[0]
         T = (shapes[1][0] + 1) // 2
         d = C // 3
-        return 2.0 * 3 * T * d * M, 4.0 * (M * C + M * d)
+        return 2.0 * 3 * T * d * M, eb * (M * C + M * d)
     if name == "csgu":
         M, C = shapes[0]
-        return 2.0 * M * (C // 2) * 31, 4.0 * (M * C + M * C // 2)
+        return 2.0 * M * (C // 2) * 31, eb * (M * C + M * C // 2)
     if name == "layernorm":
         M, D = shapes[0]
         return 8.0 * M * D, 8.0 * M * D
@@ -323,27 +346,67 @@ def op_cost(name, shapes, extra):
     return 0.0, 0.0
 
 
-# ncu --set full, C2 shapes, per launch (profiles/r01b_ncu_full_c2_summary.csv): read + write bytes
-NCU_TRAFFIC = {
-    "ffn_fused[(8000, 256), (2048, 256)]": (20.68 + 0.02) * 1e6,
-    "gemm_rowln[(8000, 256), (256, 1280)]+dual": (50.53 + 0.95) * 1e6,
-    "relpos_attn[(8000, 768), (499, 256)]": (25.17 + 0.01) * 1e6,
-    "csgu[(8000, 2048), (1024,)]": (65.77 + 4.66 + 32.77 + 0.01) * 1e6,
-    "gemm_bias_act[(8000, 256), (2048, 256)]": (10.38 + 9.40) * 1e6,
-    "gemm_bias_act[(8000, 256), (768, 256)]": (9.02 + 0.00) * 1e6,
-}
+def load_ncu_traffic():
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of an `ncu --set full`
+    capture) keyed by compute mode and op group, written by tools/ncu_traffic.py from a capture of
+    THIS build (the file records the library digest it was taken on)."""
+    path = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+    if not os.path.exists(path):
+        return {}, None
+    with open(path) as f:
+        d = json.load(f)
+    return d, path
 
 
-def profile_step(pipe, batch_dev, peaks):
+def lib_digest():
+    try:
+        with open(os.path.join(ROOT, "tailored_avsr_b200", "libtavsr_sm100.so.digest")) as f:
+            return f.read().strip()[:16]
+    except OSError:
+        return None
+
+
+def measure_dense_peaks(dev):
+    """cuBLAS dense peaks measured the MEASURED_PEAKS.json way (torch.matmul 8192^3, best of 10,
+    CUDA events): bf16 and TF32 (fp32 storage with allow_tf32).  The TF32 figure is the roofline
+    denominator of the tf32 mode; the driver's file only holds the bf16 one."""
+    out = {}
+    n = 8192
+    for name, dt, tf32 in (("bf16", torch.bfloat16, False), ("tf32", torch.float32, True)):
+        a = torch.randn(n, n, device=dev, dtype=dt)
+        b = torch.randn(n, n, device=dev, dtype=dt)
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        try:
+            best = 1e9
+            for _ in range(3):
+                torch.matmul(a, b)
+            for _ in range(10):
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                torch.matmul(a, b)
+                e1.record()
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            out[name + "_tflops"] = 2.0 * n ** 3 / (best * 1e-3) / 1e12
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+        del a, b
+    return out
+
+
+def profile_step(pipe, batch_dev, peaks, dtype, live_peaks):
     """One eager step with CUDA events around every op: per-op-group time shares + roofline of the
     dominant group."""
     from tailored_avsr_b200 import ops
+    eb = 2 if dtype == "bf16" else 4
     recs = []
     torch.cuda.synchronize()
     ops.set_profiler(recs)
     try:
         with torch.no_grad():
-            # park the GPU behind a ~40 ms spin so the whole step (125 launches + their event pairs)
+            # park the GPU behind a ~40 ms spin so the whole step (~125 launches + their event pairs)
             # is enqueued before the first kernel starts: the event deltas are then kernel
             # durations, not host launch latency
             torch.cuda._sleep(80_000_000)
@@ -356,7 +419,7 @@ def profile_step(pipe, batch_dev, peaks):
     for name, shapes, extra, e0, e1 in recs:
         ms = e0.elapsed_time(e1)
         key = f"{name}{list(shapes[:2])}" + ("+dual" if "x2" in extra else "")
-        fl, by = op_cost(name, shapes, extra)
+        fl, by = op_cost(name, shapes, extra, eb)
         g = groups.setdefault(key, {"ms": 0.0, "n": 0, "flops": fl, "bytes": by, "name": name})
         g["ms"] += ms
         g["n"] += 1
@@ -370,28 +433,231 @@ def profile_step(pipe, batch_dev, peaks):
         peak = peaks["bf16_tflops"]
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": None,
-                "peak_note": "measured dense bf16 burst (MEASURED_PEAKS.json); the kernel computes in "
-                             "TF32: tools/mma_bench.cu measures 139 cycles per 128x256x8 TF32 MMA vs "
-                             "171 per 128x256x16 bf16 MMA on this part, i.e. a TF32 ceiling of 0.615x "
-                             "the bf16 one",
-                "frac_of_tf32_peak": achieved / (peak * 0.615)}
+                "peak_note": "measured dense bf16 burst (MEASURED_PEAKS.json); in the tf32 mode the "
+                             "kernel's own ceiling is the TF32 dense peak, measured live below"}
+        if live_peaks:
+            roof["peak_bf16_tflops_live"] = live_peaks.get("bf16_tflops")
+            roof["peak_tf32_tflops_live"] = live_peaks.get("tf32_tflops")
+            if dtype != "bf16" and live_peaks.get("tf32_tflops"):
+                roof["frac_of_tf32_peak"] = achieved / live_peaks["tf32_tflops"]
     else:
         achieved = top["bytes"] / avg_s / 1e9
         peak = peaks["hbm_gbs"]
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None}
-    # DRAM traffic per launch of that kernel from the committed ncu --set full capture (cold-cache
-    # replay, C2 shapes): dram__bytes_read.sum + dram__bytes_write.sum, bytes
-    traffic = NCU_TRAFFIC.get(top_key)
-    if traffic is not None:
-        roof["traffic"] = traffic
-        roof["traffic_source"] = "profiles/r01b_ncu_full_c2_summary.csv"
-        roof["algorithmic_bytes"] = top["bytes"]
+    # DRAM traffic per launch of that kernel from an ncu --set full capture of this build
+    table, path = load_ncu_traffic()
+    entry = table.get(dtype, {}).get(top_key) if table else None
+    if entry is not None:
+        roof["traffic"] = entry
+        roof["traffic_source"] = os.path.relpath(path, ROOT)
+        roof["traffic_build_digest"] = table.get("lib_digest")
+        roof["traffic_build_matches"] = table.get("lib_digest") == lib_digest()
+    roof["algorithmic_bytes"] = top["bytes"]
+    roof["algorithmic_flops"] = top["flops"]
     roof["kernel"] = top_key
     roof["avg_launch_us"] = avg_s * 1e6
     roof["share_of_step"] = top["ms"] / total if total > 0 else None
     shares = {k: round(v["ms"] / total, 4) for k, v in sorted(groups.items(), key=lambda kv: -kv[1]["ms"])}
-    return roof, shares, total
+    per_launch_us = {k: round(v["ms"] / v["n"] * 1e3, 2) for k, v in sorted(groups.items(), key=lambda kv: -kv[1]["ms"])}
+    return roof, shares, total, per_launch_us
+
+
+# --------------------------------------------------------------------------------------------------
+# extra legs of the GPU arm
+# --------------------------------------------------------------------------------------------------
+def train_leg(args, enc, ctc, rank, world, dev, dist, steps, warmup):
+    """Training step of the workload (single-stream workloads): grad-mode encoder forward + CTC loss
+    / global batch + backward + overlapped bucketed gradient all-reduce, no optimizer.  Inputs come
+    from pinned host memory every step and the loss is read back (inside the timed region).
+    Returns a dict (rank 0) or None."""
+    from tailored_avsr_b200 import engine, ops, parallel
+    w = WORKLOAD
+    if w["kind"] != "single" or w["front"] != "linear":
+        return {"unavailable": "the training path is built for the linear / None front ends "
+                               "(MyBranchformerEncoder, ConventionalEncoder): run --workload C2"}
+    prev = engine.compute_dtype()
+    engine.set_compute_dtype("tf32")      # the training path stores fp32 and multiplies in TF32
+    host, frames = make_batch(rank)
+    host = [t.pin_memory() for t in host]
+    params = list(enc.parameters()) + list(ctc.parameters())
+    for p in params:
+        p.requires_grad_(True)
+    red = parallel.GradBucketReducer(params, bucket_mb=25.0, overlap=True)
+    Bg = w["B"] * world
+    ctc.reduce = False
+
+    def step():
+        for p in params:
+            p.grad = None
+        feats, lens, ys, ylens = (t.to(dev, non_blocking=True) for t in host)
+        out, olens, _ = enc(feats, lens)
+        vec = ctc(out, olens, ys, ylens) * w["B"]          # nll_b of the local utterances
+        loss = vec.sum() / Bg                               # ctc.py:62-66 with the GLOBAL batch
+        loss.backward()
+        e_b = torch.cuda.Event(enable_timing=True)
+        e_b.record()
+        n = red.finish()
+        e_c = torch.cuda.Event(enable_timing=True)
+        e_c.record()
+        return loss, n, e_b, e_c
+
+    for _ in range(max(1, warmup)):
+        step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    l0 = ops.launch_count()
+    evs, exposed, in_bwd = [], [], []
+    for _ in range(steps):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        red.launched_in_backward = 0
+        loss, n_coll, e_b, e_c = step()
+        loss_host = float(loss)                             # D2H read of the step's result
+        e1.record()
+        evs.append((e0, e1))
+        exposed.append((e_b, e_c))
+        in_bwd.append(red.launched_in_backward)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    launches = ops.launch_count() - l0
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    exp_ms = sum(a.elapsed_time(b) for a, b in exposed)
+    t = torch.tensor([ms, exp_ms], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, exp_ms = float(t[0]), float(t[1])
+    red.remove_hooks()
+    ctc.reduce = True
+    for p in params:
+        p.grad = None
+        p.requires_grad_(False)
+    engine.set_compute_dtype(prev)
+    if rank != 0:
+        return None
+    nbytes = sum(red.bucket_bytes())
+    return {
+        "value": frames * steps * world / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+        "steps": steps, "warmup": max(1, warmup), "dtype": "tf32 (fp32 storage)",
+        "step": "grad-mode encoder forward + CTC loss / global batch + backward + bucketed gradient "
+                "all-reduce (no optimizer); host inputs copied in and the loss read back every step",
+        "global_batch": Bg, "scaling": "weak", "loss": loss_host,
+        "kernel_launches_per_step": launches // steps,
+        "allreduce": {"bytes_per_step": nbytes if world > 1 else 0, "buckets": len(red.buckets),
+                      "bucket_mb": 25.0, "collectives_per_step": n_coll,
+                      "launched_during_backward": in_bwd[-1] if in_bwd else 0,
+                      "exposed_ms_per_step": exp_ms / steps,
+                      "note": "exposed = CUDA-event time from the end of backward() to the last "
+                              "bucket's sum being back in .grad (waits + unpack copies), max over ranks"},
+    }
+
+
+def strong_leg(args, enc, fusion, ctc, rank, world, dev, dist, steps, warmup, global_batch=64):
+    """Strong scaling: a FIXED global batch split over the ranks (utterance sharding), inference
+    step of the workload through CUDA-graph replay.  Returns a dict (rank 0) or None."""
+    from tailored_avsr_b200.pipeline import AVEncoderCTCPipeline, EncoderCTCPipeline
+    global WORKLOAD
+    if global_batch % world != 0:
+        return {"unavailable": f"global batch {global_batch} does not split over {world} ranks"}
+    saved = WORKLOAD
+    WORKLOAD = dict(saved, B=global_batch // world)
+    try:
+        host, frames = make_batch(rank)
+        batch_dev = [t.to(dev) for t in host]
+        pipe = (EncoderCTCPipeline(enc, ctc) if fusion is None
+                else AVEncoderCTCPipeline(enc, fusion, ctc))
+        for _ in range(max(3, warmup)):
+            pipe.run_device(*batch_dev)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+        evs = []
+        for _ in range(steps):
+            flush.zero_()
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            pipe.replay_static()
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms, float(frames)], device=dev, dtype=torch.float64)
+        if dist is not None:
+            tm = t[:1].clone()
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            tf = t[1:].clone()
+            dist.all_reduce(tf, op=dist.ReduceOp.SUM)
+            ms, total = float(tm[0]), float(tf[0])
+        else:
+            total = float(frames)
+        del flush
+    finally:
+        WORKLOAD = saved
+    if rank != 0:
+        return None
+    return {"value": total * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+            "global_batch": global_batch, "batch_per_gpu": global_batch // world, "scaling": "strong",
+            "steps": steps, "note": "fixed global batch split by utterance over the ranks; below ~32 "
+                                    "utterances per GPU a step sits on the launch-latency floor"}
+
+
+def gpu_eager_baseline(dev, steps=5):
+    """The plain-PyTorch port of the reference path (oracle/ref_path.py: F.linear / matmul /
+    F.conv1d / F.layer_norm, i.e. cuBLAS + ATen kernels) run eagerly on the same GPU: encoder
+    forward + torch CTC loss + argmax.  Informational (BASELINE.md §3's comparison bar)."""
+    import torch.nn.functional as F
+    from oracle import ref_path
+    w = WORKLOAD
+    if w["kind"] != "single":
+        return {"unavailable": "single-stream workloads only"}
+    cfg = enc_cfg()
+    _, _, _, sd = build_modules()
+    sd = {k: v.to(dev) for k, v in sd.items()}
+    feats, lens, ys, ylens = [t.to(dev) for t in make_batch(0)[0]]
+    out = {}
+    prev = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    try:
+        for name, tf32 in (("fp32", False), ("tf32_allowed", True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+
+            def step():
+                with torch.no_grad():
+                    y, olens, _ = ref_path.branchformer_encoder(feats, lens, sd, cfg)
+                    lp = F.log_softmax(F.linear(y, sd["ctc.ctc_lo.weight"], sd["ctc.ctc_lo.bias"]), -1)
+                    loss = F.ctc_loss(lp.transpose(0, 1), ys, olens, ylens, reduction="sum",
+                                      zero_infinity=True) / y.shape[0]
+                    return loss, lp.argmax(-1), int(w["B"] * w["T"])
+
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            times = []
+            for _ in range(steps):
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                _, _, frames = step()
+                e1.record()
+                torch.cuda.synchronize()
+                times.append(e0.elapsed_time(e1))
+            med = statistics.median(times)
+            out[name] = {"value": frames / (med * 1e-3), "unit": UNIT, "ms_per_step": med}
+    except Exception as e:  # noqa: BLE001
+        out["error"] = f"{type(e).__name__}: {e}"[:200]
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
+    out["what"] = ("oracle/ref_path.py (plain torch ops: cuBLAS GEMMs, ATen elementwise / softmax / "
+                   "LayerNorm, cuDNN depthwise conv) eager on the same GPU, encoder + torch CTC loss + "
+                   "argmax, median of %d steps" % steps)
+    return out
 
 
 def run_gpu_arm(args):
@@ -505,12 +771,23 @@ def run_gpu_arm(args):
     dev_ms, e2e_ms, e2e_call_ms = float(t[0]), float(t[1]), float(t[2])
     total_frames = frames_per_step * args.steps * world
 
+    # ---- extra legs: strong scaling and the training step (every rank takes part) ----
+    strong = train = None
+    if not args.no_extra:
+        strong = strong_leg(args, enc, fusion, ctc, rank, world, dev, dist, steps=min(args.steps, 10),
+                            warmup=3)
+        train = train_leg(args, enc, ctc, rank, world, dev, dist, steps=args.train_steps, warmup=2)
+
     line = None
     if rank == 0:
-        roof, shares, prof_total_ms = profile_step(pipe, batch_dev, peaks)
+        live_peaks = measure_dense_peaks(dev) if not args.no_extra else None
+        roof, shares, prof_total_ms, per_launch_us = profile_step(pipe, batch_dev, peaks, args.dtype,
+                                                                  live_peaks)
         roof["peak_source"] = peak_src
-        sample_B = min(8, w["B"])
-        fps_cpu, ms_cpu, cores = cpu_oracle_arm(2, 1, sample_B) if world == 1 and not args.no_cpu else (None, None, None)
+        sample_B = w["B"]
+        fps_cpu, ms_cpu, cores = (cpu_oracle_arm(CPU_STEPS, CPU_WARMUP, sample_B)
+                                  if world == 1 and not args.no_cpu else (None, None, None))
+        eager = gpu_eager_baseline(dev) if world == 1 and not args.no_extra else None
         h2d = sum(t_.numel() * t_.element_size() for t_ in host)
         d2h = 4 + w["B"] * w["T"] * 8 + w["B"] * 4
         fpf = flops_per_frame()
@@ -542,7 +819,11 @@ def run_gpu_arm(args):
             "gpu_launches_per_step": launches_per_step,
             "roofline": roof,
             "kernel_time_shares": shares,
+            "kernel_us_per_launch": per_launch_us,
             "eager_step_kernel_ms": prof_total_ms,
+            "strong": strong,
+            "train": train,
+            "gpu_eager_baseline": eager,
             "model_tflops": value * fpf / 1e12,
             "model_tflops_per_gpu": value * fpf / 1e12 / world,
             "model_frac_of_bf16_sustained": value * fpf / 1e12 / world / peaks["bf16_tflops_sustained"],
@@ -551,10 +832,22 @@ def run_gpu_arm(args):
         if fps_cpu is not None:
             line["cpu_baseline"] = {
                 "value": fps_cpu, "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": f"{sample_B} of the {w['B']} utterances per step, 2 steps after 1 warm-up "
-                          f"({ms_cpu:.0f} ms/step), fp32 oracle port, torch {torch.__version__}"}
+                "sample": f"the full {w['name']} batch per step ({sample_B}x{w['T']} frames), median of "
+                          f"{CPU_STEPS} steps after {CPU_WARMUP} warm-up ({ms_cpu:.0f} ms/step), fp32 "
+                          f"oracle port, torch {torch.__version__}"}
         else:
             line["cpu_baseline"] = None
+        if args.mode == "train" and train and "value" in train:
+            # the training step as the headline: same metric (valid frames/s), training semantics
+            line["inference"] = {k: line[k] for k in ("value", "ms_per_step", "e2e", "gpu_launches")}
+            line.update(value=train["value"], ms_per_step=train["ms_per_step"], dtype="tf32",
+                        steps=train["steps"], warmup=train["warmup"],
+                        gpu_launches=train["kernel_launches_per_step"] * train["steps"])
+            line["e2e"] = {"value": train["value"], "unit": UNIT, "h2d_bytes_per_step": h2d,
+                           "d2h_bytes_per_step": 4,
+                           "api": "encoder(...) / ctc(...) / loss.backward() / GradBucketReducer.finish()"}
+            line["config"]["step"] = train["step"]
+            line["config"]["mode"] = "train"
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
@@ -574,6 +867,11 @@ def main():
                     help="SURVEY.md §8d workload (default: the bench line, C2)")
     ap.add_argument("--batch", type=int, default=0, help="utterances per GPU (sweep)")
     ap.add_argument("--T", type=int, default=0, help="encoder frames per utterance (sweep)")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the strong-scaling / training / eager-baseline legs and the live peaks")
+    ap.add_argument("--train-steps", type=int, default=5, help="steps of the training leg")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="train: the training step becomes the headline value of the line")
     ap.add_argument("--dtype", default="tf32", choices=["tf32", "tf32x3", "bf16"],
                     help="compute mode (tailored_avsr_b200.engine): operand storage of the tensor-core products")
     args = ap.parse_args()

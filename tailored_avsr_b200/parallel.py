@@ -3,8 +3,9 @@
 Every operation of the encoder + CTC path is per-utterance, so N GPUs simply take disjoint subsets
 of the batch — there is no data-path collective.  The only cross-utterance term is the loss
 normalisation `sum_b nll_b / B` (src/ctc/ctc.py:62-66): each rank divides by the GLOBAL batch size
-and one scalar all-reduce (sum) recovers the reference value.  The training-mode gradient
-all-reduce named in BASELINE.json needs the encoder backward kernels and is not built yet.
+and one scalar all-reduce (sum) recovers the reference value.  The only collective of the path is
+the training-mode gradient all-reduce (BASELINE.json north_star): `GradBucketReducer`, bucketed and
+launched from gradient hooks WHILE the backward of the earlier blocks still runs.
 
 One process per GPU, launched by torch.distributed.run; NCCL on GPUs, gloo in the CPU tests.
 """
@@ -63,19 +64,27 @@ def max_over_ranks(value: float, device: torch.device,
 
 
 class GradBucketReducer:
-    """Bucketed gradient all-reduce (the only collective of the path, training
-    mode).  Gradients of `params` are packed into flat fp32 buckets of ~`bucket_mb` MB in REVERSE
-    parameter order (the order backward produces them), each bucket is all-reduced (sum)
-    asynchronously as soon as it is packed, and the results are copied back after the last launch,
-    so the NCCL transfers of early buckets overlap the packing of later ones.  Ranks hold disjoint
-    utterance shards and normalise their loss by the GLOBAL batch (`global_ctc_loss`), so the SUM
-    of the per-rank gradients is the full-batch gradient: no division by the world size.
+    """Bucketed gradient all-reduce overlapped with the backward pass (the only
+    collective of the path, training mode).
 
-    Today the trainable part of the B200 path is the CTC head (`CTC.forward` has its CUDA backward;
-    the encoder backward kernels are not built yet), so this runs on `ctc.parameters()`; it takes
-    any parameter list.  gloo on CPU (tests) and NCCL on GPUs use the same code."""
+    The parameters are packed into flat fp32 buckets of ~`bucket_mb` MB in REVERSE registration
+    order - the order the backward produces gradients: the CTC head first, then after_norm, block
+    11, block 10, ... (training.py makes each block one autograd node, so a block's gradients all
+    arrive when its node returns).  With `overlap=True` every parameter gets a
+    post-accumulate-grad hook; when the last gradient of a bucket has arrived the bucket is packed
+    and its `all_reduce(sum)` is launched asynchronously on the process group's stream, so the NCCL
+    transfer of block k's bucket runs under the backward kernels of blocks < k.  Buckets are always
+    launched IN ORDER (bucket i+1 never before bucket i): ranks may produce gradients in different
+    patterns (stochastic depth skips different layers on different ranks), but the sequence of
+    collectives must be identical everywhere.  `finish()` launches what is left (parameters without
+    a gradient contribute zeros), waits, and copies the sums back into `.grad`.
 
-    def __init__(self, params, bucket_mb: float = 25.0, group: Optional[dist.ProcessGroup] = None):
+    Ranks hold disjoint utterance shards and normalise their loss by the GLOBAL batch
+    (`global_ctc_loss`), so the SUM of the per-rank gradients is the full-batch gradient: no
+    division by the world size.  gloo on CPU (tests) and NCCL on GPUs use the same code."""
+
+    def __init__(self, params, bucket_mb: float = 25.0, group: Optional[dist.ProcessGroup] = None,
+                 overlap: bool = False):
         self.params = [p for p in params if p.requires_grad]
         self.group = group
         cap = max(1, int(bucket_mb * (1 << 20) // 4))
@@ -90,30 +99,65 @@ class GradBucketReducer:
         if cur:
             self.buckets.append(cur)
         self._flat: List[Optional[torch.Tensor]] = [None] * len(self.buckets)
+        self._bucket_of = {id(p): i for i, b in enumerate(self.buckets) for p in b}
+        self._works: List[Optional[object]] = [None] * len(self.buckets)
+        self._pending = [len(b) for b in self.buckets]
+        self._seen = set()
+        self._next = 0
+        self.launched_in_backward = 0
+        self._hooks = []
+        self.overlap = overlap
+        if overlap:
+            for p in self.params:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
 
-    def reduce(self) -> int:
-        """All-reduce (sum) every `.grad` in place; parameters without a gradient contribute zeros
-        (every rank must launch the same collectives).  Returns the number of collectives issued."""
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+    # ------------------------------------------------------------------------------------------
+    def _active(self) -> bool:
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def bucket_bytes(self) -> List[int]:
+        return [4 * sum(p.numel() for p in b) for b in self.buckets]
+
+    def _launch(self, i: int) -> None:
+        bucket = self.buckets[i]
+        n = sum(p.numel() for p in bucket)
+        ref = bucket[0]
+        flat = self._flat[i]
+        if flat is None or flat.numel() != n or flat.device != ref.device:
+            flat = self._flat[i] = torch.empty(n, dtype=torch.float32, device=ref.device)
+        off = 0
+        for p in bucket:
+            view = flat[off:off + p.numel()]
+            if p.grad is None:
+                view.zero_()
+            else:
+                view.copy_(p.grad.reshape(-1))
+            off += p.numel()
+        self._works[i] = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def _on_grad(self, p: torch.nn.Parameter) -> None:
+        """Gradient hook: count the bucket down, launch every bucket that has become launchable."""
+        if not self._active() or id(p) in self._seen:
+            return
+        self._seen.add(id(p))
+        i = self._bucket_of[id(p)]
+        self._pending[i] -= 1
+        while self._next < len(self.buckets) and self._pending[self._next] == 0:
+            self._launch(self._next)
+            self._next += 1
+            self.launched_in_backward += 1
+
+    def finish(self) -> int:
+        """Launch the buckets that did not complete during backward, wait for all of them (the
+        current stream waits; the host does not block on NCCL) and write the sums into `.grad`.
+        Returns the number of collectives of this step."""
+        if not self._active():
             return 0
-        works = []
+        while self._next < len(self.buckets):
+            self._launch(self._next)
+            self._next += 1
         for i, bucket in enumerate(self.buckets):
-            n = sum(p.numel() for p in bucket)
-            ref = bucket[0]
-            flat = self._flat[i]
-            if flat is None or flat.numel() != n or flat.device != ref.device:
-                flat = self._flat[i] = torch.empty(n, dtype=torch.float32, device=ref.device)
-            off = 0
-            for p in bucket:
-                view = flat[off:off + p.numel()]
-                if p.grad is None:
-                    view.zero_()
-                else:
-                    view.copy_(p.grad.reshape(-1))
-                off += p.numel()
-            works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
-        for i, (bucket, work) in enumerate(zip(self.buckets, works)):
-            work.wait()
+            self._works[i].wait()
             flat = self._flat[i]
             off = 0
             for p in bucket:
@@ -123,4 +167,19 @@ class GradBucketReducer:
                 else:
                     p.grad.copy_(g)
                 off += p.numel()
-        return len(works)
+        n = len(self.buckets)
+        self._works = [None] * n
+        self._pending = [len(b) for b in self.buckets]
+        self._seen = set()
+        self._next = 0
+        return n
+
+    def reduce(self) -> int:
+        """Non-overlapped form: call after backward() has returned."""
+        self.launched_in_backward = 0
+        return self.finish()
+
+    def remove_hooks(self) -> None:
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []

@@ -118,3 +118,71 @@ def test_grad_bucket_reducer_buckets_in_reverse_parameter_order():
     r = parallel.GradBucketReducer(ps + [frozen], bucket_mb=300 * 4 / (1 << 20))
     assert [[p.numel() for p in b] for b in r.buckets] == [[200, 5], [300], [10]]
     assert r.reduce() == 0          # no process group: nothing to do, gradients untouched
+
+
+def _overlap_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        # a 4-"block" chain; rank 1 skips block 2 (stochastic depth on one rank only), so its
+        # gradient pattern differs from rank 0's: the collectives must still pair up in order
+        blocks = [torch.nn.Linear(8, 8) for _ in range(4)]
+        params = [p for b in blocks for p in b.parameters()]
+        red = parallel.GradBucketReducer(params, bucket_mb=72 * 4 / (1 << 20), overlap=True)
+        assert len(red.buckets) == 4
+        x = synth.randn((5, 8), 3 + rank)
+
+        def fwd(skip):
+            h = x
+            for i, b in enumerate(blocks):
+                if i in skip:
+                    continue
+                h = torch.tanh(b(h))
+            return h.sum()
+
+        for step in range(2):                       # twice: the per-step state must reset
+            for p in params:
+                p.grad = None
+            fwd({2} if rank == 1 else set()).backward()
+            launched = red.launched_in_backward
+            n = red.finish()
+            got = [p.grad.clone() for p in params]
+            # reference: both ranks' gradients computed locally and summed
+            want = [torch.zeros_like(p) for p in params]
+            for r in range(world):
+                xr = synth.randn((5, 8), 3 + r)
+                h = xr
+                for i, b in enumerate(blocks):
+                    if r == 1 and i == 2:
+                        continue
+                    h = torch.tanh(b(h))
+                # autograd.grad: no .grad accumulation, so the reducer's hooks stay silent
+                gs = torch.autograd.grad(h.sum(), params, allow_unused=True)
+                for w_, gr in zip(want, gs):
+                    if gr is not None:
+                        w_ += gr
+            ok = all(torch.allclose(g, w_, rtol=1e-5, atol=1e-6) for g, w_ in zip(got, want))
+            ret[f"ok_{rank}_{step}"] = bool(ok)
+            ret[f"n_{rank}_{step}"] = n
+            ret[f"launched_{rank}_{step}"] = launched
+            red.launched_in_backward = 0
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_overlapped_reducer_launches_in_order_from_gradient_hooks():
+    """overlap=True: buckets are launched from post-accumulate-grad hooks during backward, always in
+    bucket order; a rank that skipped a block (no gradient for it) launches that bucket - and the
+    ones behind it - from finish(), and the sums still equal the sum of the per-rank gradients."""
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_overlap_worker, args=(world, port, ret), nprocs=world, join=True)
+        r = dict(ret)
+        assert all(r[f"ok_{k}_{s}"] for k in range(world) for s in range(2)), r
+        assert all(r[f"n_{k}_{s}"] == 4 for k in range(world) for s in range(2)), r
+        # rank 0 saw every gradient during backward; rank 1 stalls at the skipped block's bucket
+        assert r["launched_0_0"] == 4 and r["launched_1_0"] == 1, r
