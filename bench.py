@@ -509,13 +509,16 @@ def train_leg(args, enc, ctc, rank, world, dev, dist, steps, warmup):
         dist.barrier()
     l0 = ops.launch_count()
     evs, exposed, in_bwd = [], [], []
+    host_enqueue_s = 0.0
     for _ in range(steps):
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
         red.launched_in_backward = 0
+        th = time.perf_counter()
         loss, n_coll, e_b, e_c = step()
-        loss_host = float(loss)                             # D2H read of the step's result
+        host_enqueue_s += time.perf_counter() - th
+        loss_host = float(loss.detach())                    # D2H read of the step's result
         e1.record()
         evs.append((e0, e1))
         exposed.append((e_b, e_c))
@@ -546,6 +549,7 @@ def train_leg(args, enc, ctc, rank, world, dev, dist, steps, warmup):
                 "all-reduce (no optimizer); host inputs copied in and the loss read back every step",
         "global_batch": Bg, "scaling": "weak", "loss": loss_host,
         "kernel_launches_per_step": launches // steps,
+        "host_enqueue_ms_per_step": host_enqueue_s / steps * 1e3,
         "allreduce": {"bytes_per_step": nbytes if world > 1 else 0, "buckets": len(red.buckets),
                       "bucket_mb": 25.0, "collectives_per_step": n_coll,
                       "launched_during_backward": in_bwd[-1] if in_bwd else 0,
@@ -629,7 +633,9 @@ def gpu_eager_baseline(dev, steps=5):
             torch.backends.cudnn.allow_tf32 = tf32
 
             def step():
-                with torch.no_grad():
+                # torch.device(dev): the port's factory calls (arange, zeros, the positional table)
+                # land on the GPU too
+                with torch.no_grad(), torch.device(dev):
                     y, olens, _ = ref_path.branchformer_encoder(feats, lens, sd, cfg)
                     lp = F.log_softmax(F.linear(y, sd["ctc.ctc_lo.weight"], sd["ctc.ctc_lo.bias"]), -1)
                     loss = F.ctc_loss(lp.transpose(0, 1), ys, olens, ylens, reduction="sum",

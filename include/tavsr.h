@@ -256,6 +256,15 @@ int tavsr_merge_learned_ave_weights(const float* dots1, const float* dots2, cons
                                     float pool_b1, float pool_b2, float wproj_b1, float wproj_b2,
                                     float inv_sqrt_size, float* w1, float* w2, int B, int T,
                                     void* stream);
+/* The two steps above in ONE launch for the folded two-branch block (a1 = attention context, 256
+ * wide; a2 = gated cgMLP hidden, 1024 wide; fp32 or bf16 by `dtype`): a cluster of 4 CTAs per
+ * utterance computes the row dots, the masked softmax pooling over time and the 2-way softmax, the
+ * partials crossing the cluster over distributed shared memory.  T <= 2048. */
+int tavsr_merge_scores(const void* a1, long long ld1, int K1, const void* a2, long long ld2, int K2,
+                       const float* va1, const float* vb1, const float* va2, const float* vb2,
+                       const int32_t* lens, float pool_b1, float pool_b2, float wproj_b1,
+                       float wproj_b2, float inv_sqrt_size, float* w1, float* w2, int B, int T,
+                       int dtype, void* stream);
 /* Training form: the four biases (pool_b1, pool_b2, wproj_b1, wproj_b2) are read from the DEVICE
  * array `scal` instead of being passed by value (no host read-back of parameters per step). */
 int tavsr_merge_learned_ave_weights_dev(const float* dots1, const float* dots2, const int32_t* lens,

@@ -138,6 +138,10 @@ SIGNATURES = {
                                             c_void_p, c_void_p, c_void_p, c_longlong,
                                             c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_int,
                                             c_int, c_int, c_void_p]),
+    "tavsr_merge_scores": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_longlong, c_int, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float,
+                                   c_float, c_float, c_void_p, c_void_p, c_int, c_int, c_int,
+                                   c_void_p]),
     "tavsr_merge_learned_ave_weights_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                                     c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "tavsr_ctc_greedy": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,

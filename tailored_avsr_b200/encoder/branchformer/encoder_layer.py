@@ -171,8 +171,13 @@ class MyBranchformerEncoderLayer(torch.nn.Module):
                 ctx = engine.attention_ctx(xa, self.attn, pos_proj, lens, B, T, self._packed, "qkv")
             if learned:
                 sc = fv["sc"]
-                d1, d2 = ops.row_dots(ctx, fv["va1"], fv["vb1"], u, fv["va2"], fv["vb2"])
-                w1, w2 = ops.merge_weights(d1, d2, lens, sc[0], sc[1], sc[2], sc[3], d, B, T)
+                if engine.FUSE_SCORES and ctx.shape[1] == 256 and u.shape[1] == 1024 and T <= 2048:
+                    # row dots + pooling softmax + 2-way softmax in one launch
+                    w1, w2 = ops.merge_scores(ctx, u, fv["va1"], fv["vb1"], fv["va2"], fv["vb2"], lens,
+                                              sc[0], sc[1], sc[2], sc[3], d, B, T)
+                else:
+                    d1, d2 = ops.row_dots(ctx, fv["va1"], fv["vb1"], u, fv["va2"], fv["vb2"])
+                    w1, w2 = ops.merge_weights(d1, d2, lens, sc[0], sc[1], sc[2], sc[3], d, B, T)
                 self.weight_global = w1.view(B, 1, 1)
                 self.weight_local = w2.view(B, 1, 1)
             else:

@@ -46,6 +46,10 @@ FFN_FUSED = os.environ.get("TAVSR_FFN_FUSED", "1") != "0"
 # blocks): the merge GEMM then reads the attention context and the gated activations directly
 FOLD_MERGE = os.environ.get("TAVSR_FOLD_MERGE", "1") != "0"
 
+# learned_ave merge weights by the fused cluster kernel (row dots + pooling + softmax, one launch)
+# instead of row_dots + merge_weights (TAVSR_FUSE_SCORES=0: the two-kernel sequence)
+FUSE_SCORES = os.environ.get("TAVSR_FUSE_SCORES", "1") != "0"
+
 # run the attention and cgMLP branches of a two-branch block on two streams.  MEASURED (C2, graph
 # replay): 3.786 vs 3.789 ms per step - every kernel of the block already fills the GPU (persistent
 # GEMMs, 1 CTA/SM attention), so the branches serialise anyway; opt-in.

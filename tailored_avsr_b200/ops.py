@@ -18,7 +18,7 @@ from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, ACT_SWISH, DT_BF16, DT_LNA_BF16
 
 __all__ = [
     "ACT_NONE", "ACT_SWISH", "ACT_GELU", "ACT_RELU",
-    "gemm_bias_act", "conv2d_sub_im2col", "merge_weights2", "scale_add_rows", "cast_bf16", "split_tf32", "gemm_rowln", "ffn_fused", "layernorm", "relpos_attn", "csgu", "merge_weights",
+    "gemm_bias_act", "conv2d_sub_im2col", "merge_weights2", "scale_add_rows", "cast_bf16", "split_tf32", "gemm_rowln", "ffn_fused", "layernorm", "relpos_attn", "csgu", "merge_weights", "merge_scores", "merge_weights_dev",
     "ctc_head", "ctc_head_bwd", "vocab_residual", "row_dots", "ctc_loss", "ctc_greedy", "ctc_prefix_score", "launch_count",
 ]
 
@@ -400,6 +400,25 @@ def merge_weights(dots1: torch.Tensor, dots2: torch.Tensor, lens: Optional[torch
         dots1.data_ptr(), dots2.data_ptr(), _p(lens), pool_b1, pool_b2, wproj_b1, wproj_b2,
         1.0 / math.sqrt(size), w1.data_ptr(), w2.data_ptr(), B, T, _stream()),
         "tavsr_merge_learned_ave_weights")
+    return w1, w2
+
+
+@_profiled
+def merge_scores(a1: torch.Tensor, a2: torch.Tensor, va1: torch.Tensor, vb1: torch.Tensor,
+                 va2: torch.Tensor, vb2: torch.Tensor, lens: Optional[torch.Tensor], pool_b1: float,
+                 pool_b2: float, wproj_b1: float, wproj_b2: float, size: int, B: int, T: int):
+    """learned_ave merge weights straight from the branch activations in ONE launch
+    (tavsr_merge_scores: row dots + masked softmax pooling + 2-way softmax, a cluster of 4 CTAs per
+    utterance).  a1 (B*T, 256), a2 (B*T, 1024), fp32 or bf16 (both the same)."""
+    _chk2d(a1, "a1", None)
+    _chk2d(a2, "a2", a1.dtype)
+    w1 = torch.empty((B,), device=a1.device, dtype=torch.float32)
+    w2 = torch.empty((B,), device=a1.device, dtype=torch.float32)
+    check(_lib.load().tavsr_merge_scores(
+        a1.data_ptr(), a1.stride(0), a1.shape[1], a2.data_ptr(), a2.stride(0), a2.shape[1],
+        va1.data_ptr(), vb1.data_ptr(), va2.data_ptr(), vb2.data_ptr(), _p(lens), pool_b1, pool_b2,
+        wproj_b1, wproj_b2, 1.0 / math.sqrt(size), w1.data_ptr(), w2.data_ptr(), B, T,
+        DT_BF16 if _is_bf16(a1) else DT_TF32, _stream()), "tavsr_merge_scores")
     return w1, w2
 
 

@@ -296,3 +296,33 @@ def test_tf32x3_split_product_is_fp32_class(M, N, K):
         main = torch.empty(M, 256, device=DEV)
         ops.gemm_rowln(x3, w3, b, residual=res, alpha=0.5, out_main=main)
         assert rel_fro(main, res.double() + 0.5 * ref) < 2e-5
+
+
+@pytest.mark.parametrize("dt", [torch.float32, BF])
+@pytest.mark.parametrize("B,T,lens", [(6, 90, [90, 1, 45, 0, 89, 33]), (3, 250, [250, 130, 61]),
+                                      (2, 1500, [1500, 777]), (1, 5, [5])])
+def test_merge_scores_cluster_kernel_equals_row_dots_plus_merge_weights(dt, B, T, lens):
+    """tavsr_merge_scores (row dots + masked softmax pooling + 2-way softmax, a 4-CTA cluster per
+    utterance with a DSMEM combine) against the two-kernel sequence and the fp64 formula."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(B * T)
+    a1 = (torch.randn(B * T, 256, generator=g) * 0.5).to(DEV).to(dt)
+    a2 = (torch.randn(B * T, 1024, generator=g) * 0.5).to(DEV).to(dt)
+    v = [(torch.randn(k, generator=g) * s).to(DEV) for k, s in ((256, 0.3), (256, 0.1), (1024, 0.2), (1024, 0.05))]
+    lens_t = torch.tensor(lens, dtype=torch.int32).to(DEV)
+    pb1, pb2, wb1, wb2 = 0.3, -0.2, 0.1, 0.7
+    w1, w2 = ops.merge_scores(a1, a2, v[0], v[1], v[2], v[3], lens_t, pb1, pb2, wb1, wb2, 256, B, T)
+    d1, d2 = ops.row_dots(a1, v[0], v[1], a2, v[2], v[3])
+    r1, r2 = ops.merge_weights(d1, d2, lens_t, pb1, pb2, wb1, wb2, 256, B, T)
+    assert float((w1 - r1).abs().max()) < 2e-5 and float((w2 - r2).abs().max()) < 2e-5
+    om = []
+    for a, va, vb, pb, wb in ((a1, v[0], v[1], pb1, wb1), (a2, v[2], v[3], pb2, wb2)):
+        ad = a.double().cpu().view(B, T, -1)
+        sc = (ad @ va.double().cpu() + pb) / 16.0
+        mask = torch.arange(T)[None, :] >= torch.tensor(lens)[:, None]
+        sc = sc.masked_fill(mask, torch.finfo(torch.float32).min)
+        s = torch.softmax(sc, dim=-1).masked_fill(mask, 0.0)
+        om.append((s * (ad @ vb.double().cpu())).sum(-1) + wb)
+    ref = torch.softmax(torch.stack(om, dim=-1), dim=-1)
+    assert float((w1.double().cpu() - ref[:, 0]).abs().max()) < 2e-5
+    assert float((w2.double().cpu() - ref[:, 1]).abs().max()) < 2e-5
