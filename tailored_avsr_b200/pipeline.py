@@ -168,11 +168,32 @@ class EncoderCTCPipeline:
                 ev.record(copy)
             return tens, ev
 
+        # results leave the device asynchronously too: right after the replay of batch n its loss /
+        # tokens are copied (stream-ordered, so before batch n+1 overwrites the graph's static
+        # outputs) into one of two pinned host sets, and batch n is only waited for AFTER batch n+1
+        # has been enqueued - the GPU never idles on the host reading a result back
+        pinned = self.__dict__.setdefault("_result_pins", {})
+
+        def read_back(res, slot):
+            keys = ["loss"] + (["tokens", "ntok"] if self.greedy else [])
+            sig = tuple((k, tuple(res[k].shape), res[k].dtype) for k in keys) + (slot,)
+            bufs = pinned.get(sig)
+            if bufs is None:
+                bufs = pinned[sig] = {k: torch.empty(res[k].shape, dtype=res[k].dtype).pin_memory()
+                                      for k in keys}
+            for k in keys:
+                bufs[k].copy_(res[k], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(comp)
+            return bufs, ev, res["olens"]
+
         it = iter(batches)
         try:
             nxt = stage(next(it))
         except StopIteration:
             return
+        pending = None
+        n = 0
         while nxt is not None:
             cur = nxt
             try:
@@ -181,11 +202,17 @@ class EncoderCTCPipeline:
                 nxt = None
             comp.wait_event(cur[1])
             res = self.run_device(*cur[0])
-            out = {"olens": res["olens"], "loss": res["loss"].to("cpu")}
-            if self.greedy:
-                out["tokens"] = res["tokens"].to("cpu")
-                out["ntok"] = res["ntok"].to("cpu")
-            yield out
+            done = read_back(res, n & 1)
+            n += 1
+            if pending is not None:
+                bufs, ev, olens = pending
+                ev.synchronize()
+                yield dict({k: v.clone() for k, v in bufs.items()}, olens=olens)
+            pending = done
+        if pending is not None:
+            bufs, ev, olens = pending
+            ev.synchronize()
+            yield dict({k: v.clone() for k, v in bufs.items()}, olens=olens)
 
     @torch.no_grad()
     def run(self, *tensors) -> dict:
