@@ -310,7 +310,9 @@ int tavsr_conv2d_sub_im2col(const float* x, int B, int Tin, int F, const float* 
 
 /* ------------------------------------------------------------------------------------------------
  * CTC head: logits = hs . W^T + b in fp32 FMA (argmax must be bit-stable), then log-softmax /
- * softmax / argmax over V <= 64 (ctc.py:143,160-188).  Any of logits / logp / prob / amax may be NULL.
+ * softmax / argmax over V <= 256 (ctc.py:143,160-188; V <= 64 - the char vocabularies - on the
+ * warp-per-frame kernel with W^T in shared memory, 64 < V <= 256 - the 256-token SentencePiece
+ * alternative - on a thread-per-token kernel).  Any of logits / logp / prob / amax may be NULL.
  * ---------------------------------------------------------------------------------------------- */
 int tavsr_ctc_head(const float* hs, long long ldh, const float* w /* [V,D] */, const float* b,
                    float* logits, float* logp, float* prob, int64_t* amax, int M, int D, int V,
@@ -323,7 +325,9 @@ int tavsr_ctc_head(const float* hs, long long ldh, const float* w /* [V,D] */, c
  *   - InterCTCResidualModule      x + proj_2(softmax(proj_1(x)))
  *     (src/ctc/interctc_residual_module.py:11-16).
  * When xn != NULL it also receives LayerNorm(out; ln_g, ln_b, eps) — the next block's
- * norm_ff_macaron, so the conditioned stream needs no extra pass.  D in {128,256,512}, V <= 64.
+ * norm_ff_macaron, so the conditioned stream needs no extra pass.  D in {128,256,512}, V <= 256;
+ * for V > 64 `w` must be the TRANSPOSED matrix W^T (V,D) (rows streamed from L2 instead of staged
+ * in shared memory).
  * ---------------------------------------------------------------------------------------------- */
 int tavsr_vocab_residual(const float* x, long long ldx, const float* p, const float* w /* [D,V] */,
                          const float* b, float* out, long long ldo, const float* ln_g,
@@ -332,7 +336,7 @@ int tavsr_vocab_residual(const float* x, long long ldx, const float* p, const fl
 
 /* ------------------------------------------------------------------------------------------------
  * CTC loss, log domain, blank = 0 (torch.nn.CTCLoss(reduction="none", zero_infinity) at
- * ctc.py:41,60-61): one warp per utterance.
+ * ctc.py:41,60-61): one warp per utterance, V <= 256.
  *   logp    [B, T, V]      log-softmax (batch-major; the reference's (T,B,V) transpose is a view)
  *   targets [B, Lmax]      int64, padded (ys_pad); tlens [B] int64/int32 as int32 here
  *   hlens   [B] int32      valid frames

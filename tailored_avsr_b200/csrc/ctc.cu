@@ -110,13 +110,116 @@ ctc_head_kernel(const float* __restrict__ hs, long long ldh, const float* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
+// Head for larger vocabularies (64 < V <= 256: the 256-token SentencePiece alternative of
+// configs/ASR/branchformer_transformer+ctc_english.yaml:110-112).  CTA = 8 frames (rows in shared
+// memory) x 256 threads; thread v owns vocabulary entry v for all 8 frames and streams its W row
+// from L2 (float4, the 256 KB matrix is shared by every CTA), plain fp32 FMA in k order like the
+// small-V kernel, so the argmax is just as stable; per frame a block-wide (max, first index) and
+// sum-exp reduction.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBigV = 256;
+constexpr int kBigFrames = 8;
+
+__global__ void __launch_bounds__(256)
+ctc_head_big_kernel(const float* __restrict__ hs, long long ldh, const float* __restrict__ w,
+                    const float* __restrict__ bias, float* __restrict__ logits,
+                    float* __restrict__ logp, float* __restrict__ prob, int64_t* __restrict__ amax,
+                    int M, int D, int V) {
+  extern __shared__ float sm[];
+  float* Hs = sm;                                   // [8][D]
+  __shared__ float s_val[kBigFrames][8];
+  __shared__ int s_idx[kBigFrames][8];
+  __shared__ float s_sum[kBigFrames][8];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int v = threadIdx.x;
+  const int warp = v >> 5, lane = v & 31;
+  const int m0 = blockIdx.x * kBigFrames;
+  for (int i = threadIdx.x * 4; i < kBigFrames * D; i += 1024) {
+    const int f = i / D, k = i % D;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m0 + f < M) x = ld_act4(reinterpret_cast<const float4*>(hs + static_cast<long long>(m0 + f) * ldh + k));
+    *reinterpret_cast<float4*>(Hs + i) = x;
+  }
+  __syncthreads();
+  float acc[kBigFrames];
+  const float bv = v < V ? __ldg(bias + v) : 0.f;
+#pragma unroll
+  for (int f = 0; f < kBigFrames; ++f) acc[f] = bv;
+  if (v < V) {
+    const float4* wr = reinterpret_cast<const float4*>(w + static_cast<long long>(v) * D);
+    for (int k4 = 0; k4 < D / 4; ++k4) {
+      const float4 ww = __ldg(wr + k4);
+#pragma unroll
+      for (int f = 0; f < kBigFrames; ++f) {
+        const float4 x = *reinterpret_cast<const float4*>(Hs + f * D + 4 * k4);
+        acc[f] = fmaf(x.x, ww.x, acc[f]);
+        acc[f] = fmaf(x.y, ww.y, acc[f]);
+        acc[f] = fmaf(x.z, ww.z, acc[f]);
+        acc[f] = fmaf(x.w, ww.w, acc[f]);
+      }
+    }
+  }
+  // ---- per frame: argmax (first maximal index), log-sum-exp ----
+#pragma unroll
+  for (int f = 0; f < kBigFrames; ++f) {
+    float bvv = v < V ? acc[f] : -INFINITY;
+    int bi = v;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bvv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bvv || (ov == bvv && oi < bi)) { bvv = ov; bi = oi; }
+    }
+    if (lane == 0) { s_val[f][warp] = bvv; s_idx[f][warp] = bi; }
+  }
+  __syncthreads();
+  float mx[kBigFrames];
+  int am[kBigFrames];
+#pragma unroll
+  for (int f = 0; f < kBigFrames; ++f) {
+    float bvv = s_val[f][0];
+    int bi = s_idx[f][0];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) {
+      const float ov = s_val[f][q];
+      const int oi = s_idx[f][q];
+      if (ov > bvv || (ov == bvv && oi < bi)) { bvv = ov; bi = oi; }
+    }
+    mx[f] = bvv;
+    am[f] = bi;
+    const float e = v < V ? expf(acc[f] - bvv) : 0.f;
+    const float se = warp_sum(e);
+    if (lane == 0) s_sum[f][warp] = se;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int f = 0; f < kBigFrames; ++f) {
+    const int m = m0 + f;
+    if (m >= M) break;
+    float se = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) se += s_sum[f][q];
+    if (v < V) {
+      const long long o = static_cast<long long>(m) * V + v;
+      if (logits) logits[o] = acc[f];
+      if (logp) logp[o] = acc[f] - (mx[f] + logf(se));
+      if (prob) prob[o] = expf(acc[f] - mx[f]) / se;
+    }
+    if (amax && v == 0) amax[m] = am[f];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Vocabulary residual: out = x + p . W^T + b with p (M,V) posteriors and W (D,V) — the InterCTC
 // self-conditioning update (encoder.py:393-399) and the second half of InterCTCResidualModule
 // (interctc_residual_module.py:14).  Optionally also the LayerNorm of the updated row (the next
 // block's norm_ff_macaron), so the conditioned stream needs no extra pass.  One warp per frame,
 // lane owns channels lane + 32 c; W^T is staged once per CTA.
 // ------------------------------------------------------------------------------------------------
-template <int kC>
+// kBig: 64 < V <= 256 - the posterior row takes up to 8 values per lane and W^T (V x D floats, up
+// to 512 KB) is read through L1 / L2 from a pre-transposed global copy instead of shared memory.
+template <int kC, bool kBig = false>
 __global__ void __launch_bounds__(256)
 vocab_residual_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ p,
                       const float* __restrict__ w, const float* __restrict__ bias,
@@ -125,11 +228,16 @@ vocab_residual_kernel(const float* __restrict__ x, long long ldx, const float* _
                       long long ldn, int M, int V, int xn_bf16) {
   pdl_launch_dependents();
   constexpr int D = kC * 32;
+  constexpr int kPS = kBig ? 8 : 2;   // posterior values per lane
   extern __shared__ float sm[];
-  float* Wt = sm;  // [V][D]
-  for (int i = threadIdx.x; i < V * D; i += 256) {
-    const int v = i / D, d = i % D;
-    Wt[i] = __ldg(w + static_cast<long long>(d) * V + v);
+  const float* Wt = sm;  // [V][D]
+  if constexpr (kBig) {
+    Wt = w;   // the caller passes W^T (V, D) row-major
+  } else {
+    for (int i = threadIdx.x; i < V * D; i += 256) {
+      const int v = i / D, d = i % D;
+      sm[i] = __ldg(w + static_cast<long long>(d) * V + v);
+    }
   }
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -143,15 +251,26 @@ vocab_residual_kernel(const float* __restrict__ x, long long ldx, const float* _
   __syncthreads();
   pdl_wait();
   for (int m = blockIdx.x * 8 + warp; m < M; m += gridDim.x * 8) {
-    const float p0 = lane < V ? ld_act(p + static_cast<long long>(m) * V + lane) : 0.f;
-    const float p1 = lane + 32 < V ? ld_act(p + static_cast<long long>(m) * V + lane + 32) : 0.f;
+    float pr[kPS];
+#pragma unroll
+    for (int q = 0; q < kPS; ++q)
+      pr[q] = lane + 32 * q < V ? ld_act(p + static_cast<long long>(m) * V + lane + 32 * q) : 0.f;
     float acc[kC];
 #pragma unroll
     for (int c = 0; c < kC; ++c) acc[c] = bb[c];
-    for (int v = 0; v < V; ++v) {
-      const float pv = __shfl_sync(0xffffffffu, v < 32 ? p0 : p1, v & 31);
 #pragma unroll
-      for (int c = 0; c < kC; ++c) acc[c] = fmaf(pv, Wt[v * D + lane + 32 * c], acc[c]);
+    for (int q = 0; q < kPS; ++q) {
+      const int vend = min(32, V - 32 * q);
+      for (int vv = 0; vv < vend; ++vv) {
+        const int v = 32 * q + vv;
+        const float pv = __shfl_sync(0xffffffffu, pr[q], vv);
+#pragma unroll
+        for (int c = 0; c < kC; ++c) {
+          const float wv = kBig ? __ldg(Wt + static_cast<long long>(v) * D + lane + 32 * c)
+                                : Wt[v * D + lane + 32 * c];
+          acc[c] = fmaf(pv, wv, acc[c]);
+        }
+      }
     }
     float sum = 0.f;
 #pragma unroll
@@ -218,15 +337,17 @@ __device__ __forceinline__ float lse2(float a, float b) {
   return m + __logf(__expf(a - m) + __expf(b - m));
 }
 
-template <int kC>
+// kVS = vocabulary values per lane: 2 (V <= 64) or 8 (V <= 256)
+template <int kC, int kVS = 2>
 __global__ void __launch_bounds__(128)
 ctc_loss_kernel(const float* __restrict__ logp, const int64_t* __restrict__ targets,
                 long long ld_targets, const int32_t* __restrict__ hlens,
                 const int32_t* __restrict__ tlens, float* __restrict__ nll_out,
                 float* __restrict__ grad, float gscale, float* __restrict__ alpha_ws, int B, int T,
                 int V, int Lmax, int zero_infinity) {
-  __shared__ float s_row[4][2][kVPad];   // per warp, double-buffered log2-prob row
-  __shared__ float s_occ[4][kVPad];
+  constexpr int kVP = 32 * kVS;
+  __shared__ float s_row[4][2][kVP];   // per warp, double-buffered log2-prob row
+  __shared__ float s_occ[4][kVP];
   __shared__ float s_fin[4][2];
   pdl_launch_dependents();
   pdl_wait();
@@ -269,16 +390,20 @@ ctc_loss_kernel(const float* __restrict__ logp, const int64_t* __restrict__ targ
   // log-prob rows are prefetched one time step ahead into registers (fetch) and published to the
   // warp through shared memory (commit, converted to base 2), so the global-load latency is off
   // the serial chain.
-  float pre0 = 0.f, pre1 = 0.f;
+  float pre[kVS];
+#pragma unroll
+  for (int q = 0; q < kVS; ++q) pre[q] = 0.f;
   auto fetch = [&](int t) {
     if (t >= 0 && t < Tb) {
-      if (lane < V) pre0 = ld_act(lp + static_cast<long long>(t) * V + lane);
-      if (lane + 32 < V) pre1 = ld_act(lp + static_cast<long long>(t) * V + lane + 32);
+#pragma unroll
+      for (int q = 0; q < kVS; ++q)
+        if (lane + 32 * q < V) pre[q] = ld_act(lp + static_cast<long long>(t) * V + lane + 32 * q);
     }
   };
   auto commit = [&](int buf) {
-    if (lane < V) s_row[warp][buf][lane] = pre0 * kLog2e;
-    if (lane + 32 < V) s_row[warp][buf][lane + 32] = pre1 * kLog2e;
+#pragma unroll
+    for (int q = 0; q < kVS; ++q)
+      if (lane + 32 * q < V) s_row[warp][buf][lane + 32 * q] = pre[q] * kLog2e;
   };
 
   float nll = INFINITY;
@@ -361,7 +486,8 @@ ctc_loss_kernel(const float* __restrict__ logp, const int64_t* __restrict__ targ
     const int buf = t & 1;
     commit(buf);
     fetch(t - 1);
-    if (lane < kVPad / 2) { s_occ[warp][lane] = 0.f; s_occ[warp][lane + 32] = 0.f; }
+#pragma unroll
+    for (int q = 0; q < kVS; ++q) s_occ[warp][lane + 32 * q] = 0.f;
     float np1 = __shfl_down_sync(0xffffffffu, bt[0], 1);
     float np2 = __shfl_down_sync(0xffffffffu, bt[1], 1);
     if (lane == 31) { np1 = kNeg; np2 = kNeg; }
@@ -391,12 +517,11 @@ ctc_loss_kernel(const float* __restrict__ logp, const int64_t* __restrict__ targ
       }
     }
     __syncwarp();
-    if (lane < V)
-      gb[static_cast<long long>(t) * V + lane] =
-          gscale * (ex2f(s_row[warp][buf][lane]) - s_occ[warp][lane]);
-    if (lane + 32 < V)
-      gb[static_cast<long long>(t) * V + lane + 32] =
-          gscale * (ex2f(s_row[warp][buf][lane + 32]) - s_occ[warp][lane + 32]);
+#pragma unroll
+    for (int q = 0; q < kVS; ++q)
+      if (lane + 32 * q < V)
+        gb[static_cast<long long>(t) * V + lane + 32 * q] =
+            gscale * (ex2f(s_row[warp][buf][lane + 32 * q]) - s_occ[warp][lane + 32 * q]);
     __syncwarp();
   }
 }
@@ -583,9 +708,16 @@ extern "C" int tavsr_ctc_head(const float* hs, long long ldh, const float* w, co
                               float* logits, float* logp, float* prob, int64_t* amax, int M,
                               int D, int V, void* stream) {
   TAVSR_REQUIRE(M > 0 && D > 0 && D % 4 == 0 && D <= 512, "ctc_head: bad D=%d", D);
-  TAVSR_REQUIRE(V > 0 && V <= ctc::kVPad, "ctc_head: V=%d > 64 not built", V);
+  TAVSR_REQUIRE(V > 0 && V <= ctc::kBigV, "ctc_head: V=%d > 256 not built", V);
   TAVSR_REQUIRE(hs && w && b && ldh % 4 == 0, "ctc_head: bad arguments");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (V > ctc::kVPad) {
+    TAVSR_CUDA_OK(launch_kernel(ctc::ctc_head_big_kernel, dim3((M + ctc::kBigFrames - 1) / ctc::kBigFrames),
+                                dim3(256), static_cast<size_t>(ctc::kBigFrames * D * 4), s, 0, hs, ldh, w, b,
+                                logits, logp, prob, amax, M, D, V));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+  }
   const int smem = (D * ctc::kVPad + 8 * 4 * D) * 4;
   static PerDeviceMax configured;
   if (configured.raise(smem)) {
@@ -607,11 +739,12 @@ extern "C" int tavsr_vocab_residual(const float* x, long long ldx, const float* 
                                     int D, int V, int dtype, void* stream) {
   const int xn_bf16 = (dtype & TAVSR_DT_LNA_BF16) ? 1 : 0;
   TAVSR_REQUIRE(M > 0 && (D == 128 || D == 256 || D == 512), "vocab_residual: D=%d not built", D);
-  TAVSR_REQUIRE(V > 0 && V <= ctc::kVPad, "vocab_residual: V=%d > 64 not built", V);
+  TAVSR_REQUIRE(V > 0 && V <= ctc::kBigV, "vocab_residual: V=%d > 256 not built", V);
   TAVSR_REQUIRE(x && p && w && b && out, "vocab_residual: null pointer");
   TAVSR_REQUIRE(!xn || (ln_g && ln_b), "vocab_residual: LayerNorm output needs gamma and beta");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int smem = V * D * 4;
+  const bool big = V > ctc::kVPad;   // w is then W^T (V, D): see include/tavsr.h
+  const int smem = big ? 0 : V * D * 4;
   int grid = (M + 7) / 8;
   if (grid > 2 * num_sms()) grid = 2 * num_sms();
 #define TAVSR_VR_CASE(C)                                                                        \
@@ -621,8 +754,12 @@ extern "C" int tavsr_vocab_residual(const float* x, long long ldx, const float* 
       TAVSR_CUDA_OK(cudaFuncSetAttribute(ctc::vocab_residual_kernel<C>,                         \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));   \
     }                                                                                           \
-    TAVSR_CUDA_OK(launch_kernel(ctc::vocab_residual_kernel<C>, dim3(grid), dim3(256), smem, s, 0, x, \
-                                ldx, p, w, b, out, ldo, ln_g, ln_b, eps, xn, ldn, M, V, xn_bf16)); \
+    if (big)                                                                                    \
+      TAVSR_CUDA_OK(launch_kernel(ctc::vocab_residual_kernel<C, true>, dim3(grid), dim3(256), 0, s, 0, \
+                                  x, ldx, p, w, b, out, ldo, ln_g, ln_b, eps, xn, ldn, M, V, xn_bf16)); \
+    else                                                                                        \
+      TAVSR_CUDA_OK(launch_kernel(ctc::vocab_residual_kernel<C>, dim3(grid), dim3(256), smem, s, 0, x, \
+                                  ldx, p, w, b, out, ldo, ln_g, ln_b, eps, xn, ldn, M, V, xn_bf16)); \
   } while (0)
   if (D == 128) TAVSR_VR_CASE(4);
   else if (D == 256) TAVSR_VR_CASE(8);
@@ -640,7 +777,7 @@ extern "C" int tavsr_ctc_loss(const float* logp, const int64_t* targets, long lo
                               const int32_t* hlens, const int32_t* tlens, float* nll, float* grad,
                               float gscale, void* alpha_ws, int B, int T, int V, int Lmax,
                               int zero_infinity, void* stream) {
-  TAVSR_REQUIRE(B > 0 && T > 0 && V > 0 && V <= ctc::kVPad && Lmax >= 0, "ctc_loss: bad shape");
+  TAVSR_REQUIRE(B > 0 && T > 0 && V > 0 && V <= ctc::kBigV && Lmax >= 0, "ctc_loss: bad shape (V <= 256)");
   TAVSR_REQUIRE(logp && targets && hlens && tlens && nll, "ctc_loss: null pointer");
   TAVSR_REQUIRE(!grad || alpha_ws, "ctc_loss: gradient needs the alpha workspace");
   const int S = 2 * Lmax + 1;
@@ -649,9 +786,16 @@ extern "C" int tavsr_ctc_loss(const float* logp, const int64_t* targets, long lo
   float* aws = static_cast<float*>(alpha_ws);
   if (!grad) aws = nullptr;
 #define TAVSR_CTC_CASE(C)                                                                       \
-  TAVSR_CUDA_OK(launch_kernel(ctc::ctc_loss_kernel<C>, dim3(grid), dim3(128), 0, s, 0, logp, targets, \
-                              ld_targets, hlens, tlens, nll, grad, gscale, aws, B, T, V, Lmax,      \
-                              zero_infinity))
+  do {                                                                                          \
+    if (V > ctc::kVPad)                                                                         \
+      TAVSR_CUDA_OK(launch_kernel(ctc::ctc_loss_kernel<C, 8>, dim3(grid), dim3(128), 0, s, 0, logp, \
+                                  targets, ld_targets, hlens, tlens, nll, grad, gscale, aws, B, T, V, \
+                                  Lmax, zero_infinity));                                        \
+    else                                                                                        \
+      TAVSR_CUDA_OK(launch_kernel(ctc::ctc_loss_kernel<C>, dim3(grid), dim3(128), 0, s, 0, logp,    \
+                                  targets, ld_targets, hlens, tlens, nll, grad, gscale, aws, B, T, V, \
+                                  Lmax, zero_infinity));                                        \
+  } while (0)
   if (S <= 64) TAVSR_CTC_CASE(2);
   else if (S <= 128) TAVSR_CTC_CASE(4);
   else if (S <= 256) TAVSR_CTC_CASE(8);

@@ -29,8 +29,20 @@ class _CTCHeadLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout):
         grad, hs2d, weight = ctx.saved_tensors
-        dhs, dw, db = ops.ctc_head_bwd(grad, hs2d, weight.contiguous(),
-                                       row_scale=gout.contiguous().float(), rows_per_seg=ctx.T)
+        V = weight.shape[0]
+        if V <= 64:
+            dhs, dw, db = ops.ctc_head_bwd(grad, hs2d, weight.contiguous(),
+                                           row_scale=gout.contiguous().float(), rows_per_seg=ctx.T)
+        else:
+            # larger vocabularies: scale d logits per utterance, then dgrad / wgrad on the tcgen05
+            # GEMM like every other Linear of the training path
+            if V % 4 != 0:
+                raise NotImplementedError("CTC head backward for 64 < odim <= 256 needs odim % 4 == 0")
+            from .. import ops_backward as ob
+            g2 = grad.reshape(-1, V)
+            zero = torch.zeros_like(gout, dtype=torch.float32)
+            dl = ops.scale_add_rows(g2, g2, gout.contiguous().float(), zero, ctx.T)
+            dhs, dw, db = ob.linear_bwd(hs2d, weight.contiguous(), dl)
         return dhs, dw, db, None, None, None, None, None, None
 
 
@@ -59,9 +71,11 @@ class CTC(torch.nn.Module):
         else:
             raise ValueError(f'ctc_type must be "builtin" or "gtnctc": {self.ctc_type}')
         self.reduce = reduce
-        if odim > 64:
-            logging.warning("tailored_avsr_b200.CTC: the CUDA head is built for vocabularies <= 64 "
-                            "(char-level EN 41 / ES 37); odim=%d will raise at run time", odim)
+        if odim > 256:
+            raise NotImplementedError(
+                f"tailored_avsr_b200.CTC: the CUDA head / loss kernels are built for vocabularies up "
+                f"to 256 (char-level EN 41 / ES 37 and the 256-token SentencePiece alternative); "
+                f"odim={odim}")
 
     # ---------------------------------------------------------------------------------------
     def _head(self, hs_pad: torch.Tensor, logp=False, prob=False, amax=False):

@@ -503,6 +503,8 @@ def vocab_residual(x: torch.Tensor, p: torch.Tensor, w: torch.Tensor, b: torch.T
     V = p.shape[1]
     if w.shape != (D, V) or not w.is_contiguous() or not p.is_contiguous():
         raise ValueError("vocab_residual: w must be a contiguous (D,V) matrix, p contiguous (M,V)")
+    if V > 64:
+        w = w.t().contiguous()   # the large-vocabulary kernel streams W^T (V, D) rows from L2
     out = torch.empty((M, D), device=x.device, dtype=torch.float32)
     xn = torch.empty((M, D), device=x.device, dtype=ln_dtype) if ln is not None else None
     check(_lib.load().tavsr_vocab_residual(

@@ -224,7 +224,7 @@ def test_merge_weights():
     assert max_rel(w2, ref[:, 1]) < 1e-5
 
 
-@pytest.mark.parametrize("M,V", [(1992, 41), (100, 37), (5, 64), (3, 5)])
+@pytest.mark.parametrize("M,V", [(1992, 41), (100, 37), (5, 64), (3, 5), (1992, 256), (77, 100), (9, 65)])
 def test_ctc_head(M, V):
     ops = _ops()
     g = torch.Generator().manual_seed(V)
@@ -239,7 +239,8 @@ def test_ctc_head(M, V):
 
 
 @pytest.mark.parametrize("B,T,V,Lmax", [(8, 249, 41, 100), (4, 50, 37, 30), (3, 20, 5, 12),
-                                        (2, 300, 41, 140), (2, 600, 41, 300)])
+                                        (2, 300, 41, 140), (2, 600, 41, 300), (4, 120, 256, 40),
+                                        (3, 60, 100, 20)])
 def test_ctc_loss_and_grad(B, T, V, Lmax):
     ops = _ops()
     g = torch.Generator().manual_seed(B + T)
@@ -356,7 +357,8 @@ def _ffn_case(ops, M, variant):
         assert rel_fro(oA, _ln(v1, gA.double(), bA.double(), 1e-12)) < 3e-3
 
 
-@pytest.mark.parametrize("M,D,V,ln", [(70, 256, 41, True), (9, 128, 64, False), (33, 512, 37, True)])
+@pytest.mark.parametrize("M,D,V,ln", [(70, 256, 41, True), (9, 128, 64, False), (33, 512, 37, True),
+                                      (70, 256, 256, True), (11, 256, 100, False)])
 def test_vocab_residual(M, D, V, ln):
     ops = _ops()
     g = torch.Generator().manual_seed(M + V)

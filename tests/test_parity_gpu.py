@@ -364,3 +364,43 @@ def test_pipeline_recaptures_after_parameter_update_and_per_compute_mode():
         lb = float(pipe.run(*args)["loss"])
     assert lb != l2 and abs(lb - l2) <= 2e-2 * abs(l2)
     assert float(pipe.run(*args)["loss"]) == l2
+
+
+def test_ctc_module_with_a_256_token_vocabulary():
+    """The 256-token SentencePiece alternative (configs/ASR/branchformer_transformer+ctc_english.yaml
+    :110-112): loss, per-utterance loss, argmax (bit-exact), log-softmax, greedy lists and the
+    training gradients of the head against torch on the CPU."""
+    import torch.nn.functional as F
+    from tailored_avsr_b200.ctc.ctc import CTC
+    from oracle import ref_path, synth
+    B, T, D, V, L = 4, 90, 256, 256, 25
+    ctc = CTC(odim=V, encoder_output_size=D, dropout_rate=0.0).eval()
+    sd = synth.fill_module(ctc, seed=3, prefix="ctc.")
+    hs = synth.randn((B, T, D), 77) * 3.0
+    ys = synth.rand_targets(B, L, V, 5)
+    hl = torch.tensor([90, 61, 90, 30])
+    yl = torch.tensor([25, 20, 25, 9])
+    ctc = ctc.to(DEV)
+    with torch.no_grad():
+        loss = ctc(hs.to(DEV), hl.to(DEV), ys.to(DEV), yl.to(DEV))
+        amax = ctc.argmax(hs.to(DEV))
+        logp = ctc.log_softmax(hs.to(DEV))
+        toks = ctc.greedy_lists(hs.to(DEV), hl.to(DEV))
+    want = ref_path.ctc_loss(hs, hl, ys, yl, sd, "ctc.ctc_lo")
+    assert abs(float(loss) - float(want)) <= 1e-4 * abs(float(want)), (float(loss), float(want))
+    logits = F.linear(hs, sd["ctc.ctc_lo.weight"], sd["ctc.ctc_lo.bias"])
+    assert torch.equal(amax.cpu(), logits.argmax(-1))
+    assert (logp.cpu() - F.log_softmax(logits, -1)).abs().max() < 3e-5
+    assert toks == ref_path.ctc_greedy(hs, sd, "ctc.ctc_lo", lens=hl)
+    # training: head + loss backward
+    hsg = hs.to(DEV).requires_grad_(True)
+    for p in ctc.parameters():
+        p.requires_grad_(True)
+    ctc(hsg, hl.to(DEV), ys.to(DEV), yl.to(DEV)).backward()
+    hs_ref = hs.clone().double().requires_grad_(True)
+    sd64 = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    ref_path.ctc_loss(hs_ref, hl, ys, yl, sd64, "ctc.ctc_lo").backward()
+    for mine, ref in ((hsg.grad, hs_ref.grad), (ctc.ctc_lo.weight.grad, sd64["ctc.ctc_lo.weight"].grad),
+                      (ctc.ctc_lo.bias.grad, sd64["ctc.ctc_lo.bias"].grad)):
+        err = float((mine.cpu().double() - ref).norm() / ref.norm())
+        assert err < 3e-3, err
