@@ -537,3 +537,43 @@ def ctc_prefix_score(logp: np.ndarray, r_prev: np.ndarray, prefix: Sequence[int]
         log_psi[c] = psi
     log_psi[eos] = r_sum[T - 1]
     return r_new, log_psi
+
+
+def ctc_beam_search(logp: np.ndarray, beam: int, eos: int, blank: int = 0, ctc_weight: float = 1.0,
+                    length_bonus: float = 0.0, maxlen: Optional[int] = None, nbest: int = 1):
+    """CTC-only beam search with the semantics of espnet's BatchBeamSearch driven by the `ctc`
+    partial scorer (the object built at src/inference/asr_inference.py:142,276-303): per output
+    position every running hypothesis is extended by every token with the prefix-score difference,
+    the `beam` best (hypothesis, token) pairs survive, hypotheses ending in <eos> move to the ended
+    list, at the last position only <eos> may follow.  Plain Python over ctc_prefix_score; returns
+    [(tokens, score)] best first (the checker of tailored_avsr_b200.ctc.beam_search)."""
+    T, V = logp.shape
+    maxlen = T if maxlen is None else maxlen
+    running = [([], ctc_prefix_init(logp, blank), 0.0, 0.0)]       # (prefix, r, log_psi, score)
+    ended = []
+    for i in range(maxlen):
+        cands = []
+        for prefix, r, psi_prev, score in running:
+            r_new, log_psi = ctc_prefix_score(logp, r, prefix, blank, eos)
+            for c in range(V):
+                if c == blank or (i == maxlen - 1 and c != eos):
+                    continue
+                sc = LOGZERO if log_psi[c] <= LOGZERO / 2 else log_psi[c] - psi_prev
+                cands.append((score + ctc_weight * sc + length_bonus, prefix, c, r_new[c], log_psi[c]))
+        cands.sort(key=lambda t: -t[0])
+        running = []
+        for total, prefix, c, r_c, psi_c in cands[:beam]:
+            if total <= -1e9:
+                continue
+            if c == eos:
+                ended.append((prefix, total))
+            else:
+                running.append((prefix + [c], r_c, psi_c, total))
+        if not running:
+            break
+        if length_bonus <= 0 and len(ended) >= nbest:
+            best_end = sorted((s_ for _, s_ in ended), reverse=True)[nbest - 1]
+            if best_end >= max(t[3] for t in running):
+                break
+    ended.sort(key=lambda t: -t[1])
+    return ended[:nbest]

@@ -314,3 +314,29 @@ def test_precision_budget_of_tensor_core_operand_rounding():
     print("precision budget (max-rel, fro):", errs)
     assert max(errs["tf32"]) <= 5e-4, errs          # tf32 mode: >= 2x margin to the 1e-3 bar
     assert 5e-4 <= max(errs["bf16"]) <= 2e-2, errs   # bf16 operands: needs its own tolerance
+
+
+def test_oracle_beam_search_finds_the_most_probable_label_sequence():
+    """The reference beam search of the tests (oracle/ref_path.ctc_beam_search, espnet
+    BatchBeamSearch semantics over the CTC prefix scorer) with a beam wide enough to be exhaustive
+    returns argmax_labels p(labels | x), checked by brute force over every label sequence."""
+    import itertools
+    T, V, eos = 5, 4, 3
+    torch.manual_seed(3)
+    lp = torch.log_softmax(torch.randn(T, V) * 1.5, -1).double().numpy()
+
+    def seq_logprob(labels):
+        if len(labels) == 0:
+            return float(lp[:, 0].sum())
+        return -ref_path.ctc_nll_numpy(lp, list(labels), blank=0)
+
+    best = max(((seq_logprob(l), list(l)) for n in range(0, T + 1)
+                for l in itertools.product([1, 2], repeat=n)), key=lambda t: t[0])
+    got = ref_path.ctc_beam_search(lp, beam=64, eos=eos, nbest=3)
+    # token 3 is <eos> here: label sequences are over {1, 2}; hypotheses containing it as a label
+    # are legal CTC labels too, so compare within the {1, 2} alphabet
+    got12 = [(t, s) for t, s in got if all(x in (1, 2) for x in t)]
+    assert got12 and got12[0][0] == best[1], (got, best)
+    assert abs(got12[0][1] - best[0]) < 1e-9
+    scores = [s for _, s in got]
+    assert scores == sorted(scores, reverse=True)

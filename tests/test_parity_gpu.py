@@ -404,3 +404,65 @@ def test_ctc_module_with_a_256_token_vocabulary():
                       (ctc.ctc_lo.bias.grad, sd64["ctc.ctc_lo.bias"].grad)):
         err = float((mine.cpu().double() - ref).norm() / ref.norm())
         assert err < 3e-3, err
+
+
+@pytest.mark.parametrize("beam", [30, 40])
+def test_batched_ctc_beam_search_equals_the_oracle_beam_search(beam):
+    """(f3) tailored_avsr_b200.ctc.beam_search.CTCBeamSearch - every step one launch over all
+    hypotheses x tokens x frames, scorer state resident on the device, one host flag every 4 steps -
+    returns the same n-best token sequences as the plain-Python beam search over the oracle prefix
+    scorer, for beam 30 / 40 (configs' inference_conf) on 8 utterances."""
+    from oracle import ref_path, synth
+    from tailored_avsr_b200.ctc.beam_search import CTCBeamSearch
+    from tailored_avsr_b200.ctc.ctc import CTC
+    D, V = 256, 41
+    eos = V - 1
+    ctc = CTC(odim=V, encoder_output_size=D, dropout_rate=0.0).eval()
+    sd = synth.fill_module(ctc, seed=5, prefix="ctc.")
+    bs = CTCBeamSearch(ctc.to(DEV), beam_size=beam, sos=eos, eos=eos)
+    for u in range(8):
+        T = 18 + 3 * u
+        x = synth.randn((T, D), 100 + u) * 6.0        # peaky posteriors: ~T/2 output tokens
+        lp64 = ref_path.ctc_log_softmax(x[None], sd, "ctc.ctc_lo")[0].double().numpy()
+        want = ref_path.ctc_beam_search(lp64, beam=beam, eos=eos, nbest=3)
+        got = bs.search(x.to(DEV), nbest=3)
+        assert len(got) == len(want) and len(got) >= 1
+        assert got[0][0] == want[0][0], (u, got[0], want[0])
+        assert abs(got[0][1] - want[0][1]) <= 2e-3 * max(1.0, abs(want[0][1]))
+        for (gt, gs), (wt, ws) in zip(got, want):
+            # lower ranks may swap when two hypotheses score within fp32 noise of each other
+            assert abs(gs - ws) <= 5e-3 * max(1.0, abs(ws)), (u, gs, ws)
+        assert [t for t, _ in got] == [t for t, _ in want] or \
+            sorted(map(tuple, (t for t, _ in got))) == sorted(map(tuple, (t for t, _ in want)))
+
+
+def test_prefix_scorer_single_hypothesis_contract_of_espnet_beam_search():
+    """espnet's non-batch BeamSearch calls score_partial(y, ids, state, x) and gets
+    ONE SCORE PER ENTRY OF ids plus a state indexed by the position in ids, then
+    select_state(state, j) with two arguments.  Drive that call sequence and compare with the batch
+    form."""
+    from oracle import synth
+    from tailored_avsr_b200.ctc.ctc import CTC
+    from tailored_avsr_b200.ctc.prefix_scorer import CTCPrefixScorer
+    T, D, V = 31, 256, 41
+    eos = V - 1
+    ctc = CTC(odim=V, encoder_output_size=D, dropout_rate=0.0).eval()
+    synth.fill_module(ctc, seed=6, prefix="ctc.")
+    x = (synth.randn((T, D), 9) * 4.0).to(DEV)
+    sc = CTCPrefixScorer(ctc=ctc.to(DEV), eos=eos)
+    st = sc.init_state(x)
+    y = torch.tensor([eos], dtype=torch.int64, device=DEV)
+    ids = torch.tensor([7, 3, eos, 12], dtype=torch.int64, device=DEV)     # a pre-beam of 4 < V
+    scores, pstate = sc.score_partial(y, ids, st, x)
+    assert scores.shape == (4,)
+    full, bstate = sc.batch_score_partial(y[None], None, [st], x)
+    assert torch.equal(scores, full[0, ids])
+    # BeamSearch: weighted_scores[part_ids] += w * part_scores; then select_state(part_states, j)
+    j = 1                                                                 # token ids[1] = 3
+    s_a = sc.select_state(pstate, j)
+    s_b = sc.select_state(bstate, 0, int(ids[j]))
+    assert torch.equal(s_a[0], s_b[0]) and torch.equal(s_a[1], s_b[1])
+    y2 = torch.tensor([eos, 3], dtype=torch.int64, device=DEV)
+    sc2, _ = sc.score_partial(y2, ids, s_a, x)
+    full2, _ = sc.batch_score_partial(y2[None], None, [s_b], x)
+    assert torch.equal(sc2, full2[0, ids])
