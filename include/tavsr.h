@@ -76,6 +76,15 @@ int tavsr_gemm_bias_act(const void* x, long long ldx, const void* w, long long l
                         const float* bias, void* y, long long ldy, int M, int N, int K, int act,
                         int round_out, int dtype, void* stream);
 
+/* Two projections of the same rows in ONE launch: Y1 = X1 . W1^T + b1 (no activation: the fused
+ * linear_q|k|v, encoder_layer.py:208) and Y2 = gelu(X2 . W2^T + b2) (cgMLP channel_proj1,
+ * encoder_layer.py:220); X1 / X2 are the two LayerNorm outputs of the same block input.  Same M and
+ * K; the persistent tile scheduler walks both problems' 256-wide tiles.  dtype as above. */
+int tavsr_gemm_group2(const void* x1, long long ldx1, const void* w1, long long ldw1,
+                      const float* bias1, void* y1, long long ldy1, int N1, const void* x2,
+                      long long ldx2, const void* w2, long long ldw2, const float* bias2, void* y2,
+                      long long ldy2, int N2, int M, int K, int dtype, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Row-complete GEMM, N == 256 (the model width): one thread owns one output row, so everything that
  * follows the projection in the reference layer is fused into the epilogue:

@@ -69,6 +69,10 @@ SIGNATURES = {
     "tavsr_gemm_bias_act": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p,
                                     c_longlong, c_int, c_int, c_int, c_int, c_int, c_int,
                                     c_void_p]),
+    "tavsr_gemm_group2": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p,
+                                  c_longlong, c_int, c_void_p, c_longlong, c_void_p, c_longlong,
+                                  c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_int,
+                                  c_void_p]),
     "tavsr_gemm_rowln": (c_int, [POINTER(RowLNArgs), c_void_p]),
     "tavsr_rowln_workspace_bytes": (c_size_t, [c_int]),
     "tavsr_ffn_fused": (c_int, [POINTER(FfnArgs), c_void_p]),

@@ -125,15 +125,15 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, bool is_bf16
 // launch helpers
 // ------------------------------------------------------------------------------------------------
 template <bool kTf32, int kBlockN, int kMode, bool kDual, int kCtas, int kAct, bool kSeq = false,
-          bool kWideEpi = false>
+          bool kWideEpi = false, int kAct2 = kNoGroup>
 static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<kTf32, kBlockN, kMode, kDual, kCtas, kSeq, kWideEpi>;
-  auto kern = gemm_sm100_kernel<kTf32, kBlockN, kMode, kDual, kCtas, kAct, kSeq, kWideEpi>;
+  auto kern = gemm_sm100_kernel<kTf32, kBlockN, kMode, kDual, kCtas, kAct, kSeq, kWideEpi, kAct2>;
   static unsigned long long configured = 0;  // one bit per device ordinal
   if (first_use_on_device(configured))
     TAVSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes));
-  const int units = p.num_m_tiles * p.num_n_tiles;
+  const int units = p.num_m_tiles * (p.num_n_tiles + (kAct2 != kNoGroup ? p.num_n_tiles2 : 0));
   const int max_units = num_sms() / kCtas;
   const int grid = (units < max_units ? units : max_units) * kCtas;
   TAVSR_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, stream, kCtas, p));
@@ -222,6 +222,49 @@ extern "C" int tavsr_gemm_bias_act(const void* x, long long ldx, const void* w, 
   }
   if (bn == 128) return launch_tiled<true, 128, false>(p, s);
   return wide ? launch_tiled<true, 256, true>(p, s) : launch_tiled<true, 256, false>(p, s);
+}
+
+// Two projections of the same rows in ONE launch (the fused QKV projection and channel_proj1 + GELU
+// of a two-branch block both read LayerNorm outputs of the same x): the tile scheduler walks both
+// problems' 256-wide tiles, so the tail of the first GEMM and the head of the second share a wave
+// and one launch + prologue disappears per block.  Activations: problem 1 none, problem 2 GELU
+// (the only grouped pair the layer needs); same M, same K.
+extern "C" int tavsr_gemm_group2(const void* x1, long long ldx1, const void* w1, long long ldw1,
+                                 const float* bias1, void* y1, long long ldy1, int N1, const void* x2,
+                                 long long ldx2, const void* w2, long long ldw2, const float* bias2,
+                                 void* y2, long long ldy2, int N2, int M, int K, int dtype,
+                                 void* stream) {
+  TAVSR_REQUIRE(M > 0 && N1 > 0 && N2 > 0 && K > 0, "gemm_group2: empty problem");
+  const int op = dtype & TAVSR_DT_MASK;
+  TAVSR_REQUIRE(op == TAVSR_DT_TF32 || op == TAVSR_DT_BF16, "gemm_group2: dtype must be tf32 or bf16");
+  const bool bf16 = op == TAVSR_DT_BF16;
+  const bool out_bf16 = (dtype & TAVSR_DT_OUT_BF16) != 0;
+  TAVSR_REQUIRE(bf16 || !out_bf16, "gemm_group2: bf16 output only with bf16 operands");
+  const int eb = bf16 ? 2 : 4;
+  TAVSR_REQUIRE(K % (16 / eb) == 0 && N1 % 8 == 0 && N2 % 8 == 0, "gemm_group2: K / N alignment");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N1; p.K = K; p.N2 = N2;
+  p.bias = bias1; p.bias2 = bias2; p.act = ACT_NONE;
+  p.c_bf16 = out_bf16;
+  p.num_m_tiles = (M + 255) / 256;
+  p.num_n_tiles = (N1 + 255) / 256;
+  p.num_n_tiles2 = (N2 + 255) / 256;
+  int rc;
+  if ((rc = make_tmap_2d(&p.tmA, x1, eb, bf16, M, K, ldx1, 128, 128 / eb))) return rc;
+  if ((rc = make_tmap_2d(&p.tmA2, x2, eb, bf16, M, K, ldx2, 128, 128 / eb))) return rc;
+  if ((rc = make_tmap_2d(&p.tmB, w1, eb, bf16, N1, K, ldw1, 128, 128 / eb))) return rc;
+  if ((rc = make_tmap_2d(&p.tmB2, w2, eb, bf16, N2, K, ldw2, 128, 128 / eb))) return rc;
+  if (out_bf16) {
+    if ((rc = make_tmap_2d(&p.tmC, y1, 2, true, M, N1, ldy1, 32, 64, false))) return rc;
+    if ((rc = make_tmap_2d(&p.tmC2, y2, 2, true, M, N2, ldy2, 32, 64, false))) return rc;
+  } else {
+    if ((rc = make_tmap_2d(&p.tmC, y1, 4, false, M, N1, ldy1, 32, 32, false))) return rc;
+    if ((rc = make_tmap_2d(&p.tmC2, y2, 4, false, M, N2, ldy2, 32, 32, false))) return rc;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return bf16 ? launch_gemm<false, 256, kModeTiled, false, 2, ACT_NONE, false, true, ACT_GELU>(p, s)
+              : launch_gemm<true, 256, kModeTiled, false, 2, ACT_NONE, false, true, ACT_GELU>(p, s);
 }
 
 extern "C" size_t tavsr_rowln_workspace_bytes(int M) {

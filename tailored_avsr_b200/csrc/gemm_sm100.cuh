@@ -79,7 +79,16 @@ struct alignas(64) GemmParams {
   // ---- bf16 mode (kTf32 == false): which outputs are stored as bf16 (tensor-core operands of the
   // next kernel) instead of fp32 (residual stream, encoder output) ----
   int c_bf16, lnA_bf16, lnB_bf16;
+  // ---- grouped tiled mode (kAct2 != kNoGroup): a SECOND problem Y2 = act2(X2 . W2^T + b2) with the
+  // same M and K shares the launch; per row block the n tiles of problem 1 come first, then the
+  // num_n_tiles2 tiles of problem 2 (tmA2 = X2) ----
+  CUtensorMap tmB2;
+  CUtensorMap tmC2;
+  const float* bias2;
+  int N2, num_n_tiles2;
 };
+
+constexpr int kNoGroup = -2;
 
 // kWideEpi (tiled mode): 16 epilogue warps (four per TMEM lane quadrant, a quarter of the tile's
 // columns each) instead of 8.  The K = 256 projections are bound by their epilogue, and ncu shows it
@@ -465,10 +474,12 @@ __device__ __forceinline__ void rowln_finish(const GemmParams& p, const float* s
 }
 
 template <bool kTf32, int kBlockN, int kMode, bool kDual, int kCtas, int kAct, bool kSeq = false,
-          bool kWideEpi = false>
+          bool kWideEpi = false, int kAct2 = kNoGroup>
 __global__ void __launch_bounds__(GemmCfg<kTf32, kBlockN, kMode, kDual, kCtas, kSeq, kWideEpi>::kThreads, 1)
 gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<kTf32, kBlockN, kMode, kDual, kCtas, kSeq, kWideEpi>;
+  constexpr bool kGroup = kAct2 != kNoGroup;
+  static_assert(!kGroup || (kMode == kModeTiled && !kDual), "grouping is a tiled-mode feature");
   static_assert(!kSeq || kDual, "the sequential mode is a dual mode");
   constexpr bool kPair = kCtas == 2;
   constexpr int kStages = Cfg::kStages;
@@ -493,13 +504,15 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
   const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
   const int unit0 = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int unit_step = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;  // in units
+  const int n_per_m = p.num_n_tiles + (kGroup ? p.num_n_tiles2 : 0);   // tiles per row block
+  const int num_tiles = p.num_m_tiles * n_per_m;  // in units
   const int num_kb = (p.K + Cfg::kBlockK - 1) / Cfg::kBlockK;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
-    if (kDual) tma_prefetch_desc(&p.tmA2);
+    if (kDual || kGroup) tma_prefetch_desc(&p.tmA2);
+    if (kGroup) tma_prefetch_desc(&p.tmB2);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -541,8 +554,11 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
       int s = 0;
       uint32_t ph = 0;
       for (int tile = unit0; tile < num_tiles; tile += unit_step) {
-        const int m_blk = (tile / p.num_n_tiles) * kCtas + static_cast<int>(cta_rank);
-        const int n_blk = tile % p.num_n_tiles;
+        const int m_blk = (tile / n_per_m) * kCtas + static_cast<int>(cta_rank);
+        int n_blk = tile % n_per_m;
+        const bool prob2 = kGroup && n_blk >= p.num_n_tiles;
+        if (prob2) n_blk -= p.num_n_tiles;
+        const CUtensorMap* tma_b = prob2 ? &p.tmB2 : &p.tmB;
         // RowLN: N is one tile, the unit's n index selects the K split instead
         const int b_row0 = (kMode == kModeRowLN ? 0 : n_blk * kBlockN) +
                            static_cast<int>(cta_rank) * Cfg::kBRows;
@@ -554,7 +570,7 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
           uint8_t* sb = st + Cfg::kABytes * Cfg::kATiles;
           constexpr bool seq = kSeq;   // one A tile per stage, picked by k-block
           const bool second = seq && kb >= p.seq_kb1;
-          const CUtensorMap* tma_a = second ? &p.tmA2 : &p.tmA;
+          const CUtensorMap* tma_a = (second || prob2) ? &p.tmA2 : &p.tmA;
           const int ka = (second ? kb - p.seq_kb1 : kb) * Cfg::kBlockK;
           const uint32_t bytes = seq ? Cfg::kABytes + Cfg::kBBytes : Cfg::kStageBytes;
           if (kPair) {
@@ -564,14 +580,14 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
             if (kDual && !seq)
               tma_load_2d_2sm(st + Cfg::kABytes, &p.tmA2, &full_bar[s], kb * Cfg::kBlockK,
                               m_blk * Cfg::kBlockM);
-            tma_load_2d_2sm(sb, &p.tmB, &full_bar[s], kb * Cfg::kBlockK, b_row0);
+            tma_load_2d_2sm(sb, tma_b, &full_bar[s], kb * Cfg::kBlockK, b_row0);
           } else {
             mbar_arrive_expect_tx(&full_bar[s], bytes);
             tma_load_2d(st, tma_a, &full_bar[s], ka, m_blk * Cfg::kBlockM);
             if (kDual && !seq)
               tma_load_2d(st + Cfg::kABytes, &p.tmA2, &full_bar[s], kb * Cfg::kBlockK,
                           m_blk * Cfg::kBlockM);
-            tma_load_2d(sb, &p.tmB, &full_bar[s], kb * Cfg::kBlockK, b_row0);
+            tma_load_2d(sb, tma_b, &full_bar[s], kb * Cfg::kBlockK, b_row0);
           }
           if (++s == kStages) { s = 0; ph ^= 1; }
         }
@@ -636,10 +652,15 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
     uint32_t aph = 0;
     int it = 0;
     for (int tile = unit0; tile < num_tiles; tile += unit_step, ++it) {
-      const int m_blk = (tile / p.num_n_tiles) * kCtas + static_cast<int>(cta_rank);
-      const int n_blk = tile % p.num_n_tiles;
+      const int m_blk = (tile / n_per_m) * kCtas + static_cast<int>(cta_rank);
+      int n_blk = tile % n_per_m;
+      const bool prob2 = kGroup && n_blk >= p.num_n_tiles;   // warp-uniform
+      if (prob2) n_blk -= p.num_n_tiles;
       const int m0 = m_blk * Cfg::kBlockM;
       const int n0 = n_blk * kBlockN;
+      const float* e_bias = prob2 ? p.bias2 : p.bias;
+      const int e_N = prob2 ? p.N2 : p.N;
+      const CUtensorMap* e_tmC = prob2 ? &p.tmC2 : &p.tmC;
       const uint32_t tacc = tmem_base + lane_off + as * Cfg::kAccCols;
 
       if constexpr (kMode == kModeTiled) {
@@ -655,11 +676,11 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
           const int col = col0 + c * 32;
           // warp-uniform; a bf16 box covers a 64-column pair, stored when its first half is live
           // (columns past N are clipped by the TMA store)
-          const bool live = (!kTf32 && p.c_bf16) ? (n0 + (col & ~63) < p.N) : (n0 + col < p.N);
+          const bool live = (!kTf32 && p.c_bf16) ? (n0 + (col & ~63) < e_N) : (n0 + col < e_N);
           // bias: uniform (same address in every lane) 16-byte loads served by L1
           float bv[32];
-          if (p.bias != nullptr && n0 + col + 32 <= p.N) {
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + col);
+          if (e_bias != nullptr && n0 + col + 32 <= e_N) {
+            const float4* bp = reinterpret_cast<const float4*>(e_bias + n0 + col);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 f = __ldg(bp + j);
@@ -668,7 +689,7 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              bv[j] = (p.bias != nullptr && n0 + col + j < p.N) ? __ldg(p.bias + n0 + col + j) : 0.f;
+              bv[j] = (e_bias != nullptr && n0 + col + j < e_N) ? __ldg(e_bias + n0 + col + j) : 0.f;
           }
           tmem_ld_wait();
           if (c + 1 < kChunks) {
@@ -686,18 +707,19 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               float x = __uint_as_float(r[c & 1][j]) + bv[j];
-              x = apply_act<kAct>(x, p.act);
+              if (kGroup && prob2) x = apply_act<kGroup ? kAct2 : kAct>(x, p.act);
+              else x = apply_act<kAct>(x, p.act);
               v[j] = p.round_c ? round_tf32(x) : x;
             }
             if (!kTf32 && p.c_bf16) {
               static_assert(kTf32 || kChunks % 2 == 0, "bf16 boxes need an even number of chunks per warp");
               stager.template put_bf16<Cfg::kStageBufs - 1>(stager.buf, v, c & 1);
               if (c & 1) {
-                stager.flush_bf16(stager.buf, &p.tmC, n0 + col - 32, m0 + q * 32);
+                stager.flush_bf16(stager.buf, e_tmC, n0 + col - 32, m0 + q * 32);
                 if (Cfg::kStageBufs == 2) stager.buf ^= 1;
               }
             } else {
-              stager.store(&p.tmC, v, n0 + col, m0 + q * 32);
+              stager.store(e_tmC, v, n0 + col, m0 + q * 32);
             }
           }
         }

@@ -165,10 +165,13 @@ class MyBranchformerEncoderLayer(torch.nn.Module):
                             float(wp2.bias.double() + wp2.weight.double().reshape(-1) @ p2.bias.double())]))
             # the two branches are independent until the merge: with TAVSR_BRANCH_FORK=1 the cgMLP
             # chain runs on a side stream (a fork / join in the CUDA graph)
+            pre = engine.branch_projections(xa, xm, self.attn, self.cgmlp, self._packed)
+            qkv, g = pre if pre is not None else (None, None)
             with engine.branch_fork(dev) as side:
                 with side:
-                    u = engine.cgmlp_gated(xm, self.cgmlp, B, T, self._packed, "conv")
-                ctx = engine.attention_ctx(xa, self.attn, pos_proj, lens, B, T, self._packed, "qkv")
+                    u = engine.cgmlp_gated(xm, self.cgmlp, B, T, self._packed, "conv", g=g)
+                ctx = engine.attention_ctx(xa, self.attn, pos_proj, lens, B, T, self._packed, "qkv",
+                                           qkv=qkv)
             if learned:
                 sc = fv["sc"]
                 if engine.FUSE_SCORES and ctx.shape[1] == 256 and u.shape[1] == 1024 and T <= 2048:

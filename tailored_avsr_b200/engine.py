@@ -274,10 +274,28 @@ def qkv_weights(attn, cache: PackedCache, key: str):
         torch.cat([attn.linear_q.bias, attn.linear_k.bias, attn.linear_v.bias], 0).contiguous()))
 
 
-def attention_ctx(xa, attn, pos_proj, lens, B, T, cache: PackedCache, key: str):
+# the fused QKV projection and channel_proj1 + GELU of a two-branch block as one grouped launch
+GROUP_PROJ = os.environ.get("TAVSR_GROUP_PROJ", "1") != "0"
+
+
+def branch_projections(xa, xm, attn, cgmlp, cache: PackedCache):
+    """(qkv, g) = (xa Wqkv^T + b, gelu(xm Wc1^T + bc1)) - one grouped launch when the mode allows
+    (tf32 / bf16, equal input widths), else None (the callers then project separately)."""
+    if not GROUP_PROJ or _DTYPE == "tf32x3":
+        return None
+    lin = cgmlp.channel_proj1[0]
+    wqkv, bqkv = qkv_weights(attn, cache, "qkv")
+    if xa.shape != xm.shape or wqkv.shape[1] != lin.weight.shape[1]:
+        return None
+    return ops.gemm_group2(xa, cache.weight("qkv.w", wqkv), bqkv, xm, cache.weight("conv.p1", lin.weight),
+                           lin.bias, out_dtype=act_dtype())
+
+
+def attention_ctx(xa, attn, pos_proj, lens, B, T, cache: PackedCache, key: str, qkv=None):
     """Fused QKV projection + rel-pos attention; returns ctx (B*T, d) in operand storage."""
-    wqkv, bqkv = qkv_weights(attn, cache, key)
-    qkv = linear(xa, wqkv, bqkv, cache, key + ".w", out_dtype=act_dtype())
+    if qkv is None:
+        wqkv, bqkv = qkv_weights(attn, cache, key)
+        qkv = linear(xa, wqkv, bqkv, cache, key + ".w", out_dtype=act_dtype())
     u = attn.pos_bias_u.reshape(-1)
     v = attn.pos_bias_v.reshape(-1)
     return ops.relpos_attn(qkv, pos_proj, u, v, lens, B, T, attn.h)
@@ -290,14 +308,16 @@ def pos_projection(attn, pos_emb: torch.Tensor, cache: Optional[PackedCache] = N
     return linear(pe, attn.linear_pos.weight, None, cache, f"wpos1_{id(attn)}", out_dtype=act_dtype())
 
 
-def cgmlp_gated(xm, cgmlp, B, T, cache: PackedCache, key: str):
-    """channel_proj1 + GELU + CSGU; returns u (B*T, C/2) ready for channel_proj2."""
+def cgmlp_gated(xm, cgmlp, B, T, cache: PackedCache, key: str, g=None):
+    """channel_proj1 + GELU + CSGU; returns u (B*T, C/2) ready for channel_proj2 (`g`: the
+    GELU'd projection when the grouped launch already produced it)."""
     if cgmlp.csgu.linear is not None or cgmlp.csgu.gate_activation != "identity":
         raise NotImplementedError("use_linear_after_conv / non-identity gate_activation are not "
                                   "built on the B200 path (no shipped config uses them)")
     lin = cgmlp.channel_proj1[0]
     conv = cgmlp.csgu.conv
     cw = cache.get(key, [conv.weight], lambda: conv.weight.reshape(conv.weight.shape[0], -1).contiguous())
-    g = linear(xm, lin.weight, lin.bias, cache, key + ".p1", act=ops.ACT_GELU, out_dtype=act_dtype())
+    if g is None:
+        g = linear(xm, lin.weight, lin.bias, cache, key + ".p1", act=ops.ACT_GELU, out_dtype=act_dtype())
     return ops.csgu(g, cgmlp.csgu.norm.weight, cgmlp.csgu.norm.bias, cw, conv.bias, B, T,
                     eps=cgmlp.csgu.norm.eps)

@@ -18,7 +18,7 @@ from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, ACT_SWISH, DT_BF16, DT_LNA_BF16
 
 __all__ = [
     "ACT_NONE", "ACT_SWISH", "ACT_GELU", "ACT_RELU",
-    "gemm_bias_act", "conv2d_sub_im2col", "merge_weights2", "scale_add_rows", "cast_bf16", "split_tf32", "gemm_rowln", "ffn_fused", "layernorm", "relpos_attn", "csgu", "merge_weights", "merge_scores", "merge_weights_dev",
+    "gemm_bias_act", "gemm_group2", "conv2d_sub_im2col", "merge_weights2", "scale_add_rows", "cast_bf16", "split_tf32", "gemm_rowln", "ffn_fused", "layernorm", "relpos_attn", "csgu", "merge_weights", "merge_scores", "merge_weights_dev",
     "ctc_head", "ctc_head_bwd", "vocab_residual", "row_dots", "ctc_loss", "ctc_greedy", "ctc_prefix_score", "launch_count",
 ]
 
@@ -135,6 +135,31 @@ def gemm_bias_act(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]
                                   out.data_ptr(), out.stride(0), M, N, K, act, int(round_out),
                                   dt, _stream()), "tavsr_gemm_bias_act")
     return out
+
+
+@_profiled
+def gemm_group2(x1: torch.Tensor, w1: torch.Tensor, b1: Optional[torch.Tensor], x2: torch.Tensor,
+                w2: torch.Tensor, b2: Optional[torch.Tensor],
+                out_dtype: Optional[torch.dtype] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(x1 @ w1.T + b1, gelu(x2 @ w2.T + b2)) in one launch (tavsr_gemm_group2): the fused QKV
+    projection and channel_proj1 + GELU of a two-branch block."""
+    bf16 = x1.dtype == torch.bfloat16
+    for t, n in ((x1, "x1"), (x2, "x2"), (w1, "w1"), (w2, "w2")):
+        _chk2d(t, n, x1.dtype)
+    M, K = x1.shape
+    if x2.shape != (M, K):
+        raise _lib.TavsrError("gemm_group2: both problems must share M and K")
+    _chk_k(w1, K, "gemm_group2 (w1)")
+    _chk_k(w2, K, "gemm_group2 (w2)")
+    odt = out_dtype or torch.float32
+    y1 = torch.empty((M, w1.shape[0]), device=x1.device, dtype=odt)
+    y2 = torch.empty((M, w2.shape[0]), device=x1.device, dtype=odt)
+    dt = (DT_BF16 if bf16 else DT_TF32) | (DT_OUT_BF16 if odt == torch.bfloat16 else 0)
+    check(_lib.load().tavsr_gemm_group2(
+        x1.data_ptr(), x1.stride(0), w1.data_ptr(), w1.stride(0), _p(b1), y1.data_ptr(), y1.stride(0),
+        w1.shape[0], x2.data_ptr(), x2.stride(0), w2.data_ptr(), w2.stride(0), _p(b2), y2.data_ptr(),
+        y2.stride(0), w2.shape[0], M, K, dt, _stream()), "tavsr_gemm_group2")
+    return y1, y2
 
 
 def _fill_rowln(a: RowLNArgs, M: int, bias, residual, alpha, ln0, eps0, out_main, round_main, lnA,

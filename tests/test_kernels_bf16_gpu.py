@@ -326,3 +326,25 @@ def test_merge_scores_cluster_kernel_equals_row_dots_plus_merge_weights(dt, B, T
     ref = torch.softmax(torch.stack(om, dim=-1), dim=-1)
     assert float((w1.double().cpu() - ref[:, 0]).abs().max()) < 2e-5
     assert float((w2.double().cpu() - ref[:, 1]).abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize("dt", [torch.float32, BF])
+@pytest.mark.parametrize("M", [8000, 300, 1992])
+def test_gemm_group2_equals_the_two_projections(dt, M):
+    """The grouped launch (QKV projection without activation + channel_proj1 with GELU over one tile
+    schedule) returns exactly what the two stand-alone GEMMs return."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(M)
+    K, N1, N2 = 256, 768, 2048
+    x1 = torch.randn(M, K, generator=g).to(DEV).to(dt)
+    x2 = torch.randn(M, K, generator=g).to(DEV).to(dt)
+    w1 = (torch.randn(N1, K, generator=g) / 16).to(DEV).to(dt)
+    w2 = (torch.randn(N2, K, generator=g) / 16).to(DEV).to(dt)
+    b1, b2 = torch.randn(N1, generator=g).to(DEV), torch.randn(N2, generator=g).to(DEV)
+    y1, y2 = ops.gemm_group2(x1, w1, b1, x2, w2, b2, out_dtype=dt)
+    r1 = ops.gemm_bias_act(x1, w1, b1, act=ops.ACT_NONE, out_dtype=dt)
+    r2 = ops.gemm_bias_act(x2, w2, b2, act=ops.ACT_GELU, out_dtype=dt)
+    assert y1.dtype == dt and y2.dtype == dt
+    assert torch.equal(y1, r1) and torch.equal(y2, r2)
+    ref2 = F.gelu(x2.double() @ w2.double().t() + b2.double())
+    assert rel_fro(y2, ref2) < (OUT_BF16_FRO if dt == BF else 2e-3)
