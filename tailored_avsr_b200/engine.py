@@ -275,7 +275,7 @@ def qkv_weights(attn, cache: PackedCache, key: str):
 
 
 # the fused QKV projection and channel_proj1 + GELU of a two-branch block as one grouped launch
-GROUP_PROJ = os.environ.get("TAVSR_GROUP_PROJ", "1") != "0"
+GROUP_PROJ = os.environ.get("TAVSR_GROUP_PROJ", "0") != "0"   # measured neutral at C2 (2.431 vs 2.427 ms): opt-in
 
 
 def branch_projections(xa, xm, attn, cgmlp, cache: PackedCache):
