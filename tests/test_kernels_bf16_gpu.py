@@ -348,3 +348,29 @@ def test_gemm_group2_equals_the_two_projections(dt, M):
     assert torch.equal(y1, r1) and torch.equal(y2, r2)
     ref2 = F.gelu(x2.double() @ w2.double().t() + b2.double())
     assert rel_fro(y2, ref2) < (OUT_BF16_FRO if dt == BF else 2e-3)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, BF])
+@pytest.mark.parametrize("B,T", [(2, 64), (3, 100), (2, 250), (1, 7)])
+def test_csgu_onepass_cluster_kernel_matches_the_two_kernel_sequence(dt, B, T):
+    """Debug knob 10: LayerNorm statistics from the convolution's own tile (8-CTA cluster, DSMEM
+    partials, Chan combine) - same output and the same (mean, rstd) as the two-kernel sequence."""
+    from tailored_avsr_b200 import _lib
+    ops = _ops()
+    Ch = 1024
+    g = torch.Generator().manual_seed(B * T)
+    h = torch.randn(B * T, 2 * Ch, generator=g).to(DEV).to(dt)
+    ng, nb = torch.randn(Ch, generator=g).to(DEV), torch.randn(Ch, generator=g).to(DEV)
+    cw = (torch.randn(Ch, 31, generator=g) * 0.2).to(DEV)
+    cb = torch.randn(Ch, generator=g).to(DEV)
+    st_a = torch.empty(B * T, 2, device=DEV)
+    st_b = torch.empty(B * T, 2, device=DEV)
+    want = ops.csgu(h, ng, nb, cw, cb, B, T, round_out=False, stats=st_a)
+    lib = _lib.load()
+    lib.tavsr_debug_set(10, 1)
+    try:
+        got = ops.csgu(h, ng, nb, cw, cb, B, T, round_out=False, stats=st_b)
+    finally:
+        lib.tavsr_debug_set(10, 0)
+    assert rel_fro(got, want) < (2e-3 if dt == BF else 1e-5), rel_fro(got, want)
+    assert max_rel(st_b, st_a) < 1e-5
