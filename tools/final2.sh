@@ -1,0 +1,29 @@
+#!/bin/bash
+# Round-2 evidence pass on ONE GPU box: tests, smoke, bench lines of every workload in both
+# compute modes, launch lists, one `ncu --set full` capture per mode of an eager C2 step.
+# usage: gpurun --timeout 2400 -- 'bash tools/final2.sh'
+O=gpurun_out/final_r02
+mkdir -p $O
+python -m pytest tests -m gpu -x -q 2>&1 | tail -2 | tee $O/pytest_gpu.txt
+python __graft_entry__.py --smoke 2>&1 | tail -1 | tee $O/smoke.txt
+python bench.py --steps 20 --warmup 5 2>$O/err_c2.log | tail -1 > $O/bench_c2_bf16_1gpu.json
+python bench.py --steps 20 --warmup 5 --dtype tf32 --no-cpu 2>>$O/err_c2.log | tail -1 > $O/bench_c2_tf32_1gpu.json
+python bench.py --steps 5 --warmup 2 --impl reference 2>>$O/err_c2.log | tail -1 > $O/bench_c2_reference_arm.json
+for w in C1 C3 C4; do for dt in bf16 tf32; do
+  python bench.py --workload $w --steps 20 --warmup 5 --no-cpu --no-extra --dtype $dt 2>$O/err_$w.log | tail -1 > $O/bench_${w}_${dt}_1gpu.json
+done; done
+for f in $O/bench_*_1gpu.json; do python -c "
+import json; d=json.load(open('$f')); print('$f', d['dtype'], round(d['value']), round(d['ms_per_step'],4), round(d['e2e']['value']), round(d['roofline']['frac'],4), round(d['roofline']['avg_launch_us'],1), d['roofline']['kernel'][:24])"; done | tee $O/bench_summary.txt
+K='regex:gemm_sm100|ffn_fused|csgu|ctc_|merge_|relpos|layernorm|vocab|row_dots|conv2d|scale_add|split_tf32'
+for dt in bf16 tf32; do
+  ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" --launch-skip 230 -c 230 --csv --log-file $O/launches_c2_$dt.csv python bench.py --steps 2 --warmup 1 --no-graph --no-cpu --no-extra --dtype $dt > /dev/null 2>&1
+  python tools/ncu_launches.py $O/launches_c2_$dt.csv > $O/launches_c2_${dt}_summary.txt
+  head -14 $O/launches_c2_${dt}_summary.txt
+  ncu --set full --clock-control none --import-source on -k "$K" --launch-skip 345 -c 115 -o $O/ncu_full_c2_$dt python bench.py --steps 2 --warmup 1 --no-graph --no-cpu --no-extra --dtype $dt > /dev/null 2>&1
+  ncu -i $O/ncu_full_c2_$dt.ncu-rep --page raw --csv > $O/ncu_full_c2_${dt}_raw.csv 2>/dev/null
+  python tools/ncu_summary.py $O/ncu_full_c2_${dt}_raw.csv > $O/ncu_full_c2_${dt}_summary.csv
+  head -12 $O/ncu_full_c2_${dt}_summary.csv
+done
+python tools/ncu_traffic.py bf16=$O/ncu_full_c2_bf16_raw.csv tf32=$O/ncu_full_c2_tf32_raw.csv > $O/r02_ncu_traffic.json
+cat $O/r02_ncu_traffic.json | head -30
+rm -f $O/*.ncu-rep   # keep the merged output small: the raw csv pages are what is read back
