@@ -1,4 +1,5 @@
-"""Time the rel-pos attention kernel at the C2 shape and print its in-kernel phase stamps."""
+"""Time the rel-pos attention kernel at the C2 shape in both compute modes and print the in-kernel
+phase stamps of the tf32 build (usage: python tools/time_attn.py)."""
 import sys
 
 import numpy as np
@@ -16,8 +17,15 @@ lens = torch.full((B,), T, dtype=torch.int32, device="cuda")
 lib = _lib.load()
 
 
+qkv16, pos16 = qkv.bfloat16(), pos.bfloat16()
+
+
 def attn():
     return ops.relpos_attn(qkv, pos[:, 256:512], u, v, lens, B, T, H, round_out=True)
+
+
+def attn16():
+    return ops.relpos_attn(qkv16, pos16[:, 256:512], u, v, lens, B, T, H)
 
 
 def t(fn, n=50):
@@ -38,12 +46,8 @@ def t(fn, n=50):
     return e0.elapsed_time(e1) / n * 1e3
 
 
-print("tcgen05 attention us", t(attn))
-lib.tavsr_debug_set(8, 1)
-print("mma.sync attention us", t(attn))
-lib.tavsr_debug_set(8, 0)
-lib.tavsr_debug_set(7, 1)
-print("tcgen05 attention, no PDL us", t(attn))
+print("tf32 attention us", t(attn))
+print("bf16 attention us", t(attn16))
 nblk = 2 * H * B
 dbg = torch.zeros(nblk * 16, dtype=torch.int64, device="cuda")
 lib.tavsr_debug_set_ptr(dbg.data_ptr())
@@ -51,7 +55,6 @@ attn(); torch.cuda.synchronize()
 dbg.zero_()
 attn(); torch.cuda.synchronize()
 lib.tavsr_debug_set_ptr(None)
-lib.tavsr_debug_set(7, 0)
 d = dbg.cpu().numpy().reshape(nblk, 16).astype(np.float64)
 t0 = d[:, 0].min()
 names = {0: "start", 1: "t0 k_full", 2: "t0 cu/cv done", 3: "t0 s_done", 4: "t0 pass1", 5: "t0 pass2+rescale",
