@@ -466,9 +466,11 @@ def profile_step(pipe, batch_dev, peaks, dtype, live_peaks):
 # --------------------------------------------------------------------------------------------------
 # extra legs of the GPU arm
 # --------------------------------------------------------------------------------------------------
-def train_leg(args, enc, ctc, rank, world, dev, dist, steps, warmup):
+def train_leg(args, enc, ctc, rank, world, dev, dist, steps, warmup, train_mode=True):
     """Training step of the workload (single-stream workloads): grad-mode encoder forward + CTC loss
-    / global batch + backward + overlapped bucketed gradient all-reduce, no optimizer.  Inputs come
+    / global batch + backward + overlapped bucketed gradient all-reduce, no optimizer.  The modules
+    are in train() mode: every dropout site of the reference is active at the configured rate (0.1
+    like the shipped YAMLs; `train_mode=False` times the same step in eval() mode).  Inputs come
     from pinned host memory every step and the loss is read back (inside the timed region).
     Returns a dict (rank 0) or None."""
     from tailored_avsr_b200 import engine, ops, parallel
@@ -478,6 +480,7 @@ def train_leg(args, enc, ctc, rank, world, dev, dist, steps, warmup):
                                "(MyBranchformerEncoder, ConventionalEncoder): run --workload C2"}
     prev = engine.compute_dtype()
     engine.set_compute_dtype("tf32")      # the training path stores fp32 and multiplies in TF32
+    enc.train(train_mode)
     host, frames = make_batch(rank)
     host = [t.pin_memory() for t in host]
     params = list(enc.parameters()) + list(ctc.parameters())
@@ -538,13 +541,19 @@ def train_leg(args, enc, ctc, rank, world, dev, dist, steps, warmup):
     for p in params:
         p.grad = None
         p.requires_grad_(False)
+    enc.eval()
     engine.set_compute_dtype(prev)
     if rank != 0:
         return None
     nbytes = sum(red.bucket_bytes())
+    rates = sorted({float(m.p) for m in enc.modules() if isinstance(m, torch.nn.Dropout)} |
+                   {float(getattr(m, "dropout_rate", 0.0)) for m in enc.modules()})
     return {
         "value": frames * steps * world / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
         "steps": steps, "warmup": max(1, warmup), "dtype": "tf32 (fp32 storage)",
+        "module_mode": ("train(): dropout active at every site of the reference, rates "
+                        f"{rates}; stochastic depth / branch drop as configured (0)") if train_mode
+                       else "eval(): no dropout",
         "step": "grad-mode encoder forward + CTC loss / global batch + backward + bucketed gradient "
                 "all-reduce (no optimizer); host inputs copied in and the loss read back every step",
         "global_batch": Bg, "scaling": "weak", "loss": loss_host,
@@ -570,6 +579,7 @@ def train_graph_leg(args, enc, ctc, rank, world, dev, dist, steps, warmup):
         return None
     prev = engine.compute_dtype()
     engine.set_compute_dtype("tf32")
+    enc.train()                  # dropout active, masks drawn inside the capture (graph-safe generator)
     out = None
     params = list(enc.parameters()) + list(ctc.parameters())
     try:
@@ -655,6 +665,7 @@ def train_graph_leg(args, enc, ctc, rank, world, dev, dist, steps, warmup):
         for p in params:
             p.grad = None
             p.requires_grad_(False)
+        enc.eval()
         engine.set_compute_dtype(prev)
     return out if rank == 0 else None
 
@@ -916,6 +927,10 @@ def run_gpu_arm(args):
                                       warmup=2)
         if train is not None and train_graph is not None:
             train["cuda_graph_variant"] = train_graph
+        train_eval = train_leg(args, enc, ctc, rank, world, dev, dist, steps=max(2, args.train_steps // 2),
+                               warmup=1, train_mode=False)
+        if train is not None and train_eval is not None and "ms_per_step" in train_eval:
+            train["eval_mode_ms_per_step"] = train_eval["ms_per_step"]
 
     line = None
     if rank == 0:

@@ -219,6 +219,17 @@ int tavsr_relpos_attn_fwd(const void* qkv, long long ld_qkv, const void* pos, lo
                                         kept by the training forward for tavsr_relpos_attn_bwd */,
                           void* stream);
 
+/* Training forward with attention-probability dropout (espnet attention.py:
+ * `matmul(self.dropout(self.attn), value)`, active when attention_dropout_rate > 0 in train mode).
+ * fp32 / TF32 only.  drop_keep [(B*H*T), ld_drop] bytes: keep[b][h][i][j] != 0 keeps P_ij; ld_drop a
+ * multiple of 128 >= T; kept probabilities are scaled by drop_scale = 1 / (1 - p).  lse stays the
+ * log-sum-exp of the undropped scores. */
+int tavsr_relpos_attn_fwd_dropout(const float* qkv, long long ld_qkv, const float* pos,
+                                  long long ld_pos, const float* u, const float* v,
+                                  const int32_t* lens, float* ctx, long long ld_ctx, int B, int T,
+                                  int H, float* lse, const uint8_t* drop_keep, long long ld_drop,
+                                  float drop_scale, void* stream);
+
 /* Backward of the attention core (training).  Given dctx = d loss / d ctx, the forward's qkv, pos,
  * u, v, lens, ctx and lse (fp32), writes the k and v blocks of dqkv [B*T, 3*H*64] and ACCUMULATES
  * (fp32 atomics; zero them first) the two parts of d q into dq_ac / dq_bd [B*T, H*64]
@@ -230,7 +241,8 @@ int tavsr_relpos_attn_bwd(const float* qkv, long long ld_qkv, const float* pos, 
                           const float* u, const float* v, const int32_t* lens, const float* ctx,
                           long long ld_ctx, const float* dctx, long long ld_dctx, const float* lse,
                           float* dqkv, long long ld_dqkv, float* dq_ac, float* dq_bd, float* dpos,
-                          int B, int T, int H, void* stream);
+                          const uint8_t* drop_keep /* NULL, or the forward's keep mask */,
+                          long long ld_drop, float drop_scale, int B, int T, int H, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Convolutional spatial gating unit (espnet ConvolutionalSpatialGatingUnit.forward, reached through

@@ -15,9 +15,12 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import cases, gen_golden, reference_loader  # noqa: E402
+from oracle import cases, dropmask, gen_golden, reference_loader  # noqa: E402
 
 CASES = ["vsr_small", "asr_tailored_small", "vsr_tailored_small", "concat_small"]
+# train() mode with every dropout site active (rates of the case's config, 0.1 like the shipped
+# YAMLs), masks from oracle/dropmask.py::MaskSource(GOLDEN_SEED): grad_<case>_dropout.npz
+DROPOUT_CASES = ["vsr_small", "vsr_tailored_small", "concat_small"]
 
 
 def summarize(named_grads):
@@ -32,20 +35,30 @@ def summarize(named_grads):
 
 def main():
     ref = reference_loader.load()
-    for name in CASES:
+    for name, drop in [(n, False) for n in CASES] + [(n, True) for n in DROPOUT_CASES]:
         c = cases.CASES[name]
         inp = cases.make_inputs(name)
         enc, ctc, _ = gen_golden.build_reference(ref, name)
         x = inp["x"].clone().requires_grad_(True)
-        y, olens, _ = enc(x, inp["lens"])
-        tl = cases.target_lens(name, olens)
-        loss = ctc(y, olens, inp["ys_pad"], tl)
+        src = dropmask.MaskSource(dropmask.GOLDEN_SEED)
+        if drop:
+            enc.train()
+        with dropmask.patched_dropout(src):
+            y, olens, _ = enc(x, inp["lens"])
+            tl = cases.target_lens(name, olens)
+            loss = ctc(y, olens, inp["ys_pad"], tl)
         loss.backward()
+        if drop:
+            print(name, "dropout sites:", len(src.calls), src.calls[:14])
+            name = name + "_dropout"
         grads = [("enc." + n, p.grad) for n, p in enc.named_parameters() if p.grad is not None]
         grads += [("ctc." + n, p.grad) for n, p in ctc.named_parameters()]
         grads.append(("input", x.grad))
         out = summarize(grads)
         out["loss"] = np.array(float(loss))
+        if drop:
+            out["n_masks"] = np.array(len(src.calls))
+            out["out_sample"] = y.detach().double().reshape(-1)[::97][:64].numpy()
         np.savez_compressed(os.path.join(ROOT, "tests", "golden", f"grad_{name}.npz"), **out)
         print(name, float(loss), len(grads), "gradients")
 

@@ -82,10 +82,14 @@ SIGNATURES = {
     "tavsr_relpos_attn_fwd": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int,
                                       c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tavsr_relpos_attn_fwd_dropout": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p,
+                                              c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int,
+                                              c_int, c_void_p, c_void_p, c_longlong, c_float,
+                                              c_void_p]),
     "tavsr_relpos_attn_bwd": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_longlong, c_void_p, c_longlong, c_void_p,
-                                      c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_int,
-                                      c_int, c_int, c_void_p]),
+                                      c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_longlong, c_float, c_int, c_int, c_int, c_void_p]),
     "tavsr_act_fwd": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int,
                               c_int, c_int, c_void_p]),
     "tavsr_merge_learned_ave_weights2": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p,

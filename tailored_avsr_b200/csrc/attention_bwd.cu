@@ -60,6 +60,11 @@ struct Params {
   float* dqkv; long long ld_dqkv;       // [B*T, 3*H*64]: k and v blocks written here
   float* dq_ac; float* dq_bd;           // [B*T, H*64] each, zero-initialised, atomically accumulated
   float* dpos;                          // [2T-1, H*64] zero-initialised, atomically accumulated
+  // attention-probability dropout of the forward (optional): keep[b][h][i][j] bytes, row pitch
+  // ld_drop, kept probabilities scaled by drop_scale.  With m_ij = keep_ij * drop_scale:
+  //   o_i = sum_j m_ij P_ij v_j,  dP_ij = m_ij (do_i . v_j),  dv_j = sum_i m_ij P_ij do_i,
+  // and D_i = do_i . o_i = sum_j P_ij dP_ij still holds, so g keeps its form.
+  const uint8_t* drop_keep; long long ld_drop; float drop_scale;
   int T, H;
 };
 
@@ -246,8 +251,12 @@ relpos_attn_bwd_kernel(const Params p) {
         const float r = sR[ii * kLDR + jj - ii + (kT - 1)];
         const bool valid = (i0 + ii < T) && (j0 + jj < len);
         const float pr = valid ? exp2f((cs[a][c] + r) * scale2 - lse) : 0.f;
-        g[a][c] = pr * (ce[a][c] - Di) * scale;
-        sS[ii * kLD + jj] = pr;
+        float mk = 1.0f;
+        if (p.drop_keep != nullptr && valid)
+          mk = p.drop_keep[((static_cast<long long>(b) * H + h) * T + i0 + ii) * p.ld_drop + j0 + jj] != 0
+                   ? p.drop_scale : 0.f;
+        g[a][c] = pr * (ce[a][c] * mk - Di) * scale;
+        sS[ii * kLD + jj] = pr * mk;
         sdS[ii * kLD + jj] = g[a][c];
       }
     }
@@ -401,7 +410,8 @@ extern "C" int tavsr_relpos_attn_bwd(const float* qkv, long long ld_qkv, const f
                                      const int32_t* lens, const float* ctx, long long ld_ctx,
                                      const float* dctx, long long ld_dctx, const float* lse,
                                      float* dqkv, long long ld_dqkv, float* dq_ac, float* dq_bd,
-                                     float* dpos, int B, int T, int H, void* stream) {
+                                     float* dpos, const uint8_t* drop_keep, long long ld_drop,
+                                     float drop_scale, int B, int T, int H, void* stream) {
   TAVSR_REQUIRE(B > 0 && T > 0 && H > 0, "attn_bwd: bad shape B=%d T=%d H=%d", B, T, H);
   TAVSR_REQUIRE(qkv && pos && u && v && ctx && dctx && lse && dqkv && dq_ac && dq_bd && dpos,
                 "attn_bwd: null pointer");
@@ -412,6 +422,9 @@ extern "C" int tavsr_relpos_attn_bwd(const float* qkv, long long ld_qkv, const f
   p.qkv = qkv; p.ld_qkv = ld_qkv; p.pos = pos; p.ld_pos = ld_pos; p.u = u; p.v = v; p.lens = lens;
   p.o = ctx; p.ld_o = ld_ctx; p.dout = dctx; p.ld_do = ld_dctx; p.lse = lse;
   p.dqkv = dqkv; p.ld_dqkv = ld_dqkv; p.dq_ac = dq_ac; p.dq_bd = dq_bd; p.dpos = dpos;
+  TAVSR_REQUIRE(drop_keep == nullptr || (ld_drop >= T && drop_scale >= 1.0f),
+                "attn_bwd: keep mask pitch %lld < T or drop_scale < 1", ld_drop);
+  p.drop_keep = drop_keep; p.ld_drop = ld_drop; p.drop_scale = drop_scale;
   p.T = T; p.H = H;
   static unsigned long long configured = 0;
   if (first_use_on_device(configured))

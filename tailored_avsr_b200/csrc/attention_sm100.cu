@@ -81,6 +81,13 @@ struct Params {
   long long ld_ctx;
   int T, H, round_out;
   float* lse;      // optional [B, H, T]: base-2 log-sum-exp of the scaled scores (training forward)
+  // training only (tf32 kernel): attention-probability dropout, espnet attention.py
+  // `matmul(self.dropout(self.attn), value)`.  keep[b][h][i][j] != 0 keeps P_ij; the kept
+  // probabilities are scaled by drop_scale = 1 / (1 - p) (folded into the final 1 / l); the row
+  // sum and the log-sum-exp stay those of the undropped softmax.
+  const uint8_t* drop_keep;
+  long long ld_drop;  // row pitch in bytes, multiple of 16
+  float drop_scale;
   long long* dbg;  // optional phase timestamps (16 per CTA), tools/time_attn.py
 };
 
@@ -435,6 +442,18 @@ relpos_attn_tc_kernel(const __grid_constant__ Params p) {
             sum += pr;
             rs[e] = __float_as_uint(round_tf32(pr));
           }
+          if (p.drop_keep != nullptr && i0 + row < T) {
+            // keys kv0 + 32 c .. + 31 of this query row: 32 keep bytes (the pitch covers the
+            // last tile's overhang; masked keys are already zero)
+            const uint8_t* kp = p.drop_keep +
+                ((static_cast<long long>(b) * p.H + h) * T + i0 + row) * p.ld_drop + t * kKT + 32 * c;
+            const uint4 k0 = ld_act_u4(reinterpret_cast<const uint4*>(kp));
+            const uint4 k1 = ld_act_u4(reinterpret_cast<const uint4*>(kp) + 1);
+            const uint32_t kw[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (((kw[e >> 2] >> (8 * (e & 3))) & 0xffu) == 0u) rs[e] = 0u;
+          }
           tmem_st32(trow + kColS + 32 * c, rs);
         }
       }
@@ -487,7 +506,7 @@ relpos_attn_tc_kernel(const __grid_constant__ Params p) {
       s_sum[hf * 128 + row] = l_run;
       named_bar_sync(1, 256);
       const float l_tot = l_run + s_sum[(hf ^ 1) * 128 + row];
-      inv = 1.0f / l_tot;
+      inv = (p.drop_keep != nullptr ? p.drop_scale : 1.0f) / l_tot;
       if (p.lse != nullptr && hf == 0 && i < T)
         p.lse[(static_cast<long long>(b) * p.H + h) * T + i] = m_run + log2f(l_tot);
       mbar_wait(o_done, (n_kv - 1) & 1);
@@ -542,7 +561,8 @@ template <bool kBf16>
 static int relpos_attn_launch(const void* qkv, long long ld_qkv, const void* pos, long long ld_pos,
                               const float* u, const float* v, const int32_t* lens, void* ctx,
                               long long ld_ctx, int B, int T, int H, int round_out, float* lse,
-                              cudaStream_t s) {
+                              cudaStream_t s, const uint8_t* drop_keep = nullptr,
+                              long long ld_drop = 0, float drop_scale = 1.0f) {
   using C = attn_tc::Cfg<kBf16>;
   attn_tc::Params p;
   memset(&p, 0, sizeof(p));
@@ -562,6 +582,9 @@ static int relpos_attn_launch(const void* qkv, long long ld_qkv, const void* pos
   p.T = T;
   p.H = H;
   p.lse = lse;
+  p.drop_keep = drop_keep;
+  p.ld_drop = ld_drop;
+  p.drop_scale = drop_scale;
   p.dbg = reinterpret_cast<long long*>(g_debug_ptr);
   p.round_out = round_out ? 1 : 0;
   auto kern = attn_tc::relpos_attn_tc_kernel<kBf16>;
@@ -602,4 +625,26 @@ extern "C" int tavsr_relpos_attn_fwd(const void* qkv, long long ld_qkv, const vo
                                          round_out, lse, s)
               : relpos_attn_launch<false>(qkv, ld_qkv, pos, ld_pos, u, v, lens, ctx, ld_ctx, B, T, H,
                                           round_out, lse, s);
+}
+
+// Training forward with attention-probability dropout (tf32 storage): `drop_keep` is a (B, H, T)
+// x ld_drop byte matrix, keep[b][h][i][j] != 0 keeps P_ij, ld_drop a multiple of 128 >= T (a key
+// tile never crosses a row); kept probabilities are scaled by drop_scale = 1 / (1 - p).  `lse`
+// stays the log-sum-exp of the undropped scores, which is what tavsr_relpos_attn_bwd wants.
+extern "C" int tavsr_relpos_attn_fwd_dropout(const float* qkv, long long ld_qkv, const float* pos,
+                                             long long ld_pos, const float* u, const float* v,
+                                             const int32_t* lens, float* ctx, long long ld_ctx,
+                                             int B, int T, int H, float* lse,
+                                             const uint8_t* drop_keep, long long ld_drop,
+                                             float drop_scale, void* stream) {
+  TAVSR_REQUIRE(B > 0 && T > 0 && H > 0, "attn: bad shape B=%d T=%d H=%d", B, T, H);
+  TAVSR_REQUIRE(qkv && pos && u && v && ctx && drop_keep, "attn: null pointer");
+  TAVSR_REQUIRE(ld_qkv % 4 == 0 && ld_pos % 4 == 0 && ld_ctx % 4 == 0,
+                "attn: pitches must be multiples of 4 elements (16 bytes)");
+  TAVSR_REQUIRE(ld_drop % 128 == 0 && ld_drop >= T && (reinterpret_cast<uintptr_t>(drop_keep) & 15) == 0,
+                "attn: the keep mask needs a 16-byte aligned base and a row pitch that is a multiple "
+                "of 128 bytes >= T (got %lld)", ld_drop);
+  TAVSR_REQUIRE(drop_scale >= 1.0f, "attn: drop_scale = 1 / (1 - p) must be >= 1");
+  return relpos_attn_launch<false>(qkv, ld_qkv, pos, ld_pos, u, v, lens, ctx, ld_ctx, B, T, H, 0, lse,
+                                   static_cast<cudaStream_t>(stream), drop_keep, ld_drop, drop_scale);
 }

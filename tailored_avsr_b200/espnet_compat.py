@@ -94,6 +94,7 @@ class ConvolutionalSpatialGatingUnit(_Container):
         self.linear = torch.nn.Linear(n_channels, n_channels) if use_linear_after_conv else None
         self.gate_activation = gate_activation
         self.kernel_size = kernel_size
+        self.dropout_rate = dropout_rate
 
     def espnet_initialization_fn(self):
         torch.nn.init.normal_(self.conv.weight, std=1e-6)

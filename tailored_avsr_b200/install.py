@@ -8,6 +8,12 @@ adds to each task file
     install_asr(globals())
 
 and `avsr_main.py`, the YAML configs and checkpoints run unchanged.
+
+Training coverage of what gets installed (INTEGRATION.md "Training"): grad-mode calls are built for
+`branchformer` (front ends linear / None), `conventional` (without InterCTC) and CTC; the other
+classes are inference-only for now and raise NotImplementedError in grad mode rather than fall back.
+`only=` installs a subset, so a training run can keep the stock class where ours cannot train yet:
+`install_avsr(globals(), only=("conventional", "ctc"))`.
 """
 from __future__ import annotations
 
@@ -26,20 +32,43 @@ def _classes(registry):
     return classes
 
 
-def install_asr(namespace: dict) -> None:
-    """`namespace` is the globals() of src/tasks/asr.py."""
-    _classes(namespace["encoder_choices"])["branchformer"] = MyBranchformerEncoder
-    namespace["CTC"] = CTC
+ASR_PARTS = ("branchformer", "ctc")
+AVSR_PARTS = ("tailored", "conventional", "fusion", "embed", "ctc")
 
 
-def install_avsr(namespace: dict) -> None:
-    """`namespace` is the globals() of src/tasks/avsr.py."""
-    classes = _classes(namespace["encoder_choices"])
-    classes["tailored"] = TailoredEncoder
-    classes["conventional"] = ConventionalEncoder
-    # src/tasks/avsr.py:165-172: audiovisual_fusion_choices, key "adaptive"
-    _classes(namespace["audiovisual_fusion_choices"])["adaptive"] = AdaptiveAudioVisualFusion
-    # src/tasks/avsr.py:140-155: acoustic_embed_choices / visual_embed_choices, key "default"
-    _classes(namespace["acoustic_embed_choices"])["default"] = DefaultEmbeddingLayerForAVSR
-    _classes(namespace["visual_embed_choices"])["default"] = DefaultEmbeddingLayerForAVSR
-    namespace["CTC"] = CTC
+def _select(only, known):
+    if only is None:
+        return set(known)
+    unknown = set(only) - set(known)
+    if unknown:
+        raise ValueError(f"install: unknown part(s) {sorted(unknown)}; choose from {known}")
+    return set(only)
+
+
+def install_asr(namespace: dict, only=None) -> None:
+    """`namespace` is the globals() of src/tasks/asr.py; `only`: subset of ASR_PARTS."""
+    parts = _select(only, ASR_PARTS)
+    if "branchformer" in parts:
+        _classes(namespace["encoder_choices"])["branchformer"] = MyBranchformerEncoder
+    if "ctc" in parts:
+        namespace["CTC"] = CTC
+
+
+def install_avsr(namespace: dict, only=None) -> None:
+    """`namespace` is the globals() of src/tasks/avsr.py; `only`: subset of AVSR_PARTS."""
+    parts = _select(only, AVSR_PARTS)
+    if parts & {"tailored", "conventional"}:
+        classes = _classes(namespace["encoder_choices"])
+        if "tailored" in parts:
+            classes["tailored"] = TailoredEncoder
+        if "conventional" in parts:
+            classes["conventional"] = ConventionalEncoder
+    if "fusion" in parts:
+        # src/tasks/avsr.py:165-172: audiovisual_fusion_choices, key "adaptive"
+        _classes(namespace["audiovisual_fusion_choices"])["adaptive"] = AdaptiveAudioVisualFusion
+    if "embed" in parts:
+        # src/tasks/avsr.py:140-155: acoustic_embed_choices / visual_embed_choices, key "default"
+        _classes(namespace["acoustic_embed_choices"])["default"] = DefaultEmbeddingLayerForAVSR
+        _classes(namespace["visual_embed_choices"])["default"] = DefaultEmbeddingLayerForAVSR
+    if "ctc" in parts:
+        namespace["CTC"] = CTC

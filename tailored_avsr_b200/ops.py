@@ -303,10 +303,13 @@ def layernorm(x: torch.Tensor, gA: torch.Tensor, bA: torch.Tensor, eps: float = 
 @_profiled
 def relpos_attn(qkv: torch.Tensor, pos: torch.Tensor, u: torch.Tensor, v: torch.Tensor,
                 lens: Optional[torch.Tensor], B: int, T: int, H: int, round_out: bool = True,
-                out: Optional[torch.Tensor] = None, lse: Optional[torch.Tensor] = None):
+                out: Optional[torch.Tensor] = None, lse: Optional[torch.Tensor] = None,
+                drop: Optional[tuple] = None):
     """ctx = rel-pos MHSA(qkv) for (B*T, 3*H*64) fused projections (tavsr_relpos_attn_fwd); fp32
     qkv / pos -> fp32 ctx on TF32 MMAs, bf16 qkv / pos -> bf16 ctx on kind::f16 MMAs.  `lse`
-    (B, H, T) fp32, optional: receives the per-row log-sum-exp the backward recomputes P from."""
+    (B, H, T) fp32, optional: receives the per-row log-sum-exp the backward recomputes P from.
+    `drop` = (keep (B, H, T, Tp) uint8 with Tp a multiple of 128, scale = 1 / (1 - p)): training
+    forward with attention-probability dropout (tavsr_relpos_attn_fwd_dropout, fp32 only)."""
     _chk2d(qkv, "qkv", None)
     _chk2d(pos, "pos", qkv.dtype)
     if qkv.shape != (B * T, 3 * H * 64) or pos.shape != (2 * T - 1, H * 64) or u.numel() != H * 64 \
@@ -317,6 +320,17 @@ def relpos_attn(qkv: torch.Tensor, pos: torch.Tensor, u: torch.Tensor, v: torch.
             f"{tuple(qkv.shape)}, {tuple(pos.shape)}, {u.numel()}, {v.numel()}")
     if out is None:
         out = torch.empty((B * T, H * 64), device=qkv.device, dtype=qkv.dtype)
+    if drop is not None:
+        keep, scale = drop
+        if _is_bf16(qkv) or keep.dtype != torch.uint8 or keep.shape[:3] != (B, H, T) \
+                or not keep.is_contiguous():
+            raise _lib.TavsrError("relpos_attn: dropout needs fp32 operands and a contiguous uint8 "
+                                  f"keep mask (B, H, T, Tp); got {keep.dtype} {tuple(keep.shape)}")
+        check(_lib.load().tavsr_relpos_attn_fwd_dropout(
+            qkv.data_ptr(), qkv.stride(0), pos.data_ptr(), pos.stride(0), u.data_ptr(), v.data_ptr(),
+            _p(lens), out.data_ptr(), out.stride(0), B, T, H, _p(lse), keep.data_ptr(),
+            keep.shape[3], float(scale), _stream()), "tavsr_relpos_attn_fwd_dropout")
+        return out
     dt = (DT_BF16 | DT_OUT_BF16) if _is_bf16(qkv) else DT_TF32
     check(_lib.load().tavsr_relpos_attn_fwd(qkv.data_ptr(), qkv.stride(0), pos.data_ptr(),
                                             pos.stride(0), u.data_ptr(), v.data_ptr(), _p(lens),

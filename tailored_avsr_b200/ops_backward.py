@@ -66,8 +66,8 @@ def linear_bwd(x_in: torch.Tensor, w: torch.Tensor, dy: torch.Tensor, need_dx: b
 
 def relpos_attn_bwd(qkv: torch.Tensor, pos: torch.Tensor, u: torch.Tensor, v: torch.Tensor,
                     lens: Optional[torch.Tensor], ctx: torch.Tensor, dctx: torch.Tensor,
-                    lse: torch.Tensor, B: int, T: int, H: int):
-    """Backward of ops.relpos_attn (tavsr_relpos_attn_bwd).  Returns (dqkv (B*T, 3*H*64), dpos
+                    lse: torch.Tensor, B: int, T: int, H: int, drop: Optional[tuple] = None):
+    """Backward of ops.relpos_attn (tavsr_relpos_attn_bwd); `drop` = the forward's (keep, scale).  Returns (dqkv (B*T, 3*H*64), dpos
     (2T-1, H*64), du (H*64,), dv (H*64,)): d q = the two accumulated parts summed into dqkv's q
     block, the pos_bias gradients are the column sums of the parts."""
     from . import ops
@@ -81,8 +81,9 @@ def relpos_attn_bwd(qkv: torch.Tensor, pos: torch.Tensor, u: torch.Tensor, v: to
     check(_lib.load().tavsr_relpos_attn_bwd(
         qkv.data_ptr(), qkv.stride(0), pos.data_ptr(), pos.stride(0), u.data_ptr(), v.data_ptr(),
         _p(lens), ctx.data_ptr(), ctx.stride(0), dctx.data_ptr(), dctx.stride(0), lse.data_ptr(),
-        dqkv.data_ptr(), dqkv.stride(0), dq_ac.data_ptr(), dq_bd.data_ptr(), dpos.data_ptr(), B, T, H,
-        _stream()), "tavsr_relpos_attn_bwd")
+        dqkv.data_ptr(), dqkv.stride(0), dq_ac.data_ptr(), dq_bd.data_ptr(), dpos.data_ptr(),
+        drop[0].data_ptr() if drop is not None else None, drop[0].shape[3] if drop is not None else 0,
+        float(drop[1]) if drop is not None else 1.0, B, T, H, _stream()), "tavsr_relpos_attn_bwd")
     one = ops._cast_scalars(dev)[0]
     ops.scale_add_rows(dq_ac, dq_bd, one, one, M, out=dqkv[:, :HD])
     return dqkv, dpos, col_sums(dq_ac), col_sums(dq_bd)

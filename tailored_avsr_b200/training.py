@@ -25,10 +25,18 @@ kernels of ops_backward.py: dgrad / wgrad on the tcgen05 GEMM, LayerNorm / activ
 merge / rel-pos attention backward kernels.  Storage is fp32 and the products run on TF32 operands
 in every compute mode (the bf16 mode is an inference mode).
 
-Training-only randomness follows the reference's host RNG stream: stochastic depth draws
+Training-only randomness follows the reference's RNG streams: stochastic depth draws
 `torch.rand(1).item()` at layer entry (encoder_layer.py:180-182), attention-branch drop draws it
-inside the learned_ave merge (:233-239), in that order, layer by layer.  Dropout layers with p > 0
-are not built (every Dropout must be p = 0 or the module in eval mode): see README "Training".
+inside the learned_ave merge (:233-239), in that order, layer by layer (host RNG).  Dropout: every
+site of the reference is built - per block, in the reference's call order: FFN hidden and output
+(macaron), attention probabilities, x1, CSGU output, x2, merge output, FFN hidden and output
+(encoder_layer.py:194, 208-224, 228-306, 314 and the espnet leaves behind them); in the `linear`
+input layer the Dropout after its LayerNorm and the two of RelPositionalEncoding (x and pos_emb).
+Keep-masks are drawn per call from `torch.nn.functional.dropout` on a ones tensor of the
+reference's shape on the device - the same generator stream, kernel and shapes the reference's
+nn.Dropout modules consume - in that order, then applied by our kernels (elementwise keep * 1/(1-p)
+masks; the attention kernels take a byte keep-mask).  `set_dropout_source` swaps the generator for a
+deterministic one (tests: the same masks are injected into the live reference).
 """
 from __future__ import annotations
 
@@ -54,19 +62,39 @@ def wants_grad(module: torch.nn.Module, *tensors) -> bool:
     return any(p.requires_grad for p in module.parameters())
 
 
-def _no_dropout(module: torch.nn.Module, what: str) -> None:
-    """The parameter containers of espnet_compat.py record their dropout rates as `dropout_rate`
-    attributes (they own no Dropout module); torch.nn.Dropout modules are checked too."""
-    if not module.training:
-        return
-    for m in module.modules():
-        p = m.p if isinstance(m, torch.nn.Dropout) else getattr(m, "dropout_rate", 0.0)
-        if isinstance(p, (int, float)) and p > 0:
-            raise NotImplementedError(
-                f"tailored_avsr_b200 training path: {what} ({type(m).__name__}) has an active "
-                f"dropout rate {p}; only 0.0 is built (stochastic depth and attention-branch drop "
-                "are).  Set dropout_rate / attention_dropout_rate / positional_dropout_rate to 0.0 "
-                "in the YAML, or put the module in eval mode (gradients still flow).")
+_DROP_SOURCE = None
+
+
+def set_dropout_source(fn) -> None:
+    """fn(shape, p, device) -> fp32 mask of `shape` holding 0 or 1 / (1 - p); None restores the
+    default (torch's own dropout kernel on the device generator)."""
+    global _DROP_SOURCE
+    _DROP_SOURCE = fn
+
+
+def draw_mask(shape, p: float, device) -> Optional[torch.Tensor]:
+    """One dropout mask (already scaled by 1 / (1 - p)), or None when the site is inactive."""
+    if not p > 0:
+        return None
+    if p >= 1:
+        raise NotImplementedError("dropout with p >= 1 is not built")
+    if _DROP_SOURCE is not None:
+        return _DROP_SOURCE(tuple(shape), float(p), device).to(device=device, dtype=F32).contiguous()
+    return torch.nn.functional.dropout(torch.ones(tuple(shape), device=device, dtype=F32), float(p), True)
+
+
+def _mul(x: torch.Tensor, mask: Optional[torch.Tensor]) -> torch.Tensor:
+    """x * mask on our elementwise kernel (identity activation of tavsr_act_fwd)."""
+    return x if mask is None else ob.act_fwd(x, ops.ACT_NONE, mask=mask.view(x.shape))
+
+
+def _keep_bytes(mask: torch.Tensor, T: int) -> torch.Tensor:
+    """(B, H, T, T) scaled fp32 mask -> (B, H, T, Tp) uint8 keep flags, Tp = T rounded up to 128
+    (the layout tavsr_relpos_attn_fwd_dropout reads; host-side plumbing, once per layer call)."""
+    Tp = (T + 127) // 128 * 128
+    keep = torch.zeros(mask.shape[:3] + (Tp,), device=mask.device, dtype=torch.uint8)
+    keep[..., :T] = mask != 0
+    return keep
 
 
 def _named(layer: torch.nn.Module) -> Tuple[List[str], List[torch.nn.Parameter]]:
@@ -116,22 +144,42 @@ def _scalars(device):
 # ---------------------------------------------------------------------------------------------------
 # position-wise feed-forward (espnet PositionwiseFeedForward + the residual line around it)
 # ---------------------------------------------------------------------------------------------------
-def _ffn_forward(xn, ff, residual, out_main, lnA=None, out_lnA=None, lnB=None, out_lnB=None):
+def _residual_ln(residual, t, alpha: float, out_main, lnA=None, out_lnA=None, lnB=None, out_lnB=None):
+    """out_main = residual + alpha * t, then up to two LayerNorms of it: the un-fused form of the
+    row-complete GEMM epilogue, used where a dropout mask sits between the GEMM and the residual."""
+    dev = t.device
+    one = ops._cast_scalars(dev)[0]
+    a = _scalars(dev)[0] if alpha == 0.5 else torch.full((1,), float(alpha), device=dev)
+    ops.scale_add_rows(residual, t, one, a, max(1, t.shape[0]), out=out_main)
+    if lnA is not None:
+        if lnB is not None:
+            ops.layernorm(out_main, lnA[0], lnA[1], eps=1e-12, out=out_lnA, gB=lnB[0], bB=lnB[1],
+                          outB=out_lnB)
+        else:
+            ops.layernorm(out_main, lnA[0], lnA[1], eps=1e-12, out=out_lnA)
+
+
+def _ffn_forward(xn, ff, residual, out_main, lnA=None, out_lnA=None, lnB=None, out_lnB=None,
+                 mask_h=None, mask_o=None):
     act = engine.act_code(ff.activation_type)
     z = ops.gemm_bias_act(xn, ff.w_1.weight, ff.w_1.bias)
-    h = ob.act_fwd(z, act)
-    ops.gemm_rowln(h, ff.w_2.weight, ff.w_2.bias, residual=residual, alpha=0.5, out_main=out_main,
-                   lnA=lnA, out_lnA=out_lnA, lnB=lnB, out_lnB=out_lnB)
+    h = ob.act_fwd(z, act, mask=mask_h)
+    if mask_o is None:
+        ops.gemm_rowln(h, ff.w_2.weight, ff.w_2.bias, residual=residual, alpha=0.5, out_main=out_main,
+                       lnA=lnA, out_lnA=out_lnA, lnB=lnB, out_lnB=out_lnB)
+    else:
+        t = _mul(ops.gemm_bias_act(h, ff.w_2.weight, ff.w_2.bias), mask_o)
+        _residual_ln(residual, t, 0.5, out_main, lnA, out_lnA, lnB, out_lnB)
     return z
 
 
-def _ffn_backward(g, xn, z, ff, dout, prefix: str):
-    """dout = d loss / d (residual + 0.5 ffn(xn)); returns d loss / d xn."""
+def _ffn_backward(g, xn, z, ff, dout, prefix: str, mask_h=None, mask_o=None):
+    """dout = d loss / d (residual + 0.5 drop_o(ffn(xn))); returns d loss / d xn."""
     act = engine.act_code(ff.activation_type)
-    dhalf = _half(dout)
-    h = ob.act_fwd(z, act)                               # recomputed: only z is kept
+    dhalf = _mul(_half(dout), mask_o)
+    h = ob.act_fwd(z, act, mask=mask_h)                  # recomputed: only z is kept
     dh = _lin_bwd(g, h, ff.w_2.weight, dhalf, prefix + ".w_2.weight", prefix + ".w_2.bias")
-    dz = ob.act_bwd(z, dh, act)
+    dz = ob.act_bwd(z, _mul(dh, mask_h), act)
     return _lin_bwd(g, xn, ff.w_1.weight, dz, prefix + ".w_1.weight", prefix + ".w_1.bias")
 
 
@@ -144,6 +192,7 @@ def block_forward(L, aux, x: torch.Tensor) -> Tuple[torch.Tensor, dict]:
     dev = x.device
     new = lambda c=d: torch.empty((M, c), device=dev, dtype=F32)  # noqa: E731
     sv = {"x": x}
+    dm = aux.drop
     two = L.use_two_branches
     learned = two and L.merge_method == "learned_ave" and not aux.drop_attn
     # ---- macaron FFN ----
@@ -154,10 +203,11 @@ def block_forward(L, aux, x: torch.Tensor) -> Tuple[torch.Tensor, dict]:
     lnA = (L.norm_mha.weight, L.norm_mha.bias) if L.attn is not None else None
     lnB = (L.norm_mlp.weight, L.norm_mlp.bias) if L.cgmlp is not None else None
     if lnA is None:
-        sv["z1"] = _ffn_forward(sv["xn0"], L.feed_forward_macaron, x, x_a, lnA=lnB, out_lnA=xm)
+        sv["z1"] = _ffn_forward(sv["xn0"], L.feed_forward_macaron, x, x_a, lnA=lnB, out_lnA=xm,
+                                mask_h=dm.get("ffm_h"), mask_o=dm.get("ffm_o"))
     else:
         sv["z1"] = _ffn_forward(sv["xn0"], L.feed_forward_macaron, x, x_a, lnA=lnA, out_lnA=xa,
-                                lnB=lnB, out_lnB=xm)
+                                lnB=lnB, out_lnB=xm, mask_h=dm.get("ffm_h"), mask_o=dm.get("ffm_o"))
     sv.update(x_a=x_a, xa=xa, xm=xm)
     x1 = x2 = d1 = d2 = None
     # ---- attention branch ----
@@ -171,13 +221,19 @@ def block_forward(L, aux, x: torch.Tensor) -> Tuple[torch.Tensor, dict]:
         pp = ops.gemm_bias_act(aux.pos2d, A.linear_pos.weight, None)
         lse = torch.empty((B, A.h, T), device=dev, dtype=F32)
         ctx = ops.relpos_attn(qkv, pp, A.pos_bias_u.reshape(-1), A.pos_bias_v.reshape(-1), aux.lens,
-                              B, T, A.h, round_out=False, lse=lse)
+                              B, T, A.h, round_out=False, lse=lse, drop=dm.get("att"))
         x1 = new()
         dots = None
         if learned:
             d1 = torch.empty((M, 2), device=dev, dtype=F32)
             dots = (L.pooling_proj1.weight.reshape(-1), L.weight_proj1.weight.reshape(-1))
-        ops.gemm_rowln(ctx, A.linear_out.weight, A.linear_out.bias, out_main=x1, dots=dots, dots_out=d1)
+        if dm.get("x1") is None:
+            ops.gemm_rowln(ctx, A.linear_out.weight, A.linear_out.bias, out_main=x1, dots=dots, dots_out=d1)
+        else:   # x1 = dropout(linear_out(ctx)) (:212); the pooling scores are taken on the dropped x1
+            ops.gemm_rowln(ctx, A.linear_out.weight, A.linear_out.bias, out_main=x1)
+            x1 = _mul(x1, dm["x1"])
+            if learned:
+                d1 = ops.row_dots(x1, dots[0], dots[1])[0]
         sv.update(wqkv=wqkv, qkv=qkv, pp=pp, lse=lse, ctx=ctx, x1=x1)
     # ---- cgMLP branch ----
     if L.cgmlp is not None:
@@ -191,13 +247,20 @@ def block_forward(L, aux, x: torch.Tensor) -> Tuple[torch.Tensor, dict]:
         stats = torch.empty((M, 2), device=dev, dtype=F32)
         u = ops.csgu(hc, Cg.csgu.norm.weight, Cg.csgu.norm.bias, conv.weight.reshape(conv.weight.shape[0], -1),
                      conv.bias, B, T, eps=Cg.csgu.norm.eps, round_out=False, stats=stats)
+        u = _mul(u, dm.get("csgu"))                      # espnet cgmlp.py: dropout(x_r * x_g)
         x2 = new()
         dots = None
         if learned:
             d2 = torch.empty((M, 2), device=dev, dtype=F32)
             dots = (L.pooling_proj2.weight.reshape(-1), L.weight_proj2.weight.reshape(-1))
-        ops.gemm_rowln(u, Cg.channel_proj2.weight, Cg.channel_proj2.bias, out_main=x2, dots=dots,
-                       dots_out=d2)
+        if dm.get("x2") is None:
+            ops.gemm_rowln(u, Cg.channel_proj2.weight, Cg.channel_proj2.bias, out_main=x2, dots=dots,
+                           dots_out=d2)
+        else:
+            ops.gemm_rowln(u, Cg.channel_proj2.weight, Cg.channel_proj2.bias, out_main=x2)
+            x2 = _mul(x2, dm["x2"])
+            if learned:
+                d2 = ops.row_dots(x2, dots[0], dots[1])[0]
         sv.update(zc=zc, stats=stats, u=u, x2=x2)
     # ---- merge (:227-309) ----
     x_b, xf = new(), new()
@@ -218,22 +281,30 @@ def block_forward(L, aux, x: torch.Tensor) -> Tuple[torch.Tensor, dict]:
         else:
             w1 = torch.full((B,), 1.0 - L.cgmlp_weight, device=dev, dtype=F32)
             w2 = torch.full((B,), float(L.cgmlp_weight), device=dev, dtype=F32)
-        ops.gemm_rowln(x1, mp.weight, mp.bias, x2=x2, rowscale=(w1, w2), rows_per_seg=T, residual=x_a,
-                       alpha=aux.stoch, out_main=x_b, lnA=lnF, out_lnA=xf)
+        if dm.get("merge") is None:
+            ops.gemm_rowln(x1, mp.weight, mp.bias, x2=x2, rowscale=(w1, w2), rows_per_seg=T,
+                           residual=x_a, alpha=aux.stoch, out_main=x_b, lnA=lnF, out_lnA=xf)
+        else:
+            msrc = ops.scale_add_rows(x1, x2, w1, w2, T)
         sv.update(w1=w1, w2=w2)
     elif two:   # concat
-        cat = torch.cat([x1, x2], 1)
-        ops.gemm_rowln(cat, mp.weight, mp.bias, residual=x_a, alpha=aux.stoch, out_main=x_b, lnA=lnF,
-                       out_lnA=xf)
+        msrc = torch.cat([x1, x2], 1)
+        if dm.get("merge") is None:
+            ops.gemm_rowln(msrc, mp.weight, mp.bias, residual=x_a, alpha=aux.stoch, out_main=x_b,
+                           lnA=lnF, out_lnA=xf)
     else:
-        xs = x2 if L.attn is None else x1
-        ops.gemm_rowln(xs, mp.weight, mp.bias, residual=x_a, alpha=aux.stoch, out_main=x_b, lnA=lnF,
-                       out_lnA=xf)
+        msrc = x2 if L.attn is None else x1
+        if dm.get("merge") is None:
+            ops.gemm_rowln(msrc, mp.weight, mp.bias, residual=x_a, alpha=aux.stoch, out_main=x_b,
+                           lnA=lnF, out_lnA=xf)
+    if dm.get("merge") is not None:   # x_b = x_a + c * dropout(merge_proj(.)) (:228-306)
+        t = _mul(ops.gemm_bias_act(msrc, mp.weight, mp.bias), dm["merge"])
+        _residual_ln(x_a, t, aux.stoch, x_b, lnF, xf)
     sv.update(x_b=x_b, xf=xf, learned=learned)
     # ---- FFN + norm_final ----
     y0, y = new(), new()
     sv["z2"] = _ffn_forward(xf, L.feed_forward, x_b, y0, lnA=(L.norm_final.weight, L.norm_final.bias),
-                            out_lnA=y)
+                            out_lnA=y, mask_h=dm.get("ff_h"), mask_o=dm.get("ff_o"))
     sv["y0"] = y0
     return y, sv
 
@@ -243,10 +314,12 @@ def block_backward(L, aux, sv: dict, dy: torch.Tensor) -> Tuple[torch.Tensor, Di
     M, d = B * T, L.size
     dev = dy.device
     g: Dict[str, torch.Tensor] = {}
+    dm = aux.drop
     two = L.use_two_branches
     # ---- norm_final, FFN, norm_ff ----
     dy0 = _ln_bwd(g, sv["y0"], L.norm_final, dy, "norm_final")
-    dxf = _ffn_backward(g, sv["xf"], sv["z2"], L.feed_forward, dy0, "feed_forward")
+    dxf = _ffn_backward(g, sv["xf"], sv["z2"], L.feed_forward, dy0, "feed_forward",
+                        mask_h=dm.get("ff_h"), mask_o=dm.get("ff_o"))
     dx_b = _ln_bwd(g, sv["x_b"], L.norm_ff, dxf, "norm_ff", dres=dy0)          # residual joins here
     # ---- merge ----
     mp = L.merge_proj
@@ -254,6 +327,7 @@ def block_backward(L, aux, sv: dict, dy: torch.Tensor) -> Tuple[torch.Tensor, Di
     if aux.stoch != 1.0:   # x_b = x_a + c * (merge_proj(m)): the projection sees c * dx_b
         c = torch.full((1,), float(aux.stoch), device=dev)
         dmo = ops.scale_add_rows(dx_b, dx_b, c, _scalars(dev)[1], M)
+    dmo = _mul(dmo, dm.get("merge"))
     x1, x2 = sv.get("x1"), sv.get("x2")
     dx1 = dx2 = None
     if two and L.merge_method in ("learned_ave", "fixed_ave"):
@@ -286,10 +360,11 @@ def block_backward(L, aux, sv: dict, dy: torch.Tensor) -> Tuple[torch.Tensor, Di
     # ---- attention branch ----
     if L.attn is not None:
         A = L.attn
+        dx1 = _mul(dx1, dm.get("x1"))
         dctx = _lin_bwd(g, sv["ctx"], A.linear_out.weight, dx1, "attn.linear_out.weight", "attn.linear_out.bias")
         dqkv, dpos, du, dv = ob.relpos_attn_bwd(sv["qkv"], sv["pp"], A.pos_bias_u.reshape(-1),
                                                 A.pos_bias_v.reshape(-1), aux.lens, sv["ctx"], dctx,
-                                                sv["lse"], B, T, A.h)
+                                                sv["lse"], B, T, A.h, drop=dm.get("att"))
         _acc(g, "attn.pos_bias_u", du.view(A.h, A.d_k))
         _acc(g, "attn.pos_bias_v", dv.view(A.h, A.d_k))
         # d linear_pos.weight = dpos^T . pos_emb (reduction over the 2T-1 relative positions)
@@ -305,8 +380,9 @@ def block_backward(L, aux, sv: dict, dy: torch.Tensor) -> Tuple[torch.Tensor, Di
     if L.cgmlp is not None:
         Cg = L.cgmlp
         lin, conv = Cg.channel_proj1[0], Cg.csgu.conv
-        du_ = _lin_bwd(g, sv["u"], Cg.channel_proj2.weight, dx2, "cgmlp.channel_proj2.weight",
-                       "cgmlp.channel_proj2.bias")
+        dx2 = _mul(dx2, dm.get("x2"))
+        du_ = _mul(_lin_bwd(g, sv["u"], Cg.channel_proj2.weight, dx2, "cgmlp.channel_proj2.weight",
+                            "cgmlp.channel_proj2.bias"), dm.get("csgu"))
         hc = ob.act_fwd(sv["zc"], ops.ACT_GELU)
         dhc, dng, dnb, dcw, dcb = ob.csgu_bwd(hc, Cg.csgu.norm.weight, Cg.csgu.norm.bias,
                                               conv.weight.reshape(conv.weight.shape[0], -1), conv.bias,
@@ -320,7 +396,8 @@ def block_backward(L, aux, sv: dict, dy: torch.Tensor) -> Tuple[torch.Tensor, Di
                        "cgmlp.channel_proj1.0.bias")
         dx_a = _ln_bwd(g, sv["x_a"], L.norm_mlp, dxm, "norm_mlp", dres=dx_a)
     # ---- macaron FFN ----
-    dxn0 = _ffn_backward(g, sv["xn0"], sv["z1"], L.feed_forward_macaron, dx_a, "feed_forward_macaron")
+    dxn0 = _ffn_backward(g, sv["xn0"], sv["z1"], L.feed_forward_macaron, dx_a, "feed_forward_macaron",
+                         mask_h=dm.get("ffm_h"), mask_o=dm.get("ffm_o"))
     dx = _ln_bwd(g, sv["x"], L.norm_ff_macaron, dxn0, "norm_ff_macaron", dres=dx_a)
     return dx, g
 
@@ -366,6 +443,20 @@ class _LayerNormFn(torch.autograd.Function):
         return dx, dg, db, None, None
 
 
+class _MaskFn(torch.autograd.Function):
+    """y = x * mask (a dropout site outside the blocks)."""
+
+    @staticmethod
+    def forward(ctx, x, mask):
+        ctx.save_for_backward(mask)
+        return _mul(x.contiguous(), mask)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (mask,) = ctx.saved_tensors
+        return _mul(dy.contiguous(), mask), None
+
+
 class _LinearFn(torch.autograd.Function):
     """y = x W^T + b on the tcgen05 GEMM (the `linear` input layer)."""
 
@@ -401,14 +492,46 @@ def make_aux(layer, B: int, T: int, lens: torch.Tensor, pos_emb: Optional[torch.
         pos2d = pos_emb.reshape(-1, pos_emb.shape[-1]).contiguous().float()
         pos2d_T = ob.transpose_2d(pos2d, pad=True)
     return SimpleNamespace(B=B, T=T, lens=lens, pos2d=pos2d, pos2d_T=pos2d_T, stoch=stoch,
-                           drop_attn=drop_attn)
+                           drop_attn=drop_attn, drop=draw_block_masks(layer, B, T, lens.device))
+
+
+def draw_block_masks(layer, B: int, T: int, device) -> Dict[str, object]:
+    """The dropout masks of one block, drawn in the reference's call order (module docstring).
+    Empty in eval mode or when every rate is 0."""
+    dm: Dict[str, object] = {}
+    if not layer.training:
+        return dm
+    d = layer.size
+    p_out = float(layer.dropout.p)
+
+    def site(key, shape, p):
+        m = draw_mask(shape, p, device)
+        if m is not None:
+            dm[key] = m
+
+    def ffn(tag, ff):
+        site(tag + "_h", (B, T, ff.w_1.out_features), float(ff.dropout_rate))
+        site(tag + "_o", (B, T, d), p_out)
+
+    ffn("ffm", layer.feed_forward_macaron)
+    if layer.attn is not None:
+        p_att = float(layer.attn.dropout_rate)
+        m = draw_mask((B, layer.attn.h, T, T), p_att, device)
+        if m is not None:
+            dm["att"] = (_keep_bytes(m, T), 1.0 / (1.0 - p_att))
+        site("x1", (B, T, d), p_out)
+    if layer.cgmlp is not None:
+        site("csgu", (B, T, layer.cgmlp.channel_proj2.in_features), float(layer.cgmlp.csgu.dropout_rate))
+        site("x2", (B, T, d), p_out)
+    site("merge", (B, T, d), p_out)
+    ffn("ff", layer.feed_forward)
+    return dm
 
 
 def run_block(layer, x2d: torch.Tensor, B: int, T: int, lens: torch.Tensor,
               pos_emb: Optional[torch.Tensor], shared_pos=None) -> torch.Tensor:
     """Training forward of one block on (B*T, d) activations, as an autograd node."""
     layer._check_supported()
-    _no_dropout(layer, type(layer).__name__)
     aux = make_aux(layer, B, T, lens, pos_emb if shared_pos is None else None)
     if aux is None:
         return x2d                                     # stochastic depth: the layer is skipped
@@ -436,12 +559,22 @@ def encoder_forward(enc, xs_pad, ilens, max_layer=None, masks=None):
         B, T, _ = xs.shape
         x = xs.reshape(B * T, d).contiguous().float()
     elif isinstance(enc.embed, torch.nn.Sequential):          # input_layer == "linear"
-        _no_dropout(enc.embed, "embed")
+        # Sequential(Linear, LayerNorm, Dropout(dropout_rate), RelPositionalEncoding): dropout, then
+        # x * sqrt(d), then the positional-encoding module's dropout on x and on pos_emb
+        # (encoder.py:125-128; espnet embedding.py RelPositionalEncoding.forward)
         B, T, Fd = x_in.shape
-        lin, ln = enc.embed[0], enc.embed[1]
+        lin, ln, pe = enc.embed[0], enc.embed[1], enc.embed[3]
         e0 = _LinearFn.apply(x_in.reshape(B * T, Fd).contiguous().float(), lin.weight, lin.bias)
         x = _LayerNormFn.apply(e0, ln.weight, ln.bias, ln.eps, math.sqrt(d))
-        pos_emb = enc.embed[3].pos_emb(T, dev)
+        pos_emb = pe.pos_emb(T, dev)
+        if enc.training:
+            for shape, p in (((B, T, d), float(enc.embed[2].p)), ((B, T, d), float(pe.dropout_rate))):
+                m = draw_mask(shape, p, dev)
+                if m is not None:
+                    x = _MaskFn.apply(x, m.view(B * T, d))
+            m = draw_mask(tuple(pos_emb.shape), float(pe.dropout_rate), dev)
+            if m is not None:
+                pos_emb = _mul(pos_emb.reshape(-1, d).contiguous().float(), m.view(-1, d)).view(pos_emb.shape)
     else:
         raise NotImplementedError("the training path has no backward for the conv2d front end yet "
                                   "(input_layer 'linear' and None are built): see README 'Training'")

@@ -137,6 +137,54 @@ def test_relpos_attention_bwd(B, T, lens):
     assert _rel(du, wu.reshape(-1)) < tol and _rel(dv, wvb.reshape(-1)) < tol
 
 
+@pytest.mark.parametrize("B,T,lens", [(2, 70, [70, 41]), (2, 250, [250, 130]), (1, 300, [300])])
+def test_relpos_attention_dropout_fwd_bwd(B, T, lens):
+    """Attention-probability dropout (espnet attention.py: matmul(dropout(attn), value)) inside the
+    training forward (tavsr_relpos_attn_fwd_dropout) and its backward, against fp64 autograd of the
+    dense formula with the same keep-mask."""
+    import math
+    from tailored_avsr_b200 import ops, ops_backward as ob, training
+    H, dk, pdrop = 4, 64, 0.1
+    g = torch.Generator().manual_seed(3 * T + B)
+    qkv = torch.randn(B * T, 3 * H * dk, generator=g)
+    pos = torch.randn(2 * T - 1, H * dk, generator=g)
+    u = torch.randn(H * dk, generator=g) * 0.5
+    v = torch.randn(H * dk, generator=g) * 0.5
+    dctx = torch.randn(B * T, H * dk, generator=g)
+    mask = (torch.rand(B, H, T, T, generator=g) >= pdrop).float() / (1 - pdrop)
+    lens_t = torch.tensor(lens, dtype=torch.int32)
+    drop = (training._keep_bytes(mask.to(DEV), T), 1.0 / (1 - pdrop))
+    assert drop[0].shape[3] % 128 == 0
+    lse = torch.empty(B, H, T, device=DEV)
+    ctx = ops.relpos_attn(qkv.to(DEV), pos.to(DEV), u.to(DEV), v.to(DEV), lens_t.to(DEV), B, T, H,
+                          round_out=False, lse=lse, drop=drop)
+    lse0 = torch.empty(B, H, T, device=DEV)
+    ops.relpos_attn(qkv.to(DEV), pos.to(DEV), u.to(DEV), v.to(DEV), lens_t.to(DEV), B, T, H,
+                    round_out=False, lse=lse0)
+    assert torch.equal(lse, lse0)          # the log-sum-exp is the undropped softmax's
+    dqkv, dpos, du, dv = ob.relpos_attn_bwd(qkv.to(DEV), pos.to(DEV), u.to(DEV), v.to(DEV),
+                                            lens_t.to(DEV), ctx, dctx.to(DEV), lse, B, T, H, drop=drop)
+    torch.cuda.synchronize()
+    # fp64 autograd reference
+    qkv_r = qkv.double().requires_grad_(True)
+    pos_r = pos.double().requires_grad_(True)
+    u_r, v_r = u.double().requires_grad_(True), v.double().requires_grad_(True)
+    q, k, vv = [t.view(B, T, H, dk).transpose(1, 2) for t in qkv_r.split(H * dk, dim=1)]
+    pp = pos_r.view(2 * T - 1, H, dk).transpose(0, 1)
+    qu = q + u_r.view(H, dk)[None, :, None, :]
+    qv = q + v_r.view(H, dk)[None, :, None, :]
+    idx = (T - 1 - torch.arange(T).unsqueeze(1) + torch.arange(T).unsqueeze(0))
+    sc = (qu @ k.transpose(-2, -1) + (qv @ pp.transpose(-2, -1)[None]).gather(-1, idx.expand(B, H, T, T)))
+    inv = (torch.arange(T)[None, :] >= lens_t.long()[:, None])[:, None, None, :]
+    P = torch.softmax((sc / math.sqrt(dk)).masked_fill(inv, float("-inf")), dim=-1).masked_fill(inv, 0.0)
+    o = ((P * mask.double()) @ vv).transpose(1, 2).reshape(B * T, H * dk)
+    o.backward(dctx.double())
+    tol = 5e-3
+    assert _rel(ctx, o.detach()) < 2e-3, _rel(ctx, o.detach())
+    assert _rel(dqkv, qkv_r.grad) < tol, _rel(dqkv, qkv_r.grad)
+    assert _rel(dpos, pos_r.grad) < tol and _rel(du, u_r.grad) < tol and _rel(dv, v_r.grad) < tol
+
+
 @pytest.mark.parametrize("M,N,K", [(8000, 2048, 256), (385, 256, 1024), (1000, 768, 256)])
 def test_linear_bwd_on_the_tcgen05_gemm(M, N, K):
     from tailored_avsr_b200 import ops_backward as ob
@@ -254,6 +302,67 @@ def test_encoder_training_gradients_match_reference(name):
             sample = g[:: max(1, g.numel() // 16)][:16].numpy()
             assert np.allclose(sample, gold["sample/" + n], rtol=2e-2,
                                atol=4 * GRAD_TOL * gn / max(1.0, g.numel() ** 0.5) + 1e-9), n
+
+
+@pytest.mark.parametrize("name", ["vsr_small", "vsr_tailored_small", "concat_small"])
+def test_encoder_training_with_dropout_matches_reference(name):
+    """a11 dropout: a train()-mode step with every dropout site of the reference active (rates 0.1
+    as in the shipped YAMLs) equals the REAL reference modules run with the same masks
+    (tests/golden/grad_<case>_dropout.npz, oracle/gen_golden_grad.py): masks come from
+    oracle/dropmask.MaskSource on both sides, call k of the source is the k-th dropout call of the
+    reference, so equality also pins the site order and shapes (embed dropout, the two of the
+    positional encoding, then per block FFN hidden / output, attention probabilities, x1, CSGU, x2,
+    merge, FFN hidden / output)."""
+    import numpy as np
+    from oracle import cases, dropmask
+    from tailored_avsr_b200 import training
+    from . import _util
+    gold = dict(np.load(os.path.join(_util.GOLDEN_DIR, f"grad_{name}_dropout.npz")))
+    enc, ctc, sd = _util.build_dropin(name)
+    enc, ctc = enc.to(DEV).train(), ctc.to(DEV).eval()
+    inp = cases.make_inputs(name)
+    src = dropmask.MaskSource(dropmask.GOLDEN_SEED)
+    training.set_dropout_source(src)
+    try:
+        x = inp["x"].to(DEV).requires_grad_(True)
+        y, olens, _ = enc(x, inp["lens"].to(DEV))
+        tl = cases.target_lens(name, olens.cpu())
+        loss = ctc(y, olens, inp["ys_pad"].to(DEV), tl.to(DEV))
+        loss.backward()
+        torch.cuda.synchronize()
+    finally:
+        training.set_dropout_source(None)
+    assert len(src.calls) == int(gold["n_masks"]), (len(src.calls), int(gold["n_masks"]))
+    ys = y.detach().double().cpu().reshape(-1)[::97][:64].numpy()
+    assert np.abs(ys - gold["out_sample"]).max() <= 2e-3 * np.abs(gold["out_sample"]).max()
+    assert abs(float(loss) - float(gold["loss"])) <= 2e-3 * abs(float(gold["loss"]))
+    grads = {"input": x.grad}
+    grads.update({"enc." + n: p.grad for n, p in enc.named_parameters()})
+    grads.update({"ctc." + n: p.grad for n, p in ctc.named_parameters()})
+    checked = 0
+    for key in gold:
+        if not key.startswith("norm/"):
+            continue
+        n = key[5:]
+        gn = float(gold[key])
+        if gn < 1e-6:
+            continue
+        g = grads[n].double().cpu().reshape(-1)
+        tol = SCALAR_TOL if g.numel() == 1 else GRAD_TOL
+        assert abs(float(g.norm()) - gn) <= 2 * tol * gn, (n, float(g.norm()), gn)
+        sample = g[:: max(1, g.numel() // 16)][:16].numpy()
+        assert np.allclose(sample, gold["sample/" + n], rtol=2e-2,
+                           atol=4 * GRAD_TOL * gn / max(1.0, g.numel() ** 0.5) + 1e-9), n
+        checked += 1
+    assert checked > 80
+    # the default source (torch's dropout kernel on the device generator) is seed-reproducible and
+    # actually drops: two seeds differ, one seed repeats
+    outs = []
+    for seed in (5, 5, 6):
+        torch.manual_seed(seed)
+        yy, _, _ = enc(inp["x"].to(DEV).requires_grad_(True), inp["lens"].to(DEV))
+        outs.append(yy.detach().clone())
+    assert torch.equal(outs[0], outs[1]) and not torch.equal(outs[0], outs[2])
 
 
 def test_training_stochastic_depth_and_branch_drop_follow_the_host_rng():

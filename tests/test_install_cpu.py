@@ -69,3 +69,20 @@ def test_install_rejects_a_namespace_without_registries():
         install.install_asr({})
     with pytest.raises(TypeError):
         install.install_asr({"encoder_choices": object(), "CTC": object})
+
+
+def test_install_only_selects_a_subset():
+    """A training run can keep the stock classes where the B200 path is inference-only."""
+    ns = {"encoder_choices": FakeClassChoices("encoder", {"tailored": _RefEncoder, "conventional": _RefEncoder}),
+          "audiovisual_fusion_choices": FakeClassChoices("audiovisual_fusion", {"adaptive": _RefEncoder}),
+          "acoustic_embed_choices": FakeClassChoices("acoustic_embed", {"default": _RefEncoder}),
+          "visual_embed_choices": FakeClassChoices("visual_embed", {"default": _RefEncoder}),
+          "CTC": object}
+    install.install_avsr(ns, only=("conventional", "ctc"))
+    assert ns["encoder_choices"].get_class("conventional") is ConventionalEncoder
+    assert ns["encoder_choices"].get_class("tailored") is _RefEncoder
+    assert ns["audiovisual_fusion_choices"].get_class("adaptive") is _RefEncoder
+    assert ns["acoustic_embed_choices"].get_class("default") is _RefEncoder
+    assert ns["CTC"] is CTC
+    with pytest.raises(ValueError):
+        install.install_asr({"encoder_choices": FakeClassChoices("encoder", {}), "CTC": object}, only=("nope",))
