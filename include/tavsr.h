@@ -85,6 +85,16 @@ int tavsr_gemm_group2(const void* x1, long long ldx1, const void* w1, long long 
                       long long ldx2, const void* w2, long long ldw2, const float* bias2, void* y2,
                       long long ldy2, int N2, int M, int K, int dtype, void* stream);
 
+/* Weight-gradient product (training): out[M, N] = A[M, K] . B[N, K]^T, fp32 storage, TF32 operands,
+ * for a long reduction axis K (all frames of the batch) and few output tiles: the library splits K
+ * over CTA pairs (partial tiles in `workspace`, tavsr_gemm_wgrad_workspace_bytes) and sums the
+ * partials in a fixed order (bit-reproducible).  dW = dY^T X is the call
+ * (A = dY^T [N_out, frames], B = X^T [N_in, frames], both from tavsr_transpose_2d). */
+size_t tavsr_gemm_wgrad_workspace_bytes(int M, int N, int K);
+int tavsr_gemm_wgrad(const float* a, long long lda, const float* b, long long ldb, float* out,
+                     long long ldo, int M, int N, int K, void* workspace, long long workspace_bytes,
+                     void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Row-complete GEMM, N == 256 (the model width): one thread owns one output row, so everything that
  * follows the projection in the reference layer is fused into the epilogue:

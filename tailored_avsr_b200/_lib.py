@@ -82,6 +82,9 @@ SIGNATURES = {
     "tavsr_relpos_attn_fwd": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int,
                                       c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tavsr_gemm_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "tavsr_gemm_wgrad": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong,
+                                 c_int, c_int, c_int, c_void_p, c_longlong, c_void_p]),
     "tavsr_relpos_attn_fwd_dropout": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p,
                                               c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int,
                                               c_int, c_void_p, c_void_p, c_longlong, c_float,

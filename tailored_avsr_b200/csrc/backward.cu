@@ -46,7 +46,7 @@ transpose_kernel(const float* __restrict__ in, long long ld_in, float* __restric
 // Column sums, two stages:  part[blk][c] = sum over the CTA's rows of a[r][c] (* b[r][c]),
 // then out[c] = sum_blk part[blk][c].  (bias gradients; LayerNorm d gamma with b = x_hat.)
 // ------------------------------------------------------------------------------------------------
-constexpr int kColRows = 256;  // rows per CTA
+constexpr int kColRows = 64;  // rows per CTA of the partial stage (250 x C/128 CTAs at M = 8000)
 
 __global__ void __launch_bounds__(128)
 col_sums_partial_kernel(const float* __restrict__ a, long long lda, const float* __restrict__ b,
@@ -57,24 +57,58 @@ col_sums_partial_kernel(const float* __restrict__ a, long long lda, const float*
   const int r0 = blockIdx.y * kColRows;
   if (c >= C) return;
   const int r1 = r0 + kColRows < R ? r0 + kColRows : R;
-  float s = 0.f;
-  for (int r = r0; r < r1; ++r) {
+  // eight independent row streams per thread: the loads of one pass are all in flight together
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int r = r0;
+  for (; r + 8 <= r1; r += 8) {
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = ld_act(a + static_cast<long long>(r + k) * lda + c);
+    if (b != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] *= ld_act(b + static_cast<long long>(r + k) * ldb + c);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] += v[k];
+  }
+  for (; r < r1; ++r) {
     float v = ld_act(a + static_cast<long long>(r) * lda + c);
     if (b != nullptr) v *= ld_act(b + static_cast<long long>(r) * ldb + c);
-    s += v;
+    s[0] += v;
   }
-  part[static_cast<long long>(blockIdx.y) * C + c] = s;
+  part[static_cast<long long>(blockIdx.y) * C + c] =
+      ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
 }
 
-__global__ void __launch_bounds__(128)
+// out[c] = sum_blk part[blk][c]: CTA = 32 columns x 32 row groups (a fixed summation tree, so the
+// result is bit-reproducible); the former one-thread-per-column loop took 93 us over 1000 partial
+// rows on four CTAs.
+__global__ void __launch_bounds__(1024)
 col_sums_reduce_kernel(const float* __restrict__ part, int nblk, float* __restrict__ out, int C) {
+  __shared__ float red[32][33];
   pdl_launch_dependents();
   pdl_wait();
-  const int c = blockIdx.x * 128 + threadIdx.x;
-  if (c >= C) return;
-  float s = 0.f;
-  for (int b = 0; b < nblk; ++b) s += ld_act(part + static_cast<long long>(b) * C + c);
-  out[c] = s;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (c < C) {
+    int b = ty;
+    for (; b + 96 < nblk; b += 128) {
+      s0 += ld_act(part + static_cast<long long>(b) * C + c);
+      s1 += ld_act(part + static_cast<long long>(b + 32) * C + c);
+      s2 += ld_act(part + static_cast<long long>(b + 64) * C + c);
+      s3 += ld_act(part + static_cast<long long>(b + 96) * C + c);
+    }
+    for (; b < nblk; b += 32) s0 += ld_act(part + static_cast<long long>(b) * C + c);
+  }
+  red[ty][tx] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) s += red[k][tx];
+    out[c] = s;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -548,7 +582,7 @@ extern "C" int tavsr_col_sums(const float* a, long long lda, const float* b, lon
   float* part = static_cast<float*>(workspace);
   TAVSR_CUDA_OK(launch_kernel(bwd::col_sums_partial_kernel, dim3((C + 127) / 128, nblk), dim3(128), 0,
                               s, 0, a, lda, b, ldb, part, R, C));
-  TAVSR_CUDA_OK(launch_kernel(bwd::col_sums_reduce_kernel, dim3((C + 127) / 128), dim3(128), 0, s, 0,
+  TAVSR_CUDA_OK(launch_kernel(bwd::col_sums_reduce_kernel, dim3((C + 31) / 32), dim3(1024), 0, s, 0,
                               static_cast<const float*>(part), nblk, out, C));
   g_launches.fetch_add(2, std::memory_order_relaxed);
   return 0;
@@ -613,7 +647,7 @@ extern "C" int tavsr_layernorm_bwd(const float* x, long long ldx, const float* g
 #undef TAVSR_LNB
   // [nblk][2 D] partials -> dgamma | dbeta (contiguous [2, D])
   const int slots = (M + bwd::kLnRowsPerWarp - 1) / bwd::kLnRowsPerWarp;
-  TAVSR_CUDA_OK(launch_kernel(bwd::col_sums_reduce_kernel, dim3((2 * D + 127) / 128), dim3(128), 0, s, 0,
+  TAVSR_CUDA_OK(launch_kernel(bwd::col_sums_reduce_kernel, dim3((2 * D + 31) / 32), dim3(1024), 0, s, 0,
                               static_cast<const float*>(part), slots, dgamma, 2 * D));
   g_launches.fetch_add(2, std::memory_order_relaxed);
   return 0;
@@ -691,9 +725,9 @@ extern "C" int tavsr_merge_learned_ave_bwd(const float* x1, long long ld1, const
   TAVSR_CUDA_OK(launch_kernel(bwd::merge_learned_ave_bwd_kernel, dim3(B), dim3(256),
                               static_cast<size_t>(smem), s, 0, p));
   // reduce the per-utterance partials over b: [B][1024] -> grads[0:1024], [B][4] -> grads[1024:1028]
-  TAVSR_CUDA_OK(launch_kernel(bwd::col_sums_reduce_kernel, dim3(8), dim3(128), 0, s, 0,
+  TAVSR_CUDA_OK(launch_kernel(bwd::col_sums_reduce_kernel, dim3(32), dim3(1024), 0, s, 0,
                               static_cast<const float*>(p.part), B, grads, 1024));
-  TAVSR_CUDA_OK(launch_kernel(bwd::col_sums_reduce_kernel, dim3(1), dim3(128), 0, s, 0,
+  TAVSR_CUDA_OK(launch_kernel(bwd::col_sums_reduce_kernel, dim3(1), dim3(1024), 0, s, 0,
                               static_cast<const float*>(p.part_s), B, grads + 1024, 4));
   g_launches.fetch_add(3, std::memory_order_relaxed);
   return 0;

@@ -37,6 +37,11 @@ struct alignas(64) GemmParams {
   CUtensorMap tmLnB;  // LayerNorm output B
   int M, N, K;
   int num_m_tiles, num_n_tiles;
+  // ---- tiled split-K (weight gradients: few output tiles, K = all frames): ksplit > 1 multiplies
+  // the unit count; split s reduces k-blocks [s * split_kb, ...) and stores its partial tile into
+  // slab s of the output map, i.e. at row s * slab_rows + m (slab_rows a multiple of the unit's
+  // rows); the slabs are summed by sum_slabs_kernel.  Bias is added by split 0 only. ----
+  int ksplit, split_kb, slab_rows;
   const float* bias;
   int act;
   int round_c;  // round main output to tf32 (output only feeds tensor-core GEMMs)
@@ -505,7 +510,9 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
   const int unit0 = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int unit_step = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const int n_per_m = p.num_n_tiles + (kGroup ? p.num_n_tiles2 : 0);   // tiles per row block
-  const int num_tiles = p.num_m_tiles * n_per_m;  // in units
+  const int tiles_mn = p.num_m_tiles * n_per_m;  // in units
+  const bool ksplit_on = kMode == kModeTiled && !kGroup && p.ksplit > 1;
+  const int num_tiles = ksplit_on ? tiles_mn * p.ksplit : tiles_mn;
   const int num_kb = (p.K + Cfg::kBlockK - 1) / Cfg::kBlockK;
 
   if (warp == 0 && lane == 0) {
@@ -554,16 +561,22 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
       int s = 0;
       uint32_t ph = 0;
       for (int tile = unit0; tile < num_tiles; tile += unit_step) {
-        const int m_blk = (tile / n_per_m) * kCtas + static_cast<int>(cta_rank);
-        int n_blk = tile % n_per_m;
+        const int split = ksplit_on ? tile / tiles_mn : 0;
+        const int t_mn = ksplit_on ? tile - split * tiles_mn : tile;
+        const int m_blk = (t_mn / n_per_m) * kCtas + static_cast<int>(cta_rank);
+        int n_blk = t_mn % n_per_m;
         const bool prob2 = kGroup && n_blk >= p.num_n_tiles;
         if (prob2) n_blk -= p.num_n_tiles;
         const CUtensorMap* tma_b = prob2 ? &p.tmB2 : &p.tmB;
         // RowLN: N is one tile, the unit's n index selects the K split instead
         const int b_row0 = (kMode == kModeRowLN ? 0 : n_blk * kBlockN) +
                            static_cast<int>(cta_rank) * Cfg::kBRows;
-        const int kb_cnt = kMode == kModeRowLN ? num_kb / p.num_n_tiles : num_kb;
-        const int kb_beg = kMode == kModeRowLN ? n_blk * kb_cnt : 0;
+        int kb_cnt = kMode == kModeRowLN ? num_kb / p.num_n_tiles : num_kb;
+        int kb_beg = kMode == kModeRowLN ? n_blk * kb_cnt : 0;
+        if (ksplit_on) {
+          kb_beg = split * p.split_kb;
+          kb_cnt = num_kb - kb_beg < p.split_kb ? num_kb - kb_beg : p.split_kb;
+        }
         for (int kb = kb_beg; kb < kb_beg + kb_cnt; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* st = s_stage + s * Cfg::kStageBytes;
@@ -606,7 +619,11 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
         mbar_wait(&tempty_bar[as], aph ^ 1);
         tc_fence_after_sync();
         const uint32_t d0 = tmem_base + as * Cfg::kAccCols;
-        const int kb_cnt = kMode == kModeRowLN ? num_kb / p.num_n_tiles : num_kb;
+        int kb_cnt = kMode == kModeRowLN ? num_kb / p.num_n_tiles : num_kb;
+        if (ksplit_on) {
+          const int kb_beg = (tile / tiles_mn) * p.split_kb;
+          kb_cnt = num_kb - kb_beg < p.split_kb ? num_kb - kb_beg : p.split_kb;
+        }
         for (int kb = 0; kb < kb_cnt; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after_sync();
@@ -652,13 +669,15 @@ gemm_sm100_kernel(const __grid_constant__ GemmParams p) {
     uint32_t aph = 0;
     int it = 0;
     for (int tile = unit0; tile < num_tiles; tile += unit_step, ++it) {
-      const int m_blk = (tile / n_per_m) * kCtas + static_cast<int>(cta_rank);
-      int n_blk = tile % n_per_m;
+      const int split = ksplit_on ? tile / tiles_mn : 0;
+      const int t_mn = ksplit_on ? tile - split * tiles_mn : tile;
+      const int m_blk = (t_mn / n_per_m) * kCtas + static_cast<int>(cta_rank);
+      int n_blk = t_mn % n_per_m;
       const bool prob2 = kGroup && n_blk >= p.num_n_tiles;   // warp-uniform
       if (prob2) n_blk -= p.num_n_tiles;
-      const int m0 = m_blk * Cfg::kBlockM;
+      const int m0 = m_blk * Cfg::kBlockM + (ksplit_on ? split * p.slab_rows : 0);
       const int n0 = n_blk * kBlockN;
-      const float* e_bias = prob2 ? p.bias2 : p.bias;
+      const float* e_bias = prob2 ? p.bias2 : (split == 0 ? p.bias : nullptr);
       const int e_N = prob2 ? p.N2 : p.N;
       const CUtensorMap* e_tmC = prob2 ? &p.tmC2 : &p.tmC;
       const uint32_t tacc = tmem_base + lane_off + as * Cfg::kAccCols;

@@ -41,6 +41,24 @@ def act_fwd(z: torch.Tensor, act: int, mask: Optional[torch.Tensor] = None,
     return out
 
 
+def gemm_wgrad(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """out (M, N) = a (M, K) . b (N, K)^T with the reduction axis split over the machine
+    (tavsr_gemm_wgrad): the weight-gradient product, K = frames of the batch."""
+    _chk2d(a, "a")
+    _chk2d(b, "b")
+    M, K = a.shape
+    N = b.shape[0]
+    if b.shape[1] != K:
+        raise _lib.TavsrError(f"gemm_wgrad: reduction axes differ ({K} vs {b.shape[1]})")
+    lib = _lib.load()
+    out = torch.empty((M, N), device=a.device, dtype=torch.float32)
+    nbytes = lib.tavsr_gemm_wgrad_workspace_bytes(M, N, K)
+    ws = _ws(nbytes, a.device) if nbytes else None
+    check(lib.tavsr_gemm_wgrad(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(),
+                               out.stride(0), M, N, K, _p(ws), nbytes, _stream()), "tavsr_gemm_wgrad")
+    return out
+
+
 def linear_bwd(x_in: torch.Tensor, w: torch.Tensor, dy: torch.Tensor, need_dx: bool = True,
                need_dw: bool = True, wT: Optional[torch.Tensor] = None):
     """Backward of y = x_in W^T + b on the tcgen05 GEMM (TF32 operands, fp32 accumulate):
@@ -59,7 +77,7 @@ def linear_bwd(x_in: torch.Tensor, w: torch.Tensor, dy: torch.Tensor, need_dx: b
     if need_dw:
         dyT = transpose_2d(dy, pad=True)
         xT = transpose_2d(x_in, pad=True)
-        dw = ops.gemm_bias_act(dyT, xT, None)
+        dw = gemm_wgrad(dyT, xT)
         db = col_sums(dy)
     return dx, dw, db
 

@@ -192,7 +192,7 @@ def block_forward(L, aux, x: torch.Tensor) -> Tuple[torch.Tensor, dict]:
     dev = x.device
     new = lambda c=d: torch.empty((M, c), device=dev, dtype=F32)  # noqa: E731
     sv = {"x": x}
-    dm = aux.drop
+    drp = aux.drop
     two = L.use_two_branches
     learned = two and L.merge_method == "learned_ave" and not aux.drop_attn
     # ---- macaron FFN ----
@@ -204,10 +204,10 @@ def block_forward(L, aux, x: torch.Tensor) -> Tuple[torch.Tensor, dict]:
     lnB = (L.norm_mlp.weight, L.norm_mlp.bias) if L.cgmlp is not None else None
     if lnA is None:
         sv["z1"] = _ffn_forward(sv["xn0"], L.feed_forward_macaron, x, x_a, lnA=lnB, out_lnA=xm,
-                                mask_h=dm.get("ffm_h"), mask_o=dm.get("ffm_o"))
+                                mask_h=drp.get("ffm_h"), mask_o=drp.get("ffm_o"))
     else:
         sv["z1"] = _ffn_forward(sv["xn0"], L.feed_forward_macaron, x, x_a, lnA=lnA, out_lnA=xa,
-                                lnB=lnB, out_lnB=xm, mask_h=dm.get("ffm_h"), mask_o=dm.get("ffm_o"))
+                                lnB=lnB, out_lnB=xm, mask_h=drp.get("ffm_h"), mask_o=drp.get("ffm_o"))
     sv.update(x_a=x_a, xa=xa, xm=xm)
     x1 = x2 = d1 = d2 = None
     # ---- attention branch ----
@@ -221,17 +221,17 @@ def block_forward(L, aux, x: torch.Tensor) -> Tuple[torch.Tensor, dict]:
         pp = ops.gemm_bias_act(aux.pos2d, A.linear_pos.weight, None)
         lse = torch.empty((B, A.h, T), device=dev, dtype=F32)
         ctx = ops.relpos_attn(qkv, pp, A.pos_bias_u.reshape(-1), A.pos_bias_v.reshape(-1), aux.lens,
-                              B, T, A.h, round_out=False, lse=lse, drop=dm.get("att"))
+                              B, T, A.h, round_out=False, lse=lse, drop=drp.get("att"))
         x1 = new()
         dots = None
         if learned:
             d1 = torch.empty((M, 2), device=dev, dtype=F32)
             dots = (L.pooling_proj1.weight.reshape(-1), L.weight_proj1.weight.reshape(-1))
-        if dm.get("x1") is None:
+        if drp.get("x1") is None:
             ops.gemm_rowln(ctx, A.linear_out.weight, A.linear_out.bias, out_main=x1, dots=dots, dots_out=d1)
         else:   # x1 = dropout(linear_out(ctx)) (:212); the pooling scores are taken on the dropped x1
             ops.gemm_rowln(ctx, A.linear_out.weight, A.linear_out.bias, out_main=x1)
-            x1 = _mul(x1, dm["x1"])
+            x1 = _mul(x1, drp["x1"])
             if learned:
                 d1 = ops.row_dots(x1, dots[0], dots[1])[0]
         sv.update(wqkv=wqkv, qkv=qkv, pp=pp, lse=lse, ctx=ctx, x1=x1)
@@ -247,18 +247,18 @@ def block_forward(L, aux, x: torch.Tensor) -> Tuple[torch.Tensor, dict]:
         stats = torch.empty((M, 2), device=dev, dtype=F32)
         u = ops.csgu(hc, Cg.csgu.norm.weight, Cg.csgu.norm.bias, conv.weight.reshape(conv.weight.shape[0], -1),
                      conv.bias, B, T, eps=Cg.csgu.norm.eps, round_out=False, stats=stats)
-        u = _mul(u, dm.get("csgu"))                      # espnet cgmlp.py: dropout(x_r * x_g)
+        u = _mul(u, drp.get("csgu"))                      # espnet cgmlp.py: dropout(x_r * x_g)
         x2 = new()
         dots = None
         if learned:
             d2 = torch.empty((M, 2), device=dev, dtype=F32)
             dots = (L.pooling_proj2.weight.reshape(-1), L.weight_proj2.weight.reshape(-1))
-        if dm.get("x2") is None:
+        if drp.get("x2") is None:
             ops.gemm_rowln(u, Cg.channel_proj2.weight, Cg.channel_proj2.bias, out_main=x2, dots=dots,
                            dots_out=d2)
         else:
             ops.gemm_rowln(u, Cg.channel_proj2.weight, Cg.channel_proj2.bias, out_main=x2)
-            x2 = _mul(x2, dm["x2"])
+            x2 = _mul(x2, drp["x2"])
             if learned:
                 d2 = ops.row_dots(x2, dots[0], dots[1])[0]
         sv.update(zc=zc, stats=stats, u=u, x2=x2)
@@ -281,7 +281,7 @@ def block_forward(L, aux, x: torch.Tensor) -> Tuple[torch.Tensor, dict]:
         else:
             w1 = torch.full((B,), 1.0 - L.cgmlp_weight, device=dev, dtype=F32)
             w2 = torch.full((B,), float(L.cgmlp_weight), device=dev, dtype=F32)
-        if dm.get("merge") is None:
+        if drp.get("merge") is None:
             ops.gemm_rowln(x1, mp.weight, mp.bias, x2=x2, rowscale=(w1, w2), rows_per_seg=T,
                            residual=x_a, alpha=aux.stoch, out_main=x_b, lnA=lnF, out_lnA=xf)
         else:
@@ -289,22 +289,22 @@ def block_forward(L, aux, x: torch.Tensor) -> Tuple[torch.Tensor, dict]:
         sv.update(w1=w1, w2=w2)
     elif two:   # concat
         msrc = torch.cat([x1, x2], 1)
-        if dm.get("merge") is None:
+        if drp.get("merge") is None:
             ops.gemm_rowln(msrc, mp.weight, mp.bias, residual=x_a, alpha=aux.stoch, out_main=x_b,
                            lnA=lnF, out_lnA=xf)
     else:
         msrc = x2 if L.attn is None else x1
-        if dm.get("merge") is None:
+        if drp.get("merge") is None:
             ops.gemm_rowln(msrc, mp.weight, mp.bias, residual=x_a, alpha=aux.stoch, out_main=x_b,
                            lnA=lnF, out_lnA=xf)
-    if dm.get("merge") is not None:   # x_b = x_a + c * dropout(merge_proj(.)) (:228-306)
-        t = _mul(ops.gemm_bias_act(msrc, mp.weight, mp.bias), dm["merge"])
+    if drp.get("merge") is not None:   # x_b = x_a + c * dropout(merge_proj(.)) (:228-306)
+        t = _mul(ops.gemm_bias_act(msrc, mp.weight, mp.bias), drp["merge"])
         _residual_ln(x_a, t, aux.stoch, x_b, lnF, xf)
     sv.update(x_b=x_b, xf=xf, learned=learned)
     # ---- FFN + norm_final ----
     y0, y = new(), new()
     sv["z2"] = _ffn_forward(xf, L.feed_forward, x_b, y0, lnA=(L.norm_final.weight, L.norm_final.bias),
-                            out_lnA=y, mask_h=dm.get("ff_h"), mask_o=dm.get("ff_o"))
+                            out_lnA=y, mask_h=drp.get("ff_h"), mask_o=drp.get("ff_o"))
     sv["y0"] = y0
     return y, sv
 
@@ -314,12 +314,12 @@ def block_backward(L, aux, sv: dict, dy: torch.Tensor) -> Tuple[torch.Tensor, Di
     M, d = B * T, L.size
     dev = dy.device
     g: Dict[str, torch.Tensor] = {}
-    dm = aux.drop
+    drp = aux.drop
     two = L.use_two_branches
     # ---- norm_final, FFN, norm_ff ----
     dy0 = _ln_bwd(g, sv["y0"], L.norm_final, dy, "norm_final")
     dxf = _ffn_backward(g, sv["xf"], sv["z2"], L.feed_forward, dy0, "feed_forward",
-                        mask_h=dm.get("ff_h"), mask_o=dm.get("ff_o"))
+                        mask_h=drp.get("ff_h"), mask_o=drp.get("ff_o"))
     dx_b = _ln_bwd(g, sv["x_b"], L.norm_ff, dxf, "norm_ff", dres=dy0)          # residual joins here
     # ---- merge ----
     mp = L.merge_proj
@@ -327,7 +327,7 @@ def block_backward(L, aux, sv: dict, dy: torch.Tensor) -> Tuple[torch.Tensor, Di
     if aux.stoch != 1.0:   # x_b = x_a + c * (merge_proj(m)): the projection sees c * dx_b
         c = torch.full((1,), float(aux.stoch), device=dev)
         dmo = ops.scale_add_rows(dx_b, dx_b, c, _scalars(dev)[1], M)
-    dmo = _mul(dmo, dm.get("merge"))
+    dmo = _mul(dmo, drp.get("merge"))
     x1, x2 = sv.get("x1"), sv.get("x2")
     dx1 = dx2 = None
     if two and L.merge_method in ("learned_ave", "fixed_ave"):
@@ -360,11 +360,11 @@ def block_backward(L, aux, sv: dict, dy: torch.Tensor) -> Tuple[torch.Tensor, Di
     # ---- attention branch ----
     if L.attn is not None:
         A = L.attn
-        dx1 = _mul(dx1, dm.get("x1"))
+        dx1 = _mul(dx1, drp.get("x1"))
         dctx = _lin_bwd(g, sv["ctx"], A.linear_out.weight, dx1, "attn.linear_out.weight", "attn.linear_out.bias")
         dqkv, dpos, du, dv = ob.relpos_attn_bwd(sv["qkv"], sv["pp"], A.pos_bias_u.reshape(-1),
                                                 A.pos_bias_v.reshape(-1), aux.lens, sv["ctx"], dctx,
-                                                sv["lse"], B, T, A.h, drop=dm.get("att"))
+                                                sv["lse"], B, T, A.h, drop=drp.get("att"))
         _acc(g, "attn.pos_bias_u", du.view(A.h, A.d_k))
         _acc(g, "attn.pos_bias_v", dv.view(A.h, A.d_k))
         # d linear_pos.weight = dpos^T . pos_emb (reduction over the 2T-1 relative positions)
@@ -380,9 +380,9 @@ def block_backward(L, aux, sv: dict, dy: torch.Tensor) -> Tuple[torch.Tensor, Di
     if L.cgmlp is not None:
         Cg = L.cgmlp
         lin, conv = Cg.channel_proj1[0], Cg.csgu.conv
-        dx2 = _mul(dx2, dm.get("x2"))
+        dx2 = _mul(dx2, drp.get("x2"))
         du_ = _mul(_lin_bwd(g, sv["u"], Cg.channel_proj2.weight, dx2, "cgmlp.channel_proj2.weight",
-                            "cgmlp.channel_proj2.bias"), dm.get("csgu"))
+                            "cgmlp.channel_proj2.bias"), drp.get("csgu"))
         hc = ob.act_fwd(sv["zc"], ops.ACT_GELU)
         dhc, dng, dnb, dcw, dcb = ob.csgu_bwd(hc, Cg.csgu.norm.weight, Cg.csgu.norm.bias,
                                               conv.weight.reshape(conv.weight.shape[0], -1), conv.bias,
@@ -397,7 +397,7 @@ def block_backward(L, aux, sv: dict, dy: torch.Tensor) -> Tuple[torch.Tensor, Di
         dx_a = _ln_bwd(g, sv["x_a"], L.norm_mlp, dxm, "norm_mlp", dres=dx_a)
     # ---- macaron FFN ----
     dxn0 = _ffn_backward(g, sv["xn0"], sv["z1"], L.feed_forward_macaron, dx_a, "feed_forward_macaron",
-                         mask_h=dm.get("ffm_h"), mask_o=dm.get("ffm_o"))
+                         mask_h=drp.get("ffm_h"), mask_o=drp.get("ffm_o"))
     dx = _ln_bwd(g, sv["x"], L.norm_ff_macaron, dxn0, "norm_ff_macaron", dres=dx_a)
     return dx, g
 
@@ -505,9 +505,9 @@ def draw_block_masks(layer, B: int, T: int, device) -> Dict[str, object]:
     p_out = float(layer.dropout.p)
 
     def site(key, shape, p):
-        m = draw_mask(shape, p, device)
-        if m is not None:
-            dm[key] = m
+        m = draw_mask(shape, p, device)        # drawn with the reference's (B, T, C) shape,
+        if m is not None:                      # used on the (B*T, C) activations
+            dm[key] = m.view(B * T, shape[-1])
 
     def ffn(tag, ff):
         site(tag + "_h", (B, T, ff.w_1.out_features), float(ff.dropout_rate))

@@ -232,13 +232,14 @@ def test_product_path_fails_loudly_without_cuda():
     fusion = AdaptiveAudioVisualFusion(**cases.FUSION_DEFAULTS)
     with pytest.raises(NotImplementedError):
         fusion(torch.zeros(1, 8, 256), None, torch.zeros(1, 8, 256), None)   # no backward built
-    # training-mode dropout is not built: the training path says so instead of silently skipping it
+    # dropout masks of the training path: drawn per site in train() mode, none in eval() mode
     from tailored_avsr_b200 import training
     enc.train()
-    with pytest.raises(NotImplementedError, match="dropout"):
-        training._no_dropout(enc.encoders[0], "block")
+    masks = training.draw_block_masks(enc.encoders[0], 1, 8, torch.device("cpu"))
+    assert list(masks) == ["ffm_h", "ffm_o", "att", "x1", "csgu", "x2", "merge", "ff_h", "ff_o"]
+    assert masks["ffm_h"].shape == (8, 2048) and masks["att"][0].shape == (1, 4, 8, 128)
     enc.eval()
-    training._no_dropout(enc.encoders[0], "block")
+    assert training.draw_block_masks(enc.encoders[0], 1, 8, torch.device("cpu")) == {}
 
 
 def test_constructor_errors_match_reference_behaviour():
