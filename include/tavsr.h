@@ -411,6 +411,13 @@ int tavsr_ctc_head_bwd(const float* dlogits, const float* row_scale, int rows_pe
  * ---------------------------------------------------------------------------------------------- */
 int tavsr_transpose_2d(const float* in, long long ld_in, float* out, long long ld_out, int R, int C,
                        void* stream);
+/* Fused elementwise + transpose forms (one pass instead of an elementwise pass and a transpose):
+ *   tavsr_act_fwd_t   hT[c][m] = act(z[m][c]) (* mask[m][c]); hT rows zero-padded to a multiple of 4
+ *   tavsr_act_bwd_t   dz = dh * act'(z) row-major and dzT = dz^T                                   */
+int tavsr_act_fwd_t(const float* z, long long ldz, const float* mask, long long ldm, float* hT,
+                    long long ldt, int M, int C, int act, void* stream);
+int tavsr_act_bwd_t(const float* z, long long ldz, const float* dh, long long ldh, float* dz,
+                    long long ldd, float* dzT, long long ldt, int M, int C, int act, void* stream);
 size_t tavsr_col_sums_workspace_bytes(int R, int C);
 int tavsr_col_sums(const float* a, long long lda, const float* b, long long ldb, float* out,
                    void* workspace, long long workspace_bytes, int R, int C, void* stream);

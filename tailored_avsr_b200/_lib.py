@@ -93,6 +93,10 @@ SIGNATURES = {
                                       c_void_p, c_void_p, c_longlong, c_void_p, c_longlong, c_void_p,
                                       c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_longlong, c_float, c_int, c_int, c_int, c_void_p]),
+    "tavsr_act_fwd_t": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int,
+                                c_int, c_int, c_void_p]),
+    "tavsr_act_bwd_t": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong,
+                                c_void_p, c_longlong, c_int, c_int, c_int, c_void_p]),
     "tavsr_act_fwd": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int,
                               c_int, c_int, c_void_p]),
     "tavsr_merge_learned_ave_weights2": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p,

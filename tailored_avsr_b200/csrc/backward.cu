@@ -179,6 +179,62 @@ act_bwd_kernel(const float* __restrict__ z, long long ldz, const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
+// Elementwise op with a TRANSPOSED (and optionally also a row-major) output, 64 x 64 tiles, float4 on
+// both sides:   v = a                         (kOp 0: plain transpose)
+//               v = act(a) [* mask]           (kOp 1: the FFN hidden h recomputed from z, needed by
+//                                              the backward only as the wgrad operand h^T)
+//               v = b * act'(a)               (kOp 2: dz, needed row-major by dgrad and transposed
+//                                              by wgrad: one read of z / dh, two writes)
+// outT[c][r] = v[r][c] with the columns [R, Rpad) of outT zero-filled (a wgrad product reduces over
+// them); out (optional) gets v row-major.  Replaces an elementwise pass + a separate transpose
+// (2 x 131 MB at the FFN hidden's shape).
+// ------------------------------------------------------------------------------------------------
+template <int kOp>
+__global__ void __launch_bounds__(256)
+ew_transpose_kernel(const float* __restrict__ a, long long lda, const float* __restrict__ b,
+                    long long ldb, const float* __restrict__ mask, long long ldm,
+                    float* __restrict__ out, long long ldo, float* __restrict__ outT, long long ldt,
+                    int R, int C, int Rpad, int act) {
+  __shared__ float tile[64][65];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+  const int tq = threadIdx.x & 15, tr = threadIdx.x >> 4;   // 16 float4 per row x 16 rows per pass
+#pragma unroll
+  for (int pass = 0; pass < 4; ++pass) {
+    const int rr = tr + 16 * pass;
+    const int r = r0 + rr, c = c0 + 4 * tq;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < R && c < C) {   // C % 4 == 0: a float4 is inside or outside as a whole
+      v = ld_act4(reinterpret_cast<const float4*>(a + static_cast<long long>(r) * lda + c));
+      if (kOp == 1) {
+        v = make_float4(act_val(v.x, act), act_val(v.y, act), act_val(v.z, act), act_val(v.w, act));
+        if (mask != nullptr) {
+          const float4 k = ld_act4(reinterpret_cast<const float4*>(mask + static_cast<long long>(r) * ldm + c));
+          v.x *= k.x; v.y *= k.y; v.z *= k.z; v.w *= k.w;
+        }
+      } else if (kOp == 2) {
+        const float4 g = ld_act4(reinterpret_cast<const float4*>(b + static_cast<long long>(r) * ldb + c));
+        v = make_float4(g.x * act_grad(v.x, act), g.y * act_grad(v.y, act), g.z * act_grad(v.z, act),
+                        g.w * act_grad(v.w, act));
+      }
+      if (out != nullptr)
+        *reinterpret_cast<float4*>(out + static_cast<long long>(r) * ldo + c) = v;
+    }
+    tile[rr][4 * tq] = v.x; tile[rr][4 * tq + 1] = v.y; tile[rr][4 * tq + 2] = v.z; tile[rr][4 * tq + 3] = v.w;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int pass = 0; pass < 4; ++pass) {
+    const int cc = tr + 16 * pass;            // output row = input column
+    const int c = c0 + cc, r = r0 + 4 * tq;   // output columns r .. r + 3
+    if (c < C && r < Rpad)                    // Rpad % 4 == 0; rows >= R of the tile hold zeros
+      *reinterpret_cast<float4*>(outT + static_cast<long long>(c) * ldt + r) =
+          make_float4(tile[4 * tq][cc], tile[4 * tq + 1][cc], tile[4 * tq + 2][cc], tile[4 * tq + 3][cc]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // LayerNorm backward, one warp per row (D = 128 * kVec), rows of a CTA = 8 warps x kLnRowsPerWarp:
 //   x_hat = (x - mu) rstd;  g = dy * gamma;  dx = rstd (g - mean(g) - x_hat mean(g x_hat)) [+ dres]
 //   per-warp partials of d gamma = sum dy x_hat and d beta = sum dy -> part[warp slot][2][D]
@@ -297,39 +353,66 @@ csgu_conv_bwd_kernel(const float* __restrict__ h, long long ldh, const float* __
   const int t0 = blockIdx.y * kSeg;
   const int b = blockIdx.z;
   const long long row0 = static_cast<long long>(b) * T;
-  for (int r = 0; r < kRows; ++r) {
-    const int t = t0 - kHalo + r;
-    float nv = 0.f, dcv = 0.f;
-    if (t >= 0 && t < T) {
-      const float2 st = stats[row0 + t];
-      const float g = ld_act(h + (row0 + t) * ldh + Ch + c);
-      nv = (g - st.x) * st.y * gam + bet;
-      dcv = ld_act(du + (row0 + t) * ldu + c) * ld_act(h + (row0 + t) * ldh + c);
+  // tile load, eight rows per pass with all 32 loads of a pass in flight before the first use (one
+  // row at a time the kernel spent most of its 280 us waiting on dependent L2 round trips)
+  for (int rb = 0; rb < kRows; rb += 8) {
+    float2 st[8];
+    float gq[8], uq[8], rq[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int t = t0 - kHalo + rb + i;
+      const bool in = rb + i < kRows && t >= 0 && t < T;
+      st[i] = in ? stats[row0 + t] : make_float2(0.f, 0.f);
+      gq[i] = in ? ld_act(h + (row0 + t) * ldh + Ch + c) : 0.f;
+      uq[i] = in ? ld_act(du + (row0 + t) * ldu + c) : 0.f;
+      rq[i] = in ? ld_act(h + (row0 + t) * ldh + c) : 0.f;
     }
-    s_n[r * kCh + threadIdx.x] = nv;
-    s_dc[r * kCh + threadIdx.x] = dcv;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int t = t0 - kHalo + rb + i;
+      if (rb + i < kRows) {
+        const bool in = t >= 0 && t < T;
+        s_n[(rb + i) * kCh + threadIdx.x] = in ? (gq[i] - st[i].x) * st[i].y * gam + bet : 0.f;
+        s_dc[(rb + i) * kCh + threadIdx.x] = uq[i] * rq[i];
+      }
+    }
   }
   // every thread only reads the column it wrote: no barrier needed
   float dw[kTaps];
 #pragma unroll
   for (int k = 0; k < kTaps; ++k) dw[k] = 0.f;
   float dcb = 0.f;
-  for (int o = 0; o < kSeg; ++o) {
-    const int t = t0 + o;
-    if (t >= T) break;
-    const int rc = o + kHalo;  // tile row of frame t
-    float conv = cb, dnv = 0.f;
-    const float dct = s_dc[rc * kCh + threadIdx.x];
+  // 16 output frames per pass out of a REGISTER window of the 46 tile rows they touch (the
+  // one-frame-at-a-time form issued 62 shared-memory loads per 93 FMAs and ran at 286 us; here the
+  // 1488 FMAs of a pass read 92 values once)
+  constexpr int kOut = 16, kWin = kOut + 2 * kHalo;
+  static_assert(kSeg % kOut == 0, "segment is a whole number of passes");
+  for (int o0 = 0; o0 < kSeg; o0 += kOut) {
+    if (t0 + o0 >= T) break;
+    float nw[kWin], dcw[kWin];
 #pragma unroll
-    for (int k = 0; k < kTaps; ++k) {
-      const float nk = s_n[(rc + k - kHalo) * kCh + threadIdx.x];
-      conv = fmaf(w[k], nk, conv);                                        // c[t]
-      dnv = fmaf(w[k], s_dc[(rc - k + kHalo) * kCh + threadIdx.x], dnv);  // dn[t]
-      dw[k] = fmaf(dct, nk, dw[k]);                                       // d w[k]
+    for (int i = 0; i < kWin; ++i) {
+      nw[i] = s_n[(o0 + i) * kCh + threadIdx.x];      // tile row o0 + i <-> frame t0 + o0 - kHalo + i
+      dcw[i] = s_dc[(o0 + i) * kCh + threadIdx.x];
     }
-    dcb += dct;
-    dh[(row0 + t) * lddh + c] = ld_act(du + (row0 + t) * ldu + c) * conv;  // dr
-    dn[(row0 + t) * lddn + c] = dnv;
+#pragma unroll
+    for (int j = 0; j < kOut; ++j) {
+      const int t = t0 + o0 + j;
+      float conv = cb, dnv = 0.f;
+      const float dct = dcw[j + kHalo];               // 0 for t >= T: no contribution below
+#pragma unroll
+      for (int k = 0; k < kTaps; ++k) {
+        const float nk = nw[j + k];
+        conv = fmaf(w[k], nk, conv);                  // c[t]
+        dnv = fmaf(w[k], dcw[j + 2 * kHalo - k], dnv);  // dn[t]
+        dw[k] = fmaf(dct, nk, dw[k]);                 // d w[k]
+      }
+      dcb += dct;
+      if (t < T) {
+        dh[(row0 + t) * lddh + c] = ld_act(du + (row0 + t) * ldu + c) * conv;  // dr
+        dn[(row0 + t) * lddn + c] = dnv;
+      }
+    }
   }
   float* pp = part + ((static_cast<long long>(b) * gridDim.y + blockIdx.y) * Ch + c) * 32;
 #pragma unroll
@@ -353,9 +436,8 @@ csgu_conv_bwd_reduce_kernel(const float* __restrict__ part, int nblk, int Ch,
 
 
 // ------------------------------------------------------------------------------------------------
-// learned_ave merge backward (oracle/bwd_formulas.py::learned_ave_merge_bwd), one CTA of 256 threads
-// per utterance, D == 256.  NOT YET RUN ON A GPU (written after the round's GPU budget was spent):
-// its test is gated behind TAVSR_TEST_BWD_WIP=1.
+// learned_ave merge backward (oracle/bwd_formulas.py::learned_ave_merge_bwd), one CTA of 1024 threads
+// per utterance, D == 256 (tests/test_backward_gpu.py::test_merge_learned_ave_bwd).
 //   forward:  score_i[t] = (x_i[t].a_i + c_i)/sqrt(D) (t < len), s_i = softmax_t, pooled_i = sum_t
 //             s_i[t] x_i[t], omega_i = pooled_i.b_i + e_i, w = softmax(omega), m = w1 x1 + w2 x2
 //   given dm: dw_i = sum_{t,d} dm x_i (ALL T frames: the sum m is dense), domega = w (dw - w.dw),
@@ -368,24 +450,28 @@ csgu_conv_bwd_reduce_kernel(const float* __restrict__ part, int nblk, int Ch,
 // ------------------------------------------------------------------------------------------------
 constexpr int kMergeT = 2048;  // frames per utterance held in shared memory
 
-__device__ __forceinline__ float block_sum_256(float v, float* s_red) {
+constexpr int kMergeThreads = 1024;  // 32 warps: only B CTAs exist, so a CTA takes a whole SM
+constexpr int kMergeWarps = kMergeThreads / 32;
+constexpr int kMergeGroups = kMergeThreads / 256;   // row groups of the thread-per-column phases
+
+__device__ __forceinline__ float block_sum_merge(float v, float* s_red) {
   v = warp_sum(v);
   __syncthreads();
   if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
   __syncthreads();
   float r = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) r += s_red[i];
+  for (int i = 0; i < kMergeWarps; ++i) r += s_red[i];
   return r;
 }
-__device__ __forceinline__ float block_max_256(float v, float* s_red) {
+__device__ __forceinline__ float block_max_merge(float v, float* s_red) {
   v = warp_max(v);
   __syncthreads();
   if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
   __syncthreads();
   float r = s_red[0];
 #pragma unroll
-  for (int i = 1; i < 8; ++i) r = fmaxf(r, s_red[i]);
+  for (int i = 1; i < kMergeWarps; ++i) r = fmaxf(r, s_red[i]);
   return r;
 }
 
@@ -402,21 +488,25 @@ struct MergeBwdParams {
   int T;
 };
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kMergeThreads)
 merge_learned_ave_bwd_kernel(const MergeBwdParams p) {
   constexpr int D = 256;
   extern __shared__ float s_mem[];
   float* s_s = s_mem;                  // [2][T]  scores -> softmax weights s_i[t]
   float* s_d = s_mem + 2 * p.T;        // [2][T]  ds_i[t] -> dsc_i[t]
   __shared__ float s_vec[4][D];        // a1, a2 -> later dpool1, dpool2 in rows 2, 3
-  __shared__ float s_red[8];
+  __shared__ float s_grp[2][kMergeGroups][D];   // per row-group partials of the column phases
+  __shared__ float s_red[kMergeWarps];
   pdl_launch_dependents();
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5;
+  const int col = tid & (D - 1), grp = tid >> 8;
   const uint32_t lane = lane_id();
   const int T = p.T;
-  s_vec[0][tid] = __ldg(p.a1 + tid);
-  s_vec[1][tid] = __ldg(p.a2 + tid);
-  const float bb1 = __ldg(p.b1 + tid), bb2 = __ldg(p.b2 + tid);
+  if (tid < D) {
+    s_vec[0][tid] = __ldg(p.a1 + tid);
+    s_vec[1][tid] = __ldg(p.a2 + tid);
+  }
+  const float bb1 = __ldg(p.b1 + col), bb2 = __ldg(p.b2 + col);
   pdl_wait();
   const float pc1 = ld_act(p.scal), pe1 = ld_act(p.scal + 1), pc2 = ld_act(p.scal + 2), pe2 = ld_act(p.scal + 3);
   int len = p.lens ? p.lens[b] : T;
@@ -426,7 +516,7 @@ merge_learned_ave_bwd_kernel(const MergeBwdParams p) {
   __syncthreads();
   // ---- phase 1 (warp per row): scores and the dense dw_i = sum dm . x_i ----
   float dw1 = 0.f, dw2 = 0.f;
-  for (int t = warp; t < T; t += 8) {
+  for (int t = warp; t < T; t += kMergeWarps) {
     const float4* r1 = reinterpret_cast<const float4*>(p.x1 + (row0 + t) * p.ld1);
     const float4* r2 = reinterpret_cast<const float4*>(p.x2 + (row0 + t) * p.ld2);
     const float4* rm = reinterpret_cast<const float4*>(p.dm + (row0 + t) * p.ldm);
@@ -450,49 +540,56 @@ merge_learned_ave_bwd_kernel(const MergeBwdParams p) {
     }
   }
   // one lane per warp carries the warp's dw partial into the block sums
-  dw1 = block_sum_256(lane == 0 ? dw1 : 0.f, s_red);
-  dw2 = block_sum_256(lane == 0 ? dw2 : 0.f, s_red);
+  dw1 = block_sum_merge(lane == 0 ? dw1 : 0.f, s_red);
+  dw2 = block_sum_merge(lane == 0 ? dw2 : 0.f, s_red);
   // ---- phase 2: masked softmax over t < len for both branches ----
-  float se[2];
 #pragma unroll
   for (int br = 0; br < 2; ++br) {
     float* sc = s_s + br * T;
     float mx = -INFINITY;
-    for (int t = tid; t < len; t += 256) mx = fmaxf(mx, sc[t]);
-    mx = block_max_256(mx, s_red);
+    for (int t = tid; t < len; t += kMergeThreads) mx = fmaxf(mx, sc[t]);
+    mx = block_max_merge(mx, s_red);
     float sum = 0.f;
-    for (int t = tid; t < T; t += 256) {
+    for (int t = tid; t < T; t += kMergeThreads) {
       const float e = t < len ? expf(sc[t] - mx) : 0.f;
       sc[t] = e;
       sum += e;
     }
-    se[br] = block_sum_256(sum, s_red);
-    const float inv = len > 0 ? 1.0f / se[br] : 0.f;
-    for (int t = tid; t < T; t += 256) sc[t] *= inv;
+    const float se = block_sum_merge(sum, s_red);
+    const float inv = len > 0 ? 1.0f / se : 0.f;
+    for (int t = tid; t < T; t += kMergeThreads) sc[t] *= inv;
   }
   __syncthreads();
-  // ---- phase 3 (thread per column): pooled_i[d], omega, w, domega, dpool ----
+  // ---- phase 3 (thread per column, rows split over the groups): pooled_i[d], omega, w, domega ----
   float pool1 = 0.f, pool2 = 0.f;
-  for (int t = 0; t < len; ++t) {
-    pool1 = fmaf(s_s[t], ld_act(p.x1 + (row0 + t) * p.ld1 + tid), pool1);
-    pool2 = fmaf(s_s[T + t], ld_act(p.x2 + (row0 + t) * p.ld2 + tid), pool2);
+  for (int t = grp; t < len; t += kMergeGroups) {
+    pool1 = fmaf(s_s[t], ld_act(p.x1 + (row0 + t) * p.ld1 + col), pool1);
+    pool2 = fmaf(s_s[T + t], ld_act(p.x2 + (row0 + t) * p.ld2 + col), pool2);
   }
-  const float om1 = block_sum_256(pool1 * bb1, s_red) + pe1;
-  const float om2 = block_sum_256(pool2 * bb2, s_red) + pe2;
+  s_grp[0][grp][col] = pool1;
+  s_grp[1][grp][col] = pool2;
+  __syncthreads();
+  pool1 = 0.f; pool2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < kMergeGroups; ++k) { pool1 += s_grp[0][k][col]; pool2 += s_grp[1][k][col]; }
+  const float om1 = block_sum_merge(grp == 0 ? pool1 * bb1 : 0.f, s_red) + pe1;
+  const float om2 = block_sum_merge(grp == 0 ? pool2 * bb2 : 0.f, s_red) + pe2;
   const float mo = fmaxf(om1, om2);
   const float e1 = expf(om1 - mo), e2 = expf(om2 - mo);
   const float w1 = e1 / (e1 + e2), w2 = e2 / (e1 + e2);
   const float wd = w1 * dw1 + w2 * dw2;
   const float dom1 = w1 * (dw1 - wd), dom2 = w2 * (dw2 - wd);
   const float dp1 = dom1 * bb1, dp2 = dom2 * bb2;   // dpool_i[d]
-  s_vec[2][tid] = dp1;
-  s_vec[3][tid] = dp2;
   float* pp = p.part + static_cast<long long>(b) * 4 * D;
-  pp[1 * D + tid] = dom1 * pool1;  // db1
-  pp[3 * D + tid] = dom2 * pool2;  // db2
+  if (grp == 0) {
+    s_vec[2][col] = dp1;
+    s_vec[3][col] = dp2;
+    pp[1 * D + col] = dom1 * pool1;  // db1
+    pp[3 * D + col] = dom2 * pool2;  // db2
+  }
   __syncthreads();
   // ---- phase 4 (warp per row): ds_i[t] = x_i[t] . dpool_i ----
-  for (int t = warp; t < len; t += 8) {
+  for (int t = warp; t < len; t += kMergeWarps) {
     const float4* r1 = reinterpret_cast<const float4*>(p.x1 + (row0 + t) * p.ld1);
     const float4* r2 = reinterpret_cast<const float4*>(p.x2 + (row0 + t) * p.ld2);
     float s1 = 0.f, s2 = 0.f;
@@ -513,37 +610,45 @@ merge_learned_ave_bwd_kernel(const MergeBwdParams p) {
 #pragma unroll
   for (int br = 0; br < 2; ++br) {
     float acc = 0.f;
-    for (int t = tid; t < len; t += 256) acc += s_s[br * T + t] * s_d[br * T + t];
-    const float sds = block_sum_256(acc, s_red);
+    for (int t = tid; t < len; t += kMergeThreads) acc += s_s[br * T + t] * s_d[br * T + t];
+    const float sds = block_sum_merge(acc, s_red);
     float dc = 0.f;
-    for (int t = tid; t < T; t += 256) {
+    for (int t = tid; t < T; t += kMergeThreads) {
       const float v = t < len ? s_s[br * T + t] * (s_d[br * T + t] - sds) * rs : 0.f;
       s_d[br * T + t] = v;
       dc += v;
     }
-    dcs[br] = block_sum_256(dc, s_red);
+    dcs[br] = block_sum_merge(dc, s_red);
   }
   __syncthreads();
-  // ---- phase 6 (thread per column): dx_i and da_i ----
-  const float av1 = s_vec[0][tid], av2 = s_vec[1][tid];
+  // ---- phase 6 (thread per column, rows split over the groups): dx_i and da_i ----
+  const float av1 = s_vec[0][col], av2 = s_vec[1][col];
   float da1 = 0.f, da2 = 0.f;
-  for (int t = 0; t < T; ++t) {
-    const float g = ld_act(p.dm + (row0 + t) * p.ldm + tid);
+  for (int t = grp; t < T; t += kMergeGroups) {
+    const float g = ld_act(p.dm + (row0 + t) * p.ldm + col);
     float o1 = w1 * g, o2 = w2 * g;
     if (t < len) {
-      const float v1 = ld_act(p.x1 + (row0 + t) * p.ld1 + tid);
-      const float v2 = ld_act(p.x2 + (row0 + t) * p.ld2 + tid);
+      const float v1 = ld_act(p.x1 + (row0 + t) * p.ld1 + col);
+      const float v2 = ld_act(p.x2 + (row0 + t) * p.ld2 + col);
       const float k1 = s_d[t], k2 = s_d[T + t];
       o1 += s_s[t] * dp1 + k1 * av1;
       o2 += s_s[T + t] * dp2 + k2 * av2;
       da1 = fmaf(k1, v1, da1);
       da2 = fmaf(k2, v2, da2);
     }
-    p.dx1[(row0 + t) * p.ldd1 + tid] = o1;
-    p.dx2[(row0 + t) * p.ldd2 + tid] = o2;
+    p.dx1[(row0 + t) * p.ldd1 + col] = o1;
+    p.dx2[(row0 + t) * p.ldd2 + col] = o2;
   }
-  pp[0 * D + tid] = da1;
-  pp[2 * D + tid] = da2;
+  s_grp[0][grp][col] = da1;
+  s_grp[1][grp][col] = da2;
+  __syncthreads();
+  if (grp == 0) {
+    da1 = 0.f; da2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMergeGroups; ++k) { da1 += s_grp[0][k][col]; da2 += s_grp[1][k][col]; }
+    pp[0 * D + col] = da1;
+    pp[2 * D + col] = da2;
+  }
   if (tid == 0) {
     float* ps = p.part_s + b * 4;
     ps[0] = dcs[0]; ps[1] = dom1; ps[2] = dcs[1]; ps[3] = dom2;
@@ -555,16 +660,59 @@ merge_learned_ave_bwd_kernel(const MergeBwdParams p) {
 
 using namespace tavsr;
 
+static int launch_ew_transpose(int op, const float* a, long long lda, const float* b, long long ldb,
+                               const float* mask, long long ldm, float* out, long long ldo,
+                               float* outT, long long ldt, int R, int C, int act, cudaStream_t s) {
+  // the tail of every transposed row up to the next multiple of 4 (within the pitch) is zero-filled
+  const int Rpad = static_cast<int>(ldt < ((R + 3) / 4) * 4 ? ldt : ((R + 3) / 4) * 4);
+  const dim3 grid((C + 63) / 64, (R + 63) / 64);
+  if (op == 0)
+    TAVSR_CUDA_OK(launch_kernel(bwd::ew_transpose_kernel<0>, grid, dim3(256), 0, s, 0, a, lda, b, ldb, mask,
+                                ldm, out, ldo, outT, ldt, R, C, Rpad, act));
+  else if (op == 1)
+    TAVSR_CUDA_OK(launch_kernel(bwd::ew_transpose_kernel<1>, grid, dim3(256), 0, s, 0, a, lda, b, ldb, mask,
+                                ldm, out, ldo, outT, ldt, R, C, Rpad, act));
+  else
+    TAVSR_CUDA_OK(launch_kernel(bwd::ew_transpose_kernel<2>, grid, dim3(256), 0, s, 0, a, lda, b, ldb, mask,
+                                ldm, out, ldo, outT, ldt, R, C, Rpad, act));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
 extern "C" int tavsr_transpose_2d(const float* in, long long ld_in, float* out, long long ld_out,
                                   int R, int C, void* stream) {
   TAVSR_REQUIRE(R > 0 && C > 0 && in && out && ld_in >= C && ld_out >= R, "transpose: bad arguments");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (C % 4 == 0 && ld_in % 4 == 0 && ld_out % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(out) & 15) == 0 && ld_out >= ((R + 3) / 4) * 4)
+    return launch_ew_transpose(0, in, ld_in, nullptr, 0, nullptr, 0, nullptr, 0, out, ld_out, R, C, 0, s);
   // the tail of every output row up to the next multiple of 4 (within the pitch) is zero-filled
   const int Rpad = static_cast<int>(ld_out < ((R + 3) / 4) * 4 ? ld_out : ((R + 3) / 4) * 4);
   TAVSR_CUDA_OK(launch_kernel(bwd::transpose_kernel, dim3((C + 31) / 32, (R + 31) / 32), dim3(256), 0,
                               s, 0, in, ld_in, out, ld_out, R, C, Rpad));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
+}
+
+// h^T = (act(z) [* mask])^T: the recomputed FFN hidden in the operand form of its weight gradient.
+extern "C" int tavsr_act_fwd_t(const float* z, long long ldz, const float* mask, long long ldm,
+                               float* hT, long long ldt, int M, int C, int act, void* stream) {
+  TAVSR_REQUIRE(M > 0 && C > 0 && C % 4 == 0 && ldz % 4 == 0 && ldt % 4 == 0 && ldt >= ((M + 3) / 4) * 4 &&
+                    (!mask || ldm % 4 == 0) && z && hT && act >= 0 && act <= 3,
+                "act_fwd_t: bad arguments (M=%d C=%d act=%d)", M, C, act);
+  return launch_ew_transpose(1, z, ldz, nullptr, 0, mask, ldm, nullptr, 0, hT, ldt, M, C, act,
+                             static_cast<cudaStream_t>(stream));
+}
+
+// dz = dh * act'(z), written row-major (dgrad operand) AND transposed (wgrad operand) in one pass.
+extern "C" int tavsr_act_bwd_t(const float* z, long long ldz, const float* dh, long long ldh, float* dz,
+                               long long ldd, float* dzT, long long ldt, int M, int C, int act,
+                               void* stream) {
+  TAVSR_REQUIRE(M > 0 && C > 0 && C % 4 == 0 && ldz % 4 == 0 && ldh % 4 == 0 && ldd % 4 == 0 &&
+                    ldt % 4 == 0 && ldt >= ((M + 3) / 4) * 4 && z && dh && dz && dzT && act >= 0 && act <= 3,
+                "act_bwd_t: bad arguments (M=%d C=%d act=%d)", M, C, act);
+  return launch_ew_transpose(2, z, ldz, dh, ldh, nullptr, 0, dz, ldd, dzT, ldt, M, C, act,
+                             static_cast<cudaStream_t>(stream));
 }
 
 extern "C" size_t tavsr_col_sums_workspace_bytes(int R, int C) {
@@ -722,7 +870,7 @@ extern "C" int tavsr_merge_learned_ave_bwd(const float* x1, long long ld1, const
     TAVSR_CUDA_OK(cudaFuncSetAttribute(bwd::merge_learned_ave_bwd_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   }
-  TAVSR_CUDA_OK(launch_kernel(bwd::merge_learned_ave_bwd_kernel, dim3(B), dim3(256),
+  TAVSR_CUDA_OK(launch_kernel(bwd::merge_learned_ave_bwd_kernel, dim3(B), dim3(bwd::kMergeThreads),
                               static_cast<size_t>(smem), s, 0, p));
   // reduce the per-utterance partials over b: [B][1024] -> grads[0:1024], [B][4] -> grads[1024:1028]
   TAVSR_CUDA_OK(launch_kernel(bwd::col_sums_reduce_kernel, dim3(32), dim3(1024), 0, s, 0,

@@ -41,6 +41,30 @@ def act_fwd(z: torch.Tensor, act: int, mask: Optional[torch.Tensor] = None,
     return out
 
 
+def act_fwd_t(z: torch.Tensor, act: int, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(act(z) * mask)^T as a (C, ceil4(M)) wgrad operand in one pass (tavsr_act_fwd_t)."""
+    _chk2d(z, "z")
+    M, C = z.shape
+    out = torch.empty((C, (M + 3) // 4 * 4), device=z.device, dtype=torch.float32)
+    check(_lib.load().tavsr_act_fwd_t(z.data_ptr(), z.stride(0), _p(mask),
+                                      mask.stride(0) if mask is not None else 0, out.data_ptr(),
+                                      out.stride(0), M, C, act, _stream()), "tavsr_act_fwd_t")
+    return out
+
+
+def act_bwd_t(z: torch.Tensor, dh: torch.Tensor, act: int):
+    """dz = dh * act'(z) row-major plus its transpose (C, ceil4(M)) in one pass (tavsr_act_bwd_t)."""
+    _chk2d(z, "z")
+    _chk2d(dh, "dh")
+    M, C = z.shape
+    dz = torch.empty((M, C), device=z.device, dtype=torch.float32)
+    dzT = torch.empty((C, (M + 3) // 4 * 4), device=z.device, dtype=torch.float32)
+    check(_lib.load().tavsr_act_bwd_t(z.data_ptr(), z.stride(0), dh.data_ptr(), dh.stride(0),
+                                      dz.data_ptr(), dz.stride(0), dzT.data_ptr(), dzT.stride(0), M, C,
+                                      act, _stream()), "tavsr_act_bwd_t")
+    return dz, dzT
+
+
 def gemm_wgrad(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """out (M, N) = a (M, K) . b (N, K)^T with the reduction axis split over the machine
     (tavsr_gemm_wgrad): the weight-gradient product, K = frames of the batch."""
@@ -59,14 +83,16 @@ def gemm_wgrad(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def linear_bwd(x_in: torch.Tensor, w: torch.Tensor, dy: torch.Tensor, need_dx: bool = True,
-               need_dw: bool = True, wT: Optional[torch.Tensor] = None):
+def linear_bwd(x_in: Optional[torch.Tensor], w: torch.Tensor, dy: torch.Tensor, need_dx: bool = True,
+               need_dw: bool = True, wT: Optional[torch.Tensor] = None,
+               xT: Optional[torch.Tensor] = None, dyT: Optional[torch.Tensor] = None):
     """Backward of y = x_in W^T + b on the tcgen05 GEMM (TF32 operands, fp32 accumulate):
          dx = dy W            = gemm(dy, (W^T) as the (K, N) weight operand)
          dW = dy^T x_in       = gemm(dy^T (N, M), x_in^T (K, M)): reduction over the M rows
          db = column sums of dy
     Both products want K-major operands, hence the transposed copies (a 32 x 32 tile transpose
     kernel; the bf16 path can read MN-major operands directly and will not need them).
+    `xT` / `dyT`: operands already transposed by a fused producer (act_fwd_t / act_bwd_t).
     Returns (dx or None, dW or None, db or None)."""
     from . import ops
     dx = dw = db = None
@@ -75,8 +101,10 @@ def linear_bwd(x_in: torch.Tensor, w: torch.Tensor, dy: torch.Tensor, need_dx: b
             wT = transpose_2d(w.contiguous() if w.stride(1) != 1 else w)
         dx = ops.gemm_bias_act(dy, wT, None)
     if need_dw:
-        dyT = transpose_2d(dy, pad=True)
-        xT = transpose_2d(x_in, pad=True)
+        if dyT is None:
+            dyT = transpose_2d(dy, pad=True)
+        if xT is None:
+            xT = transpose_2d(x_in, pad=True)
         dw = gemm_wgrad(dyT, xT)
         db = col_sums(dy)
     return dx, dw, db

@@ -109,8 +109,10 @@ def _acc(g: Dict[str, torch.Tensor], key: str, val: torch.Tensor) -> None:
     g[key] = g[key] + val if key in g else val
 
 
-def _lin_bwd(g, x_in, lin_w, dy, wname: Optional[str], bname: Optional[str], need_dx=True):
-    dx, dw, db = ob.linear_bwd(x_in, lin_w, dy, need_dx=need_dx, need_dw=wname is not None)
+def _lin_bwd(g, x_in, lin_w, dy, wname: Optional[str], bname: Optional[str], need_dx=True, xT=None,
+             dyT=None):
+    dx, dw, db = ob.linear_bwd(x_in, lin_w, dy, need_dx=need_dx, need_dw=wname is not None, xT=xT,
+                               dyT=dyT)
     if wname is not None:
         _acc(g, wname, dw)
         if bname is not None:
@@ -177,10 +179,12 @@ def _ffn_backward(g, xn, z, ff, dout, prefix: str, mask_h=None, mask_o=None):
     """dout = d loss / d (residual + 0.5 drop_o(ffn(xn))); returns d loss / d xn."""
     act = engine.act_code(ff.activation_type)
     dhalf = _mul(_half(dout), mask_o)
-    h = ob.act_fwd(z, act, mask=mask_h)                  # recomputed: only z is kept
-    dh = _lin_bwd(g, h, ff.w_2.weight, dhalf, prefix + ".w_2.weight", prefix + ".w_2.bias")
-    dz = ob.act_bwd(z, _mul(dh, mask_h), act)
-    return _lin_bwd(g, xn, ff.w_1.weight, dz, prefix + ".w_1.weight", prefix + ".w_1.bias")
+    # h is recomputed from z (only z is kept) and is needed only as the wgrad operand h^T; dz is
+    # needed row-major (dgrad) and transposed (wgrad): both come out of fused one-pass kernels
+    hT = ob.act_fwd_t(z, act, mask=mask_h)
+    dh = _lin_bwd(g, None, ff.w_2.weight, dhalf, prefix + ".w_2.weight", prefix + ".w_2.bias", xT=hT)
+    dz, dzT = ob.act_bwd_t(z, _mul(dh, mask_h), act)
+    return _lin_bwd(g, xn, ff.w_1.weight, dz, prefix + ".w_1.weight", prefix + ".w_1.bias", dyT=dzT)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -391,9 +395,9 @@ def block_backward(L, aux, sv: dict, dy: torch.Tensor) -> Tuple[torch.Tensor, Di
         _acc(g, "cgmlp.csgu.norm.bias", dnb)
         _acc(g, "cgmlp.csgu.conv.weight", dcw.view_as(conv.weight))
         _acc(g, "cgmlp.csgu.conv.bias", dcb)
-        dzc = ob.act_bwd(sv["zc"], dhc, ops.ACT_GELU)
+        dzc, dzcT = ob.act_bwd_t(sv["zc"], dhc, ops.ACT_GELU)
         dxm = _lin_bwd(g, sv["xm"], lin.weight, dzc, "cgmlp.channel_proj1.0.weight",
-                       "cgmlp.channel_proj1.0.bias")
+                       "cgmlp.channel_proj1.0.bias", dyT=dzcT)
         dx_a = _ln_bwd(g, sv["x_a"], L.norm_mlp, dxm, "norm_mlp", dres=dx_a)
     # ---- macaron FFN ----
     dxn0 = _ffn_backward(g, sv["xn0"], sv["z1"], L.feed_forward_macaron, dx_a, "feed_forward_macaron",

@@ -185,6 +185,29 @@ def test_relpos_attention_dropout_fwd_bwd(B, T, lens):
     assert _rel(dpos, pos_r.grad) < tol and _rel(du, u_r.grad) < tol and _rel(dv, v_r.grad) < tol
 
 
+@pytest.mark.parametrize("M,C", [(8000, 2048), (141, 256), (499, 1024), (64, 64), (3, 4)])
+def test_fused_elementwise_transpose(M, C):
+    """tavsr_act_fwd_t / tavsr_act_bwd_t / the float4 path of tavsr_transpose_2d: one-pass forms of
+    (elementwise op, transpose), bit-identical to the two-pass forms, padding columns zero."""
+    from tailored_avsr_b200 import ops, ops_backward as ob
+    g = torch.Generator().manual_seed(M + C)
+    z = torch.randn(M, C, generator=g).to(DEV)
+    dh = torch.randn(M, C, generator=g).to(DEV)
+    mask = ((torch.rand(M, C, generator=g) > 0.1).float() / 0.9).to(DEV)
+    Mp = (M + 3) // 4 * 4
+    xt = ob.transpose_2d(z, pad=True)
+    assert xt.shape == (C, Mp) and torch.equal(xt[:, :M], z.t()) and float(xt[:, M:].abs().sum()) == 0.0
+    for act in (ops.ACT_SWISH, ops.ACT_GELU):
+        for mk in (None, mask):
+            hT = ob.act_fwd_t(z, act, mask=mk)
+            assert torch.equal(hT[:, :M], ob.act_fwd(z, act, mask=mk).t())
+            assert float(hT[:, M:].abs().sum()) == 0.0
+        dz, dzT = ob.act_bwd_t(z, dh, act)
+        want = ob.act_bwd(z, dh, act)
+        assert torch.equal(dz, want) and torch.equal(dzT[:, :M], want.t())
+        assert float(dzT[:, M:].abs().sum()) == 0.0
+
+
 @pytest.mark.parametrize("M,N,K", [(2048, 256, 8000), (256, 256, 8000), (256, 2048, 8000), (768, 256, 1000),
                                    (256, 512, 140), (1024, 256, 8000), (41 * 4, 256, 2004)])
 def test_gemm_wgrad_split_k(M, N, K):
@@ -379,8 +402,8 @@ def test_encoder_training_with_dropout_matches_reference(name):
         worst = max(worst, (dev_n / tol, n, dev_n))
         assert dev_n <= 2 * tol, (n, float(g.norm()), gn)
         sample = g[:: max(1, g.numel() // 16)][:16].numpy()
-        assert np.allclose(sample, gold["sample/" + n], rtol=2e-2,
-                           atol=4 * tol * gn / max(1.0, g.numel() ** 0.5) + 1e-9), n
+        assert np.allclose(sample, gold["sample/" + n], rtol=5e-2 if pool else 2e-2,
+                           atol=(10 if pool else 4) * tol * gn / max(1.0, g.numel() ** 0.5) + 1e-9), n
         checked += 1
     print(f"TRAIN+DROPOUT {name}: {checked} gradients, worst norm deviation {worst[1]} {worst[2]:.2e}")
     assert checked > 80
