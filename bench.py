@@ -569,10 +569,12 @@ def train_leg(args, enc, ctc, rank, world, dev, dist, steps, warmup, train_mode=
 
 
 def train_graph_leg(args, enc, ctc, rank, world, dev, dist, steps, warmup):
-    """The same training step with forward + loss + backward captured ONCE into a CUDA graph and
-    replayed (the eager step is bound by ~1400 Python-side launches); the gradient all-reduce then
-    runs after the replay (gradient hooks do not fire inside a replay), i.e. NOT overlapped.
-    Returns a dict (rank 0) or None."""
+    """The same training step captured ONCE into a CUDA graph and replayed (the eager step is bound
+    by ~1500 Python-side launches).  First choice: the bucketed all-reduce is captured too, launched
+    by the gradient hooks during the captured backward, so the replayed graph overlaps the NCCL
+    transfers with the backward kernels exactly like the eager step.  If NCCL capture is refused the
+    graph holds forward + loss + backward and the all-reduce runs after the replay (not overlapped);
+    the result says which.  Returns a dict (rank 0) or None."""
     from tailored_avsr_b200 import engine, parallel
     w = WORKLOAD
     if w["kind"] != "single" or w["front"] != "linear":
@@ -582,23 +584,26 @@ def train_graph_leg(args, enc, ctc, rank, world, dev, dist, steps, warmup):
     enc.train()                  # dropout active, masks drawn inside the capture (graph-safe generator)
     out = None
     params = list(enc.parameters()) + list(ctc.parameters())
-    try:
-        host, frames = make_batch(rank)
-        host = [t.pin_memory() for t in host]
-        static = [t.to(dev) for t in host]
+    host, frames = make_batch(rank)
+    host = [t.pin_memory() for t in host]
+    static = [t.to(dev) for t in host]
+    Bg = w["B"] * world
+    ctc.reduce = False
+
+    def attempt(overlap):
         for p in params:
             p.requires_grad_(True)
             p.grad = None
-        red = parallel.GradBucketReducer(params, bucket_mb=25.0, overlap=False)
-        Bg = w["B"] * world
-        ctc.reduce = False
+        red = parallel.GradBucketReducer(params, bucket_mb=25.0, overlap=overlap)
 
         def fwd_bwd():
+            red.launched_in_backward = 0
             o, olens, _ = enc(static[0], static[1])
             vec = ctc(o, olens, static[2], static[3]) * w["B"]
             loss = vec.sum() / Bg
             loss.backward()
-            return loss
+            n = red.finish() if overlap else 0
+            return loss, n
 
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -613,7 +618,8 @@ def train_graph_leg(args, enc, ctc, rank, world, dev, dist, steps, warmup):
             p.grad = None
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            loss = fwd_bwd()
+            loss, n_in_graph = fwd_bwd()
+        in_bwd = red.launched_in_backward
 
         def step():
             for d_, h_ in zip(static, host):
@@ -621,7 +627,7 @@ def train_graph_leg(args, enc, ctc, rank, world, dev, dist, steps, warmup):
             graph.replay()
             e_b = torch.cuda.Event(enable_timing=True)
             e_b.record()
-            n = red.reduce()
+            n = n_in_graph if overlap else red.reduce()
             e_c = torch.cuda.Event(enable_timing=True)
             e_c.record()
             return n, e_b, e_c
@@ -650,13 +656,32 @@ def train_graph_leg(args, enc, ctc, rank, world, dev, dist, steps, warmup):
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, exp_ms = float(t[0]), float(t[1])
-        out = {"value": frames * steps * world / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+        res = {"value": frames * steps * world / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
                "steps": steps, "loss": loss_host, "global_batch": Bg,
-               "step": "CUDA-graph replay of forward + loss + backward, then the bucketed gradient "
-                       "all-reduce (not overlapped); host inputs copied in and the loss read back",
-               "allreduce": {"collectives_per_step": n_coll, "exposed_ms_per_step": exp_ms / steps,
+               "step": ("ONE CUDA-graph replay of forward + loss + backward + the bucketed gradient "
+                        "all-reduce (NCCL nodes captured where the gradient hooks launched them: "
+                        "overlapped with the backward)") if overlap else
+                       ("CUDA-graph replay of forward + loss + backward, then the bucketed gradient "
+                        "all-reduce (not overlapped)"),
+               "io": "host inputs copied in and the loss read back every step",
+               "allreduce": {"collectives_per_step": n_coll, "captured_in_graph": bool(overlap),
+                             "launched_during_backward": in_bwd if overlap else 0,
+                             "exposed_ms_per_step": None if overlap else exp_ms / steps,
                              "bytes_per_step": sum(red.bucket_bytes()) if world > 1 else 0}}
+        red.remove_hooks()
         del graph
+        return res
+
+    try:
+        try:
+            out = attempt(overlap=world > 1)
+        except Exception as e:  # noqa: BLE001
+            if world == 1:
+                raise
+            torch.cuda.synchronize()
+            first = f"{type(e).__name__}: {e}"[:200]
+            out = attempt(overlap=False)
+            out["overlapped_capture_failed"] = first
     except Exception as e:  # noqa: BLE001
         out = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
         torch.cuda.synchronize()
@@ -925,12 +950,21 @@ def run_gpu_arm(args):
         train = train_leg(args, enc, ctc, rank, world, dev, dist, steps=args.train_steps, warmup=2)
         train_graph = train_graph_leg(args, enc, ctc, rank, world, dev, dist, steps=args.train_steps,
                                       warmup=2)
-        if train is not None and train_graph is not None:
-            train["cuda_graph_variant"] = train_graph
         train_eval = train_leg(args, enc, ctc, rank, world, dev, dist, steps=max(2, args.train_steps // 2),
                                warmup=1, train_mode=False)
         if train is not None and train_eval is not None and "ms_per_step" in train_eval:
             train["eval_mode_ms_per_step"] = train_eval["ms_per_step"]
+        if train is not None and train_graph is not None:
+            if "value" in train_graph and "value" in train:
+                # the graph replay is the training step to quote (the eager step is bound by the
+                # Python-side enqueue of ~1500 launches); the eager, hook-driven step stays beside it
+                eager = train
+                train = dict(train_graph)
+                for k in ("dtype", "module_mode", "warmup", "scaling", "kernel_launches_per_step"):
+                    train[k] = eager.get(k)
+                train["eager_variant"] = eager
+            else:
+                train["cuda_graph_variant"] = train_graph
 
     line = None
     if rank == 0:
