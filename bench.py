@@ -480,6 +480,11 @@ def train_leg(args, enc, ctc, rank, world, dev, dist, steps, warmup, train_mode=
                                "(MyBranchformerEncoder, ConventionalEncoder): run --workload C2"}
     prev = engine.compute_dtype()
     engine.set_compute_dtype("tf32")      # the training path stores fp32 and multiplies in TF32
+    cpu_threads = torch.get_num_threads()
+    if os.environ.get("TAVSR_BENCH_KEEP_THREADS", "0") != "1":
+        # the eager step is bound by its Python-side launches; torch's intra-op CPU pool (idle here)
+        # measurably slows that thread when left at the core count, torchrun sets it to 1 anyway
+        torch.set_num_threads(1)
     enc.train(train_mode)
     host, frames = make_batch(rank)
     host = [t.pin_memory() for t in host]
@@ -490,19 +495,28 @@ def train_leg(args, enc, ctc, rank, world, dev, dist, steps, warmup, train_mode=
     Bg = w["B"] * world
     ctc.reduce = False
 
+    host_split = [0.0, 0.0, 0.0, 0.0]   # forward, loss, backward, finish (host enqueue seconds)
+
     def step():
         for p in params:
             p.grad = None
+        t0 = time.perf_counter()
         feats, lens, ys, ylens = (t.to(dev, non_blocking=True) for t in host)
         out, olens, _ = enc(feats, lens)
+        t1 = time.perf_counter()
         vec = ctc(out, olens, ys, ylens) * w["B"]          # nll_b of the local utterances
         loss = vec.sum() / Bg                               # ctc.py:62-66 with the GLOBAL batch
+        t2 = time.perf_counter()
         loss.backward()
+        t3 = time.perf_counter()
         e_b = torch.cuda.Event(enable_timing=True)
         e_b.record()
         n = red.finish()
         e_c = torch.cuda.Event(enable_timing=True)
         e_c.record()
+        t4 = time.perf_counter()
+        for i, dt in enumerate((t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
+            host_split[i] += dt
         return loss, n, e_b, e_c
 
     for _ in range(max(1, warmup)):
@@ -513,6 +527,7 @@ def train_leg(args, enc, ctc, rank, world, dev, dist, steps, warmup, train_mode=
     l0 = ops.launch_count()
     evs, exposed, in_bwd = [], [], []
     host_enqueue_s = 0.0
+    host_split[:] = [0.0, 0.0, 0.0, 0.0]
     for _ in range(steps):
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
@@ -543,6 +558,7 @@ def train_leg(args, enc, ctc, rank, world, dev, dist, steps, warmup, train_mode=
         p.requires_grad_(False)
     enc.eval()
     engine.set_compute_dtype(prev)
+    torch.set_num_threads(cpu_threads)
     if rank != 0:
         return None
     nbytes = sum(red.bucket_bytes())
@@ -559,6 +575,8 @@ def train_leg(args, enc, ctc, rank, world, dev, dist, steps, warmup, train_mode=
         "global_batch": Bg, "scaling": "weak", "loss": loss_host,
         "kernel_launches_per_step": launches // steps,
         "host_enqueue_ms_per_step": host_enqueue_s / steps * 1e3,
+        "host_enqueue_split_ms": {k: round(v / steps * 1e3, 2) for k, v in
+                                  zip(("forward", "loss", "backward", "finish"), host_split)},
         "allreduce": {"bytes_per_step": nbytes if world > 1 else 0, "buckets": len(red.buckets),
                       "bucket_mb": 25.0, "collectives_per_step": n_coll,
                       "launched_during_backward": in_bwd[-1] if in_bwd else 0,

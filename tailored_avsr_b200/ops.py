@@ -60,7 +60,16 @@ def _profiled(fn):
     return wrapper
 
 
+try:   # the raw handle without building a torch.cuda.Stream object per launch (~10 us each)
+    _raw_stream = torch._C._cuda_getCurrentRawStream
+    _cur_device = torch._C._cuda_getDevice
+except AttributeError:  # pragma: no cover - older / CPU-only torch builds
+    _raw_stream = _cur_device = None
+
+
 def _stream() -> int:
+    if _raw_stream is not None:
+        return _raw_stream(_cur_device())
     return torch.cuda.current_stream().cuda_stream
 
 

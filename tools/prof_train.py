@@ -51,6 +51,17 @@ def main():
     for _ in range(3):
         step()
     step(timed=True)
+    if "--cprofile" in sys.argv:       # where the HOST time of a step goes (forward thread only)
+        import cProfile
+        import pstats
+        import time
+        pr = cProfile.Profile()
+        t0 = time.perf_counter()
+        pr.enable()
+        step()
+        pr.disable()
+        print("host wall of the profiled step: %.1f ms" % ((time.perf_counter() - t0) * 1e3))
+        pstats.Stats(pr).sort_stats("tottime").print_stats(18)
     torch.cuda.profiler.start()
     step()
     torch.cuda.profiler.stop()
