@@ -15,9 +15,13 @@
 //
 // One CTA = 64 keys of one (utterance, head); it loops over the 64-query tiles and owns its dk / dv
 // rows (plain stores); dq parts and dp are accumulated with fp32 atomics (4 key tiles per query row
-// at T = 250; dp additionally across utterances).  All products run as 64 x 64 x 64 register-tiled
-// FMA mini-GEMMs out of shared memory (fp32 CUDA cores: the first training version; the tensor-core
-// tiling is fixed by the same index algebra).
+// at T = 250; dp additionally across utterances).  All products run as warp-level TF32 tensor-core
+// MMAs (mma.sync.m16n8k8, fp32 accumulate) out of shared memory: the eight products of a tile pair
+// need their operands in both orientations (P^T do, g^T (q+u), g K, ...), which the register
+// fragments of mma.sync read from ONE row-major copy - strides (1, 68) / (68, 1) are both bank-
+// conflict free - where tcgen05 would need K-major transposed copies of five tiles.  Operands are
+// rounded to TF32 (nearest) when they enter shared memory, like the forward's TMA loads.  The fp32
+// FMA version of this kernel took 506 us per launch at the C2 shape.
 #include <atomic>
 
 #include "host.h"
@@ -73,6 +77,41 @@ __device__ __forceinline__ void red_add(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
+__device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                         uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+               "{%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// One warp: acc[16 x 8 NT] += A[16 x 8 KS] . B[8 KS x 8 NT] out of shared memory.
+// A(m, k) = a[m * a_sm + k * a_sk], B(k, n) = b[k * b_sk + n * b_sn]; g = lane >> 2, t = lane & 3.
+// Fragment layout of mma.m16n8k8: a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4); b0 (t, g)
+// b1 (t+4, g); c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1).
+template <int NT, int KS>
+__device__ __forceinline__ void warp_mma(float (&acc)[NT][4], const float* a, int a_sm, int a_sk,
+                                         const float* b, int b_sk, int b_sn, int g, int t) {
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    const int k0 = 8 * ks + t;
+    const uint32_t a0 = __float_as_uint(a[g * a_sm + k0 * a_sk]);
+    const uint32_t a1 = __float_as_uint(a[(g + 8) * a_sm + k0 * a_sk]);
+    const uint32_t a2 = __float_as_uint(a[g * a_sm + (k0 + 4) * a_sk]);
+    const uint32_t a3 = __float_as_uint(a[(g + 8) * a_sm + (k0 + 4) * a_sk]);
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const uint32_t b0 = __float_as_uint(b[k0 * b_sk + (8 * nt + g) * b_sn]);
+      const uint32_t b1 = __float_as_uint(b[(k0 + 4) * b_sk + (8 * nt + g) * b_sn]);
+      mma_tf32(acc[nt], a0, a1, a2, a3, b0, b1);
+    }
+  }
+}
+
+__device__ __forceinline__ float4 tf32x4(float4 v) {
+  return make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 relpos_attn_bwd_kernel(const Params p) {
   extern __shared__ __align__(16) float sm[];
@@ -91,7 +130,10 @@ relpos_attn_bwd_kernel(const Params p) {
   pdl_launch_dependents();
   pdl_wait();
   const int tid = threadIdx.x;
-  const int ti = tid >> 4, tj = tid & 15;   // 16 x 16 thread grid
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t4 = lane & 3;        // mma fragment coordinates
+  const int wr = 16 * (warp & 3);                // this warp's 16 rows of a 64-row output tile
+  const int wc = 32 * (warp >> 2);               // ... and its 32 columns
   const int T = p.T, H = p.H;
   const int h = blockIdx.y, b = blockIdx.z;
   const int j0 = blockIdx.x * kT;
@@ -125,13 +167,13 @@ relpos_attn_bwd_kernel(const Params p) {
       kk = ld_act4(reinterpret_cast<const float4*>(base + HD));
       vv = ld_act4(reinterpret_cast<const float4*>(base + 2 * HD));
     }
-    *reinterpret_cast<float4*>(sK + jj * kLD + 4 * q4) = kk;
-    *reinterpret_cast<float4*>(sV + jj * kLD + 4 * q4) = vv;
+    *reinterpret_cast<float4*>(sK + jj * kLD + 4 * q4) = tf32x4(kk);
+    *reinterpret_cast<float4*>(sV + jj * kLD + 4 * q4) = tf32x4(vv);
   }
 
   const float scale = 0.125f;                       // 1 / sqrt(d_k)
   const float scale2 = 0.125f * 1.4426950408889634f; // the forward's exp2-domain scale
-  // dk / dv accumulators: rows (keys) 4 ti .. +3, columns 4 tj .. +3
+  // dk / dv accumulators in mma layout: keys wr + g (+8), columns wc + 8 nt + 2 t4 (+1)
   float acc_dk[4][4], acc_dv[4][4];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
@@ -153,9 +195,9 @@ relpos_attn_bwd_kernel(const Params p) {
       }
       const float4 uu = __ldg(reinterpret_cast<const float4*>(p.u + hcol + 4 * q4));
       const float4 vb = __ldg(reinterpret_cast<const float4*>(p.v + hcol + 4 * q4));
-      *reinterpret_cast<float4*>(sQu + ii * kLD + 4 * q4) = make_float4(q.x + uu.x, q.y + uu.y, q.z + uu.z, q.w + uu.w);
-      *reinterpret_cast<float4*>(sQv + ii * kLD + 4 * q4) = make_float4(q.x + vb.x, q.y + vb.y, q.z + vb.z, q.w + vb.w);
-      *reinterpret_cast<float4*>(sdO + ii * kLD + 4 * q4) = d4;
+      *reinterpret_cast<float4*>(sQu + ii * kLD + 4 * q4) = tf32x4(make_float4(q.x + uu.x, q.y + uu.y, q.z + uu.z, q.w + uu.w));
+      *reinterpret_cast<float4*>(sQv + ii * kLD + 4 * q4) = tf32x4(make_float4(q.x + vb.x, q.y + vb.y, q.z + vb.z, q.w + vb.w));
+      *reinterpret_cast<float4*>(sdO + ii * kLD + 4 * q4) = tf32x4(d4);
     }
     {
       // D_i: four threads per query row, 16 columns each
@@ -185,217 +227,140 @@ relpos_attn_bwd_kernel(const Params p) {
       float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r >= 0 && r <= 2 * T - 2 && c < kBand - 1)
         x = ld_act4(reinterpret_cast<const float4*>(p.pos + static_cast<long long>(r) * p.ld_pos + hcol + 4 * q4));
-      *reinterpret_cast<float4*>(sPb + c * kLD + 4 * q4) = x;
+      *reinterpret_cast<float4*>(sPb + c * kLD + 4 * q4) = tf32x4(x);
     }
     __syncthreads();
 
-    // ---- S = (q+u) K^T, dP = do V^T   (rows i = ti + 16 a, columns j = tj + 16 c) ----
+    // ---- R = (q+v) Pband^T: 64 x 128, this warp rows wr .., band columns 64 (warp >> 2) .. ----
+    {
+      float cr[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) cr[nt][e] = 0.f;
+      const int wcb = 64 * (warp >> 2);
+      warp_mma<8, 8>(cr, sQv + wr * kLD, kLD, 1, sPb + wcb * kLD, 1, kLD, g, t4);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int col = wcb + 8 * nt + 2 * t4;
+        *reinterpret_cast<float2*>(sR + (wr + g) * kLDR + col) = make_float2(cr[nt][0], cr[nt][1]);
+        *reinterpret_cast<float2*>(sR + (wr + g + 8) * kLDR + col) = make_float2(cr[nt][2], cr[nt][3]);
+      }
+    }
+    // ---- S = (q+u) K^T, dP = do V^T: this warp rows wr .., key columns wc .. ----
     float cs[4][4], ce[4][4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) { cs[a][c] = 0.f; ce[a][c] = 0.f; }
-#pragma unroll 4
-    for (int d4 = 0; d4 < kD / 4; ++d4) {
-      float4 qa[4], da[4], kb[4], vb[4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        qa[a] = lds4(sQu + (ti + 16 * a) * kLD + 4 * d4);
-        da[a] = lds4(sdO + (ti + 16 * a) * kLD + 4 * d4);
-        kb[a] = lds4(sK + (tj + 16 * a) * kLD + 4 * d4);
-        vb[a] = lds4(sV + (tj + 16 * a) * kLD + 4 * d4);
-      }
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          cs[a][c] += qa[a].x * kb[c].x + qa[a].y * kb[c].y + qa[a].z * kb[c].z + qa[a].w * kb[c].w;
-          ce[a][c] += da[a].x * vb[c].x + da[a].y * vb[c].y + da[a].z * vb[c].z + da[a].w * vb[c].w;
-        }
-    }
-    // ---- R = (q+v) Pband^T   (rows ti + 16 a, band columns tj + 16 c, c < 8) ----
-    {
-      float cr[4][8];
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) cr[a][c] = 0.f;
-#pragma unroll 2
-      for (int d4 = 0; d4 < kD / 4; ++d4) {
-        float4 qa[4], pb[8];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) qa[a] = lds4(sQv + (ti + 16 * a) * kLD + 4 * d4);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) pb[c] = lds4(sPb + (tj + 16 * c) * kLD + 4 * d4);
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-            cr[a][c] += qa[a].x * pb[c].x + qa[a].y * pb[c].y + qa[a].z * pb[c].z + qa[a].w * pb[c].w;
-      }
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) sR[(ti + 16 * a) * kLDR + tj + 16 * c] = cr[a][c];
-    }
-    __syncthreads();
+      for (int e = 0; e < 4; ++e) { cs[nt][e] = 0.f; ce[nt][e] = 0.f; }
+    warp_mma<4, 8>(cs, sQu + wr * kLD, kLD, 1, sK + wc * kLD, 1, kLD, g, t4);
+    warp_mma<4, 8>(ce, sdO + wr * kLD, kLD, 1, sV + wc * kLD, 1, kLD, g, t4);
+    __syncthreads();   // every band score is in sR
     // ---- P and g = dL / d a  for this thread's 16 (i, j) ----
-    float g[4][4];
+    float gk[4][4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const int ii = ti + 16 * a;
+    for (int h2 = 0; h2 < 2; ++h2) {
+      const int ii = wr + g + 8 * h2;
       const float lse = s_lse[ii], Di = s_Di[ii];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int jj = tj + 16 * c;
-        const float r = sR[ii * kLDR + jj - ii + (kT - 1)];
-        const bool valid = (i0 + ii < T) && (j0 + jj < len);
-        const float pr = valid ? exp2f((cs[a][c] + r) * scale2 - lse) : 0.f;
-        float mk = 1.0f;
-        if (p.drop_keep != nullptr && valid)
-          mk = p.drop_keep[((static_cast<long long>(b) * H + h) * T + i0 + ii) * p.ld_drop + j0 + jj] != 0
-                   ? p.drop_scale : 0.f;
-        g[a][c] = pr * (ce[a][c] * mk - Di) * scale;
-        sS[ii * kLD + jj] = pr * mk;
-        sdS[ii * kLD + jj] = g[a][c];
-      }
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e2 = 0; e2 < 2; ++e2) {
+          const int e = 2 * h2 + e2;
+          const int jj = wc + 8 * nt + 2 * t4 + e2;
+          const float r = sR[ii * kLDR + jj - ii + (kT - 1)];
+          const bool valid = (i0 + ii < T) && (j0 + jj < len);
+          const float pr = valid ? exp2f((cs[nt][e] + r) * scale2 - lse) : 0.f;
+          float mk = 1.0f;
+          if (p.drop_keep != nullptr && valid)
+            mk = p.drop_keep[((static_cast<long long>(b) * H + h) * T + i0 + ii) * p.ld_drop + j0 + jj] != 0
+                     ? p.drop_scale : 0.f;
+          gk[nt][e] = round_tf32(pr * (ce[nt][e] * mk - Di) * scale);
+          sS[ii * kLD + jj] = round_tf32(pr * mk);
+          sdS[ii * kLD + jj] = gk[nt][e];
+        }
     }
     __syncthreads();  // every band score has been read
     for (int idx = tid; idx < kT * kLDR / 4; idx += kThreads)
       reinterpret_cast<float4*>(sR)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int ii = ti + 16 * a, jj = tj + 16 * c;
-        sR[ii * kLDR + jj - ii + (kT - 1)] = g[a][c];   // g in band layout: column = jj - ii + 63
+      for (int e = 0; e < 4; ++e) {
+        const int ii = wr + g + 8 * (e >> 1), jj = wc + 8 * nt + 2 * t4 + (e & 1);
+        sR[ii * kLDR + jj - ii + (kT - 1)] = gk[nt][e];   // g in band layout: column = jj - ii + 63
       }
     __syncthreads();
 
     // ---- dv[j][d] += sum_i P[i][j] do[i][d],  dk[j][d] += sum_i g[i][j] (q+u)[i][d]
-    //      (rows j = 4 ti .. +3, columns d = 4 tj .. +3) ----
-#pragma unroll 4
-    for (int i = 0; i < kT; ++i) {
-      const float4 pr = lds4(sS + i * kLD + 4 * ti);
-      const float4 gg = lds4(sdS + i * kLD + 4 * ti);
-      const float4 od = lds4(sdO + i * kLD + 4 * tj);
-      const float4 qu = lds4(sQu + i * kLD + 4 * tj);
-      const float pv[4] = {pr.x, pr.y, pr.z, pr.w};
-      const float gv[4] = {gg.x, gg.y, gg.z, gg.w};
-      const float ov[4] = {od.x, od.y, od.z, od.w};
-      const float qv[4] = {qu.x, qu.y, qu.z, qu.w};
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          acc_dv[a][c] = fmaf(pv[a], ov[c], acc_dv[a][c]);
-          acc_dk[a][c] = fmaf(gv[a], qv[c], acc_dk[a][c]);
-        }
-    }
-    // ---- dq_ac[i][d] = sum_j g[i][j] K[j][d],  dq_bd[i][d] = sum_c gband[i][c] Pband[c][d]
-    //      (rows i = 4 ti .. +3, columns d = 4 tj .. +3) ----
+    //      (this warp: keys wr .., columns wc ..; A read transposed out of the row-major tiles) ----
+    warp_mma<4, 8>(acc_dv, sS + wr, 1, kLD, sdO + wc, kLD, 1, g, t4);
+    warp_mma<4, 8>(acc_dk, sdS + wr, 1, kLD, sQu + wc, kLD, 1, g, t4);
+    // ---- dq_ac[i][d] = sum_j g[i][j] K[j][d],  dq_bd[i][d] = sum_c gband[i][c] Pband[c][d] ----
     {
       float qa[4][4], qb[4][4];
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { qa[a][c] = 0.f; qb[a][c] = 0.f; }
-#pragma unroll 2
-      for (int j4 = 0; j4 < kT / 4; ++j4) {
-        float4 gs[4], kr[4];
+        for (int e = 0; e < 4; ++e) { qa[nt][e] = 0.f; qb[nt][e] = 0.f; }
+      warp_mma<4, 8>(qa, sdS + wr * kLD, kLD, 1, sK + wc, kLD, 1, g, t4);
+      warp_mma<4, 16>(qb, sR + wr * kLDR, kLDR, 1, sPb + wc, kLD, 1, g, t4);
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          gs[a] = lds4(sdS + (4 * ti + a) * kLD + 4 * j4);
-          kr[a] = lds4(sK + (4 * j4 + a) * kLD + 4 * tj);
-        }
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          const float ga[4] = {gs[a].x, gs[a].y, gs[a].z, gs[a].w};
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            qa[a][0] = fmaf(ga[jj], kr[jj].x, qa[a][0]);
-            qa[a][1] = fmaf(ga[jj], kr[jj].y, qa[a][1]);
-            qa[a][2] = fmaf(ga[jj], kr[jj].z, qa[a][2]);
-            qa[a][3] = fmaf(ga[jj], kr[jj].w, qa[a][3]);
-          }
-        }
-      }
-#pragma unroll 2
-      for (int c4 = 0; c4 < kBand / 4; ++c4) {
-        float4 gs[4], pr[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          gs[a] = lds4(sR + (4 * ti + a) * kLDR + 4 * c4);
-          pr[a] = lds4(sPb + (4 * c4 + a) * kLD + 4 * tj);
-        }
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          const float ga[4] = {gs[a].x, gs[a].y, gs[a].z, gs[a].w};
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            qb[a][0] = fmaf(ga[cc], pr[cc].x, qb[a][0]);
-            qb[a][1] = fmaf(ga[cc], pr[cc].y, qb[a][1]);
-            qb[a][2] = fmaf(ga[cc], pr[cc].z, qb[a][2]);
-            qb[a][3] = fmaf(ga[cc], pr[cc].w, qb[a][3]);
-          }
-        }
-      }
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const int i = i0 + 4 * ti + a;
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const int i = i0 + wr + g + 8 * h2;
         if (i < T) {
-          float* pa = p.dq_ac + (row0 + i) * HD + hcol + 4 * tj;
-          float* pb = p.dq_bd + (row0 + i) * HD + hcol + 4 * tj;
+          float* pa = p.dq_ac + (row0 + i) * HD + hcol + wc + 2 * t4;
+          float* pb = p.dq_bd + (row0 + i) * HD + hcol + wc + 2 * t4;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            red_add(pa + c, qa[a][c]);
-            red_add(pb + c, qb[a][c]);
+          for (int nt = 0; nt < 4; ++nt) {
+            red_add(pa + 8 * nt, qa[nt][2 * h2]);
+            red_add(pa + 8 * nt + 1, qa[nt][2 * h2 + 1]);
+            red_add(pb + 8 * nt, qb[nt][2 * h2]);
+            red_add(pb + 8 * nt + 1, qb[nt][2 * h2 + 1]);
           }
         }
       }
     }
-    // ---- dp[rbase + c][d] += sum_i gband[i][c] (q+v)[i][d]   (band rows 8 ti .. +7, columns 4 tj .. +3)
-    {
-      float pp[8][4];
+    // ---- dp[rbase + c][d] += sum_i gband[i][c] (q+v)[i][d]: 128 band rows x 64, this warp band
+    //      rows 32 (warp & 3) .. +31 (two m-tiles), columns wc .. ----
 #pragma unroll
-      for (int a = 0; a < 8; ++a)
+    for (int mt = 0; mt < 2; ++mt) {
+      float pp[4][4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) pp[a][c] = 0.f;
-#pragma unroll 4
-      for (int i = 0; i < kT; ++i) {
-        const float4 g0 = lds4(sR + i * kLDR + 8 * ti);
-        const float4 g1 = lds4(sR + i * kLDR + 8 * ti + 4);
-        const float4 qv = lds4(sQv + i * kLD + 4 * tj);
-        const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-        for (int a = 0; a < 8; ++a) {
-          pp[a][0] = fmaf(gv[a], qv.x, pp[a][0]);
-          pp[a][1] = fmaf(gv[a], qv.y, pp[a][1]);
-          pp[a][2] = fmaf(gv[a], qv.z, pp[a][2]);
-          pp[a][3] = fmaf(gv[a], qv.w, pp[a][3]);
-        }
-      }
+        for (int e = 0; e < 4; ++e) pp[nt][e] = 0.f;
+      const int c0 = 32 * (warp & 3) + 16 * mt;
+      warp_mma<4, 8>(pp, sR + c0, 1, kLDR, sQv + wc, kLD, 1, g, t4);
 #pragma unroll
-      for (int a = 0; a < 8; ++a) {
-        const int r = rbase + 8 * ti + a;
-        if (r >= 0 && r <= 2 * T - 2 && 8 * ti + a < kBand - 1) {
-          float* dst = p.dpos + static_cast<long long>(r) * HD + hcol + 4 * tj;
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const int c = c0 + g + 8 * h2;
+        const int r = rbase + c;
+        if (r >= 0 && r <= 2 * T - 2 && c < kBand - 1) {
+          float* dst = p.dpos + static_cast<long long>(r) * HD + hcol + wc + 2 * t4;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) red_add(dst + c, pp[a][c]);
+          for (int nt = 0; nt < 4; ++nt) {
+            red_add(dst + 8 * nt, pp[nt][2 * h2]);
+            red_add(dst + 8 * nt + 1, pp[nt][2 * h2 + 1]);
+          }
         }
       }
     }
   }
   // ---- this CTA's dk / dv rows ----
 #pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const int j = j0 + 4 * ti + a;
+  for (int h2 = 0; h2 < 2; ++h2) {
+    const int j = j0 + wr + g + 8 * h2;
     if (j < T) {
-      *reinterpret_cast<float4*>(dk_out + (row0 + j) * p.ld_dqkv + 4 * tj) =
-          make_float4(acc_dk[a][0], acc_dk[a][1], acc_dk[a][2], acc_dk[a][3]);
-      *reinterpret_cast<float4*>(dv_out + (row0 + j) * p.ld_dqkv + 4 * tj) =
-          make_float4(acc_dv[a][0], acc_dv[a][1], acc_dv[a][2], acc_dv[a][3]);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int d = wc + 8 * nt + 2 * t4;
+        *reinterpret_cast<float2*>(dk_out + (row0 + j) * p.ld_dqkv + d) =
+            make_float2(acc_dk[nt][2 * h2], acc_dk[nt][2 * h2 + 1]);
+        *reinterpret_cast<float2*>(dv_out + (row0 + j) * p.ld_dqkv + d) =
+            make_float2(acc_dv[nt][2 * h2], acc_dv[nt][2 * h2 + 1]);
+      }
     }
   }
 }
