@@ -242,15 +242,16 @@ int tavsr_relpos_attn_fwd_dropout(const float* qkv, long long ld_qkv, const floa
 
 /* Backward of the attention core (training).  Given dctx = d loss / d ctx, the forward's qkv, pos,
  * u, v, lens, ctx and lse (fp32), writes the k and v blocks of dqkv [B*T, 3*H*64] and ACCUMULATES
- * (fp32 atomics; zero them first) the two parts of d q into dq_ac / dq_bd [B*T, H*64]
- * (d q = dq_ac + dq_bd; d pos_bias_u = column sums of dq_ac, d pos_bias_v = column sums of dq_bd)
- * and d linear_pos(pos_emb) into dpos [2T-1, H*64] (summed over utterances).  Probabilities are
- * recomputed from lse: nothing of size T x T is stored.  Arithmetic:
- * oracle/bwd_formulas.py::relpos_attn_core_bwd (verified against autograd). */
+ * (fp32 atomics; zero them first): d q into the q block of dqkv, d pos_bias_u / d pos_bias_v into
+ * du / dvb [H*64], and d linear_pos(pos_emb) into PER-UTTERANCE slabs dpos [B][2T-1][H*64] (the
+ * caller sums the slabs: tavsr_col_sums over a [B, (2T-1)*H*64] view).  Probabilities are
+ * recomputed from lse: nothing of size T x T is stored.  The products run as TF32 mma.sync
+ * tensor-core MMAs with fp32 accumulation.  Arithmetic: oracle/bwd_formulas.py::relpos_attn_core_bwd
+ * (verified against autograd). */
 int tavsr_relpos_attn_bwd(const float* qkv, long long ld_qkv, const float* pos, long long ld_pos,
                           const float* u, const float* v, const int32_t* lens, const float* ctx,
                           long long ld_ctx, const float* dctx, long long ld_dctx, const float* lse,
-                          float* dqkv, long long ld_dqkv, float* dq_ac, float* dq_bd, float* dpos,
+                          float* dqkv, long long ld_dqkv, float* du, float* dvb, float* dpos,
                           const uint8_t* drop_keep /* NULL, or the forward's keep mask */,
                           long long ld_drop, float drop_scale, int B, int T, int H, void* stream);
 

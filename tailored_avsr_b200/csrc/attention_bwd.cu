@@ -61,9 +61,11 @@ struct Params {
   const float* o; long long ld_o;       // forward context [B*T, H*64]
   const float* dout; long long ld_do;   // d loss / d context
   const float* lse;                     // [B, H, T] base-2 log-sum-exp of the scaled scores
-  float* dqkv; long long ld_dqkv;       // [B*T, 3*H*64]: k and v blocks written here
-  float* dq_ac; float* dq_bd;           // [B*T, H*64] each, zero-initialised, atomically accumulated
-  float* dpos;                          // [2T-1, H*64] zero-initialised, atomically accumulated
+  float* dqkv; long long ld_dqkv;       // [B*T, 3*H*64]: k and v blocks written; the q block is
+                                        // zero-initialised by the caller and atomically accumulated
+  float* du; float* dvb;                // [H*64] each, zero-initialised: d pos_bias_u / d pos_bias_v
+  float* dpos;                          // [B][2T-1][H*64] zero-initialised: PER-UTTERANCE slabs (the
+                                        // caller sums them): no cross-utterance atomic contention
   // attention-probability dropout of the forward (optional): keep[b][h][i][j] bytes, row pitch
   // ld_drop, kept probabilities scaled by drop_scale.  With m_ij = keep_ij * drop_scale:
   //   o_i = sum_j m_ij P_ij v_j,  dP_ij = m_ij (do_i . v_j),  dv_j = sum_i m_ij P_ij do_i,
@@ -75,6 +77,26 @@ struct Params {
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void red_add(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+// Accumulate one mma C fragment (rows g / g + 8, column pairs 2 t4) with 16-byte reductions: lanes
+// t4 and t4 ^ 1 swap halves so that the even lane owns four consecutive columns of row g and the
+// odd lane four of row g + 8 (a quarter of the scalar red count: the kernel is bound by its
+// reductions into dq / dpos once the products run on tensor cores).
+// `base` points at (row 0, column 8 nt) of the fragment; `row_ok(r)` guards the fragment row r.
+__device__ __forceinline__ void red_add_v4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w) : "memory");
+}
+template <typename RowOk>
+__device__ __forceinline__ void red_fragment(float* base, long long ld, const float (&c)[4], int g, int t4,
+                                             RowOk row_ok) {
+  const bool odd = (t4 & 1) != 0;
+  const float s0 = odd ? c[0] : c[2], s1 = odd ? c[1] : c[3];
+  const float r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+  const float4 v = odd ? make_float4(r0, r1, c[2], c[3]) : make_float4(c[0], c[1], r0, r1);
+  const int row = odd ? g + 8 : g;
+  if (row_ok(row)) red_add_v4(base + row * ld + 2 * (t4 & ~1), v);
 }
 
 __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
@@ -180,6 +202,11 @@ relpos_attn_bwd_kernel(const Params p) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) { acc_dk[a][c] = 0.f; acc_dv[a][c] = 0.f; }
 
+  float su[4][2], sv[4][2];   // per-thread column sums of the two dq parts (d pos_bias_u / _v)
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) { su[nt][0] = su[nt][1] = 0.f; sv[nt][0] = sv[nt][1] = 0.f; }
+  float pp[2][4][4];          // dpos accumulator carried across two consecutive query tiles
+  float* dpos_b = p.dpos + static_cast<long long>(b) * (2 * T - 1) * HD;
   const int n_qt = (T + kT - 1) / kT;
   for (int qt = 0; qt < n_qt; ++qt) {
     const int i0 = qt * kT;
@@ -297,7 +324,8 @@ relpos_attn_bwd_kernel(const Params p) {
     //      (this warp: keys wr .., columns wc ..; A read transposed out of the row-major tiles) ----
     warp_mma<4, 8>(acc_dv, sS + wr, 1, kLD, sdO + wc, kLD, 1, g, t4);
     warp_mma<4, 8>(acc_dk, sdS + wr, 1, kLD, sQu + wc, kLD, 1, g, t4);
-    // ---- dq_ac[i][d] = sum_j g[i][j] K[j][d],  dq_bd[i][d] = sum_c gband[i][c] Pband[c][d] ----
+    // ---- dq[i][d] = sum_j g[i][j] K[j][d]  +  sum_c gband[i][c] Pband[c][d]; the column sums of
+    //      the two parts are d pos_bias_u / d pos_bias_v (kept per thread, reduced at the end) ----
     {
       float qa[4][4], qb[4][4];
 #pragma unroll
@@ -306,48 +334,70 @@ relpos_attn_bwd_kernel(const Params p) {
         for (int e = 0; e < 4; ++e) { qa[nt][e] = 0.f; qb[nt][e] = 0.f; }
       warp_mma<4, 8>(qa, sdS + wr * kLD, kLD, 1, sK + wc, kLD, 1, g, t4);
       warp_mma<4, 16>(qb, sR + wr * kLDR, kLDR, 1, sPb + wc, kLD, 1, g, t4);
+      float* pq = p.dqkv + (row0 + i0 + wr) * p.ld_dqkv + hcol + wc;
+      auto q_ok = [&](int r) { return i0 + wr + r < T; };
 #pragma unroll
-      for (int h2 = 0; h2 < 2; ++h2) {
-        const int i = i0 + wr + g + 8 * h2;
-        if (i < T) {
-          float* pa = p.dq_ac + (row0 + i) * HD + hcol + wc + 2 * t4;
-          float* pb = p.dq_bd + (row0 + i) * HD + hcol + wc + 2 * t4;
-#pragma unroll
-          for (int nt = 0; nt < 4; ++nt) {
-            red_add(pa + 8 * nt, qa[nt][2 * h2]);
-            red_add(pa + 8 * nt + 1, qa[nt][2 * h2 + 1]);
-            red_add(pb + 8 * nt, qb[nt][2 * h2]);
-            red_add(pb + 8 * nt + 1, qb[nt][2 * h2 + 1]);
-          }
-        }
+      for (int nt = 0; nt < 4; ++nt) {
+        // rows >= T have g == 0, so the unguarded column sums are exact
+        su[nt][0] += qa[nt][0] + qa[nt][2]; su[nt][1] += qa[nt][1] + qa[nt][3];
+        sv[nt][0] += qb[nt][0] + qb[nt][2]; sv[nt][1] += qb[nt][1] + qb[nt][3];
+        const float qs[4] = {qa[nt][0] + qb[nt][0], qa[nt][1] + qb[nt][1], qa[nt][2] + qb[nt][2],
+                             qa[nt][3] + qb[nt][3]};
+        red_fragment(pq + 8 * nt, p.ld_dqkv, qs, g, t4, q_ok);
       }
     }
-    // ---- dp[rbase + c][d] += sum_i gband[i][c] (q+v)[i][d]: 128 band rows x 64, this warp band
-    //      rows 32 (warp & 3) .. +31 (two m-tiles), columns wc .. ----
+    // ---- dp[rbase + c][d] += sum_i gband[i][c] (q+v)[i][d]: 128 band rows x 64.  Consecutive query
+    //      tiles shift the band by 64 rows, so the lower half of this pair's band is the upper half
+    //      of the next pair's: a warp takes band chunk ((warp & 3) + 2 qt) mod 4 (32 rows), i.e. it
+    //      alternates lower half -> upper half over the SAME absolute rows, keeps the accumulator in
+    //      registers in between and emits once per two pairs (half the reductions) ----
+    {
+      const int chunk = ((warp & 3) + 2 * qt) & 3;
+      const bool lower = chunk < 2;
+      if (lower || qt == 0) {
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-      float pp[4][4];
+        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
+          for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) pp[nt][e] = 0.f;
-      const int c0 = 32 * (warp & 3) + 16 * mt;
-      warp_mma<4, 8>(pp, sR + c0, 1, kLDR, sQv + wc, kLD, 1, g, t4);
+            for (int e = 0; e < 4; ++e) pp[mt][nt][e] = 0.f;
+      }
 #pragma unroll
-      for (int h2 = 0; h2 < 2; ++h2) {
-        const int c = c0 + g + 8 * h2;
-        const int r = rbase + c;
-        if (r >= 0 && r <= 2 * T - 2 && c < kBand - 1) {
-          float* dst = p.dpos + static_cast<long long>(r) * HD + hcol + wc + 2 * t4;
+      for (int mt = 0; mt < 2; ++mt)
+        warp_mma<4, 8>(pp[mt], sR + 32 * chunk + 16 * mt, 1, kLDR, sQv + wc, kLD, 1, g, t4);
+      if (!lower || qt == n_qt - 1) {
 #pragma unroll
-          for (int nt = 0; nt < 4; ++nt) {
-            red_add(dst + 8 * nt, pp[nt][2 * h2]);
-            red_add(dst + 8 * nt + 1, pp[nt][2 * h2 + 1]);
-          }
+        for (int mt = 0; mt < 2; ++mt) {
+          const int c0 = 32 * chunk + 16 * mt;
+          // (rbase + c0 may be negative: the row guard keeps every dereferenced address in range;
+          // band column 127 only ever carries the previous pair's row 63 - its own operands are 0)
+          float* dst = dpos_b + (static_cast<long long>(rbase) + c0) * HD + hcol + wc;
+          auto r_ok = [&](int r) {
+            const int rr = rbase + c0 + r;
+            return rr >= 0 && rr <= 2 * T - 2;
+          };
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) red_fragment(dst + 8 * nt, HD, pp[mt][nt], g, t4, r_ok);
         }
       }
     }
   }
+  // ---- d pos_bias_u / d pos_bias_v: column sums over this CTA's query rows (all tiles) ----
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      float a = su[nt][e], c = sv[nt][e];
+#pragma unroll
+      for (int off = 4; off < 32; off <<= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, off);
+        c += __shfl_xor_sync(0xffffffffu, c, off);
+      }
+      if (g == 0) {
+        red_add(p.du + hcol + wc + 8 * nt + 2 * t4 + e, a);
+        red_add(p.dvb + hcol + wc + 8 * nt + 2 * t4 + e, c);
+      }
+    }
   // ---- this CTA's dk / dv rows ----
 #pragma unroll
   for (int h2 = 0; h2 < 2; ++h2) {
@@ -374,11 +424,11 @@ extern "C" int tavsr_relpos_attn_bwd(const float* qkv, long long ld_qkv, const f
                                      long long ld_pos, const float* u, const float* v,
                                      const int32_t* lens, const float* ctx, long long ld_ctx,
                                      const float* dctx, long long ld_dctx, const float* lse,
-                                     float* dqkv, long long ld_dqkv, float* dq_ac, float* dq_bd,
+                                     float* dqkv, long long ld_dqkv, float* du, float* dvb,
                                      float* dpos, const uint8_t* drop_keep, long long ld_drop,
                                      float drop_scale, int B, int T, int H, void* stream) {
   TAVSR_REQUIRE(B > 0 && T > 0 && H > 0, "attn_bwd: bad shape B=%d T=%d H=%d", B, T, H);
-  TAVSR_REQUIRE(qkv && pos && u && v && ctx && dctx && lse && dqkv && dq_ac && dq_bd && dpos,
+  TAVSR_REQUIRE(qkv && pos && u && v && ctx && dctx && lse && dqkv && du && dvb && dpos,
                 "attn_bwd: null pointer");
   TAVSR_REQUIRE(ld_qkv % 4 == 0 && ld_pos % 4 == 0 && ld_ctx % 4 == 0 && ld_dctx % 4 == 0 &&
                     ld_dqkv % 4 == 0,
@@ -386,7 +436,7 @@ extern "C" int tavsr_relpos_attn_bwd(const float* qkv, long long ld_qkv, const f
   attn_bwd::Params p;
   p.qkv = qkv; p.ld_qkv = ld_qkv; p.pos = pos; p.ld_pos = ld_pos; p.u = u; p.v = v; p.lens = lens;
   p.o = ctx; p.ld_o = ld_ctx; p.dout = dctx; p.ld_do = ld_dctx; p.lse = lse;
-  p.dqkv = dqkv; p.ld_dqkv = ld_dqkv; p.dq_ac = dq_ac; p.dq_bd = dq_bd; p.dpos = dpos;
+  p.dqkv = dqkv; p.ld_dqkv = ld_dqkv; p.du = du; p.dvb = dvb; p.dpos = dpos;
   TAVSR_REQUIRE(drop_keep == nullptr || (ld_drop >= T && drop_scale >= 1.0f),
                 "attn_bwd: keep mask pitch %lld < T or drop_scale < 1", ld_drop);
   p.drop_keep = drop_keep; p.ld_drop = ld_drop; p.drop_scale = drop_scale;

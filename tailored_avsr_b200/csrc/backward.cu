@@ -353,28 +353,40 @@ csgu_conv_bwd_kernel(const float* __restrict__ h, long long ldh, const float* __
   const int t0 = blockIdx.y * kSeg;
   const int b = blockIdx.z;
   const long long row0 = static_cast<long long>(b) * T;
-  // tile load, eight rows per pass with all 32 loads of a pass in flight before the first use (one
-  // row at a time the kernel spent most of its 280 us waiting on dependent L2 round trips)
-  for (int rb = 0; rb < kRows; rb += 8) {
-    float2 st[8];
-    float gq[8], uq[8], rq[8];
+  // tile load, eight rows per pass, software-pipelined: the 32 loads of pass p + 1 are issued
+  // before pass p's values are consumed, so the kernel waits for one L2 round trip per tile instead
+  // of one per pass (one row at a time it spent most of its 280 us on dependent round trips)
+  struct RowBatch { float2 st[8]; float gq[8], uq[8], rq[8]; };
+  auto fetch = [&](RowBatch& v, int rb) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int t = t0 - kHalo + rb + i;
       const bool in = rb + i < kRows && t >= 0 && t < T;
-      st[i] = in ? stats[row0 + t] : make_float2(0.f, 0.f);
-      gq[i] = in ? ld_act(h + (row0 + t) * ldh + Ch + c) : 0.f;
-      uq[i] = in ? ld_act(du + (row0 + t) * ldu + c) : 0.f;
-      rq[i] = in ? ld_act(h + (row0 + t) * ldh + c) : 0.f;
+      v.st[i] = in ? stats[row0 + t] : make_float2(0.f, 0.f);
+      v.gq[i] = in ? ld_act(h + (row0 + t) * ldh + Ch + c) : 0.f;
+      v.uq[i] = in ? ld_act(du + (row0 + t) * ldu + c) : 0.f;
+      v.rq[i] = in ? ld_act(h + (row0 + t) * ldh + c) : 0.f;
     }
+  };
+  auto stash = [&](const RowBatch& v, int rb) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int t = t0 - kHalo + rb + i;
       if (rb + i < kRows) {
         const bool in = t >= 0 && t < T;
-        s_n[(rb + i) * kCh + threadIdx.x] = in ? (gq[i] - st[i].x) * st[i].y * gam + bet : 0.f;
-        s_dc[(rb + i) * kCh + threadIdx.x] = uq[i] * rq[i];
+        s_n[(rb + i) * kCh + threadIdx.x] = in ? (v.gq[i] - v.st[i].x) * v.st[i].y * gam + bet : 0.f;
+        s_dc[(rb + i) * kCh + threadIdx.x] = v.uq[i] * v.rq[i];
       }
+    }
+  };
+  {
+    RowBatch ba, bb;
+    fetch(ba, 0);
+    for (int rb = 0; rb < kRows; rb += 16) {
+      fetch(bb, rb + 8);
+      stash(ba, rb);
+      fetch(ba, rb + 16);
+      stash(bb, rb + 8);
     }
   }
   // every thread only reads the column it wrote: no barrier needed

@@ -506,16 +506,24 @@ ctc_loss_kernel(const float* __restrict__ logp, const int64_t* __restrict__ targ
       }
       n[i] = live[i] ? v + s_row[warp][buf][lab[i]] : kNeg;
     }
+    // occupancies: the L + 1 blank states (even s, label 0 = blank) all add into one slot - summed
+    // in registers and reduced by shuffles instead of ~100 same-address shared-memory atomics per
+    // time step, which made the gradient pass 10x the forward pass; label states keep the atomics
+    // (a label repeats a few times per utterance at most)
+    float occ_blank = 0.f;
 #pragma unroll
     for (int i = 0; i < kC; ++i) {
       bt[i] = n[i];
       const int s = lane * kC + i;
       if (s < S) {
         const float e = ex2f(apre[i] + bt[i] + nll2 - s_row[warp][buf][lab[i]]);
-        if (e > 0.f) atomicAdd(&s_occ[warp][lab[i]], e);
+        if ((s & 1) == 0) occ_blank += e;
+        else if (e > 0.f) atomicAdd(&s_occ[warp][lab[i]], e);
         if (t > 0) apre[i] = aws[static_cast<long long>(t - 1) * Sws + s];
       }
     }
+    occ_blank = warp_sum(occ_blank);
+    if (lane == 0 && occ_blank > 0.f) atomicAdd(&s_occ[warp][0], occ_blank);
     __syncwarp();
 #pragma unroll
     for (int q = 0; q < kVS; ++q)

@@ -114,25 +114,24 @@ def relpos_attn_bwd(qkv: torch.Tensor, pos: torch.Tensor, u: torch.Tensor, v: to
                     lens: Optional[torch.Tensor], ctx: torch.Tensor, dctx: torch.Tensor,
                     lse: torch.Tensor, B: int, T: int, H: int, drop: Optional[tuple] = None):
     """Backward of ops.relpos_attn (tavsr_relpos_attn_bwd); `drop` = the forward's (keep, scale).  Returns (dqkv (B*T, 3*H*64), dpos
-    (2T-1, H*64), du (H*64,), dv (H*64,)): d q = the two accumulated parts summed into dqkv's q
-    block, the pos_bias gradients are the column sums of the parts."""
+    (2T-1, H*64), du (H*64,), dv (H*64,))."""
     from . import ops
     for t, n in ((qkv, "qkv"), (pos, "pos"), (ctx, "ctx"), (dctx, "dctx")):
         _chk2d(t, n)
     M, HD = B * T, H * 64
     dev = qkv.device
-    dqkv = torch.empty((M, 3 * HD), device=dev, dtype=torch.float32)
-    acc = torch.zeros((2 * M + 2 * T - 1, HD), device=dev, dtype=torch.float32)   # one memset
-    dq_ac, dq_bd, dpos = acc[:M], acc[M:2 * M], acc[2 * M:]
+    R = 2 * T - 1
+    dqkv = torch.zeros((M, 3 * HD), device=dev, dtype=torch.float32)     # the q block is accumulated
+    acc = torch.zeros(B * R * HD + 2 * HD, device=dev, dtype=torch.float32)   # one memset
+    dpos_b, du, dv = acc[:B * R * HD], acc[B * R * HD:B * R * HD + HD], acc[B * R * HD + HD:]
     check(_lib.load().tavsr_relpos_attn_bwd(
         qkv.data_ptr(), qkv.stride(0), pos.data_ptr(), pos.stride(0), u.data_ptr(), v.data_ptr(),
         _p(lens), ctx.data_ptr(), ctx.stride(0), dctx.data_ptr(), dctx.stride(0), lse.data_ptr(),
-        dqkv.data_ptr(), dqkv.stride(0), dq_ac.data_ptr(), dq_bd.data_ptr(), dpos.data_ptr(),
+        dqkv.data_ptr(), dqkv.stride(0), du.data_ptr(), dv.data_ptr(), dpos_b.data_ptr(),
         drop[0].data_ptr() if drop is not None else None, drop[0].shape[3] if drop is not None else 0,
         float(drop[1]) if drop is not None else 1.0, B, T, H, _stream()), "tavsr_relpos_attn_bwd")
-    one = ops._cast_scalars(dev)[0]
-    ops.scale_add_rows(dq_ac, dq_bd, one, one, M, out=dqkv[:, :HD])
-    return dqkv, dpos, col_sums(dq_ac), col_sums(dq_bd)
+    dpos = col_sums(dpos_b.view(B, R * HD)).view(R, HD)     # sum of the per-utterance slabs
+    return dqkv, dpos, du, dv
 
 
 def col_sums(a: torch.Tensor, b: Optional[torch.Tensor] = None) -> torch.Tensor:
