@@ -300,6 +300,7 @@ int tavsr_merge_scores(const void* a1, long long ld1, int K1, const void* a2, lo
 /* Training form: the four biases (pool_b1, pool_b2, wproj_b1, wproj_b2) are read from the DEVICE
  * array `scal` instead of being passed by value (no host read-back of parameters per step). */
 int tavsr_merge_learned_ave_weights_dev(const float* dots1, const float* dots2, const int32_t* lens,
+                                        const int32_t* lens2 /* NULL, or branch 2's own lengths */,
                                         const float* scal, float inv_sqrt_size, float* w1, float* w2,
                                         int B, int T, void* stream);
 /* General form: dotsK holds npK partial pairs per frame ([B*T, npK, 2], summed inside) and each
@@ -448,6 +449,8 @@ int tavsr_csgu_conv_bwd(const float* h, long long ldh, const float* norm_g, cons
 size_t tavsr_merge_learned_ave_bwd_workspace_bytes(int B);
 int tavsr_merge_learned_ave_bwd(const float* x1, long long ld1, const float* x2, long long ld2,
                                 const float* dm, long long ldm, const int32_t* lens,
+                                const int32_t* lens2 /* NULL: branch 2 uses lens too; else its own
+                                                        lengths (audio-visual fusion) */,
                                 const float* a1, const float* b1, const float* a2, const float* b2,
                                 const float* scal, float* dx1, long long ldd1, float* dx2,
                                 long long ldd2, float* grads, void* workspace,

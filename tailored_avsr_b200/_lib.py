@@ -149,7 +149,7 @@ SIGNATURES = {
                                     c_int, c_int, c_int, c_void_p]),
     "tavsr_merge_learned_ave_bwd_workspace_bytes": (c_size_t, [c_int]),
     "tavsr_merge_learned_ave_bwd": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p,
-                                            c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,
+                                            c_longlong, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                             c_void_p, c_void_p, c_void_p, c_longlong,
                                             c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_int,
                                             c_int, c_int, c_void_p]),
@@ -157,7 +157,7 @@ SIGNATURES = {
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float,
                                    c_float, c_float, c_void_p, c_void_p, c_int, c_int, c_int,
                                    c_void_p]),
-    "tavsr_merge_learned_ave_weights_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+    "tavsr_merge_learned_ave_weights_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                                     c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "tavsr_ctc_greedy": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                  c_void_p]),

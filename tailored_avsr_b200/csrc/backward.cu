@@ -491,6 +491,7 @@ struct MergeBwdParams {
   const float* x1; const float* x2; const float* dm;
   long long ld1, ld2, ldm;
   const int32_t* lens;
+  const int32_t* lens2;   // optional: branch 2 masked by its own lengths (audio-visual fusion)
   const float* a1; const float* b1; const float* a2; const float* b2;  // [D] vectors
   const float* scal;   // device [4]: c1, e1, c2, e2 (the Linear(D,1) biases; no host read-back)
   float* dx1; float* dx2;
@@ -521,8 +522,13 @@ merge_learned_ave_bwd_kernel(const MergeBwdParams p) {
   const float bb1 = __ldg(p.b1 + col), bb2 = __ldg(p.b2 + col);
   pdl_wait();
   const float pc1 = ld_act(p.scal), pe1 = ld_act(p.scal + 1), pc2 = ld_act(p.scal + 2), pe2 = ld_act(p.scal + 3);
-  int len = p.lens ? p.lens[b] : T;
-  len = len < 0 ? 0 : (len > T ? T : len);
+  int len1 = p.lens ? p.lens[b] : T;
+  len1 = len1 < 0 ? 0 : (len1 > T ? T : len1);
+  int len2 = p.lens2 ? p.lens2[b] : len1;
+  len2 = len2 < 0 ? 0 : (len2 > T ? T : len2);
+  // softmax weights, ds and dsc of a branch are exactly 0 at and beyond that branch's length, so the
+  // phases that walk both branches together run to the longer one
+  const int len = len1 > len2 ? len1 : len2;
   const long long row0 = static_cast<long long>(b) * T;
   const float rs = rsqrtf(static_cast<float>(D));
   __syncthreads();
@@ -558,17 +564,18 @@ merge_learned_ave_bwd_kernel(const MergeBwdParams p) {
 #pragma unroll
   for (int br = 0; br < 2; ++br) {
     float* sc = s_s + br * T;
+    const int lb = br == 0 ? len1 : len2;
     float mx = -INFINITY;
-    for (int t = tid; t < len; t += kMergeThreads) mx = fmaxf(mx, sc[t]);
+    for (int t = tid; t < lb; t += kMergeThreads) mx = fmaxf(mx, sc[t]);
     mx = block_max_merge(mx, s_red);
     float sum = 0.f;
     for (int t = tid; t < T; t += kMergeThreads) {
-      const float e = t < len ? expf(sc[t] - mx) : 0.f;
+      const float e = t < lb ? expf(sc[t] - mx) : 0.f;
       sc[t] = e;
       sum += e;
     }
     const float se = block_sum_merge(sum, s_red);
-    const float inv = len > 0 ? 1.0f / se : 0.f;
+    const float inv = lb > 0 ? 1.0f / se : 0.f;
     for (int t = tid; t < T; t += kMergeThreads) sc[t] *= inv;
   }
   __syncthreads();
@@ -621,12 +628,13 @@ merge_learned_ave_bwd_kernel(const MergeBwdParams p) {
   float dcs[2];
 #pragma unroll
   for (int br = 0; br < 2; ++br) {
+    const int lb = br == 0 ? len1 : len2;
     float acc = 0.f;
-    for (int t = tid; t < len; t += kMergeThreads) acc += s_s[br * T + t] * s_d[br * T + t];
+    for (int t = tid; t < lb; t += kMergeThreads) acc += s_s[br * T + t] * s_d[br * T + t];
     const float sds = block_sum_merge(acc, s_red);
     float dc = 0.f;
     for (int t = tid; t < T; t += kMergeThreads) {
-      const float v = t < len ? s_s[br * T + t] * (s_d[br * T + t] - sds) * rs : 0.f;
+      const float v = t < lb ? s_s[br * T + t] * (s_d[br * T + t] - sds) * rs : 0.f;
       s_d[br * T + t] = v;
       dc += v;
     }
@@ -855,9 +863,10 @@ extern "C" size_t tavsr_merge_learned_ave_bwd_workspace_bytes(int B) {
 // grads: [4][256] = (da1, db1, da2, db2) then [4] = (dc1, de1, dc2, de2), i.e. 1028 floats.
 extern "C" int tavsr_merge_learned_ave_bwd(const float* x1, long long ld1, const float* x2,
                                            long long ld2, const float* dm, long long ldm,
-                                           const int32_t* lens, const float* a1, const float* b1,
-                                           const float* a2, const float* b2, const float* scal,
-                                           float* dx1, long long ldd1,
+                                           const int32_t* lens, const int32_t* lens2,
+                                           const float* a1, const float* b1, const float* a2,
+                                           const float* b2, const float* scal, float* dx1,
+                                           long long ldd1,
                                            float* dx2, long long ldd2, float* grads, void* workspace,
                                            long long workspace_bytes, int B, int T, int D,
                                            void* stream) {
@@ -871,6 +880,7 @@ extern "C" int tavsr_merge_learned_ave_bwd(const float* x1, long long ld1, const
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   bwd::MergeBwdParams p;
   p.x1 = x1; p.x2 = x2; p.dm = dm; p.ld1 = ld1; p.ld2 = ld2; p.ldm = ldm; p.lens = lens;
+  p.lens2 = lens2;
   p.a1 = a1; p.b1 = b1; p.a2 = a2; p.b2 = b2; p.scal = scal;
   p.dx1 = dx1; p.dx2 = dx2; p.ldd1 = ldd1; p.ldd2 = ldd2;
   p.part = static_cast<float*>(workspace);

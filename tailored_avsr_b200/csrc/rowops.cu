@@ -623,7 +623,8 @@ __global__ void __launch_bounds__(128)
 merge_weights_plain_kernel(const float2* __restrict__ dots1, const float2* __restrict__ dots2,
                      const int32_t* __restrict__ lens, float pool_b1, float pool_b2, float wproj_b1,
                      float wproj_b2, float inv_sqrt, float* __restrict__ w1, float* __restrict__ w2,
-                     int B, int T, const float* __restrict__ scal) {
+                     int B, int T, const float* __restrict__ scal,
+                     const int32_t* __restrict__ lens2 = nullptr) {
   pdl_launch_dependents();
   pdl_wait();
   if (scal != nullptr) {   // training: the biases live on the device
@@ -633,11 +634,14 @@ merge_weights_plain_kernel(const float2* __restrict__ dots1, const float2* __res
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
   const uint32_t lane = lane_id();
-  int len = lens ? lens[b] : T;
-  len = len < 0 ? 0 : (len > T ? T : len);
+  int len_a = lens ? lens[b] : T;
+  len_a = len_a < 0 ? 0 : (len_a > T ? T : len_a);
+  int len_b = lens2 ? lens2[b] : len_a;   // the AV fusion masks each modality with its own lengths
+  len_b = len_b < 0 ? 0 : (len_b > T ? T : len_b);
   float omega[2];
 #pragma unroll
   for (int br = 0; br < 2; ++br) {
+    const int len = br == 0 ? len_a : len_b;
     const float2* d = (br == 0 ? dots1 : dots2) + static_cast<long long>(b) * T;
     const float pb = br == 0 ? pool_b1 : pool_b2;
     float mx = -INFINITY;
@@ -941,15 +945,15 @@ extern "C" int tavsr_merge_scores(const void* a1, long long ld1, int K1, const v
 }
 
 extern "C" int tavsr_merge_learned_ave_weights_dev(const float* dots1, const float* dots2,
-                                                   const int32_t* lens, const float* scal,
-                                                   float inv_sqrt_size, float* w1, float* w2, int B,
-                                                   int T, void* stream) {
+                                                   const int32_t* lens, const int32_t* lens2,
+                                                   const float* scal, float inv_sqrt_size, float* w1,
+                                                   float* w2, int B, int T, void* stream) {
   TAVSR_REQUIRE(B > 0 && T > 0 && dots1 && dots2 && scal && w1 && w2, "merge_weights: bad arguments");
   TAVSR_CUDA_OK(launch_kernel(merge_weights_plain_kernel, dim3((B + 3) / 4), dim3(128), 0,
                               static_cast<cudaStream_t>(stream), 0,
                               reinterpret_cast<const float2*>(dots1),
                               reinterpret_cast<const float2*>(dots2), lens, 0.f, 0.f, 0.f, 0.f,
-                              inv_sqrt_size, w1, w2, B, T, scal));
+                              inv_sqrt_size, w1, w2, B, T, scal, lens2));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }

@@ -472,13 +472,14 @@ def merge_scores(a1: torch.Tensor, a2: torch.Tensor, va1: torch.Tensor, vb1: tor
 
 @_profiled
 def merge_weights_dev(dots1: torch.Tensor, dots2: torch.Tensor, lens: Optional[torch.Tensor],
-                      scal: torch.Tensor, size: int, B: int, T: int):
+                      scal: torch.Tensor, size: int, B: int, T: int, lens2: Optional[torch.Tensor] = None):
     """merge_weights with the four biases (pool_b1, pool_b2, wproj_b1, wproj_b2) read from the device
-    tensor `scal` (training: parameters change every step, no host read-back)."""
+    tensor `scal` (training: parameters change every step, no host read-back); `lens2`: branch 2
+    masked by its own lengths (audio-visual fusion)."""
     w1 = torch.empty((B,), device=dots1.device, dtype=torch.float32)
     w2 = torch.empty((B,), device=dots1.device, dtype=torch.float32)
     check(_lib.load().tavsr_merge_learned_ave_weights_dev(
-        dots1.data_ptr(), dots2.data_ptr(), _p(lens), scal.data_ptr(), 1.0 / math.sqrt(size),
+        dots1.data_ptr(), dots2.data_ptr(), _p(lens), _p(lens2), scal.data_ptr(), 1.0 / math.sqrt(size),
         w1.data_ptr(), w2.data_ptr(), B, T, _stream()), "tavsr_merge_learned_ave_weights_dev")
     return w1, w2
 

@@ -200,9 +200,10 @@ def csgu_bwd(h: torch.Tensor, norm_g: torch.Tensor, norm_b: torch.Tensor, conv_w
 
 def merge_learned_ave_bwd(x1: torch.Tensor, x2: torch.Tensor, dm: torch.Tensor, lens: torch.Tensor,
                           a1: torch.Tensor, b1: torch.Tensor, a2: torch.Tensor, b2: torch.Tensor,
-                          scal: torch.Tensor, B: int, T: int):
+                          scal: torch.Tensor, B: int, T: int, lens2: Optional[torch.Tensor] = None):
     """Returns (dx1, dx2, grads (1028,)): see tavsr_merge_learned_ave_bwd in include/tavsr.h.
-    scal: device tensor [c1, e1, c2, e2] (pooling_proj / weight_proj biases)."""
+    scal: device tensor [c1, e1, c2, e2] (pooling_proj / weight_proj biases); lens2: branch 2's own
+    lengths (audio-visual fusion), default = lens."""
     _chk2d(x1, "x1")
     _chk2d(x2, "x2")
     _chk2d(dm, "dm")
@@ -214,7 +215,7 @@ def merge_learned_ave_bwd(x1: torch.Tensor, x2: torch.Tensor, dm: torch.Tensor, 
     ws = _ws(lib.tavsr_merge_learned_ave_bwd_workspace_bytes(B), x1.device)
     check(lib.tavsr_merge_learned_ave_bwd(
         x1.data_ptr(), x1.stride(0), x2.data_ptr(), x2.stride(0), dm.data_ptr(), dm.stride(0),
-        _p(lens), a1.data_ptr(), b1.data_ptr(), a2.data_ptr(), b2.data_ptr(), scal.data_ptr(),
+        _p(lens), _p(lens2), a1.data_ptr(), b1.data_ptr(), a2.data_ptr(), b2.data_ptr(), scal.data_ptr(),
         dx1.data_ptr(), dx1.stride(0), dx2.data_ptr(), dx2.stride(0), grads.data_ptr(), ws.data_ptr(),
         ws.numel() * 4, B, T, D, _stream()), "tavsr_merge_learned_ave_bwd")
     return dx1, dx2, grads
