@@ -20,7 +20,10 @@ from oracle import cases, dropmask, gen_golden, reference_loader  # noqa: E402
 CASES = ["vsr_small", "asr_tailored_small", "vsr_tailored_small", "concat_small"]
 # train() mode with every dropout site active (rates of the case's config, 0.1 like the shipped
 # YAMLs), masks from oracle/dropmask.py::MaskSource(GOLDEN_SEED): grad_<case>_dropout.npz
-DROPOUT_CASES = ["vsr_small", "vsr_tailored_small", "concat_small"]
+DROPOUT_CASES = ["vsr_small", "vsr_tailored_small", "concat_small", "av_fusion_conventional"]
+# audio-visual: ConventionalEncoder + AdaptiveAudioVisualFusion + CTC on the fused stream
+# (avsr_espnet_model.py:467,678), different audio / video masks
+AV_CASES = ["av_fusion_conventional"]
 
 
 def summarize(named_grads):
@@ -35,25 +38,44 @@ def summarize(named_grads):
 
 def main():
     ref = reference_loader.load()
-    for name, drop in [(n, False) for n in CASES] + [(n, True) for n in DROPOUT_CASES]:
+    for name, drop in [(n, False) for n in CASES + AV_CASES] + [(n, True) for n in DROPOUT_CASES]:
         c = cases.CASES[name]
         inp = cases.make_inputs(name)
-        enc, ctc, _ = gen_golden.build_reference(ref, name)
-        x = inp["x"].clone().requires_grad_(True)
+        enc, ctc, fusion = gen_golden.build_reference(ref, name)
         src = dropmask.MaskSource(dropmask.GOLDEN_SEED)
         if drop:
             enc.train()
-        with dropmask.patched_dropout(src):
-            y, olens, _ = enc(x, inp["lens"])
-            tl = cases.target_lens(name, olens)
-            loss = ctc(y, olens, inp["ys_pad"], tl)
+            if fusion is not None:
+                fusion.train()
+        if c["kind"] == "single":
+            x = inp["x"].clone().requires_grad_(True)
+            with dropmask.patched_dropout(src):
+                y, olens, _ = enc(x, inp["lens"])
+                tl = cases.target_lens(name, olens)
+                loss = ctc(y, olens, inp["ys_pad"], tl)
+            inputs = [("input", x)]
+        else:
+            from oracle.ref_path import make_valid_mask, rel_pos_emb
+            d, T = c["cfg"]["output_size"], c["T"]
+            pos = rel_pos_emb(T, d)
+            mask, mask_v = make_valid_mask(inp["lens"], T), make_valid_mask(inp["lens_video"], T)
+            a = inp["audio"].clone().requires_grad_(True)
+            v = inp["video"].clone().requires_grad_(True)
+            with dropmask.patched_dropout(src):
+                ya, _, yv, _, _ = enc((a, pos), mask, (v, pos), mask_v)
+                y, olens = fusion(ya, mask, yv, mask_v)
+                tl = cases.target_lens(name, olens)
+                loss = ctc(y, olens, inp["ys_pad"], tl)
+            inputs = [("input_audio", a), ("input_video", v)]
         loss.backward()
         if drop:
             print(name, "dropout sites:", len(src.calls), src.calls[:14])
             name = name + "_dropout"
         grads = [("enc." + n, p.grad) for n, p in enc.named_parameters() if p.grad is not None]
         grads += [("ctc." + n, p.grad) for n, p in ctc.named_parameters()]
-        grads.append(("input", x.grad))
+        if fusion is not None:
+            grads += [("fusion." + n, p.grad) for n, p in fusion.named_parameters() if p.grad is not None]
+        grads += [(n, t.grad) for n, t in inputs]
         out = summarize(grads)
         out["loss"] = np.array(float(loss))
         if drop:

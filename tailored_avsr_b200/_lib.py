@@ -149,10 +149,11 @@ SIGNATURES = {
                                     c_int, c_int, c_int, c_void_p]),
     "tavsr_merge_learned_ave_bwd_workspace_bytes": (c_size_t, [c_int]),
     "tavsr_merge_learned_ave_bwd": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p,
-                                            c_longlong, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                            c_void_p, c_void_p, c_void_p, c_longlong,
-                                            c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_int,
-                                            c_int, c_int, c_void_p]),
+                                            c_longlong, c_void_p, c_void_p,            # lens, lens2
+                                            c_void_p, c_void_p, c_void_p, c_void_p,    # a1 b1 a2 b2
+                                            c_void_p, c_void_p, c_longlong, c_void_p, c_longlong,
+                                            c_void_p, c_void_p, c_longlong, c_int, c_int, c_int,
+                                            c_void_p]),
     "tavsr_merge_scores": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_longlong, c_int, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float,
                                    c_float, c_float, c_void_p, c_void_p, c_int, c_int, c_int,

@@ -72,8 +72,9 @@ class AdaptiveAudioVisualFusion(AudioVisualFusionAbsModule):
         if d != 256 or self._output_size != 256:
             raise NotImplementedError("the B200 row-complete epilogue is built for size=256")
         if self.training and (self.acoustic_branch_drop_rate > 0 or self.audiovisual_layer.dropout_rate > 0):
-            raise NotImplementedError("training-mode dropout / branch drop are not built on the "
-                                      "B200 path yet; use .eval()")
+            raise NotImplementedError("a no-grad call in train() mode with dropout / branch drop "
+                                      "enabled: the inference kernels have no random paths; use "
+                                      ".eval() (or a grad-mode call: training.py)")
         if self.merge_method == "learned_ave":
             ap, aw = self.acoustic_pooling_proj, self.acoustic_weight_proj
             vp, vw = self.visual_pooling_proj, self.visual_weight_proj
@@ -108,7 +109,7 @@ class AdaptiveAudioVisualFusion(AudioVisualFusionAbsModule):
         olens (B,))."""
         if cache is not None:
             raise NotImplementedError("cache is not None, which is not tested")
-        engine.require_inference(self, audio_pad, video_pad)
+        engine.require_cuda(audio_pad, video_pad)
         if audio_pad.shape != video_pad.shape:
             raise NotImplementedError("the B200 fusion expects time-aligned streams of equal shape "
                                       "(avsr_espnet_model.py:439 aligns them)")
@@ -117,7 +118,11 @@ class AdaptiveAudioVisualFusion(AudioVisualFusionAbsModule):
         v2 = video_pad.reshape(B * T, d).contiguous().float()
         la = engine.lens_from_mask(audio_masks, B, T, a2.device)
         lv = engine.lens_from_mask(video_masks, B, T, a2.device)
-        out = self.run(a2, v2, la, lv, B, T).view(B, T, d)
+        from .. import training
+        if training.wants_grad(self, audio_pad, video_pad):
+            out = training.fusion_forward(self, a2, v2, la, lv, B, T).view(B, T, d)
+        else:
+            out = self.run(a2, v2, la, lv, B, T).view(B, T, d)
         if audio_masks is None or video_masks is None:
             olens = torch.full((B,), T, dtype=torch.int64, device=a2.device)
         else:

@@ -624,7 +624,7 @@ merge_weights_plain_kernel(const float2* __restrict__ dots1, const float2* __res
                      const int32_t* __restrict__ lens, float pool_b1, float pool_b2, float wproj_b1,
                      float wproj_b2, float inv_sqrt, float* __restrict__ w1, float* __restrict__ w2,
                      int B, int T, const float* __restrict__ scal,
-                     const int32_t* __restrict__ lens2 = nullptr) {
+                     const int32_t* __restrict__ lens2) {
   pdl_launch_dependents();
   pdl_wait();
   if (scal != nullptr) {   // training: the biases live on the device
@@ -906,7 +906,8 @@ extern "C" int tavsr_merge_learned_ave_weights2(const float* dots1, int np1, con
                                 reinterpret_cast<const float2*>(dots1),
                                 reinterpret_cast<const float2*>(dots2), lens1, pool_b1, pool_b2,
                                 wproj_b1, wproj_b2, inv_sqrt_size, w1, w2, B, T,
-                                static_cast<const float*>(nullptr)));
+                                static_cast<const float*>(nullptr),
+                                static_cast<const int32_t*>(nullptr)));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return 0;
   }

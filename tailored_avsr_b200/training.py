@@ -477,6 +477,112 @@ class _LinearFn(torch.autograd.Function):
         return dx, dw, db
 
 
+# ---------------------------------------------------------------------------------------------------
+# AdaptiveAudioVisualFusion (src/audiovisual_fusion/adaptive_audiovisual_fusion.py:113-215)
+#   (w_a, w_v) = learned_ave(audio, video) with one mask per modality   (or fixed weights)
+#   out = norm_final(FFN(w_a audio + w_v video)),  FFN = w_2(dropout(act(w_1 .)))   - no residual
+# ---------------------------------------------------------------------------------------------------
+def fusion_forward_impl(Fm, aux, a: torch.Tensor, v: torch.Tensor):
+    B, T = aux.B, aux.T
+    d = Fm.input_size
+    dev = a.device
+    ff = Fm.audiovisual_layer
+    learned = Fm.merge_method == "learned_ave" and not aux.drop_acoustic
+    if Fm.merge_method == "learned_ave":
+        if learned:
+            ap, aw = Fm.acoustic_pooling_proj, Fm.acoustic_weight_proj
+            vp, vw = Fm.visual_pooling_proj, Fm.visual_weight_proj
+            d1, d2 = ops.row_dots(a, ap.weight.reshape(-1), aw.weight.reshape(-1),
+                                  v, vp.weight.reshape(-1), vw.weight.reshape(-1))
+            scal = torch.cat([ap.bias, vp.bias, aw.bias, vw.bias]).float()
+            w_a, w_v = ops.merge_weights_dev(d1, d2, aux.lens_a, scal, d, B, T, lens2=aux.lens_v)
+        else:   # acoustic branch dropped for this step (:138-143)
+            w_a = torch.zeros((B,), device=dev, dtype=F32)
+            w_v = torch.ones((B,), device=dev, dtype=F32)
+        Fm.acoustic_weight, Fm.visual_weight = w_a.detach().view(B, 1, 1), w_v.detach().view(B, 1, 1)
+    else:
+        wa = float(Fm.acoustic_weight)
+        w_a = torch.full((B,), wa, device=dev, dtype=F32)
+        w_v = torch.full((B,), 1.0 - wa, device=dev, dtype=F32)
+    m = ops.scale_add_rows(a, v, w_a, w_v, T)
+    act = engine.act_code(ff.activation_type)
+    z = ops.gemm_bias_act(m, ff.w_1.weight, ff.w_1.bias)
+    h = ob.act_fwd(z, act, mask=aux.mask_h)
+    y0 = ops.gemm_bias_act(h, ff.w_2.weight, ff.w_2.bias)
+    out = ops.layernorm(y0, Fm.norm_final.weight, Fm.norm_final.bias, eps=1e-12)
+    return out, dict(a=a, v=v, w_a=w_a, w_v=w_v, m=m, z=z, y0=y0, learned=learned)
+
+
+def fusion_backward_impl(Fm, aux, sv: dict, dout: torch.Tensor):
+    B, T = aux.B, aux.T
+    d = Fm.input_size
+    g: Dict[str, torch.Tensor] = {}
+    ff = Fm.audiovisual_layer
+    act = engine.act_code(ff.activation_type)
+    dy0 = _ln_bwd(g, sv["y0"], Fm.norm_final, dout, "norm_final")
+    hT = ob.act_fwd_t(sv["z"], act, mask=aux.mask_h)
+    dh = _lin_bwd(g, None, ff.w_2.weight, dy0, "audiovisual_layer.w_2.weight", "audiovisual_layer.w_2.bias",
+                  xT=hT)
+    dz, dzT = ob.act_bwd_t(sv["z"], _mul(dh, aux.mask_h), act)
+    dm = _lin_bwd(g, sv["m"], ff.w_1.weight, dz, "audiovisual_layer.w_1.weight",
+                  "audiovisual_layer.w_1.bias", dyT=dzT)
+    if sv["learned"]:
+        ap, aw = Fm.acoustic_pooling_proj, Fm.acoustic_weight_proj
+        vp, vw = Fm.visual_pooling_proj, Fm.visual_weight_proj
+        scal = torch.cat([ap.bias, aw.bias, vp.bias, vw.bias]).float()
+        da, dv, gr = ob.merge_learned_ave_bwd(sv["a"], sv["v"], dm, aux.lens_a, ap.weight.reshape(-1),
+                                              aw.weight.reshape(-1), vp.weight.reshape(-1),
+                                              vw.weight.reshape(-1), scal, B, T, lens2=aux.lens_v)
+        for k, name in enumerate(("acoustic_pooling_proj", "acoustic_weight_proj", "visual_pooling_proj",
+                                  "visual_weight_proj")):
+            _acc(g, name + ".weight", gr[k * d:(k + 1) * d].reshape(1, d))
+            _acc(g, name + ".bias", gr[4 * d + k:4 * d + k + 1])
+    else:
+        zero = torch.zeros((B,), device=dout.device, dtype=F32)
+        da = ops.scale_add_rows(dm, dm, sv["w_a"], zero, T)
+        dv = ops.scale_add_rows(dm, dm, sv["w_v"], zero, T)
+    return da, dv, g
+
+
+class _FusionFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, Fm, aux, names, a, v, *params):
+        out, sv = fusion_forward_impl(Fm, aux, a.contiguous(), v.contiguous())
+        ctx.Fm, ctx.aux, ctx.sv, ctx.names, ctx.params = Fm, aux, sv, names, params
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        da, dv, g = fusion_backward_impl(ctx.Fm, ctx.aux, ctx.sv, dout.contiguous())
+        ctx.sv = None
+        grads = []
+        for n, p in zip(ctx.names, ctx.params):
+            gp = g.get(n)
+            grads.append(gp.reshape(p.shape) if gp is not None and p.requires_grad else None)
+        return (None, None, None, da, dv) + tuple(grads)
+
+
+def fusion_forward(Fm, a2d: torch.Tensor, v2d: torch.Tensor, lens_a: torch.Tensor, lens_v: torch.Tensor,
+                   B: int, T: int) -> torch.Tensor:
+    """Training forward of AdaptiveAudioVisualFusion on (B*T, d) streams as one autograd node.
+    Randomness in the reference's order: the acoustic-branch drop draws torch.rand(1) on the host
+    (:138-143), then the FFN's hidden dropout."""
+    if Fm.input_size != 256 or Fm._output_size != 256:
+        raise NotImplementedError("the B200 fusion is built for size=256")
+    drop_acoustic = False
+    if Fm.merge_method == "learned_ave" and Fm.training and Fm.acoustic_branch_drop_rate > 0:
+        drop_acoustic = torch.rand(1).item() < Fm.acoustic_branch_drop_rate
+    mask_h = None
+    if Fm.training:
+        ff = Fm.audiovisual_layer
+        m = draw_mask((B, T, ff.w_1.out_features), float(ff.dropout_rate), a2d.device)
+        mask_h = None if m is None else m.view(B * T, -1)
+    aux = SimpleNamespace(B=B, T=T, lens_a=lens_a, lens_v=lens_v, drop_acoustic=drop_acoustic,
+                          mask_h=mask_h)
+    names, params = _named(Fm)
+    return _FusionFn.apply(Fm, aux, names, a2d, v2d, *params)
+
+
 def make_aux(layer, B: int, T: int, lens: torch.Tensor, pos_emb: Optional[torch.Tensor]):
     """Per-call constants of a block plus the training-only random decisions, drawn from the host
     RNG exactly where the reference draws them (encoder_layer.py:176-189, 233-239).  Returns None
