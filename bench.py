@@ -466,7 +466,35 @@ def profile_step(pipe, batch_dev, peaks, dtype, live_peaks):
 # --------------------------------------------------------------------------------------------------
 # extra legs of the GPU arm
 # --------------------------------------------------------------------------------------------------
-def train_leg(args, enc, ctc, rank, world, dev, dist, steps, warmup, train_mode=True):
+def trainable_workload():
+    w = WORKLOAD
+    return (w["kind"] == "single" and w["front"] == "linear") or w["kind"] in ("conventional", "tailored")
+
+
+def train_forward(enc, fusion, ctc, batch):
+    """Grad-mode forward of the trainable workloads: (nll vector of the local utterances).  C2:
+    encoder + CTC; C3 / C4: ConventionalEncoder (two stacks) / TailoredEncoder +
+    AdaptiveAudioVisualFusion + CTC on the fused stream (avsr_espnet_model.py:467,678)."""
+    w = WORKLOAD
+    if w["kind"] == "single":
+        feats, lens, ys, ylens = batch
+        out, olens, _ = enc(feats, lens)
+        return ctc(out, olens, ys, ylens)
+    from tailored_avsr_b200.espnet_compat import RelPositionalEncoding
+    a, v, lens_a, lens_v, ys, ylens = batch
+    B, T, d = a.shape
+    pos = _TRAIN_POS.setdefault(d, RelPositionalEncoding(d, 0.0)).pos_emb(T, a.device)
+    ar = torch.arange(T, device=a.device)[None, :]
+    ma, mv = (ar < lens_a[:, None]).unsqueeze(1), (ar < lens_v[:, None]).unsqueeze(1)
+    ya, _, yv, _, _ = enc((a, pos), ma, (v, pos), mv)
+    y, olens = fusion(ya, ma, yv, mv)
+    return ctc(y, olens, ys, ylens)
+
+
+_TRAIN_POS = {}
+
+
+def train_leg(args, enc, ctc, rank, world, dev, dist, steps, warmup, train_mode=True, fusion=None):
     """Training step of the workload (single-stream workloads): grad-mode encoder forward + CTC loss
     / global batch + backward + overlapped bucketed gradient all-reduce, no optimizer.  The modules
     are in train() mode: every dropout site of the reference is active at the configured rate (0.1
@@ -475,9 +503,9 @@ def train_leg(args, enc, ctc, rank, world, dev, dist, steps, warmup, train_mode=
     Returns a dict (rank 0) or None."""
     from tailored_avsr_b200 import engine, ops, parallel
     w = WORKLOAD
-    if w["kind"] != "single" or w["front"] != "linear":
-        return {"unavailable": "the training path is built for the linear / None front ends "
-                               "(MyBranchformerEncoder, ConventionalEncoder): run --workload C2"}
+    if not trainable_workload():
+        return {"unavailable": "the training path has no backward for the conv2d front end yet: run "
+                               "--workload C2, C3 or C4"}
     prev = engine.compute_dtype()
     engine.set_compute_dtype("tf32")      # the training path stores fp32 and multiplies in TF32
     cpu_threads = torch.get_num_threads()
@@ -486,9 +514,13 @@ def train_leg(args, enc, ctc, rank, world, dev, dist, steps, warmup, train_mode=
         # measurably slows that thread when left at the core count, torchrun sets it to 1 anyway
         torch.set_num_threads(1)
     enc.train(train_mode)
+    if fusion is not None:
+        fusion.train(train_mode)
     host, frames = make_batch(rank)
     host = [t.pin_memory() for t in host]
     params = list(enc.parameters()) + list(ctc.parameters())
+    if fusion is not None:
+        params += list(fusion.parameters())
     for p in params:
         p.requires_grad_(True)
     red = parallel.GradBucketReducer(params, bucket_mb=25.0, overlap=True)
@@ -501,10 +533,9 @@ def train_leg(args, enc, ctc, rank, world, dev, dist, steps, warmup, train_mode=
         for p in params:
             p.grad = None
         t0 = time.perf_counter()
-        feats, lens, ys, ylens = (t.to(dev, non_blocking=True) for t in host)
-        out, olens, _ = enc(feats, lens)
+        batch = [t.to(dev, non_blocking=True) for t in host]
+        vec = train_forward(enc, fusion, ctc, batch) * w["B"]   # nll_b of the local utterances
         t1 = time.perf_counter()
-        vec = ctc(out, olens, ys, ylens) * w["B"]          # nll_b of the local utterances
         loss = vec.sum() / Bg                               # ctc.py:62-66 with the GLOBAL batch
         t2 = time.perf_counter()
         loss.backward()
@@ -557,6 +588,8 @@ def train_leg(args, enc, ctc, rank, world, dev, dist, steps, warmup, train_mode=
         p.grad = None
         p.requires_grad_(False)
     enc.eval()
+    if fusion is not None:
+        fusion.eval()
     engine.set_compute_dtype(prev)
     torch.set_num_threads(cpu_threads)
     if rank != 0:
@@ -576,7 +609,8 @@ def train_leg(args, enc, ctc, rank, world, dev, dist, steps, warmup, train_mode=
         "kernel_launches_per_step": launches // steps,
         "host_enqueue_ms_per_step": host_enqueue_s / steps * 1e3,
         "host_enqueue_split_ms": {k: round(v / steps * 1e3, 2) for k, v in
-                                  zip(("forward", "loss", "backward", "finish"), host_split)},
+                                  zip(("forward + loss kernels", "loss normalisation", "backward", "finish"),
+                                      host_split)},
         "allreduce": {"bytes_per_step": nbytes if world > 1 else 0, "buckets": len(red.buckets),
                       "bucket_mb": 25.0, "collectives_per_step": n_coll,
                       "launched_during_backward": in_bwd[-1] if in_bwd else 0,
@@ -586,7 +620,7 @@ def train_leg(args, enc, ctc, rank, world, dev, dist, steps, warmup, train_mode=
     }
 
 
-def train_graph_leg(args, enc, ctc, rank, world, dev, dist, steps, warmup):
+def train_graph_leg(args, enc, ctc, rank, world, dev, dist, steps, warmup, fusion=None):
     """The same training step captured ONCE into a CUDA graph and replayed (the eager step is bound
     by ~1500 Python-side launches).  First choice: the bucketed all-reduce is captured too, launched
     by the gradient hooks during the captured backward, so the replayed graph overlaps the NCCL
@@ -595,13 +629,16 @@ def train_graph_leg(args, enc, ctc, rank, world, dev, dist, steps, warmup):
     the result says which.  Returns a dict (rank 0) or None."""
     from tailored_avsr_b200 import engine, parallel
     w = WORKLOAD
-    if w["kind"] != "single" or w["front"] != "linear":
+    if not trainable_workload():
         return None
     prev = engine.compute_dtype()
     engine.set_compute_dtype("tf32")
     enc.train()                  # dropout active, masks drawn inside the capture (graph-safe generator)
     out = None
     params = list(enc.parameters()) + list(ctc.parameters())
+    if fusion is not None:
+        fusion.train()
+        params += list(fusion.parameters())
     host, frames = make_batch(rank)
     host = [t.pin_memory() for t in host]
     static = [t.to(dev) for t in host]
@@ -616,8 +653,7 @@ def train_graph_leg(args, enc, ctc, rank, world, dev, dist, steps, warmup):
 
         def fwd_bwd():
             red.launched_in_backward = 0
-            o, olens, _ = enc(static[0], static[1])
-            vec = ctc(o, olens, static[2], static[3]) * w["B"]
+            vec = train_forward(enc, fusion, ctc, static) * w["B"]
             loss = vec.sum() / Bg
             loss.backward()
             n = red.finish() if overlap else 0
@@ -709,6 +745,8 @@ def train_graph_leg(args, enc, ctc, rank, world, dev, dist, steps, warmup):
             p.grad = None
             p.requires_grad_(False)
         enc.eval()
+        if fusion is not None:
+            fusion.eval()
         engine.set_compute_dtype(prev)
     return out if rank == 0 else None
 
@@ -965,11 +1003,12 @@ def run_gpu_arm(args):
     if not args.no_extra:
         strong = strong_leg(args, enc, fusion, ctc, rank, world, dev, dist, steps=min(args.steps, 10),
                             warmup=3)
-        train = train_leg(args, enc, ctc, rank, world, dev, dist, steps=args.train_steps, warmup=2)
+        train = train_leg(args, enc, ctc, rank, world, dev, dist, steps=args.train_steps, warmup=2,
+                          fusion=fusion)
         train_graph = train_graph_leg(args, enc, ctc, rank, world, dev, dist, steps=args.train_steps,
-                                      warmup=2)
+                                      warmup=2, fusion=fusion)
         train_eval = train_leg(args, enc, ctc, rank, world, dev, dist, steps=max(2, args.train_steps // 2),
-                               warmup=1, train_mode=False)
+                               warmup=1, train_mode=False, fusion=fusion)
         if train is not None and train_eval is not None and "ms_per_step" in train_eval:
             train["eval_mode_ms_per_step"] = train_eval["ms_per_step"]
         if train is not None and train_graph is not None:

@@ -156,7 +156,10 @@ class TailoredEncoder(AudioVisualAbsEncoder):
                                  "`conditioning_layer` (avsr_espnet_model.py)")
         audio, a_pos = audio_pad if isinstance(audio_pad, tuple) else (audio_pad, None)
         video, v_pos = video_pad if isinstance(video_pad, tuple) else (video_pad, None)
-        engine.require_inference(self, audio, video)
+        engine.require_cuda(audio, video)
+        from .... import training
+        if training.wants_grad(self, audio, video):
+            return training.tailored_encoder_forward(self, audio_pad, audio_masks, video_pad, video_masks)
         if audio.shape != video.shape:
             raise NotImplementedError("the B200 tailored encoder expects time-aligned streams of "
                                       "equal shape (avsr_espnet_model.py:439 aligns them)")

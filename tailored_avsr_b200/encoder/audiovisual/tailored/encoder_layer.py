@@ -59,9 +59,11 @@ class TailoredEncoderLayer(torch.nn.Module):
                 raise NotImplementedError(
                     f"the B200 attention kernel is built for head width d_k = 64; {tag} attention "
                     f"has h={a.h}, d_k={a.d_k}")
-        if self.training and (self.dropout.p > 0 or self.stochastic_depth_rate > 0):
-            raise NotImplementedError("training-mode dropout / stochastic depth are not built on "
-                                      "the B200 path yet; use .eval()")
+        if self.training and not torch.is_grad_enabled() and (
+                self.dropout.p > 0 or self.stochastic_depth_rate > 0):
+            raise NotImplementedError("a no-grad call in train() mode with dropout / stochastic depth "
+                                      "enabled: the inference kernels have no random paths; use "
+                                      ".eval() (or a grad-mode call: training.py)")
 
     def run(self, x, xn, pos_proj_a, pos_proj_v, lens_a, lens_v, B, T, next_norm=None,
             next_norm_dtype=None):
@@ -120,12 +122,31 @@ class TailoredEncoderLayer(torch.nn.Module):
         audio, audio_pos = audio_input if isinstance(audio_input, tuple) else (audio_input, None)
         video, video_pos = video_input if isinstance(video_input, tuple) else (video_input, None)
         self._check_supported()
-        engine.require_inference(self, audio, video)
+        engine.require_cuda(audio, video)
         if audio.shape != video.shape:
             raise NotImplementedError("the B200 tailored layer expects time-aligned streams of "
                                       "equal shape (avsr_espnet_model.py:439 aligns them)")
         B, T, d = audio.shape
         M = B * T
+        from .... import training
+        if training.wants_grad(self, audio, video):
+            from .... import ops_backward as ob
+            dev = audio.device
+
+            def pair(pos):
+                if pos is None:
+                    return None
+                p2 = pos.reshape(-1, d).contiguous().float()
+                return p2, ob.transpose_2d(p2, pad=True)
+
+            a_out, v_out = training.tailored_layer_forward(
+                self, audio.reshape(M, d).contiguous().float(), video.reshape(M, d).contiguous().float(),
+                B, T, engine.lens_from_mask(audio_masks, B, T, dev),
+                engine.lens_from_mask(video_masks, B, T, dev), pair(audio_pos), pair(video_pos))
+            a_out, v_out = a_out.view(B, T, d), v_out.view(B, T, d)
+            a_ret = (a_out, audio_pos) if audio_pos is not None else a_out
+            v_ret = (v_out, video_pos) if video_pos is not None else v_out
+            return a_ret, audio_masks, v_ret, video_masks
         x = torch.cat([audio.reshape(M, d), video.reshape(M, d)], 0).contiguous().float()
         xn = ops.layernorm(x, self.norm_ff_macaron.weight, self.norm_ff_macaron.bias, eps=1e-12,
                            out_dtype=engine.act_dtype())

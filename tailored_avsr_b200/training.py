@@ -270,9 +270,14 @@ def block_forward(L, aux, x: torch.Tensor) -> Tuple[torch.Tensor, dict]:
     x_b, xf = new(), new()
     lnF = (L.norm_ff.weight, L.norm_ff.bias)
     mp = L.merge_proj
-    if isinstance(mp, torch.nn.Identity):
-        raise NotImplementedError("single-branch block built with merge_proj=Identity is not built")
-    if two and L.merge_method in ("learned_ave", "fixed_ave"):
+    ident = isinstance(mp, torch.nn.Identity)
+    if ident:
+        # single branch added straight onto the residual: x_b = x_a + c * branch (the tailored AV
+        # layer, tailored/encoder_layer.py:185-207; its branch dropout is the x1 / x2 site)
+        if two:
+            raise NotImplementedError("two-branch block with merge_proj=Identity is not built")
+        _residual_ln(x_a, x2 if L.attn is None else x1, aux.stoch, x_b, lnF, xf)
+    elif two and L.merge_method in ("learned_ave", "fixed_ave"):
         if L.merge_method == "learned_ave":
             if learned:
                 scal = torch.cat([L.pooling_proj1.bias, L.pooling_proj2.bias, L.weight_proj1.bias,
@@ -301,7 +306,7 @@ def block_forward(L, aux, x: torch.Tensor) -> Tuple[torch.Tensor, dict]:
         if drp.get("merge") is None:
             ops.gemm_rowln(msrc, mp.weight, mp.bias, residual=x_a, alpha=aux.stoch, out_main=x_b,
                            lnA=lnF, out_lnA=xf)
-    if drp.get("merge") is not None:   # x_b = x_a + c * dropout(merge_proj(.)) (:228-306)
+    if drp.get("merge") is not None and not ident:   # x_b = x_a + c * dropout(merge_proj(.)) (:228-306)
         t = _mul(ops.gemm_bias_act(msrc, mp.weight, mp.bias), drp["merge"])
         _residual_ln(x_a, t, aux.stoch, x_b, lnF, xf)
     sv.update(x_b=x_b, xf=xf, learned=learned)
@@ -331,10 +336,14 @@ def block_backward(L, aux, sv: dict, dy: torch.Tensor) -> Tuple[torch.Tensor, Di
     if aux.stoch != 1.0:   # x_b = x_a + c * (merge_proj(m)): the projection sees c * dx_b
         c = torch.full((1,), float(aux.stoch), device=dev)
         dmo = ops.scale_add_rows(dx_b, dx_b, c, _scalars(dev)[1], M)
-    dmo = _mul(dmo, drp.get("merge"))
+    ident = isinstance(mp, torch.nn.Identity)
+    if not ident:
+        dmo = _mul(dmo, drp.get("merge"))
     x1, x2 = sv.get("x1"), sv.get("x2")
     dx1 = dx2 = None
-    if two and L.merge_method in ("learned_ave", "fixed_ave"):
+    if ident:
+        dx1, dx2 = (None, dmo) if L.attn is None else (dmo, None)
+    elif two and L.merge_method in ("learned_ave", "fixed_ave"):
         w1, w2 = sv["w1"], sv["w2"]
         m = ops.scale_add_rows(x1, x2, w1, w2, T)
         dm = _lin_bwd(g, m, mp.weight, dmo, "merge_proj.weight", "merge_proj.bias")
@@ -475,6 +484,116 @@ class _LinearFn(torch.autograd.Function):
         x, weight = ctx.saved_tensors
         dx, dw, db = ob.linear_bwd(x, weight, dy.contiguous(), need_dx=ctx.need_dx)
         return dx, dw, db
+
+
+# ---------------------------------------------------------------------------------------------------
+# TailoredEncoderLayer (src/encoder/audiovisual/tailored/encoder_layer.py:118-260): per stream
+#   x = x + .5 drop(FFN_mac(LN_mac(x)));  x = x + c drop(branch(LN_branch(x)));  x = x + .5 drop(FFN(LN_ff(x)));
+#   x = LN_final(x)      with branch = rel-pos attention OR cgMLP, FFNs / LN_mac / LN_ff / LN_final SHARED
+# i.e. a single-branch Branchformer block without merge_proj.  Each stream is one autograd node built
+# on block_forward / block_backward through a view of the layer that names the stream's modules the
+# way a Branchformer block does; the shared parameters get the sum of both nodes' gradients.
+# ---------------------------------------------------------------------------------------------------
+class _StreamView:
+    """The modules one stream of a TailoredEncoderLayer uses, under MyBranchformerEncoderLayer names."""
+    use_two_branches = False
+    merge_method = "identity"
+    attn_branch_drop_rate = 0.0
+    merge_proj = torch.nn.Identity()
+
+    def __init__(self, layer, tag: str):
+        self.size = layer.size
+        self.training = layer.training
+        self.dropout = layer.dropout
+        self.attn = getattr(layer, tag + "_attn")
+        self.cgmlp = getattr(layer, tag + "_cgmlp")
+        self.norm_mha = getattr(layer, tag + "_norm_mha", None)
+        self.norm_mlp = getattr(layer, tag + "_norm_cgmlp", None)
+        for n in ("norm_ff_macaron", "feed_forward_macaron", "norm_ff", "feed_forward", "norm_final"):
+            setattr(self, n, getattr(layer, n))
+        self.rename = {"attn.": tag + "_attn.", "cgmlp.": tag + "_cgmlp.", "norm_mha.": tag + "_norm_mha.",
+                       "norm_mlp.": tag + "_norm_cgmlp."}
+
+    def real_name(self, key: str) -> str:
+        for k, v in self.rename.items():
+            if key.startswith(k):
+                return v + key[len(k):]
+        return key
+
+
+class _TailoredStreamFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, view, aux, names, x, *params):
+        y, sv = block_forward(view, aux, x.contiguous())
+        ctx.view, ctx.aux, ctx.sv, ctx.names, ctx.params = view, aux, sv, names, params
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dx, g = block_backward(ctx.view, ctx.aux, ctx.sv, dy.contiguous())
+        ctx.sv = None
+        g = {ctx.view.real_name(k): v for k, v in g.items()}
+        grads = []
+        for n, p in zip(ctx.names, ctx.params):
+            gp = g.get(n)
+            grads.append(gp.reshape(p.shape) if gp is not None and p.requires_grad else None)
+        return (None, None, None, dx) + tuple(grads)
+
+
+def tailored_layer_forward(layer, a2d, v2d, B: int, T: int, lens_a, lens_v, pos_a, pos_v):
+    """Training forward of one TailoredEncoderLayer on (B*T, d) streams.  One stochastic-depth draw
+    for the layer (:152-165), then the audio stream's dropout sites, then the video stream's."""
+    layer._check_supported()
+    stoch = 1.0
+    if layer.training and layer.stochastic_depth_rate > 0:
+        skip = torch.rand(1).item() < layer.stochastic_depth_rate
+        stoch = 1.0 / (1 - layer.stochastic_depth_rate)
+        if skip:
+            return a2d, v2d
+    names, params = _named(layer)
+    outs = []
+    for tag, x, lens, pos in (("acoustic", a2d, lens_a, pos_a), ("visual", v2d, lens_v, pos_v)):
+        view = _StreamView(layer, tag)
+        pos2d, pos2d_T = pos if pos is not None else (None, None)
+        aux = SimpleNamespace(B=B, T=T, lens=lens, pos2d=pos2d, pos2d_T=pos2d_T, stoch=stoch,
+                              drop_attn=False, drop=draw_block_masks(view, B, T, x.device))
+        outs.append(_TailoredStreamFn.apply(view, aux, names, x, *params))
+    return outs[0], outs[1]
+
+
+def tailored_encoder_forward(enc, audio_pad, audio_masks, video_pad, video_masks):
+    """Training forward of TailoredEncoder (tailored/encoder.py:221-330 without InterCTC taps):
+    modality encoding, the layer stack, the shared after_norm on both streams."""
+    if len(enc.interctc_layer_idx) > 0:
+        raise NotImplementedError("audio-visual InterCTC is not built on the training path")
+    audio, a_pos = audio_pad if isinstance(audio_pad, tuple) else (audio_pad, None)
+    video, v_pos = video_pad if isinstance(video_pad, tuple) else (video_pad, None)
+    if audio.shape != video.shape:
+        raise NotImplementedError("the B200 tailored encoder expects time-aligned streams of equal shape")
+    B, T, d = audio.shape
+    M = B * T
+    dev = audio.device
+    me = enc.modality_encoding.weight
+    # modality encoding (:251-263): a broadcast add, left to torch (and its autograd) like the
+    # inference path does
+    a = (audio.float() + me[0]).reshape(M, d).contiguous()
+    v = (video.float() + me[1]).reshape(M, d).contiguous()
+    la = engine.lens_from_mask(audio_masks, B, T, dev)
+    lv = engine.lens_from_mask(video_masks, B, T, dev)
+
+    def pos_pair(pos):
+        if pos is None:
+            return None
+        p2 = pos.reshape(-1, d).contiguous().float()
+        return p2, ob.transpose_2d(p2, pad=True)
+
+    pa, pv = pos_pair(a_pos), pos_pair(v_pos)
+    for layer in enc.encoders:
+        a, v = tailored_layer_forward(layer, a, v, B, T, la, lv, pa, pv)
+    if enc.normalize_before:
+        a = _LayerNormFn.apply(a, enc.after_norm.weight, enc.after_norm.bias, 1e-12, 1.0)
+        v = _LayerNormFn.apply(v, enc.after_norm.weight, enc.after_norm.bias, 1e-12, 1.0)
+    return a.view(B, T, d), audio_masks, v.view(B, T, d), video_masks, None
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -633,7 +752,8 @@ def draw_block_masks(layer, B: int, T: int, device) -> Dict[str, object]:
     if layer.cgmlp is not None:
         site("csgu", (B, T, layer.cgmlp.channel_proj2.in_features), float(layer.cgmlp.csgu.dropout_rate))
         site("x2", (B, T, d), p_out)
-    site("merge", (B, T, d), p_out)
+    if not isinstance(layer.merge_proj, torch.nn.Identity):
+        site("merge", (B, T, d), p_out)
     ffn("ff", layer.feed_forward)
     return dm
 

@@ -421,18 +421,19 @@ def test_encoder_training_with_dropout_matches_reference(name):
 
 
 @pytest.mark.parametrize("drop", [False, True])
-def test_av_training_conventional_encoder_plus_fusion_matches_reference(drop):
-    """The audio-visual training step of the conventional configuration: ConventionalEncoder (two
-    stacks) -> AdaptiveAudioVisualFusion with different audio / video masks -> CTC on the fused
-    stream (avsr_espnet_model.py:467,678).  Gradients of both inputs and of every encoder, fusion
-    and CTC parameter against the REAL reference modules (tests/golden/grad_av_fusion_conventional*.npz),
-    in eval mode and in train() mode with all 37 dropout sites active (masks injected on both sides)."""
+@pytest.mark.parametrize("name", ["av_fusion_conventional", "av_fusion_tailored"])
+def test_av_training_encoder_plus_fusion_matches_reference(name, drop):
+    """The audio-visual training step: ConventionalEncoder (two stacks) or TailoredEncoder
+    (heterogeneous per-layer modules, shared FFNs) -> AdaptiveAudioVisualFusion with different audio
+    / video masks -> CTC on the fused stream (avsr_espnet_model.py:467,678).  Gradients of both
+    inputs and of every encoder, fusion and CTC parameter against the REAL reference modules
+    (tests/golden/grad_av_fusion_*.npz), in eval mode and in train() mode with all 37 dropout sites
+    active (masks injected on both sides)."""
     import numpy as np
     from oracle import cases, dropmask
     from oracle.ref_path import make_valid_mask, rel_pos_emb
     from tailored_avsr_b200 import training
     from . import _util
-    name = "av_fusion_conventional"
     gold = dict(np.load(os.path.join(_util.GOLDEN_DIR, f"grad_{name}{'_dropout' if drop else ''}.npz")))
     enc, ctc, sd = _util.build_dropin(name)
     fusion = enc.test_fusion[0].to(DEV)
@@ -486,8 +487,8 @@ def test_av_training_conventional_encoder_plus_fusion_matches_reference(drop):
         assert np.allclose(sample, gold["sample/" + n], rtol=5e-2 if pool else 2e-2,
                            atol=(10 if pool else 4) * tol * gn / max(1.0, g.numel() ** 0.5) + floor + 1e-9), n
         checked += 1
-    print(f"AV TRAIN drop={drop}: {checked} gradients, worst norm deviation {worst[1]} {worst[2]:.2e}")
-    assert checked > 180
+    print(f"AV TRAIN {name} drop={drop}: {checked} gradients, worst norm deviation {worst[1]} {worst[2]:.2e}")
+    assert checked > (180 if "conventional" in name else 120)
 
 
 def test_training_stochastic_depth_and_branch_drop_follow_the_host_rng():
