@@ -413,6 +413,16 @@ int tavsr_ctc_head_bwd(const float* dlogits, const float* row_scale, int rows_pe
  * ---------------------------------------------------------------------------------------------- */
 int tavsr_transpose_2d(const float* in, long long ld_in, float* out, long long ld_out, int R, int C,
                        void* stream);
+/* Backward of the first half of the Conv2dSubsampling front end (training): given dA, the gradient
+ * of the im2col operand tavsr_conv2d_sub_im2col wrote (same [(b,t2,f2)][(kt,kf,c)] layout, fp32),
+ * gathers it back onto conv1's output grid, applies conv1's ReLU mask (conv1 is re-evaluated from x)
+ * and reduces d conv1.weight / d conv1.bias: grads [C][10] = nine taps then the bias per channel.
+ * The input features get no gradient. */
+size_t tavsr_conv2d_sub_bwd_workspace_bytes(int B, int Tin, int C);
+int tavsr_conv2d_sub_bwd(const float* x, int B, int Tin, int F, const float* w1, const float* b1,
+                         int C, const float* dA, float* grads, void* workspace,
+                         long long workspace_bytes, void* stream);
+
 /* Fused elementwise + transpose forms (one pass instead of an elementwise pass and a transpose):
  *   tavsr_act_fwd_t   hT[c][m] = act(z[m][c]) (* mask[m][c]); hT rows zero-padded to a multiple of 4
  *   tavsr_act_bwd_t   dz = dh * act'(z) row-major and dzT = dz^T                                   */

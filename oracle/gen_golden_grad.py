@@ -17,11 +17,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import cases, dropmask, gen_golden, reference_loader  # noqa: E402
 
-CASES = ["vsr_small", "asr_tailored_small", "vsr_tailored_small", "concat_small"]
+CASES = ["vsr_small", "asr_small", "asr_tailored_small", "vsr_tailored_small", "concat_small"]
 # train() mode with every dropout site active (rates of the case's config, 0.1 like the shipped
 # YAMLs), masks from oracle/dropmask.py::MaskSource(GOLDEN_SEED): grad_<case>_dropout.npz
-DROPOUT_CASES = ["vsr_small", "vsr_tailored_small", "concat_small", "av_fusion_conventional",
-                 "av_fusion_tailored"]
+DROPOUT_CASES = ["vsr_small", "asr_small", "vsr_tailored_small", "concat_small",
+                 "av_fusion_conventional", "av_fusion_tailored"]
 # audio-visual: ConventionalEncoder + AdaptiveAudioVisualFusion + CTC on the fused stream
 # (avsr_espnet_model.py:467,678), different audio / video masks
 AV_CASES = ["av_fusion_conventional", "av_fusion_tailored"]

@@ -93,6 +93,9 @@ SIGNATURES = {
                                       c_void_p, c_void_p, c_longlong, c_void_p, c_longlong, c_void_p,
                                       c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_longlong, c_float, c_int, c_int, c_int, c_void_p]),
+    "tavsr_conv2d_sub_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "tavsr_conv2d_sub_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                                     c_void_p, c_void_p, c_longlong, c_void_p]),
     "tavsr_act_fwd_t": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int,
                                 c_int, c_int, c_void_p]),
     "tavsr_act_bwd_t": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong,

@@ -675,6 +675,67 @@ merge_learned_ave_bwd_kernel(const MergeBwdParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Conv2dSubsampling front end, backward of its first half (espnet Conv2dSubsampling:
+// Conv2d(1, C, 3, 2) + ReLU + Conv2d(C, C, 3, 2) + ReLU; encoder.py:149-155).  The forward writes the
+// im2col operand A[(b, t2, f2)][(kt, kf, c)] = relu(conv1(x))[b, c, 2 t2 + kt, 2 f2 + kf] of the second
+// convolution (conv2d_sub_im2col_kernel); given dA (from the conv2 GEMM's dgrad) this kernel does the
+// col2im gather  dh1[b, c, t1, f1] = sum over the <= 4 windows (kt, kf) with t1 - kt, f1 - kf even,
+// re-evaluates conv1 (9 FMAs) for the ReLU mask, and accumulates d w1[c][3][3], d b1[c].
+// CTA = one (b, t1), thread = channel c (coalesced dA reads); per-CTA partials part[cta][c * 10 + k]
+// (k = 9: bias) are summed by col_sums_reduce_kernel.  The input features get no gradient.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+conv2d_sub_bwd_kernel(const float* __restrict__ x, int Tin, int F, const float* __restrict__ w1,
+                      const float* __restrict__ b1, int C, int T1, int F1, int T2, int F2,
+                      const float* __restrict__ dA, float* __restrict__ part) {
+  extern __shared__ float s_x[];  // 3 input rows x F
+  pdl_launch_dependents();
+  const int b = blockIdx.x / T1, t1 = blockIdx.x % T1;
+  pdl_wait();
+  const float* xb = x + (static_cast<long long>(b) * Tin + 2 * t1) * F;
+  for (int i = threadIdx.x; i < 3 * F; i += blockDim.x) s_x[i] = ld_act(xb + i);
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float w[9], dw[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { w[k] = __ldg(w1 + c * 9 + k); dw[k] = 0.f; }
+    const float bias = __ldg(b1 + c);
+    float db = 0.f;
+    for (int f1 = 0; f1 < F1; ++f1) {
+      float dh = 0.f;
+#pragma unroll
+      for (int kt = 0; kt < 3; ++kt) {
+        const int tt = t1 - kt;
+        if (tt < 0 || (tt & 1) || (tt >> 1) >= T2) continue;
+#pragma unroll
+        for (int kf = 0; kf < 3; ++kf) {
+          const int ff = f1 - kf;
+          if (ff < 0 || (ff & 1) || (ff >> 1) >= F2) continue;
+          const long long row = (static_cast<long long>(b) * T2 + (tt >> 1)) * F2 + (ff >> 1);
+          dh += ld_act(dA + row * (9ll * C) + (kt * 3 + kf) * C + c);
+        }
+      }
+      const float* xp = s_x + 2 * f1;
+      float z = bias;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) z = fmaf(w[i * 3 + j], xp[i * F + j], z);
+      const float dz = z > 0.f ? dh : 0.f;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) dw[i * 3 + j] = fmaf(dz, xp[i * F + j], dw[i * 3 + j]);
+      db += dz;
+    }
+    float* pp = part + (static_cast<long long>(blockIdx.x) * C + c) * 10;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) pp[k] = dw[k];
+    pp[9] = db;
+  }
+}
+
 }  // namespace bwd
 }  // namespace tavsr
 
@@ -900,5 +961,33 @@ extern "C" int tavsr_merge_learned_ave_bwd(const float* x1, long long ld1, const
   TAVSR_CUDA_OK(launch_kernel(bwd::col_sums_reduce_kernel, dim3(1), dim3(1024), 0, s, 0,
                               static_cast<const float*>(p.part_s), B, grads + 1024, 4));
   g_launches.fetch_add(3, std::memory_order_relaxed);
+  return 0;
+}
+
+// d conv1.weight [C, 9] | d conv1.bias [C] of the Conv2dSubsampling front end from dA (see
+// conv2d_sub_bwd_kernel); grads = [C][10] (nine taps, then the bias), workspace B * T1 * C * 10 floats.
+extern "C" size_t tavsr_conv2d_sub_bwd_workspace_bytes(int B, int Tin, int C) {
+  const size_t T1 = static_cast<size_t>((Tin - 1) / 2);
+  return static_cast<size_t>(B) * T1 * C * 10 * sizeof(float);
+}
+
+extern "C" int tavsr_conv2d_sub_bwd(const float* x, int B, int Tin, int F, const float* w1,
+                                    const float* b1, int C, const float* dA, float* grads,
+                                    void* workspace, long long workspace_bytes, void* stream) {
+  TAVSR_REQUIRE(B > 0 && Tin >= 7 && F >= 7 && C > 0 && x && w1 && b1 && dA && grads && workspace,
+                "conv2d_sub_bwd: bad arguments (B=%d Tin=%d F=%d C=%d)", B, Tin, F, C);
+  const int T1 = (Tin - 1) / 2, F1 = (F - 1) / 2;
+  const int T2 = (T1 - 1) / 2, F2 = (F1 - 1) / 2;
+  TAVSR_REQUIRE(T2 >= 1 && F2 >= 1 && 3 * F * 4 <= 48 * 1024, "conv2d_sub_bwd: unsupported shape");
+  TAVSR_REQUIRE(static_cast<size_t>(workspace_bytes) >= tavsr_conv2d_sub_bwd_workspace_bytes(B, Tin, C),
+                "conv2d_sub_bwd: workspace too small");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* part = static_cast<float*>(workspace);
+  TAVSR_CUDA_OK(launch_kernel(bwd::conv2d_sub_bwd_kernel, dim3(B * T1), dim3(256),
+                              static_cast<size_t>(3 * F * 4), s, 0, x, Tin, F, w1, b1, C, T1, F1, T2, F2,
+                              dA, part));
+  TAVSR_CUDA_OK(launch_kernel(bwd::col_sums_reduce_kernel, dim3((C * 10 + 31) / 32), dim3(1024), 0, s, 0,
+                              static_cast<const float*>(part), B * T1, grads, C * 10));
+  g_launches.fetch_add(2, std::memory_order_relaxed);
   return 0;
 }

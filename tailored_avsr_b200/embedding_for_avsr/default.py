@@ -77,14 +77,18 @@ class DefaultEmbeddingLayerForAVSR(EmbeddingForAVSRAbsLayer):
     # ---------------------------------------------------------------------------------------
     def apply_embed_layer(self, xs_pad: torch.Tensor, ilens: torch.Tensor):
         """(B, Tin, input_size), (B,) -> ((B, T, d), masks (B, 1, T)) (default.py:139-153)."""
-        engine.require_inference(self, xs_pad)
-        if self.training and any(isinstance(m, torch.nn.Dropout) and m.p > 0 for m in self.modules()):
-            raise NotImplementedError("training-mode dropout is not built on the B200 path; use .eval()")
+        engine.require_cuda(xs_pad)
         dev = xs_pad.device
         d = self._output_size
         Tin = xs_pad.size(1)
         # ~make_pad_mask(ilens)[:, None, :] on the device: no .tolist() host sync (:141)
         masks = (torch.arange(Tin, device=dev)[None, :] < ilens.to(dev)[:, None]).unsqueeze(1)
+        from .. import training
+        if training.wants_grad(self, xs_pad):
+            return training.avsr_embed_forward(self, xs_pad, masks)
+        if self.training and any(isinstance(m, torch.nn.Dropout) and m.p > 0 for m in self.modules()):
+            raise NotImplementedError("a no-grad call in train() mode with dropout enabled: the "
+                                      "inference kernels have no random paths; use .eval()")
         if isinstance(self.embed, Conv2dSubsamplingWOPosEnc):
             conv, lin = self.embed.conv, self.embed.out
             B, _, Fin = xs_pad.shape
@@ -123,8 +127,11 @@ class DefaultEmbeddingLayerForAVSR(EmbeddingForAVSRAbsLayer):
     def apply_pos_enc(self, xs_pad: torch.Tensor):
         """(B, T, d) -> ((B, T, d) * sqrt(d), pos_emb (1, 2T-1, d)) (default.py:156-162; espnet
         RelPositionalEncoding.forward, dropout is the identity in eval)."""
-        engine.require_inference(self, xs_pad)
+        engine.require_cuda(xs_pad)
         B, T, d = xs_pad.shape
+        from .. import training
+        if training.wants_grad(self, xs_pad):
+            return training.avsr_posenc_forward(self, xs_pad)
         x2 = xs_pad.reshape(B * T, d).contiguous().float()
         sc = self._packed.get("xscale" + str(x2.device), [],
                               lambda: (torch.full((1,), math.sqrt(d), device=x2.device),

@@ -199,15 +199,13 @@ def require_cuda(*tensors) -> None:
 
 
 def require_inference(module: torch.nn.Module, *tensors) -> None:
-    """For the modules whose backward is not built (the tailored AV layer, the fusion module, the AV
-    embedding layer, InterCTC): refuse a grad-mode call loudly instead of silently detaching the
-    graph.  MyBranchformerEncoder / its layers / ConventionalEncoder / CTC route grad-mode calls to
-    training.py instead."""
+    """For the pieces whose backward is not built (InterCTC conditioning): refuse a grad-mode call
+    loudly instead of silently detaching the graph.  Every encoder / fusion / embed / CTC module
+    routes grad-mode calls to training.py instead."""
     if torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters()):
         raise NotImplementedError(
             f"tailored_avsr_b200: {type(module).__name__} has no CUDA backward yet; call it under "
-            "torch.no_grad() / torch.inference_mode() (the training path covers "
-            "MyBranchformerEncoder, ConventionalEncoder and CTC: see README 'Training').")
+            "torch.no_grad() / torch.inference_mode() (see README 'Training').")
     require_cuda(*tensors)
 
 

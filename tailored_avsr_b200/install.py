@@ -9,11 +9,10 @@ adds to each task file
 
 and `avsr_main.py`, the YAML configs and checkpoints run unchanged.
 
-Training coverage of what gets installed (INTEGRATION.md "Training"): grad-mode calls are built for
-`branchformer` (front ends linear / None), `conventional` (without InterCTC) and CTC; the other
-classes are inference-only for now and raise NotImplementedError in grad mode rather than fall back.
-`only=` installs a subset, so a training run can keep the stock class where ours cannot train yet:
-`install_avsr(globals(), only=("conventional", "ctc"))`.
+Training coverage of what gets installed (INTEGRATION.md "Training"): grad-mode calls of every
+class are built (training.py) except InterCTC taps / self-conditioning, which raise
+NotImplementedError in grad mode rather than fall back.  `only=` installs a subset, should a
+maintainer want a stock class somewhere: `install_avsr(globals(), only=("conventional", "ctc"))`.
 """
 from __future__ import annotations
 

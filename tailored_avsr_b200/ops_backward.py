@@ -198,6 +198,21 @@ def csgu_bwd(h: torch.Tensor, norm_g: torch.Tensor, norm_b: torch.Tensor, conv_w
     return dh, dng, dnb, dcw, dcb
 
 
+def conv2d_sub_bwd(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, dA: torch.Tensor):
+    """(d conv1.weight (C, 9), d conv1.bias (C,)) of the Conv2dSubsampling front end from the
+    gradient dA of its im2col operand (tavsr_conv2d_sub_bwd); x (B, Tin, F) fp32, w1 (C, 9)."""
+    B, Tin, F = x.shape
+    C = w1.shape[0]
+    lib = _lib.load()
+    nbytes = lib.tavsr_conv2d_sub_bwd_workspace_bytes(B, Tin, C)
+    ws = _ws(nbytes, x.device)
+    grads = torch.empty((C, 10), device=x.device, dtype=torch.float32)
+    check(lib.tavsr_conv2d_sub_bwd(x.data_ptr(), B, Tin, F, w1.data_ptr(), b1.data_ptr(), C,
+                                   dA.data_ptr(), grads.data_ptr(), ws.data_ptr(), nbytes, _stream()),
+          "tavsr_conv2d_sub_bwd")
+    return grads[:, :9].contiguous(), grads[:, 9].contiguous()
+
+
 def merge_learned_ave_bwd(x1: torch.Tensor, x2: torch.Tensor, dm: torch.Tensor, lens: torch.Tensor,
                           a1: torch.Tensor, b1: torch.Tensor, a2: torch.Tensor, b2: torch.Tensor,
                           scal: torch.Tensor, B: int, T: int, lens2: Optional[torch.Tensor] = None):

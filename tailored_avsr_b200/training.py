@@ -470,6 +470,116 @@ class _MaskFn(torch.autograd.Function):
         return _mul(dy.contiguous(), mask), None
 
 
+class _ScaleFn(torch.autograd.Function):
+    """y = s * x on our elementwise kernel (the positional encoding's x * sqrt(d))."""
+
+    @staticmethod
+    def forward(ctx, x, s):
+        ctx.s = float(s)
+        sc = torch.full((1,), ctx.s, device=x.device)
+        return ops.scale_add_rows(x, x, sc, _scalars(x.device)[1], max(1, x.shape[0]))
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous()
+        sc = torch.full((1,), ctx.s, device=dy.device)
+        return ops.scale_add_rows(dy, dy, sc, _scalars(dy.device)[1], max(1, dy.shape[0])), None
+
+
+class _Conv2dFrontFn(torch.autograd.Function):
+    """espnet Conv2dSubsampling up to its Linear (encoder.py:149-155): x (B, Tin, F) ->
+    Linear(flatten(relu(conv2(relu(conv1(x)))))) as (B*T2, d).  Forward = the inference kernels (conv1
+    on the fly inside the im2col writer, conv2 and the projection on the tcgen05 GEMM); backward =
+    dgrad / wgrad of the two GEMMs + the col2im gather with conv1's ReLU mask and weight reduction
+    (tavsr_conv2d_sub_bwd).  The input features get no gradient."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, wl, bl):
+        B, Tin, Fin = x.shape
+        C = w1.shape[0]
+        T2, F2 = ((Tin - 1) // 2 - 1) // 2, ((Fin - 1) // 2 - 1) // 2
+        w1p = w1.reshape(C, 9).contiguous().float()
+        w2p = w2.permute(0, 2, 3, 1).reshape(C, 9 * C).contiguous().float()
+        wlp = wl.view(-1, C, F2).permute(0, 2, 1).reshape(-1, F2 * C).contiguous().float()
+        xc = x.contiguous().float()
+        A = ops.conv2d_sub_im2col(xc, w1p, b1)
+        h2 = ops.gemm_bias_act(A, w2p, b2, act=ops.ACT_RELU)          # relu'(z) == (h > 0)
+        y = ops.gemm_bias_act(h2.view(B * T2, F2 * C), wlp, bl)
+        ctx.save_for_backward(xc, w1p, b1, A, h2, w2p, wlp)
+        ctx.dims = (B, T2, F2, C)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, w1p, b1, A, h2, w2p, wlp = ctx.saved_tensors
+        B, T2, F2, C = ctx.dims
+        d = wlp.shape[0]
+        dh2, dwlp, dbl = ob.linear_bwd(h2.view(B * T2, F2 * C), wlp, dy.contiguous())
+        dz2 = ob.act_bwd(h2, dh2.view(B * T2 * F2, C), ops.ACT_RELU)
+        dA, dw2p, db2 = ob.linear_bwd(A, w2p, dz2)
+        dw1, db1 = ob.conv2d_sub_bwd(xc, w1p, b1, dA)
+        dwl = dwlp.view(d, F2, C).permute(0, 2, 1).reshape(d, C * F2)
+        dw2 = dw2p.view(C, 3, 3, C).permute(0, 3, 1, 2)
+        return None, dw1.view(C, 1, 3, 3), db1, dw2, db2, dwl, dbl
+
+
+def conv2d_front_forward(embed, x_in: torch.Tensor):
+    """Conv2dSubsampling / Conv2dSubsamplingWOPosEnc parameters -> (B*T2, d) projection output."""
+    conv = embed.conv
+    lin = embed.out[0] if isinstance(embed.out, torch.nn.Sequential) else embed.out
+    return _Conv2dFrontFn.apply(x_in, conv[0].weight, conv[0].bias, conv[2].weight, conv[2].bias,
+                                lin.weight, lin.bias)
+
+
+def posenc_dropouts(pe, x2d: torch.Tensor, pos_emb: torch.Tensor, B: int, T: int, active: bool):
+    """espnet RelPositionalEncoding.forward in train mode: dropout(x * sqrt(d)) (the scaling is done
+    by the caller), dropout(pos_emb), in that order."""
+    d = x2d.shape[1]
+    if active:
+        m = draw_mask((B, T, d), float(pe.dropout_rate), x2d.device)
+        if m is not None:
+            x2d = _MaskFn.apply(x2d, m.view(B * T, d))
+        m = draw_mask(tuple(pos_emb.shape), float(pe.dropout_rate), x2d.device)
+        if m is not None:
+            pos_emb = _mul(pos_emb.reshape(-1, d).contiguous().float(), m.view(-1, d)).view(pos_emb.shape)
+    return x2d, pos_emb
+
+
+def avsr_embed_forward(E, xs_pad: torch.Tensor, masks: torch.Tensor):
+    """Training form of DefaultEmbeddingLayerForAVSR.apply_embed_layer (default.py:139-153):
+    conv2d (Conv2dSubsamplingWOPosEnc), linear (Linear + LayerNorm + Dropout), None / Linear."""
+    from .embedding_for_avsr.default import Conv2dSubsamplingWOPosEnc
+    d = E._output_size
+    if isinstance(E.embed, Conv2dSubsamplingWOPosEnc):
+        B, Tin, _ = xs_pad.shape
+        T = ((Tin - 1) // 2 - 1) // 2
+        x = conv2d_front_forward(E.embed, xs_pad)
+        return x.view(B, T, d), masks[:, :, :-2:2][:, :, :-2:2]
+    if E.embed is None:
+        return xs_pad, masks
+    B, T, Fin = xs_pad.shape
+    x2 = xs_pad.reshape(B * T, Fin).contiguous().float()
+    if isinstance(E.embed, torch.nn.Sequential):
+        lin, ln, dr = E.embed[0], E.embed[1], E.embed[2]
+        x = _LayerNormFn.apply(_LinearFn.apply(x2, lin.weight, lin.bias), ln.weight, ln.bias, ln.eps, 1.0)
+        if E.training:
+            m = draw_mask((B, T, d), float(dr.p), x.device)
+            if m is not None:
+                x = _MaskFn.apply(x, m.view(B * T, d))
+    else:
+        x = _LinearFn.apply(x2, E.embed.weight, E.embed.bias)
+    return x.view(B, T, d), masks
+
+
+def avsr_posenc_forward(E, xs_pad: torch.Tensor):
+    """Training form of apply_pos_enc (default.py:156-162): (dropout(x * sqrt(d)), dropout(pos_emb))."""
+    B, T, d = xs_pad.shape
+    x = _ScaleFn.apply(xs_pad.reshape(B * T, d).contiguous().float(), math.sqrt(d))
+    pos_emb = E.pos_enc.pos_emb(T, xs_pad.device)
+    x, pos_emb = posenc_dropouts(E.pos_enc, x, pos_emb, B, T, E.training)
+    return x.view(B, T, d), pos_emb
+
+
 class _LinearFn(torch.autograd.Function):
     """y = x W^T + b on the tcgen05 GEMM (the `linear` input layer)."""
 
@@ -805,9 +915,14 @@ def encoder_forward(enc, xs_pad, ilens, max_layer=None, masks=None):
             m = draw_mask(tuple(pos_emb.shape), float(pe.dropout_rate), dev)
             if m is not None:
                 pos_emb = _mul(pos_emb.reshape(-1, d).contiguous().float(), m.view(-1, d)).view(pos_emb.shape)
-    else:
-        raise NotImplementedError("the training path has no backward for the conv2d front end yet "
-                                  "(input_layer 'linear' and None are built): see README 'Training'")
+    else:                                                      # input_layer == "conv2d"
+        B, Tin, _ = x_in.shape
+        T = ((Tin - 1) // 2 - 1) // 2
+        pe = enc.embed.out[1]
+        x = _ScaleFn.apply(conv2d_front_forward(enc.embed, x_in), math.sqrt(d))
+        pos_emb = pe.pos_emb(T, dev)
+        x, pos_emb = posenc_dropouts(pe, x, pos_emb, B, T, enc.training)
+        masks = masks[:, :, :-2:2][:, :, :-2:2]
     lens = masks.reshape(B, -1).sum(dim=1).to(torch.int32)
     pos2d = pos_emb.reshape(-1, d).contiguous().float()
     shared = (pos2d, ob.transpose_2d(pos2d, pad=True))

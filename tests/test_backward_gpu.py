@@ -256,6 +256,11 @@ def test_act_fwd_with_and_without_mask(act):
 # ---------------------------------------------------------------------------------------------------
 GRAD_TOL = 2e-3   # ||g - g_ref||_F / ||g_ref||_F per tensor; TF32 products forward and backward
 SCALAR_TOL = 5e-3  # the Linear(256, 1) biases: one number each, no averaging over entries
+BIAS_UV_TOL = 4e-3  # attn.pos_bias_u / _v: column sums over every frame of d q parts whose terms cancel
+                    # row-wise (sum_j g_ij = 0); the TF32 rounding of g in the tensor-core backward
+                    # breaks the exact cancellation (measured worst 2.1e-3)
+CONV_TOL = 3e-2    # conv2d front-end weights against an fp32 / fp64 reference whose ReLU decisions differ
+                   # from the TF32 forward's in a few near-zero entries (test_conv2d_front_end_backward)
 POOL_TOL = 5e-3    # pooling-head weights in the dropout test (see there)
 POOL_SCALAR_TOL = 3e-2   # ... and their biases: single numbers of size 1e-3, sums of cancelling terms
 POOL_SCALAR_ATOL = 5e-4  # absolute floor for those biases: sum over utterances of d omega_b, which have
@@ -292,7 +297,7 @@ def _train_step(name, stoch=None, drop=None):
 
 
 @pytest.mark.parametrize("name", ["vsr_small", "vsr_tailored_small", "concat_small", "fixed_ave_small",
-                                  "vsr_max_layer"])
+                                  "vsr_max_layer", "asr_small", "asr_tailored_small"])
 def test_encoder_training_gradients_match_reference(name):
     """Gradients of the input and of EVERY encoder / CTC parameter from the CUDA training path equal
     (a) autograd through the CPU oracle port on the same inputs and (b) where stored, the golden
@@ -310,7 +315,8 @@ def test_encoder_training_gradients_match_reference(name):
     assert abs(float(loss) - float(lr)) <= 2e-3 * abs(float(lr)), (float(loss), float(lr))
     worst = ("", 0.0)
     checked = 0
-    pairs = [("input", x.grad, xr.grad)]
+    # the conv2d front end gives its input features no gradient (asr_* cases)
+    pairs = [("input", x.grad, xr.grad)] if c["cfg"]["input_layer"] != "conv2d" else []
     pairs += [("enc." + n, p.grad, leaf[n].grad) for n, p in enc.named_parameters()]
     pairs += [("ctc." + n, p.grad, leaf["ctc." + n].grad) for n, p in ctc.named_parameters()]
     for n, got, want in pairs:
@@ -327,7 +333,9 @@ def test_encoder_training_gradients_match_reference(name):
         checked += 1
         if err > worst[1]:
             worst = (n, err)
-        assert err <= (SCALAR_TOL if want.numel() == 1 else GRAD_TOL), (n, err)
+        tol_n = CONV_TOL if ".embed.conv." in n else (
+            BIAS_UV_TOL if ".pos_bias_" in n else (SCALAR_TOL if want.numel() == 1 else GRAD_TOL))
+        assert err <= tol_n, (n, err)
     print(f"TRAIN {name}: {checked} gradients, worst {worst[0]} {worst[1]:.2e}")
     gpath = os.path.join(_util.GOLDEN_DIR, f"grad_{name}.npz")
     if os.path.exists(gpath):
@@ -339,17 +347,20 @@ def test_encoder_training_gradients_match_reference(name):
             if not key.startswith("norm/"):
                 continue
             n = key[5:]
+            if n == "input" and grads[n] is None:
+                continue
             gn = float(gold[key])
             g = grads[n].double().cpu().reshape(-1)
             if gn < 1e-6:
                 continue
-            assert abs(float(g.norm()) - gn) <= 2 * GRAD_TOL * gn, (n, float(g.norm()), gn)
+            tol_n = CONV_TOL if ".embed.conv." in n else GRAD_TOL
+            assert abs(float(g.norm()) - gn) <= 2 * tol_n * gn, (n, float(g.norm()), gn)
             sample = g[:: max(1, g.numel() // 16)][:16].numpy()
             assert np.allclose(sample, gold["sample/" + n], rtol=2e-2,
-                               atol=4 * GRAD_TOL * gn / max(1.0, g.numel() ** 0.5) + 1e-9), n
+                               atol=4 * tol_n * gn / max(1.0, g.numel() ** 0.5) + 1e-9), n
 
 
-@pytest.mark.parametrize("name", ["vsr_small", "vsr_tailored_small", "concat_small"])
+@pytest.mark.parametrize("name", ["vsr_small", "vsr_tailored_small", "concat_small", "asr_small"])
 def test_encoder_training_with_dropout_matches_reference(name):
     """a11 dropout: a train()-mode step with every dropout site of the reference active (rates 0.1
     as in the shipped YAMLs) equals the REAL reference modules run with the same masks
@@ -391,7 +402,7 @@ def test_encoder_training_with_dropout_matches_reference(name):
             continue
         n = key[5:]
         gn = float(gold[key])
-        if gn < 1e-6:
+        if gn < 1e-6 or (n == "input" and grads[n] is None):   # conv2d front: no input gradient
             continue
         g = grads[n].double().cpu().reshape(-1)
         # the learned_ave pooling head (pooling_proj / weight_proj: 4 small tensors per block whose
@@ -399,7 +410,7 @@ def test_encoder_training_with_dropout_matches_reference(name):
         # POOL_TOL; everything else the tolerances of the dropout-free test
         pool = ".pooling_proj" in n or ".weight_proj" in n
         tol = (POOL_SCALAR_TOL if g.numel() == 1 else POOL_TOL) if pool else \
-            (SCALAR_TOL if g.numel() == 1 else GRAD_TOL)
+            (CONV_TOL if ".embed.conv." in n else (SCALAR_TOL if g.numel() == 1 else GRAD_TOL))
         dev_n = abs(float(g.norm()) - gn) / gn
         worst = max(worst, (dev_n / tol, n, dev_n))
         floor = POOL_SCALAR_ATOL if (pool and g.numel() == 1) else 0.0
@@ -489,6 +500,76 @@ def test_av_training_encoder_plus_fusion_matches_reference(name, drop):
         checked += 1
     print(f"AV TRAIN {name} drop={drop}: {checked} gradients, worst norm deviation {worst[1]} {worst[2]:.2e}")
     assert checked > (180 if "conventional" in name else 120)
+
+
+@pytest.mark.parametrize("B,Tin,F", [(2, 43, 80), (3, 27, 23), (1, 7, 7)])
+def test_conv2d_front_end_backward(B, Tin, F):
+    """Conv2dSubsampling up to its Linear as an autograd node on the CUDA kernels (im2col forward, GEMM
+    dgrad / wgrad, col2im gather + conv1 ReLU mask + weight reduction) against torch autograd of
+    F.conv2d / F.linear in fp64.  The reference takes conv2's ReLU decisions from the CUDA forward:
+    its pre-activations are TF32 products, a handful of entries near zero fall on the other side of
+    the ReLU than in fp64, and with unstructured random data (gradients = sums of random-sign terms
+    over a few hundred rows) each such entry moves a weight gradient by percents - a property of the
+    comparison, not of the kernels (with the decisions shared, everything agrees to 1e-3)."""
+    import torch.nn.functional as Fn
+    from tailored_avsr_b200 import ops, training
+    C, d = 256, 256
+    g = torch.Generator().manual_seed(B * Tin + F)
+    T2, F2 = ((Tin - 1) // 2 - 1) // 2, ((F - 1) // 2 - 1) // 2
+    x = torch.randn(B, Tin, F, generator=g)
+    ps = [torch.randn(C, 1, 3, 3, generator=g) * 0.3, torch.randn(C, generator=g) * 0.1,
+          torch.randn(C, C, 3, 3, generator=g) * 0.02, torch.randn(C, generator=g) * 0.1,
+          torch.randn(d, C * F2, generator=g) * 0.02, torch.randn(d, generator=g) * 0.1]
+    dy = torch.randn(B * T2, d, generator=g)
+    mine = [p.to(DEV).requires_grad_(True) for p in ps]
+    y = training._Conv2dFrontFn.apply(x.to(DEV), *mine)
+    y.backward(dy.to(DEV))
+    torch.cuda.synchronize()
+    with torch.no_grad():   # conv2's ReLU decisions of the CUDA forward, as a (B, C, T2, F2) mask
+        A = ops.conv2d_sub_im2col(x.to(DEV), ps[0].reshape(C, 9).contiguous().to(DEV), ps[1].to(DEV))
+        h2 = ops.gemm_bias_act(A, ps[2].permute(0, 2, 3, 1).reshape(C, 9 * C).contiguous().to(DEV),
+                               ps[3].to(DEV), act=ops.ACT_RELU)
+        m2 = (h2 > 0).view(B, T2, F2, C).permute(0, 3, 1, 2).cpu().double()
+    ref = [p.double().requires_grad_(True) for p in ps]
+    h = Fn.relu(Fn.conv2d(x.double().unsqueeze(1), ref[0], ref[1], stride=2))
+    h = Fn.conv2d(h, ref[2], ref[3], stride=2) * m2
+    yr = Fn.linear(h.transpose(1, 2).contiguous().view(B * T2, C * F2), ref[4], ref[5])
+    yr.backward(dy.double())
+    assert _rel(y, yr.detach()) < 2e-3
+    errs = {n: _rel(a.grad, b.grad) for a, b, n in zip(mine, ref, ("w1", "b1", "w2", "b2", "wl", "bl"))}
+    print("CONV2D BWD", (B, Tin, F), {k: f"{v:.1e}" for k, v in errs.items()})
+    assert max(errs.values()) < 3e-3, errs
+
+
+@pytest.mark.parametrize("input_layer", ["conv2d", "linear"])
+def test_avsr_embed_layer_training_gradients(input_layer):
+    """DefaultEmbeddingLayerForAVSR.forward (embed + positional encoding) in grad mode against torch
+    autograd through the oracle port (oracle/ref_path.py::avsr_embed_layer / rel_pos_enc)."""
+    from oracle import ref_path, synth
+    from tailored_avsr_b200.embedding_for_avsr.default import DefaultEmbeddingLayerForAVSR
+    Fin, d, B, Tin = (80, 256, 2, 47) if input_layer == "conv2d" else (512, 256, 2, 19)
+    E = DefaultEmbeddingLayerForAVSR(Fin, d, input_layer=input_layer).eval()
+    sd = synth.fill_module(E, seed=5, prefix="e.")
+    E = E.to(DEV)
+    xs = synth.randn((B, Tin, Fin), 9)
+    ilens = torch.tensor([Tin, Tin - 5])
+    (x, pos), masks = E(xs.to(DEV).requires_grad_(input_layer == "linear"), ilens.to(DEV))
+    assert x.requires_grad
+    R = synth.randn(tuple(x.shape), 10)
+    (x * R.to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    leaf = {k: v.clone().double().requires_grad_(True) for k, v in sd.items()}
+    xr, mr = ref_path.avsr_embed_layer(xs.double(), ilens, leaf, "e.", input_layer)
+    xr, posr = ref_path.rel_pos_enc(xr)
+    (xr * R.double()).sum().backward()
+    assert torch.equal(masks.cpu(), mr) and _rel(x, xr.detach()) < 2e-3 and _rel(pos, posr) < 1e-5
+    for n, p in E.named_parameters():
+        # conv weights: ReLU decisions of conv2 differ between the TF32 forward and the fp64 port in
+        # a few entries (see test_conv2d_front_end_backward, which shares them and agrees to 1e-3)
+        # (loose bound here: this test's loss is a random projection of ~20 output rows, the worst
+        # case for that effect; the plumbing - names, layouts, permutations - is what it checks)
+        tol = 0.25 if ".conv." in n else 3e-3
+        assert _rel(p.grad, leaf["e." + n].grad) < tol, (n, _rel(p.grad, leaf["e." + n].grad))
 
 
 def test_training_stochastic_depth_and_branch_drop_follow_the_host_rng():
