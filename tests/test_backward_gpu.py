@@ -256,9 +256,10 @@ def test_act_fwd_with_and_without_mask(act):
 # ---------------------------------------------------------------------------------------------------
 GRAD_TOL = 2e-3   # ||g - g_ref||_F / ||g_ref||_F per tensor; TF32 products forward and backward
 SCALAR_TOL = 5e-3  # the Linear(256, 1) biases: one number each, no averaging over entries
-BIAS_UV_TOL = 4e-3  # attn.pos_bias_u / _v: column sums over every frame of d q parts whose terms cancel
-                    # row-wise (sum_j g_ij = 0); the TF32 rounding of g in the tensor-core backward
-                    # breaks the exact cancellation (measured worst 2.1e-3)
+BIAS_UV_TOL = 4e-3  # attn.pos_bias_u / _v and attn.linear_pos.weight: sums over every frame (and
+                    # utterance) of terms that cancel row-wise (sum_j g_ij = 0 for a softmax); the TF32
+                    # rounding of g in the tensor-core backward breaks the exact cancellation
+                    # (measured worst 2.3e-3; 1.1e-3 with the fp32-FMA backward it replaced)
 CONV_TOL = 3e-2    # conv2d front-end weights against an fp32 / fp64 reference whose ReLU decisions differ
                    # from the TF32 forward's in a few near-zero entries (test_conv2d_front_end_backward)
 POOL_TOL = 5e-3    # pooling-head weights in the dropout test (see there)
@@ -334,7 +335,8 @@ def test_encoder_training_gradients_match_reference(name):
         if err > worst[1]:
             worst = (n, err)
         tol_n = CONV_TOL if ".embed.conv." in n else (
-            BIAS_UV_TOL if ".pos_bias_" in n else (SCALAR_TOL if want.numel() == 1 else GRAD_TOL))
+            BIAS_UV_TOL if (".pos_bias_" in n or ".linear_pos." in n) else (
+                SCALAR_TOL if want.numel() == 1 else GRAD_TOL))
         assert err <= tol_n, (n, err)
     print(f"TRAIN {name}: {checked} gradients, worst {worst[0]} {worst[1]:.2e}")
     gpath = os.path.join(_util.GOLDEN_DIR, f"grad_{name}.npz")
