@@ -12,7 +12,10 @@ python bench.py --steps 5 --warmup 2 --impl reference 2>>$O/err_c2.log | tail -1
 for w in C1 C3 C4; do for dt in bf16 tf32; do
   python bench.py --workload $w --steps 20 --warmup 5 --no-cpu --no-extra --dtype $dt 2>$O/err_$w.log | tail -1 > $O/bench_${w}_${dt}_1gpu.json
 done; done
-for f in $O/bench_*_1gpu.json; do python -c "
+for w in C1 C3 C4; do
+  python bench.py --workload $w --mode train --train-steps 5 --steps 5 --warmup 3 --no-cpu 2>>$O/err_$w.log | tail -1 > $O/bench_${w}_train_1gpu.json
+done
+for f in $O/bench_*_bf16_1gpu.json $O/bench_*_tf32_1gpu.json; do python -c "
 import json; d=json.load(open('$f')); print('$f', d['dtype'], round(d['value']), round(d['ms_per_step'],4), round(d['e2e']['value']), round(d['roofline']['frac'],4), round(d['roofline']['avg_launch_us'],1), d['roofline']['kernel'][:24])"; done | tee $O/bench_summary.txt
 K='regex:gemm_sm100|ffn_fused|csgu|ctc_|merge_|relpos|layernorm|vocab|row_dots|conv2d|scale_add|split_tf32'
 for dt in bf16 tf32; do
@@ -24,6 +27,9 @@ for dt in bf16 tf32; do
   python tools/ncu_summary.py $O/ncu_full_c2_${dt}_raw.csv > $O/ncu_full_c2_${dt}_summary.csv
   head -12 $O/ncu_full_c2_${dt}_summary.csv
 done
+for f in $O/bench_c2_bf16_1gpu.json $O/bench_C*_train_1gpu.json; do python -c "
+import json; d=json.load(open('$f')); t=d.get('train') or {}; e=t.get('eager_variant') or {}
+print('$f', 'train graph ms', t.get('ms_per_step'), 'frames/s', t.get('value'), 'eager ms', e.get('ms_per_step'), 'eval-mode ms', e.get('eval_mode_ms_per_step'))"; done | tee $O/train_summary.txt
 python tools/ncu_traffic.py bf16=$O/ncu_full_c2_bf16_raw.csv tf32=$O/ncu_full_c2_tf32_raw.csv > $O/r02_ncu_traffic.json
 cat $O/r02_ncu_traffic.json | head -30
 rm -f $O/*.ncu-rep   # keep the merged output small: the raw csv pages are what is read back
