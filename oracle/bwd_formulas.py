@@ -1,9 +1,9 @@
 """TEST INFRASTRUCTURE: explicit (autograd-free) backward formulas of the hot-path leaves, written
-the way the CUDA backward kernels will compute them and
-verified against torch.autograd on the oracle port (tests/test_bwd_formulas_cpu.py).  The encoder
-backward kernels are not built yet; this file fixes their arithmetic - in particular the
-rel-shift scatter of the attention backward and the two-level softmax of the learned_ave merge -
-ahead of time.  Plain torch in whatever dtype the caller passes (tests use float64).
+the way the CUDA backward kernels compute them (csrc/backward.cu, csrc/attention_bwd.cu) and
+verified against torch.autograd on the oracle port (tests/test_bwd_formulas_cpu.py).  This file
+fixes the kernels' arithmetic - in particular the rel-shift scatter of the attention backward and
+the two-level softmax of the learned_ave merge - and is what their GPU tests compare against.
+Plain torch in whatever dtype the caller passes (tests use float64).
 
 Reference forward definitions: espnet leaves as restated in oracle/ref_path.py (SURVEY.md
 Appendix A), called from src/encoder/branchformer/encoder_layer.py:193-316."""

@@ -1,10 +1,11 @@
-"""TEST INFRASTRUCTURE: golden GRADIENTS of the hot path for the training rows of SURVEY.md §8
-(encoder backward, not built yet): the REAL reference modules (eval mode: dropout and stochastic
-depth are identities, the arithmetic is the training arithmetic) run live over oracle/espnet_shim
-with autograd on, loss = CTC loss of the case; per parameter the gradient's L2 norm, its sum and
-a strided sample are stored.  The functional port (oracle/ref_path.py, plain differentiable torch)
-must reproduce them (tests/test_oracle_cpu.py), which pins the oracle the backward kernels will
-be checked against.  Run in the build container:  python -m oracle.gen_golden_grad"""
+"""TEST INFRASTRUCTURE: golden GRADIENTS of the hot path for the training rows of SURVEY.md §8: the
+REAL reference modules run live over oracle/espnet_shim with autograd on, loss = CTC loss of the
+case (on the fused stream for the audio-visual cases); per parameter and input the gradient's L2
+norm, its sum and a strided sample are stored.  Two sets: eval mode (dropout and stochastic depth
+are identities, the arithmetic is the training arithmetic) and train() mode with every dropout
+active and masks injected from oracle/dropmask.py (grad_<case>_dropout.npz).  The functional port
+(oracle/ref_path.py) must reproduce the eval set (tests/test_oracle_cpu.py), and the CUDA training
+path both (tests/test_backward_gpu.py).  Run in the build container:  python -m oracle.gen_golden_grad"""
 from __future__ import annotations
 
 import os

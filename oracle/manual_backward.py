@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE: the backward of one two-branch learned_ave Branchformer block composed BY
 HAND from the leaf formulas of oracle/bwd_formulas.py, in the order and with the saved tensors the
-CUDA training path will use: which activations are kept from the forward,
+CUDA training path uses (tailored_avsr_b200/training.py): which activations are kept from the forward,
 where the residual gradients join, how the merge gradient splits into the two branches.  Verified
 against torch.autograd on ref_path.branchformer_layer (tests/test_bwd_formulas_cpu.py).
 
