@@ -395,6 +395,10 @@ int tavsr_ctc_head_bwd(const float* dlogits, const float* row_scale, int rows_pe
                        float* dw, float* db, void* workspace, long long workspace_bytes, int M,
                        int D, int V, void* stream);
 
+/* Softmax backward over the vocabulary (training of InterCTC self-conditioning, encoder.py:393-401):
+ * dlogits[m][v] = p[m][v] * (dp[m][v] - sum_v p[m][v] dp[m][v]); p, dp, dlogits contiguous [M, V]. */
+int tavsr_softmax_bwd(const float* p, const float* dp, float* dlogits, int M, int V, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Backward kernels of the encoder (training): transcriptions of
  * oracle/bwd_formulas.py (verified against autograd on the CPU), checked on the GPU in

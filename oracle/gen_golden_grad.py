@@ -18,14 +18,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import cases, dropmask, gen_golden, reference_loader  # noqa: E402
 
-CASES = ["vsr_small", "asr_small", "asr_tailored_small", "vsr_tailored_small", "concat_small"]
+CASES = ["vsr_small", "asr_small", "asr_tailored_small", "vsr_tailored_small", "concat_small",
+         "asr_interctc_cond"]
+INTERCTC_WEIGHT = 0.5   # InterCTC cases: loss = CTC(final) + 0.5 * sum over taps of CTC(tap)
 # train() mode with every dropout site active (rates of the case's config, 0.1 like the shipped
 # YAMLs), masks from oracle/dropmask.py::MaskSource(GOLDEN_SEED): grad_<case>_dropout.npz
 DROPOUT_CASES = ["vsr_small", "asr_small", "vsr_tailored_small", "concat_small",
-                 "av_fusion_conventional", "av_fusion_tailored"]
+                 "av_fusion_conventional", "av_fusion_tailored", "asr_interctc_cond",
+                 "av_tailored_interctc", "av_conventional_interctc"]
 # audio-visual: ConventionalEncoder + AdaptiveAudioVisualFusion + CTC on the fused stream
 # (avsr_espnet_model.py:467,678), different audio / video masks
-AV_CASES = ["av_fusion_conventional", "av_fusion_tailored"]
+AV_CASES = ["av_fusion_conventional", "av_fusion_tailored", "av_tailored_interctc",
+            "av_tailored_interctc_sep", "av_conventional_interctc"]
 
 
 def summarize(named_grads):
@@ -52,9 +56,14 @@ def main():
         if c["kind"] == "single":
             x = inp["x"].clone().requires_grad_(True)
             with dropmask.patched_dropout(src):
-                y, olens, _ = enc(x, inp["lens"])
+                y, olens, _ = enc(x, inp["lens"], ctc=ctc)
                 tl = cases.target_lens(name, olens)
+                taps = []
+                if isinstance(y, tuple):
+                    y, taps = y
                 loss = ctc(y, olens, inp["ys_pad"], tl)
+                for _, tap in taps:
+                    loss = loss + INTERCTC_WEIGHT * ctc(tap, olens, inp["ys_pad"], tl)
             inputs = [("input", x)]
         else:
             from oracle.ref_path import make_valid_mask, rel_pos_emb
@@ -64,10 +73,15 @@ def main():
             a = inp["audio"].clone().requires_grad_(True)
             v = inp["video"].clone().requires_grad_(True)
             with dropmask.patched_dropout(src):
-                ya, _, yv, _, _ = enc((a, pos), mask, (v, pos), mask_v)
+                ya, _, yv, _, _ = enc((a, pos), mask, (v, pos), mask_v, ctc=ctc, audiovisual_fusion=fusion)
+                taps = []
+                if isinstance(ya, tuple):
+                    ya, taps = ya
                 y, olens = fusion(ya, mask, yv, mask_v)
                 tl = cases.target_lens(name, olens)
                 loss = ctc(y, olens, inp["ys_pad"], tl)
+                for _, tap in taps:      # the fused intermediate outputs (avsr_espnet_model.py)
+                    loss = loss + INTERCTC_WEIGHT * ctc(tap, olens, inp["ys_pad"], tl)
             inputs = [("input_audio", a), ("input_video", v)]
         loss.backward()
         if drop:

@@ -163,6 +163,7 @@ SIGNATURES = {
                                    c_void_p]),
     "tavsr_merge_learned_ave_weights_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                                     c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "tavsr_softmax_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "tavsr_ctc_greedy": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                  c_void_p]),
     "tavsr_ctc_prefix_score": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

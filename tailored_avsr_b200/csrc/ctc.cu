@@ -535,6 +535,28 @@ ctc_loss_kernel(const float* __restrict__ logp, const int64_t* __restrict__ targ
 }
 
 // ------------------------------------------------------------------------------------------------
+// Softmax backward over the vocabulary, one warp per row:  dl = p * (dp - sum_v p dp).
+// (InterCTC self-conditioning on the training path: the gradient that comes back through
+// conditioning_layer(ctc.softmax(tap)), encoder.py:393-401, on its way to ctc_lo and the tap.)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+softmax_bwd_kernel(const float* __restrict__ p, const float* __restrict__ dp, float* __restrict__ dl,
+                   int M, int V) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const float* pr = p + static_cast<long long>(row) * V;
+  const float* dr = dp + static_cast<long long>(row) * V;
+  float s = 0.f;
+  for (int v = lane; v < V; v += 32) s = fmaf(ld_act(pr + v), ld_act(dr + v), s);
+  s = warp_sum(s);
+  for (int v = lane; v < V; v += 32)
+    dl[static_cast<long long>(row) * V + v] = ld_act(pr + v) * (ld_act(dr + v) - s);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Greedy decode: collapse repeats, drop blank.  One warp per utterance, ballot compaction.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
@@ -868,5 +890,14 @@ extern "C" int tavsr_ctc_head_bwd(const float* dlogits, const float* row_scale, 
                               static_cast<const float*>(part_w), static_cast<const float*>(part_b),
                               nblk, dw, db, V));
   g_launches.fetch_add(2, std::memory_order_relaxed);
+  return 0;
+}
+
+extern "C" int tavsr_softmax_bwd(const float* p, const float* dp, float* dlogits, int M, int V,
+                                 void* stream) {
+  TAVSR_REQUIRE(M > 0 && V > 0 && p && dp && dlogits, "softmax_bwd: bad arguments (M=%d V=%d)", M, V);
+  TAVSR_CUDA_OK(launch_kernel(ctc::softmax_bwd_kernel, dim3((M + 7) / 8), dim3(256), 0,
+                              static_cast<cudaStream_t>(stream), 0, p, dp, dlogits, M, V));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }

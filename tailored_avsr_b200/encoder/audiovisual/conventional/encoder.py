@@ -93,11 +93,8 @@ class ConventionalEncoder(AudioVisualAbsEncoder):
         from .... import training
         if training.wants_grad(self, a0, v0):
             # training step: the two stacks as autograd graphs of per-block nodes (training.py)
-            if len(self.interctc_layer_idx) > 0:
-                raise NotImplementedError("audio-visual InterCTC is not built on the training path")
-            ya, _, _ = training.encoder_forward(self.acoustic_encoder, audio_pad, None, masks=audio_masks)
-            yv, _, _ = training.encoder_forward(self.visual_encoder, video_pad, None, masks=video_masks)
-            return ya, audio_masks, yv, video_masks, None
+            return training.conventional_encoder_forward(self, audio_pad, audio_masks, video_pad,
+                                                         video_masks, ctc=ctc, fusion=audiovisual_fusion)
         if len(self.interctc_layer_idx) > 0:
             return self._forward_interctc(audio_pad, audio_masks, video_pad, video_masks, ctc,
                                           audiovisual_fusion)

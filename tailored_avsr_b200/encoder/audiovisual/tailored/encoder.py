@@ -159,7 +159,8 @@ class TailoredEncoder(AudioVisualAbsEncoder):
         engine.require_cuda(audio, video)
         from .... import training
         if training.wants_grad(self, audio, video):
-            return training.tailored_encoder_forward(self, audio_pad, audio_masks, video_pad, video_masks)
+            return training.tailored_encoder_forward(self, audio_pad, audio_masks, video_pad, video_masks,
+                                                     ctc=ctc, fusion=audiovisual_fusion)
         if audio.shape != video.shape:
             raise NotImplementedError("the B200 tailored encoder expects time-aligned streams of "
                                       "equal shape (avsr_espnet_model.py:439 aligns them)")

@@ -289,7 +289,7 @@ class MyBranchformerEncoder(AbsEncoder):
         engine.require_cuda(x_in)
         if training.wants_grad(self, x_in):
             # training step: one autograd node per block on the backward kernels (training.py)
-            return training.encoder_forward(self, xs_pad, ilens, max_layer=max_layer)
+            return training.encoder_forward(self, xs_pad, ilens, max_layer=max_layer, ctc=ctc)
         if self.interctc_use_conditioning and len(self.interctc_layer_idx) > 0:
             if ctc is None or self.conditioning_layer is None:
                 raise ValueError("InterCTC self-conditioning needs the `ctc` module and an assigned "

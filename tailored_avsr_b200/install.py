@@ -10,8 +10,8 @@ adds to each task file
 and `avsr_main.py`, the YAML configs and checkpoints run unchanged.
 
 Training coverage of what gets installed (INTEGRATION.md "Training"): grad-mode calls of every
-class are built (training.py) except InterCTC taps / self-conditioning, which raise
-NotImplementedError in grad mode rather than fall back.  `only=` installs a subset, should a
+class are built (training.py), InterCTC taps and self-conditioning included.  `only=` installs a
+subset, should a
 maintainer want a stock class somewhere: `install_avsr(globals(), only=("conventional", "ctc"))`.
 """
 from __future__ import annotations

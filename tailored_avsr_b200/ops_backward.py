@@ -198,6 +198,18 @@ def csgu_bwd(h: torch.Tensor, norm_g: torch.Tensor, norm_b: torch.Tensor, conv_w
     return dh, dng, dnb, dcw, dcb
 
 
+def softmax_bwd(p: torch.Tensor, dp: torch.Tensor) -> torch.Tensor:
+    """dlogits = p * (dp - sum_v p dp) over the last axis of contiguous (M, V) tensors
+    (tavsr_softmax_bwd)."""
+    if p.shape != dp.shape or not p.is_contiguous() or not dp.is_contiguous() or p.dtype != torch.float32:
+        raise _lib.TavsrError("softmax_bwd: p and dp must be contiguous fp32 tensors of one shape")
+    M, V = p.shape
+    out = torch.empty_like(p)
+    check(_lib.load().tavsr_softmax_bwd(p.data_ptr(), dp.data_ptr(), out.data_ptr(), M, V, _stream()),
+          "tavsr_softmax_bwd")
+    return out
+
+
 def conv2d_sub_bwd(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, dA: torch.Tensor):
     """(d conv1.weight (C, 9), d conv1.bias (C,)) of the Conv2dSubsampling front end from the
     gradient dA of its im2col operand (tavsr_conv2d_sub_bwd); x (B, Tin, F) fp32, w1 (C, 9)."""

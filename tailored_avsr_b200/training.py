@@ -470,6 +470,35 @@ class _MaskFn(torch.autograd.Function):
         return _mul(dy.contiguous(), mask), None
 
 
+class _CondFn(torch.autograd.Function):
+    """InterCTC self-conditioning, x + conditioning_layer(softmax(ctc_lo(tap))) (encoder.py:393-401;
+    ctc.py:160-168), as one autograd node: the CTC head and vocab-residual kernels forward; backward
+    = conditioning_layer's dgrad / wgrad over the vocabulary on the CTC head kernels, the softmax
+    backward, then the CTC head backward (gradients for x, the tap, ctc_lo and conditioning_layer)."""
+
+    @staticmethod
+    def forward(ctx, x, tap, wc, bc, wl, bl):
+        if wc.shape[0] > 64:
+            raise NotImplementedError("InterCTC conditioning on the training path is built for odim <= 64")
+        _, prob, _ = ops.ctc_head(tap.contiguous(), wc, bc, want_logp=False, want_prob=True)
+        out, _ = ops.vocab_residual(x.contiguous(), prob, wl.contiguous(), bl)
+        ctx.save_for_backward(tap, prob, wc, wl)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        tap, prob, wc, wl = ctx.saved_tensors
+        dout = dout.contiguous()
+        V = wc.shape[0]
+        wlT = ob.transpose_2d(wl.contiguous())                        # (V, d)
+        zero_b = torch.zeros((V,), device=dout.device, dtype=F32)
+        dp = ops.ctc_head(dout, wlT, zero_b, want_logp=False, want_logits=True)[3]     # dout . Wl
+        _, dwlT, _ = ops.ctc_head_bwd(prob, dout, wlT)                # (V, d) = prob^T . dout
+        dl = ob.softmax_bwd(prob, dp)
+        dtap, dwc, dbc = ops.ctc_head_bwd(dl, tap.contiguous(), wc.contiguous())
+        return dout, dtap, dwc, dbc, ob.transpose_2d(dwlT), ob.col_sums(dout)
+
+
 class _ScaleFn(torch.autograd.Function):
     """y = s * x on our elementwise kernel (the positional encoding's x * sqrt(d))."""
 
@@ -671,11 +700,82 @@ def tailored_layer_forward(layer, a2d, v2d, B: int, T: int, lens_a, lens_v, pos_
     return outs[0], outs[1]
 
 
-def tailored_encoder_forward(enc, audio_pad, audio_masks, video_pad, video_masks):
-    """Training forward of TailoredEncoder (tailored/encoder.py:221-330 without InterCTC taps):
-    modality encoding, the layer stack, the shared after_norm on both streams."""
-    if len(enc.interctc_layer_idx) > 0:
-        raise NotImplementedError("audio-visual InterCTC is not built on the training path")
+def _av_tap(enc, norm_a, norm_v, a, v, la, lv, B, T, ctc, fusion, inter, idx):
+    """One audio-visual InterCTC tap (tailored/encoder.py:270-318, conventional/encoder.py:156-199):
+    both streams normalised, fused (the fused stream is what the intermediate CTC loss sees), and with
+    self-conditioning the posteriors - of the fused stream, or of each stream - are added back to
+    BOTH streams through conditioning_layer.  Returns the (possibly conditioned) streams."""
+    d = a.shape[1]
+    ta = _LayerNormFn.apply(a, norm_a.weight, norm_a.bias, 1e-12, 1.0) if norm_a is not None else a
+    tv = _LayerNormFn.apply(v, norm_v.weight, norm_v.bias, 1e-12, 1.0) if norm_v is not None else v
+    fused = fusion_forward(fusion, ta, tv, la, lv, B, T)
+    inter.append((idx, fused.view(B, T, d)))
+    if enc.interctc_use_conditioning:
+        cl = enc.conditioning_layer
+        wc, bc = ctc.ctc_lo.weight, ctc.ctc_lo.bias
+        if enc.audiovisual_interctc_conditioning:
+            a = _CondFn.apply(a, fused, wc, bc, cl.weight, cl.bias)
+            v = _CondFn.apply(v, fused, wc, bc, cl.weight, cl.bias)
+        else:
+            a = _CondFn.apply(a, ta, wc, bc, cl.weight, cl.bias)
+            v = _CondFn.apply(v, tv, wc, bc, cl.weight, cl.bias)
+    return a, v
+
+
+def _check_av_taps(enc, ctc, fusion):
+    if fusion is None or not hasattr(fusion, "run"):
+        raise ValueError("audio-visual InterCTC taps need the B200 `audiovisual_fusion` module")
+    if enc.interctc_use_conditioning and (ctc is None or enc.conditioning_layer is None):
+        raise ValueError("InterCTC self-conditioning needs the `ctc` module and an assigned "
+                         "`conditioning_layer`")
+
+
+def conventional_encoder_forward(enc, audio_pad, audio_masks, video_pad, video_masks, ctc=None,
+                                 fusion=None):
+    """Training forward of ConventionalEncoder (conventional/encoder.py:116-215): the two stacks, or
+    with InterCTC taps their layer-zipped form."""
+    if len(enc.interctc_layer_idx) == 0:
+        ya, _, _ = encoder_forward(enc.acoustic_encoder, audio_pad, None, masks=audio_masks)
+        yv, _, _ = encoder_forward(enc.visual_encoder, video_pad, None, masks=video_masks)
+        return ya, audio_masks, yv, video_masks, None
+    _check_av_taps(enc, ctc, fusion)
+    ea, ev = enc.acoustic_encoder, enc.visual_encoder
+    if ea.embed is not None or ev.embed is not None:
+        raise NotImplementedError("the conventional AV encoder expects (x, pos_emb) inputs")
+    (audio, a_pos), (video, v_pos) = audio_pad, video_pad
+    B, T, d = audio.shape
+    dev = audio.device
+    a = audio.reshape(B * T, d).contiguous().float()
+    v = video.reshape(B * T, d).contiguous().float()
+    la = engine.lens_from_mask(audio_masks, B, T, dev)
+    lv = engine.lens_from_mask(video_masks, B, T, dev)
+
+    def pos_pair(pos):
+        p2 = pos.reshape(-1, d).contiguous().float()
+        return p2, ob.transpose_2d(p2, pad=True)
+
+    pa, pv = pos_pair(a_pos), pos_pair(v_pos)
+    inter = []
+    for i, (layer_a, layer_v) in enumerate(zip(ea.encoders, ev.encoders)):
+        a = run_block(layer_a, a, B, T, la, a_pos, shared_pos=pa)
+        v = run_block(layer_v, v, B, T, lv, v_pos, shared_pos=pv)
+        if (i + 1) in enc.interctc_layer_idx:
+            a, v = _av_tap(enc, ea.after_norm if ea.normalize_before else None,
+                           ev.after_norm if ev.normalize_before else None, a, v, la, lv, B, T, ctc,
+                           fusion, inter, i + 1)
+    if ea.normalize_before:
+        a = _LayerNormFn.apply(a, ea.after_norm.weight, ea.after_norm.bias, 1e-12, 1.0)
+    if ev.normalize_before:
+        v = _LayerNormFn.apply(v, ev.after_norm.weight, ev.after_norm.bias, 1e-12, 1.0)
+    return (a.view(B, T, d), inter), audio_masks, v.view(B, T, d), video_masks, None
+
+
+def tailored_encoder_forward(enc, audio_pad, audio_masks, video_pad, video_masks, ctc=None, fusion=None):
+    """Training forward of TailoredEncoder (tailored/encoder.py:221-330): modality encoding, the layer
+    stack with optional audio-visual InterCTC taps, the shared after_norm on both streams."""
+    taps_on = len(enc.interctc_layer_idx) > 0
+    if taps_on:
+        _check_av_taps(enc, ctc, fusion)
     audio, a_pos = audio_pad if isinstance(audio_pad, tuple) else (audio_pad, None)
     video, v_pos = video_pad if isinstance(video_pad, tuple) else (video_pad, None)
     if audio.shape != video.shape:
@@ -698,12 +798,17 @@ def tailored_encoder_forward(enc, audio_pad, audio_masks, video_pad, video_masks
         return p2, ob.transpose_2d(p2, pad=True)
 
     pa, pv = pos_pair(a_pos), pos_pair(v_pos)
-    for layer in enc.encoders:
+    inter = []
+    norm = enc.after_norm if enc.normalize_before else None
+    for i, layer in enumerate(enc.encoders):
         a, v = tailored_layer_forward(layer, a, v, B, T, la, lv, pa, pv)
+        if taps_on and (i + 1) in enc.interctc_layer_idx:
+            a, v = _av_tap(enc, norm, norm, a, v, la, lv, B, T, ctc, fusion, inter, i + 1)
     if enc.normalize_before:
         a = _LayerNormFn.apply(a, enc.after_norm.weight, enc.after_norm.bias, 1e-12, 1.0)
         v = _LayerNormFn.apply(v, enc.after_norm.weight, enc.after_norm.bias, 1e-12, 1.0)
-    return a.view(B, T, d), audio_masks, v.view(B, T, d), video_masks, None
+    a_out = a.view(B, T, d)
+    return ((a_out, inter) if inter else a_out), audio_masks, v.view(B, T, d), video_masks, None
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -881,13 +986,15 @@ def run_block(layer, x2d: torch.Tensor, B: int, T: int, lens: torch.Tensor,
     return _BlockFn.apply(layer, aux, names, x2d, *params)
 
 
-def encoder_forward(enc, xs_pad, ilens, max_layer=None, masks=None):
-    """Training forward of MyBranchformerEncoder (encoder.py:324-412, plain layer loop and the
-    max_layer early exit).  Returns (out (B,T,d), olens, None) with an autograd graph behind `out`.
+def encoder_forward(enc, xs_pad, ilens, max_layer=None, masks=None, ctc=None):
+    """Training forward of MyBranchformerEncoder (encoder.py:324-412: the layer loop, the max_layer
+    early exit, InterCTC taps with optional self-conditioning).  Returns (out (B,T,d) or (out,
+    [(layer, tap (B,T,d)), ...]), olens, None) with an autograd graph behind every returned tensor.
     `masks` (B,1,T): given by the AV wrappers instead of `ilens`."""
-    if len(enc.interctc_layer_idx) > 0:
-        raise NotImplementedError("InterCTC taps / self-conditioning are not built on the training path "
-                                  "(no shipped config uses them: interctc_weight = 0.0 everywhere)")
+    taps_on = len(enc.interctc_layer_idx) > 0
+    if taps_on and enc.interctc_use_conditioning and (ctc is None or enc.conditioning_layer is None):
+        raise ValueError("InterCTC self-conditioning needs the `ctc` module and an assigned "
+                         "`conditioning_layer` (espnet_model.py:106-112)")
     x_in = xs_pad[0] if isinstance(xs_pad, tuple) else xs_pad
     dev = x_in.device
     d = enc._output_size
@@ -927,11 +1034,23 @@ def encoder_forward(enc, xs_pad, ilens, max_layer=None, masks=None):
     pos2d = pos_emb.reshape(-1, d).contiguous().float()
     shared = (pos2d, ob.transpose_2d(pos2d, pad=True))
     n = len(enc.encoders)
-    last = n - 1 if (max_layer is None or not 0 <= max_layer < n) else max_layer
+    last = n - 1 if (taps_on or max_layer is None or not 0 <= max_layer < n) else max_layer
+    inter = []
     for i, layer in enumerate(enc.encoders):
         if i > last:
             break
         x = run_block(layer, x, B, T, lens, pos_emb, shared_pos=shared)
+        if taps_on and (i + 1) in enc.interctc_layer_idx:
+            # intermediate outputs are normalised too (:387-389), then fed back as posteriors (:393-401)
+            tap = (_LayerNormFn.apply(x, enc.after_norm.weight, enc.after_norm.bias, 1e-12, 1.0)
+                   if enc.normalize_before else x)
+            inter.append((i + 1, tap.view(B, T, d)))
+            if enc.interctc_use_conditioning:
+                cl = enc.conditioning_layer
+                x = _CondFn.apply(x, tap, ctc.ctc_lo.weight, ctc.ctc_lo.bias, cl.weight, cl.bias)
     if enc.normalize_before:
         x = _LayerNormFn.apply(x, enc.after_norm.weight, enc.after_norm.bias, 1e-12, 1.0)
-    return x.view(B, T, d), masks.squeeze(1).sum(1), None
+    olens = masks.squeeze(1).sum(1)
+    if inter:
+        return (x.view(B, T, d), inter), olens, None
+    return x.view(B, T, d), olens, None
