@@ -358,6 +358,33 @@ def load_ncu_traffic():
     return d, path
 
 
+KERNEL_SOURCES = {   # the files that define each measured kernel group (tools/ncu_traffic.py writes
+    # their digest at capture time; a late change elsewhere in the library does not stale them)
+    "ffn_fused": ["ffn_sm100.cu", "ffn_sm100.cuh", "gemm_sm100.cuh", "ptx.cuh", "host.h"],
+    "gemm": ["gemm_sm100.cu", "gemm_sm100.cuh", "ptx.cuh", "host.h"],
+    "relpos_attn": ["attention_sm100.cu", "ptx.cuh", "host.h"],
+    "csgu": ["rowops.cu", "ptx.cuh", "host.h"],
+    "merge_scores": ["rowops.cu", "ptx.cuh", "host.h"],
+    "ctc": ["ctc.cu", "ptx.cuh", "host.h"],
+}
+
+
+def kernel_source_digest(group):
+    import hashlib
+    files = KERNEL_SOURCES.get(group)
+    if files is None:
+        return None
+    h = hashlib.sha256()
+    try:
+        for f in files:
+            with open(os.path.join(ROOT, "tailored_avsr_b200", "csrc", f), "rb") as fh:
+                h.update(f.encode())
+                h.update(fh.read())
+    except OSError:
+        return None
+    return h.hexdigest()[:16]
+
+
 def lib_digest():
     try:
         with open(os.path.join(ROOT, "tailored_avsr_b200", "libtavsr_sm100.so.digest")) as f:
@@ -453,6 +480,12 @@ def profile_step(pipe, batch_dev, peaks, dtype, live_peaks):
         roof["traffic_source"] = os.path.relpath(path, ROOT)
         roof["traffic_build_digest"] = table.get("lib_digest")
         roof["traffic_build_matches"] = table.get("lib_digest") == lib_digest()
+        # the capture also records a digest of the source files that define each kernel group: the
+        # figure is current as long as THOSE files are byte-identical, whatever else changed
+        grp = next((g for g in KERNEL_SOURCES if top_key.startswith(g)), None)
+        rec = (table.get("kernel_source_digests") or {}).get(grp)
+        roof["traffic_kernel_sources_match"] = (rec is not None and rec == kernel_source_digest(grp))
+        roof["traffic_captured_on_commit"] = table.get("captured_on_commit")
     roof["algorithmic_bytes"] = top["bytes"]
     roof["algorithmic_flops"] = top["flops"]
     roof["kernel"] = top_key

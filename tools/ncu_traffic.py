@@ -56,8 +56,12 @@ def main():
         digest = open(os.path.join(ROOT, "tailored_avsr_b200", "libtavsr_sm100.so.digest")).read().strip()[:16]
     except OSError:
         pass
+    sys.path.insert(0, ROOT)
+    import bench
     res = {"lib_digest": digest, "unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
-           "how": "ncu --set full --clock-control none on one eager C2 step per mode (tools/final2.sh)"}
+           "how": "ncu --set full --clock-control none on one eager C2 step per mode (tools/final2.sh)",
+           "kernel_source_digests": {g: bench.kernel_source_digest(g) for g in bench.KERNEL_SOURCES},
+           "kernel_source_files": bench.KERNEL_SOURCES}
     for arg in sys.argv[1:]:
         mode, path = arg.split("=", 1)
         res[mode] = load(path)
