@@ -242,6 +242,40 @@ def test_product_path_fails_loudly_without_cuda():
     assert training.draw_block_masks(enc.encoders[0], 1, 8, torch.device("cpu")) == {}
 
 
+def test_training_host_logic_of_the_tailored_layer_views():
+    """training.py host side, no GPU: a stream of a TailoredEncoderLayer is presented to the block
+    forward / backward under MyBranchformerEncoderLayer names; gradient keys map back to the
+    tailored layer's parameter names; the dropout sites of a stream follow the reference's order
+    (tailored/encoder_layer.py:170-215: FFN hidden / output, branch module, branch output, FFN
+    hidden / output - no merge site)."""
+    import copy
+    from tailored_avsr_b200 import training
+    from tailored_avsr_b200.encoder.audiovisual.tailored.encoder import TailoredEncoder
+    cfg = dict(copy.deepcopy(cases.BASE_TAILORED), num_blocks=1, acoustic_use_attn=[True],
+               visual_use_attn=[False])
+    enc = TailoredEncoder(embed_pos_enc_layer_type="rel_pos", embed_rel_pos_type="latest", **cfg).train()
+    layer = enc.encoders[0]
+    va, vv = training._StreamView(layer, "acoustic"), training._StreamView(layer, "visual")
+    assert va.attn is layer.acoustic_attn and va.cgmlp is None and vv.cgmlp is layer.visual_cgmlp
+    assert va.feed_forward is vv.feed_forward is layer.feed_forward           # shared between streams
+    names = {n for n, _ in layer.named_parameters()}
+    for key in ("attn.linear_q.weight", "norm_mha.bias", "feed_forward.w_1.weight", "norm_final.weight"):
+        assert va.real_name(key) in names, key
+    for key in ("cgmlp.csgu.conv.weight", "norm_mlp.weight", "norm_ff_macaron.bias"):
+        assert vv.real_name(key) in names, key
+    dev = torch.device("cpu")
+    assert list(training.draw_block_masks(va, 1, 8, dev)) == ["ffm_h", "ffm_o", "att", "x1", "ff_h", "ff_o"]
+    assert list(training.draw_block_masks(vv, 1, 8, dev)) == ["ffm_h", "ffm_o", "csgu", "x2", "ff_h", "ff_o"]
+    # a custom mask source sees the reference's shapes in call order
+    seen = []
+    training.set_dropout_source(lambda shape, p, device: (seen.append((shape, p)), torch.ones(shape))[1])
+    try:
+        training.draw_block_masks(va, 2, 8, dev)
+    finally:
+        training.set_dropout_source(None)
+    assert [s for s, _ in seen] == [(2, 8, 2048), (2, 8, 256), (2, 4, 8, 8), (2, 8, 256), (2, 8, 2048), (2, 8, 256)]
+
+
 def test_constructor_errors_match_reference_behaviour():
     from tailored_avsr_b200.ctc.ctc import CTC
     from tailored_avsr_b200.encoder.branchformer.encoder import MyBranchformerEncoder
