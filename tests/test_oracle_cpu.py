@@ -215,6 +215,55 @@ def test_c_abi_exports_every_declared_symbol():
     assert ctypes.sizeof(_lib.RowLNArgs) % 8 == 0
 
 
+def test_c_abi_signatures_in_the_bindings_match_the_header():
+    """Every prototype of include/tavsr.h against the ctypes table of _lib.py: parameter count and
+    parameter class (pointer / int / long long / float / size_t), return type.  A binding that
+    drifts from the header shifts every later argument silently; names alone do not catch that."""
+    from tailored_avsr_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "tavsr.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)          # comments (also inside prototypes)
+    header = re.sub(r"//[^\n]*", " ", header)
+    protos = re.findall(r"\b(int|size_t|const\s+char\s*\*|long\s+long|void)\s+(tavsr_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;",
+                        header, flags=re.S)
+    assert len(protos) == len(_lib.SIGNATURES), (len(protos), len(_lib.SIGNATURES))
+
+    def cls_of_c(decl):
+        decl = " ".join(decl.split())
+        if "*" in decl:
+            return "ptr"
+        if "long long" in decl:
+            return "ll"
+        if "size_t" in decl:
+            return "size"
+        if "float" in decl:
+            return "float"
+        if re.search(r"\bint\b", decl):
+            return "int"
+        raise AssertionError(f"unclassified parameter {decl!r}")
+
+    def cls_of_ctypes(t):
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or (isinstance(t, type) and issubclass(t, ctypes._Pointer)):
+            return "ptr"
+        return {ctypes.c_longlong: "ll", ctypes.c_size_t: "size", ctypes.c_float: "float",
+                ctypes.c_int: "int"}[t]
+
+    for ret, name, params in protos:
+        restype, argtypes = _lib.SIGNATURES[name]
+        plist = [] if params.strip() in ("", "void") else [x for x in params.split(",")]
+        assert len(plist) == len(argtypes), (name, len(plist), len(argtypes))
+        got = [cls_of_ctypes(t) for t in argtypes]
+        want = [cls_of_c(x) for x in plist]
+        assert got == want, (name, [(i, a, b) for i, (a, b) in enumerate(zip(got, want)) if a != b])
+        want_ret = {"int": ctypes.c_int, "size_t": ctypes.c_size_t, "void": None}.get(
+            ret.replace(" ", ""), None)
+        if ret.startswith("const"):
+            assert restype is ctypes.c_char_p, name
+        elif ret.replace(" ", "") == "longlong":
+            assert restype is ctypes.c_longlong, name
+        else:
+            assert restype is want_ret, (name, restype, ret)
+
+
 def test_product_path_fails_loudly_without_cuda():
     """No CPU fallback: CPU tensors are rejected in inference and in grad mode (the training path
     runs on the CUDA kernels too); modules without a backward refuse grad-mode calls."""
