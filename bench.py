@@ -881,6 +881,56 @@ def gpu_eager_baseline(dev, steps=5):
             out[name] = {"value": frames / (med * 1e-3), "unit": UNIT, "ms_per_step": med}
     except Exception as e:  # noqa: BLE001
         out["error"] = f"{type(e).__name__}: {e}"[:200]
+    # the same port with its launch overhead removed: the encoder forward (all but ~1 % of the work)
+    # captured into a CUDA graph, TF32 allowed.  torch's CTC loss reads its length tensors on the host
+    # and cannot be captured, so this figure is encoder-only and is given beside the eager encoder-only
+    # time; a port that syncs inside the encoder reports why it cannot be captured.
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cudnn.allow_tf32 = True
+
+        def enc_only():
+            with torch.no_grad(), torch.device(dev):
+                return ref_path.branchformer_encoder(feats, lens, sd, cfg)[0]
+
+        def timed(fn):
+            ts = []
+            for _ in range(steps):
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            return statistics.median(ts)
+
+        frames = int(w["B"] * w["T"])
+        enc_only()
+        torch.cuda.synchronize()
+        eager_ms = timed(enc_only)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            enc_only()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            enc_only()
+        graph.replay()
+        torch.cuda.synchronize()
+        graph_ms = timed(graph.replay)
+        out["tf32_allowed_encoder_only"] = {
+            "eager_ms_per_step": eager_ms, "cuda_graph_ms_per_step": graph_ms,
+            "cuda_graph_value": frames / (graph_ms * 1e-3), "unit": UNIT}
+        del graph
+    except Exception as e:  # noqa: BLE001
+        out["tf32_allowed_encoder_only"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+        try:
+            torch.cuda.synchronize()
+        except Exception:  # noqa: BLE001
+            pass
     finally:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
     out["what"] = ("oracle/ref_path.py (plain torch ops: cuBLAS GEMMs, ATen elementwise / softmax / "
