@@ -29,6 +29,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--max-rows", type=int, default=400000, help="skip points with B*T above this")
     ap.add_argument("--dtype", default="bf16", choices=["tf32", "tf32x3", "bf16"])
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="train: the CUDA-graph training step of bench.py (forward + loss + backward "
+                         "+ gradient all-reduce, every dropout active) instead of the inference step")
     a = ap.parse_args()
     from tailored_avsr_b200 import engine
     from tailored_avsr_b200.pipeline import AVEncoderCTCPipeline, EncoderCTCPipeline
@@ -54,6 +57,18 @@ def main():
                 mods = (enc.to(dev).eval(), fusion.to(dev).eval() if fusion is not None else None,
                         ctc.to(dev).eval())
             enc, fusion, ctc = mods
+            if a.mode == "train":
+                targs = types.SimpleNamespace()
+                res = bench.train_graph_leg(targs, enc, ctc, rank, world, dev, dist, steps=a.steps,
+                                            warmup=max(1, a.warmup), fusion=fusion)
+                if rank == 0:
+                    res = res or {}
+                    print(json.dumps({"workload": a.workload, "mode": "train", "B": B, "T": T,
+                                      "ms_per_step": res.get("ms_per_step"), "frames_per_s": res.get("value"),
+                                      "unavailable": res.get("unavailable"), "n_gpus": world,
+                                      "batch_per_gpu": B, "step": res.get("step")}), flush=True)
+                torch.cuda.empty_cache()
+                continue
             pipe = (EncoderCTCPipeline(enc, ctc) if fusion is None
                     else AVEncoderCTCPipeline(enc, fusion, ctc))
             host, frames = bench.make_batch(rank)
